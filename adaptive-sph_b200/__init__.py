@@ -1,0 +1,15 @@
+"""adaptive-sph_b200 — B200-native step loop for kaegi/adaptive-sph (hot path only).
+
+The directory name carries a hyphen (it is the name the task fixes); import it with
+`importlib.import_module("adaptive-sph_b200")` or through `asph_b200.py` at the repo root.
+"""
+from .binding import (AsphError, FluidSimulation, StatisticsRecorder, init_fluid_sim, load_library, FIELDS,
+                      LEVEL_INTERIOR, PRODUCT_LIB)
+from .params import SimulationParams, merge_overwrite
+from .scene import SceneConfig, add_fluid_block, init_simulation_params, scene_boundary, scene_particles
+from .split_patterns import SplitPatterns, load_split_patterns_from_file
+
+__all__ = ["AsphError", "FluidSimulation", "StatisticsRecorder", "init_fluid_sim", "load_library", "FIELDS",
+           "LEVEL_INTERIOR", "PRODUCT_LIB", "SimulationParams", "merge_overwrite", "SceneConfig", "add_fluid_block",
+           "init_simulation_params", "scene_boundary", "scene_particles", "SplitPatterns",
+           "load_split_patterns_from_file"]

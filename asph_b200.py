@@ -1,0 +1,10 @@
+"""Import shim: `import asph_b200` == the package in ./adaptive-sph_b200/ (a hyphen is not importable by name)."""
+import importlib
+import os
+import sys
+
+_root = os.path.dirname(os.path.abspath(__file__))
+if _root not in sys.path:
+    sys.path.insert(0, _root)
+_pkg = importlib.import_module("adaptive-sph_b200")
+sys.modules[__name__] = _pkg
