@@ -94,6 +94,8 @@ def _declare(lib):
     lib.asph_get_counters.restype = C.c_int
     lib.asph_last_error.argtypes = [_P]
     lib.asph_last_error.restype = C.c_char_p
+    lib.asph_kernel_launches.argtypes = [_P]
+    lib.asph_kernel_launches.restype = C.c_uint64
     lib.asph_backend_name.argtypes = []
     lib.asph_backend_name.restype = C.c_char_p
     lib.asph_kernel_w.argtypes = [C.c_float, C.c_float]
@@ -271,6 +273,9 @@ class FluidSimulation:
         out = np.empty(n, dtype=np.uint32)
         self._check(self.lib.asph_get_global_index(self._h, out.ctypes.data_as(C.POINTER(C.c_uint32)), n))
         return out
+
+    def kernel_launches(self):
+        return int(self.lib.asph_kernel_launches(self._h))
 
     def backend(self):
         return self.lib.asph_backend_name().decode()

@@ -1,0 +1,538 @@
+// capi.cu — the C ABI of include/asph.h on top of the CUDA kernels: handle lifetime, the step orchestration of
+// FluidSimulation::single_step (simulation.rs:1973-2796) and read-back in reference particle order.
+//
+// There is no CPU path here: without a usable CUDA device asph_create returns ASPH_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "sim.cuh"
+
+int dist_step_physics(asph_sim* sim);  // dist.cu (multi-GPU orchestration); unused when sim->dist == nullptr
+
+namespace {
+
+constexpr int kThreads = 256;
+
+int pack_params(asph_sim* sim, const asph_params* p) {
+  PackedParams& q = sim->pp;
+  memset(&q, 0, sizeof(q));
+  q.rest_density = float(p->rest_density); q.cfl_factor = float(p->cfl_factor); q.max_dt = float(p->max_dt);
+  q.viscosity = float(p->viscosity); q.gravity = float(p->gravity); q.jacobi_omega = float(p->jacobi_omega);
+  q.sdf_gradient_eps = float(p->sdf_gradient_eps);
+  q.particle_radius_fine = float(p->particle_radius_fine); q.particle_radius_base = float(p->particle_radius_base);
+  q.maximum_surface_distance = float(p->maximum_surface_distance);
+  // mass_fine / mass_base: radius_to_volume(r) * rest_density in fp32 (simulation_parameters.rs:124-131)
+  const float PI_F = 3.14159265358979323846f;
+  q.mass_fine = ((PI_F * q.particle_radius_fine) * q.particle_radius_fine) * q.rest_density;
+  q.mass_base = ((PI_F * q.particle_radius_base) * q.particle_radius_base) * q.rest_density;
+  q.max_mass_transfer_sharing = float(p->max_mass_transfer_sharing);
+  q.max_share_distance = float(p->max_share_distance); q.max_merge_distance = float(p->max_merge_distance);
+  q.max_avg_density_error_iisph = float(p->iisph_max_avg_density_error); q.hybrid_factor = float(p->hybrid_dfsph_factor);
+  q.max_avg_density_error = float(p->hybrid_dfsph_max_avg_density_error);
+  q.max_avg_divergence_error = float(p->hybrid_dfsph_max_avg_divergence_error);
+  q.f_ext = float(p->level_estimation_range) / 1.9f;  // level_estimation_range / ETA in FT, simulation.rs:2028
+  q.f_near = 2.f;
+  q.pull_x = float(p->pull_fluid_to[0]); q.pull_y = float(p->pull_fluid_to[1]);
+  q.has_pull = p->has_pull_fluid_to; q.viscosity_type = p->viscosity_type; q.level_method = p->level_estimation_method;
+  q.solver = p->pressure_solver_method; q.density_source = p->hybrid_dfsph_density_source_term;
+  q.np_before_div = p->hybrid_dfsph_non_pressure_accel_before_divergence_free; q.penalty = p->boundary_penalty_term;
+  q.sizing = p->sizing_function; q.opdisc = p->operator_discretization;
+  q.boundary_is_fluid_surface = p->boundary_is_fluid_surface;
+  q.max_iters = int(std::min<int64_t>(p->max_iters, 1 << 28));
+  q.min_share_partners = p->minimum_share_partners; q.min_merge_partners = p->minimum_merge_partners;
+  q.allow_merge_optimal = p->allow_merge_with_optimal_particle; q.allow_share_optimal = p->allow_share_with_optimal_particle;
+  q.allow_share_too_small = p->allow_share_with_too_small_particle; q.allow_merge_size_diff = p->allow_merge_on_size_difference;
+  q.fail_on_missing_split_pattern = p->fail_on_missing_split_pattern;
+  q.n_planes = sim->boundary.kind == ASPH_BND_PLANES ? sim->boundary.n_planes : 0;
+  for (int s = 0; s < q.n_planes; s++) for (int k = 0; k < 3; k++) q.planes[s][k] = sim->boundary.planes[s][k];
+
+  auto unsupported = [&](const char* what) { sim->last_error = std::string(what) + " is not implemented yet (SURVEY.md §8f)"; return ASPH_ERR_UNSUPPORTED; };
+  if (p->support_length_estimation != ASPH_H_FROM_MASS) return unsupported("support_length_estimation != FromMass");
+  if (p->constrain_neighborhood_count) return unsupported("constrain_neighborhood_count");
+  if (p->level_estimation_method == ASPH_LEVEL_CENTER_DIFF) return unsupported("level_estimation_method CenterDiff");
+  if (p->operator_discretization == ASPH_OP_WINCHENBACH2020) return unsupported("operator_discretization Winchenbach2020");
+  if (p->pressure_solver_method == ASPH_SOLVER_IISPH2) return unsupported("pressure_solver_method IISPH2");
+  if (p->viscosity_type == ASPH_VISC_XSPH) return unsupported("viscosity_type XSPH (todo!() in the reference)");
+  if (sim->boundary.kind == ASPH_BND_POLYGON) return unsupported("AnalyticUnderestimate polygon boundary");
+  if (p->level_estimation_after_advection) return unsupported("level_estimation_after_advection");
+  return ASPH_OK;
+}
+
+// ---- PerformanceCounters (simulation.rs:159-189): CUDA-event intervals per label ----------------------------
+struct PcInterval { int label; cudaEvent_t b, e; bool counts_call; };
+struct PcState { std::vector<PcInterval> open; std::vector<cudaEvent_t> pool; };
+PcState& pc_of(asph_sim* sim) {
+  static thread_local std::vector<std::pair<asph_sim*, PcState*>> table;
+  for (auto& kv : table) if (kv.first == sim) return *kv.second;
+  table.push_back({sim, new PcState()});
+  return *table.back().second;
+}
+cudaEvent_t pc_event(PcState& s) {
+  if (!s.pool.empty()) { cudaEvent_t e = s.pool.back(); s.pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void pc_begin(asph_sim* sim, int label, bool counts_call = true) {
+  if (!sim->counters) return;
+  PcState& s = pc_of(sim);
+  PcInterval iv{label, pc_event(s), pc_event(s), counts_call};
+  cudaEventRecord(iv.b, sim->stream);
+  s.open.push_back(iv);
+}
+void pc_end(asph_sim* sim, int label) {
+  if (!sim->counters) return;
+  PcState& s = pc_of(sim);
+  for (int k = int(s.open.size()) - 1; k >= 0; k--)
+    if (s.open[k].label == label) { cudaEventRecord(s.open[k].e, sim->stream); return; }
+}
+void pc_collect(asph_sim* sim) {
+  if (!sim->counters) return;
+  PcState& s = pc_of(sim);
+  cudaStreamSynchronize(sim->stream);
+  for (auto& iv : s.open) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, iv.b, iv.e) == cudaSuccess) {
+      sim->pc_ms[iv.label] += ms;
+      if (iv.counts_call) sim->pc_calls[iv.label]++;
+    }
+    s.pool.push_back(iv.b); s.pool.push_back(iv.e);
+  }
+  s.open.clear();
+  cudaGetLastError();
+}
+
+__global__ void k_init_ids(uint32_t n, uint32_t* refid, float* level) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { refid[i] = i; level[i] = ASPH_LEVEL_INTERIOR; }
+}
+
+// field extraction into reference order: out[refid[i] * comps + c]
+__global__ void k_extract(uint32_t n, int field, const uint32_t* __restrict__ refid, const float2* pos, const float2* vel,
+                          const float* mass, const float4* xyhm, const float* rho, const float4* packP, const float4* pconst,
+                          const float4* packA, const float* level, const uint8_t* size_class, const uint32_t* cnt,
+                          const uint8_t* flags, const float* lam_sum, const float2* lam_grad, const uint32_t* merge_partner,
+                          const uint32_t* merge_counter, void* out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t r = refid[i];
+  float* f = (float*)out;
+  switch (field) {
+    case ASPH_F_POSITION: f[2 * r] = pos[i].x; f[2 * r + 1] = pos[i].y; break;
+    case ASPH_F_VELOCITY: f[2 * r] = vel[i].x; f[2 * r + 1] = vel[i].y; break;
+    case ASPH_F_MASS: f[r] = mass[i]; break;
+    case ASPH_F_H: f[r] = xyhm[i].z; break;
+    case ASPH_F_DENSITY: f[r] = rho[i]; break;
+    case ASPH_F_PRESSURE: f[r] = packP[i].w; break;
+    case ASPH_F_AII: f[r] = pconst[i].z; break;
+    case ASPH_F_SOURCE_TERM: f[r] = pconst[i].w; break;
+    case ASPH_F_PRESSURE_ACCEL: f[2 * r] = packA[i].z; f[2 * r + 1] = packA[i].w; break;
+    case ASPH_F_LEVEL: f[r] = level[i]; break;
+    case ASPH_F_SIZE_CLASS: ((uint8_t*)out)[r] = size_class[i]; break;
+    case ASPH_F_NEIGHBOR_COUNT: ((uint32_t*)out)[r] = cnt[i] & 0xffffu; break;
+    case ASPH_F_FLAG_SURFACE: ((uint8_t*)out)[r] = flags[i] & 1u; break;
+    case ASPH_F_FLAG_INSUFFICIENT: ((uint8_t*)out)[r] = (flags[i] >> 1) & 1u; break;
+    case ASPH_F_LAMBDA_SUM: f[r] = lam_sum[i]; break;
+    case ASPH_F_LAMBDA_GRAD: f[2 * r] = lam_grad[i].x; f[2 * r + 1] = lam_grad[i].y; break;
+    case ASPH_F_MERGE_PARTNER: {
+      // partner indices are device indices internally; report reference indices
+      uint32_t p = merge_partner[i];
+      ((uint32_t*)out)[r] = (p >= ASPH_MERGE_PARTNER_DELETE) ? p : refid[p];
+      break;
+    }
+    case ASPH_F_MERGE_COUNTER: ((uint16_t*)out)[r] = uint16_t(merge_counter[i]); break;
+  }
+}
+
+int field_elem_bytes(int field, int* comps) {
+  *comps = 1;
+  switch (field) {
+    case ASPH_F_POSITION: case ASPH_F_VELOCITY: case ASPH_F_PRESSURE_ACCEL: case ASPH_F_LAMBDA_GRAD: *comps = 2; return 4;
+    case ASPH_F_SIZE_CLASS: case ASPH_F_FLAG_SURFACE: case ASPH_F_FLAG_INSUFFICIENT: return 1;
+    case ASPH_F_MERGE_COUNTER: return 2;
+    case ASPH_F_NEIGHBOR_COUNT: case ASPH_F_MERGE_PARTNER: return 4;
+    case ASPH_F_MASS: case ASPH_F_H: case ASPH_F_DENSITY: case ASPH_F_PRESSURE: case ASPH_F_AII: case ASPH_F_SOURCE_TERM:
+    case ASPH_F_LEVEL: case ASPH_F_LAMBDA_SUM: return 4;
+  }
+  return 0;
+}
+
+}  // namespace
+
+int check_error_flags(asph_sim* sim) {
+  const unsigned int f = sim->ctl_host->error_flags;
+  if (!f) return ASPH_OK;
+  if (f & ERRF_CELL_BUDGET) { sim->last_error = "cell grid does not fit the cell budget"; return ASPH_ERR_CAPACITY; }
+  if (f & ERRF_NEIGHBOR_OVERFLOW) { sim->last_error = "exceeded maximum allowed number of 20000 neighbors"; return ASPH_ERR_NEIGHBOR_OVERFLOW; }
+  if (f & ERRF_NONFINITE) { sim->last_error = "assert!(is_finite) failed (density / a_ii / position / velocity)"; return ASPH_ERR_NONFINITE; }
+  if (f & ERRF_DENSITY) { sim->last_error = "assert!(*p_density > 0.0001) failed"; return ASPH_ERR_DENSITY; }
+  if (f & ERRF_NEG_AII) { sim->last_error = "AII should not be negative!"; return ASPH_ERR_NEG_AII; }
+  if (f & ERRF_SOLVER_NONFINITE) { sim->last_error = "'!a_p.is_finite()' failed. Pressure values probably have exploded!"; return ASPH_ERR_NONFINITE; }
+  if (f & ERRF_LEVEL_WEIGHT) { sim->last_error = "smooth_level_estimation_field: weight <= 0"; return ASPH_ERR_NONFINITE; }
+  if (f & ERRF_PARTICLE_CAPACITY) { sim->last_error = "particle capacity exhausted by splitting"; return ASPH_ERR_CAPACITY; }
+  if (f & ERRF_SPLIT_PATTERN) { sim->last_error = "no split pattern for a 1-to-n split"; return ASPH_ERR_INVALID; }
+  if (f & ERRF_SPLIT_CHILDREN) { sim->last_error = "assert!(num_children > 1)"; return ASPH_ERR_INVALID; }
+  if (f & ERRF_PARTNER_VALIDATION) { sim->last_error = "validate_share_partners / validate_merge_partners failed"; return ASPH_ERR_INVALID; }
+  sim->last_error = "device error flag " + std::to_string(f);
+  return ASPH_ERR_INVALID;
+}
+
+static int step_physics(asph_sim* sim, const asph_params* params, float* dt_out) {
+  TRY(pack_params(sim, params));
+  const PackedParams& P = sim->pp;
+  memset(&sim->info, 0, sizeof(sim->info));
+  sim->info.n_particles_begin = sim->dist ? sim->n_owned : sim->n;
+  const bool lvl = P.level_method != ASPH_LEVEL_NONE;
+  if (lvl && !params->use_extended_range_for_level_estimation) {  // simulation.rs:2020
+    sim->last_error = "level estimation before advection needs use_extended_range_for_level_estimation";
+    return ASPH_ERR_INVALID;
+  }
+  pc_begin(sim, ASPH_PC_SIMULATION_STEP);
+  // With no level estimation the extended-range lists are never read (perform_level_estimation is a no-op,
+  // simulation.rs:2034-2057), so only N_2 is built.
+  const float f_ext = lvl ? P.f_ext : P.f_near;
+  if (sim->dist) {
+    int rc = dist_step_physics(sim);
+    if (rc != ASPH_OK) return rc;
+  } else {
+    pc_begin(sim, ASPH_PC_NEIGHBORHOOD);
+    TRY(launch_sort_and_grid(sim, std::max(f_ext, P.f_near)));
+    TRY(launch_neighbors(sim, f_ext, P.f_near));
+    pc_end(sim, ASPH_PC_NEIGHBORHOOD);
+    if (sim->n == 0) {
+      sim->info.dt = P.max_dt;
+    } else {
+      TRY(check_error_flags(sim));
+      sim->info.dt = sim->ctl_host->dt;
+      if (lvl) {
+        pc_begin(sim, ASPH_PC_LEVEL_ESTIMATION);
+        TRY(launch_level_estimation(sim));
+        pc_end(sim, ASPH_PC_LEVEL_ESTIMATION);
+      }
+      int iters = 0, sweeps = 0;
+      switch (P.solver) {
+        case ASPH_SOLVER_IISPH:  // simulation.rs:2389-2446
+          TRY(launch_viscosity(sim));
+          TRY(launch_source(sim, 2));
+          pc_begin(sim, ASPH_PC_DENSITY_SOLVER);
+          TRY(launch_solver(sim, true, P.max_avg_density_error_iisph, &iters, &sweeps, &sim->info.last_avg_error_density));
+          sim->info.density_iterations = iters; sim->info.density_sweeps = sweeps;
+          TRY(launch_final_accel(sim, 3));
+          pc_end(sim, ASPH_PC_DENSITY_SOLVER);
+          break;
+        case ASPH_SOLVER_ONLY_DIVERGENCE:  // simulation.rs:2448-2500
+          TRY(launch_viscosity(sim));
+          TRY(launch_source(sim, 0));
+          pc_begin(sim, ASPH_PC_DIV_SOLVER);
+          TRY(launch_solver(sim, false, P.max_avg_divergence_error, &iters, &sweeps, &sim->info.last_avg_error_div));
+          sim->info.div_iterations = iters; sim->info.div_sweeps = sweeps;
+          TRY(launch_final_accel(sim, 3));
+          pc_end(sim, ASPH_PC_DIV_SOLVER);
+          break;
+        default:  // HybridDFSPH, simulation.rs:2502-2670
+          if (P.np_before_div) TRY(launch_viscosity(sim));
+          pc_begin(sim, ASPH_PC_DIV_SOLVER);
+          TRY(launch_source(sim, 0));
+          TRY(launch_solver(sim, false, P.max_avg_divergence_error, &iters, &sweeps, &sim->info.last_avg_error_div));
+          sim->info.div_iterations = iters; sim->info.div_sweeps = sweeps;
+          TRY(launch_final_accel(sim, 1));
+          pc_end(sim, ASPH_PC_DIV_SOLVER);
+          if (!P.np_before_div) TRY(launch_viscosity(sim));
+          pc_begin(sim, ASPH_PC_DENSITY_SOLVER);
+          TRY(launch_source(sim, P.density_source == ASPH_SRC_ONLY_DENSITY ? 1 : 2));
+          TRY(launch_solver(sim, true, P.max_avg_density_error, &iters, &sweeps, &sim->info.last_avg_error_density));
+          sim->info.density_iterations = iters; sim->info.density_sweeps = sweeps;
+          TRY(launch_final_accel(sim, 2));
+          pc_end(sim, ASPH_PC_DENSITY_SOLVER);
+          break;
+      }
+      if (lvl) {
+        pc_begin(sim, ASPH_PC_LEVEL_ESTIMATION, false);
+        TRY(launch_level_smoothing(sim));
+        pc_end(sim, ASPH_PC_LEVEL_ESTIMATION);
+      }
+      TRY(sync_ctl(sim));
+      TRY(check_error_flags(sim));
+    }
+  }
+  const float dt = sim->info.dt;
+  sim->last_dt = dt;
+  sim->time_f += dt;  // time: FT in the reference (simulation.rs:2724)
+  sim->time = double(sim->time_f);
+  sim->step_number += 1;
+  sim->step_fields_valid = true;
+  pc_end(sim, ASPH_PC_SIMULATION_STEP);
+  pc_collect(sim);
+  if (dt_out) *dt_out = dt;
+  sim->info.n_particles_end = sim->dist ? sim->n_owned : sim->n;
+  return ASPH_OK;
+}
+
+static int step_adaptivity(asph_sim* sim, const asph_params* params, float dt) {
+  TRY(pack_params(sim, params));
+  const bool any = params->sharing || params->merging || params->splitting;
+  if (any && params->level_estimation_method == ASPH_LEVEL_NONE) {
+    sim->last_error = "resampling needs a level estimation (level() on FluidInterior is unreachable!, simulation.rs:204-211)";
+    return ASPH_ERR_INVALID;
+  }
+  if (!any) return ASPH_OK;
+  if (sim->dist) { sim->last_error = "resampling across GPU slabs"; return ASPH_ERR_UNSUPPORTED; }
+  if (!sim->lists_valid || !sim->level_valid) {
+    sim->last_error = "single_step_adaptivity needs the neighbour lists and level field of the preceding physics step";
+    return ASPH_ERR_INVALID;
+  }
+  pc_begin(sim, ASPH_PC_SIMULATION_STEP, false);
+  pc_begin(sim, ASPH_PC_ADAPTIVITY);
+  sim->share_enabled = params->sharing != 0; sim->merge_enabled = params->merging != 0; sim->split_enabled = params->splitting != 0;
+  int rc = launch_adaptivity(sim, dt);
+  pc_end(sim, ASPH_PC_ADAPTIVITY);
+  pc_end(sim, ASPH_PC_SIMULATION_STEP);
+  pc_collect(sim);
+  sim->info.n_particles_end = sim->n;
+  return rc;
+}
+
+extern "C" {
+
+const char* asph_backend_name(void) { return "cuda-sm100a"; }
+
+int asph_set_state(asph_sim* sim, const float* pos, const float* vel, const float* mass, uint64_t n) {
+  if (!sim || (n && (!pos || !vel || !mass))) return ASPH_ERR_INVALID;
+  if (n > 0xFFFFFFF0ull) return ASPH_ERR_CAPACITY;
+  CUDA_TRY(cudaSetDevice(sim->device));
+  if (n > sim->cap) { sim->n = 0; TRY(ensure_capacity(sim, uint32_t(n + n / 4 + 1024))); }
+  sim->n = uint32_t(n); sim->n_owned = uint32_t(n);
+  const int c = sim->cur;
+  if (n) {
+    CUDA_TRY(cudaMemcpyAsync(sim->pos[c].p, pos, n * sizeof(float2), cudaMemcpyHostToDevice, sim->stream));
+    CUDA_TRY(cudaMemcpyAsync(sim->vel[c].p, vel, n * sizeof(float2), cudaMemcpyHostToDevice, sim->stream));
+    CUDA_TRY(cudaMemcpyAsync(sim->mass[c].p, mass, n * sizeof(float), cudaMemcpyHostToDevice, sim->stream));
+    k_init_ids<<<(uint32_t(n) + kThreads - 1) / kThreads, kThreads, 0, sim->stream>>>(uint32_t(n), sim->refid[c].p, sim->level[c].p);
+    LAUNCH_CHECK();
+  }
+  CUDA_TRY(cudaStreamSynchronize(sim->stream));
+  sim->lists_valid = false; sim->level_valid = false; sim->step_fields_valid = false;
+  return ASPH_OK;
+}
+
+int asph_create(const asph_params* params, const float* pos, const float* vel, const float* mass, uint64_t n,
+                const asph_boundary* boundary, const asph_split_patterns* split, int counters_enabled, uint64_t capacity,
+                asph_sim** out) {
+  if (!params || !out || (n && (!pos || !vel || !mass))) return ASPH_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return ASPH_ERR_NO_DEVICE; }
+  int device = 0;
+  if (const char* e = getenv("ASPH_DEVICE")) device = atoi(e);
+  else if (const char* e2 = getenv("LOCAL_RANK")) device = atoi(e2) % ndev;
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return ASPH_ERR_NO_DEVICE; }
+  asph_sim* sim = new asph_sim();
+  sim->device = device;
+  auto fail = [&](int rc) { asph_destroy(sim); return rc; };
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(ASPH_ERR_NO_DEVICE);
+  sim->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ASPH_ERR_CUDA);
+  if (cudaMalloc((void**)&sim->ctl, sizeof(StepCtl)) != cudaSuccess) return fail(ASPH_ERR_CUDA);
+  if (cudaMemset(sim->ctl, 0, sizeof(StepCtl)) != cudaSuccess) return fail(ASPH_ERR_CUDA);
+  if (cudaMallocHost((void**)&sim->ctl_host, sizeof(StepCtl)) != cudaSuccess) return fail(ASPH_ERR_CUDA);
+  memset(sim->ctl_host, 0, sizeof(StepCtl));
+  sim->counters = counters_enabled != 0;
+  if (boundary) sim->boundary = *boundary; else memset(&sim->boundary, 0, sizeof(sim->boundary));
+  {  // λ / λ′ lookup tables (BoundaryWinchenbach2020::new, boundary_winchenbach2020.rs:33-45)
+    std::vector<float> lam, dlam;
+    asph_host_build_luts(lam, dlam);
+    if (sim->lut.ensure(2 * 10001) != cudaSuccess) return fail(ASPH_ERR_CUDA);
+    cudaMemcpy(sim->lut.p, lam.data(), 10001 * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemcpy(sim->lut.p + 10001, dlam.data(), 10001 * sizeof(float), cudaMemcpyHostToDevice);
+  }
+  if (split && split->max_children >= 2) {
+    sim->max_children = split->max_children;
+    const int total = split->offset[split->max_children - 2] + split->max_children;
+    if (sim->split_off.ensure(split->max_children - 1) != cudaSuccess || sim->split_pos.ensure(2 * size_t(total)) != cudaSuccess)
+      return fail(ASPH_ERR_CUDA);
+    cudaMemcpy(sim->split_off.p, split->offset, (split->max_children - 1) * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(sim->split_pos.p, split->pos_xy, 2 * size_t(total) * sizeof(float), cudaMemcpyHostToDevice);
+  }
+  uint64_t cap = capacity ? capacity : (2 * n + 1024);
+  if (cap < n) cap = n;
+  if (cap > 0xFFFFFFF0ull) return fail(ASPH_ERR_CAPACITY);
+  int rc = ensure_capacity(sim, uint32_t(cap));
+  if (rc != ASPH_OK) return fail(rc);
+  rc = pack_params(sim, params);
+  if (rc != ASPH_OK && rc != ASPH_ERR_UNSUPPORTED) return fail(rc);
+  rc = asph_set_state(sim, pos, vel, mass, n);
+  if (rc != ASPH_OK) return fail(rc);
+  memset(&sim->info, 0, sizeof(sim->info));
+  *out = sim;
+  return ASPH_OK;
+}
+
+void asph_destroy(asph_sim* sim) {
+  if (!sim) return;
+  cudaSetDevice(sim->device);
+  if (sim->stream) cudaStreamSynchronize(sim->stream);
+  for (int b = 0; b < 2; b++) {
+    sim->pos[b].release(); sim->vel[b].release(); sim->mass[b].release(); sim->level[b].release(); sim->refid[b].release();
+    sim->xv[b].release(); sim->packP[b].release(); sim->front[b].release(); sim->work[b].release();
+  }
+  sim->xyhm.release(); sim->packA.release(); sim->pconst.release(); sim->h_tmp.release(); sim->rho.release(); sim->lam_sum.release();
+  sim->nrm.release(); sim->gB.release(); sim->lam_grad.release(); sim->key.release(); sim->cellcount.release(); sim->cellstart.release();
+  sim->order.release(); sim->scan_sums.release(); sim->cnt.release(); sim->slice_base.release(); sim->slice_cbase.release();
+  sim->nidx.release(); sim->ncoef.release(); sim->size_class.release(); sim->flags.release(); sim->merge_partner.release();
+  sim->cand.release(); for (int k = 0; k < 4; k++) sim->scratch_u[k].release();
+  sim->merge_counter.release(); sim->stamp.release(); sim->scratch_f.release(); sim->lut.release(); sim->split_pos.release();
+  sim->split_off.release(); sim->blockstats.release();
+  if (sim->ctl) cudaFree(sim->ctl);
+  if (sim->ctl_host) cudaFreeHost(sim->ctl_host);
+  if (sim->stream) cudaStreamDestroy(sim->stream);
+  cudaGetLastError();
+  delete sim;
+}
+
+int asph_step_physics(asph_sim* sim, const asph_params* params, float* dt_out) {
+  if (!sim || !params) return ASPH_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(sim->device));
+  return step_physics(sim, params, dt_out);
+}
+int asph_step_adaptivity(asph_sim* sim, const asph_params* params, float dt) {
+  if (!sim || !params) return ASPH_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(sim->device));
+  return step_adaptivity(sim, params, dt);
+}
+int asph_step(asph_sim* sim, const asph_params* params, float* dt_out) {  // simulation.rs:1973-1978
+  if (!sim || !params) return ASPH_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(sim->device));
+  float dt = 0.f;
+  TRY(step_physics(sim, params, &dt));
+  if (dt_out) *dt_out = dt;
+  return step_adaptivity(sim, params, dt);
+}
+
+uint64_t asph_num_particles(const asph_sim* sim) { return sim->dist ? sim->n_owned : sim->n; }
+double asph_time(const asph_sim* sim) { return sim->time; }
+uint64_t asph_step_number(const asph_sim* sim) { return sim->step_number; }
+
+int asph_get_field(asph_sim* sim, int field, void* dst, uint64_t bytes) {
+  if (!sim || !dst) return ASPH_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(sim->device));
+  int comps = 1;
+  const int eb = field_elem_bytes(field, &comps);
+  if (eb == 0) { sim->last_error = "field not available from the CUDA backend"; return ASPH_ERR_UNSUPPORTED; }
+  const uint32_t n = sim->dist ? sim->n_owned : sim->n;
+  const uint64_t need = uint64_t(n) * comps * eb;
+  if (bytes < need) return ASPH_ERR_INVALID;
+  const bool persistent = field == ASPH_F_POSITION || field == ASPH_F_VELOCITY || field == ASPH_F_MASS || field == ASPH_F_LEVEL;
+  if (!persistent && !sim->step_fields_valid) {
+    sim->last_error = "per-step field requested before a physics step (or after resampling changed the particle set)";
+    return ASPH_ERR_INVALID;
+  }
+  if (n == 0) return ASPH_OK;
+  // scatter into reference order in scratch (scratch_f holds 2 * cap floats)
+  void* tmp = sim->scratch_f.p;
+  const int c = sim->cur;
+  k_extract<<<(n + kThreads - 1) / kThreads, kThreads, 0, sim->stream>>>(
+      n, field, sim->dist ? sim->scratch_u[3].p : sim->refid[c].p, sim->pos[c].p, sim->vel[c].p, sim->mass[c].p, sim->xyhm.p, sim->rho.p,
+      sim->packP[sim->p_cur].p, sim->pconst.p, sim->packA.p, sim->level[c].p, sim->size_class.p, sim->cnt.p, sim->flags.p,
+      sim->lam_sum.p, sim->lam_grad.p, sim->merge_partner.p, sim->merge_counter.p, tmp);
+  LAUNCH_CHECK();
+  CUDA_TRY(cudaMemcpyAsync(dst, tmp, need, cudaMemcpyDeviceToHost, sim->stream));
+  CUDA_TRY(cudaStreamSynchronize(sim->stream));
+  return ASPH_OK;
+}
+
+int asph_get_neighbors_csr(asph_sim* sim, uint64_t* offsets, uint32_t* idx, uint64_t cap, uint64_t* nnz_out) {
+  if (!sim) return ASPH_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(sim->device));
+  if (!sim->lists_valid) { sim->last_error = "no neighbour lists (call asph_build_neighbors or step first)"; return ASPH_ERR_INVALID; }
+  if (sim->dist) { sim->last_error = "neighbour read-back on a distributed handle"; return ASPH_ERR_UNSUPPORTED; }
+  const uint32_t n = sim->n;
+  std::vector<uint32_t> cnt(n), refid(n), sbase((n + 31) / 32);
+  TRY(sync_ctl(sim));
+  const size_t used = sim->ctl_host->list_used;
+  std::vector<uint32_t> pool(used);
+  if (n) {
+    CUDA_TRY(cudaMemcpy(cnt.data(), sim->cnt.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(refid.data(), sim->refid[sim->cur].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(sbase.data(), sim->slice_base.p, sbase.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (used) CUDA_TRY(cudaMemcpy(pool.data(), sim->nidx.p, used * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  }
+  uint64_t nnz = 0;
+  for (uint32_t i = 0; i < n; i++) nnz += cnt[i] & 0xffffu;
+  if (nnz_out) *nnz_out = nnz;
+  if (!idx) return ASPH_OK;
+  if (cap < nnz || !offsets) return ASPH_ERR_INVALID;
+  std::vector<uint32_t> where(n);  // reference index -> device index
+  for (uint32_t i = 0; i < n; i++) where[refid[i]] = i;
+  uint64_t o = 0;
+  for (uint32_t r = 0; r < n; r++) {
+    const uint32_t i = where[r];
+    offsets[r] = o;
+    const uint32_t c = cnt[i] & 0xffffu;
+    const size_t base = size_t(sbase[i >> 5]) + (i & 31);
+    for (uint32_t k = 0; k < c; k++) idx[o + k] = refid[pool[base + 32u * k]];
+    std::sort(idx + o, idx + o + c);
+    o += c;
+  }
+  offsets[n] = o;
+  return ASPH_OK;
+}
+
+int asph_build_neighbors(asph_sim* sim, const asph_params* params, float f) {
+  if (!sim || !params) return ASPH_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(sim->device));
+  int rc = pack_params(sim, params);
+  if (rc != ASPH_OK && rc != ASPH_ERR_UNSUPPORTED) return rc;
+  if (sim->dist) { sim->last_error = "asph_build_neighbors on a distributed handle"; return ASPH_ERR_UNSUPPORTED; }
+  TRY(launch_sort_and_grid(sim, f));
+  TRY(launch_neighbors(sim, f, f));
+  const unsigned int fl = sim->ctl_host->error_flags;
+  if (fl & ERRF_NEIGHBOR_OVERFLOW) return check_error_flags(sim);
+  if (fl & ERRF_CELL_BUDGET) return check_error_flags(sim);
+  sim->step_fields_valid = true;
+  return ASPH_OK;
+}
+
+int asph_get_step_info(const asph_sim* sim, asph_step_info* out) { *out = sim->info; return ASPH_OK; }
+int asph_get_counters(const asph_sim* sim, double ms[ASPH_PC_COUNT], uint64_t calls[ASPH_PC_COUNT]) {
+  for (int i = 0; i < ASPH_PC_COUNT; i++) { ms[i] = sim->pc_ms[i]; calls[i] = sim->pc_calls[i]; }
+  return ASPH_OK;
+}
+const char* asph_last_error(const asph_sim* sim) { return sim ? sim->last_error.c_str() : ""; }
+
+// ---- pure helpers (host code) ------------------------------------------------------------------------------
+// cubic_kernel_2d / cubic_kernel_2d_deriv, sph_kernels.rs:49-71
+float asph_kernel_w(float r, float h) {
+  const float nf = 10.f / (7.f * 3.14159265358979323846f * (h * h));
+  const float q = r / (2.f * h);
+  float w;
+  if (q < 0.5f) w = 6.f * (q * q * q - q * q) + 1.f;
+  else if (q < 1.f) { float v = 1.f - q; w = 2.f * (v * v * v); }
+  else w = 0.f;
+  return nf * w;
+}
+void asph_kernel_grad(float dx, float dy, float h, float* gx, float* gy) {
+  const float r = std::sqrt(dx * dx + dy * dy);
+  const float q = r / (2.f * h);
+  if (q <= 1.0e-5f) { *gx = 0.f; *gy = 0.f; return; }
+  const float nf = 10.f / (7.f * 3.14159265358979323846f * (h * h));
+  float dw;
+  if (q < 0.5f) dw = 18.f * q * q - 12.f * q;
+  else if (q < 1.f) { float v = 1.f - q; dw = -6.f * v * v; }
+  else dw = 0.f;
+  const float s = nf * dw / (2.f * h);
+  *gx = s * (dx / r); *gy = s * (dy / r);
+}
+double asph_lambda(double d) { return asph_host_lambda(d); }
+double asph_dlambda(double d) { return asph_host_dlambda(d); }
+static std::vector<float>& host_lut(int which) {
+  static std::vector<float> lam, dlam;
+  if (lam.empty()) asph_host_build_luts(lam, dlam);
+  return which ? dlam : lam;
+}
+float asph_lambda_lut(float d) { return asph_host_lut_get(host_lut(0), d); }
+float asph_dlambda_lut(float d) { return asph_host_lut_get(host_lut(1), d); }
+
+// kernels launched by this handle so far (bench.py reports it as gpu_launches)
+uint64_t asph_kernel_launches(const asph_sim* sim) { return sim ? sim->kernel_launches : 0; }
+
+}  // extern "C"

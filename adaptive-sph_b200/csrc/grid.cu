@@ -1,0 +1,341 @@
+// grid.cu — per-step preparation: h from mass, CFL minimum, bounding box, multi-resolution cell grid,
+// deterministic counting sort of the particles by (size level, cell) and the physical reorder of the SoA.
+//
+// Replaces (semantically) the R*-tree bulk load of neighborhood_search.rs:113-119 and h_next_from_mass
+// (simulation.rs:1865-1871), plus the CFL reduce of simulation.rs:2182-2191.
+//
+// Multi-resolution grid: level L holds particles with h in [hmin*2^L, hmin*2^(L+1)); its cells have edge
+// f_search * hmax_L * SLACK with hmax_L = min(hmin*2^(L+1), hmax).  A pair (i in level a, j in level b) has
+// support f*(h_i+h_j)/2 <= f*(h_i + hmax_b)/2, so i finds all its level-b neighbours in the cells of grid b that
+// overlap the box of that radius around x_i (neighbors.cu).  With uniform h there is one level whose cell is
+// exactly the support radius.
+#include "sim.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__global__ void k_ctl_reset(StepCtl* ctl) {
+  ctl->hmin_enc = 0xFFFFFFFFu; ctl->minx_enc = 0xFFFFFFFFu; ctl->miny_enc = 0xFFFFFFFFu; ctl->cfl_enc = 0xFFFFFFFFu;
+  ctl->hmax_enc = 0u; ctl->maxx_enc = 0u; ctl->maxy_enc = 0u;
+  ctl->list_used = 0; ctl->coef_used = 0; ctl->max_count = 0;
+  ctl->error_flags = 0;
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// K1 + K8 + bounding box.  h is bit-exact (neighbour predicate); the CFL term follows simulation.rs:2184-2186
+// operation by operation ((2h)^2 / (v.v + 0.01)), and min is order independent, so dt is bit-exact too.
+__global__ void k_prepare(uint32_t n, const float2* __restrict__ pos, const float2* __restrict__ vel,
+                          const float* __restrict__ mass, float rho0, float* __restrict__ h_out, StepCtl* ctl) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float inf = __int_as_float(0x7f800000);
+  float hmin = inf, hmax = -inf, minx = inf, miny = inf, maxx = -inf, maxy = -inf, cfl = inf;
+  if (i < n) {
+    float2 x = pos[i], v = vel[i];
+    float h = h_from_mass(mass[i], rho0);
+    h_out[i] = h;
+    hmin = hmax = h;
+    minx = maxx = x.x; miny = maxy = x.y;
+    float sr = __fmul_rn(h, 2.f);
+    cfl = __fdiv_rn(__fmul_rn(sr, sr), __fadd_rn(dist_sq_exact(v.x, v.y), 0.01f));
+  }
+  hmin = warp_min(hmin); hmax = warp_max(hmax); minx = warp_min(minx); miny = warp_min(miny);
+  maxx = warp_max(maxx); maxy = warp_max(maxy); cfl = warp_min(cfl);
+  __shared__ float s[7][kThreads / 32];
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s[0][w] = hmin; s[1][w] = hmax; s[2][w] = minx; s[3][w] = miny; s[4][w] = maxx; s[5][w] = maxy; s[6][w] = cfl; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = kThreads / 32;
+    hmin = l < nw ? s[0][l] : inf; hmax = l < nw ? s[1][l] : -inf; minx = l < nw ? s[2][l] : inf;
+    miny = l < nw ? s[3][l] : inf; maxx = l < nw ? s[4][l] : -inf; maxy = l < nw ? s[5][l] : -inf;
+    cfl = l < nw ? s[6][l] : inf;
+    hmin = warp_min(hmin); hmax = warp_max(hmax); minx = warp_min(minx); miny = warp_min(miny);
+    maxx = warp_max(maxx); maxy = warp_max(maxy); cfl = warp_min(cfl);
+    if (l == 0) {
+      atomicMin(&ctl->hmin_enc, enc_f(hmin)); atomicMax(&ctl->hmax_enc, enc_f(hmax));
+      atomicMin(&ctl->minx_enc, enc_f(minx)); atomicMin(&ctl->miny_enc, enc_f(miny));
+      atomicMax(&ctl->maxx_enc, enc_f(maxx)); atomicMax(&ctl->maxy_enc, enc_f(maxy));
+      atomicMin(&ctl->cfl_enc, enc_f(cfl));
+    }
+  }
+}
+
+// Single thread: decide levels, cell sizes and grid dimensions; dt = min(max_dt, cfl * sqrt(min)) (simulation.rs:2188-2191).
+__global__ void k_make_levels(StepCtl* ctl, float f_search, uint32_t cells_budget, float max_dt, float cfl_factor) {
+  float hmin = dec_f(ctl->hmin_enc), hmax = dec_f(ctl->hmax_enc);
+  float minx = dec_f(ctl->minx_enc), miny = dec_f(ctl->miny_enc), maxx = dec_f(ctl->maxx_enc), maxy = dec_f(ctl->maxy_enc);
+  ctl->hmin = hmin; ctl->hmax = hmax; ctl->origin_x = minx; ctl->origin_y = miny;
+  ctl->dt = fminf(max_dt, __fmul_rn(cfl_factor, __fsqrt_rn(dec_f(ctl->cfl_enc))));
+  int nl = 1;
+  {
+    float bound = hmin * 2.f;
+    while (hmax >= bound && nl < ASPH_MAX_LEVELS) { nl++; bound *= 2.f; }
+  }
+  ctl->nlevels = nl;
+  float scale = 1.f;
+  for (int attempt = 0; attempt < 64; attempt++) {
+    unsigned long long total = 0;
+    float upper = hmin * 2.f;
+    for (int L = 0; L < nl; L++) {
+      float hm = (L == nl - 1) ? hmax : fminf(upper, hmax);
+      float cell = f_search * hm * ASPH_SLACK * scale;
+      GridLevel g;
+      g.hmax = hm; g.cell = cell; g.inv_cell = 1.f / cell;
+      g.nx = int(floorf((maxx - minx) * g.inv_cell)) + 1;
+      g.ny = int(floorf((maxy - miny) * g.inv_cell)) + 1;
+      g.base = uint32_t(total);
+      ctl->lv[L] = g;
+      total += (unsigned long long)g.nx * (unsigned long long)g.ny;
+      upper *= 2.f;
+    }
+    if (total <= cells_budget) { ctl->total_cells = uint32_t(total); return; }
+    scale *= 1.5f;
+  }
+  ctl->total_cells = 0;
+  atomicOr(&ctl->error_flags, ERRF_CELL_BUDGET);
+}
+
+__global__ void k_zero_cells(const StepCtl* __restrict__ ctl, uint32_t* __restrict__ cellcount) {
+  uint32_t total = ctl->total_cells + 1;
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < total; c += gridDim.x * blockDim.x) cellcount[c] = 0;
+}
+
+__device__ __forceinline__ int level_of(float h, float hmin, int nl) {
+  int L = 0;
+  float bound = hmin * 2.f;
+  while (L < nl - 1 && h >= bound) { L++; bound *= 2.f; }
+  return L;
+}
+
+__global__ void k_bin(uint32_t n, const float2* __restrict__ pos, const float* __restrict__ h, const StepCtl* __restrict__ ctl,
+                      uint32_t* __restrict__ key, uint32_t* __restrict__ cellcount) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int L = level_of(h[i], ctl->hmin, ctl->nlevels);
+  GridLevel g = ctl->lv[L];
+  float2 x = pos[i];
+  int cx = min(g.nx - 1, max(0, int(floorf((x.x - ctl->origin_x) * g.inv_cell))));
+  int cy = min(g.ny - 1, max(0, int(floorf((x.y - ctl->origin_y) * g.inv_cell))));
+  uint32_t k = g.base + uint32_t(cy) * uint32_t(g.nx) + uint32_t(cx);
+  key[i] = k;
+  atomicAdd(&cellcount[k], 1u);
+}
+
+// ---- exclusive scan over a device-side length (3 kernels; tiles of 2048) ---------------------------------
+constexpr int kScanTile = 2048;  // 256 threads * 8
+
+__global__ void k_scan_tiles(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t* __restrict__ sums,
+                             const uint32_t* __restrict__ n_dev, uint32_t n_add) {
+  const uint32_t n = *n_dev + n_add;
+  const uint32_t tile0 = blockIdx.x * kScanTile;
+  if (tile0 >= n) return;
+  uint32_t v[8], local = 0;
+  const uint32_t base = tile0 + threadIdx.x * 8;
+#pragma unroll
+  for (int k = 0; k < 8; k++) { v[k] = (base + k < n) ? in[base + k] : 0u; local += v[k]; }
+  // block exclusive scan of `local`
+  __shared__ uint32_t ws[kThreads / 32];
+  uint32_t incl = local;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) ws[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t x = lane < kThreads / 32 ? ws[lane] : 0u, xi = x;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= o) xi += t; }
+    if (lane < kThreads / 32) ws[lane] = xi - x;
+    if (lane == kThreads / 32 - 1) sums[blockIdx.x] = xi;
+  }
+  __syncthreads();
+  uint32_t run = ws[w] + incl - local;
+#pragma unroll
+  for (int k = 0; k < 8; k++) { if (base + k < n) out[base + k] = run; run += v[k]; }
+}
+__global__ void k_scan_sums(uint32_t* __restrict__ sums, const uint32_t* __restrict__ n_dev, uint32_t n_add) {
+  const uint32_t n = *n_dev + n_add;
+  const uint32_t nt = (n + kScanTile - 1) / kScanTile;
+  __shared__ uint32_t ws[32];
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (uint32_t t0 = 0; t0 < nt; t0 += blockDim.x) {
+    uint32_t t = t0 + threadIdx.x;
+    uint32_t x = t < nt ? sums[t] : 0u, incl = x;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    if (lane == 31) ws[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      uint32_t a = lane < (blockDim.x >> 5) ? ws[lane] : 0u, ai = a;
+      for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, ai, o); if (lane >= o) ai += y; }
+      ws[lane] = ai - a;
+    }
+    __syncthreads();
+    uint32_t carry = carry_s;
+    uint32_t excl = carry + ws[w] + incl - x;
+    if (t < nt) sums[t] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = excl + x;
+    __syncthreads();
+  }
+}
+__global__ void k_scan_add(uint32_t* __restrict__ out, const uint32_t* __restrict__ sums, const uint32_t* __restrict__ n_dev,
+                           uint32_t n_add) {
+  const uint32_t n = *n_dev + n_add;
+  const uint32_t tile0 = blockIdx.x * kScanTile;
+  if (tile0 >= n) return;
+  const uint32_t add = sums[blockIdx.x];
+  const uint32_t base = tile0 + threadIdx.x * 8;
+#pragma unroll
+  for (int k = 0; k < 8; k++) if (base + k < n) out[base + k] += add;
+}
+
+// slot = cellstart + (count-- - 1): leaves cellcount all zero again
+__global__ void k_scatter(uint32_t n, const uint32_t* __restrict__ key, const uint32_t* __restrict__ cellstart,
+                          uint32_t* __restrict__ cellcount, uint32_t* __restrict__ order) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k = key[i];
+  uint32_t c = atomicSub(&cellcount[k], 1u);
+  order[cellstart[k] + c - 1u] = i;
+}
+// make the counting sort stable (deterministic): ascending source index inside each cell
+__global__ void k_sort_cells(const StepCtl* __restrict__ ctl, const uint32_t* __restrict__ cellstart, uint32_t* __restrict__ order) {
+  const uint32_t total = ctl->total_cells;
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < total; c += gridDim.x * blockDim.x) {
+    uint32_t s = cellstart[c], e = cellstart[c + 1];
+    for (uint32_t a = s + 1; a < e; a++) {
+      uint32_t v = order[a];
+      uint32_t b = a;
+      while (b > s && order[b - 1] > v) { order[b] = order[b - 1]; b--; }
+      order[b] = v;
+    }
+  }
+}
+
+__global__ void k_reorder(uint32_t n, const uint32_t* __restrict__ order, const float2* __restrict__ pos, const float2* __restrict__ vel,
+                          const float* __restrict__ mass, const uint32_t* __restrict__ refid, const float* __restrict__ level,
+                          const float* __restrict__ h, float2* __restrict__ pos_o, float2* __restrict__ vel_o,
+                          float* __restrict__ mass_o, uint32_t* __restrict__ refid_o, float* __restrict__ level_o,
+                          float4* __restrict__ xyhm, float4* __restrict__ xv) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  uint32_t src = order[s];
+  float2 x = pos[src], v = vel[src];
+  float m = mass[src];
+  pos_o[s] = x; vel_o[s] = v; mass_o[s] = m; refid_o[s] = refid[src]; level_o[s] = level[src];
+  xyhm[s] = make_float4(x.x, x.y, h[src], m);
+  xv[s] = make_float4(x.x, x.y, v.x, v.y);
+}
+
+}  // namespace
+
+int sync_ctl(asph_sim* sim) {
+  CUDA_TRY(cudaMemcpyAsync(sim->ctl_host, sim->ctl, sizeof(StepCtl), cudaMemcpyDeviceToHost, sim->stream));
+  CUDA_TRY(cudaStreamSynchronize(sim->stream));
+  return ASPH_OK;
+}
+
+int launch_exclusive_scan(asph_sim* sim, const uint32_t* in, uint32_t* data, const uint32_t* n_dev, uint32_t n_add,
+                          uint32_t n_max) {
+  const uint32_t tiles = (n_max + kScanTile - 1) / kScanTile;
+  CUDA_TRY(sim->scan_sums.ensure(tiles + 1));
+  k_scan_tiles<<<tiles, kThreads, 0, sim->stream>>>(in, data, sim->scan_sums.p, n_dev, n_add);
+  LAUNCH_CHECK();
+  k_scan_sums<<<1, 1024, 0, sim->stream>>>(sim->scan_sums.p, n_dev, n_add);
+  LAUNCH_CHECK();
+  k_scan_add<<<tiles, kThreads, 0, sim->stream>>>(data, sim->scan_sums.p, n_dev, n_add);
+  LAUNCH_CHECK();
+  return ASPH_OK;
+}
+
+int ensure_capacity(asph_sim* sim, uint32_t want) {
+  if (want <= sim->cap && sim->cap > 0) return ASPH_OK;
+  // growing: persistent arrays must be preserved
+  uint32_t newcap = want;
+  const uint32_t old_n = sim->n;
+  for (int b = 0; b < 2; b++) {
+    if (b == sim->cur && sim->cap > 0 && old_n > 0) {
+      DevBuf<float2> p2, v2; DevBuf<float> m2, l2; DevBuf<uint32_t> r2;
+      CUDA_TRY(p2.ensure(newcap)); CUDA_TRY(v2.ensure(newcap)); CUDA_TRY(m2.ensure(newcap)); CUDA_TRY(l2.ensure(newcap));
+      CUDA_TRY(r2.ensure(newcap));
+      CUDA_TRY(cudaMemcpyAsync(p2.p, sim->pos[b].p, old_n * sizeof(float2), cudaMemcpyDeviceToDevice, sim->stream));
+      CUDA_TRY(cudaMemcpyAsync(v2.p, sim->vel[b].p, old_n * sizeof(float2), cudaMemcpyDeviceToDevice, sim->stream));
+      CUDA_TRY(cudaMemcpyAsync(m2.p, sim->mass[b].p, old_n * sizeof(float), cudaMemcpyDeviceToDevice, sim->stream));
+      CUDA_TRY(cudaMemcpyAsync(l2.p, sim->level[b].p, old_n * sizeof(float), cudaMemcpyDeviceToDevice, sim->stream));
+      CUDA_TRY(cudaMemcpyAsync(r2.p, sim->refid[b].p, old_n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sim->stream));
+      CUDA_TRY(cudaStreamSynchronize(sim->stream));
+      sim->pos[b].release(); sim->vel[b].release(); sim->mass[b].release(); sim->level[b].release(); sim->refid[b].release();
+      sim->pos[b] = p2; sim->vel[b] = v2; sim->mass[b] = m2; sim->level[b] = l2; sim->refid[b] = r2;
+    } else {
+      CUDA_TRY(sim->pos[b].ensure(newcap)); CUDA_TRY(sim->vel[b].ensure(newcap)); CUDA_TRY(sim->mass[b].ensure(newcap));
+      CUDA_TRY(sim->level[b].ensure(newcap)); CUDA_TRY(sim->refid[b].ensure(newcap));
+    }
+  }
+  CUDA_TRY(sim->xyhm.ensure(newcap)); CUDA_TRY(sim->xv[0].ensure(newcap)); CUDA_TRY(sim->xv[1].ensure(newcap));
+  CUDA_TRY(sim->packP[0].ensure(newcap)); CUDA_TRY(sim->packP[1].ensure(newcap)); CUDA_TRY(sim->packA.ensure(newcap));
+  CUDA_TRY(sim->pconst.ensure(newcap));
+  CUDA_TRY(sim->h_tmp.ensure(newcap)); CUDA_TRY(sim->rho.ensure(newcap)); CUDA_TRY(sim->lam_sum.ensure(newcap));
+  CUDA_TRY(sim->nrm.ensure(newcap)); CUDA_TRY(sim->gB.ensure(newcap)); CUDA_TRY(sim->lam_grad.ensure(newcap));
+  CUDA_TRY(sim->key.ensure(newcap)); CUDA_TRY(sim->order.ensure(newcap));
+  CUDA_TRY(sim->cnt.ensure(newcap));
+  const uint32_t nslices = (newcap + 31) / 32 + 1;
+  CUDA_TRY(sim->slice_base.ensure(nslices)); CUDA_TRY(sim->slice_cbase.ensure(nslices));
+  CUDA_TRY(sim->size_class.ensure(newcap)); CUDA_TRY(sim->flags.ensure(newcap));
+  CUDA_TRY(sim->merge_partner.ensure(newcap)); CUDA_TRY(sim->merge_counter.ensure(newcap));
+  CUDA_TRY(sim->front[0].ensure(newcap)); CUDA_TRY(sim->front[1].ensure(newcap)); CUDA_TRY(sim->cand.ensure(newcap));
+  CUDA_TRY(sim->work[0].ensure(newcap)); CUDA_TRY(sim->work[1].ensure(newcap));
+  for (int k = 0; k < 4; k++) CUDA_TRY(sim->scratch_u[k].ensure(size_t(newcap) + 1));
+  CUDA_TRY(sim->stamp.ensure(newcap));
+  CUDA_TRY(sim->scratch_f.ensure(size_t(newcap) * 2));
+  sim->cells_budget = 2u * newcap + 65536u;
+  CUDA_TRY(sim->cellcount.ensure(size_t(sim->cells_budget) + 2));
+  CUDA_TRY(sim->cellstart.ensure(size_t(sim->cells_budget) + 2));
+  CUDA_TRY(cudaMemsetAsync(sim->cellcount.p, 0, (size_t(sim->cells_budget) + 2) * sizeof(uint32_t), sim->stream));
+  sim->cap = newcap;
+  sim->lists_valid = false;
+  return ASPH_OK;
+}
+
+// h, bbox, CFL/dt, levels, counting sort, reorder.  Afterwards the persistent arrays live in buffer `cur`
+// in sorted order and xyhm / xv[xv_cur] hold the step's snapshot.
+int launch_sort_and_grid(asph_sim* sim, float f_search) {
+  const uint32_t n = sim->n;
+  cudaStream_t st = sim->stream;
+  k_ctl_reset<<<1, 1, 0, st>>>(sim->ctl);
+  LAUNCH_CHECK();
+  if (n == 0) return ASPH_OK;
+  const uint32_t blocks = (n + kThreads - 1) / kThreads;
+  const int c = sim->cur;
+  k_prepare<<<blocks, kThreads, 0, st>>>(n, sim->pos[c].p, sim->vel[c].p, sim->mass[c].p, sim->pp.rest_density, sim->h_tmp.p, sim->ctl);
+  LAUNCH_CHECK();
+  k_make_levels<<<1, 1, 0, st>>>(sim->ctl, f_search, sim->cells_budget, sim->pp.max_dt, sim->pp.cfl_factor);
+  LAUNCH_CHECK();
+  const int wide = sim->sm_count * 8;
+  k_zero_cells<<<wide, kThreads, 0, st>>>(sim->ctl, sim->cellcount.p);
+  LAUNCH_CHECK();
+  k_bin<<<blocks, kThreads, 0, st>>>(n, sim->pos[c].p, sim->h_tmp.p, sim->ctl, sim->key.p, sim->cellcount.p);
+  LAUNCH_CHECK();
+  // cellstart = exclusive scan of cellcount over total_cells + 1 entries
+  TRY(launch_exclusive_scan(sim, sim->cellcount.p, sim->cellstart.p, &sim->ctl->total_cells, 1, sim->cells_budget + 1));
+  k_scatter<<<blocks, kThreads, 0, st>>>(n, sim->key.p, sim->cellstart.p, sim->cellcount.p, sim->order.p);
+  LAUNCH_CHECK();
+  k_sort_cells<<<wide, kThreads, 0, st>>>(sim->ctl, sim->cellstart.p, sim->order.p);
+  LAUNCH_CHECK();
+  sim->xv_cur = 0;
+  k_reorder<<<blocks, kThreads, 0, st>>>(n, sim->order.p, sim->pos[c].p, sim->vel[c].p, sim->mass[c].p, sim->refid[c].p,
+                                         sim->level[c].p, sim->h_tmp.p, sim->pos[1 - c].p, sim->vel[1 - c].p, sim->mass[1 - c].p,
+                                         sim->refid[1 - c].p, sim->level[1 - c].p, sim->xyhm.p, sim->xv[0].p);
+  LAUNCH_CHECK();
+  sim->cur = 1 - c;
+  return ASPH_OK;
+}

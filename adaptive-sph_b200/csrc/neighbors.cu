@@ -1,0 +1,243 @@
+// neighbors.cu — neighbour lists (sliced ELL) from the multi-resolution cell grid, fused with every per-particle
+// quantity that only needs the pre-advection snapshot {x, h, m}: boundary terms (K7), density (K9), the a_ii
+// diagonal (K11) and the un-normalised surface normal of the level-set detector (first half of K3).
+//
+// Neighbour set (bit exact): N_f(i) = { j : |x_ij|^2 < ((h_i+h_j)*0.5*f)^2 }, fp32, no FMA contraction —
+// the final set of build_neighborhood_list_rstar after its symmetrize pass (neighborhood_search.rs:123-185, checked
+// by the reference's own brute-force test at :216-237 and simulation.rs:1810-1863).  Rows 0..cnt_near-1 of a
+// particle's ELL column are N_2 (what NeighborhoodCache::filter_down leaves, neighborhood_search.rs:56-70), rows
+// cnt_near..cnt_ext-1 the rest of N_{f_ext} used only by the level-set estimation.
+#include "sim.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+
+// LookupTable1D::get over [-1, 1], 10000 steps (lookup_table.rs:32-48), same operation order
+__device__ __forceinline__ float lut_get(const float* __restrict__ data, float x) {
+  float fidx = __fmul_rn(__fmul_rn(__fsub_rn(x, -1.f), 0.5f), 10000.f);
+  float fl = floorf(fidx);
+  float t = __fsub_rn(fidx, fl);
+  int idx = int(fl);
+  if (idx + 1 >= 10001) return data[idx];
+  return __fadd_rn(__fmul_rn(data[idx], __fsub_rn(1.f, t)), __fmul_rn(data[idx + 1], t));
+}
+
+__device__ __forceinline__ float plane_probe(const float* pl, float x, float y) {  // SdfPlane::probe sdf_plane.rs:36-38
+  return __fadd_rn(__fadd_rn(__fmul_rn(pl[0], x), __fmul_rn(pl[1], y)), pl[2]);
+}
+
+// BoundaryWinchenbach2020::update_after_advect (boundary_winchenbach2020.rs:58-152): Σ λ·penalty and Σ ∇(λ·penalty)
+__device__ __forceinline__ void boundary_terms(const PackedParams& P, const float* __restrict__ lut, float x, float y, float h,
+                                               float& lam_sum, float& gx_sum, float& gy_sum) {
+  lam_sum = 0.f; gx_sum = 0.f; gy_sum = 0.f;
+  const float sr = __fmul_rn(h, 2.f);
+  const float eps = P.sdf_gradient_eps;
+  const float inv_2eps = __fdiv_rn(1.f, __fmul_rn(2.f, eps));
+  for (int s = 0; s < P.n_planes; s++) {
+    const float* pl = P.planes[s];
+    float d = __fdiv_rn(plane_probe(pl, x, y), sr);
+    if (!(d < 1.f)) continue;
+    // finite_diff_gradient sdf.rs:50-62
+    float gx = __fmul_rn(__fsub_rn(plane_probe(pl, __fadd_rn(x, eps), y), plane_probe(pl, __fsub_rn(x, eps), y)), inv_2eps);
+    float gy = __fmul_rn(__fsub_rn(plane_probe(pl, x, __fadd_rn(y, eps)), plane_probe(pl, x, __fsub_rn(y, eps))), inv_2eps);
+    float gn = __fsqrt_rn(dist_sq_exact(gx, gy));
+    if (gn < 0.00001f) continue;
+    gx = __fdiv_rn(gx, gn); gy = __fdiv_rn(gy, gn);
+    float pen, pder;
+    switch (P.penalty) {
+      case ASPH_PENALTY_NONE: pen = 1.f; pder = 0.f; break;
+      case ASPH_PENALTY_LINEAR: pen = __fsub_rn(1.f, d); pder = -1.f; break;
+      case ASPH_PENALTY_QUADRATIC1:
+        if (d > 0.f) { pen = 1.f; pder = 0.f; }
+        else if (d > -1.f) { pen = __fadd_rn(__fmul_rn(__fmul_rn(0.5f, d), d), 1.f); pder = d; }
+        else { pen = __fsub_rn(0.5f, d); pder = -1.f; }
+        break;
+      default:
+        if (d > 0.f) { pen = 1.f; pder = 0.f; }
+        else if (d > -0.5f) { pen = __fadd_rn(__fmul_rn(d, d), 1.f); pder = __fmul_rn(2.f, d); }
+        else { pen = __fsub_rn(0.75f, d); pder = -1.f; }
+        break;
+    }
+    float lam, lamd;
+    if (d <= -1.f) { lam = 1.f; lamd = 0.f; }
+    else { lam = lut_get(lut, d); lamd = lut_get(lut + 10001, d); }
+    float scale = __fadd_rn(__fmul_rn(pder, lam), __fmul_rn(pen, lamd));
+    lam_sum = __fadd_rn(lam_sum, __fmul_rn(lam, pen));
+    gx_sum = __fadd_rn(gx_sum, __fmul_rn(__fdiv_rn(gx, sr), scale));
+    gy_sum = __fadd_rn(gy_sum, __fmul_rn(__fdiv_rn(gy, sr), scale));
+  }
+}
+
+// Visit every particle j stored in a grid cell that overlaps the search box of particle i, level by level.
+template <class F>
+__device__ __forceinline__ void for_each_candidate(float xi, float yi, float hi, const StepCtl* __restrict__ ctl,
+                                                   const uint32_t* __restrict__ cellstart, float f_search, F f) {
+  const int nl = ctl->nlevels;
+  const float ox = ctl->origin_x, oy = ctl->origin_y;
+  for (int b = 0; b < nl; b++) {
+    const GridLevel g = ctl->lv[b];
+    const float r = f_search * (hi + g.hmax) * 0.5f * ASPH_SLACK;
+    const int cx0 = max(0, int(floorf((xi - r - ox) * g.inv_cell)));
+    const int cx1 = min(g.nx - 1, int(floorf((xi + r - ox) * g.inv_cell)));
+    const int cy0 = max(0, int(floorf((yi - r - oy) * g.inv_cell)));
+    const int cy1 = min(g.ny - 1, int(floorf((yi + r - oy) * g.inv_cell)));
+    if (cx0 > cx1) continue;
+    for (int cy = cy0; cy <= cy1; cy++) {
+      const uint32_t row = g.base + uint32_t(cy) * uint32_t(g.nx);
+      const uint32_t s = cellstart[row + cx0], e = cellstart[row + cx1 + 1];
+      for (uint32_t j = s; j < e; j++) f(j);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restrict__ ctl_in, StepCtl* ctl,
+            const uint32_t* __restrict__ cellstart, const PackedParams P, const float* __restrict__ lut, float f_ext, float f_near,
+            uint32_t list_cap, uint32_t coef_cap, uint32_t* __restrict__ nidx, float* __restrict__ ncoef,
+            uint32_t* __restrict__ slice_base, uint32_t* __restrict__ slice_cbase, uint32_t* __restrict__ cnt,
+            float* __restrict__ rho_out, float2* __restrict__ gB_out, float4* __restrict__ pconst, float* __restrict__ lam_sum_out,
+            float2* __restrict__ lam_grad_out, float2* __restrict__ nrm_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool active = i < n;
+  float4 me = make_float4(0.f, 0.f, 1.f, 0.f);
+  if (active) me = xyhm[i];
+  const float xi = me.x, yi = me.y, hi = me.z;
+
+  // pass 1: counts
+  uint32_t cn = 0, ce = 0;
+  if (active) {
+    for_each_candidate(xi, yi, hi, ctl_in, cellstart, f_ext, [&](uint32_t j) {
+      const float4 o = __ldg(&xyhm[j]);
+      const float d2 = dist_sq_exact(__fsub_rn(xi, o.x), __fsub_rn(yi, o.y));
+      if (d2 < support_sq_exact(hi, o.z, f_ext)) {
+        ce++;
+        if (d2 < support_sq_exact(hi, o.z, f_near)) cn++;
+      }
+    });
+  }
+  uint32_t wn = cn, we = ce;
+  for (int o = 16; o > 0; o >>= 1) {
+    wn = max(wn, __shfl_xor_sync(0xffffffffu, wn, o));
+    we = max(we, __shfl_xor_sync(0xffffffffu, we, o));
+  }
+  uint32_t base = 0, cbase = 0;
+  if (lane == 0) {
+    base = atomicAdd(&ctl->list_used, 32u * we);
+    cbase = atomicAdd(&ctl->coef_used, 32u * wn);
+    atomicMax(&ctl->max_count, we);
+    if (we > 20000u) atomicOr(&ctl->error_flags, ERRF_NEIGHBOR_OVERFLOW);  // MAX_NEIGHBOR_COUNT neighborhood_search.rs:3,148-150
+    if (base + 32u * we > list_cap || cbase + 32u * wn > coef_cap || base + 32u * we < base) atomicOr(&ctl->error_flags, ERRF_LIST_CAPACITY);
+    slice_base[i >> 5] = base;
+    slice_cbase[i >> 5] = cbase;
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  cbase = __shfl_sync(0xffffffffu, cbase, 0);
+  if (!active) return;
+  cnt[i] = cn | (ce << 16);
+  if (base + 32u * we > list_cap || cbase + 32u * wn > coef_cap || base + 32u * we < base) return;
+
+  // boundary terms
+  float lam, Gx, Gy;
+  boundary_terms(P, lut, xi, yi, hi, lam, Gx, Gy);
+
+  // pass 2: fill + pair sums
+  uint32_t kn = 0, ke = cn;
+  float rho = 0.f, Sx = 0.f, Sy = 0.f, Q = 0.f, Nx = 0.f, Ny = 0.f;
+  uint32_t* col = nidx + base + lane;
+  float* ccol = ncoef + cbase + lane;
+  for_each_candidate(xi, yi, hi, ctl_in, cellstart, f_ext, [&](uint32_t j) {
+    const float4 o = __ldg(&xyhm[j]);
+    const float dx = __fsub_rn(xi, o.x), dy = __fsub_rn(yi, o.y);
+    const float d2 = dist_sq_exact(dx, dy);
+    if (d2 < support_sq_exact(hi, o.z, f_near)) {
+      const float hij = (hi + o.z) * 0.5f;  // smoothing_length sph_kernels.rs:273-278
+      const float r = sqrtf(d2);
+      const float nf = kernel_norm(hij);
+      const float q = r / (2.f * hij);
+      rho += o.w * (nf * cubic_w(q));
+      float g = 0.f;
+      if (q > 1.0e-5f) {
+        const float dwdr = nf * cubic_dw(q) / (2.f * hij);
+        g = dwdr / r;
+        Q += o.w * (dwdr * dwdr);
+      }
+      const float c = o.w * g;
+      Sx += c * dx; Sy += c * dy;
+      Nx += g * dx; Ny += g * dy;
+      col[32u * kn] = j;
+      ccol[32u * kn] = c;
+      kn++;
+    } else if (d2 < support_sq_exact(hi, o.z, f_ext)) {
+      col[32u * ke] = j;
+      ke++;
+    }
+  });
+
+  // density, simulation.rs:1018-1047
+  rho += lam;
+  unsigned int err = 0;
+  if (!isfinite(rho)) err |= ERRF_NONFINITE;
+  else if (!(rho > 0.0001f)) err |= ERRF_DENSITY;
+  // a_ii, iisph_aii boundary_winchenbach2020.rs:270-304 (Consistent{Simple,Symmetric}Gradient)
+  const float rho0 = P.rest_density;
+  const float rho2 = rho * rho;
+  const float Bc = (P.opdisc == ASPH_OP_CONSISTENT_SYMMETRIC_GRADIENT) ? rho0 * (1.f / rho2 + 1.f / (rho0 * rho0)) : rho0 / rho2;
+  const float ax = Sx / rho2 + Bc * Gx, ay = Sy / rho2 + Bc * Gy;
+  const float bx = Sx / rho + rho0 * Gx / rho, by = Sy / rho + rho0 * Gy / rho;
+  const float aii = (ax * bx + ay * by) + (me.w * Q) / (rho2 * rho);
+  if (!isfinite(aii)) err |= ERRF_NONFINITE;
+  else if (aii < 0.f) err |= ERRF_NEG_AII;
+  if (err) atomicOr(&ctl->error_flags, err);
+  rho_out[i] = rho;
+  gB_out[i] = make_float2(Bc * Gx, Bc * Gy);
+  pconst[i] = make_float4(rho0 * Gx / rho, rho0 * Gy / rho, aii, 0.f);
+  lam_sum_out[i] = lam;
+  lam_grad_out[i] = make_float2(Gx, Gy);
+  nrm_out[i] = make_float2(Nx, Ny);  // Σ_j ∇W_ij; K3 scales it by -(m_i/ρ0)
+}
+
+}  // namespace
+
+int launch_neighbors(asph_sim* sim, float f_ext, float f_near) {
+  const uint32_t n = sim->n;
+  sim->lists_valid = false;
+  if (n == 0) { sim->lists_valid = true; return ASPH_OK; }
+  const uint32_t blocks = (n + kThreads - 1) / kThreads;
+  for (int attempt = 0; attempt < 6; attempt++) {
+    if (sim->nidx.cap == 0) {
+      // first guess: 24 (2h) / 48 (extended) entries per particle
+      size_t per = (f_ext > f_near) ? 48 : 24;
+      CUDA_TRY(sim->nidx.ensure(size_t(sim->cap) * per + 4096));
+      CUDA_TRY(sim->ncoef.ensure(size_t(sim->cap) * 24 + 4096));
+    }
+    const uint32_t list_cap = uint32_t(std::min<size_t>(sim->nidx.cap, 0xFFFFFFF0u));
+    const uint32_t coef_cap = uint32_t(std::min<size_t>(sim->ncoef.cap, 0xFFFFFFF0u));
+    k_neighbors<<<blocks, kThreads, 0, sim->stream>>>(n, sim->xyhm.p, sim->ctl, sim->ctl, sim->cellstart.p, sim->pp, sim->lut.p, f_ext,
+                                                      f_near, list_cap, coef_cap, sim->nidx.p, sim->ncoef.p, sim->slice_base.p,
+                                                      sim->slice_cbase.p, sim->cnt.p, sim->rho.p, sim->gB.p, sim->pconst.p,
+                                                      sim->lam_sum.p, sim->lam_grad.p, sim->nrm.p);
+    LAUNCH_CHECK();
+    TRY(sync_ctl(sim));
+    const StepCtl& c = *sim->ctl_host;
+    if (!(c.error_flags & ERRF_LIST_CAPACITY)) {
+      sim->lists_valid = true;
+      return ASPH_OK;
+    }
+    // pool too small: grow to what this step asked for (plus slack) and redo the pass
+    size_t want_idx = size_t(c.list_used) + size_t(c.list_used) / 4 + 4096;
+    size_t want_coef = size_t(c.coef_used) + size_t(c.coef_used) / 4 + 4096;
+    if (c.list_used < sim->nidx.cap && c.coef_used < sim->ncoef.cap) { want_idx = sim->nidx.cap * 2; want_coef = sim->ncoef.cap * 2; }
+    if (want_idx > 0xFFFFFFF0u) { sim->last_error = "neighbour list pool exceeds 2^32 entries"; return ASPH_ERR_CAPACITY; }
+    CUDA_TRY(sim->nidx.ensure(want_idx));
+    CUDA_TRY(sim->ncoef.ensure(want_coef));
+    // reset the pool counters and the capacity flag, keep the rest of the control block
+    StepCtl patch = c;
+    patch.list_used = 0; patch.coef_used = 0; patch.max_count = 0; patch.error_flags = c.error_flags & ~ERRF_LIST_CAPACITY;
+    CUDA_TRY(cudaMemcpyAsync(sim->ctl, &patch, sizeof(StepCtl), cudaMemcpyHostToDevice, sim->stream));
+    CUDA_TRY(cudaStreamSynchronize(sim->stream));
+  }
+  sim->last_error = "neighbour list pool could not be sized";
+  return ASPH_ERR_CAPACITY;
+}

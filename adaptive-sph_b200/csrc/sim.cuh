@@ -1,55 +1,48 @@
 // sim.cuh — internal declarations of libasph_b200.so (hand-written sm_100a CUDA; no tensor cores: the
 // path has no dense contraction).  Device state layout, device math, launcher prototypes.
 //
-// Data layout in HBM (all SoA, fp32, particles kept SORTED by (size level, cell) every step):
+// Data layout in HBM (all SoA, fp32; particles are physically re-sorted by (size level, grid cell) every step):
 //   persistent  pos float2 | vel float2 | mass f32 | refid u32 (index in the reference's ParticleVec) | level f32
-//   per step    xyhm float4 {x, y, h, m}  (one 16 B gather per neighbour candidate)
-//               neighbour lists in sliced-ELL: slice = 32 consecutive particles = one warp; entry k of lane l at
+//   per step    xyhm float4 {x, y, h, m}   pre-advection snapshot, one 16 B gather per neighbour candidate
+//               neighbour lists in sliced ELL: slice = 32 consecutive particles = one warp; entry k of lane l at
 //               slice_base[s] + 32*k + l  -> every warp load of idx/coef is one fully coalesced 128 B line.
-//               Row k < cnt_near holds the 2h neighbours, cnt_near <= k < cnt_ext the extended-range
+//               Rows k < cnt_near hold the 2h neighbours, cnt_near <= k < cnt_ext the extended-range
 //               (level-set) ones, so NeighborhoodCache::filter_down (neighborhood_search.rs:56) is free.
 //               coef[k] = m_j * dW/dr / r  so that  m_j * gradW_ij = coef * (x_i - x_j)
-//   solver      packP float4 {x, y, p/rho^2, p} | packA float4 {x, y, a^p_x, a^p_y} | jc float4 {rho0*G, s, a_ii}
+//   solver      packP float4 {x, y, p/rho^2, p} | packA float4 {x, y, a^p_x, a^p_y} | pconst float4 {Gx, Gy, a_ii, s}
+//               xv float4 {x, y, vx, vy}
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
 #include "../../include/asph.h"
 
-#define ASPH_MAX_LEVELS 10
+#define ASPH_MAX_LEVELS 12
 #define ASPH_SLACK 1.00390625f  // 1 + 1/256: cell / search-radius safety factor against fp32 binning error
 
-#define CUDA_TRY(x)                                                                              \
-  do {                                                                                           \
-    cudaError_t e__ = (x);                                                                       \
-    if (e__ != cudaSuccess) {                                                                    \
-      sim->last_error = std::string(#x) + ": " + cudaGetErrorString(e__);                        \
-      return ASPH_ERR_CUDA;                                                                      \
-    }                                                                                            \
-  } while (0)
-
 // ------------------------------------------------------------------------------------------------
-// device-visible control block: everything data-dependent that decides control flow lives here so that the
-// step needs ONE host synchronisation (at its end) plus one per solver batch.
+// device-visible control block: everything data-dependent that decides control flow lives here, so the host
+// synchronises only a handful of times per step (after the neighbour build, once per solver batch).
 // ------------------------------------------------------------------------------------------------
 enum {
   ERRF_NONFINITE = 1, ERRF_NEG_AII = 2, ERRF_DENSITY = 4, ERRF_NEIGHBOR_OVERFLOW = 8, ERRF_LIST_CAPACITY = 16,
-  ERRF_PARTICLE_CAPACITY = 32, ERRF_SPLIT_PATTERN = 64, ERRF_LEVEL_WEIGHT = 128
+  ERRF_PARTICLE_CAPACITY = 32, ERRF_SPLIT_PATTERN = 64, ERRF_LEVEL_WEIGHT = 128, ERRF_CELL_BUDGET = 256,
+  ERRF_SPLIT_CHILDREN = 512, ERRF_SOLVER_NONFINITE = 1024, ERRF_PARTNER_VALIDATION = 2048
 };
 
 struct GridLevel {
   float cell, inv_cell, hmax;
   int nx, ny;
-  uint32_t base;   // first cell of this level in the concatenated cell array
-  uint32_t count;  // particles in this level
+  uint32_t base;  // first cell of this level in the concatenated cell array
 };
 
 struct SolverCtl {
-  int k;        // index of the sweep being executed (num_pressure_iters, simulation.rs:1388)
-  int done;     // set by the sweep that satisfies the stop rule of simulation.rs:1453-1477
-  int sweeps;   // sweeps executed
+  int k;       // index of the sweep being executed (num_pressure_iters, simulation.rs:1388)
+  int done;    // set by the sweep that satisfies the stop rule of simulation.rs:1453-1477
+  int sweeps;  // sweeps executed
   unsigned long long normal, singular, negative;
   float err_sum, max_err, avg;
   unsigned int ticket;
@@ -58,24 +51,23 @@ struct SolverCtl {
 struct StepCtl {
   // order-preserving encodings (see enc_f / dec_f) for atomicMin / atomicMax on floats
   unsigned int hmin_enc, hmax_enc, minx_enc, miny_enc, maxx_enc, maxy_enc, cfl_enc;
-  unsigned int lvl_hmax_enc[ASPH_MAX_LEVELS];
-  unsigned int lvl_count[ASPH_MAX_LEVELS];
   int nlevels;
-  float hmin, origin_x, origin_y;
+  float hmin, hmax, origin_x, origin_y;
   GridLevel lv[ASPH_MAX_LEVELS];
   uint32_t total_cells;
   float dt;
   unsigned int error_flags;
-  unsigned long long list_entries;  // total sliced-ELL entries needed this step
-  uint32_t max_count;               // largest neighbour count
+  unsigned int list_used, coef_used;  // sliced-ELL pool entries handed out this step
+  uint32_t max_count;                 // largest neighbour count
   SolverCtl solver;
   // level set
-  uint32_t front_size[2];
-  int level_sweeps;
+  uint32_t front_n[2], cand_n[2];
+  int level_live[2];
+  int level_sweep, level_done;
   // adaptivity
-  uint32_t n_new;                 // particle count after merge / split
+  uint32_t n_new;  // particle count after merge / split
   uint32_t n_shared, n_merged, n_split_parents;
-  uint32_t undecided;
+  uint32_t work_n[2], rounds;
   double mass_before, mass_after;
 };
 
@@ -101,18 +93,20 @@ template <class T> struct DevBuf {
     if (n <= cap) return cudaSuccess;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
-    size_t want = n + n / 8 + 64;
-    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
-    if (e == cudaSuccess) cap = want;
+    cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
     return e;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+struct DistState;  // dist.cu
+
 struct asph_sim {
   int device = 0;
   cudaStream_t stream = nullptr;
-  uint32_t n = 0, cap = 0;
+  uint32_t n = 0;        // particles on this device (owned + ghosts)
+  uint32_t cap = 0;      // particle capacity
   uint32_t cells_budget = 0;
   // persistent, double buffered for the per-step reorder
   DevBuf<float2> pos[2], vel[2];
@@ -120,29 +114,35 @@ struct asph_sim {
   DevBuf<uint32_t> refid[2];
   int cur = 0;
   // per step
-  DevBuf<float4> xyhm, xyv, packP, packA, jc;
-  DevBuf<float> h_unsorted, rho, aii, src, lam_sum, dens_err;
-  DevBuf<float2> lam_grad, sumgrad, paccel;
-  DevBuf<uint32_t> cellkey, cellcount, cellstart, order_tmp, order, scan_tmp;
-  DevBuf<uint32_t> cnt_near, cnt_ext, slice_width, slice_base;
+  DevBuf<float4> xyhm, xv[2], packP[2], packA, pconst;
+  int xv_cur = 0, p_cur = 0;
+  DevBuf<float> h_tmp, rho, lam_sum;
+  DevBuf<float2> nrm, gB, lam_grad;
+  DevBuf<uint32_t> key, cellcount, cellstart, order, scan_sums;
+  DevBuf<uint32_t> cnt, slice_base, slice_cbase;
   DevBuf<uint32_t> nidx;
   DevBuf<float> ncoef;
-  DevBuf<uint8_t> size_class, flag_surface, flag_insufficient;
-  DevBuf<uint32_t> merge_partner, front[2], work_a, work_b, work_c;
-  DevBuf<uint16_t> merge_counter;
-  DevBuf<int> assigned;
-  DevBuf<float> lut;        // 2 * 10001 floats: λ then λ′
-  DevBuf<float> split_pos;  // flattened patterns
+  DevBuf<uint8_t> size_class, flags;  // flags: bit0 surface, bit1 insufficient neighbours
+  DevBuf<uint32_t> merge_partner, front[2], cand, work[2], scratch_u[4];
+  DevBuf<uint32_t> merge_counter;
+  DevBuf<int> stamp;
+  DevBuf<float> scratch_f;
+  DevBuf<float> lut;         // 2 * 10001 floats: λ then λ′
+  DevBuf<float> split_pos;   // flattened patterns
   DevBuf<int> split_off;
-  DevBuf<float> blockstats; // per-block partials of the Jacobi reduction
-  StepCtl* ctl = nullptr;   // device
+  DevBuf<float> blockstats;  // per-block partials of the Jacobi reduction
+  StepCtl* ctl = nullptr;       // device
   StepCtl* ctl_host = nullptr;  // pinned mirror
+  PackedParams* pp_dev = nullptr;
   PackedParams pp;
   int max_children = 0;
   asph_boundary boundary;
   bool lists_valid = false;
-  float lists_factor = 0;
-  bool have_level = false;
+  bool level_valid = false;
+  bool step_fields_valid = false;
+  bool level_cutoff = true;  // stop the level-set propagation once every new value is below -maximum_surface_distance
+  bool share_enabled = false, merge_enabled = false, split_enabled = false;
+  float last_dt = 0;
   // bookkeeping
   double time = 0;
   float time_f = 0;
@@ -151,14 +151,37 @@ struct asph_sim {
   bool counters = false;
   double pc_ms[ASPH_PC_COUNT] = {0};
   uint64_t pc_calls[ASPH_PC_COUNT] = {0};
-  cudaEvent_t ev[16];
+  cudaEvent_t ev_begin[ASPH_PC_COUNT], ev_end[ASPH_PC_COUNT];
   int sm_count = 148;
   std::string last_error;
   uint64_t kernel_launches = 0;
   // multi-GPU
-  int rank = 0, n_ranks = 1;
-  void* comm = nullptr;
+  DistState* dist = nullptr;
+  uint32_t n_owned = 0;  // == n when single GPU
 };
+
+#define CUDA_TRY(x)                                                                              \
+  do {                                                                                           \
+    cudaError_t e__ = (x);                                                                       \
+    if (e__ != cudaSuccess) {                                                                    \
+      sim->last_error = std::string(#x) + ": " + cudaGetErrorString(e__);                        \
+      return ASPH_ERR_CUDA;                                                                      \
+    }                                                                                            \
+  } while (0)
+#define TRY(x)                       \
+  do {                               \
+    int rc__ = (x);                  \
+    if (rc__ != ASPH_OK) return rc__; \
+  } while (0)
+#define LAUNCH_CHECK()                                                       \
+  do {                                                                       \
+    sim->kernel_launches++;                                                  \
+    cudaError_t e__ = cudaGetLastError();                                    \
+    if (e__ != cudaSuccess) {                                                \
+      sim->last_error = std::string("kernel launch: ") + cudaGetErrorString(e__); \
+      return ASPH_ERR_CUDA;                                                  \
+    }                                                                        \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // host-side λ tables (plane_lambda.cpp)
@@ -169,18 +192,28 @@ void asph_host_build_luts(std::vector<float>& lam, std::vector<float>& dlam);
 float asph_host_lut_get(const std::vector<float>& data, float x);
 
 // ------------------------------------------------------------------------------------------------
-// launchers (sim_core.cu / sim_adapt.cu)
+// launchers
 // ------------------------------------------------------------------------------------------------
+// grid.cu
+int ensure_capacity(asph_sim* sim, uint32_t n_particles);
+int sync_ctl(asph_sim* sim);  // copies the control block to the pinned mirror and synchronises the stream
 int launch_sort_and_grid(asph_sim* sim, float f_search);
-int launch_neighbors(asph_sim* sim, float f_ext, float f_near, bool physics);
-int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error);
+int launch_exclusive_scan(asph_sim* sim, const uint32_t* in, uint32_t* out, const uint32_t* n_dev, uint32_t n_add,
+                          uint32_t n_max);  // out[i] = sum(in[0..i)) for i < *n_dev + n_add
+// neighbors.cu
+int launch_neighbors(asph_sim* sim, float f_ext, float f_near);
+// solver.cu
 int launch_viscosity(asph_sim* sim);
 int launch_source(asph_sim* sim, int kind);  // 0 divergence, 1 only density, 2 full
-int launch_final_accel(asph_sim* sim, int mode);  // see sim_core.cu
+int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* iters_out, int* sweeps_out, double* avg_out);
+int launch_final_accel(asph_sim* sim, int mode);  // 1: v += dt a (xv pack); 2: hybrid integrate; 3: IISPH integrate
+// level.cu
 int launch_level_estimation(asph_sim* sim);
 int launch_level_smoothing(asph_sim* sim);
+// adapt.cu
 int launch_adaptivity(asph_sim* sim, float dt);
-int launch_exclusive_scan(asph_sim* sim, uint32_t* data, uint32_t n, DevBuf<uint32_t>& tmp);
+// capi.cu
+int check_error_flags(asph_sim* sim);
 
 // ------------------------------------------------------------------------------------------------
 // device math
@@ -225,11 +258,11 @@ __device__ __forceinline__ float cubic_dw(float q) {
 }
 __device__ __forceinline__ float kernel_norm(float h) { return 10.f / (7.f * ASPH_PI_F * (h * h)); }
 __device__ __forceinline__ float kernel_w(float r, float h) { return kernel_norm(h) * cubic_w(r / (2.f * h)); }
-// dW/dr / r, i.e. gradW = kernel_dcoef * x_ij (zero when q <= 1e-5, sph_kernels.rs:64-66)
-__device__ __forceinline__ float kernel_dcoef(float r, float h) {
+// dW/dr (zero when q <= 1e-5, sph_kernels.rs:64-66); gradW = dwdr * x_ij / r
+__device__ __forceinline__ float kernel_dwdr(float r, float h) {
   float q = r / (2.f * h);
   if (q <= 1.0e-5f) return 0.f;
-  return kernel_norm(h) * cubic_dw(q) / (2.f * h) / r;
+  return kernel_norm(h) * cubic_dw(q) / (2.f * h);
 }
 __device__ __forceinline__ float radius_to_volume(float r) { return ASPH_PI_F * r * r; }
 __device__ __forceinline__ float volume_to_radius(float a) { return sqrtf(a * ASPH_FRAC_1_PI_F); }

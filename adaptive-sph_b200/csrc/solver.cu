@@ -1,0 +1,359 @@
+// solver.cu — the pair-sum passes of the step that run on the stored sliced-ELL lists: non-pressure acceleration
+// (K12), PPE source terms (K13), the relaxed-Jacobi pressure sweeps (K14 + K15) with their device-side loop
+// control, and the integrators (K16).
+//
+// Every pass is one thread per particle; a warp reads row k of its slice's idx/coef columns as one coalesced 128 B
+// line and gathers one float4 per neighbour.  With coef = m_j * dW/dr / r stored once per step,
+//   m_j * gradW_ij = coef * x_ij
+// so a sweep needs no sqrt / division per pair.
+//
+// Reference: simulation.rs:931-1005 (non-pressure accel), :1552-1592 (divergence operator), :1633-1748 (sources),
+// :1751-1808 (pressure accel), :1207-1322 (Jacobi sweep + PressureSolverStatistics), :1378-1516 (loop control),
+// :2389-2446 / :2502-2670 (IISPH / HybridDFSPH step orders); boundary terms boundary_winchenbach2020.rs:164-223.
+#include "sim.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct Lists {
+  const uint32_t* __restrict__ nidx;
+  const float* __restrict__ ncoef;
+  const uint32_t* __restrict__ slice_base;
+  const uint32_t* __restrict__ slice_cbase;
+  const uint32_t* __restrict__ cnt;
+};
+
+__global__ void k_solver_reset(StepCtl* ctl) {
+  SolverCtl s;
+  s.k = 0; s.done = 0; s.sweeps = 0; s.normal = 0; s.singular = 0; s.negative = 0;
+  s.err_sum = 0.f; s.max_err = 0.f; s.avg = 0.f; s.ticket = 0;
+  ctl->solver = s;
+}
+
+// ---------------------------------------------------------------------------------------------- K12
+__global__ void __launch_bounds__(kThreads)
+k_viscosity(uint32_t n, Lists L, const float4* __restrict__ xyhm, const float4* __restrict__ xv_in, const float* __restrict__ rho,
+            const PackedParams P, const StepCtl* __restrict__ ctl, float4* __restrict__ xv_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float dt = ctl->dt;
+  const float4 me = xyhm[i];
+  const float4 mv = xv_in[i];
+  const float rho_i = rho[i];
+  const uint32_t cn = L.cnt[i] & 0xffffu;
+  const uint32_t* col = L.nidx + L.slice_base[i >> 5] + (i & 31);
+  const float* ccol = L.ncoef + L.slice_cbase[i >> 5] + (i & 31);
+  float ax = 0.f, ay = 0.f;
+  if (P.viscosity_type != ASPH_VISC_XSPH) {
+    for (uint32_t k = 0; k < cn; k++) {
+      const uint32_t j = __ldcs(col + 32u * k);
+      const float c = __ldcs(ccol + 32u * k);
+      const float4 o = __ldg(&xyhm[j]);
+      const float4 ov = __ldg(&xv_in[j]);
+      const float dx = me.x - o.x, dy = me.y - o.y;
+      const float est = dx * (mv.z - ov.z) + dy * (mv.w - ov.w);
+      if (!(est < 0.f)) continue;
+      const float hij = (me.z + o.z) * 0.5f;
+      const float d2 = dx * dx + dy * dy;
+      float f;
+      if (P.viscosity_type == ASPH_VISC_APPROX_LAPLACE) {
+        const float rho_ij = (rho_i + __ldg(&rho[j])) * 0.5f;
+        f = P.viscosity * (8.f * est / (rho_ij * (d2 + 0.01f * hij * hij)));  // 2(D+2), D = 2
+      } else {  // WCSPH, speed of sound 88
+        const float visc = 2.f * P.viscosity * hij * 88.f / (rho_i + __ldg(&rho[j]));
+        f = visc * est / (d2 + 0.001f * hij * hij);
+      }
+      ax += f * c * dx; ay += f * c * dy;
+    }
+  }
+  ay += P.gravity;
+  if (P.has_pull) {
+    const float px = P.pull_x - me.x, py = P.pull_y - me.y;
+    const float pn = sqrtf(px * px + py * py);
+    ax += px / pn * 13.f; ay += py / pn * 13.f;
+  }
+  xv_out[i] = make_float4(me.x, me.y, mv.z + dt * ax, mv.w + dt * ay);
+}
+
+// ---------------------------------------------------------------------------------------------- K13
+// kind 0: -div(v)/dt; 1: -(rho0-rho)/(rho dt^2); 2: both.  Also p <- 0 (packP[0]).
+__global__ void __launch_bounds__(kThreads)
+k_source(uint32_t n, Lists L, const float4* __restrict__ xv, const float* __restrict__ rho, float4* __restrict__ pconst,
+         float4* __restrict__ packP0, const StepCtl* __restrict__ ctl, float rho0, int kind) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float dt = ctl->dt;
+  const float4 me = xv[i];
+  float4 pc = pconst[i];
+  const float rho_i = rho[i];
+  float s = 0.f;
+  if (kind != 1) {
+    const uint32_t cn = L.cnt[i] & 0xffffu;
+    const uint32_t* col = L.nidx + L.slice_base[i >> 5] + (i & 31);
+    const float* ccol = L.ncoef + L.slice_cbase[i >> 5] + (i & 31);
+    float sum = 0.f;
+#pragma unroll 4
+    for (uint32_t k = 0; k < cn; k++) {
+      const uint32_t j = __ldcs(col + 32u * k);
+      const float c = __ldcs(ccol + 32u * k);
+      const float4 o = __ldg(&xv[j]);
+      sum += c * ((o.z - me.z) * (me.x - o.x) + (o.w - me.w) * (me.y - o.y));
+    }
+    const float div = sum / rho_i - (me.z * pc.x + me.w * pc.y);
+    s = -div / dt;
+  }
+  if (kind != 0) s += -(rho0 - rho_i) / (rho_i * dt * dt);
+  pc.w = s;
+  pconst[i] = pc;
+  packP0[i] = make_float4(me.x, me.y, 0.f, 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------- K14
+// a^p_i = -Σ coef (P_i + P_j) x_ij - p_i * Bc * G_i,  P = p / rho^2.
+// MODE 0: sweep (skipped once the solver is done); 1: final, v += dt a^p into the xv pack; 2: final + HybridDFSPH
+// integration (simulation.rs:2622-2669); 3: final + IISPH integration (simulation.rs:2433-2444); 4: final only.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+k_accel(uint32_t n, Lists L, const float4* __restrict__ packP, const float2* __restrict__ gB, float4* __restrict__ packA,
+        StepCtl* ctl, float4* __restrict__ xv, float2* __restrict__ pos, float2* __restrict__ vel, float hybrid_factor) {
+  if (MODE == 0 && ctl->solver.done) return;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 me = packP[i];
+  const uint32_t cn = L.cnt[i] & 0xffffu;
+  const uint32_t* col = L.nidx + L.slice_base[i >> 5] + (i & 31);
+  const float* ccol = L.ncoef + L.slice_cbase[i >> 5] + (i & 31);
+  float ax = 0.f, ay = 0.f;
+#pragma unroll 4
+  for (uint32_t k = 0; k < cn; k++) {
+    const uint32_t j = __ldcs(col + 32u * k);
+    const float c = __ldcs(ccol + 32u * k);
+    const float4 o = __ldg(&packP[j]);
+    const float f = c * (me.z + o.z);
+    ax -= f * (me.x - o.x);
+    ay -= f * (me.y - o.y);
+  }
+  const float2 g = gB[i];
+  ax -= me.w * g.x;
+  ay -= me.w * g.y;
+  packA[i] = make_float4(me.x, me.y, ax, ay);
+  if (MODE == 1) {
+    const float dt = ctl->dt;
+    float4 v = xv[i];
+    v.z += dt * ax; v.w += dt * ay;
+    xv[i] = v;
+  } else if (MODE == 2) {
+    const float dt = ctl->dt;
+    const float4 v = xv[i];
+    const float fac = fminf(dt * hybrid_factor, 1.f);
+    const float2 x = make_float2(me.x + (dt * v.z + (dt * dt) * ax), me.y + (dt * v.w + (dt * dt) * ay));
+    const float2 vn = make_float2(v.z + (dt * ax) * fac, v.w + (dt * ay) * fac);
+    pos[i] = x; vel[i] = vn;
+    if (!(isfinite(x.x) && isfinite(x.y) && isfinite(vn.x) && isfinite(vn.y))) atomicOr(&ctl->error_flags, ERRF_NONFINITE);
+  } else if (MODE == 3) {
+    const float dt = ctl->dt;
+    const float4 v = xv[i];
+    const float2 vn = make_float2(v.z + dt * ax, v.w + dt * ay);
+    const float2 x = make_float2(me.x + dt * vn.x, me.y + dt * vn.y);
+    pos[i] = x; vel[i] = vn;
+    if (!(isfinite(x.x) && isfinite(x.y) && isfinite(vn.x) && isfinite(vn.y))) atomicOr(&ctl->error_flags, ERRF_NONFINITE);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- K15
+// (Ap)_i = div(a^p)_i; p' = p + ω (s - Ap) / a_ii, clamped at 0; PressureSolverStatistics reduced per block,
+// then by the last block to finish (fixed order => deterministic), which also evaluates the stop rule.
+__global__ void __launch_bounds__(kThreads)
+k_jacobi(uint32_t n, Lists L, const float4* __restrict__ packA, const float4* __restrict__ packP, float4* __restrict__ packP_next,
+         const float4* __restrict__ pconst, const float* __restrict__ rho, StepCtl* ctl, float* __restrict__ blockstats, float omega,
+         float rho0, float tol, int max_iters, int density_mode) {
+  if (ctl->solver.done) return;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float dt = ctl->dt;
+  uint32_t c_normal = 0, c_sing = 0, c_neg = 0;
+  float e_sum = 0.f, e_max = 0.f;
+  bool bad = false;
+  if (i < n) {
+    const float4 me = packA[i];
+    const float4 pc = pconst[i];
+    const float4 pp = packP[i];
+    float pn = 0.f;
+    const float rho_i = rho[i];
+    if (fabsf(pc.z) < 10e-4f) {
+      c_sing = 1;
+    } else {
+      const uint32_t cn = L.cnt[i] & 0xffffu;
+      const uint32_t* col = L.nidx + L.slice_base[i >> 5] + (i & 31);
+      const float* ccol = L.ncoef + L.slice_cbase[i >> 5] + (i & 31);
+      float sum = 0.f;
+#pragma unroll 4
+      for (uint32_t k = 0; k < cn; k++) {
+        const uint32_t j = __ldcs(col + 32u * k);
+        const float c = __ldcs(ccol + 32u * k);
+        const float4 o = __ldg(&packA[j]);
+        sum += c * ((o.z - me.z) * (me.x - o.x) + (o.w - me.w) * (me.y - o.y));
+      }
+      const float Ap = sum / rho_i - (me.z * pc.x + me.w * pc.y);
+      const float resid = pc.w - Ap;
+      pn = pp.w + omega * resid / pc.z;
+      if (!isfinite(Ap) || !isfinite(pn)) bad = true;
+      const float perr = density_mode ? rho_i * dt * dt * resid : dt * resid;
+      if (pn <= 0.f) { pn = 0.f; c_neg = 1; }
+      else { c_normal = 1; e_sum = perr; e_max = fabsf(perr); }
+    }
+    packP_next[i] = make_float4(me.x, me.y, pn / (rho_i * rho_i), pn);
+  }
+  if (bad) atomicOr(&ctl->error_flags, ERRF_SOLVER_NONFINITE);
+  // block reduction
+  for (int o = 16; o > 0; o >>= 1) {
+    c_normal += __shfl_xor_sync(0xffffffffu, c_normal, o);
+    c_sing += __shfl_xor_sync(0xffffffffu, c_sing, o);
+    c_neg += __shfl_xor_sync(0xffffffffu, c_neg, o);
+    e_sum += __shfl_xor_sync(0xffffffffu, e_sum, o);
+    e_max = fmaxf(e_max, __shfl_xor_sync(0xffffffffu, e_max, o));
+  }
+  __shared__ float sh[5][kThreads];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { sh[0][w] = float(c_normal); sh[1][w] = float(c_sing); sh[2][w] = float(c_neg); sh[3][w] = e_sum; sh[4][w] = e_max; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f, c = 0.f, d = 0.f, e = 0.f;
+    for (int k = 0; k < kThreads / 32; k++) { a += sh[0][k]; b += sh[1][k]; c += sh[2][k]; d += sh[3][k]; e = fmaxf(e, sh[4][k]); }
+    float* out = blockstats + 5 * size_t(blockIdx.x);
+    out[0] = a; out[1] = b; out[2] = c; out[3] = d; out[4] = e;  // counts <= 256 are exact in fp32
+    __threadfence();
+    const unsigned int t = atomicAdd(&ctl->solver.ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // final reduction in a fixed order: thread t takes blocks t, t+256, ...; then a fixed tree
+  unsigned long long tn = 0, ts = 0, tg = 0;
+  float td = 0.f, te = 0.f;
+  for (uint32_t b = threadIdx.x; b < gridDim.x; b += kThreads) {
+    const float* in = blockstats + 5 * size_t(b);
+    tn += (unsigned long long)__ldcg(in + 0); ts += (unsigned long long)__ldcg(in + 1); tg += (unsigned long long)__ldcg(in + 2);
+    td += __ldcg(in + 3); te = fmaxf(te, __ldcg(in + 4));
+  }
+  __shared__ unsigned long long shn[kThreads], shs[kThreads], shg[kThreads];
+  shn[threadIdx.x] = tn; shs[threadIdx.x] = ts; shg[threadIdx.x] = tg; sh[3][threadIdx.x] = td; sh[4][threadIdx.x] = te;
+  __syncthreads();
+  for (int s = kThreads / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      shn[threadIdx.x] += shn[threadIdx.x + s]; shs[threadIdx.x] += shs[threadIdx.x + s]; shg[threadIdx.x] += shg[threadIdx.x + s];
+      sh[3][threadIdx.x] += sh[3][threadIdx.x + s]; sh[4][threadIdx.x] = fmaxf(sh[4][threadIdx.x], sh[4][threadIdx.x + s]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    SolverCtl s = ctl->solver;
+    s.normal = shn[0]; s.singular = shs[0]; s.negative = shg[0]; s.err_sum = sh[3][0]; s.max_err = sh[4][0];
+    s.ticket = 0;
+    s.sweeps += 1;
+    const float avg = s.normal > 0 ? s.err_sum / float(s.normal) : __int_as_float(0x7fc00000);
+    s.avg = avg;
+    // simulation.rs:1453-1477
+    bool stop;
+    if (density_mode) stop = (s.normal == 0) || (fabsf(avg / rho0) < tol && s.k > 1);
+    else stop = (s.normal == 0) || (fabsf(avg) < tol / dt && s.k > 1);
+    if (stop || s.k == max_iters || (ctl->error_flags & ERRF_SOLVER_NONFINITE)) s.done = 1;
+    else s.k += 1;
+    ctl->solver = s;
+  }
+}
+
+Lists lists_of(asph_sim* sim) {
+  Lists L;
+  L.nidx = sim->nidx.p; L.ncoef = sim->ncoef.p; L.slice_base = sim->slice_base.p; L.slice_cbase = sim->slice_cbase.p; L.cnt = sim->cnt.p;
+  return L;
+}
+
+}  // namespace
+
+int launch_viscosity(asph_sim* sim) {
+  const uint32_t n = sim->n;
+  if (n == 0) return ASPH_OK;
+  const uint32_t blocks = (n + kThreads - 1) / kThreads;
+  const int a = sim->xv_cur;
+  k_viscosity<<<blocks, kThreads, 0, sim->stream>>>(n, lists_of(sim), sim->xyhm.p, sim->xv[a].p, sim->rho.p, sim->pp, sim->ctl,
+                                                    sim->xv[1 - a].p);
+  LAUNCH_CHECK();
+  sim->xv_cur = 1 - a;
+  return ASPH_OK;
+}
+
+int launch_source(asph_sim* sim, int kind) {
+  const uint32_t n = sim->n;
+  if (n == 0) return ASPH_OK;
+  const uint32_t blocks = (n + kThreads - 1) / kThreads;
+  k_source<<<blocks, kThreads, 0, sim->stream>>>(n, lists_of(sim), sim->xv[sim->xv_cur].p, sim->rho.p, sim->pconst.p, sim->packP[0].p,
+                                                 sim->ctl, sim->pp.rest_density, kind);
+  LAUNCH_CHECK();
+  sim->p_cur = 0;
+  return ASPH_OK;
+}
+
+// iisph_pressure_iterations (simulation.rs:1378-1516).  Sweeps are enqueued in batches; each kernel returns
+// immediately once the device-side stop rule has fired, and the host looks at the control block once per batch.
+int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* iters_out, int* sweeps_out, double* avg_out) {
+  const uint32_t n = sim->n;
+  *iters_out = 0; *sweeps_out = 0; *avg_out = 0;
+  if (n == 0) return ASPH_OK;
+  const uint32_t blocks = (n + kThreads - 1) / kThreads;
+  CUDA_TRY(sim->blockstats.ensure(size_t(blocks) * 5 + 8));
+  cudaStream_t st = sim->stream;
+  k_solver_reset<<<1, 1, 0, st>>>(sim->ctl);
+  LAUNCH_CHECK();
+  const Lists L = lists_of(sim);
+  int launched = 0;
+  int batch = 4;
+  const int max_sweeps = sim->pp.max_iters + 1;
+  for (;;) {
+    for (int b = 0; b < batch && launched < max_sweeps; b++, launched++) {
+      const int in = launched & 1;
+      k_accel<0><<<blocks, kThreads, 0, st>>>(n, L, sim->packP[in].p, sim->gB.p, sim->packA.p, sim->ctl, nullptr, nullptr, nullptr, 0.f);
+      LAUNCH_CHECK();
+      k_jacobi<<<blocks, kThreads, 0, st>>>(n, L, sim->packA.p, sim->packP[in].p, sim->packP[1 - in].p, sim->pconst.p, sim->rho.p, sim->ctl,
+                                            sim->blockstats.p, sim->pp.jacobi_omega, sim->pp.rest_density, max_avg_error,
+                                            sim->pp.max_iters, density_mode ? 1 : 0);
+      LAUNCH_CHECK();
+    }
+    TRY(sync_ctl(sim));
+    const SolverCtl& s = sim->ctl_host->solver;
+    if (sim->ctl_host->error_flags & ERRF_SOLVER_NONFINITE) {
+      sim->last_error = "'!a_p.is_finite()' failed. Pressure values probably have exploded!";
+      return ASPH_ERR_NONFINITE;
+    }
+    if (s.done || launched >= max_sweeps) break;
+    batch = std::min(batch * 2, 32);
+  }
+  const SolverCtl& s = sim->ctl_host->solver;
+  sim->p_cur = s.sweeps & 1;
+  *iters_out = s.k;
+  *sweeps_out = s.sweeps;
+  *avg_out = double(s.avg);
+  return ASPH_OK;
+}
+
+int launch_final_accel(asph_sim* sim, int mode) {
+  const uint32_t n = sim->n;
+  if (n == 0) return ASPH_OK;
+  const uint32_t blocks = (n + kThreads - 1) / kThreads;
+  const Lists L = lists_of(sim);
+  cudaStream_t st = sim->stream;
+  const float4* P = sim->packP[sim->p_cur].p;
+  float4* xv = sim->xv[sim->xv_cur].p;
+  float2* pos = sim->pos[sim->cur].p;
+  float2* vel = sim->vel[sim->cur].p;
+  switch (mode) {
+    case 1: k_accel<1><<<blocks, kThreads, 0, st>>>(n, L, P, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f); break;
+    case 2: k_accel<2><<<blocks, kThreads, 0, st>>>(n, L, P, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, sim->pp.hybrid_factor); break;
+    case 3: k_accel<3><<<blocks, kThreads, 0, st>>>(n, L, P, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f); break;
+    default: k_accel<4><<<blocks, kThreads, 0, st>>>(n, L, P, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f); break;
+  }
+  LAUNCH_CHECK();
+  return ASPH_OK;
+}

@@ -216,6 +216,8 @@ int asph_get_step_info(const asph_sim* sim, asph_step_info* out);
 int asph_get_counters(const asph_sim* sim, double ms_sum[ASPH_PC_COUNT], uint64_t calls[ASPH_PC_COUNT]);
 const char* asph_last_error(const asph_sim* sim);
 const char* asph_backend_name(void);               /* "cuda-sm100a" | "oracle-f32" | "oracle-f64" */
+/* number of GPU kernels this handle has launched so far (0 on the CPU oracle); bench.py reports it */
+uint64_t asph_kernel_launches(const asph_sim* sim);
 
 /* ------------------------------------------------------------------ pure helpers (host side, no GPU needed)
  * sph_kernels.rs:49-71 (cubic spline, h = smoothing length, support 2h) and

@@ -212,6 +212,7 @@ int asph_get_counters(const asph_sim* sim, double ms[ASPH_PC_COUNT], uint64_t ca
   return ASPH_OK;
 }
 const char* asph_last_error(const asph_sim* sim) { return sim->s.last_error.c_str(); }
+uint64_t asph_kernel_launches(const asph_sim*) { return 0; }
 
 float asph_kernel_w(float r, float h) { return float(kernel_w<FT>(FT(r), FT(h))); }
 void asph_kernel_grad(float dx, float dy, float h, float* gx, float* gy) {
