@@ -380,7 +380,7 @@ void asph_destroy(asph_sim* sim) {
   sim->order.release(); sim->scan_sums.release(); sim->cnt.release(); sim->slice_base.release(); sim->slice_cbase.release();
   sim->nidx.release(); sim->ncoef.release(); sim->size_class.release(); sim->flags.release(); sim->merge_partner.release();
   sim->cand.release(); for (int k = 0; k < 4; k++) sim->scratch_u[k].release();
-  sim->merge_counter.release(); sim->stamp.release(); sim->scratch_f.release(); sim->lut.release(); sim->split_pos.release();
+  sim->merge_counter.release(); sim->stamp.release(); sim->stampkey.release(); sim->scratch_f.release(); sim->lut.release(); sim->split_pos.release();
   sim->split_off.release(); sim->blockstats.release();
   if (sim->ctl) cudaFree(sim->ctl);
   if (sim->ctl_host) cudaFreeHost(sim->ctl_host);
@@ -531,6 +531,23 @@ static std::vector<float>& host_lut(int which) {
 }
 float asph_lambda_lut(float d) { return asph_host_lut_get(host_lut(0), d); }
 float asph_dlambda_lut(float d) { return asph_host_lut_get(host_lut(1), d); }
+
+// ---- diagnostics used by the parity tests: drive single_step_adaptivity from a prescribed level field / step parity
+int asph_set_level(asph_sim* sim, const float* level_ref_order, uint64_t n) {
+  if (!sim || !level_ref_order || n != sim->n || sim->dist) return ASPH_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(sim->device));
+  std::vector<uint32_t> refid(n);
+  std::vector<float> lv(n);
+  if (n) {
+    CUDA_TRY(cudaMemcpy(refid.data(), sim->refid[sim->cur].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < n; i++) lv[i] = level_ref_order[refid[i]];
+    CUDA_TRY(cudaMemcpy(sim->level[sim->cur].p, lv.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  sim->level_valid = true;
+  return ASPH_OK;
+}
+void asph_set_step_number(asph_sim* sim, uint64_t k) { if (sim) sim->step_number = k; }
+uint64_t asph_adapt_rounds(const asph_sim* sim) { return sim ? sim->adapt_rounds : 0; }
 
 // kernels launched by this handle so far (bench.py reports it as gpu_launches)
 uint64_t asph_kernel_launches(const asph_sim* sim) { return sim ? sim->kernel_launches : 0; }

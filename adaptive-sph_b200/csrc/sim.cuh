@@ -67,7 +67,7 @@ struct StepCtl {
   // adaptivity
   uint32_t n_new;  // particle count after merge / split
   uint32_t n_shared, n_merged, n_split_parents;
-  uint32_t work_n[2], rounds;
+  uint32_t work_n[2], rounds, n_claims;
   double mass_before, mass_after;
 };
 
@@ -126,6 +126,8 @@ struct asph_sim {
   DevBuf<uint32_t> merge_partner, front[2], cand, work[2], scratch_u[4];
   DevBuf<uint32_t> merge_counter;
   DevBuf<int> stamp;
+  DevBuf<unsigned long long> stampkey;  // partner search: round:~refid stamps
+  uint64_t adapt_rounds = 0;
   DevBuf<float> scratch_f;
   DevBuf<float> lut;         // 2 * 10001 floats: λ then λ′
   DevBuf<float> split_pos;   // flattened patterns

@@ -175,5 +175,88 @@ def test_full_size_properties(asph, cuda_lib, default_params):
     assert np.array_equal(g.get_field("mass"), mass)
     rho = g.get_field("density")
     interior = cnt == cnt.max()
-    assert abs(float(rho[interior].mean()) - 1.0) < 0.05
+    # lattice at rest: density = volume_fill_ratio * rho0 up to the kernel's lattice quadrature error
+    assert abs(float(rho[interior].mean()) - 0.93) < 0.02
     g.close()
+
+
+# ------------------------------------------------------------------------------------------------ resampling
+def _adaptive_case(asph, default_params, seed, n_side=48):
+    """A jittered lattice with masses spread over all five size classes of a prescribed level field."""
+    rng = np.random.default_rng(seed)
+    sp = np.float32(0.01)
+    blk = dict(pos=(np.float32(-0.4), np.float32(-0.4)), size=(np.float32(n_side * 0.01 + 0.001), np.float32(n_side * 0.01 + 0.001)),
+               spacing=sp, volume_fill_ratio=np.float32(0.93), velocity=(np.float32(0), np.float32(0)))
+    pos, vel, mass = asph.add_fluid_block(blk)
+    pos = (pos + rng.uniform(-0.25, 0.25, pos.shape).astype(np.float32) * sp).astype(np.float32)
+    vel = (rng.standard_normal(pos.shape) * 0.1).astype(np.float32)
+    mass = (mass * rng.uniform(0.3, 2.6, mass.shape)).astype(np.float32)
+    level = (-(0.08 - pos[:, 1]) * 0.5).astype(np.float32)          # "depth" below y = 0.08, always <= 0 here
+    level = np.minimum(level, np.float32(0.0))
+    r0 = float(np.sqrt(0.93e-4 / np.pi))
+    params = default_params.replace(particle_radius_fine=r0, particle_radius_base=2.0 * r0, maximum_surface_distance=0.2)
+    return pos, vel, mass, level, params
+
+
+def _hooks(g, o):
+    import ctypes as C
+    fp = C.POINTER(C.c_float)
+    g.lib.asph_set_level.argtypes = [C.c_void_p, fp, C.c_uint64]; g.lib.asph_set_level.restype = C.c_int
+    g.lib.asph_set_step_number.argtypes = [C.c_void_p, C.c_uint64]; g.lib.asph_set_step_number.restype = None
+    o.lib.oracle_set_level.argtypes = [C.c_void_p, fp, C.c_uint64]; o.lib.oracle_set_level.restype = C.c_int
+    o.lib.oracle_set_step_number.argtypes = [C.c_void_p, C.c_uint64]; o.lib.oracle_set_step_number.restype = None
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+@pytest.mark.parametrize("phase", ["share", "merge", "split", "share+merge", "share+split"])
+def test_resampling_phase_parity(asph, cuda_lib, oracle32, default_params, split_patterns, phase, seed):
+    """single_step_adaptivity on identical inputs (state, 2h neighbour lists, level field): the same donors pick the
+    same receivers, the same particles are deleted / split, and the resulting particle set is BIT-identical, in
+    the reference's particle order (swap-with-last deletion, append-at-end children)."""
+    import ctypes as C
+    pos, vel, mass, level, params = _adaptive_case(asph, default_params, seed)
+    params = params.replace(sharing="share" in phase, merging="merge" in phase, splitting="split" in phase)
+    step_number = 2 if "merge" in phase else 3
+    b = asph.scene_boundary(_scene(asph, "default-scene.yaml"), "AnalyticOverestimate")
+    g, o = _pair(asph, cuda_lib, oracle32, params, pos, vel, mass, b, split_patterns)
+    _hooks(g, o)
+    g.build_neighbors(np.float32(2.0)); o.build_neighbors(np.float32(2.0))
+    lp = level.ctypes.data_as(C.POINTER(C.c_float))
+    assert g.lib.asph_set_level(g._h, lp, len(level)) == 0
+    assert o.lib.oracle_set_level(o._h, lp, len(level)) == 0
+    g.lib.asph_set_step_number(g._h, step_number); o.lib.oracle_set_step_number(o._h, step_number)
+    dt = 0.002
+    g.single_step_adaptivity(dt=dt); o.single_step_adaptivity(dt=dt)
+    gi, oi = g.step_info(), o.step_info()
+    assert (gi["n_shared"], gi["n_merged"], gi["n_split_parents"]) == (oi["n_shared"], oi["n_merged"], oi["n_split_parents"]), (gi, oi)
+    if "share" in phase:
+        assert oi["n_shared"] > 0
+    if "merge" in phase:
+        assert oi["n_merged"] > 0
+    if "split" in phase:
+        assert oi["n_split_parents"] > 0
+    assert g.num_fluid_particles() == o.num_fluid_particles()
+    for f in ("mass", "position", "velocity"):
+        assert np.array_equal(g.get_field(f), o.get_field(f)), f
+    if phase == "share":
+        assert np.array_equal(g.get_field("merge_partner"), o.get_field("merge_partner"))
+        assert np.array_equal(g.get_field("merge_counter"), o.get_field("merge_counter"))
+        assert np.array_equal(g.get_field("particle_size_class"), o.get_field("particle_size_class"))
+    g.close(); o.close()
+
+
+def test_trajectory_c1_resampling(asph, cuda_lib, oracle32, default_params, split_patterns):
+    """C1 with level set + share / merge / split on: particle counts per step and final positions vs the oracle."""
+    sc = _scene(asph, "default-scene.yaml")
+    g = asph.init_fluid_sim(default_params, sc, split_patterns, lib=cuda_lib)
+    o = asph.init_fluid_sim(default_params, sc, split_patterns, lib=oracle32)
+    counts = []
+    for k in range(40):
+        g.single_step(); o.single_step()
+        counts.append((g.num_fluid_particles(), o.num_fluid_particles()))
+    assert all(a == b for a, b in counts), counts
+    err = np.abs(g.get_field("position") - o.get_field("position")).max() / 2.0
+    print(f"C1 40 steps with resampling: N = {counts[-1][0]}, |gpu - oracle32| / L = {err:.3e}")
+    assert err <= 1e-5
+    assert abs(float(g.get_field("mass").sum()) - float(o.get_field("mass").sum())) < 1e-5
+    g.close(); o.close()
