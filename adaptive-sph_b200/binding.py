@@ -94,6 +94,10 @@ def _declare(lib):
     lib.asph_get_counters.restype = C.c_int
     lib.asph_last_error.argtypes = [_P]
     lib.asph_last_error.restype = C.c_char_p
+    lib.asph_set_kernel_timing.argtypes = [_P, C.c_int]
+    lib.asph_set_kernel_timing.restype = C.c_int
+    lib.asph_get_kernel_timing.argtypes = [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    lib.asph_get_kernel_timing.restype = C.c_int
     lib.asph_kernel_launches.argtypes = [_P]
     lib.asph_kernel_launches.restype = C.c_uint64
     lib.asph_backend_name.argtypes = []
@@ -273,6 +277,16 @@ class FluidSimulation:
         out = np.empty(n, dtype=np.uint32)
         self._check(self.lib.asph_get_global_index(self._h, out.ctypes.data_as(C.POINTER(C.c_uint32)), n))
         return out
+
+    def set_kernel_timing(self, sample_every):
+        self._check(self.lib.asph_set_kernel_timing(self._h, int(sample_every)))
+
+    def kernel_timing(self):
+        ms = (C.c_double * 4)()
+        cnt = (C.c_uint64 * 4)()
+        self._check(self.lib.asph_get_kernel_timing(self._h, ms, cnt))
+        names = ["accel_sweep", "jacobi_sweep", "neighbors", "sort_grid"]
+        return {names[k]: (ms[k], cnt[k]) for k in range(4)}
 
     def kernel_launches(self):
         return int(self.lib.asph_kernel_launches(self._h))

@@ -1,0 +1,96 @@
+"""Headless `run <config> <scene>` — the reference's desktop command line without the window.
+
+Mirrors the clap definition of platform/desktop/main_loop.rs:25-103 for the `run` sub-command:
+  run SIMULATION_CONFIG SCENE_CONFIG [-s/--max-seconds S] [-c/--overwrite-config-file F] [-p/--statistics-enabled]
+                                     [-w/--statistics-path F]
+and its flow (main_loop.rs:105-189, 209-358): read YAML -> optional key-wise overwrite -> init_simulation_params ->
+load split patterns -> init_fluid_sim -> loop { single_step } until the simulated time reaches --max-seconds.
+`image` (Cairo/ffmpeg export) and `generate-split-patterns` (offline optimiser) are out of scope.
+Added: --max-steps, --backend {cuda,oracle} (oracle = the CPU restatement, for comparison only), --dump state.npz.
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+from .binding import StatisticsRecorder, init_fluid_sim, load_library
+from .params import SimulationParams
+from .scene import SceneConfig, init_simulation_params
+from .split_patterns import load_split_patterns_from_file
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def build_parser():
+    ap = argparse.ArgumentParser(prog="asph_b200", description="Adaptive SPH step loop on B200 (headless)")
+    sub = ap.add_subparsers(dest="command", required=True)
+    run = sub.add_parser("run", help="Run a simulation")
+    run.add_argument("simulation_config", metavar="SIMULATION_CONFIG")
+    run.add_argument("scene_config", metavar="SCENE_CONFIG")
+    run.add_argument("-s", "--max-seconds", type=float, default=None, help="Stops the simulation after n simulated seconds")
+    run.add_argument("-c", "--overwrite-config-file", default=None)
+    run.add_argument("-p", "--statistics-enabled", action="store_true")
+    run.add_argument("-w", "--statistics-path", default=None)
+    run.add_argument("--max-steps", type=int, default=None)
+    run.add_argument("--backend", choices=["cuda", "oracle"], default="cuda")
+    run.add_argument("--split-patterns", default=None, help="default: ./split-patterns.yaml if present, else the shipped file")
+    run.add_argument("--dump", default=None, help="write the final state (position, velocity, mass) to this .npz")
+    run.add_argument("-q", "--quiet", action="store_true")
+    for name in ("image", "generate-split-patterns"):
+        sub.add_parser(name, help="not available in the headless B200 build")
+    return ap
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    if args.command != "run":
+        print(f"`{args.command}` is out of scope of this build (rendering / offline pattern optimiser)", file=sys.stderr)
+        return 2
+    if args.max_seconds is None and args.max_steps is None:
+        print("headless run needs --max-seconds or --max-steps", file=sys.stderr)
+        return 2
+    params = SimulationParams.from_yaml(args.simulation_config, overwrite_path=args.overwrite_config_file)
+    scene = SceneConfig.from_yaml(args.scene_config)
+    params = init_simulation_params(params, scene)
+    sp_path = args.split_patterns or ("./split-patterns.yaml" if os.path.exists("./split-patterns.yaml") else None)  # main_loop.rs:225
+    split = load_split_patterns_from_file(sp_path)
+    lib = load_library() if args.backend == "cuda" else load_library(os.path.join(ROOT, "oracle", "liboracle_f32.so"))
+    stats_on = args.statistics_enabled or args.statistics_path is not None
+    sim = init_fluid_sim(params, scene, split, counters_enabled=stats_on, lib=lib)
+    rec = StatisticsRecorder()
+    step = 0
+    t0 = time.perf_counter()
+    while True:
+        if args.max_seconds is not None and sim.time >= args.max_seconds:
+            break
+        if args.max_steps is not None and step >= args.max_steps:
+            break
+        ts = time.perf_counter()
+        dt = sim.single_step(params)
+        info = sim.step_info()
+        rec.record_step(info)
+        step += 1
+        if not args.quiet:
+            print(f"step {step}: t={sim.time:.5f} dt={dt:.3e} n={info['n_particles_end']} div-iters={info['div_iterations']} "
+                  f"density-iters={info['density_iterations']} shared={info['n_shared']} merged={info['n_merged']} "
+                  f"split={info['n_split_parents']}  {1e3 * (time.perf_counter() - ts):.2f}ms")
+    wall = time.perf_counter() - t0
+    print(f"{step} steps, simulated {sim.time:.4f} s, {sim.num_fluid_particles()} particles, wall {wall:.2f} s, backend {sim.backend()}")
+    if stats_on:
+        text = rec.write_statistics(sim)
+        if args.statistics_path:
+            with open(args.statistics_path, "w") as f:
+                f.write(text)
+        else:
+            print(text)
+    if args.dump:
+        np.savez_compressed(args.dump, position=sim.get_field("position"), velocity=sim.get_field("velocity"),
+                            mass=sim.get_field("mass"))
+    sim.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -158,6 +158,14 @@ int field_elem_bytes(int field, int* comps) {
 
 }  // namespace
 
+cudaEvent_t kt_event(asph_sim* sim) {
+  if (!sim->kt_pool.empty()) { cudaEvent_t e = sim->kt_pool.back(); sim->kt_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+void kt_release(asph_sim* sim, cudaEvent_t e) { sim->kt_pool.push_back(e); }
+
 int check_error_flags(asph_sim* sim) {
   const unsigned int f = sim->ctl_host->error_flags;
   if (!f) return ASPH_OK;
@@ -195,8 +203,21 @@ static int step_physics(asph_sim* sim, const asph_params* params, float* dt_out)
     if (rc != ASPH_OK) return rc;
   } else {
     pc_begin(sim, ASPH_PC_NEIGHBORHOOD);
+    cudaEvent_t kt0 = nullptr, kt1 = nullptr, kt2 = nullptr;
+    if (sim->kt_every > 0) { kt0 = kt_event(sim); kt1 = kt_event(sim); kt2 = kt_event(sim); cudaEventRecord(kt0, sim->stream); }
     TRY(launch_sort_and_grid(sim, std::max(f_ext, P.f_near)));
+    if (kt1) cudaEventRecord(kt1, sim->stream);
     TRY(launch_neighbors(sim, f_ext, P.f_near));
+    if (kt2) {
+      cudaEventRecord(kt2, sim->stream);
+      cudaEventSynchronize(kt2);
+      float a = 0.f, b = 0.f;
+      if (cudaEventElapsedTime(&a, kt0, kt1) == cudaSuccess && cudaEventElapsedTime(&b, kt1, kt2) == cudaSuccess) {
+        sim->kt_ms[ASPH_KT_SORT_GRID] += a; sim->kt_samples[ASPH_KT_SORT_GRID]++;
+        sim->kt_ms[ASPH_KT_NEIGHBORS] += b; sim->kt_samples[ASPH_KT_NEIGHBORS]++;
+      }
+      kt_release(sim, kt0); kt_release(sim, kt1); kt_release(sim, kt2);
+    }
     pc_end(sim, ASPH_PC_NEIGHBORHOOD);
     if (sim->n == 0) {
       sim->info.dt = P.max_dt;
@@ -384,6 +405,7 @@ void asph_destroy(asph_sim* sim) {
   sim->split_off.release(); sim->blockstats.release();
   if (sim->ctl) cudaFree(sim->ctl);
   if (sim->ctl_host) cudaFreeHost(sim->ctl_host);
+  for (cudaEvent_t e : sim->kt_pool) cudaEventDestroy(e);
   if (sim->stream) cudaStreamDestroy(sim->stream);
   cudaGetLastError();
   delete sim;
@@ -548,6 +570,18 @@ int asph_set_level(asph_sim* sim, const float* level_ref_order, uint64_t n) {
 }
 void asph_set_step_number(asph_sim* sim, uint64_t k) { if (sim) sim->step_number = k; }
 uint64_t asph_adapt_rounds(const asph_sim* sim) { return sim ? sim->adapt_rounds : 0; }
+
+int asph_set_kernel_timing(asph_sim* sim, int sample_every) {
+  if (!sim) return ASPH_ERR_INVALID;
+  sim->kt_every = sample_every > 0 ? sample_every : 0;
+  for (int k = 0; k < ASPH_KT_COUNT; k++) { sim->kt_ms[k] = 0; sim->kt_samples[k] = 0; }
+  return ASPH_OK;
+}
+int asph_get_kernel_timing(asph_sim* sim, double ms_sum[ASPH_KT_COUNT], uint64_t samples[ASPH_KT_COUNT]) {
+  if (!sim) return ASPH_ERR_INVALID;
+  for (int k = 0; k < ASPH_KT_COUNT; k++) { ms_sum[k] = sim->kt_ms[k]; samples[k] = sim->kt_samples[k]; }
+  return ASPH_OK;
+}
 
 // kernels launched by this handle so far (bench.py reports it as gpu_launches)
 uint64_t asph_kernel_launches(const asph_sim* sim) { return sim ? sim->kernel_launches : 0; }

@@ -157,6 +157,11 @@ struct asph_sim {
   int sm_count = 148;
   std::string last_error;
   uint64_t kernel_launches = 0;
+  // kernel timing (asph_set_kernel_timing)
+  int kt_every = 0;
+  double kt_ms[ASPH_KT_COUNT] = {0};
+  uint64_t kt_samples[ASPH_KT_COUNT] = {0};
+  std::vector<cudaEvent_t> kt_pool;
   // multi-GPU
   DistState* dist = nullptr;
   uint32_t n_owned = 0;  // == n when single GPU
@@ -216,6 +221,8 @@ int launch_level_smoothing(asph_sim* sim);
 int launch_adaptivity(asph_sim* sim, float dt);
 // capi.cu
 int check_error_flags(asph_sim* sim);
+cudaEvent_t kt_event(asph_sim* sim);           // event from the handle's pool
+void kt_release(asph_sim* sim, cudaEvent_t e);
 
 // ------------------------------------------------------------------------------------------------
 // device math

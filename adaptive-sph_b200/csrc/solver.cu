@@ -311,18 +311,34 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
   int launched = 0;
   int batch = 4;
   const int max_sweeps = sim->pp.max_iters + 1;
+  struct Timed { int sweep; cudaEvent_t e0, e1, e2; };
+  std::vector<Timed> timed;
   for (;;) {
     for (int b = 0; b < batch && launched < max_sweeps; b++, launched++) {
       const int in = launched & 1;
+      const bool time_it = sim->kt_every > 0 && (launched % sim->kt_every) == 0;
+      Timed tm{launched, nullptr, nullptr, nullptr};
+      if (time_it) { tm.e0 = kt_event(sim); tm.e1 = kt_event(sim); tm.e2 = kt_event(sim); cudaEventRecord(tm.e0, st); }
       k_accel<0><<<blocks, kThreads, 0, st>>>(n, L, sim->packP[in].p, sim->gB.p, sim->packA.p, sim->ctl, nullptr, nullptr, nullptr, 0.f);
       LAUNCH_CHECK();
+      if (time_it) cudaEventRecord(tm.e1, st);
       k_jacobi<<<blocks, kThreads, 0, st>>>(n, L, sim->packA.p, sim->packP[in].p, sim->packP[1 - in].p, sim->pconst.p, sim->rho.p, sim->ctl,
                                             sim->blockstats.p, sim->pp.jacobi_omega, sim->pp.rest_density, max_avg_error,
                                             sim->pp.max_iters, density_mode ? 1 : 0);
       LAUNCH_CHECK();
+      if (time_it) { cudaEventRecord(tm.e2, st); timed.push_back(tm); }
     }
     TRY(sync_ctl(sim));
     const SolverCtl& s = sim->ctl_host->solver;
+    for (const Timed& tm : timed) {
+      float a = 0.f, b2 = 0.f;
+      if (tm.sweep < s.sweeps && cudaEventElapsedTime(&a, tm.e0, tm.e1) == cudaSuccess && cudaEventElapsedTime(&b2, tm.e1, tm.e2) == cudaSuccess) {
+        sim->kt_ms[ASPH_KT_ACCEL_SWEEP] += a; sim->kt_samples[ASPH_KT_ACCEL_SWEEP]++;
+        sim->kt_ms[ASPH_KT_JACOBI_SWEEP] += b2; sim->kt_samples[ASPH_KT_JACOBI_SWEEP]++;
+      }
+      kt_release(sim, tm.e0); kt_release(sim, tm.e1); kt_release(sim, tm.e2);
+    }
+    timed.clear();
     if (sim->ctl_host->error_flags & ERRF_SOLVER_NONFINITE) {
       sim->last_error = "'!a_p.is_finite()' failed. Pressure values probably have exploded!";
       return ASPH_ERR_NONFINITE;

@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of the SPH step loop (BASELINE.json metric) on N B200s, plus the CPU arm.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (CUDA library through the C ABI)
+  python bench.py --impl reference [...]                       the reference arm: the CPU restatement (oracle/,
+                                                               kind "port" — the Rust reference cannot be built
+                                                               in this image) on all host cores
+
+Workload at N = 1: BASELINE.json configs[1] — 2-D dam break, uniform h, 999 292 particles, HybridDFSPH
+(`default-scene-web.yaml` geometry at spacing 1.122e-3, default-config with the reference's "Uniform SPH" overrides
+of media/motivation-video.yaml:42-57).  At N > 1 the tank and the block are widened N-fold (weak scaling: 999 292
+particles per GPU) and split into N vertical slabs.
+A "step" is one FluidSimulation::single_step over the whole particle set.  value = Σ_steps N_step / device time.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "particle-steps/sec on 2D dam-break at 1/2/4/8 B200; HBM GB/s vs roofline"
+UNIT = "particle-steps/s"
+SPACING_C2 = 1.122e-3
+SPACING_REF_SAMPLE = 2.244e-3  # same geometry, 1/4 of the particles: the bounded CPU sample
+
+
+def uniform_params(A):
+    p = A.SimulationParams.from_yaml(os.path.join(ROOT, "configs", "default-config.yaml"))
+    return p.replace(merging=False, sharing=False, splitting=False, level_estimation_method="None")
+
+
+def dam_break(A, spacing, n_gpus=1):
+    w = 2.0 * n_gpus
+    return A.SceneConfig.dam_break(spacing, pos=(-w / 2 + 0.05, -0.9), size=(0.7 * n_gpus, 1.8), width=w, height=2.0)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def pinned(shape, dtype=np.float32):
+    """numpy view of page-locked host memory (cudaHostAlloc through torch)."""
+    import torch
+    t = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+    return t.numpy(), t
+
+
+def run_ours(args):
+    import asph_b200 as A
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        return run_ours_distributed(args, A, rank, world)
+    lib = A.load_library()
+    params = uniform_params(A)
+    scene = dam_break(A, SPACING_C2)
+    pos, vel, mass = A.scene_particles(scene)
+    boundary = A.scene_boundary(scene, "AnalyticOverestimate")
+    n = len(mass)
+    sim = A.FluidSimulation(params, pos, vel, mass, boundary, counters_enabled=True, lib=lib)
+    assert sim.backend() == "cuda-sm100a"
+    K, W = args.steps, args.warmup
+
+    # ---- device-resident arm: W warm-up steps, K timed steps; time = CUDA-event time of the step counter -------
+    for _ in range(W):
+        sim.single_step()
+    warm_state = (sim.get_field("position"), sim.get_field("velocity"), sim.get_field("mass"))
+    sim.set_state(*warm_state)   # same state again, so the e2e arm and the CPU baseline can start from it too
+    sim.set_kernel_timing(4)
+    c0 = sim.counters()["simulation-step"][0]
+    l0 = sim.kernel_launches()
+    clocks = ClockSampler()
+    clocks.start()
+    t0 = time.perf_counter()
+    particle_steps, sweeps_div, sweeps_den, per_step = 0, 0, 0, []
+    for k in range(K):
+        sim.single_step()
+        info = sim.step_info()
+        particle_steps += info["n_particles_begin"]
+        sweeps_div += info["div_sweeps"]; sweeps_den += info["density_sweeps"]
+        per_step.append((info["div_sweeps"], info["density_sweeps"], info["dt"]))
+    wall = time.perf_counter() - t0
+    clk = clocks.stop()
+    dev_ms = sim.counters()["simulation-step"][0] - c0
+    launches = sim.kernel_launches() - l0
+    kt = sim.kernel_timing()
+    sim.set_kernel_timing(0)
+    value = particle_steps / (dev_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (the Jacobi update pass, K15) -------------------------------------------
+    peak, peak_src = peaks()
+    roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+            "kernel": "k_jacobi (K15: x,m,rho,a^p,p,s,a_ii -> p'; 40 B/particle algorithmic)", "peak_source": peak_src}
+    extra = {}
+    if kt["jacobi_sweep"][1] > 0:
+        ms_j = kt["jacobi_sweep"][0] / kt["jacobi_sweep"][1]
+        ms_a = kt["accel_sweep"][0] / kt["accel_sweep"][1]
+        roof["achieved"] = 40.0 * n / (ms_j * 1e-3) / 1e9
+        roof["frac"] = roof["achieved"] / peak
+        roof["avg_launch_ms"] = ms_j
+        extra["roofline_accel"] = {"kernel": "k_accel<0> (K14: x,m,rho,p -> a^p; 28 B/particle algorithmic)",
+                                   "achieved": 28.0 * n / (ms_a * 1e-3) / 1e9, "avg_launch_ms": ms_a,
+                                   "frac": 28.0 * n / (ms_a * 1e-3) / 1e9 / peak}
+    if kt["neighbors"][1] > 0:
+        extra["neighbors_ms"] = kt["neighbors"][0] / kt["neighbors"][1]
+        extra["sort_grid_ms"] = kt["sort_grid"][0] / kt["sort_grid"][1]
+    # whole step against SURVEY.md §8d: B = 260 + 68 (S_div + S_den) bytes per particle-step
+    b_step = 260.0 + 68.0 * (sweeps_div + sweeps_den) / max(K, 1)
+    extra["step_roofline"] = {"bytes_per_particle_step": b_step, "achieved": b_step * value / 1e9,
+                              "frac": b_step * value / 1e9 / peak}
+
+    # ---- e2e arm: host buffers in, host buffers out, every step (same K steps from the same warm state) ---------
+    hp, _tp = pinned((n, 2)); hv, _tv = pinned((n, 2)); hm, _tm = pinned((n,))
+    op, _to = pinned((n, 2)); ov, _tov = pinned((n, 2))
+    hp[:] = warm_state[0]; hv[:] = warm_state[1]; hm[:] = warm_state[2]
+    sim.set_state(hp, hv, hm); sim.single_step()  # one untimed pass through this path
+    hp[:] = warm_state[0]; hv[:] = warm_state[1]; hm[:] = warm_state[2]
+    t0 = time.perf_counter()
+    e2e_particle_steps = 0
+    for k in range(K):
+        sim.set_state(hp, hv, hm)                   # H2D of this step's inputs (x, v, m)
+        sim.single_step()
+        sim.get_field("position", out=op)           # D2H of the step's result (x, v), reference particle order
+        sim.get_field("velocity", out=ov)
+        e2e_particle_steps += n
+        hp[:] = op; hv[:] = ov                      # next step's input is this step's output
+    e2e_s = time.perf_counter() - t0
+    e2e = {"value": e2e_particle_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * 20), "d2h_bytes_per_step": int(n * 16)}
+
+    # ---- CPU baseline: the oracle (port of the reference) from the same warm state, bounded sample -----------------
+    cpu = cpu_baseline_from(A, params, boundary, warm_state, budget_s=args.cpu_budget)
+    sim.close()
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": dev_ms / max(K, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: 2D dam-break, uniform h, 999292 particles, HybridDFSPH (default-scene-web geometry, "
+                               "spacing 1.122e-3; default-config with merging/sharing/splitting off, level_estimation None)",
+                   "particles": n, "l2": "working set per step (neighbour lists + SoA, ~400 MB) exceeds the 126 MB L2; no flush",
+                   "avg_div_sweeps": sweeps_div / max(K, 1), "avg_density_sweeps": sweeps_den / max(K, 1),
+                   "timing": "CUDA events on the library stream around every step (PerformanceCounters 'simulation-step')",
+                   "wall_ms_per_step": wall * 1e3 / max(K, 1)},
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+    }
+    out.update(extra)
+    log = os.environ.get("ASPH_BENCH_LOG")
+    if log:
+        with open(log, "w") as f:
+            json.dump({"per_step": per_step}, f)
+    print(json.dumps(out))
+
+
+def cpu_baseline_from(A, params, boundary, state, budget_s):
+    oracle_path = os.path.join(ROOT, "oracle", "liboracle_f32.so")
+    if not os.path.exists(oracle_path):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j", "2"], stdout=subprocess.DEVNULL)
+    olib = A.load_library(oracle_path)
+    olib.oracle_max_threads.restype = C.c_int
+    cores = int(olib.oracle_max_threads())
+    o = A.FluidSimulation(params, state[0], state[1], state[2], boundary, lib=olib)
+    t0 = time.perf_counter()
+    ps, steps = 0, 0
+    while steps < 2 or (time.perf_counter() - t0) < budget_s:
+        o.single_step()
+        ps += o.step_info()["n_particles_begin"]
+        steps += 1
+        if steps >= 200:
+            break
+    el = time.perf_counter() - t0
+    o.close()
+    return {"value": ps / el, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} steps of the same 999292-particle workload from the post-warm-up state ({el:.1f} s of CPU time, "
+                      f"OpenMP over particles, serial phases as in the reference)"}
+
+
+def run_reference(args):
+    """The reference arm: the reference's CPU implementation of the path.  The Rust crate cannot be built here
+    (no cargo/rustc), so this is the oracle port (kind 'port'), all host threads, on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import asph_b200 as A
+    oracle_path = os.path.join(ROOT, "oracle", "liboracle_f32.so")
+    if not os.path.exists(oracle_path):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j", "2"], stdout=subprocess.DEVNULL)
+    olib = A.load_library(oracle_path)
+    olib.oracle_max_threads.restype = C.c_int
+    cores = int(olib.oracle_max_threads())
+    params = uniform_params(A)
+    scene = dam_break(A, SPACING_REF_SAMPLE)
+    pos, vel, mass = A.scene_particles(scene)
+    boundary = A.scene_boundary(scene, "AnalyticOverestimate")
+    o = A.FluidSimulation(params, pos, vel, mass, boundary, lib=olib)
+    for _ in range(args.warmup):
+        o.single_step()
+    t0 = time.perf_counter()
+    ps, done = 0, 0
+    for _ in range(args.steps):
+        o.single_step()
+        ps += o.step_info()["n_particles_begin"]
+        done += 1
+        if time.perf_counter() - t0 > args.ref_budget:
+            break
+    el = time.perf_counter() - t0
+    value = ps / el
+    sample = (f"{done} steps (of {args.steps} asked) of the same dam-break geometry at spacing {SPACING_REF_SAMPLE} = {len(mass)} particles "
+              f"(1/4 of the GPU arm's), uniform h, HybridDFSPH, after {args.warmup} warm-up steps")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done, "warmup": args.warmup,
+        "ms_per_step": el * 1e3 / max(done, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "configs[1] dam-break geometry, bounded CPU sample", "particles": int(len(mass))},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours_distributed(args, A, rank, world):
+    from bench_dist import run  # multi-GPU arm (slab decomposition + NCCL halos)
+    return run(args, A, rank, world)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU time for the cpu_baseline leg")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="time cap of the reference arm's timed steps")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -219,6 +219,14 @@ const char* asph_backend_name(void);               /* "cuda-sm100a" | "oracle-f3
 /* number of GPU kernels this handle has launched so far (0 on the CPU oracle); bench.py reports it */
 uint64_t asph_kernel_launches(const asph_sim* sim);
 
+/* ------------------------------------------------------------------ kernel timing (measurement only)
+ * CUDA-event durations, on the handle's own stream, of sampled launches of the hot kernels, accumulated since
+ * asph_set_kernel_timing was last called.  sample_every = 0 switches it off; k > 0 times every k-th Jacobi sweep
+ * (its pressure-acceleration pass and its update pass separately) and every neighbour build. */
+enum { ASPH_KT_ACCEL_SWEEP = 0, ASPH_KT_JACOBI_SWEEP = 1, ASPH_KT_NEIGHBORS = 2, ASPH_KT_SORT_GRID = 3, ASPH_KT_COUNT = 4 };
+int asph_set_kernel_timing(asph_sim* sim, int sample_every);
+int asph_get_kernel_timing(asph_sim* sim, double ms_sum[ASPH_KT_COUNT], uint64_t samples[ASPH_KT_COUNT]);
+
 /* ------------------------------------------------------------------ pure helpers (host side, no GPU needed)
  * sph_kernels.rs:49-71 (cubic spline, h = smoothing length, support 2h) and
  * boundary_handler/sdf_boundary_handler/plane_numerics.rs:19-152 (λ, λ′ in double). */

@@ -213,6 +213,11 @@ int asph_get_counters(const asph_sim* sim, double ms[ASPH_PC_COUNT], uint64_t ca
 }
 const char* asph_last_error(const asph_sim* sim) { return sim->s.last_error.c_str(); }
 uint64_t asph_kernel_launches(const asph_sim*) { return 0; }
+int asph_set_kernel_timing(asph_sim*, int) { return ASPH_OK; }
+int asph_get_kernel_timing(asph_sim*, double ms[ASPH_KT_COUNT], uint64_t n[ASPH_KT_COUNT]) {
+  for (int k = 0; k < ASPH_KT_COUNT; k++) { ms[k] = 0; n[k] = 0; }
+  return ASPH_OK;
+}
 
 float asph_kernel_w(float r, float h) { return float(kernel_w<FT>(FT(r), FT(h))); }
 void asph_kernel_grad(float dx, float dy, float h, float* gx, float* gy) {
