@@ -16,7 +16,7 @@
 // and is final.  Donors claimed as receivers meanwhile drop out.  Particles live on the device in grid-cell order;
 // `refid` carries the reference index, and the reference's swap-with-last deletion and append-at-end splitting are
 // reproduced in reference-index space with prefix sums.
-#include "sim.cuh"
+#include "lists.cuh"
 
 namespace {
 
@@ -25,9 +25,7 @@ constexpr uint32_t AVAILABLE = ASPH_MERGE_PARTNER_AVAILABLE;
 constexpr uint32_t DELETE_ = ASPH_MERGE_PARTNER_DELETE;
 
 struct AdaptArgs {
-  const uint32_t* __restrict__ nidx;
-  const uint32_t* __restrict__ slice_base;
-  const uint32_t* __restrict__ cnt;
+  NbLists L;
   const float4* __restrict__ xyhm;  // .z = h of this step (h2, unchanged since the step started)
   float2* pos;
   float2* vel;
@@ -110,10 +108,10 @@ k_mark(AdaptArgs A, const PackedParams P, int merging, uint32_t round, const uin
     atomicMax(&A.stampkey[d], key);
     const float2 xd = A.pos[d];
     const float hd = A.xyhm[d].z, md = A.mass[d];
-    const uint32_t cn = A.cnt[d] & 0xffffu;
-    const uint32_t* col = A.nidx + A.slice_base[d >> 5] + (d & 31);
+    const uint32_t cn = A.L.cnt[d] & 0xffffu;
+    const NbCol col(A.L, d);
     for (uint32_t k = 0; k < cn; k++) {
-      const uint32_t j = col[32u * k];
+      const uint32_t j = col.get(k);
       if (j == d || A.partner[j] != AVAILABLE) continue;
       if (static_eligible(A, P, merging != 0, d, j, xd, hd, md)) atomicMax(&A.stampkey[j], key);
     }
@@ -133,11 +131,11 @@ k_decide(AdaptArgs A, const PackedParams P, int merging, uint32_t round, float d
     const unsigned long long key = stamp_of(round, A.refid[d]);
     const float2 xd = A.pos[d];
     const float hd = A.xyhm[d].z, md = A.mass[d];
-    const uint32_t cn = A.cnt[d] & 0xffffu;
-    const uint32_t* col = A.nidx + A.slice_base[d >> 5] + (d & 31);
+    const uint32_t cn = A.L.cnt[d] & 0xffffu;
+    const NbCol col(A.L, d);
     bool ready = A.stampkey[d] == key;
     for (uint32_t k = 0; k < cn && ready; k++) {
-      const uint32_t j = col[32u * k];
+      const uint32_t j = col.get(k);
       if (j == d || A.partner[j] != AVAILABLE) continue;
       if (static_eligible(A, P, merging != 0, d, j, xd, hd, md) && A.stampkey[j] != key) ready = false;
     }
@@ -150,7 +148,7 @@ k_decide(AdaptArgs A, const PackedParams P, int merging, uint32_t round, float d
       uint32_t best_j = 0xFFFFFFFFu;
       long long best_r = 0x7FFFFFFFFFFFFFFFll;
       for (uint32_t k = 0; k < cn; k++) {
-        const uint32_t j = col[32u * k];
+        const uint32_t j = col.get(k);
         const long long r = (long long)A.refid[j];
         if (r > last && r < best_r) { best_r = r; best_j = j; }
       }
@@ -183,9 +181,9 @@ k_validate(uint32_t n, AdaptArgs A, uint8_t donor_class, StepCtl* ctl) {
   if (c > 0) {
     if (A.size_class[i] != donor_class || p != DELETE_) ok = false;
     uint32_t c2 = 0;
-    const uint32_t cn = A.cnt[i] & 0xffffu;
-    const uint32_t* col = A.nidx + A.slice_base[i >> 5] + (i & 31);
-    for (uint32_t k = 0; k < cn; k++) if (A.partner[col[32u * k]] == i) c2++;
+    const uint32_t cn = A.L.cnt[i] & 0xffffu;
+    const NbCol col(A.L, i);
+    for (uint32_t k = 0; k < cn; k++) if (A.partner[col.get(k)] == i) c2++;
     if (c2 != c) ok = false;
   } else {
     if (p == DELETE_) ok = false;
@@ -322,7 +320,7 @@ __global__ void k_split_apply(uint32_t n, uint32_t cap, const uint8_t* __restric
 AdaptArgs args_of(asph_sim* sim) {
   AdaptArgs A;
   const int c = sim->cur;
-  A.nidx = sim->nidx.p; A.slice_base = sim->slice_base.p; A.cnt = sim->cnt.p; A.xyhm = sim->xyhm.p;
+  A.L.pool = sim->nbpool.p; A.L.slice_base = sim->slice_base.p; A.L.cnt = sim->cnt.p; A.xyhm = sim->xyhm.p;
   A.pos = sim->pos[c].p; A.vel = sim->vel[c].p; A.mass = sim->mass[c].p; A.level = sim->level[c].p; A.refid = sim->refid[c].p;
   A.size_class = sim->size_class.p; A.partner = sim->merge_partner.p; A.counter = sim->merge_counter.p;
   A.stampkey = sim->stampkey.p;

@@ -184,6 +184,87 @@ int check_error_flags(asph_sim* sim) {
   return ASPH_ERR_INVALID;
 }
 
+// One attempt at the physics part of the step from the neighbour pass on.  Returns ASPH_RETRY_LISTS when the first
+// synchronisation shows that the neighbour pool was too small (nothing irreversible has happened by then).
+static int physics_after_sort(asph_sim* sim, bool lvl, float f_ext) {
+  const PackedParams& P = sim->pp;
+  cudaEvent_t kt1 = nullptr, kt2 = nullptr;
+  if (sim->kt_every > 0) { kt1 = kt_event(sim); kt2 = kt_event(sim); cudaEventRecord(kt1, sim->stream); }
+  TRY(launch_neighbors(sim, f_ext, P.f_near));
+  if (kt2) cudaEventRecord(kt2, sim->stream);
+  pc_end(sim, ASPH_PC_NEIGHBORHOOD);
+  auto finish_kt = [&]() {
+    if (!kt2) return;
+    float b = 0.f;
+    if (cudaEventSynchronize(kt2) == cudaSuccess && cudaEventElapsedTime(&b, kt1, kt2) == cudaSuccess) {
+      sim->kt_ms[ASPH_KT_NEIGHBORS] += b; sim->kt_samples[ASPH_KT_NEIGHBORS]++;
+    }
+    kt_release(sim, kt1); kt_release(sim, kt2);
+    kt1 = kt2 = nullptr;
+  };
+  int rc = ASPH_OK;
+  auto guard = [&](int r) { if (r != ASPH_OK && rc == ASPH_OK) rc = r; return r == ASPH_OK; };
+  do {
+    if (lvl) {
+      pc_begin(sim, ASPH_PC_LEVEL_ESTIMATION);
+      if (!guard(launch_level_estimation(sim))) break;
+      pc_end(sim, ASPH_PC_LEVEL_ESTIMATION);
+      TRY(check_error_flags(sim));  // density / a_ii asserts of the neighbour pass (simulation.rs:1046-1047, 1390)
+    }
+    int iters = 0, sweeps = 0;
+    bool first = !lvl;  // the first synchronisation after the neighbour pass also validates its error flags
+    auto solve = [&](bool density, float tol, double* avg) {
+      int r = launch_solver(sim, density, tol, &iters, &sweeps, avg);
+      if (r == ASPH_OK && first) { r = check_error_flags(sim); first = false; }
+      return r;
+    };
+    switch (P.solver) {
+      case ASPH_SOLVER_IISPH:  // simulation.rs:2389-2446
+        if (!guard(launch_viscosity(sim)) || !guard(launch_source(sim, 2))) break;
+        pc_begin(sim, ASPH_PC_DENSITY_SOLVER);
+        if (!guard(solve(true, P.max_avg_density_error_iisph, &sim->info.last_avg_error_density))) break;
+        sim->info.density_iterations = iters; sim->info.density_sweeps = sweeps;
+        if (!guard(launch_final_accel(sim, 3))) break;
+        pc_end(sim, ASPH_PC_DENSITY_SOLVER);
+        break;
+      case ASPH_SOLVER_ONLY_DIVERGENCE:  // simulation.rs:2448-2500
+        if (!guard(launch_viscosity(sim)) || !guard(launch_source(sim, 0))) break;
+        pc_begin(sim, ASPH_PC_DIV_SOLVER);
+        if (!guard(solve(false, P.max_avg_divergence_error, &sim->info.last_avg_error_div))) break;
+        sim->info.div_iterations = iters; sim->info.div_sweeps = sweeps;
+        if (!guard(launch_final_accel(sim, 3))) break;
+        pc_end(sim, ASPH_PC_DIV_SOLVER);
+        break;
+      default:  // HybridDFSPH, simulation.rs:2502-2670
+        if (P.np_before_div && !guard(launch_viscosity(sim))) break;
+        pc_begin(sim, ASPH_PC_DIV_SOLVER);
+        if (!guard(launch_source(sim, 0))) break;
+        if (!guard(solve(false, P.max_avg_divergence_error, &sim->info.last_avg_error_div))) break;
+        sim->info.div_iterations = iters; sim->info.div_sweeps = sweeps;
+        if (!guard(launch_final_accel(sim, 1))) break;
+        pc_end(sim, ASPH_PC_DIV_SOLVER);
+        if (!P.np_before_div && !guard(launch_viscosity(sim))) break;
+        pc_begin(sim, ASPH_PC_DENSITY_SOLVER);
+        if (!guard(launch_source(sim, P.density_source == ASPH_SRC_ONLY_DENSITY ? 1 : 2))) break;
+        if (!guard(solve(true, P.max_avg_density_error, &sim->info.last_avg_error_density))) break;
+        sim->info.density_iterations = iters; sim->info.density_sweeps = sweeps;
+        if (!guard(launch_final_accel(sim, 2))) break;
+        pc_end(sim, ASPH_PC_DENSITY_SOLVER);
+        break;
+    }
+    if (rc != ASPH_OK) break;
+    if (lvl) {
+      pc_begin(sim, ASPH_PC_LEVEL_ESTIMATION, false);
+      if (!guard(launch_level_smoothing(sim))) break;
+      pc_end(sim, ASPH_PC_LEVEL_ESTIMATION);
+    }
+    if (!guard(sync_ctl(sim))) break;
+    guard(check_error_flags(sim));
+  } while (false);
+  finish_kt();
+  return rc;
+}
+
 static int step_physics(asph_sim* sim, const asph_params* params, float* dt_out) {
   TRY(pack_params(sim, params));
   const PackedParams& P = sim->pp;
@@ -201,79 +282,32 @@ static int step_physics(asph_sim* sim, const asph_params* params, float* dt_out)
   if (sim->dist) {
     int rc = dist_step_physics(sim);
     if (rc != ASPH_OK) return rc;
+  } else if (sim->n == 0) {
+    sim->info.dt = P.max_dt;
   } else {
     pc_begin(sim, ASPH_PC_NEIGHBORHOOD);
-    cudaEvent_t kt0 = nullptr, kt1 = nullptr, kt2 = nullptr;
-    if (sim->kt_every > 0) { kt0 = kt_event(sim); kt1 = kt_event(sim); kt2 = kt_event(sim); cudaEventRecord(kt0, sim->stream); }
+    cudaEvent_t kt0 = nullptr, kt1 = nullptr;
+    if (sim->kt_every > 0) { kt0 = kt_event(sim); kt1 = kt_event(sim); cudaEventRecord(kt0, sim->stream); }
     TRY(launch_sort_and_grid(sim, std::max(f_ext, P.f_near)));
     if (kt1) cudaEventRecord(kt1, sim->stream);
-    TRY(launch_neighbors(sim, f_ext, P.f_near));
-    if (kt2) {
-      cudaEventRecord(kt2, sim->stream);
-      cudaEventSynchronize(kt2);
-      float a = 0.f, b = 0.f;
-      if (cudaEventElapsedTime(&a, kt0, kt1) == cudaSuccess && cudaEventElapsedTime(&b, kt1, kt2) == cudaSuccess) {
+    int rc = ASPH_OK;
+    for (int attempt = 0; attempt < 6; attempt++) {
+      sim->xv_cur = 0;
+      rc = physics_after_sort(sim, lvl, f_ext);
+      if (rc != ASPH_RETRY_LISTS) break;
+      TRY(neighbors_grow(sim));
+      pc_begin(sim, ASPH_PC_NEIGHBORHOOD, false);
+    }
+    if (kt1) {
+      float a = 0.f;
+      if (cudaEventSynchronize(kt1) == cudaSuccess && cudaEventElapsedTime(&a, kt0, kt1) == cudaSuccess) {
         sim->kt_ms[ASPH_KT_SORT_GRID] += a; sim->kt_samples[ASPH_KT_SORT_GRID]++;
-        sim->kt_ms[ASPH_KT_NEIGHBORS] += b; sim->kt_samples[ASPH_KT_NEIGHBORS]++;
       }
-      kt_release(sim, kt0); kt_release(sim, kt1); kt_release(sim, kt2);
+      kt_release(sim, kt0); kt_release(sim, kt1);
     }
-    pc_end(sim, ASPH_PC_NEIGHBORHOOD);
-    if (sim->n == 0) {
-      sim->info.dt = P.max_dt;
-    } else {
-      TRY(check_error_flags(sim));
-      sim->info.dt = sim->ctl_host->dt;
-      if (lvl) {
-        pc_begin(sim, ASPH_PC_LEVEL_ESTIMATION);
-        TRY(launch_level_estimation(sim));
-        pc_end(sim, ASPH_PC_LEVEL_ESTIMATION);
-      }
-      int iters = 0, sweeps = 0;
-      switch (P.solver) {
-        case ASPH_SOLVER_IISPH:  // simulation.rs:2389-2446
-          TRY(launch_viscosity(sim));
-          TRY(launch_source(sim, 2));
-          pc_begin(sim, ASPH_PC_DENSITY_SOLVER);
-          TRY(launch_solver(sim, true, P.max_avg_density_error_iisph, &iters, &sweeps, &sim->info.last_avg_error_density));
-          sim->info.density_iterations = iters; sim->info.density_sweeps = sweeps;
-          TRY(launch_final_accel(sim, 3));
-          pc_end(sim, ASPH_PC_DENSITY_SOLVER);
-          break;
-        case ASPH_SOLVER_ONLY_DIVERGENCE:  // simulation.rs:2448-2500
-          TRY(launch_viscosity(sim));
-          TRY(launch_source(sim, 0));
-          pc_begin(sim, ASPH_PC_DIV_SOLVER);
-          TRY(launch_solver(sim, false, P.max_avg_divergence_error, &iters, &sweeps, &sim->info.last_avg_error_div));
-          sim->info.div_iterations = iters; sim->info.div_sweeps = sweeps;
-          TRY(launch_final_accel(sim, 3));
-          pc_end(sim, ASPH_PC_DIV_SOLVER);
-          break;
-        default:  // HybridDFSPH, simulation.rs:2502-2670
-          if (P.np_before_div) TRY(launch_viscosity(sim));
-          pc_begin(sim, ASPH_PC_DIV_SOLVER);
-          TRY(launch_source(sim, 0));
-          TRY(launch_solver(sim, false, P.max_avg_divergence_error, &iters, &sweeps, &sim->info.last_avg_error_div));
-          sim->info.div_iterations = iters; sim->info.div_sweeps = sweeps;
-          TRY(launch_final_accel(sim, 1));
-          pc_end(sim, ASPH_PC_DIV_SOLVER);
-          if (!P.np_before_div) TRY(launch_viscosity(sim));
-          pc_begin(sim, ASPH_PC_DENSITY_SOLVER);
-          TRY(launch_source(sim, P.density_source == ASPH_SRC_ONLY_DENSITY ? 1 : 2));
-          TRY(launch_solver(sim, true, P.max_avg_density_error, &iters, &sweeps, &sim->info.last_avg_error_density));
-          sim->info.density_iterations = iters; sim->info.density_sweeps = sweeps;
-          TRY(launch_final_accel(sim, 2));
-          pc_end(sim, ASPH_PC_DENSITY_SOLVER);
-          break;
-      }
-      if (lvl) {
-        pc_begin(sim, ASPH_PC_LEVEL_ESTIMATION, false);
-        TRY(launch_level_smoothing(sim));
-        pc_end(sim, ASPH_PC_LEVEL_ESTIMATION);
-      }
-      TRY(sync_ctl(sim));
-      TRY(check_error_flags(sim));
-    }
+    if (rc == ASPH_RETRY_LISTS) { sim->last_error = "neighbour list pool could not be sized"; rc = ASPH_ERR_CAPACITY; }
+    if (rc != ASPH_OK) { pc_collect(sim); return rc; }
+    sim->info.dt = sim->ctl_host->dt;
   }
   const float dt = sim->info.dt;
   sim->last_dt = dt;
@@ -398,8 +432,8 @@ void asph_destroy(asph_sim* sim) {
   }
   sim->xyhm.release(); sim->packA.release(); sim->pconst.release(); sim->h_tmp.release(); sim->rho.release(); sim->lam_sum.release();
   sim->nrm.release(); sim->gB.release(); sim->lam_grad.release(); sim->key.release(); sim->cellcount.release(); sim->cellstart.release();
-  sim->order.release(); sim->scan_sums.release(); sim->cnt.release(); sim->slice_base.release(); sim->slice_cbase.release();
-  sim->nidx.release(); sim->ncoef.release(); sim->size_class.release(); sim->flags.release(); sim->merge_partner.release();
+  sim->order.release(); sim->scan_sums.release(); sim->cnt.release(); sim->slice_base.release();
+  sim->nbpool.release(); sim->hm.release(); sim->size_class.release(); sim->flags.release(); sim->merge_partner.release();
   sim->cand.release(); for (int k = 0; k < 4; k++) sim->scratch_u[k].release();
   sim->merge_counter.release(); sim->stamp.release(); sim->stampkey.release(); sim->scratch_f.release(); sim->lut.release(); sim->split_pos.release();
   sim->split_off.release(); sim->blockstats.release();
@@ -470,13 +504,13 @@ int asph_get_neighbors_csr(asph_sim* sim, uint64_t* offsets, uint32_t* idx, uint
   const uint32_t n = sim->n;
   std::vector<uint32_t> cnt(n), refid(n), sbase((n + 31) / 32);
   TRY(sync_ctl(sim));
-  const size_t used = sim->ctl_host->list_used;
-  std::vector<uint32_t> pool(used);
+  const size_t used = size_t(sim->ctl_host->list_used) * 64;  // uint16 units
+  std::vector<uint16_t> pool(used);
   if (n) {
     CUDA_TRY(cudaMemcpy(cnt.data(), sim->cnt.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(refid.data(), sim->refid[sim->cur].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(sbase.data(), sim->slice_base.p, sbase.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    if (used) CUDA_TRY(cudaMemcpy(pool.data(), sim->nidx.p, used * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (used) CUDA_TRY(cudaMemcpy(pool.data(), sim->nbpool.p, used * sizeof(uint16_t), cudaMemcpyDeviceToHost));
   }
   uint64_t nnz = 0;
   for (uint32_t i = 0; i < n; i++) nnz += cnt[i] & 0xffffu;
@@ -490,8 +524,16 @@ int asph_get_neighbors_csr(asph_sim* sim, uint64_t* offsets, uint32_t* idx, uint
     const uint32_t i = where[r];
     offsets[r] = o;
     const uint32_t c = cnt[i] & 0xffffu;
-    const size_t base = size_t(sbase[i >> 5]) + (i & 31);
-    for (uint32_t k = 0; k < c; k++) idx[o + k] = refid[pool[base + 32u * k]];
+    const uint32_t sb = sbase[i >> 5];
+    const bool wide = (sb >> 31) != 0;
+    const size_t base = size_t(sb & 0x7fffffffu) * 64;
+    const uint32_t lane = i & 31u, bias = (i & ~31u) - 32768u;
+    for (uint32_t k = 0; k < c; k++) {
+      uint32_t j;
+      if (wide) j = reinterpret_cast<const uint32_t*>(pool.data() + base)[(k >> 2) * 128u + lane * 4u + (k & 3u)];
+      else j = bias + uint32_t(pool[base + (k >> 3) * 256u + lane * 8u + (k & 7u)]);
+      idx[o + k] = refid[j];
+    }
     std::sort(idx + o, idx + o + c);
     o += c;
   }
@@ -505,11 +547,17 @@ int asph_build_neighbors(asph_sim* sim, const asph_params* params, float f) {
   int rc = pack_params(sim, params);
   if (rc != ASPH_OK && rc != ASPH_ERR_UNSUPPORTED) return rc;
   if (sim->dist) { sim->last_error = "asph_build_neighbors on a distributed handle"; return ASPH_ERR_UNSUPPORTED; }
+  if (sim->n == 0) { sim->lists_valid = true; return ASPH_OK; }
   TRY(launch_sort_and_grid(sim, f));
-  TRY(launch_neighbors(sim, f, f));
+  for (int attempt = 0;; attempt++) {
+    TRY(launch_neighbors(sim, f, f));
+    TRY(sync_ctl(sim));
+    if (!(sim->ctl_host->error_flags & ERRF_LIST_CAPACITY)) break;
+    if (attempt >= 6) { sim->last_error = "neighbour list pool could not be sized"; return ASPH_ERR_CAPACITY; }
+    TRY(neighbors_grow(sim));
+  }
   const unsigned int fl = sim->ctl_host->error_flags;
-  if (fl & ERRF_NEIGHBOR_OVERFLOW) return check_error_flags(sim);
-  if (fl & ERRF_CELL_BUDGET) return check_error_flags(sim);
+  if (fl & (ERRF_NEIGHBOR_OVERFLOW | ERRF_CELL_BUDGET)) return check_error_flags(sim);
   sim->step_fields_valid = true;
   return ASPH_OK;
 }

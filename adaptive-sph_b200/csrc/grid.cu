@@ -18,7 +18,7 @@ constexpr int kThreads = 256;
 __global__ void k_ctl_reset(StepCtl* ctl) {
   ctl->hmin_enc = 0xFFFFFFFFu; ctl->minx_enc = 0xFFFFFFFFu; ctl->miny_enc = 0xFFFFFFFFu; ctl->cfl_enc = 0xFFFFFFFFu;
   ctl->hmax_enc = 0u; ctl->maxx_enc = 0u; ctl->maxy_enc = 0u;
-  ctl->list_used = 0; ctl->coef_used = 0; ctl->max_count = 0;
+  ctl->list_used = 0; ctl->max_count = 0;
   ctl->error_flags = 0;
 }
 
@@ -226,7 +226,7 @@ __global__ void k_reorder(uint32_t n, const uint32_t* __restrict__ order, const 
                           const float* __restrict__ mass, const uint32_t* __restrict__ refid, const float* __restrict__ level,
                           const float* __restrict__ h, float2* __restrict__ pos_o, float2* __restrict__ vel_o,
                           float* __restrict__ mass_o, uint32_t* __restrict__ refid_o, float* __restrict__ level_o,
-                          float4* __restrict__ xyhm, float4* __restrict__ xv) {
+                          float4* __restrict__ xyhm, float4* __restrict__ xv, float2* __restrict__ hm) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   uint32_t src = order[s];
@@ -235,6 +235,7 @@ __global__ void k_reorder(uint32_t n, const uint32_t* __restrict__ order, const 
   pos_o[s] = x; vel_o[s] = v; mass_o[s] = m; refid_o[s] = refid[src]; level_o[s] = level[src];
   xyhm[s] = make_float4(x.x, x.y, h[src], m);
   xv[s] = make_float4(x.x, x.y, v.x, v.y);
+  hm[s] = make_float2(h[src], m);
 }
 
 }  // namespace
@@ -289,7 +290,7 @@ int ensure_capacity(asph_sim* sim, uint32_t want) {
   CUDA_TRY(sim->key.ensure(newcap)); CUDA_TRY(sim->order.ensure(newcap));
   CUDA_TRY(sim->cnt.ensure(newcap));
   const uint32_t nslices = (newcap + 31) / 32 + 1;
-  CUDA_TRY(sim->slice_base.ensure(nslices)); CUDA_TRY(sim->slice_cbase.ensure(nslices));
+  CUDA_TRY(sim->slice_base.ensure(nslices)); CUDA_TRY(sim->hm.ensure(newcap));
   CUDA_TRY(sim->size_class.ensure(newcap)); CUDA_TRY(sim->flags.ensure(newcap));
   CUDA_TRY(sim->merge_partner.ensure(newcap)); CUDA_TRY(sim->merge_counter.ensure(newcap));
   CUDA_TRY(sim->front[0].ensure(newcap)); CUDA_TRY(sim->front[1].ensure(newcap)); CUDA_TRY(sim->cand.ensure(newcap));
@@ -334,7 +335,7 @@ int launch_sort_and_grid(asph_sim* sim, float f_search) {
   sim->xv_cur = 0;
   k_reorder<<<blocks, kThreads, 0, st>>>(n, sim->order.p, sim->pos[c].p, sim->vel[c].p, sim->mass[c].p, sim->refid[c].p,
                                          sim->level[c].p, sim->h_tmp.p, sim->pos[1 - c].p, sim->vel[1 - c].p, sim->mass[1 - c].p,
-                                         sim->refid[1 - c].p, sim->level[1 - c].p, sim->xyhm.p, sim->xv[0].p);
+                                         sim->refid[1 - c].p, sim->level[1 - c].p, sim->xyhm.p, sim->xv[0].p, sim->hm.p);
   LAUNCH_CHECK();
   sim->cur = 1 - c;
   return ASPH_OK;

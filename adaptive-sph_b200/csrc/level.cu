@@ -11,17 +11,13 @@
 // max_j(φ_j − |x_ij|) for the claimed ones over neighbours stamped in EARLIER sweeps.  max is order independent and
 // the distance is computed without contraction, so the field is bit-identical to the reference's Jacobi sweeps.
 // `level` encoding: value <= 0 = FluidSurface(value); ASPH_LEVEL_INTERIOR (1.0) = FluidInterior.
-#include "sim.cuh"
+#include "lists.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
 
-struct Lists {
-  const uint32_t* __restrict__ nidx;
-  const uint32_t* __restrict__ slice_base;
-  const uint32_t* __restrict__ cnt;
-};
+typedef NbLists Lists;
 
 __global__ void k_level_reset(StepCtl* ctl) {
   ctl->front_n[0] = 0; ctl->front_n[1] = 0; ctl->cand_n[0] = 0; ctl->cand_n[1] = 0;
@@ -57,9 +53,9 @@ k_surface(uint32_t n, Lists L, const float4* __restrict__ xyhm, const float2* __
       interior = false;
       const float nn = sqrtf(nx * nx + ny * ny);
       nx /= nn; ny /= nn;
-      const uint32_t* col = L.nidx + L.slice_base[i >> 5] + (i & 31);
+      const NbCol col(L, i);
       for (uint32_t k = 0; k < ce; k++) {
-        const uint32_t j = col[32u * k];
+        const uint32_t j = col.get(k);
         const float4 o = __ldg(&xyhm[j]);
         const float dx = o.x - me.x, dy = o.y - me.y;
         const float inv = 1.f / (sqrtf(dx * dx + dy * dy) + 0.000001f);
@@ -93,9 +89,9 @@ k_expand(Lists L, int t, const uint32_t* __restrict__ front_in, uint32_t* __rest
   for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
     const uint32_t j = front_in[f];
     const uint32_t ce = L.cnt[j] >> 16;
-    const uint32_t* col = L.nidx + L.slice_base[j >> 5] + (j & 31);
+    const NbCol col(L, j);
     for (uint32_t k = 0; k < ce; k++) {
-      const uint32_t i = col[32u * k];
+      const uint32_t i = col.get(k);
       if (stamp[i] == -1 && atomicCAS(&stamp[i], -1, -2) == -1) cand[atomicAdd(&ctl->cand_n[t & 1], 1u)] = i;
     }
   }
@@ -116,10 +112,10 @@ k_assign(Lists L, int t, const uint32_t* __restrict__ cand, const float4* __rest
     const uint32_t i = cand[f];
     const float4 me = xyhm[i];
     const uint32_t ce = L.cnt[i] >> 16;
-    const uint32_t* col = L.nidx + L.slice_base[i >> 5] + (i & 31);
+    const NbCol col(L, i);
     float best = -__int_as_float(0x7f800000);
     for (uint32_t k = 0; k < ce; k++) {
-      const uint32_t j = col[32u * k];
+      const uint32_t j = col.get(k);
       const int sj = stamp[j];
       if (sj < 0 || sj >= t) continue;
       const float4 o = __ldg(&xyhm[j]);
@@ -136,18 +132,17 @@ k_assign(Lists L, int t, const uint32_t* __restrict__ cand, const float4* __rest
 
 // K17: φ_i = Σ φ~_j V_j W_ij / Σ V_j W_ij with post-advection positions, pre-advection lists / densities
 __global__ void __launch_bounds__(kThreads)
-k_smooth(uint32_t n, const uint32_t* __restrict__ nidx, const uint32_t* __restrict__ slice_base, const uint32_t* __restrict__ cnt,
-         const float2* __restrict__ pos, const float4* __restrict__ xyhm, const float* __restrict__ rho, const float* __restrict__ level,
+k_smooth(uint32_t n, Lists L, const float2* __restrict__ pos, const float4* __restrict__ xyhm, const float* __restrict__ rho, const float* __restrict__ level,
          float* __restrict__ level_out, float dmax, StepCtl* ctl) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float2 xi = pos[i];
   const float hi = xyhm[i].z;
-  const uint32_t cn = cnt[i] & 0xffffu;
-  const uint32_t* col = nidx + slice_base[i >> 5] + (i & 31);
+  const uint32_t cn = L.cnt[i] & 0xffffu;
+  const NbCol col(L, i);
   float num = 0.f, den = 0.f;
   for (uint32_t k = 0; k < cn; k++) {
-    const uint32_t j = col[32u * k];
+    const uint32_t j = col.get(k);
     const float2 xj = __ldg(&pos[j]);
     const float4 o = __ldg(&xyhm[j]);
     const float lj = __ldg(&level[j]);
@@ -171,7 +166,7 @@ int launch_level_estimation(asph_sim* sim) {
   if (n == 0) return ASPH_OK;
   cudaStream_t st = sim->stream;
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
-  Lists L{sim->nidx.p, sim->slice_base.p, sim->cnt.p};
+  Lists L{sim->nbpool.p, sim->slice_base.p, sim->cnt.p};
   const float cos_threshold = std::cos(50.f * (3.14159265358979323846f / 180.f));
   float* level = sim->level[sim->cur].p;
   k_level_reset<<<1, 1, 0, st>>>(sim->ctl);
@@ -191,6 +186,7 @@ int launch_level_estimation(asph_sim* sim) {
       LAUNCH_CHECK();
     }
     TRY(sync_ctl(sim));
+    if (sim->ctl_host->error_flags & ERRF_LIST_CAPACITY) return ASPH_RETRY_LISTS;
     if (sim->ctl_host->level_done) break;
     if (t > int(n) + 2) { sim->last_error = "level-set propagation did not terminate"; return ASPH_ERR_INVALID; }
     batch = std::min(batch * 2, 64);
@@ -205,7 +201,8 @@ int launch_level_smoothing(asph_sim* sim) {
   if (n == 0) { sim->level_valid = true; return ASPH_OK; }
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
   const int c = sim->cur;
-  k_smooth<<<blocks, kThreads, 0, sim->stream>>>(n, sim->nidx.p, sim->slice_base.p, sim->cnt.p, sim->pos[c].p, sim->xyhm.p, sim->rho.p,
+  Lists L{sim->nbpool.p, sim->slice_base.p, sim->cnt.p};
+  k_smooth<<<blocks, kThreads, 0, sim->stream>>>(n, L, sim->pos[c].p, sim->xyhm.p, sim->rho.p,
                                                  sim->level[c].p, sim->scratch_f.p, sim->pp.maximum_surface_distance, sim->ctl);
   LAUNCH_CHECK();
   CUDA_TRY(cudaMemcpyAsync(sim->level[c].p, sim->scratch_f.p, size_t(n) * sizeof(float), cudaMemcpyDeviceToDevice, sim->stream));

@@ -1,4 +1,4 @@
-// neighbors.cu — neighbour lists (sliced ELL) from the multi-resolution cell grid, fused with every per-particle
+// neighbors.cu — neighbour lists (sliced ELL, lists.cuh) from the multi-resolution cell grid, fused with every per-particle
 // quantity that only needs the pre-advection snapshot {x, h, m}: boundary terms (K7), density (K9), the a_ii
 // diagonal (K11) and the un-normalised surface normal of the level-set detector (first half of K3).
 //
@@ -7,7 +7,7 @@
 // by the reference's own brute-force test at :216-237 and simulation.rs:1810-1863).  Rows 0..cnt_near-1 of a
 // particle's ELL column are N_2 (what NeighborhoodCache::filter_down leaves, neighborhood_search.rs:56-70), rows
 // cnt_near..cnt_ext-1 the rest of N_{f_ext} used only by the level-set estimation.
-#include "sim.cuh"
+#include "lists.cuh"
 
 namespace {
 
@@ -94,19 +94,20 @@ __device__ __forceinline__ void for_each_candidate(float xi, float yi, float hi,
 __global__ void __launch_bounds__(kThreads)
 k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restrict__ ctl_in, StepCtl* ctl,
             const uint32_t* __restrict__ cellstart, const PackedParams P, const float* __restrict__ lut, float f_ext, float f_near,
-            uint32_t list_cap, uint32_t coef_cap, uint32_t* __restrict__ nidx, float* __restrict__ ncoef,
-            uint32_t* __restrict__ slice_base, uint32_t* __restrict__ slice_cbase, uint32_t* __restrict__ cnt,
+            uint32_t pool_cap64, uint16_t* __restrict__ pool, uint32_t* __restrict__ slice_base, uint32_t* __restrict__ cnt,
             float* __restrict__ rho_out, float2* __restrict__ gB_out, float4* __restrict__ pconst, float* __restrict__ lam_sum_out,
             float2* __restrict__ lam_grad_out, float2* __restrict__ nrm_out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t i0 = i & ~31u;
   const bool active = i < n;
   float4 me = make_float4(0.f, 0.f, 1.f, 0.f);
   if (active) me = xyhm[i];
   const float xi = me.x, yi = me.y, hi = me.z;
 
-  // pass 1: counts
+  // pass 1: counts, and whether every neighbour index fits the 16-bit window around the slice
   uint32_t cn = 0, ce = 0;
+  bool fits = true;
   if (active) {
     for_each_candidate(xi, yi, hi, ctl_in, cellstart, f_ext, [&](uint32_t j) {
       const float4 o = __ldg(&xyhm[j]);
@@ -114,66 +115,65 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
       if (d2 < support_sq_exact(hi, o.z, f_ext)) {
         ce++;
         if (d2 < support_sq_exact(hi, o.z, f_near)) cn++;
+        if (j - i0 + 32768u > 65535u) fits = false;
       }
     });
   }
-  uint32_t wn = cn, we = ce;
-  for (int o = 16; o > 0; o >>= 1) {
-    wn = max(wn, __shfl_xor_sync(0xffffffffu, wn, o));
-    we = max(we, __shfl_xor_sync(0xffffffffu, we, o));
-  }
-  uint32_t base = 0, cbase = 0;
+  uint32_t we = ce;
+  for (int o = 16; o > 0; o >>= 1) we = max(we, __shfl_xor_sync(0xffffffffu, we, o));
+  const bool wide = !__all_sync(0xffffffffu, fits);
+  const uint32_t units = nb_slice_units(we, wide);
+  uint32_t base64 = 0;
   if (lane == 0) {
-    base = atomicAdd(&ctl->list_used, 32u * we);
-    cbase = atomicAdd(&ctl->coef_used, 32u * wn);
+    base64 = atomicAdd(&ctl->list_used, units);
     atomicMax(&ctl->max_count, we);
     if (we > 20000u) atomicOr(&ctl->error_flags, ERRF_NEIGHBOR_OVERFLOW);  // MAX_NEIGHBOR_COUNT neighborhood_search.rs:3,148-150
-    if (base + 32u * we > list_cap || cbase + 32u * wn > coef_cap || base + 32u * we < base) atomicOr(&ctl->error_flags, ERRF_LIST_CAPACITY);
-    slice_base[i >> 5] = base;
-    slice_cbase[i >> 5] = cbase;
+    if (base64 + units > pool_cap64 || base64 + units < base64) atomicOr(&ctl->error_flags, ERRF_LIST_CAPACITY);
+    slice_base[i >> 5] = base64 | (wide ? 0x80000000u : 0u);
   }
-  base = __shfl_sync(0xffffffffu, base, 0);
-  cbase = __shfl_sync(0xffffffffu, cbase, 0);
+  base64 = __shfl_sync(0xffffffffu, base64, 0);
   if (!active) return;
+  if (base64 + units > pool_cap64 || base64 + units < base64) { cnt[i] = 0u; return; }  // empty column: later passes stay in bounds
   cnt[i] = cn | (ce << 16);
-  if (base + 32u * we > list_cap || cbase + 32u * wn > coef_cap || base + 32u * we < base) return;
+
+  // pass 2: write the indices (2h neighbours first, then the extended-range rest)
+  uint16_t* slice = pool + size_t(base64) * 64u;
+  {
+    const uint32_t bias = i0 - 32768u;
+    uint32_t kn = 0, ke = cn;
+    for_each_candidate(xi, yi, hi, ctl_in, cellstart, f_ext, [&](uint32_t j) {
+      const float4 o = __ldg(&xyhm[j]);
+      const float d2 = dist_sq_exact(__fsub_rn(xi, o.x), __fsub_rn(yi, o.y));
+      uint32_t row;
+      if (d2 < support_sq_exact(hi, o.z, f_near)) row = kn++;
+      else if (d2 < support_sq_exact(hi, o.z, f_ext)) row = ke++;
+      else return;
+      nb_store(slice, wide, lane, row, j, bias);
+    });
+  }
 
   // boundary terms
   float lam, Gx, Gy;
   boundary_terms(P, lut, xi, yi, hi, lam, Gx, Gy);
 
-  // pass 2: fill + pair sums
-  uint32_t kn = 0, ke = cn;
+  // pass 3: pair sums over the thread's own 2h column (all lanes busy, no predicate divergence)
   float rho = 0.f, Sx = 0.f, Sy = 0.f, Q = 0.f, Nx = 0.f, Ny = 0.f;
-  uint32_t* col = nidx + base + lane;
-  float* ccol = ncoef + cbase + lane;
-  for_each_candidate(xi, yi, hi, ctl_in, cellstart, f_ext, [&](uint32_t j) {
-    const float4 o = __ldg(&xyhm[j]);
-    const float dx = __fsub_rn(xi, o.x), dy = __fsub_rn(yi, o.y);
-    const float d2 = dist_sq_exact(dx, dy);
-    if (d2 < support_sq_exact(hi, o.z, f_near)) {
-      const float hij = (hi + o.z) * 0.5f;  // smoothing_length sph_kernels.rs:273-278
-      const float r = sqrtf(d2);
-      const float nf = kernel_norm(hij);
-      const float q = r / (2.f * hij);
-      rho += o.w * (nf * cubic_w(q));
-      float g = 0.f;
-      if (q > 1.0e-5f) {
-        const float dwdr = nf * cubic_dw(q) / (2.f * hij);
-        g = dwdr / r;
-        Q += o.w * (dwdr * dwdr);
-      }
+  {
+    const uint32_t bias = i0 - 32768u;
+    for (uint32_t k = 0; k < cn; k++) {
+      const uint32_t j = wide ? reinterpret_cast<const uint32_t*>(slice)[(k >> 2) * 128u + lane * 4u + (k & 3u)]
+                              : bias + uint32_t(slice[(k >> 3) * 256u + lane * 8u + (k & 7u)]);
+      const float4 o = __ldg(&xyhm[j]);
+      const float dx = xi - o.x, dy = yi - o.y;
+      float w, g;
+      pair_wg(dx * dx + dy * dy, (hi + o.z) * 0.5f, w, g);
+      rho += o.w * w;
       const float c = o.w * g;
       Sx += c * dx; Sy += c * dy;
+      Q += c * g * (dx * dx + dy * dy);  // m_j |gradW|^2
       Nx += g * dx; Ny += g * dy;
-      col[32u * kn] = j;
-      ccol[32u * kn] = c;
-      kn++;
-    } else if (d2 < support_sq_exact(hi, o.z, f_ext)) {
-      col[32u * ke] = j;
-      ke++;
     }
-  });
+  }
 
   // density, simulation.rs:1018-1047
   rho += lam;
@@ -205,39 +205,31 @@ int launch_neighbors(asph_sim* sim, float f_ext, float f_near) {
   sim->lists_valid = false;
   if (n == 0) { sim->lists_valid = true; return ASPH_OK; }
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
-  for (int attempt = 0; attempt < 6; attempt++) {
-    if (sim->nidx.cap == 0) {
-      // first guess: 24 (2h) / 48 (extended) entries per particle
-      size_t per = (f_ext > f_near) ? 48 : 24;
-      CUDA_TRY(sim->nidx.ensure(size_t(sim->cap) * per + 4096));
-      CUDA_TRY(sim->ncoef.ensure(size_t(sim->cap) * 24 + 4096));
-    }
-    const uint32_t list_cap = uint32_t(std::min<size_t>(sim->nidx.cap, 0xFFFFFFF0u));
-    const uint32_t coef_cap = uint32_t(std::min<size_t>(sim->ncoef.cap, 0xFFFFFFF0u));
-    k_neighbors<<<blocks, kThreads, 0, sim->stream>>>(n, sim->xyhm.p, sim->ctl, sim->ctl, sim->cellstart.p, sim->pp, sim->lut.p, f_ext,
-                                                      f_near, list_cap, coef_cap, sim->nidx.p, sim->ncoef.p, sim->slice_base.p,
-                                                      sim->slice_cbase.p, sim->cnt.p, sim->rho.p, sim->gB.p, sim->pconst.p,
-                                                      sim->lam_sum.p, sim->lam_grad.p, sim->nrm.p);
-    LAUNCH_CHECK();
-    TRY(sync_ctl(sim));
-    const StepCtl& c = *sim->ctl_host;
-    if (!(c.error_flags & ERRF_LIST_CAPACITY)) {
-      sim->lists_valid = true;
-      return ASPH_OK;
-    }
-    // pool too small: grow to what this step asked for (plus slack) and redo the pass
-    size_t want_idx = size_t(c.list_used) + size_t(c.list_used) / 4 + 4096;
-    size_t want_coef = size_t(c.coef_used) + size_t(c.coef_used) / 4 + 4096;
-    if (c.list_used < sim->nidx.cap && c.coef_used < sim->ncoef.cap) { want_idx = sim->nidx.cap * 2; want_coef = sim->ncoef.cap * 2; }
-    if (want_idx > 0xFFFFFFF0u) { sim->last_error = "neighbour list pool exceeds 2^32 entries"; return ASPH_ERR_CAPACITY; }
-    CUDA_TRY(sim->nidx.ensure(want_idx));
-    CUDA_TRY(sim->ncoef.ensure(want_coef));
-    // reset the pool counters and the capacity flag, keep the rest of the control block
-    StepCtl patch = c;
-    patch.list_used = 0; patch.coef_used = 0; patch.max_count = 0; patch.error_flags = c.error_flags & ~ERRF_LIST_CAPACITY;
-    CUDA_TRY(cudaMemcpyAsync(sim->ctl, &patch, sizeof(StepCtl), cudaMemcpyHostToDevice, sim->stream));
-    CUDA_TRY(cudaStreamSynchronize(sim->stream));
+  if (sim->nbpool.cap == 0) {
+    // first guess: 24 (2h) / 48 (extended) 16-bit entries per particle
+    const size_t per = (f_ext > f_near) ? 48 : 24;
+    CUDA_TRY(sim->nbpool.ensure(size_t(sim->cap) * per + 8192));
   }
-  sim->last_error = "neighbour list pool could not be sized";
-  return ASPH_ERR_CAPACITY;
+  const uint32_t cap64 = uint32_t(std::min<size_t>(sim->nbpool.cap / 64, 0x7FFFFFF0u));
+  k_neighbors<<<blocks, kThreads, 0, sim->stream>>>(n, sim->xyhm.p, sim->ctl, sim->ctl, sim->cellstart.p, sim->pp, sim->lut.p, f_ext, f_near,
+                                                    cap64, sim->nbpool.p, sim->slice_base.p, sim->cnt.p, sim->rho.p, sim->gB.p,
+                                                    sim->pconst.p, sim->lam_sum.p, sim->lam_grad.p, sim->nrm.p);
+  LAUNCH_CHECK();
+  sim->lists_valid = true;  // provisional: the caller checks ERRF_LIST_CAPACITY at its next synchronisation (neighbors_grow)
+  return ASPH_OK;
+}
+
+// Called after a synchronisation showed ERRF_LIST_CAPACITY: grow the pool to what the step asked for and clear the
+// flag and counters so the neighbour pass can be launched again (nothing irreversible has happened yet).
+int neighbors_grow(asph_sim* sim) {
+  const StepCtl& c = *sim->ctl_host;
+  size_t want = (size_t(c.list_used) + size_t(c.list_used) / 4 + 128) * 64;
+  if (want <= sim->nbpool.cap) want = sim->nbpool.cap * 2;
+  if (want / 64 > 0x7FFFFFF0u) { sim->last_error = "neighbour list pool exceeds its addressable size"; return ASPH_ERR_CAPACITY; }
+  CUDA_TRY(sim->nbpool.ensure(want));
+  StepCtl patch = c;
+  patch.list_used = 0; patch.max_count = 0; patch.error_flags = c.error_flags & ~ERRF_LIST_CAPACITY;
+  CUDA_TRY(cudaMemcpyAsync(sim->ctl, &patch, sizeof(StepCtl), cudaMemcpyHostToDevice, sim->stream));
+  CUDA_TRY(cudaStreamSynchronize(sim->stream));
+  return ASPH_OK;
 }

@@ -4,13 +4,9 @@
 // Data layout in HBM (all SoA, fp32; particles are physically re-sorted by (size level, grid cell) every step):
 //   persistent  pos float2 | vel float2 | mass f32 | refid u32 (index in the reference's ParticleVec) | level f32
 //   per step    xyhm float4 {x, y, h, m}   pre-advection snapshot, one 16 B gather per neighbour candidate
-//               neighbour lists in sliced ELL: slice = 32 consecutive particles = one warp; entry k of lane l at
-//               slice_base[s] + 32*k + l  -> every warp load of idx/coef is one fully coalesced 128 B line.
-//               Rows k < cnt_near hold the 2h neighbours, cnt_near <= k < cnt_ext the extended-range
-//               (level-set) ones, so NeighborhoodCache::filter_down (neighborhood_search.rs:56) is free.
-//               coef[k] = m_j * dW/dr / r  so that  m_j * gradW_ij = coef * (x_i - x_j)
-//   solver      packP float4 {x, y, p/rho^2, p} | packA float4 {x, y, a^p_x, a^p_y} | pconst float4 {Gx, Gy, a_ii, s}
-//               xv float4 {x, y, vx, vy}
+//               neighbour lists: sliced ELL of 16-bit relative indices (lists.cuh); no stored pair coefficients
+//   solver      packP float4 {x, y, p/rho^2, p} | packA float4 {x, y, a^p_x, a^p_y} | pconst float4 {Gs.x, Gs.y, a_ii, s}
+//               xv float4 {x, y, vx, vy} | hm float2 {h, m} (adaptive h only)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -21,6 +17,7 @@
 #include "../../include/asph.h"
 
 #define ASPH_MAX_LEVELS 12
+#define ASPH_RETRY_LISTS 1000  // internal: the neighbour pool was too small; grow it and redo the step from the neighbour pass
 #define ASPH_SLACK 1.00390625f  // 1 + 1/256: cell / search-radius safety factor against fp32 binning error
 
 // ------------------------------------------------------------------------------------------------
@@ -57,7 +54,7 @@ struct StepCtl {
   uint32_t total_cells;
   float dt;
   unsigned int error_flags;
-  unsigned int list_used, coef_used;  // sliced-ELL pool entries handed out this step
+  unsigned int list_used;  // sliced-ELL pool units (64 uint16) handed out this step
   uint32_t max_count;                 // largest neighbour count
   SolverCtl solver;
   // level set
@@ -119,9 +116,10 @@ struct asph_sim {
   DevBuf<float> h_tmp, rho, lam_sum;
   DevBuf<float2> nrm, gB, lam_grad;
   DevBuf<uint32_t> key, cellcount, cellstart, order, scan_sums;
-  DevBuf<uint32_t> cnt, slice_base, slice_cbase;
-  DevBuf<uint32_t> nidx;
-  DevBuf<float> ncoef;
+  DevBuf<uint32_t> cnt, slice_base;
+  DevBuf<uint16_t> nbpool;  // sliced-ELL neighbour lists (lists.cuh)
+  DevBuf<float2> hm;        // {h, m} per particle: second gather of the adaptive-h pair passes
+  int predicted_sweeps[2] = {1, 1};  // sweeps of the divergence / density solve in the previous step
   DevBuf<uint8_t> size_class, flags;  // flags: bit0 surface, bit1 insufficient neighbours
   DevBuf<uint32_t> merge_partner, front[2], cand, work[2], scratch_u[4];
   DevBuf<uint32_t> merge_counter;
@@ -209,6 +207,7 @@ int launch_exclusive_scan(asph_sim* sim, const uint32_t* in, uint32_t* out, cons
                           uint32_t n_max);  // out[i] = sum(in[0..i)) for i < *n_dev + n_add
 // neighbors.cu
 int launch_neighbors(asph_sim* sim, float f_ext, float f_near);
+int neighbors_grow(asph_sim* sim);
 // solver.cu
 int launch_viscosity(asph_sim* sim);
 int launch_source(asph_sim* sim, int kind);  // 0 divergence, 1 only density, 2 full

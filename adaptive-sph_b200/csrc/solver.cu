@@ -1,28 +1,20 @@
-// solver.cu — the pair-sum passes of the step that run on the stored sliced-ELL lists: non-pressure acceleration
-// (K12), PPE source terms (K13), the relaxed-Jacobi pressure sweeps (K14 + K15) with their device-side loop
-// control, and the integrators (K16).
+// solver.cu — the pair-sum passes of the step that run on the stored neighbour lists: non-pressure acceleration
+// (K12), PPE source terms (K13), the relaxed-Jacobi pressure sweeps (K14 + K15) with their device-side stop rule,
+// and the integrators (K16).
 //
-// Every pass is one thread per particle; a warp reads row k of its slice's idx/coef columns as one coalesced 128 B
-// line and gathers one float4 per neighbour.  With coef = m_j * dW/dr / r stored once per step,
-//   m_j * gradW_ij = coef * x_ij
-// so a sweep needs no sqrt / division per pair.
+// Every pass is one thread per particle.  A warp reads row k of its slice's 16-bit index column as one coalesced
+// 64 B line, gathers ONE float4 per neighbour (plus {h, m} when h is not uniform) and recomputes
+//   m_j * gradW_ij = m_j * pair_g(|x_ij|^2, h_ij) * x_ij
+// in registers (lists.cuh), so a sweep streams 2 B per neighbour from HBM instead of 8.
 //
 // Reference: simulation.rs:931-1005 (non-pressure accel), :1552-1592 (divergence operator), :1633-1748 (sources),
 // :1751-1808 (pressure accel), :1207-1322 (Jacobi sweep + PressureSolverStatistics), :1378-1516 (loop control),
 // :2389-2446 / :2502-2670 (IISPH / HybridDFSPH step orders); boundary terms boundary_winchenbach2020.rs:164-223.
-#include "sim.cuh"
+#include "lists.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
-
-struct Lists {
-  const uint32_t* __restrict__ nidx;
-  const float* __restrict__ ncoef;
-  const uint32_t* __restrict__ slice_base;
-  const uint32_t* __restrict__ slice_cbase;
-  const uint32_t* __restrict__ cnt;
-};
 
 __global__ void k_solver_reset(StepCtl* ctl) {
   SolverCtl s;
@@ -31,41 +23,60 @@ __global__ void k_solver_reset(StepCtl* ctl) {
   ctl->solver = s;
 }
 
-// ---------------------------------------------------------------------------------------------- K12
-__global__ void __launch_bounds__(kThreads)
-k_viscosity(uint32_t n, Lists L, const float4* __restrict__ xyhm, const float4* __restrict__ xv_in, const float* __restrict__ rho,
-            const PackedParams P, const StepCtl* __restrict__ ctl, float4* __restrict__ xv_out) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float dt = ctl->dt;
-  const float4 me = xyhm[i];
-  const float4 mv = xv_in[i];
-  const float rho_i = rho[i];
-  const uint32_t cn = L.cnt[i] & 0xffffu;
-  const uint32_t* col = L.nidx + L.slice_base[i >> 5] + (i & 31);
-  const float* ccol = L.ncoef + L.slice_cbase[i >> 5] + (i & 31);
-  float ax = 0.f, ay = 0.f;
-  if (P.viscosity_type != ASPH_VISC_XSPH) {
-    for (uint32_t k = 0; k < cn; k++) {
-      const uint32_t j = __ldcs(col + 32u * k);
-      const float c = __ldcs(ccol + 32u * k);
-      const float4 o = __ldg(&xyhm[j]);
-      const float4 ov = __ldg(&xv_in[j]);
-      const float dx = me.x - o.x, dy = me.y - o.y;
-      const float est = dx * (mv.z - ov.z) + dy * (mv.w - ov.w);
-      if (!(est < 0.f)) continue;
-      const float hij = (me.z + o.z) * 0.5f;
-      const float d2 = dx * dx + dy * dy;
-      float f;
-      if (P.viscosity_type == ASPH_VISC_APPROX_LAPLACE) {
-        const float rho_ij = (rho_i + __ldg(&rho[j])) * 0.5f;
-        f = P.viscosity * (8.f * est / (rho_ij * (d2 + 0.01f * hij * hij)));  // 2(D+2), D = 2
-      } else {  // WCSPH, speed of sound 88
-        const float visc = 2.f * P.viscosity * hij * 88.f / (rho_i + __ldg(&rho[j]));
-        f = visc * est / (d2 + 0.001f * hij * hij);
-      }
-      ax += f * c * dx; ay += f * c * dy;
+// Σ over N_2(i): f(pack[j], x_ij, m_j * dW/dr / r).  UNI: h and m are the same for every particle of this step.
+// A column is consumed 8 entries at a time: one vector load of indices, then 8 independent gathers in flight, then the
+// arithmetic.  Padding entries point at the particle itself (zero distance => pair_g = 0 => no contribution).
+template <bool UNI, class F>
+__device__ __forceinline__ void for_each_pair(const NbLists& L, uint32_t i, const float4* __restrict__ pack, const float2* __restrict__ hm,
+                                              float xi, float yi, float hi, float mi, F f) {
+  const NbCol col(L, i);
+  const uint32_t cn = __ldg(&L.cnt[i]) & 0xffffu;
+  float inv2h = 0.f, nfac = 0.f;
+  if (UNI) { inv2h = __frcp_rn(2.f * hi); nfac = ASPH_KNORM * inv2h * inv2h * inv2h; }
+  for (uint32_t k0 = 0; k0 < cn; k0 += 8u) {
+    uint32_t j[8];
+    col.get8(k0, cn, j);
+    float4 o[8];
+    float2 t[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      o[u] = __ldg(&pack[j[u]]);
+      if (!UNI) t[u] = __ldg(&hm[j[u]]);
     }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const float dx = xi - o[u].x, dy = yi - o[u].y;
+      const float d2 = dx * dx + dy * dy;
+      const float c = UNI ? mi * pair_g_uniform(d2, inv2h, nfac) : t[u].y * pair_g(d2, (hi + t[u].x) * 0.5f);
+      f(o[u], dx, dy, c, j[u]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- K12
+template <bool UNI>
+__device__ __forceinline__ void viscosity_body(uint32_t i, const NbLists& L, const float4* __restrict__ xv_in, const float2* __restrict__ hm,
+                                               const float* __restrict__ rho, const PackedParams& P, float dt, float4* __restrict__ xv_out) {
+  const float4 me = xv_in[i];
+  const float2 own = hm[i];
+  const float rho_i = rho[i];
+  float ax = 0.f, ay = 0.f;
+  if (P.viscosity_type != ASPH_VISC_XSPH && P.viscosity != 0.f) {
+    for_each_pair<UNI>(L, i, xv_in, hm, me.x, me.y, own.x, own.y, [&](const float4& o, float dx, float dy, float c, uint32_t j) {
+      const float est = dx * (me.z - o.z) + dy * (me.w - o.w);
+      if (est < 0.f) {
+        const float hij = UNI ? own.x : (own.x + __ldg(&hm[j]).x) * 0.5f;
+        const float d2 = dx * dx + dy * dy;
+        const float rho_j = __ldg(&rho[j]);
+        float f;
+        if (P.viscosity_type == ASPH_VISC_APPROX_LAPLACE) {
+          f = P.viscosity * (8.f * est / ((rho_i + rho_j) * 0.5f * (d2 + 0.01f * hij * hij)));  // 2(D+2), D = 2
+        } else {  // WCSPH, speed of sound 88
+          f = (2.f * P.viscosity * hij * 88.f / (rho_i + rho_j)) * est / (d2 + 0.001f * hij * hij);
+        }
+        ax += f * c * dx; ay += f * c * dy;
+      }
+    });
   }
   ay += P.gravity;
   if (P.has_pull) {
@@ -73,14 +84,24 @@ k_viscosity(uint32_t n, Lists L, const float4* __restrict__ xyhm, const float4* 
     const float pn = sqrtf(px * px + py * py);
     ax += px / pn * 13.f; ay += py / pn * 13.f;
   }
-  xv_out[i] = make_float4(me.x, me.y, mv.z + dt * ax, mv.w + dt * ay);
+  xv_out[i] = make_float4(me.x, me.y, me.z + dt * ax, me.w + dt * ay);
+}
+__global__ void __launch_bounds__(kThreads)
+k_viscosity(uint32_t n, NbLists L, const float4* __restrict__ xv_in, const float2* __restrict__ hm, const float* __restrict__ rho,
+            const PackedParams P, const StepCtl* __restrict__ ctl, float4* __restrict__ xv_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (ctl->hmin == ctl->hmax) viscosity_body<true>(i, L, xv_in, hm, rho, P, ctl->dt, xv_out);
+  else viscosity_body<false>(i, L, xv_in, hm, rho, P, ctl->dt, xv_out);
 }
 
 // ---------------------------------------------------------------------------------------------- K13
-// kind 0: -div(v)/dt; 1: -(rho0-rho)/(rho dt^2); 2: both.  Also p <- 0 (packP[0]).
+// kind 0: -div(v)/dt; 1: -(rho0-rho)/(rho dt^2); 2: both.  Also p <- 0 (packP[0]) and a^p <- 0 (what K14 gives for p = 0,
+// so the first sweep does not launch its pressure-acceleration pass).
 __global__ void __launch_bounds__(kThreads)
-k_source(uint32_t n, Lists L, const float4* __restrict__ xv, const float* __restrict__ rho, float4* __restrict__ pconst,
-         float4* __restrict__ packP0, const StepCtl* __restrict__ ctl, float rho0, int kind) {
+k_source(uint32_t n, NbLists L, const float4* __restrict__ xv, const float2* __restrict__ hm, const float* __restrict__ rho,
+         float4* __restrict__ pconst, float4* __restrict__ packP0, float4* __restrict__ packA, const StepCtl* __restrict__ ctl,
+         float rho0, int kind) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float dt = ctl->dt;
@@ -89,17 +110,11 @@ k_source(uint32_t n, Lists L, const float4* __restrict__ xv, const float* __rest
   const float rho_i = rho[i];
   float s = 0.f;
   if (kind != 1) {
-    const uint32_t cn = L.cnt[i] & 0xffffu;
-    const uint32_t* col = L.nidx + L.slice_base[i >> 5] + (i & 31);
-    const float* ccol = L.ncoef + L.slice_cbase[i >> 5] + (i & 31);
+    const float2 own = hm[i];
     float sum = 0.f;
-#pragma unroll 4
-    for (uint32_t k = 0; k < cn; k++) {
-      const uint32_t j = __ldcs(col + 32u * k);
-      const float c = __ldcs(ccol + 32u * k);
-      const float4 o = __ldg(&xv[j]);
-      sum += c * ((o.z - me.z) * (me.x - o.x) + (o.w - me.w) * (me.y - o.y));
-    }
+    auto body = [&](const float4& o, float dx, float dy, float c, uint32_t) { sum += c * ((o.z - me.z) * dx + (o.w - me.w) * dy); };
+    if (ctl->hmin == ctl->hmax) for_each_pair<true>(L, i, xv, hm, me.x, me.y, own.x, own.y, body);
+    else for_each_pair<false>(L, i, xv, hm, me.x, me.y, own.x, own.y, body);
     const float div = sum / rho_i - (me.z * pc.x + me.w * pc.y);
     s = -div / dt;
   }
@@ -107,36 +122,40 @@ k_source(uint32_t n, Lists L, const float4* __restrict__ xv, const float* __rest
   pc.w = s;
   pconst[i] = pc;
   packP0[i] = make_float4(me.x, me.y, 0.f, 0.f);
+  packA[i] = make_float4(me.x, me.y, 0.f, 0.f);  // a^p of the first sweep: p = 0 everywhere => exactly zero (simulation.rs:1792-1807)
 }
 
 // ---------------------------------------------------------------------------------------------- K14
-// a^p_i = -Σ coef (P_i + P_j) x_ij - p_i * Bc * G_i,  P = p / rho^2.
+// a^p_i = -Σ m_j (P_i + P_j) gradW_ij - p_i * Bc * G_i,  P = p / rho^2.
 // MODE 0: sweep (skipped once the solver is done); 1: final, v += dt a^p into the xv pack; 2: final + HybridDFSPH
 // integration (simulation.rs:2622-2669); 3: final + IISPH integration (simulation.rs:2433-2444); 4: final only.
+// P0 / P1: the two pressure packs; the current one is chosen by the parity of the sweeps executed so far, read from
+// the control block, so the launch sequence does not depend on when the solver stops.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
-k_accel(uint32_t n, Lists L, const float4* __restrict__ packP, const float2* __restrict__ gB, float4* __restrict__ packA,
-        StepCtl* ctl, float4* __restrict__ xv, float2* __restrict__ pos, float2* __restrict__ vel, float hybrid_factor) {
+k_accel(uint32_t n, NbLists L, const float4* __restrict__ P0, const float4* __restrict__ P1, const float2* __restrict__ hm,
+        const float2* __restrict__ gB, float4* __restrict__ packA, StepCtl* ctl, float4* __restrict__ xv, float2* __restrict__ pos,
+        float2* __restrict__ vel, float hybrid_factor) {
   if (MODE == 0 && ctl->solver.done) return;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const float4* __restrict__ packP = (ctl->solver.sweeps & 1) ? P1 : P0;
   const float4 me = packP[i];
-  const uint32_t cn = L.cnt[i] & 0xffffu;
-  const uint32_t* col = L.nidx + L.slice_base[i >> 5] + (i & 31);
-  const float* ccol = L.ncoef + L.slice_cbase[i >> 5] + (i & 31);
   float ax = 0.f, ay = 0.f;
-#pragma unroll 4
-  for (uint32_t k = 0; k < cn; k++) {
-    const uint32_t j = __ldcs(col + 32u * k);
-    const float c = __ldcs(ccol + 32u * k);
-    const float4 o = __ldg(&packP[j]);
-    const float f = c * (me.z + o.z);
-    ax -= f * (me.x - o.x);
-    ay -= f * (me.y - o.y);
+  // After a sweep that left no particle with positive pressure (normal == 0: every p' was clamped to 0 or was
+  // singular) the whole pressure field is zero and so is a^p; skip the pair sum.
+  if (MODE == 0 || ctl->solver.normal != 0) {
+    const float2 own = hm[i];
+    auto body = [&](const float4& o, float dx, float dy, float c, uint32_t) {
+      const float f = c * (me.z + o.z);
+      ax -= f * dx; ay -= f * dy;
+    };
+    if (ctl->hmin == ctl->hmax) for_each_pair<true>(L, i, packP, hm, me.x, me.y, own.x, own.y, body);
+    else for_each_pair<false>(L, i, packP, hm, me.x, me.y, own.x, own.y, body);
+    const float2 g = gB[i];
+    ax -= me.w * g.x;
+    ay -= me.w * g.y;
   }
-  const float2 g = gB[i];
-  ax -= me.w * g.x;
-  ay -= me.w * g.y;
   packA[i] = make_float4(me.x, me.y, ax, ay);
   if (MODE == 1) {
     const float dt = ctl->dt;
@@ -165,38 +184,35 @@ k_accel(uint32_t n, Lists L, const float4* __restrict__ packP, const float2* __r
 // (Ap)_i = div(a^p)_i; p' = p + ω (s - Ap) / a_ii, clamped at 0; PressureSolverStatistics reduced per block,
 // then by the last block to finish (fixed order => deterministic), which also evaluates the stop rule.
 __global__ void __launch_bounds__(kThreads)
-k_jacobi(uint32_t n, Lists L, const float4* __restrict__ packA, const float4* __restrict__ packP, float4* __restrict__ packP_next,
-         const float4* __restrict__ pconst, const float* __restrict__ rho, StepCtl* ctl, float* __restrict__ blockstats, float omega,
-         float rho0, float tol, int max_iters, int density_mode) {
+k_jacobi(uint32_t n, NbLists L, const float4* __restrict__ packA, float4* __restrict__ P0, float4* __restrict__ P1,
+         const float2* __restrict__ hm, const float4* __restrict__ pconst, const float* __restrict__ rho, StepCtl* ctl,
+         float* __restrict__ blockstats, float omega, float rho0, float tol, int max_iters, int density_mode) {
   if (ctl->solver.done) return;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const float dt = ctl->dt;
+  const bool odd = (ctl->solver.sweeps & 1) != 0;
+  const float4* __restrict__ packP = odd ? P1 : P0;
+  float4* __restrict__ packP_next = odd ? P0 : P1;
   uint32_t c_normal = 0, c_sing = 0, c_neg = 0;
   float e_sum = 0.f, e_max = 0.f;
   bool bad = false;
   if (i < n) {
     const float4 me = packA[i];
     const float4 pc = pconst[i];
-    const float4 pp = packP[i];
+    const float p_old = packP[i].w;
     float pn = 0.f;
     const float rho_i = rho[i];
     if (fabsf(pc.z) < 10e-4f) {
       c_sing = 1;
     } else {
-      const uint32_t cn = L.cnt[i] & 0xffffu;
-      const uint32_t* col = L.nidx + L.slice_base[i >> 5] + (i & 31);
-      const float* ccol = L.ncoef + L.slice_cbase[i >> 5] + (i & 31);
+      const float2 own = hm[i];
       float sum = 0.f;
-#pragma unroll 4
-      for (uint32_t k = 0; k < cn; k++) {
-        const uint32_t j = __ldcs(col + 32u * k);
-        const float c = __ldcs(ccol + 32u * k);
-        const float4 o = __ldg(&packA[j]);
-        sum += c * ((o.z - me.z) * (me.x - o.x) + (o.w - me.w) * (me.y - o.y));
-      }
+      auto body = [&](const float4& o, float dx, float dy, float c, uint32_t) { sum += c * ((o.z - me.z) * dx + (o.w - me.w) * dy); };
+      if (ctl->hmin == ctl->hmax) for_each_pair<true>(L, i, packA, hm, me.x, me.y, own.x, own.y, body);
+      else for_each_pair<false>(L, i, packA, hm, me.x, me.y, own.x, own.y, body);
       const float Ap = sum / rho_i - (me.z * pc.x + me.w * pc.y);
       const float resid = pc.w - Ap;
-      pn = pp.w + omega * resid / pc.z;
+      pn = p_old + omega * resid / pc.z;
       if (!isfinite(Ap) || !isfinite(pn)) bad = true;
       const float perr = density_mode ? rho_i * dt * dt * resid : dt * resid;
       if (pn <= 0.f) { pn = 0.f; c_neg = 1; }
@@ -265,9 +281,9 @@ k_jacobi(uint32_t n, Lists L, const float4* __restrict__ packA, const float4* __
   }
 }
 
-Lists lists_of(asph_sim* sim) {
-  Lists L;
-  L.nidx = sim->nidx.p; L.ncoef = sim->ncoef.p; L.slice_base = sim->slice_base.p; L.slice_cbase = sim->slice_cbase.p; L.cnt = sim->cnt.p;
+NbLists lists_of(asph_sim* sim) {
+  NbLists L;
+  L.pool = sim->nbpool.p; L.slice_base = sim->slice_base.p; L.cnt = sim->cnt.p;
   return L;
 }
 
@@ -278,8 +294,7 @@ int launch_viscosity(asph_sim* sim) {
   if (n == 0) return ASPH_OK;
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
   const int a = sim->xv_cur;
-  k_viscosity<<<blocks, kThreads, 0, sim->stream>>>(n, lists_of(sim), sim->xyhm.p, sim->xv[a].p, sim->rho.p, sim->pp, sim->ctl,
-                                                    sim->xv[1 - a].p);
+  k_viscosity<<<blocks, kThreads, 0, sim->stream>>>(n, lists_of(sim), sim->xv[a].p, sim->hm.p, sim->rho.p, sim->pp, sim->ctl, sim->xv[1 - a].p);
   LAUNCH_CHECK();
   sim->xv_cur = 1 - a;
   return ASPH_OK;
@@ -289,8 +304,10 @@ int launch_source(asph_sim* sim, int kind) {
   const uint32_t n = sim->n;
   if (n == 0) return ASPH_OK;
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
-  k_source<<<blocks, kThreads, 0, sim->stream>>>(n, lists_of(sim), sim->xv[sim->xv_cur].p, sim->rho.p, sim->pconst.p, sim->packP[0].p,
-                                                 sim->ctl, sim->pp.rest_density, kind);
+  k_solver_reset<<<1, 1, 0, sim->stream>>>(sim->ctl);
+  LAUNCH_CHECK();
+  k_source<<<blocks, kThreads, 0, sim->stream>>>(n, lists_of(sim), sim->xv[sim->xv_cur].p, sim->hm.p, sim->rho.p, sim->pconst.p,
+                                                 sim->packP[0].p, sim->packA.p, sim->ctl, sim->pp.rest_density, kind);
   LAUNCH_CHECK();
   sim->p_cur = 0;
   return ASPH_OK;
@@ -298,6 +315,7 @@ int launch_source(asph_sim* sim, int kind) {
 
 // iisph_pressure_iterations (simulation.rs:1378-1516).  Sweeps are enqueued in batches; each kernel returns
 // immediately once the device-side stop rule has fired, and the host looks at the control block once per batch.
+// The first batch is sized from the sweep count of the same solve in the previous step.
 int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* iters_out, int* sweeps_out, double* avg_out) {
   const uint32_t n = sim->n;
   *iters_out = 0; *sweeps_out = 0; *avg_out = 0;
@@ -305,25 +323,26 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
   CUDA_TRY(sim->blockstats.ensure(size_t(blocks) * 5 + 8));
   cudaStream_t st = sim->stream;
-  k_solver_reset<<<1, 1, 0, st>>>(sim->ctl);
-  LAUNCH_CHECK();
-  const Lists L = lists_of(sim);
+  const NbLists L = lists_of(sim);
   int launched = 0;
-  int batch = 4;
+  int& predicted = sim->predicted_sweeps[density_mode ? 1 : 0];
+  int batch = std::max(1, std::min(predicted, 256));
   const int max_sweeps = sim->pp.max_iters + 1;
   struct Timed { int sweep; cudaEvent_t e0, e1, e2; };
   std::vector<Timed> timed;
   for (;;) {
     for (int b = 0; b < batch && launched < max_sweeps; b++, launched++) {
-      const int in = launched & 1;
       const bool time_it = sim->kt_every > 0 && (launched % sim->kt_every) == 0;
       Timed tm{launched, nullptr, nullptr, nullptr};
       if (time_it) { tm.e0 = kt_event(sim); tm.e1 = kt_event(sim); tm.e2 = kt_event(sim); cudaEventRecord(tm.e0, st); }
-      k_accel<0><<<blocks, kThreads, 0, st>>>(n, L, sim->packP[in].p, sim->gB.p, sim->packA.p, sim->ctl, nullptr, nullptr, nullptr, 0.f);
-      LAUNCH_CHECK();
+      if (launched > 0) {  // sweep 0: a^p = 0 was written by k_source
+        k_accel<0><<<blocks, kThreads, 0, st>>>(n, L, sim->packP[0].p, sim->packP[1].p, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, nullptr,
+                                                nullptr, nullptr, 0.f);
+        LAUNCH_CHECK();
+      }
       if (time_it) cudaEventRecord(tm.e1, st);
-      k_jacobi<<<blocks, kThreads, 0, st>>>(n, L, sim->packA.p, sim->packP[in].p, sim->packP[1 - in].p, sim->pconst.p, sim->rho.p, sim->ctl,
-                                            sim->blockstats.p, sim->pp.jacobi_omega, sim->pp.rest_density, max_avg_error,
+      k_jacobi<<<blocks, kThreads, 0, st>>>(n, L, sim->packA.p, sim->packP[0].p, sim->packP[1].p, sim->hm.p, sim->pconst.p, sim->rho.p,
+                                            sim->ctl, sim->blockstats.p, sim->pp.jacobi_omega, sim->pp.rest_density, max_avg_error,
                                             sim->pp.max_iters, density_mode ? 1 : 0);
       LAUNCH_CHECK();
       if (time_it) { cudaEventRecord(tm.e2, st); timed.push_back(tm); }
@@ -333,20 +352,23 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
     for (const Timed& tm : timed) {
       float a = 0.f, b2 = 0.f;
       if (tm.sweep < s.sweeps && cudaEventElapsedTime(&a, tm.e0, tm.e1) == cudaSuccess && cudaEventElapsedTime(&b2, tm.e1, tm.e2) == cudaSuccess) {
-        sim->kt_ms[ASPH_KT_ACCEL_SWEEP] += a; sim->kt_samples[ASPH_KT_ACCEL_SWEEP]++;
+        if (tm.sweep > 0) { sim->kt_ms[ASPH_KT_ACCEL_SWEEP] += a; sim->kt_samples[ASPH_KT_ACCEL_SWEEP]++; }  // sweep 0 has no K14 launch
         sim->kt_ms[ASPH_KT_JACOBI_SWEEP] += b2; sim->kt_samples[ASPH_KT_JACOBI_SWEEP]++;
       }
       kt_release(sim, tm.e0); kt_release(sim, tm.e1); kt_release(sim, tm.e2);
     }
     timed.clear();
+    if (sim->ctl_host->error_flags & ERRF_LIST_CAPACITY) return ASPH_RETRY_LISTS;
     if (sim->ctl_host->error_flags & ERRF_SOLVER_NONFINITE) {
       sim->last_error = "'!a_p.is_finite()' failed. Pressure values probably have exploded!";
       return ASPH_ERR_NONFINITE;
     }
     if (s.done || launched >= max_sweeps) break;
-    batch = std::min(batch * 2, 32);
+    // not done: continue with small batches that grow (each synchronisation costs about as much as two idle launches)
+    batch = (launched <= predicted) ? 2 : std::min(batch * 2, 64);
   }
   const SolverCtl& s = sim->ctl_host->solver;
+  predicted = s.sweeps;
   sim->p_cur = s.sweeps & 1;
   *iters_out = s.k;
   *sweeps_out = s.sweeps;
@@ -358,17 +380,18 @@ int launch_final_accel(asph_sim* sim, int mode) {
   const uint32_t n = sim->n;
   if (n == 0) return ASPH_OK;
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
-  const Lists L = lists_of(sim);
+  const NbLists L = lists_of(sim);
   cudaStream_t st = sim->stream;
-  const float4* P = sim->packP[sim->p_cur].p;
+  const float4* P0 = sim->packP[0].p;
+  const float4* P1 = sim->packP[1].p;
   float4* xv = sim->xv[sim->xv_cur].p;
   float2* pos = sim->pos[sim->cur].p;
   float2* vel = sim->vel[sim->cur].p;
   switch (mode) {
-    case 1: k_accel<1><<<blocks, kThreads, 0, st>>>(n, L, P, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f); break;
-    case 2: k_accel<2><<<blocks, kThreads, 0, st>>>(n, L, P, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, sim->pp.hybrid_factor); break;
-    case 3: k_accel<3><<<blocks, kThreads, 0, st>>>(n, L, P, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f); break;
-    default: k_accel<4><<<blocks, kThreads, 0, st>>>(n, L, P, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f); break;
+    case 1: k_accel<1><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f); break;
+    case 2: k_accel<2><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, sim->pp.hybrid_factor); break;
+    case 3: k_accel<3><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f); break;
+    default: k_accel<4><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f); break;
   }
   LAUNCH_CHECK();
   return ASPH_OK;
