@@ -6,10 +6,14 @@ The directory name carries a hyphen (it is the name the task fixes); import it w
 from .binding import (AsphError, FluidSimulation, StatisticsRecorder, init_fluid_sim, load_library, FIELDS,
                       LEVEL_INTERIOR, PRODUCT_LIB)
 from .params import SimulationParams, merge_overwrite
-from .scene import SceneConfig, add_fluid_block, init_simulation_params, scene_boundary, scene_particles
+from .scene import (SceneConfig, add_fluid_block, init_simulation_params, scene_boundary, scene_particle_count,
+                    scene_particles)
+from .distributed import (DistributedFluidSimulation, broadcast_unique_id, gather_by_global_index, owner_of, share_range,
+                          slab_bounds_from_histogram)
 from .split_patterns import SplitPatterns, load_split_patterns_from_file
 
 __all__ = ["AsphError", "FluidSimulation", "StatisticsRecorder", "init_fluid_sim", "load_library", "FIELDS",
            "LEVEL_INTERIOR", "PRODUCT_LIB", "SimulationParams", "merge_overwrite", "SceneConfig", "add_fluid_block",
-           "init_simulation_params", "scene_boundary", "scene_particles", "SplitPatterns",
-           "load_split_patterns_from_file"]
+           "init_simulation_params", "scene_boundary", "scene_particles", "scene_particle_count", "SplitPatterns",
+           "load_split_patterns_from_file", "DistributedFluidSimulation", "broadcast_unique_id", "gather_by_global_index",
+           "owner_of", "share_range", "slab_bounds_from_histogram"]

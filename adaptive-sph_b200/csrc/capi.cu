@@ -8,7 +8,6 @@
 
 #include "sim.cuh"
 
-int dist_step_physics(asph_sim* sim);  // dist.cu (multi-GPU orchestration); unused when sim->dist == nullptr
 
 namespace {
 
@@ -115,6 +114,7 @@ __global__ void k_extract(uint32_t n, int field, const uint32_t* __restrict__ re
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t r = refid[i];
+  if (r == 0xFFFFFFFFu) return;  // multi-GPU read-back map: ghost particle
   float* f = (float*)out;
   switch (field) {
     case ASPH_F_POSITION: f[2 * r] = pos[i].x; f[2 * r + 1] = pos[i].y; break;
@@ -269,7 +269,7 @@ static int step_physics(asph_sim* sim, const asph_params* params, float* dt_out)
   TRY(pack_params(sim, params));
   const PackedParams& P = sim->pp;
   memset(&sim->info, 0, sizeof(sim->info));
-  sim->info.n_particles_begin = sim->dist ? sim->n_owned : sim->n;
+  sim->info.n_particles_begin = sim->n;
   const bool lvl = P.level_method != ASPH_LEVEL_NONE;
   if (lvl && !params->use_extended_range_for_level_estimation) {  // simulation.rs:2020
     sim->last_error = "level estimation before advection needs use_extended_range_for_level_estimation";
@@ -280,9 +280,17 @@ static int step_physics(asph_sim* sim, const asph_params* params, float* dt_out)
   // simulation.rs:2034-2057), so only N_2 is built.
   const float f_ext = lvl ? P.f_ext : P.f_near;
   if (sim->dist) {
-    int rc = dist_step_physics(sim);
-    if (rc != ASPH_OK) return rc;
-  } else if (sim->n == 0) {
+    if (lvl) { sim->last_error = "level estimation across GPU slabs"; return ASPH_ERR_UNSUPPORTED; }
+    int rc = dist_begin_step(sim, std::max(f_ext, P.f_near));  // migration + ghost exchange; sim->n = owned + ghosts
+    if (rc != ASPH_OK) { pc_collect(sim); return rc; }
+    sim->info.n_particles_begin = sim->n_owned;
+    if (sim->n_owned == 0) {  // every collective below assumes all ranks take part
+      sim->last_error = "a rank owns no particles (more GPUs than the particle set can be split over)";
+      pc_collect(sim);
+      return ASPH_ERR_INVALID;
+    }
+  }
+  if (sim->n == 0) {
     sim->info.dt = P.max_dt;
   } else {
     pc_begin(sim, ASPH_PC_NEIGHBORHOOD);
@@ -352,7 +360,8 @@ const char* asph_backend_name(void) { return "cuda-sm100a"; }
 
 int asph_set_state(asph_sim* sim, const float* pos, const float* vel, const float* mass, uint64_t n) {
   if (!sim || (n && (!pos || !vel || !mass))) return ASPH_ERR_INVALID;
-  if (n > 0xFFFFFFF0ull) return ASPH_ERR_CAPACITY;
+  if (n > 0x7FFFFFF0ull) return ASPH_ERR_CAPACITY;  // bit 31 of the particle index marks ghosts (multi-GPU)
+  if (sim->dist) { sim->last_error = "asph_set_state on a distributed handle"; return ASPH_ERR_UNSUPPORTED; }
   CUDA_TRY(cudaSetDevice(sim->device));
   if (n > sim->cap) { sim->n = 0; TRY(ensure_capacity(sim, uint32_t(n + n / 4 + 1024))); }
   sim->n = uint32_t(n); sim->n_owned = uint32_t(n);
@@ -410,7 +419,7 @@ int asph_create(const asph_params* params, const float* pos, const float* vel, c
   }
   uint64_t cap = capacity ? capacity : (2 * n + 1024);
   if (cap < n) cap = n;
-  if (cap > 0xFFFFFFF0ull) return fail(ASPH_ERR_CAPACITY);
+  if (cap > 0x7FFFFFF0ull) return fail(ASPH_ERR_CAPACITY);
   int rc = ensure_capacity(sim, uint32_t(cap));
   if (rc != ASPH_OK) return fail(rc);
   rc = pack_params(sim, params);
@@ -426,6 +435,7 @@ void asph_destroy(asph_sim* sim) {
   if (!sim) return;
   cudaSetDevice(sim->device);
   if (sim->stream) cudaStreamSynchronize(sim->stream);
+  dist_destroy(sim);
   for (int b = 0; b < 2; b++) {
     sim->pos[b].release(); sim->vel[b].release(); sim->mass[b].release(); sim->level[b].release(); sim->refid[b].release();
     sim->xv[b].release(); sim->packP[b].release(); sim->front[b].release(); sim->work[b].release();
@@ -474,15 +484,17 @@ int asph_get_field(asph_sim* sim, int field, void* dst, uint64_t bytes) {
   int comps = 1;
   const int eb = field_elem_bytes(field, &comps);
   if (eb == 0) { sim->last_error = "field not available from the CUDA backend"; return ASPH_ERR_UNSUPPORTED; }
-  const uint32_t n = sim->dist ? sim->n_owned : sim->n;
-  const uint64_t need = uint64_t(n) * comps * eb;
+  const uint32_t n_out = sim->dist ? sim->n_owned : sim->n;  // ghosts are not reported
+  const uint32_t n = sim->n;
+  const uint64_t need = uint64_t(n_out) * comps * eb;
   if (bytes < need) return ASPH_ERR_INVALID;
   const bool persistent = field == ASPH_F_POSITION || field == ASPH_F_VELOCITY || field == ASPH_F_MASS || field == ASPH_F_LEVEL;
   if (!persistent && !sim->step_fields_valid) {
     sim->last_error = "per-step field requested before a physics step (or after resampling changed the particle set)";
     return ASPH_ERR_INVALID;
   }
-  if (n == 0) return ASPH_OK;
+  if (n_out == 0) return ASPH_OK;
+  if (sim->dist) TRY(dist_local_map(sim));  // multi-GPU: owned particles in local (sorted) order; asph_get_global_index names them
   // scatter into reference order in scratch (scratch_f holds 2 * cap floats)
   void* tmp = sim->scratch_f.p;
   const int c = sim->cur;

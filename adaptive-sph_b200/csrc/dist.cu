@@ -1,17 +1,642 @@
-// dist.cu — multi-GPU slab decomposition (placeholder until the halo exchange lands)
+// dist.cu — multi-GPU: 1-D slab decomposition of the particle set along x with a one-support-radius ghost halo.
+//
+// One process per GPU (rank r owns the particles with bounds[r] <= x < bounds[r+1]); the processes are tied together
+// by an NCCL communicator whose unique id the host harness broadcasts (asph_comm_unique_id, asph_create_distributed).
+// The reference has no counterpart (single address space); what has to hold is that the N-GPU
+// step computes what the 1-GPU step computes: the neighbour set of every owned particle is complete (ghost width =
+// largest pair support f * h_max), and every pass that reads a neighbour field written by the previous pass sees the
+// owner's value (one halo exchange per such pass: rho, v after the non-pressure forces, a^p and p per Jacobi sweep, ...).
+//
+// Per step (dist_begin_step):  drop last step's ghosts, hand particles that left the slab to the neighbour rank
+// (migration), pick the border particles within the ghost width and send them to the neighbour (ghost exchange),
+// then the ordinary single-GPU sort / grid / neighbour build runs over owned + ghost particles.  Ghosts carry
+// ASPH_GHOST_BIT in refid (refid = global particle index); they are computed like any particle (their results are
+// garbage near the outer edge of the halo and are overwritten by the owner's values) but never counted in reductions.
+// Global scalars: dt (min of the CFL term), the 4 Jacobi statistics per sweep (sum), error flags (max).
+//
+// NCCL is bound at run time (dlopen "libnccl.so.2"): a single-GPU user of the library needs no NCCL at all, and in a
+// process that already loaded torch's NCCL the same copy is used.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstring>
+
 #include "sim.cuh"
-int dist_step_physics(asph_sim* sim) {
-  sim->last_error = "multi-GPU step not built yet";
-  return ASPH_ERR_UNSUPPORTED;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr int kHistBins = 8192;
+
+// host copy of sim.cuh's dec_f (order-preserving float encoding used with atomicMin / atomicMax)
+inline float host_dec_f(uint32_t e) {
+  const uint32_t u = (e & 0x80000000u) ? (e & 0x7fffffffu) : ~e;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
 }
-extern "C" {
-int asph_comm_unique_id(uint8_t*) { return ASPH_ERR_UNSUPPORTED; }
-int asph_create_distributed(const asph_params*, const float*, const float*, const float*, const uint32_t*, uint64_t, uint64_t,
-                            const asph_boundary*, const asph_split_patterns*, int, uint64_t, const uint8_t*, int, int, int,
-                            asph_sim**) { return ASPH_ERR_UNSUPPORTED; }
-int asph_get_global_index(asph_sim* sim, uint32_t* dst, uint64_t cap) {
-  if (!sim || cap < sim->n) return ASPH_ERR_INVALID;
-  for (uint32_t i = 0; i < sim->n; i++) dst[i] = i;
+
+struct Nccl {
+  void* so = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+Nccl& nccl() {
+  static Nccl api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    api.so = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (api.so) break;
+  }
+  if (!api.so) return api;
+  bool all = true;
+  auto sym = [&](const char* s) { void* p = dlsym(api.so, s); if (!p) all = false; return p; };
+  api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+  api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+  api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+  api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+  api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+  api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+  api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+  api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+  api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+  api.ok = all;
+  return api;
+}
+
+// device words gathered over all ranks once per phase
+enum { W_STAY = 0, W_LEFT = 1, W_RIGHT = 2, W_HMAX = 3, W_GLEFT = 4, W_GRIGHT = 5, W_MINX = 6, W_MAXX = 7, W_COUNT = 8 };
+
+}  // namespace
+
+struct DistState {
+  int rank = 0, nranks = 1;
+  ncclComm_t comm = nullptr;
+  uint64_t n_global = 0;
+  std::vector<float> bounds;  // nranks + 1 entries; bounds[0] = -inf, bounds[nranks] = +inf
+  bool rebalance_due = true, full_migration = true;
+  uint64_t steps = 0;
+  float ghost_w = 0.f;
+  uint32_t cap_h = 0;         // halo / migration buffer capacity in particles per side
+  uint32_t n_send[2] = {0, 0}, n_recv[2] = {0, 0};  // ghost halo sizes; [0] = towards / from rank-1, [1] = rank+1
+  DevBuf<uint32_t> send_idx, recv_idx;  // sorted particle indices, left part then right part
+  DevBuf<uint32_t> slot[2];             // per pre-sort owned particle: position in the send list of that side or kNone
+  DevBuf<float4> sendbuf, recvbuf;      // 2 float4 per particle and side
+  DevBuf<uint32_t> words, gather, hist;
+  uint32_t* gather_host = nullptr;      // pinned: nranks * W_COUNT words, or the histogram
+  bool map_valid = false;
+  uint64_t halo_calls = 0, halo_bytes = 0;
+};
+
+namespace {
+
+#define NCCL_TRY(x)                                                                                   \
+  do {                                                                                                \
+    ncclResult_t r__ = (x);                                                                           \
+    if (r__ != ncclSuccess) {                                                                         \
+      sim->last_error = std::string(#x) + ": " + (nccl().GetErrorString ? nccl().GetErrorString(r__) : "nccl error"); \
+      return ASPH_ERR_NCCL;                                                                           \
+    }                                                                                                 \
+  } while (0)
+
+__global__ void k_words_reset(uint32_t* w) {
+  w[W_STAY] = 0; w[W_LEFT] = 0; w[W_RIGHT] = 0; w[W_HMAX] = 0; w[W_GLEFT] = 0; w[W_GRIGHT] = 0;
+  w[W_MINX] = 0xFFFFFFFFu; w[W_MAXX] = 0;
+}
+
+// Owned particles are partitioned into stay (compacted into the other buffer) / leave-left / leave-right (packed into
+// the send buffer); last step's ghosts are dropped.  Warp-aggregated appends: the arrival order is arbitrary, the
+// cell sort orders by global index afterwards.  Also h_max and the x-extent of the owned particles.
+__global__ void __launch_bounds__(kThreads)
+k_owner_split(uint32_t n, const float2* __restrict__ pos, const float2* __restrict__ vel, const float* __restrict__ mass,
+              const float* __restrict__ level, const uint32_t* __restrict__ refid, float lo, float hi, float rho0,
+              float2* __restrict__ pos_o, float2* __restrict__ vel_o, float* __restrict__ mass_o, float* __restrict__ level_o,
+              uint32_t* __restrict__ refid_o, float4* __restrict__ send_l, float4* __restrict__ send_r, uint32_t cap_h,
+              uint32_t* __restrict__ w) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  int dest = -1;  // -1 none (out of range or ghost), 0 stay, 1 left, 2 right
+  float2 x = make_float2(0.f, 0.f), v = x;
+  float m = 0.f, lv = 0.f;
+  uint32_t id = 0;
+  if (i < n) {
+    id = refid[i];
+    if (!(id & ASPH_GHOST_BIT)) {
+      x = pos[i]; v = vel[i]; m = mass[i]; lv = level[i];
+      dest = x.x < lo ? 1 : (x.x >= hi ? 2 : 0);
+    }
+  }
+  float hm = dest >= 0 ? h_from_mass(m, rho0) : 0.f;
+  float mnx = dest >= 0 ? x.x : __int_as_float(0x7f800000), mxx = dest >= 0 ? x.x : -__int_as_float(0x7f800000);
+  for (int o = 16; o > 0; o >>= 1) {
+    hm = fmaxf(hm, __shfl_xor_sync(0xffffffffu, hm, o));
+    mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+    mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+  }
+  if (lane == 0 && hm > 0.f) { atomicMax(&w[W_HMAX], enc_f(hm)); atomicMin(&w[W_MINX], enc_f(mnx)); atomicMax(&w[W_MAXX], enc_f(mxx)); }
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const unsigned int mask = __ballot_sync(0xffffffffu, dest == d);
+    if (!mask) continue;
+    uint32_t base = 0;
+    const int leader = __ffs(mask) - 1;
+    if (int(lane) == leader) base = atomicAdd(&w[d], uint32_t(__popc(mask)));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (dest != d) continue;
+    const uint32_t k = base + uint32_t(__popc(mask & ((1u << lane) - 1u)));
+    if (d == 0) {
+      pos_o[k] = x; vel_o[k] = v; mass_o[k] = m; level_o[k] = lv; refid_o[k] = id;
+    } else if (k < cap_h) {
+      float4* dst = (d == 1 ? send_l : send_r) + 2 * size_t(k);
+      dst[0] = make_float4(x.x, x.y, v.x, v.y);
+      dst[1] = make_float4(m, lv, __uint_as_float(id), 0.f);
+    }
+  }
+}
+
+// Border particles within the ghost width of a slab face: packed for the neighbour and remembered by slot.
+__global__ void __launch_bounds__(kThreads)
+k_ghost_select(uint32_t n_owned, const float2* __restrict__ pos, const float2* __restrict__ vel, const float* __restrict__ mass,
+               const float* __restrict__ level, const uint32_t* __restrict__ refid, float left_below, float right_from,
+               uint32_t* __restrict__ slot_l, uint32_t* __restrict__ slot_r, float4* __restrict__ send_l, float4* __restrict__ send_r,
+               uint32_t cap_h, uint32_t* __restrict__ w) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  bool to_l = false, to_r = false;
+  float2 x = make_float2(0.f, 0.f);
+  if (i < n_owned) { x = pos[i]; to_l = x.x < left_below; to_r = x.x >= right_from; }
+#pragma unroll
+  for (int d = 0; d < 2; d++) {
+    const bool mine = d == 0 ? to_l : to_r;
+    const unsigned int mask = __ballot_sync(0xffffffffu, mine);
+    uint32_t k = kNone;
+    if (mask) {
+      uint32_t base = 0;
+      const int leader = __ffs(mask) - 1;
+      if (int(lane) == leader) base = atomicAdd(&w[d == 0 ? W_GLEFT : W_GRIGHT], uint32_t(__popc(mask)));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (mine) {
+        k = base + uint32_t(__popc(mask & ((1u << lane) - 1u)));
+        if (k < cap_h) {
+          const float2 v = vel[i];
+          float4* dst = (d == 0 ? send_l : send_r) + 2 * size_t(k);
+          dst[0] = make_float4(x.x, x.y, v.x, v.y);
+          dst[1] = make_float4(mass[i], level[i], __uint_as_float(refid[i]), 0.f);
+        }
+      }
+    }
+    if (i < n_owned) (d == 0 ? slot_l : slot_r)[i] = k;
+  }
+}
+
+__global__ void k_append(uint32_t count, const float4* __restrict__ recv, uint32_t at, uint32_t idbits, float2* __restrict__ pos,
+                         float2* __restrict__ vel, float* __restrict__ mass, float* __restrict__ level, uint32_t* __restrict__ refid) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const float4 a = recv[2 * size_t(k)], b = recv[2 * size_t(k) + 1];
+  pos[at + k] = make_float2(a.x, a.y); vel[at + k] = make_float2(a.z, a.w);
+  mass[at + k] = b.x; level[at + k] = b.y; refid[at + k] = __float_as_uint(b.z) | idbits;
+}
+
+// After the sort: where did each halo particle end up?  order[s] = pre-sort index of sorted particle s.
+__global__ void k_build_maps(uint32_t n, const uint32_t* __restrict__ order, uint32_t n_owned, uint32_t recv_l,
+                             const uint32_t* __restrict__ slot_l, const uint32_t* __restrict__ slot_r, uint32_t send_l,
+                             uint32_t* __restrict__ send_idx, uint32_t* __restrict__ recv_idx) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const uint32_t src = order[s];
+  if (src >= n_owned) { recv_idx[src - n_owned] = s; return; }  // ghosts were appended left part first
+  const uint32_t a = slot_l[src], b = slot_r[src];
+  if (a != kNone) send_idx[a] = s;
+  if (b != kNone) send_idx[send_l + b] = s;
+  (void)recv_l;
+}
+
+// field[idx[k]] -> buf[k] (words 32-bit words per element); P0/P1 + ctl: pick the pressure pack by sweep parity
+__global__ void k_pack(uint32_t count, int words, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ f0,
+                       const uint32_t* __restrict__ f1, const StepCtl* __restrict__ ctl, uint32_t* __restrict__ buf) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count * uint32_t(words)) return;
+  const uint32_t* __restrict__ f = (ctl && (ctl->solver.sweeps & 1)) ? f1 : f0;
+  const uint32_t k = t / uint32_t(words), c = t - k * uint32_t(words);
+  buf[t] = f[size_t(idx[k]) * words + c];
+}
+__global__ void k_unpack(uint32_t count, int words, const uint32_t* __restrict__ idx, uint32_t* __restrict__ f0,
+                         uint32_t* __restrict__ f1, const StepCtl* __restrict__ ctl, const uint32_t* __restrict__ buf) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count * uint32_t(words)) return;
+  uint32_t* __restrict__ f = (ctl && (ctl->solver.sweeps & 1)) ? f1 : f0;
+  const uint32_t k = t / uint32_t(words), c = t - k * uint32_t(words);
+  f[size_t(idx[k]) * words + c] = buf[t];
+}
+
+__global__ void k_hist(uint32_t n, const float2* __restrict__ pos, const uint32_t* __restrict__ refid, float x0, float inv_w,
+                       uint32_t* __restrict__ hist) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || (refid[i] & ASPH_GHOST_BIT)) return;
+  const int b = min(kHistBins - 1, max(0, int((pos[i].x - x0) * inv_w)));
+  atomicAdd(&hist[b], 1u);
+}
+
+__global__ void k_owned_flag(uint32_t n, const uint32_t* __restrict__ refid, uint32_t* __restrict__ flag) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (refid[i] & ASPH_GHOST_BIT) ? 0u : 1u;
+}
+__global__ void k_mask_ghost_slots(uint32_t n, const uint32_t* __restrict__ refid, uint32_t* __restrict__ map) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (refid[i] & ASPH_GHOST_BIT)) map[i] = kNone;
+}
+__global__ void k_global_index(uint32_t n, const uint32_t* __restrict__ refid, const uint32_t* __restrict__ map, uint32_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && map[i] != kNone) out[map[i]] = refid[i] & ~ASPH_GHOST_BIT;
+}
+
+int gather_words(asph_sim* sim) {  // all ranks' phase words -> D->gather_host
+  DistState* D = sim->dist;
+  NCCL_TRY(nccl().AllGather(D->words.p, D->gather.p, W_COUNT, ncclUint32, D->comm, sim->stream));
+  CUDA_TRY(cudaMemcpyAsync(D->gather_host, D->gather.p, size_t(D->nranks) * W_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, sim->stream));
+  CUDA_TRY(cudaStreamSynchronize(sim->stream));
   return ASPH_OK;
 }
+
+int ensure_halo_capacity(asph_sim* sim, uint32_t want) {
+  DistState* D = sim->dist;
+  if (want <= D->cap_h) return ASPH_OK;
+  D->cap_h = want;
+  CUDA_TRY(D->sendbuf.ensure(size_t(want) * 4)); CUDA_TRY(D->recvbuf.ensure(size_t(want) * 4));
+  CUDA_TRY(D->send_idx.ensure(size_t(want) * 2)); CUDA_TRY(D->recv_idx.ensure(size_t(want) * 2));
+  return ASPH_OK;
 }
+
+// payloads of 2 float4 per particle to / from the two neighbour ranks; receives land contiguously (left part first)
+int exchange_particles(asph_sim* sim, uint32_t out_l, uint32_t out_r, uint32_t in_l, uint32_t in_r) {
+  DistState* D = sim->dist;
+  if (!(out_l | out_r | in_l | in_r)) return ASPH_OK;
+  const Nccl& N = nccl();
+  NCCL_TRY(N.GroupStart());
+  if (out_l) NCCL_TRY(N.Send(D->sendbuf.p, size_t(out_l) * 8, ncclFloat, D->rank - 1, D->comm, sim->stream));
+  if (out_r) NCCL_TRY(N.Send(D->sendbuf.p + 2 * size_t(D->cap_h), size_t(out_r) * 8, ncclFloat, D->rank + 1, D->comm, sim->stream));
+  if (in_l) NCCL_TRY(N.Recv(D->recvbuf.p, size_t(in_l) * 8, ncclFloat, D->rank - 1, D->comm, sim->stream));
+  if (in_r) NCCL_TRY(N.Recv(D->recvbuf.p + 2 * size_t(in_l), size_t(in_r) * 8, ncclFloat, D->rank + 1, D->comm, sim->stream));
+  NCCL_TRY(N.GroupEnd());
+  return ASPH_OK;
+}
+
+// Slab faces from the global x-histogram of the owned particles: equal particle counts per rank.
+int rebalance(asph_sim* sim) {
+  DistState* D = sim->dist;
+  const int R = D->nranks;
+  D->bounds.assign(size_t(R) + 1, 0.f);
+  D->bounds[0] = -INFINITY; D->bounds[R] = INFINITY;
+  D->rebalance_due = false;
+  D->full_migration = true;
+  if (R == 1) return ASPH_OK;
+  cudaStream_t st = sim->stream;
+  const int c = sim->cur;
+  const uint32_t n = sim->n;
+  // global x-extent: run the owner split's statistics only (a split with lo = -inf, hi = +inf moves nothing)
+  k_words_reset<<<1, 1, 0, st>>>(D->words.p);
+  LAUNCH_CHECK();
+  if (n) {
+    k_owner_split<<<(n + kThreads - 1) / kThreads, kThreads, 0, st>>>(
+        n, sim->pos[c].p, sim->vel[c].p, sim->mass[c].p, sim->level[c].p, sim->refid[c].p, -INFINITY, INFINITY, sim->pp.rest_density,
+        sim->pos[1 - c].p, sim->vel[1 - c].p, sim->mass[1 - c].p, sim->level[1 - c].p, sim->refid[1 - c].p, D->sendbuf.p,
+        D->sendbuf.p + 2 * size_t(D->cap_h), D->cap_h, D->words.p);
+    LAUNCH_CHECK();
+  }
+  TRY(gather_words(sim));
+  float gmin = INFINITY, gmax = -INFINITY;
+  uint64_t total = 0;
+  for (int r = 0; r < R; r++) {
+    const uint32_t* w = D->gather_host + size_t(r) * W_COUNT;
+    if (w[W_STAY] == 0) continue;
+    total += w[W_STAY];
+    gmin = std::min(gmin, host_dec_f(w[W_MINX])); gmax = std::max(gmax, host_dec_f(w[W_MAXX]));
+  }
+  if (total == 0 || !(gmax > gmin)) {  // nothing to split by position: equal-width faces are as good as any
+    for (int r = 1; r < R; r++) D->bounds[r] = (total == 0 ? 0.f : gmin) + float(r);
+    return ASPH_OK;
+  }
+  const float binw = (gmax - gmin) / float(kHistBins);
+  CUDA_TRY(cudaMemsetAsync(D->hist.p, 0, kHistBins * sizeof(uint32_t), st));
+  if (n) {
+    k_hist<<<(n + kThreads - 1) / kThreads, kThreads, 0, st>>>(n, sim->pos[c].p, sim->refid[c].p, gmin, 1.f / binw, D->hist.p);
+    LAUNCH_CHECK();
+  }
+  NCCL_TRY(nccl().AllReduce(D->hist.p, D->hist.p, kHistBins, ncclUint32, ncclSum, D->comm, st));
+  std::vector<uint32_t> hist(kHistBins);
+  CUDA_TRY(cudaMemcpyAsync(hist.data(), D->hist.p, kHistBins * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  uint64_t cum = 0;
+  int b = 0;
+  for (int r = 1; r < R; r++) {
+    const uint64_t target = total * uint64_t(r) / uint64_t(R);
+    while (b < kHistBins && cum + hist[b] < target) { cum += hist[b]; b++; }
+    const float frac = (b < kHistBins && hist[b] > 0) ? float(double(target - cum) / double(hist[b])) : 0.f;
+    D->bounds[r] = gmin + (float(b) + frac) * binw;
+  }
+  return ASPH_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// step hooks
+// ------------------------------------------------------------------------------------------------------------
+int dist_begin_step(asph_sim* sim, float f_search) {
+  DistState* D = sim->dist;
+  const int R = D->nranks, r = D->rank;
+  cudaStream_t st = sim->stream;
+  D->map_valid = false;
+  if (D->steps > 0 && (D->steps % 64) == 0 && R > 1) {  // imbalance check on the counts every rank already holds
+    uint64_t total = 0, worst = 0;
+    for (int k = 0; k < R; k++) { const uint64_t c = D->gather_host[size_t(k) * W_COUNT + W_STAY]; total += c; worst = std::max(worst, c); }
+    if (total > 0 && double(worst) * R > 1.10 * double(total)) D->rebalance_due = true;
+  }
+  D->steps++;
+  if (D->rebalance_due) TRY(rebalance(sim));
+  const float lo = D->bounds[r], hi = D->bounds[r + 1];
+  float hmax_g = 0.f;
+  // ---- migration: one round normally (a particle moves less than a slab per step); after a rebalance as many
+  //      rounds as it takes for every particle to reach its owner, one rank per round
+  for (int round = 0; round < R + 1; round++) {
+    const int c = sim->cur;
+    const uint32_t n = sim->n;
+    uint32_t out_l = 0, out_r = 0, in_l = 0, in_r = 0, n_stay = 0;
+    uint64_t moved = 0;
+    for (;;) {
+      k_words_reset<<<1, 1, 0, st>>>(D->words.p);
+      LAUNCH_CHECK();
+      if (n) {
+        k_owner_split<<<(n + kThreads - 1) / kThreads, kThreads, 0, st>>>(
+            n, sim->pos[c].p, sim->vel[c].p, sim->mass[c].p, sim->level[c].p, sim->refid[c].p, lo, hi, sim->pp.rest_density,
+            sim->pos[1 - c].p, sim->vel[1 - c].p, sim->mass[1 - c].p, sim->level[1 - c].p, sim->refid[1 - c].p, D->sendbuf.p,
+            D->sendbuf.p + 2 * size_t(D->cap_h), D->cap_h, D->words.p);
+        LAUNCH_CHECK();
+      }
+      TRY(gather_words(sim));
+      uint32_t need = 0;
+      moved = 0; hmax_g = 0.f;
+      for (int k = 0; k < R; k++) {
+        const uint32_t* w = D->gather_host + size_t(k) * W_COUNT;
+        need = std::max(need, std::max(w[W_LEFT], w[W_RIGHT]));
+        moved += uint64_t(w[W_LEFT]) + w[W_RIGHT];
+        if (w[W_HMAX]) hmax_g = std::max(hmax_g, host_dec_f(w[W_HMAX]));
+      }
+      if (need <= D->cap_h) break;
+      TRY(ensure_halo_capacity(sim, need + need / 2));  // same decision on every rank (all see all counts); split again
+    }
+    const uint32_t* me = D->gather_host + size_t(r) * W_COUNT;
+    n_stay = me[W_STAY]; out_l = me[W_LEFT]; out_r = me[W_RIGHT];
+    in_l = r > 0 ? D->gather_host[size_t(r - 1) * W_COUNT + W_RIGHT] : 0u;
+    in_r = r < R - 1 ? D->gather_host[size_t(r + 1) * W_COUNT + W_LEFT] : 0u;
+    sim->cur = 1 - c;
+    sim->n = n_stay;
+    const uint64_t n_new = uint64_t(n_stay) + in_l + in_r;
+    if (n_new + 2 * uint64_t(D->cap_h) > sim->cap) TRY(ensure_capacity(sim, uint32_t(std::min<uint64_t>(n_new + n_new / 4 + 2 * uint64_t(D->cap_h) + 1024, 0x7FFFFFF0ull))));
+    TRY(exchange_particles(sim, out_l, out_r, in_l, in_r));
+    if (in_l + in_r) {
+      k_append<<<(in_l + in_r + kThreads - 1) / kThreads, kThreads, 0, st>>>(in_l + in_r, D->recvbuf.p, n_stay, 0u, sim->pos[sim->cur].p,
+                                                                             sim->vel[sim->cur].p, sim->mass[sim->cur].p,
+                                                                             sim->level[sim->cur].p, sim->refid[sim->cur].p);
+      LAUNCH_CHECK();
+    }
+    sim->n = uint32_t(n_new);
+    sim->n_owned = sim->n;
+    if (!D->full_migration || moved == 0) break;
+  }
+  D->full_migration = false;
+  // ---- ghost exchange
+  const float W = f_search * hmax_g * 1.0001f;
+  D->ghost_w = W;
+  for (int k = 1; k + 1 < R; k++) {
+    if (!(D->bounds[k + 1] - D->bounds[k] >= W)) {
+      sim->last_error = "a slab is narrower than the ghost width (too many GPUs for this particle size)";
+      return ASPH_ERR_INVALID;
+    }
+  }
+  const int c = sim->cur;
+  const uint32_t no = sim->n_owned;
+  CUDA_TRY(D->slot[0].ensure(sim->cap)); CUDA_TRY(D->slot[1].ensure(sim->cap));
+  uint32_t gs_l = 0, gs_r = 0, gr_l = 0, gr_r = 0;
+  for (;;) {
+    k_words_reset<<<1, 1, 0, st>>>(D->words.p);
+    LAUNCH_CHECK();
+    if (no) {
+      k_ghost_select<<<(no + kThreads - 1) / kThreads, kThreads, 0, st>>>(
+          no, sim->pos[c].p, sim->vel[c].p, sim->mass[c].p, sim->level[c].p, sim->refid[c].p, r > 0 ? lo + W : -INFINITY,
+          r < R - 1 ? hi - W : INFINITY, D->slot[0].p, D->slot[1].p, D->sendbuf.p, D->sendbuf.p + 2 * size_t(D->cap_h), D->cap_h, D->words.p);
+      LAUNCH_CHECK();
+    }
+    TRY(gather_words(sim));
+    uint32_t need = 0;
+    for (int k = 0; k < R; k++) {
+      const uint32_t* w = D->gather_host + size_t(k) * W_COUNT;
+      need = std::max(need, std::max(w[W_GLEFT], w[W_GRIGHT]));
+    }
+    if (need <= D->cap_h) break;
+    TRY(ensure_halo_capacity(sim, need + need / 2));
+  }
+  {
+    const uint32_t* me = D->gather_host + size_t(r) * W_COUNT;
+    gs_l = me[W_GLEFT]; gs_r = me[W_GRIGHT];
+    gr_l = r > 0 ? D->gather_host[size_t(r - 1) * W_COUNT + W_GRIGHT] : 0u;
+    gr_r = r < R - 1 ? D->gather_host[size_t(r + 1) * W_COUNT + W_GLEFT] : 0u;
+    // keep the owned count in the gathered words for the imbalance check
+    for (int k = 0; k < R; k++) D->gather_host[size_t(k) * W_COUNT + W_STAY] = (k == r) ? no : D->gather_host[size_t(k) * W_COUNT + W_STAY];
+  }
+  const uint64_t n_all = uint64_t(no) + gr_l + gr_r;
+  if (n_all > sim->cap) TRY(ensure_capacity(sim, uint32_t(std::min<uint64_t>(n_all + n_all / 4 + 1024, 0x7FFFFFF0ull))));
+  TRY(exchange_particles(sim, gs_l, gs_r, gr_l, gr_r));
+  if (gr_l + gr_r) {
+    k_append<<<(gr_l + gr_r + kThreads - 1) / kThreads, kThreads, 0, st>>>(gr_l + gr_r, D->recvbuf.p, no, ASPH_GHOST_BIT, sim->pos[sim->cur].p,
+                                                                           sim->vel[sim->cur].p, sim->mass[sim->cur].p, sim->level[sim->cur].p,
+                                                                           sim->refid[sim->cur].p);
+    LAUNCH_CHECK();
+  }
+  sim->n = uint32_t(n_all);
+  D->n_send[0] = gs_l; D->n_send[1] = gs_r; D->n_recv[0] = gr_l; D->n_recv[1] = gr_r;
+  return ASPH_OK;
+}
+
+int dist_allreduce_cfl(asph_sim* sim) {
+  DistState* D = sim->dist;
+  if (D->nranks == 1) return ASPH_OK;
+  NCCL_TRY(nccl().AllReduce(&sim->ctl->cfl_enc, &sim->ctl->cfl_enc, 1, ncclUint32, ncclMin, D->comm, sim->stream));
+  return ASPH_OK;
+}
+
+int dist_after_sort(asph_sim* sim) {
+  DistState* D = sim->dist;
+  const uint32_t n = sim->n;
+  if (n == 0 || D->nranks == 1) return ASPH_OK;
+  k_build_maps<<<(n + kThreads - 1) / kThreads, kThreads, 0, sim->stream>>>(n, sim->order.p, sim->n_owned, D->n_recv[0], D->slot[0].p, D->slot[1].p,
+                                                                           D->n_send[0], D->send_idx.p, D->recv_idx.p);
+  LAUNCH_CHECK();
+  return ASPH_OK;
+}
+
+static int halo_impl(asph_sim* sim, void* f0, void* f1, const StepCtl* ctl, int elem_bytes) {
+  DistState* D = sim->dist;
+  if (D->nranks == 1) return ASPH_OK;
+  const Nccl& N = nccl();
+  cudaStream_t st = sim->stream;
+  const int words = elem_bytes / 4;
+  const uint32_t ns = D->n_send[0] + D->n_send[1], nr = D->n_recv[0] + D->n_recv[1];
+  uint32_t* sb = reinterpret_cast<uint32_t*>(D->sendbuf.p);
+  uint32_t* rb = reinterpret_cast<uint32_t*>(D->recvbuf.p);
+  if (ns) {
+    k_pack<<<(ns * words + kThreads - 1) / kThreads, kThreads, 0, st>>>(ns, words, D->send_idx.p, (const uint32_t*)f0, (const uint32_t*)f1, ctl, sb);
+    LAUNCH_CHECK();
+  }
+  if (ns | nr) {
+    NCCL_TRY(N.GroupStart());
+    if (D->n_send[0]) NCCL_TRY(N.Send(sb, size_t(D->n_send[0]) * words, ncclFloat, D->rank - 1, D->comm, st));
+    if (D->n_send[1]) NCCL_TRY(N.Send(sb + size_t(D->n_send[0]) * words, size_t(D->n_send[1]) * words, ncclFloat, D->rank + 1, D->comm, st));
+    if (D->n_recv[0]) NCCL_TRY(N.Recv(rb, size_t(D->n_recv[0]) * words, ncclFloat, D->rank - 1, D->comm, st));
+    if (D->n_recv[1]) NCCL_TRY(N.Recv(rb + size_t(D->n_recv[0]) * words, size_t(D->n_recv[1]) * words, ncclFloat, D->rank + 1, D->comm, st));
+    NCCL_TRY(N.GroupEnd());
+  }
+  if (nr) {
+    k_unpack<<<(nr * words + kThreads - 1) / kThreads, kThreads, 0, st>>>(nr, words, D->recv_idx.p, (uint32_t*)f0, (uint32_t*)f1, ctl, rb);
+    LAUNCH_CHECK();
+  }
+  D->halo_calls++;
+  D->halo_bytes += uint64_t(ns) * elem_bytes;
+  return ASPH_OK;
+}
+
+int dist_halo(asph_sim* sim, void* field, int elem_bytes) { return halo_impl(sim, field, field, nullptr, elem_bytes); }
+int dist_halo_pressure(asph_sim* sim) { return halo_impl(sim, sim->packP[0].p, sim->packP[1].p, sim->ctl, 16); }
+
+int dist_solver_reduce(asph_sim* sim) {
+  DistState* D = sim->dist;
+  if (D->nranks == 1) return ASPH_OK;
+  NCCL_TRY(nccl().AllReduce(sim->ctl->solver.partial, sim->ctl->solver.partial, 4, ncclDouble, ncclSum, D->comm, sim->stream));
+  return ASPH_OK;
+}
+
+int dist_reduce_flags(asph_sim* sim, bool) {
+  DistState* D = sim->dist;
+  if (D->nranks == 1) return ASPH_OK;
+  NCCL_TRY(nccl().AllReduce(&sim->ctl->error_flags, &sim->ctl->error_flags, 1, ncclUint32, ncclMax, D->comm, sim->stream));
+  return ASPH_OK;
+}
+
+int dist_local_map(asph_sim* sim) {
+  DistState* D = sim->dist;
+  if (D->map_valid) return ASPH_OK;
+  const uint32_t n = sim->n;
+  if (n) {
+    cudaStream_t st = sim->stream;
+    const uint32_t blocks = (n + kThreads - 1) / kThreads;
+    const uint32_t* refid = sim->refid[sim->cur].p;
+    k_owned_flag<<<blocks, kThreads, 0, st>>>(n, refid, sim->scratch_u[2].p);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(D->words.p, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    TRY(launch_exclusive_scan(sim, sim->scratch_u[2].p, sim->scratch_u[3].p, D->words.p, 0, n));
+    k_mask_ghost_slots<<<blocks, kThreads, 0, st>>>(n, refid, sim->scratch_u[3].p);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  D->map_valid = true;
+  return ASPH_OK;
+}
+
+void dist_destroy(asph_sim* sim) {
+  DistState* D = sim->dist;
+  if (!D) return;
+  if (D->comm && nccl().CommDestroy) nccl().CommDestroy(D->comm);
+  D->send_idx.release(); D->recv_idx.release(); D->slot[0].release(); D->slot[1].release();
+  D->sendbuf.release(); D->recvbuf.release(); D->words.release(); D->gather.release(); D->hist.release();
+  if (D->gather_host) cudaFreeHost(D->gather_host);
+  delete D;
+  sim->dist = nullptr;
+}
+
+extern "C" {
+
+int asph_comm_unique_id(uint8_t id_out[128]) {
+  if (!id_out) return ASPH_ERR_INVALID;
+  if (!nccl().ok) return ASPH_ERR_NCCL;
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  if (nccl().GetUniqueId(&id) != ncclSuccess) return ASPH_ERR_NCCL;
+  memcpy(id_out, &id, 128);
+  return ASPH_OK;
+}
+
+int asph_create_distributed(const asph_params* params, const float* pos, const float* vel, const float* mass, const uint32_t* global_index,
+                            uint64_t n_local, uint64_t n_global, const asph_boundary* boundary, const asph_split_patterns* split,
+                            int counters_enabled, uint64_t capacity, const uint8_t nccl_id[128], int rank, int n_ranks, int device,
+                            asph_sim** out) {
+  if (!out) return ASPH_ERR_INVALID;
+  *out = nullptr;
+  if (!nccl_id || rank < 0 || n_ranks < 1 || rank >= n_ranks || n_global >= 0x7FFFFFF0ull || (n_local && !global_index)) return ASPH_ERR_INVALID;
+  if (!nccl().ok) return ASPH_ERR_NCCL;
+  if (device >= 0) {
+    char buf[32];
+    snprintf(buf, sizeof buf, "%d", device);
+    setenv("ASPH_DEVICE", buf, 1);
+  }
+  uint64_t cap = capacity ? capacity : (n_local + n_local / 2 + 65536);
+  asph_sim* sim = nullptr;
+  int rc = asph_create(params, pos, vel, mass, n_local, boundary, split, counters_enabled, cap, &sim);
+  if (rc != ASPH_OK) return rc;
+  DistState* D = new DistState();
+  sim->dist = D;
+  D->rank = rank; D->nranks = n_ranks; D->n_global = n_global;
+  auto fail = [&](int code) { asph_destroy(sim); return code; };
+  if (n_local) {  // refid = global particle index
+    if (cudaMemcpy(sim->refid[sim->cur].p, global_index, n_local * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) return fail(ASPH_ERR_CUDA);
+  }
+  ncclUniqueId id;
+  memcpy(&id, nccl_id, 128);
+  if (nccl().CommInitRank(&D->comm, n_ranks, id, rank) != ncclSuccess) { D->comm = nullptr; return fail(ASPH_ERR_NCCL); }
+  if (D->words.ensure(W_COUNT) != cudaSuccess || D->gather.ensure(size_t(n_ranks) * W_COUNT) != cudaSuccess ||
+      D->hist.ensure(kHistBins) != cudaSuccess ||
+      cudaMallocHost((void**)&D->gather_host, std::max<size_t>(size_t(n_ranks) * W_COUNT, 16) * sizeof(uint32_t)) != cudaSuccess)
+    return fail(ASPH_ERR_CUDA);
+  memset(D->gather_host, 0, std::max<size_t>(size_t(n_ranks) * W_COUNT, 16) * sizeof(uint32_t));
+  if (ensure_halo_capacity(sim, uint32_t(std::max<uint64_t>(1u << 16, cap / 8))) != ASPH_OK) return fail(ASPH_ERR_CUDA);
+  *out = sim;
+  return ASPH_OK;
+}
+
+int asph_get_global_index(asph_sim* sim, uint32_t* dst, uint64_t cap) {
+  if (!sim || !dst) return ASPH_ERR_INVALID;
+  const uint32_t no = sim->dist ? sim->n_owned : sim->n;
+  if (cap < no) return ASPH_ERR_INVALID;
+  if (no == 0) return ASPH_OK;
+  CUDA_TRY(cudaSetDevice(sim->device));
+  const uint32_t n = sim->n;
+  uint32_t* tmp = reinterpret_cast<uint32_t*>(sim->scratch_f.p);
+  if (sim->dist) {
+    TRY(dist_local_map(sim));
+    k_global_index<<<(n + kThreads - 1) / kThreads, kThreads, 0, sim->stream>>>(n, sim->refid[sim->cur].p, sim->scratch_u[3].p, tmp);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(dst, tmp, size_t(no) * sizeof(uint32_t), cudaMemcpyDeviceToHost, sim->stream));
+    CUDA_TRY(cudaStreamSynchronize(sim->stream));
+  } else {
+    for (uint32_t i = 0; i < no; i++) dst[i] = i;  // read-backs of a single-GPU handle are in reference order already
+  }
+  return ASPH_OK;
+}
+
+}  // extern "C"

@@ -209,14 +209,22 @@ __global__ void k_scatter(uint32_t n, const uint32_t* __restrict__ key, const ui
   order[cellstart[k] + c - 1u] = i;
 }
 // make the counting sort stable (deterministic): ascending source index inside each cell
-__global__ void k_sort_cells(const StepCtl* __restrict__ ctl, const uint32_t* __restrict__ cellstart, uint32_t* __restrict__ order) {
+// gid != nullptr (multi-GPU): ascending global particle index instead — owned particles and ghosts arrive in arbitrary
+// order, the global index makes the sorted order (and with it every fp32 sum) reproducible
+__global__ void k_sort_cells(const StepCtl* __restrict__ ctl, const uint32_t* __restrict__ cellstart, uint32_t* __restrict__ order,
+                             const uint32_t* __restrict__ gid) {
   const uint32_t total = ctl->total_cells;
   for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < total; c += gridDim.x * blockDim.x) {
     uint32_t s = cellstart[c], e = cellstart[c + 1];
     for (uint32_t a = s + 1; a < e; a++) {
       uint32_t v = order[a];
       uint32_t b = a;
-      while (b > s && order[b - 1] > v) { order[b] = order[b - 1]; b--; }
+      if (gid) {
+        const uint32_t kv = gid[v] & ~ASPH_GHOST_BIT;
+        while (b > s && (gid[order[b - 1]] & ~ASPH_GHOST_BIT) > kv) { order[b] = order[b - 1]; b--; }
+      } else {
+        while (b > s && order[b - 1] > v) { order[b] = order[b - 1]; b--; }
+      }
       order[b] = v;
     }
   }
@@ -241,6 +249,7 @@ __global__ void k_reorder(uint32_t n, const uint32_t* __restrict__ order, const 
 }  // namespace
 
 int sync_ctl(asph_sim* sim) {
+  if (sim->dist) TRY(dist_reduce_flags(sim, false));  // every rank sees the same error flags => the same control flow
   CUDA_TRY(cudaMemcpyAsync(sim->ctl_host, sim->ctl, sizeof(StepCtl), cudaMemcpyDeviceToHost, sim->stream));
   CUDA_TRY(cudaStreamSynchronize(sim->stream));
   return ASPH_OK;
@@ -319,6 +328,7 @@ int launch_sort_and_grid(asph_sim* sim, float f_search) {
   const int c = sim->cur;
   k_prepare<<<blocks, kThreads, 0, st>>>(n, sim->pos[c].p, sim->vel[c].p, sim->mass[c].p, sim->pp.rest_density, sim->h_tmp.p, sim->ctl);
   LAUNCH_CHECK();
+  if (sim->dist) TRY(dist_allreduce_cfl(sim));  // dt is global: min over all ranks
   k_make_levels<<<1, 1, 0, st>>>(sim->ctl, f_search, sim->cells_budget, sim->pp.max_dt, sim->pp.cfl_factor);
   LAUNCH_CHECK();
   const int wide = sim->sm_count * 8;
@@ -330,7 +340,7 @@ int launch_sort_and_grid(asph_sim* sim, float f_search) {
   TRY(launch_exclusive_scan(sim, sim->cellcount.p, sim->cellstart.p, &sim->ctl->total_cells, 1, sim->cells_budget + 1));
   k_scatter<<<blocks, kThreads, 0, st>>>(n, sim->key.p, sim->cellstart.p, sim->cellcount.p, sim->order.p);
   LAUNCH_CHECK();
-  k_sort_cells<<<wide, kThreads, 0, st>>>(sim->ctl, sim->cellstart.p, sim->order.p);
+  k_sort_cells<<<wide, kThreads, 0, st>>>(sim->ctl, sim->cellstart.p, sim->order.p, sim->dist ? sim->refid[c].p : nullptr);
   LAUNCH_CHECK();
   sim->xv_cur = 0;
   k_reorder<<<blocks, kThreads, 0, st>>>(n, sim->order.p, sim->pos[c].p, sim->vel[c].p, sim->mass[c].p, sim->refid[c].p,
@@ -338,5 +348,6 @@ int launch_sort_and_grid(asph_sim* sim, float f_search) {
                                          sim->refid[1 - c].p, sim->level[1 - c].p, sim->xyhm.p, sim->xv[0].p, sim->hm.p);
   LAUNCH_CHECK();
   sim->cur = 1 - c;
+  if (sim->dist) TRY(dist_after_sort(sim));
   return ASPH_OK;
 }

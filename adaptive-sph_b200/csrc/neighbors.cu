@@ -96,7 +96,7 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
             const uint32_t* __restrict__ cellstart, const PackedParams P, const float* __restrict__ lut, float f_ext, float f_near,
             uint32_t pool_cap64, uint16_t* __restrict__ pool, uint32_t* __restrict__ slice_base, uint32_t* __restrict__ cnt,
             float* __restrict__ rho_out, float2* __restrict__ gB_out, float4* __restrict__ pconst, float* __restrict__ lam_sum_out,
-            float2* __restrict__ lam_grad_out, float2* __restrict__ nrm_out) {
+            float2* __restrict__ lam_grad_out, float2* __restrict__ nrm_out, const uint32_t* __restrict__ gid) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t i0 = i & ~31u;
@@ -189,7 +189,7 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
   const float aii = (ax * bx + ay * by) + (me.w * Q) / (rho2 * rho);
   if (!isfinite(aii)) err |= ERRF_NONFINITE;
   else if (aii < 0.f) err |= ERRF_NEG_AII;
-  if (err) atomicOr(&ctl->error_flags, err);
+  if (err && !(gid && (gid[i] & ASPH_GHOST_BIT))) atomicOr(&ctl->error_flags, err);  // a ghost's neighbourhood is incomplete by design
   rho_out[i] = rho;
   gB_out[i] = make_float2(Bc * Gx, Bc * Gy);
   pconst[i] = make_float4(rho0 * Gx / rho, rho0 * Gy / rho, aii, 0.f);
@@ -213,8 +213,10 @@ int launch_neighbors(asph_sim* sim, float f_ext, float f_near) {
   const uint32_t cap64 = uint32_t(std::min<size_t>(sim->nbpool.cap / 64, 0x7FFFFFF0u));
   k_neighbors<<<blocks, kThreads, 0, sim->stream>>>(n, sim->xyhm.p, sim->ctl, sim->ctl, sim->cellstart.p, sim->pp, sim->lut.p, f_ext, f_near,
                                                     cap64, sim->nbpool.p, sim->slice_base.p, sim->cnt.p, sim->rho.p, sim->gB.p,
-                                                    sim->pconst.p, sim->lam_sum.p, sim->lam_grad.p, sim->nrm.p);
+                                                    sim->pconst.p, sim->lam_sum.p, sim->lam_grad.p, sim->nrm.p,
+                                                    sim->dist ? sim->refid[sim->cur].p : nullptr);
   LAUNCH_CHECK();
+  if (sim->dist) TRY(dist_halo(sim, sim->rho.p, 4));  // K12 / K17 read the neighbours' densities
   sim->lists_valid = true;  // provisional: the caller checks ERRF_LIST_CAPACITY at its next synchronisation (neighbors_grow)
   return ASPH_OK;
 }
@@ -223,10 +225,14 @@ int launch_neighbors(asph_sim* sim, float f_ext, float f_near) {
 // flag and counters so the neighbour pass can be launched again (nothing irreversible has happened yet).
 int neighbors_grow(asph_sim* sim) {
   const StepCtl& c = *sim->ctl_host;
-  size_t want = (size_t(c.list_used) + size_t(c.list_used) / 4 + 128) * 64;
-  if (want <= sim->nbpool.cap) want = sim->nbpool.cap * 2;
-  if (want / 64 > 0x7FFFFFF0u) { sim->last_error = "neighbour list pool exceeds its addressable size"; return ASPH_ERR_CAPACITY; }
-  CUDA_TRY(sim->nbpool.ensure(want));
+  // multi-GPU: the flag is shared by all ranks, the pool only grows on the ranks whose own request did not fit
+  const bool overflowed = size_t(c.list_used) * 64 > sim->nbpool.cap || !sim->dist;
+  if (overflowed) {
+    size_t want = (size_t(c.list_used) + size_t(c.list_used) / 4 + 128) * 64;
+    if (want <= sim->nbpool.cap) want = sim->nbpool.cap * 2;
+    if (want / 64 > 0x7FFFFFF0u) { sim->last_error = "neighbour list pool exceeds its addressable size"; return ASPH_ERR_CAPACITY; }
+    CUDA_TRY(sim->nbpool.ensure(want));
+  }
   StepCtl patch = c;
   patch.list_used = 0; patch.max_count = 0; patch.error_flags = c.error_flags & ~ERRF_LIST_CAPACITY;
   CUDA_TRY(cudaMemcpyAsync(sim->ctl, &patch, sizeof(StepCtl), cudaMemcpyHostToDevice, sim->stream));

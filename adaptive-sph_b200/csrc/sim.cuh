@@ -43,6 +43,9 @@ struct SolverCtl {
   unsigned long long normal, singular, negative;
   float err_sum, max_err, avg;
   unsigned int ticket;
+  // multi-GPU: this rank's statistics of the sweep {normal, singular, negative, err_sum}; summed over the ranks
+  // (dist.cu) before k_solver_decide applies the stop rule identically everywhere
+  double partial[4];
 };
 
 struct StepCtl {
@@ -98,6 +101,7 @@ template <class T> struct DevBuf {
 };
 
 struct DistState;  // dist.cu
+#define ASPH_GHOST_BIT 0x80000000u  // refid of a ghost particle (owned by a neighbouring slab) carries this bit
 
 struct asph_sim {
   int device = 0;
@@ -218,6 +222,16 @@ int launch_level_estimation(asph_sim* sim);
 int launch_level_smoothing(asph_sim* sim);
 // adapt.cu
 int launch_adaptivity(asph_sim* sim, float dt);
+// dist.cu — multi-GPU slab decomposition (all are no-ops / never called when sim->dist == nullptr)
+int dist_begin_step(asph_sim* sim, float f_search);        // migrate, exchange ghosts; afterwards sim->n = owned + ghosts
+int dist_allreduce_cfl(asph_sim* sim);                     // min over ranks of the CFL term, between k_prepare and k_make_levels
+int dist_after_sort(asph_sim* sim);                        // halo index maps in sorted order
+int dist_halo(asph_sim* sim, void* field, int elem_bytes); // owner -> ghost copies of one per-particle field
+int dist_halo_pressure(asph_sim* sim);                     // same for the pressure pack the device-side sweep parity selects
+int dist_solver_reduce(asph_sim* sim);                     // sum SolverCtl::partial over ranks
+int dist_reduce_flags(asph_sim* sim, bool with_lists);     // make error flags (and "lists too small") agree on all ranks
+int dist_local_map(asph_sim* sim);                         // scratch_u[3][i] = slot of owned particle i in read-backs, ~0u for ghosts
+void dist_destroy(asph_sim* sim);
 // capi.cu
 int check_error_flags(asph_sim* sim);
 cudaEvent_t kt_event(asph_sim* sim);           // event from the handle's pool

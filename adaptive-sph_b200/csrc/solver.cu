@@ -135,7 +135,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 k_accel(uint32_t n, NbLists L, const float4* __restrict__ P0, const float4* __restrict__ P1, const float2* __restrict__ hm,
         const float2* __restrict__ gB, float4* __restrict__ packA, StepCtl* ctl, float4* __restrict__ xv, float2* __restrict__ pos,
-        float2* __restrict__ vel, float hybrid_factor) {
+        float2* __restrict__ vel, float hybrid_factor, const uint32_t* __restrict__ gid) {
   if (MODE == 0 && ctl->solver.done) return;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -169,15 +169,30 @@ k_accel(uint32_t n, NbLists L, const float4* __restrict__ P0, const float4* __re
     const float2 x = make_float2(me.x + (dt * v.z + (dt * dt) * ax), me.y + (dt * v.w + (dt * dt) * ay));
     const float2 vn = make_float2(v.z + (dt * ax) * fac, v.w + (dt * ay) * fac);
     pos[i] = x; vel[i] = vn;
-    if (!(isfinite(x.x) && isfinite(x.y) && isfinite(vn.x) && isfinite(vn.y))) atomicOr(&ctl->error_flags, ERRF_NONFINITE);
+    if (!(isfinite(x.x) && isfinite(x.y) && isfinite(vn.x) && isfinite(vn.y)) && !(gid && (gid[i] & ASPH_GHOST_BIT)))
+      atomicOr(&ctl->error_flags, ERRF_NONFINITE);
   } else if (MODE == 3) {
     const float dt = ctl->dt;
     const float4 v = xv[i];
     const float2 vn = make_float2(v.z + dt * ax, v.w + dt * ay);
     const float2 x = make_float2(me.x + dt * vn.x, me.y + dt * vn.y);
     pos[i] = x; vel[i] = vn;
-    if (!(isfinite(x.x) && isfinite(x.y) && isfinite(vn.x) && isfinite(vn.y))) atomicOr(&ctl->error_flags, ERRF_NONFINITE);
+    if (!(isfinite(x.x) && isfinite(x.y) && isfinite(vn.x) && isfinite(vn.y)) && !(gid && (gid[i] & ASPH_GHOST_BIT)))
+      atomicOr(&ctl->error_flags, ERRF_NONFINITE);
   }
+}
+
+// loop control of iisph_pressure_iterations after a sweep (simulation.rs:1453-1477)
+__device__ __forceinline__ void solver_decide(SolverCtl& s, unsigned int error_flags, float dt, float rho0, float tol, int max_iters,
+                                              int density_mode) {
+  s.sweeps += 1;
+  const float avg = s.normal > 0 ? s.err_sum / float(s.normal) : __int_as_float(0x7fc00000);
+  s.avg = avg;
+  bool stop;
+  if (density_mode) stop = (s.normal == 0) || (fabsf(avg / rho0) < tol && s.k > 1);
+  else stop = (s.normal == 0) || (fabsf(avg) < tol / dt && s.k > 1);
+  if (stop || s.k == max_iters || (error_flags & ERRF_SOLVER_NONFINITE)) s.done = 1;
+  else s.k += 1;
 }
 
 // ---------------------------------------------------------------------------------------------- K15
@@ -186,7 +201,8 @@ k_accel(uint32_t n, NbLists L, const float4* __restrict__ P0, const float4* __re
 __global__ void __launch_bounds__(kThreads)
 k_jacobi(uint32_t n, NbLists L, const float4* __restrict__ packA, float4* __restrict__ P0, float4* __restrict__ P1,
          const float2* __restrict__ hm, const float4* __restrict__ pconst, const float* __restrict__ rho, StepCtl* ctl,
-         float* __restrict__ blockstats, float omega, float rho0, float tol, int max_iters, int density_mode) {
+         float* __restrict__ blockstats, float omega, float rho0, float tol, int max_iters, int density_mode,
+         const uint32_t* __restrict__ gid) {
   if (ctl->solver.done) return;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const float dt = ctl->dt;
@@ -196,7 +212,9 @@ k_jacobi(uint32_t n, NbLists L, const float4* __restrict__ packA, float4* __rest
   uint32_t c_normal = 0, c_sing = 0, c_neg = 0;
   float e_sum = 0.f, e_max = 0.f;
   bool bad = false;
-  if (i < n) {
+  // gid != nullptr: multi-GPU.  Ghost particles are skipped (their p' arrives from the owner rank) and the stop rule is
+  // applied by k_solver_decide once the statistics of all ranks are summed.
+  if (i < n && !(gid && (gid[i] & ASPH_GHOST_BIT))) {
     const float4 me = packA[i];
     const float4 pc = pconst[i];
     const float p_old = packP[i].w;
@@ -265,20 +283,29 @@ k_jacobi(uint32_t n, NbLists L, const float4* __restrict__ packA, float4* __rest
     __syncthreads();
   }
   if (threadIdx.x == 0) {
+    if (gid) {
+      ctl->solver.partial[0] = double(shn[0]); ctl->solver.partial[1] = double(shs[0]); ctl->solver.partial[2] = double(shg[0]);
+      ctl->solver.partial[3] = double(sh[3][0]);
+      ctl->solver.max_err = sh[4][0];
+      ctl->solver.ticket = 0;
+      return;
+    }
     SolverCtl s = ctl->solver;
     s.normal = shn[0]; s.singular = shs[0]; s.negative = shg[0]; s.err_sum = sh[3][0]; s.max_err = sh[4][0];
     s.ticket = 0;
-    s.sweeps += 1;
-    const float avg = s.normal > 0 ? s.err_sum / float(s.normal) : __int_as_float(0x7fc00000);
-    s.avg = avg;
-    // simulation.rs:1453-1477
-    bool stop;
-    if (density_mode) stop = (s.normal == 0) || (fabsf(avg / rho0) < tol && s.k > 1);
-    else stop = (s.normal == 0) || (fabsf(avg) < tol / dt && s.k > 1);
-    if (stop || s.k == max_iters || (ctl->error_flags & ERRF_SOLVER_NONFINITE)) s.done = 1;
-    else s.k += 1;
+    solver_decide(s, ctl->error_flags, dt, rho0, tol, max_iters, density_mode);
     ctl->solver = s;
   }
+}
+
+// multi-GPU: the stop rule on the statistics summed over all ranks (every rank computes the same decision)
+__global__ void k_solver_decide(StepCtl* ctl, float rho0, float tol, int max_iters, int density_mode) {
+  SolverCtl s = ctl->solver;
+  if (s.done) return;
+  s.normal = (unsigned long long)s.partial[0]; s.singular = (unsigned long long)s.partial[1]; s.negative = (unsigned long long)s.partial[2];
+  s.err_sum = float(s.partial[3]);
+  solver_decide(s, ctl->error_flags, ctl->dt, rho0, tol, max_iters, density_mode);
+  ctl->solver = s;
 }
 
 NbLists lists_of(asph_sim* sim) {
@@ -297,6 +324,7 @@ int launch_viscosity(asph_sim* sim) {
   k_viscosity<<<blocks, kThreads, 0, sim->stream>>>(n, lists_of(sim), sim->xv[a].p, sim->hm.p, sim->rho.p, sim->pp, sim->ctl, sim->xv[1 - a].p);
   LAUNCH_CHECK();
   sim->xv_cur = 1 - a;
+  if (sim->dist) TRY(dist_halo(sim, sim->xv[sim->xv_cur].p, 16));  // neighbours read the new velocities (K13)
   return ASPH_OK;
 }
 
@@ -324,6 +352,7 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
   CUDA_TRY(sim->blockstats.ensure(size_t(blocks) * 5 + 8));
   cudaStream_t st = sim->stream;
   const NbLists L = lists_of(sim);
+  const uint32_t* gid = sim->dist ? sim->refid[sim->cur].p : nullptr;
   int launched = 0;
   int& predicted = sim->predicted_sweeps[density_mode ? 1 : 0];
   int batch = std::max(1, std::min(predicted, 256));
@@ -337,14 +366,21 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
       if (time_it) { tm.e0 = kt_event(sim); tm.e1 = kt_event(sim); tm.e2 = kt_event(sim); cudaEventRecord(tm.e0, st); }
       if (launched > 0) {  // sweep 0: a^p = 0 was written by k_source
         k_accel<0><<<blocks, kThreads, 0, st>>>(n, L, sim->packP[0].p, sim->packP[1].p, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, nullptr,
-                                                nullptr, nullptr, 0.f);
+                                                nullptr, nullptr, 0.f, gid);
         LAUNCH_CHECK();
+        if (sim->dist) TRY(dist_halo(sim, sim->packA.p, 16));
       }
       if (time_it) cudaEventRecord(tm.e1, st);
       k_jacobi<<<blocks, kThreads, 0, st>>>(n, L, sim->packA.p, sim->packP[0].p, sim->packP[1].p, sim->hm.p, sim->pconst.p, sim->rho.p,
                                             sim->ctl, sim->blockstats.p, sim->pp.jacobi_omega, sim->pp.rest_density, max_avg_error,
-                                            sim->pp.max_iters, density_mode ? 1 : 0);
+                                            sim->pp.max_iters, density_mode ? 1 : 0, gid);
       LAUNCH_CHECK();
+      if (sim->dist) {
+        TRY(dist_solver_reduce(sim));
+        k_solver_decide<<<1, 1, 0, st>>>(sim->ctl, sim->pp.rest_density, max_avg_error, sim->pp.max_iters, density_mode ? 1 : 0);
+        LAUNCH_CHECK();
+        TRY(dist_halo_pressure(sim));
+      }
       if (time_it) { cudaEventRecord(tm.e2, st); timed.push_back(tm); }
     }
     TRY(sync_ctl(sim));
@@ -387,12 +423,14 @@ int launch_final_accel(asph_sim* sim, int mode) {
   float4* xv = sim->xv[sim->xv_cur].p;
   float2* pos = sim->pos[sim->cur].p;
   float2* vel = sim->vel[sim->cur].p;
+  const uint32_t* gid = sim->dist ? sim->refid[sim->cur].p : nullptr;
   switch (mode) {
-    case 1: k_accel<1><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f); break;
-    case 2: k_accel<2><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, sim->pp.hybrid_factor); break;
-    case 3: k_accel<3><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f); break;
-    default: k_accel<4><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f); break;
+    case 1: k_accel<1><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f, gid); break;
+    case 2: k_accel<2><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, sim->pp.hybrid_factor, gid); break;
+    case 3: k_accel<3><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f, gid); break;
+    default: k_accel<4><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f, gid); break;
   }
   LAUNCH_CHECK();
+  if (sim->dist && mode == 1) TRY(dist_halo(sim, xv, 16));  // the density solve's source term reads the neighbours' new velocities
   return ASPH_OK;
 }

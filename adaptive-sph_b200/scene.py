@@ -78,13 +78,51 @@ def add_fluid_block(block):
     return pos, vel, mass
 
 
-def scene_particles(scene):
-    ps, vs, ms = [], [], []
+def block_lattice(block):
+    """(nx, ny, xs, ys, particle_mass) of add_fluid_block's lattice (simulation.rs:2957-2971)."""
+    spacing = f32(block["spacing"])
+    mn = np.array(block["pos"], dtype=f32)
+    mx = np.array([block["pos"][0] + block["size"][0], block["pos"][1] + block["size"][1]], dtype=f32)
+    particle_volume = f32(f32(spacing * spacing) * f32(block["volume_fill_ratio"]))
+    particle_mass = f32(particle_volume * f32(1.0))
+    box = (mx - mn).astype(f32)
+    nx = int(np.floor(f32(box[0] / spacing)))
+    ny = int(np.floor(f32(box[1] / spacing)))
+    xs = (np.arange(nx, dtype=f32) * spacing + mn[0]).astype(f32)
+    ys = (np.arange(ny, dtype=f32) * spacing + mn[1]).astype(f32)
+    return nx, ny, xs, ys, particle_mass
+
+
+def scene_particle_count(scene):
+    return sum(block_lattice(b)[0] * block_lattice(b)[1] for b in scene.blocks)
+
+
+def scene_particles(scene, index_range=None):
+    """All particles of the scene in the reference's order (blocks in file order, x-major inside a block), or only
+    those with reference index in [lo, hi) — a rank of a multi-GPU run generates just its own share."""
+    if index_range is None:
+        ps, vs, ms = [], [], []
+        for blk in scene.blocks:
+            p, v, m = add_fluid_block(blk)
+            ps.append(p); vs.append(v); ms.append(m)
+        if not ps:
+            return np.zeros((0, 2), f32), np.zeros((0, 2), f32), np.zeros(0, f32)
+        return np.concatenate(ps), np.concatenate(vs), np.concatenate(ms)
+    lo, hi = int(index_range[0]), int(index_range[1])
+    ps, vs, ms = [np.zeros((0, 2), f32)], [np.zeros((0, 2), f32)], [np.zeros(0, f32)]
+    base = 0
     for blk in scene.blocks:
-        p, v, m = add_fluid_block(blk)
-        ps.append(p); vs.append(v); ms.append(m)
-    if not ps:
-        return np.zeros((0, 2), f32), np.zeros((0, 2), f32), np.zeros(0, f32)
+        nx, ny, xs, ys, pm = block_lattice(blk)
+        a, b = max(lo, base), min(hi, base + nx * ny)
+        if a < b:
+            idx = np.arange(a - base, b - base, dtype=np.int64)
+            p = np.empty((len(idx), 2), dtype=f32)
+            p[:, 0] = xs[idx // ny]
+            p[:, 1] = ys[idx % ny]
+            v = np.empty_like(p)
+            v[:, 0] = blk["velocity"][0]; v[:, 1] = blk["velocity"][1]
+            ps.append(p); vs.append(v); ms.append(np.full(len(idx), pm, dtype=f32))
+        base += nx * ny
     return np.concatenate(ps), np.concatenate(vs), np.concatenate(ms)
 
 
