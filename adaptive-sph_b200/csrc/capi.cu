@@ -6,7 +6,7 @@
 #include <cmath>
 #include <cstring>
 
-#include "sim.cuh"
+#include "lists.cuh"
 
 
 namespace {
@@ -141,6 +141,15 @@ __global__ void k_extract(uint32_t n, int field, const uint32_t* __restrict__ re
     }
     case ASPH_F_MERGE_COUNTER: ((uint16_t*)out)[r] = uint16_t(merge_counter[i]); break;
   }
+}
+
+// multi-GPU asph_set_state: host arrays are in the handle's read-back order; map[i] = slot of sorted particle i
+template <class T>
+__global__ void k_scatter_state(uint32_t n, const uint32_t* __restrict__ map, const T* __restrict__ src, T* __restrict__ dst) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t r = map[i];
+  if (r != 0xFFFFFFFFu) dst[i] = src[r];
 }
 
 int field_elem_bytes(int field, int* comps) {
@@ -361,7 +370,28 @@ const char* asph_backend_name(void) { return "cuda-sm100a"; }
 int asph_set_state(asph_sim* sim, const float* pos, const float* vel, const float* mass, uint64_t n) {
   if (!sim || (n && (!pos || !vel || !mass))) return ASPH_ERR_INVALID;
   if (n > 0x7FFFFFF0ull) return ASPH_ERR_CAPACITY;  // bit 31 of the particle index marks ghosts (multi-GPU)
-  if (sim->dist) { sim->last_error = "asph_set_state on a distributed handle"; return ASPH_ERR_UNSUPPORTED; }
+  if (sim->dist) {
+    // this rank's owned particles, in the order asph_get_field reports them; identities (global indices) are kept
+    if (n != sim->n_owned) { sim->last_error = "asph_set_state on a distributed handle: n must equal the owned particle count"; return ASPH_ERR_INVALID; }
+    CUDA_TRY(cudaSetDevice(sim->device));
+    if (n == 0) return ASPH_OK;
+    TRY(dist_local_map(sim));
+    const int c = sim->cur;
+    const uint32_t na = sim->n, blocks = (na + kThreads - 1) / kThreads;
+    const uint32_t* map = sim->scratch_u[3].p;
+    CUDA_TRY(cudaMemcpyAsync(sim->scratch_f.p, pos, n * sizeof(float2), cudaMemcpyHostToDevice, sim->stream));
+    k_scatter_state<float2><<<blocks, kThreads, 0, sim->stream>>>(na, map, (const float2*)sim->scratch_f.p, sim->pos[c].p);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(sim->scratch_f.p, vel, n * sizeof(float2), cudaMemcpyHostToDevice, sim->stream));
+    k_scatter_state<float2><<<blocks, kThreads, 0, sim->stream>>>(na, map, (const float2*)sim->scratch_f.p, sim->vel[c].p);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(sim->scratch_f.p, mass, n * sizeof(float), cudaMemcpyHostToDevice, sim->stream));
+    k_scatter_state<float><<<blocks, kThreads, 0, sim->stream>>>(na, map, (const float*)sim->scratch_f.p, sim->mass[c].p);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaStreamSynchronize(sim->stream));
+    sim->lists_valid = false; sim->level_valid = false; sim->step_fields_valid = false;
+    return ASPH_OK;
+  }
   CUDA_TRY(cudaSetDevice(sim->device));
   if (n > sim->cap) { sim->n = 0; TRY(ensure_capacity(sim, uint32_t(n + n / 4 + 1024))); }
   sim->n = uint32_t(n); sim->n_owned = uint32_t(n);
@@ -539,7 +569,7 @@ int asph_get_neighbors_csr(asph_sim* sim, uint64_t* offsets, uint32_t* idx, uint
     const uint32_t sb = sbase[i >> 5];
     const bool wide = (sb >> 31) != 0;
     const size_t base = size_t(sb & 0x7fffffffu) * 64;
-    const uint32_t lane = i & 31u, bias = (i & ~31u) - 32768u;
+    const uint32_t lane = i & 31u, bias = nb_bias(i);
     for (uint32_t k = 0; k < c; k++) {
       uint32_t j;
       if (wide) j = reinterpret_cast<const uint32_t*>(pool.data() + base)[(k >> 2) * 128u + lane * 4u + (k & 3u)];

@@ -94,7 +94,7 @@ __global__ void k_make_levels(StepCtl* ctl, float f_search, uint32_t cells_budge
       g.ny = int(floorf((maxy - miny) * g.inv_cell)) + 1;
       g.base = uint32_t(total);
       ctl->lv[L] = g;
-      total += (unsigned long long)g.nx * (unsigned long long)g.ny;
+      total += level_cells(g.nx, g.ny);
       upper *= 2.f;
     }
     if (total <= cells_budget) { ctl->total_cells = uint32_t(total); return; }
@@ -125,7 +125,7 @@ __global__ void k_bin(uint32_t n, const float2* __restrict__ pos, const float* _
   float2 x = pos[i];
   int cx = min(g.nx - 1, max(0, int(floorf((x.x - ctl->origin_x) * g.inv_cell))));
   int cy = min(g.ny - 1, max(0, int(floorf((x.y - ctl->origin_y) * g.inv_cell))));
-  uint32_t k = g.base + uint32_t(cy) * uint32_t(g.nx) + uint32_t(cx);
+  uint32_t k = cell_index(g, cx, cy);
   key[i] = k;
   atomicAdd(&cellcount[k], 1u);
 }

@@ -83,10 +83,13 @@ __device__ __forceinline__ void for_each_candidate(float xi, float yi, float hi,
     const int cy0 = max(0, int(floorf((yi - r - oy) * g.inv_cell)));
     const int cy1 = min(g.ny - 1, int(floorf((yi + r - oy) * g.inv_cell)));
     if (cx0 > cx1) continue;
+    // cells are stored strip-major (grid.cu): a row's cells are contiguous inside one strip of ASPH_STRIP columns
     for (int cy = cy0; cy <= cy1; cy++) {
-      const uint32_t row = g.base + uint32_t(cy) * uint32_t(g.nx);
-      const uint32_t s = cellstart[row + cx0], e = cellstart[row + cx1 + 1];
-      for (uint32_t j = s; j < e; j++) f(j);
+      for (int st = cx0 >> ASPH_STRIP_LOG2; st <= (cx1 >> ASPH_STRIP_LOG2); st++) {
+        const int ca = max(cx0, st << ASPH_STRIP_LOG2), cb = min(cx1, (st << ASPH_STRIP_LOG2) + ASPH_STRIP - 1);
+        const uint32_t s = cellstart[cell_index(g, ca, cy)], e = cellstart[cell_index(g, cb, cy) + 1];
+        for (uint32_t j = s; j < e; j++) f(j);
+      }
     }
   }
 }
@@ -99,7 +102,7 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
             float2* __restrict__ lam_grad_out, float2* __restrict__ nrm_out, const uint32_t* __restrict__ gid) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t i0 = i & ~31u;
+  const uint32_t i0 = i & ~(ASPH_PAIR_BLOCK - 1u);  // the index bias is per 256-particle block (lists.cuh)
   const bool active = i < n;
   float4 me = make_float4(0.f, 0.f, 1.f, 0.f);
   if (active) me = xyhm[i];
@@ -119,15 +122,18 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
       }
     });
   }
-  uint32_t we = ce;
-  for (int o = 16; o > 0; o >>= 1) we = max(we, __shfl_xor_sync(0xffffffffu, we, o));
+  uint32_t we = nb_col_rows(cn, ce), ce_max = ce;
+  for (int o = 16; o > 0; o >>= 1) {
+    we = max(we, __shfl_xor_sync(0xffffffffu, we, o));
+    ce_max = max(ce_max, __shfl_xor_sync(0xffffffffu, ce_max, o));
+  }
   const bool wide = !__all_sync(0xffffffffu, fits);
   const uint32_t units = nb_slice_units(we, wide);
   uint32_t base64 = 0;
   if (lane == 0) {
     base64 = atomicAdd(&ctl->list_used, units);
-    atomicMax(&ctl->max_count, we);
-    if (we > 20000u) atomicOr(&ctl->error_flags, ERRF_NEIGHBOR_OVERFLOW);  // MAX_NEIGHBOR_COUNT neighborhood_search.rs:3,148-150
+    atomicMax(&ctl->max_count, ce_max);
+    if (ce_max > 20000u) atomicOr(&ctl->error_flags, ERRF_NEIGHBOR_OVERFLOW);  // MAX_NEIGHBOR_COUNT neighborhood_search.rs:3,148-150
     if (base64 + units > pool_cap64 || base64 + units < base64) atomicOr(&ctl->error_flags, ERRF_LIST_CAPACITY);
     slice_base[i >> 5] = base64 | (wide ? 0x80000000u : 0u);
   }
@@ -140,7 +146,7 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
   uint16_t* slice = pool + size_t(base64) * 64u;
   {
     const uint32_t bias = i0 - 32768u;
-    uint32_t kn = 0, ke = cn;
+    uint32_t kn = 0, ke = (cn + 7u) & ~7u;
     for_each_candidate(xi, yi, hi, ctl_in, cellstart, f_ext, [&](uint32_t j) {
       const float4 o = __ldg(&xyhm[j]);
       const float d2 = dist_sq_exact(__fsub_rn(xi, o.x), __fsub_rn(yi, o.y));
@@ -150,6 +156,7 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
       else return;
       nb_store(slice, wide, lane, row, j, bias);
     });
+    for (uint32_t r = cn; r < ((cn + 7u) & ~7u); r++) nb_store(slice, wide, lane, r, i, bias);  // padding: the particle itself
   }
 
   // boundary terms

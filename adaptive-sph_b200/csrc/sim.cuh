@@ -30,11 +30,24 @@ enum {
   ERRF_SPLIT_CHILDREN = 512, ERRF_SOLVER_NONFINITE = 1024, ERRF_PARTNER_VALIDATION = 2048
 };
 
+// Cells of a level are numbered STRIP-MAJOR: the grid is cut into vertical strips of ASPH_STRIP columns; inside a strip
+// cells run row by row.  Particles are sorted by cell number, so the particles of the 3 x 3 (or wider) cell block
+// around a cell lie within a few hundred positions of each other in memory (one strip row = ASPH_STRIP cells), apart
+// from the cells across a strip edge.  The pair passes stage that window in shared memory (solver.cu).
+#define ASPH_STRIP_LOG2 4
+#define ASPH_STRIP (1 << ASPH_STRIP_LOG2)
 struct GridLevel {
   float cell, inv_cell, hmax;
   int nx, ny;
   uint32_t base;  // first cell of this level in the concatenated cell array
 };
+__host__ __device__ __forceinline__ uint32_t cell_index(const GridLevel& g, int cx, int cy) {
+  const uint32_t st = uint32_t(cx) >> ASPH_STRIP_LOG2;
+  return g.base + ((st * uint32_t(g.ny) + uint32_t(cy)) << ASPH_STRIP_LOG2) + (uint32_t(cx) & (ASPH_STRIP - 1));
+}
+__host__ __device__ __forceinline__ unsigned long long level_cells(int nx, int ny) {
+  return (unsigned long long)((nx + ASPH_STRIP - 1) >> ASPH_STRIP_LOG2) * (unsigned long long)ny * ASPH_STRIP;
+}
 
 struct SolverCtl {
   int k;       // index of the sweep being executed (num_pressure_iters, simulation.rs:1388)

@@ -23,51 +23,112 @@ __global__ void k_solver_reset(StepCtl* ctl) {
   ctl->solver = s;
 }
 
-// Σ over N_2(i): f(pack[j], x_ij, m_j * dW/dr / r).  UNI: h and m are the same for every particle of this step.
-// A column is consumed 8 entries at a time: one vector load of indices, then 8 independent gathers in flight, then the
-// arithmetic.  Padding entries point at the particle itself (zero distance => pair_g = 0 => no contribution).
-template <bool UNI, class F>
-__device__ __forceinline__ void for_each_pair(const NbLists& L, uint32_t i, const float4* __restrict__ pack, const float2* __restrict__ hm,
-                                              float xi, float yi, float hi, float mi, F f) {
-  const NbCol col(L, i);
-  const uint32_t cn = __ldg(&L.cnt[i]) & 0xffffu;
-  float inv2h = 0.f, nfac = 0.f;
-  if (UNI) { inv2h = __frcp_rn(2.f * hi); nfac = ASPH_KNORM * inv2h * inv2h * inv2h; }
-  for (uint32_t k0 = 0; k0 < cn; k0 += 8u) {
-    uint32_t j[8];
-    col.get8(k0, cn, j);
-    float4 o[8];
-    float2 t[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      o[u] = __ldg(&pack[j[u]]);
-      if (!UNI) t[u] = __ldg(&hm[j[u]]);
-    }
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const float dx = xi - o[u].x, dy = yi - o[u].y;
-      const float d2 = dx * dx + dy * dy;
-      const float c = UNI ? mi * pair_g_uniform(d2, inv2h, nfac) : t[u].y * pair_g(d2, (hi + t[u].x) * 0.5f);
-      f(o[u], dx, dy, c, j[u]);
+// ---- shared-memory window ------------------------------------------------------------------------------------
+// Particles are sorted by strip-major cell number (sim.cuh), so almost every 2h neighbour of the kThreads consecutive
+// particles of a block lies within kHalo positions of the block's range.  The block stages that window of the gathered
+// pack (and of {h, m} when h is not uniform) in shared memory with coalesced loads; a neighbour outside the window
+// (across a strip edge, or in another size level's grid) is read from global memory instead.  Correctness never
+// depends on the window, only the speed does.  Slot t of the window holds particle wa + t, wa = block_first - kHalo
+// (mod 2^32: for the first block the slots of "negative" particles stay unused).
+static_assert(kThreads == int(ASPH_PAIR_BLOCK), "the neighbour index bias is aligned to the pair-pass block size");
+constexpr uint32_t kHalo = 192;
+constexpr uint32_t kWin = kThreads + 2 * kHalo;
+
+template <bool AUX>
+__device__ __forceinline__ void stage_window(uint32_t n, bool uni, const float4* __restrict__ pack, const float2* __restrict__ hm,
+                                             const float* __restrict__ aux, float4 (&s_pack)[kWin], float2 (&s_hm)[kWin], float* s_aux) {
+  const uint32_t wa = blockIdx.x * kThreads - kHalo;
+  for (uint32_t t = threadIdx.x; t < kWin; t += kThreads) {
+    const uint32_t g = wa + t;
+    if (g < n) {
+      s_pack[t] = __ldg(&pack[g]);
+      if (!uni) s_hm[t] = __ldg(&hm[g]);
+      if (AUX) s_aux[t] = __ldg(&aux[g]);
     }
   }
+  __syncthreads();
+}
+
+// Σ over N_2(i) of f(pack[j], x_ij, c_ij, h_ij, aux[j]); the caller multiplies its sums by the returned scale:
+//   uniform h (UNI):  c_ij = w'(q)/r un-normalised,   scale = m * 40 / (7 pi (2h)^3)
+//   otherwise:        c_ij = m_j * dW/dr / r,         scale = 1
+// (every f is linear in c).  A column is consumed 8 rows at a time: one vector load of indices, then the gathers
+// (shared memory, or global for the few outside the window), then the arithmetic.  Padding rows point at the particle
+// itself (zero distance => c = 0), so there are no per-entry bounds checks.
+template <bool UNI, bool AUX, bool WIDE, class F>
+__device__ __forceinline__ void pair_rows(const NbCol& col, uint32_t sp, uint32_t sh, uint32_t sa, const float4* __restrict__ pack,
+                                          const float2* __restrict__ hm, const float* __restrict__ aux, float xi, float yi, float hi,
+                                          const PairShape& shape, F& f) {
+  const uint32_t wa = blockIdx.x * kThreads - kHalo;
+  for (uint32_t k0 = 0; k0 < col.cn; k0 += 8u) {
+    uint32_t off[8];
+    col.get8_off<WIDE>(k0, kHalo, off);
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      float4 o[4];
+      float2 t[4];
+      float a[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t of = off[half * 4 + u];
+        if (of < kWin) {
+          o[u] = lds_f4(sp + of * 16u);
+          if (!UNI) t[u] = lds_f2(sh + of * 8u);
+          if (AUX) a[u] = lds_f1(sa + of * 4u);
+        } else {
+          const uint32_t jj = wa + of;
+          o[u] = __ldg(pack + jj);
+          if (!UNI) t[u] = __ldg(hm + jj);
+          if (AUX) a[u] = __ldg(aux + jj);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const float dx = xi - o[u].x, dy = yi - o[u].y;
+        const float d2 = dx * dx + dy * dy;
+        if (UNI) {
+          f(o[u], dx, dy, shape(d2), hi, AUX ? a[u] : 0.f);
+        } else {
+          const float hij = (hi + t[u].x) * 0.5f;
+          f(o[u], dx, dy, t[u].y * pair_g(d2, hij), hij, AUX ? a[u] : 0.f);
+        }
+      }
+    }
+  }
+}
+template <bool UNI, bool AUX, class F>
+__device__ __forceinline__ float for_each_pair(const NbLists& L, uint32_t i, const float4 (&s_pack)[kWin], const float2 (&s_hm)[kWin],
+                                               const float* s_aux, const float4* __restrict__ pack, const float2* __restrict__ hm,
+                                               const float* __restrict__ aux, float xi, float yi, float hi, float mi, F f) {
+  const NbCol col(L, i);
+  const float inv2h = fast_rcp(2.f * hi);
+  const PairShape shape(inv2h);
+  // shared-window base addresses, pinned in registers (the compiler would otherwise re-derive them from the CTA id
+  // special register at every gather)
+  uint32_t sp = uint32_t(__cvta_generic_to_shared(&s_pack[0]));
+  uint32_t sh = uint32_t(__cvta_generic_to_shared(&s_hm[0]));
+  uint32_t sa = AUX ? uint32_t(__cvta_generic_to_shared(s_aux)) : 0u;
+  asm volatile("" : "+r"(sp), "+r"(sh), "+r"(sa));
+  if (!col.wide) pair_rows<UNI, AUX, false>(col, sp, sh, sa, pack, hm, aux, xi, yi, hi, shape, f);
+  else pair_rows<UNI, AUX, true>(col, sp, sh, sa, pack, hm, aux, xi, yi, hi, shape, f);
+  return UNI ? mi * (ASPH_KNORM * inv2h * inv2h * inv2h) : 1.f;
 }
 
 // ---------------------------------------------------------------------------------------------- K12
 template <bool UNI>
-__device__ __forceinline__ void viscosity_body(uint32_t i, const NbLists& L, const float4* __restrict__ xv_in, const float2* __restrict__ hm,
+__device__ __forceinline__ void viscosity_body(uint32_t i, const NbLists& L, const float4 (&s_pack)[kWin], const float2 (&s_hm)[kWin],
+                                               const float* s_aux, const float4* __restrict__ xv_in, const float2* __restrict__ hm,
                                                const float* __restrict__ rho, const PackedParams& P, float dt, float4* __restrict__ xv_out) {
   const float4 me = xv_in[i];
   const float2 own = hm[i];
   const float rho_i = rho[i];
   float ax = 0.f, ay = 0.f;
   if (P.viscosity_type != ASPH_VISC_XSPH && P.viscosity != 0.f) {
-    for_each_pair<UNI>(L, i, xv_in, hm, me.x, me.y, own.x, own.y, [&](const float4& o, float dx, float dy, float c, uint32_t j) {
+    const float scale = for_each_pair<UNI, true>(L, i, s_pack, s_hm, s_aux, xv_in, hm, rho, me.x, me.y, own.x, own.y,
+                             [&](const float4& o, float dx, float dy, float c, float hij, float rho_j) {
       const float est = dx * (me.z - o.z) + dy * (me.w - o.w);
       if (est < 0.f) {
-        const float hij = UNI ? own.x : (own.x + __ldg(&hm[j]).x) * 0.5f;
         const float d2 = dx * dx + dy * dy;
-        const float rho_j = __ldg(&rho[j]);
         float f;
         if (P.viscosity_type == ASPH_VISC_APPROX_LAPLACE) {
           f = P.viscosity * (8.f * est / ((rho_i + rho_j) * 0.5f * (d2 + 0.01f * hij * hij)));  // 2(D+2), D = 2
@@ -77,6 +138,7 @@ __device__ __forceinline__ void viscosity_body(uint32_t i, const NbLists& L, con
         ax += f * c * dx; ay += f * c * dy;
       }
     });
+    ax *= scale; ay *= scale;
   }
   ay += P.gravity;
   if (P.has_pull) {
@@ -89,10 +151,15 @@ __device__ __forceinline__ void viscosity_body(uint32_t i, const NbLists& L, con
 __global__ void __launch_bounds__(kThreads)
 k_viscosity(uint32_t n, NbLists L, const float4* __restrict__ xv_in, const float2* __restrict__ hm, const float* __restrict__ rho,
             const PackedParams P, const StepCtl* __restrict__ ctl, float4* __restrict__ xv_out) {
+  __shared__ float4 s_pack[kWin];
+  __shared__ float2 s_hm[kWin];
+  __shared__ float s_aux[kWin];
+  const bool uni = ctl->hmin == ctl->hmax;
+  stage_window<true>(n, uni, xv_in, hm, rho, s_pack, s_hm, s_aux);
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (ctl->hmin == ctl->hmax) viscosity_body<true>(i, L, xv_in, hm, rho, P, ctl->dt, xv_out);
-  else viscosity_body<false>(i, L, xv_in, hm, rho, P, ctl->dt, xv_out);
+  if (uni) viscosity_body<true>(i, L, s_pack, s_hm, s_aux, xv_in, hm, rho, P, ctl->dt, xv_out);
+  else viscosity_body<false>(i, L, s_pack, s_hm, s_aux, xv_in, hm, rho, P, ctl->dt, xv_out);
 }
 
 // ---------------------------------------------------------------------------------------------- K13
@@ -102,6 +169,10 @@ __global__ void __launch_bounds__(kThreads)
 k_source(uint32_t n, NbLists L, const float4* __restrict__ xv, const float2* __restrict__ hm, const float* __restrict__ rho,
          float4* __restrict__ pconst, float4* __restrict__ packP0, float4* __restrict__ packA, const StepCtl* __restrict__ ctl,
          float rho0, int kind) {
+  __shared__ float4 s_pack[kWin];
+  __shared__ float2 s_hm[kWin];
+  const bool uni = ctl->hmin == ctl->hmax;
+  if (kind != 1) stage_window<false>(n, uni, xv, hm, nullptr, s_pack, s_hm, nullptr);
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float dt = ctl->dt;
@@ -112,9 +183,10 @@ k_source(uint32_t n, NbLists L, const float4* __restrict__ xv, const float2* __r
   if (kind != 1) {
     const float2 own = hm[i];
     float sum = 0.f;
-    auto body = [&](const float4& o, float dx, float dy, float c, uint32_t) { sum += c * ((o.z - me.z) * dx + (o.w - me.w) * dy); };
-    if (ctl->hmin == ctl->hmax) for_each_pair<true>(L, i, xv, hm, me.x, me.y, own.x, own.y, body);
-    else for_each_pair<false>(L, i, xv, hm, me.x, me.y, own.x, own.y, body);
+    auto body = [&](const float4& o, float dx, float dy, float c, float, float) { sum += c * ((o.z - me.z) * dx + (o.w - me.w) * dy); };
+    const float scale = uni ? for_each_pair<true, false>(L, i, s_pack, s_hm, nullptr, xv, hm, nullptr, me.x, me.y, own.x, own.y, body)
+                            : for_each_pair<false, false>(L, i, s_pack, s_hm, nullptr, xv, hm, nullptr, me.x, me.y, own.x, own.y, body);
+    sum *= scale;
     const float div = sum / rho_i - (me.z * pc.x + me.w * pc.y);
     s = -div / dt;
   }
@@ -137,21 +209,27 @@ k_accel(uint32_t n, NbLists L, const float4* __restrict__ P0, const float4* __re
         const float2* __restrict__ gB, float4* __restrict__ packA, StepCtl* ctl, float4* __restrict__ xv, float2* __restrict__ pos,
         float2* __restrict__ vel, float hybrid_factor, const uint32_t* __restrict__ gid) {
   if (MODE == 0 && ctl->solver.done) return;
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  __shared__ float4 s_pack[kWin];
+  __shared__ float2 s_hm[kWin];
   const float4* __restrict__ packP = (ctl->solver.sweeps & 1) ? P1 : P0;
-  const float4 me = packP[i];
-  float ax = 0.f, ay = 0.f;
   // After a sweep that left no particle with positive pressure (normal == 0: every p' was clamped to 0 or was
   // singular) the whole pressure field is zero and so is a^p; skip the pair sum.
-  if (MODE == 0 || ctl->solver.normal != 0) {
+  const bool pairs = MODE == 0 || ctl->solver.normal != 0;
+  const bool uni = ctl->hmin == ctl->hmax;
+  if (pairs) stage_window<false>(n, uni, packP, hm, nullptr, s_pack, s_hm, nullptr);
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 me = packP[i];
+  float ax = 0.f, ay = 0.f;
+  if (pairs) {
     const float2 own = hm[i];
-    auto body = [&](const float4& o, float dx, float dy, float c, uint32_t) {
+    auto body = [&](const float4& o, float dx, float dy, float c, float, float) {
       const float f = c * (me.z + o.z);
       ax -= f * dx; ay -= f * dy;
     };
-    if (ctl->hmin == ctl->hmax) for_each_pair<true>(L, i, packP, hm, me.x, me.y, own.x, own.y, body);
-    else for_each_pair<false>(L, i, packP, hm, me.x, me.y, own.x, own.y, body);
+    const float scale = uni ? for_each_pair<true, false>(L, i, s_pack, s_hm, nullptr, packP, hm, nullptr, me.x, me.y, own.x, own.y, body)
+                            : for_each_pair<false, false>(L, i, s_pack, s_hm, nullptr, packP, hm, nullptr, me.x, me.y, own.x, own.y, body);
+    ax *= scale; ay *= scale;
     const float2 g = gB[i];
     ax -= me.w * g.x;
     ay -= me.w * g.y;
@@ -204,6 +282,10 @@ k_jacobi(uint32_t n, NbLists L, const float4* __restrict__ packA, float4* __rest
          float* __restrict__ blockstats, float omega, float rho0, float tol, int max_iters, int density_mode,
          const uint32_t* __restrict__ gid) {
   if (ctl->solver.done) return;
+  __shared__ float4 s_pack[kWin];
+  __shared__ float2 s_hm[kWin];
+  const bool uni = ctl->hmin == ctl->hmax;
+  stage_window<false>(n, uni, packA, hm, nullptr, s_pack, s_hm, nullptr);
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const float dt = ctl->dt;
   const bool odd = (ctl->solver.sweeps & 1) != 0;
@@ -225,9 +307,10 @@ k_jacobi(uint32_t n, NbLists L, const float4* __restrict__ packA, float4* __rest
     } else {
       const float2 own = hm[i];
       float sum = 0.f;
-      auto body = [&](const float4& o, float dx, float dy, float c, uint32_t) { sum += c * ((o.z - me.z) * dx + (o.w - me.w) * dy); };
-      if (ctl->hmin == ctl->hmax) for_each_pair<true>(L, i, packA, hm, me.x, me.y, own.x, own.y, body);
-      else for_each_pair<false>(L, i, packA, hm, me.x, me.y, own.x, own.y, body);
+      auto body = [&](const float4& o, float dx, float dy, float c, float, float) { sum += c * ((o.z - me.z) * dx + (o.w - me.w) * dy); };
+      const float scale = uni ? for_each_pair<true, false>(L, i, s_pack, s_hm, nullptr, packA, hm, nullptr, me.x, me.y, own.x, own.y, body)
+                              : for_each_pair<false, false>(L, i, s_pack, s_hm, nullptr, packA, hm, nullptr, me.x, me.y, own.x, own.y, body);
+      sum *= scale;
       const float Ap = sum / rho_i - (me.z * pc.x + me.w * pc.y);
       const float resid = pc.w - Ap;
       pn = p_old + omega * resid / pc.z;
@@ -357,41 +440,44 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
   int& predicted = sim->predicted_sweeps[density_mode ? 1 : 0];
   int batch = std::max(1, std::min(predicted, 256));
   const int max_sweeps = sim->pp.max_iters + 1;
-  struct Timed { int sweep; cudaEvent_t e0, e1, e2; };
+  struct Timed { int sweep; cudaEvent_t e0, e1, e1b, e2; };  // e0..e1: K14; e1b..e2: K15 (halo exchanges excluded)
   std::vector<Timed> timed;
   for (;;) {
     for (int b = 0; b < batch && launched < max_sweeps; b++, launched++) {
       const bool time_it = sim->kt_every > 0 && (launched % sim->kt_every) == 0;
-      Timed tm{launched, nullptr, nullptr, nullptr};
-      if (time_it) { tm.e0 = kt_event(sim); tm.e1 = kt_event(sim); tm.e2 = kt_event(sim); cudaEventRecord(tm.e0, st); }
+      Timed tm{launched, nullptr, nullptr, nullptr, nullptr};
+      if (time_it) { tm.e0 = kt_event(sim); tm.e1 = kt_event(sim); tm.e1b = kt_event(sim); tm.e2 = kt_event(sim); cudaEventRecord(tm.e0, st); }
       if (launched > 0) {  // sweep 0: a^p = 0 was written by k_source
         k_accel<0><<<blocks, kThreads, 0, st>>>(n, L, sim->packP[0].p, sim->packP[1].p, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, nullptr,
                                                 nullptr, nullptr, 0.f, gid);
         LAUNCH_CHECK();
+        if (time_it) cudaEventRecord(tm.e1, st);
         if (sim->dist) TRY(dist_halo(sim, sim->packA.p, 16));
+      } else if (time_it) {
+        cudaEventRecord(tm.e1, st);
       }
-      if (time_it) cudaEventRecord(tm.e1, st);
+      if (time_it) cudaEventRecord(tm.e1b, st);
       k_jacobi<<<blocks, kThreads, 0, st>>>(n, L, sim->packA.p, sim->packP[0].p, sim->packP[1].p, sim->hm.p, sim->pconst.p, sim->rho.p,
                                             sim->ctl, sim->blockstats.p, sim->pp.jacobi_omega, sim->pp.rest_density, max_avg_error,
                                             sim->pp.max_iters, density_mode ? 1 : 0, gid);
       LAUNCH_CHECK();
+      if (time_it) { cudaEventRecord(tm.e2, st); timed.push_back(tm); }
       if (sim->dist) {
         TRY(dist_solver_reduce(sim));
         k_solver_decide<<<1, 1, 0, st>>>(sim->ctl, sim->pp.rest_density, max_avg_error, sim->pp.max_iters, density_mode ? 1 : 0);
         LAUNCH_CHECK();
         TRY(dist_halo_pressure(sim));
       }
-      if (time_it) { cudaEventRecord(tm.e2, st); timed.push_back(tm); }
     }
     TRY(sync_ctl(sim));
     const SolverCtl& s = sim->ctl_host->solver;
     for (const Timed& tm : timed) {
       float a = 0.f, b2 = 0.f;
-      if (tm.sweep < s.sweeps && cudaEventElapsedTime(&a, tm.e0, tm.e1) == cudaSuccess && cudaEventElapsedTime(&b2, tm.e1, tm.e2) == cudaSuccess) {
+      if (tm.sweep < s.sweeps && cudaEventElapsedTime(&a, tm.e0, tm.e1) == cudaSuccess && cudaEventElapsedTime(&b2, tm.e1b, tm.e2) == cudaSuccess) {
         if (tm.sweep > 0) { sim->kt_ms[ASPH_KT_ACCEL_SWEEP] += a; sim->kt_samples[ASPH_KT_ACCEL_SWEEP]++; }  // sweep 0 has no K14 launch
         sim->kt_ms[ASPH_KT_JACOBI_SWEEP] += b2; sim->kt_samples[ASPH_KT_JACOBI_SWEEP]++;
       }
-      kt_release(sim, tm.e0); kt_release(sim, tm.e1); kt_release(sim, tm.e2);
+      kt_release(sim, tm.e0); kt_release(sim, tm.e1); kt_release(sim, tm.e1b); kt_release(sim, tm.e2);
     }
     timed.clear();
     if (sim->ctl_host->error_flags & ERRF_LIST_CAPACITY) return ASPH_RETRY_LISTS;

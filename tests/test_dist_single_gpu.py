@@ -28,7 +28,8 @@ def test_one_rank_distributed_equals_plain(asph, cuda_lib, default_params):
         dt_d, dt_s = d.single_step(), s.single_step()
         assert dt_d == dt_s
         assert d.step_info()["density_sweeps"] == s.step_info()["density_sweeps"]
-        most = max(most, s.step_info()["density_sweeps"])
+        assert d.step_info()["div_sweeps"] == s.step_info()["div_sweeps"]
+        most = max(most, s.step_info()["density_sweeps"], s.step_info()["div_sweeps"])
     assert d.num_fluid_particles() == n
     gidx = d.global_index()
     assert np.array_equal(np.sort(gidx), np.arange(n, dtype=np.uint32))
