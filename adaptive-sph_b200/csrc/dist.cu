@@ -523,12 +523,12 @@ static int halo_impl(asph_sim* sim, void* f0, void* f1, const StepCtl* ctl, int 
 }
 
 int dist_halo(asph_sim* sim, void* field, int elem_bytes) { return halo_impl(sim, field, field, nullptr, elem_bytes); }
-int dist_halo_pressure(asph_sim* sim) { return halo_impl(sim, sim->packP[0].p, sim->packP[1].p, sim->ctl, 16); }
 
-int dist_solver_reduce(asph_sim* sim) {
+int dist_solver_reduce(asph_sim* sim, int slot) {
   DistState* D = sim->dist;
   if (D->nranks == 1) return ASPH_OK;
-  NCCL_TRY(nccl().AllReduce(sim->ctl->solver.partial, sim->ctl->solver.partial, 4, ncclDouble, ncclSum, D->comm, sim->stream));
+  unsigned long long* acc = sim->ctl->solver.acc[slot];
+  NCCL_TRY(nccl().AllReduce(acc, acc, ASPH_ACC_WORDS, ncclUint64, ncclSum, D->comm, sim->stream));
   return ASPH_OK;
 }
 

@@ -36,6 +36,7 @@ struct NbCol {
   uint32_t bias;        // i0 - 32768 (mod 2^32)
   uint32_t cn, ce;      // real neighbours in the 2h range / in the extended range
   bool wide;
+  __device__ __forceinline__ NbCol() : p16(nullptr), p32(nullptr), bias(0), cn(0), ce(0), wide(false) {}  // empty column
   __device__ __forceinline__ NbCol(const NbLists& L, uint32_t i) {
     const uint32_t sb = __ldg(&L.slice_base[i >> 5]);
     const uint32_t c = __ldg(&L.cnt[i]);
@@ -66,6 +67,15 @@ struct NbCol {
       j[0] = a.x; j[1] = a.y; j[2] = a.z; j[3] = a.w;
       j[4] = b.x; j[5] = b.y; j[6] = b.z; j[7] = b.w;
     }
+  }
+  // raw rows [k0, k0 + 8) of a narrow column (8 x uint16), and their decoding into window offsets
+  __device__ __forceinline__ uint4 raw8(uint32_t k0) const { return __ldcs(reinterpret_cast<const uint4*>(p16 + (k0 >> 3) * 256u)); }
+  static __device__ __forceinline__ void decode8(const uint4& v, uint32_t halo, uint32_t (&off)[8]) {
+    const uint32_t K = 32768u - halo;
+    off[0] = (v.x & 0xffffu) - K; off[1] = (v.x >> 16) - K;
+    off[2] = (v.y & 0xffffu) - K; off[3] = (v.y >> 16) - K;
+    off[4] = (v.z & 0xffffu) - K; off[5] = (v.z >> 16) - K;
+    off[6] = (v.w & 0xffffu) - K; off[7] = (v.w >> 16) - K;
   }
   // same rows as window offsets: off = j - wa with wa = b0 - halo (mod 2^32); narrow rows need one subtraction.
   // WIDE is warp-uniform (a property of the slice), so callers branch on it once outside their loops.
@@ -138,6 +148,11 @@ __device__ __forceinline__ float2 lds_f2(uint32_t addr) {
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
   return v;
 }
+// asynchronous global -> shared copies (LDGSTS): no register staging, completion awaited by cp_async_wait_all
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async8(uint32_t saddr, const void* g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(saddr), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(saddr), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ float lds_f1(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));

@@ -49,16 +49,23 @@ __host__ __device__ __forceinline__ unsigned long long level_cells(int nx, int n
   return (unsigned long long)((nx + ASPH_STRIP - 1) >> ASPH_STRIP_LOG2) * (unsigned long long)ny * ASPH_STRIP;
 }
 
+// Relaxed-Jacobi solver state.  Sweep number s (0, 1, ...) accumulates its PressureSolverStatistics
+// (simulation.rs:397-469) into slot s % 3 with integer atomics only — counts, and the error sum in 2^-32 fixed point —
+// so the totals do not depend on the order in which blocks finish, and (multi-GPU) a plain integer all-reduce of the slot
+// gives every rank the same numbers.  The loop control (simulation.rs:1453-1477) is evaluated from the slot by the next
+// kernel in the stream: every block of the next pressure-acceleration pass derives the same stop decision in its
+// prologue (no ticket, no fence, no extra launch); block 0 records it here for the host.
+#define ASPH_ACC_COPIES 8   // each slot is spread over 8 copies (by block index) to keep same-address atomics apart
+#define ASPH_ACC_WORDS (2 * ASPH_ACC_COPIES + 1)
 struct SolverCtl {
   int k;       // index of the sweep being executed (num_pressure_iters, simulation.rs:1388)
-  int done;    // set by the sweep that satisfies the stop rule of simulation.rs:1453-1477
-  int sweeps;  // sweeps executed
-  unsigned long long normal, singular, negative;
+  int done;    // set once a sweep satisfies the stop rule
+  int sweeps;  // sweeps executed and evaluated
+  unsigned long long normal, singular, negative;  // statistics of the last evaluated sweep
   float err_sum, max_err, avg;
-  unsigned int ticket;
-  // multi-GPU: this rank's statistics of the sweep {normal, singular, negative, err_sum}; summed over the ranks
-  // (dist.cu) before k_solver_decide applies the stop rule identically everywhere
-  double partial[4];
+  unsigned int maxerr_enc[3];
+  // [slot][2 * copy + 0] = normal | negative << 32; [2 * copy + 1] = sum of err * 2^32 (two's complement); [16] = singular
+  unsigned long long acc[3][ASPH_ACC_WORDS];
 };
 
 struct StepCtl {
@@ -240,8 +247,7 @@ int dist_begin_step(asph_sim* sim, float f_search);        // migrate, exchange 
 int dist_allreduce_cfl(asph_sim* sim);                     // min over ranks of the CFL term, between k_prepare and k_make_levels
 int dist_after_sort(asph_sim* sim);                        // halo index maps in sorted order
 int dist_halo(asph_sim* sim, void* field, int elem_bytes); // owner -> ghost copies of one per-particle field
-int dist_halo_pressure(asph_sim* sim);                     // same for the pressure pack the device-side sweep parity selects
-int dist_solver_reduce(asph_sim* sim);                     // sum SolverCtl::partial over ranks
+int dist_solver_reduce(asph_sim* sim, int slot);           // sum SolverCtl::acc[slot] over ranks
 int dist_reduce_flags(asph_sim* sim, bool with_lists);     // make error flags (and "lists too small") agree on all ranks
 int dist_local_map(asph_sim* sim);                         // scratch_u[3][i] = slot of owned particle i in read-backs, ~0u for ghosts
 void dist_destroy(asph_sim* sim);

@@ -17,10 +17,62 @@ namespace {
 constexpr int kThreads = 256;
 
 __global__ void k_solver_reset(StepCtl* ctl) {
-  SolverCtl s;
-  s.k = 0; s.done = 0; s.sweeps = 0; s.normal = 0; s.singular = 0; s.negative = 0;
-  s.err_sum = 0.f; s.max_err = 0.f; s.avg = 0.f; s.ticket = 0;
-  ctl->solver = s;
+  SolverCtl& s = ctl->solver;
+  if (threadIdx.x == 0) {
+    s.k = 0; s.done = 0; s.sweeps = 0; s.normal = 0; s.singular = 0; s.negative = 0;
+    s.err_sum = 0.f; s.max_err = 0.f; s.avg = 0.f;
+    s.maxerr_enc[0] = s.maxerr_enc[1] = s.maxerr_enc[2] = 0u;
+  }
+  for (int t = threadIdx.x; t < 3 * ASPH_ACC_WORDS; t += blockDim.x) (&s.acc[0][0])[t] = 0ull;
+}
+
+// ---- loop control of iisph_pressure_iterations (simulation.rs:1405-1480) -------------------------------------------
+struct SweepTotals {
+  unsigned long long normal, negative, singular;
+  float err_sum;
+};
+__device__ __forceinline__ SweepTotals read_totals(const StepCtl* ctl, int sweep) {
+  const unsigned long long* acc = ctl->solver.acc[sweep % 3];
+  unsigned long long nn = 0, ng = 0;
+  long long e = 0;
+#pragma unroll
+  for (int c = 0; c < ASPH_ACC_COPIES; c++) {
+    const unsigned long long a = acc[2 * c], b = acc[2 * c + 1];  // written by an earlier kernel: ordinary cached loads
+    nn += a & 0xffffffffull; ng += a >> 32;
+    e += (long long)b;
+  }
+  SweepTotals t;
+  t.normal = nn; t.negative = ng; t.singular = acc[2 * ASPH_ACC_COPIES];
+  t.err_sum = float(double(e) * (1.0 / 4294967296.0));
+  return t;
+}
+// has the solver finished after sweep number `sweep` with these totals?
+__device__ __forceinline__ bool sweep_stops(const SweepTotals& t, int sweep, unsigned int error_flags, float dt, float rho0, float tol,
+                                            int max_iters, int density_mode) {
+  const float avg = t.normal > 0 ? t.err_sum / float(t.normal) : __int_as_float(0x7fc00000);
+  bool stop;
+  if (density_mode) stop = (t.normal == 0) || (fabsf(avg / rho0) < tol && sweep > 1);
+  else stop = (t.normal == 0) || (fabsf(avg) < tol / dt && sweep > 1);
+  return stop || sweep == max_iters || (error_flags & ERRF_SOLVER_NONFINITE) != 0u;
+}
+// one thread: publish the evaluation of sweep number `sweep` for the host and recycle the accumulator slot of sweep + 2
+__device__ __forceinline__ void record_sweep(StepCtl* ctl, const SweepTotals& t, int sweep, bool stop) {
+  SolverCtl& s = ctl->solver;
+  s.normal = t.normal; s.negative = t.negative; s.singular = t.singular; s.err_sum = t.err_sum;
+  s.avg = t.normal > 0 ? t.err_sum / float(t.normal) : __int_as_float(0x7fc00000);
+  s.max_err = dec_f(s.maxerr_enc[sweep % 3]);
+  s.sweeps = sweep + 1;
+  if (stop) { s.done = 1; s.k = sweep; }
+  else s.k = sweep + 1;
+  unsigned long long* nxt = s.acc[(sweep + 2) % 3];
+  for (int c = 0; c < ASPH_ACC_WORDS; c++) nxt[c] = 0ull;
+  s.maxerr_enc[(sweep + 2) % 3] = 0u;
+}
+// end of a batch of sweeps: evaluate the last one launched (the next batch's first kernel would do the same)
+__global__ void k_solver_decide(StepCtl* ctl, int sweep, float rho0, float tol, int max_iters, int density_mode) {
+  if (ctl->solver.done || ctl->solver.sweeps > sweep) return;
+  const SweepTotals t = read_totals(ctl, sweep);
+  record_sweep(ctl, t, sweep, sweep_stops(t, sweep, ctl->error_flags, ctl->dt, rho0, tol, max_iters, density_mode));
 }
 
 // ---- shared-memory window ------------------------------------------------------------------------------------
@@ -34,97 +86,127 @@ static_assert(kThreads == int(ASPH_PAIR_BLOCK), "the neighbour index bias is ali
 constexpr uint32_t kHalo = 192;
 constexpr uint32_t kWin = kThreads + 2 * kHalo;
 
-template <bool AUX>
-__device__ __forceinline__ void stage_window(uint32_t n, bool uni, const float4* __restrict__ pack, const float2* __restrict__ hm,
-                                             const float* __restrict__ aux, float4 (&s_pack)[kWin], float2 (&s_hm)[kWin], float* s_aux) {
-  const uint32_t wa = blockIdx.x * kThreads - kHalo;
-  for (uint32_t t = threadIdx.x; t < kWin; t += kThreads) {
-    const uint32_t g = wa + t;
-    if (g < n) {
-      s_pack[t] = __ldg(&pack[g]);
-      if (!uni) s_hm[t] = __ldg(&hm[g]);
-      if (AUX) s_aux[t] = __ldg(&aux[g]);
+// Per-block context of a pair pass.  Order inside a kernel: issue() the asynchronous window copy, construct the
+// thread's PairCol (slice header, counts, first two index chunks) and load the thread's own values, then wait() —
+// so the three kinds of global-memory latency overlap instead of following one another.
+struct PairWindow {
+  uint32_t sp, sh, sa;  // shared addresses of the staged pack / {h, m} / aux arrays
+  template <bool AUX>
+  __device__ __forceinline__ void issue(uint32_t n, bool uni, const float4* __restrict__ pack, const float2* __restrict__ hm,
+                                        const float* __restrict__ aux, float4 (&s_pack)[kWin], float2 (&s_hm)[kWin], float* s_aux) {
+    sp = uint32_t(__cvta_generic_to_shared(&s_pack[0]));
+    sh = uint32_t(__cvta_generic_to_shared(&s_hm[0]));
+    sa = AUX ? uint32_t(__cvta_generic_to_shared(s_aux)) : 0u;
+    // pinned in registers (the compiler would otherwise re-derive them from the CTA id special register at every gather)
+    asm volatile("" : "+r"(sp), "+r"(sh), "+r"(sa));
+    const uint32_t wa = blockIdx.x * kThreads - kHalo;
+    for (uint32_t t = threadIdx.x; t < kWin; t += kThreads) {
+      const uint32_t g = wa + t;
+      if (g < n) {
+        cp_async16(sp + t * 16u, pack + g);
+        if (!uni) cp_async8(sh + t * 8u, hm + g);
+        if (AUX) cp_async4(sa + t * 4u, aux + g);
+      }
     }
   }
-  __syncthreads();
-}
+  __device__ __forceinline__ void wait() const {
+    cp_async_wait_all();
+    __syncthreads();
+  }
+};
+
+struct PairCol {  // a thread's column header plus its first 16 rows, requested before the window barrier
+  NbCol col;
+  uint4 c0, c1;
+  __device__ __forceinline__ PairCol(const NbLists& L, uint32_t i, bool active) : c0(make_uint4(0, 0, 0, 0)), c1(make_uint4(0, 0, 0, 0)) {
+    if (active) {
+      col = NbCol(L, i);
+      if (!col.wide) {
+        if (col.cn > 0u) c0 = col.raw8(0);
+        if (col.cn > 8u) c1 = col.raw8(8);
+      }
+    }
+  }
+};
 
 // Σ over N_2(i) of f(pack[j], x_ij, c_ij, h_ij, aux[j]); the caller multiplies its sums by the returned scale:
 //   uniform h (UNI):  c_ij = w'(q)/r un-normalised,   scale = m * 40 / (7 pi (2h)^3)
 //   otherwise:        c_ij = m_j * dW/dr / r,         scale = 1
-// (every f is linear in c).  A column is consumed 8 rows at a time: one vector load of indices, then the gathers
-// (shared memory, or global for the few outside the window), then the arithmetic.  Padding rows point at the particle
-// itself (zero distance => c = 0), so there are no per-entry bounds checks.
-template <bool UNI, bool AUX, bool WIDE, class F>
-__device__ __forceinline__ void pair_rows(const NbCol& col, uint32_t sp, uint32_t sh, uint32_t sa, const float4* __restrict__ pack,
-                                          const float2* __restrict__ hm, const float* __restrict__ aux, float xi, float yi, float hi,
-                                          const PairShape& shape, F& f) {
+// (every f is linear in c).  A column is consumed 8 rows at a time: the gathers (shared memory, or global for the few
+// rows outside the window), then the arithmetic.  Padding rows point at the particle itself (zero distance =>
+// c = 0), so there are no per-entry bounds checks.  The index chunk two iterations ahead is always in flight.
+template <bool UNI, bool AUX, class F>
+__device__ __forceinline__ void pair_chunk(const uint32_t (&off)[8], const PairWindow& W, const float4* __restrict__ pack,
+                                           const float2* __restrict__ hm, const float* __restrict__ aux, float xi, float yi, float hi,
+                                           const PairShape& shape, F& f) {
   const uint32_t wa = blockIdx.x * kThreads - kHalo;
-  for (uint32_t k0 = 0; k0 < col.cn; k0 += 8u) {
-    uint32_t off[8];
-    col.get8_off<WIDE>(k0, kHalo, off);
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
-      float4 o[4];
-      float2 t[4];
-      float a[4];
+  for (int half = 0; half < 2; half++) {
+    float4 o[4];
+    float2 t[4];
+    float a[4];
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const uint32_t of = off[half * 4 + u];
-        if (of < kWin) {
-          o[u] = lds_f4(sp + of * 16u);
-          if (!UNI) t[u] = lds_f2(sh + of * 8u);
-          if (AUX) a[u] = lds_f1(sa + of * 4u);
-        } else {
-          const uint32_t jj = wa + of;
-          o[u] = __ldg(pack + jj);
-          if (!UNI) t[u] = __ldg(hm + jj);
-          if (AUX) a[u] = __ldg(aux + jj);
-        }
+    for (int u = 0; u < 4; u++) {
+      const uint32_t of = off[half * 4 + u];
+      if (of < kWin) {
+        o[u] = lds_f4(W.sp + of * 16u);
+        if (!UNI) t[u] = lds_f2(W.sh + of * 8u);
+        if (AUX) a[u] = lds_f1(W.sa + of * 4u);
+      } else {
+        const uint32_t jj = wa + of;
+        o[u] = __ldg(pack + jj);
+        if (!UNI) t[u] = __ldg(hm + jj);
+        if (AUX) a[u] = __ldg(aux + jj);
       }
+    }
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const float dx = xi - o[u].x, dy = yi - o[u].y;
-        const float d2 = dx * dx + dy * dy;
-        if (UNI) {
-          f(o[u], dx, dy, shape(d2), hi, AUX ? a[u] : 0.f);
-        } else {
-          const float hij = (hi + t[u].x) * 0.5f;
-          f(o[u], dx, dy, t[u].y * pair_g(d2, hij), hij, AUX ? a[u] : 0.f);
-        }
+    for (int u = 0; u < 4; u++) {
+      const float dx = xi - o[u].x, dy = yi - o[u].y;
+      const float d2 = dx * dx + dy * dy;
+      if (UNI) {
+        f(o[u], dx, dy, shape(d2), hi, AUX ? a[u] : 0.f);
+      } else {
+        const float hij = (hi + t[u].x) * 0.5f;
+        f(o[u], dx, dy, t[u].y * pair_g(d2, hij), hij, AUX ? a[u] : 0.f);
       }
     }
   }
 }
 template <bool UNI, bool AUX, class F>
-__device__ __forceinline__ float for_each_pair(const NbLists& L, uint32_t i, const float4 (&s_pack)[kWin], const float2 (&s_hm)[kWin],
-                                               const float* s_aux, const float4* __restrict__ pack, const float2* __restrict__ hm,
-                                               const float* __restrict__ aux, float xi, float yi, float hi, float mi, F f) {
-  const NbCol col(L, i);
+__device__ __forceinline__ float for_each_pair(const PairCol& P, const PairWindow& W, const float4* __restrict__ pack,
+                                               const float2* __restrict__ hm, const float* __restrict__ aux, float xi, float yi, float hi,
+                                               float mi, F f) {
+  const NbCol& col = P.col;
   const float inv2h = fast_rcp(2.f * hi);
   const PairShape shape(inv2h);
-  // shared-window base addresses, pinned in registers (the compiler would otherwise re-derive them from the CTA id
-  // special register at every gather)
-  uint32_t sp = uint32_t(__cvta_generic_to_shared(&s_pack[0]));
-  uint32_t sh = uint32_t(__cvta_generic_to_shared(&s_hm[0]));
-  uint32_t sa = AUX ? uint32_t(__cvta_generic_to_shared(s_aux)) : 0u;
-  asm volatile("" : "+r"(sp), "+r"(sh), "+r"(sa));
-  if (!col.wide) pair_rows<UNI, AUX, false>(col, sp, sh, sa, pack, hm, aux, xi, yi, hi, shape, f);
-  else pair_rows<UNI, AUX, true>(col, sp, sh, sa, pack, hm, aux, xi, yi, hi, shape, f);
+  if (!col.wide) {
+    uint4 cur = P.c0, nxt = P.c1;
+    for (uint32_t k0 = 0; k0 < col.cn; k0 += 8u) {
+      const uint4 v = cur;
+      cur = nxt;
+      if (k0 + 16u < col.cn) nxt = col.raw8(k0 + 16u);
+      uint32_t off[8];
+      NbCol::decode8(v, kHalo, off);
+      pair_chunk<UNI, AUX>(off, W, pack, hm, aux, xi, yi, hi, shape, f);
+    }
+  } else {
+    for (uint32_t k0 = 0; k0 < col.cn; k0 += 8u) {
+      uint32_t off[8];
+      col.get8_off<true>(k0, kHalo, off);
+      pair_chunk<UNI, AUX>(off, W, pack, hm, aux, xi, yi, hi, shape, f);
+    }
+  }
   return UNI ? mi * (ASPH_KNORM * inv2h * inv2h * inv2h) : 1.f;
 }
 
 // ---------------------------------------------------------------------------------------------- K12
 template <bool UNI>
-__device__ __forceinline__ void viscosity_body(uint32_t i, const NbLists& L, const float4 (&s_pack)[kWin], const float2 (&s_hm)[kWin],
-                                               const float* s_aux, const float4* __restrict__ xv_in, const float2* __restrict__ hm,
-                                               const float* __restrict__ rho, const PackedParams& P, float dt, float4* __restrict__ xv_out) {
-  const float4 me = xv_in[i];
-  const float2 own = hm[i];
-  const float rho_i = rho[i];
+__device__ __forceinline__ void viscosity_body(uint32_t i, const PairCol& C, const PairWindow& W, const float4& me, const float2& own, float rho_i,
+                                               const float4* __restrict__ xv_in, const float2* __restrict__ hm, const float* __restrict__ rho,
+                                               const PackedParams& P, float dt, float4* __restrict__ xv_out) {
   float ax = 0.f, ay = 0.f;
   if (P.viscosity_type != ASPH_VISC_XSPH && P.viscosity != 0.f) {
-    const float scale = for_each_pair<UNI, true>(L, i, s_pack, s_hm, s_aux, xv_in, hm, rho, me.x, me.y, own.x, own.y,
+    const float scale = for_each_pair<UNI, true>(C, W, xv_in, hm, rho, me.x, me.y, own.x, own.y,
                              [&](const float4& o, float dx, float dy, float c, float hij, float rho_j) {
       const float est = dx * (me.z - o.z) + dy * (me.w - o.w);
       if (est < 0.f) {
@@ -155,11 +237,19 @@ k_viscosity(uint32_t n, NbLists L, const float4* __restrict__ xv_in, const float
   __shared__ float2 s_hm[kWin];
   __shared__ float s_aux[kWin];
   const bool uni = ctl->hmin == ctl->hmax;
-  stage_window<true>(n, uni, xv_in, hm, rho, s_pack, s_hm, s_aux);
+  PairWindow W;
+  W.issue<true>(n, uni, xv_in, hm, rho, s_pack, s_hm, s_aux);
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (uni) viscosity_body<true>(i, L, s_pack, s_hm, s_aux, xv_in, hm, rho, P, ctl->dt, xv_out);
-  else viscosity_body<false>(i, L, s_pack, s_hm, s_aux, xv_in, hm, rho, P, ctl->dt, xv_out);
+  const bool active = i < n;
+  const PairCol C(L, i, active);
+  float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+  float2 own = make_float2(1.f, 0.f);
+  float rho_i = 1.f;
+  if (active) { me = xv_in[i]; own = hm[i]; rho_i = rho[i]; }
+  W.wait();
+  if (!active) return;
+  if (uni) viscosity_body<true>(i, C, W, me, own, rho_i, xv_in, hm, rho, P, ctl->dt, xv_out);
+  else viscosity_body<false>(i, C, W, me, own, rho_i, xv_in, hm, rho, P, ctl->dt, xv_out);
 }
 
 // ---------------------------------------------------------------------------------------------- K13
@@ -172,20 +262,25 @@ k_source(uint32_t n, NbLists L, const float4* __restrict__ xv, const float2* __r
   __shared__ float4 s_pack[kWin];
   __shared__ float2 s_hm[kWin];
   const bool uni = ctl->hmin == ctl->hmax;
-  if (kind != 1) stage_window<false>(n, uni, xv, hm, nullptr, s_pack, s_hm, nullptr);
+  const bool pairs = kind != 1;
+  PairWindow W;
+  if (pairs) W.issue<false>(n, uni, xv, hm, nullptr, s_pack, s_hm, nullptr);
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const bool active = i < n;
+  const PairCol C(L, i, active && pairs);
+  float4 me = make_float4(0.f, 0.f, 0.f, 0.f), pc = me;
+  float2 own = make_float2(1.f, 0.f);
+  float rho_i = 1.f;
+  if (active) { me = xv[i]; pc = pconst[i]; rho_i = rho[i]; own = hm[i]; }
+  if (pairs) W.wait();
+  if (!active) return;
   const float dt = ctl->dt;
-  const float4 me = xv[i];
-  float4 pc = pconst[i];
-  const float rho_i = rho[i];
   float s = 0.f;
-  if (kind != 1) {
-    const float2 own = hm[i];
+  if (pairs) {
     float sum = 0.f;
     auto body = [&](const float4& o, float dx, float dy, float c, float, float) { sum += c * ((o.z - me.z) * dx + (o.w - me.w) * dy); };
-    const float scale = uni ? for_each_pair<true, false>(L, i, s_pack, s_hm, nullptr, xv, hm, nullptr, me.x, me.y, own.x, own.y, body)
-                            : for_each_pair<false, false>(L, i, s_pack, s_hm, nullptr, xv, hm, nullptr, me.x, me.y, own.x, own.y, body);
+    const float scale = uni ? for_each_pair<true, false>(C, W, xv, hm, nullptr, me.x, me.y, own.x, own.y, body)
+                            : for_each_pair<false, false>(C, W, xv, hm, nullptr, me.x, me.y, own.x, own.y, body);
     sum *= scale;
     const float div = sum / rho_i - (me.z * pc.x + me.w * pc.y);
     s = -div / dt;
@@ -207,28 +302,45 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 k_accel(uint32_t n, NbLists L, const float4* __restrict__ P0, const float4* __restrict__ P1, const float2* __restrict__ hm,
         const float2* __restrict__ gB, float4* __restrict__ packA, StepCtl* ctl, float4* __restrict__ xv, float2* __restrict__ pos,
-        float2* __restrict__ vel, float hybrid_factor, const uint32_t* __restrict__ gid) {
-  if (MODE == 0 && ctl->solver.done) return;
+        float2* __restrict__ vel, float hybrid_factor, const uint32_t* __restrict__ gid, int sweep, float rho0, float tol, int max_iters,
+        int density_mode) {
   __shared__ float4 s_pack[kWin];
   __shared__ float2 s_hm[kWin];
-  const float4* __restrict__ packP = (ctl->solver.sweeps & 1) ? P1 : P0;
+  __shared__ int s_stop;
+  if (MODE == 0 && ctl->solver.done) return;
+  const int parity = MODE == 0 ? (sweep & 1) : (ctl->solver.sweeps & 1);  // final passes run after k_solver_decide
+  const float4* __restrict__ packP = parity ? P1 : P0;
   // After a sweep that left no particle with positive pressure (normal == 0: every p' was clamped to 0 or was
   // singular) the whole pressure field is zero and so is a^p; skip the pair sum.
   const bool pairs = MODE == 0 || ctl->solver.normal != 0;
   const bool uni = ctl->hmin == ctl->hmax;
-  if (pairs) stage_window<false>(n, uni, packP, hm, nullptr, s_pack, s_hm, nullptr);
+  PairWindow W;
+  if (pairs) W.issue<false>(n, uni, packP, hm, nullptr, s_pack, s_hm, nullptr);
+  if (MODE == 0 && threadIdx.x == 0) {
+    // prologue of sweep number `sweep` >= 1: the stop rule for sweep - 1 from its totals, once per block, while the
+    // window copy is in flight; block 0 also records it for the host
+    const SweepTotals t = read_totals(ctl, sweep - 1);
+    const bool stop = sweep_stops(t, sweep - 1, ctl->error_flags, ctl->dt, rho0, tol, max_iters, density_mode);
+    if (blockIdx.x == 0) record_sweep(ctl, t, sweep - 1, stop);
+    s_stop = stop ? 1 : 0;
+  }
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 me = packP[i];
+  const bool active = i < n;
+  const PairCol C(L, i, active && pairs);
+  float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+  float2 own = make_float2(1.f, 0.f), g = make_float2(0.f, 0.f);
+  if (active) { me = packP[i]; own = hm[i]; g = gB[i]; }
+  if (pairs) W.wait();
+  if (MODE == 0 && s_stop) return;  // the solve ended with the previous sweep
+  if (!active) return;
   float ax = 0.f, ay = 0.f;
   if (pairs) {
-    const float2 own = hm[i];
     auto body = [&](const float4& o, float dx, float dy, float c, float, float) {
       const float f = c * (me.z + o.z);
       ax -= f * dx; ay -= f * dy;
     };
-    const float scale = uni ? for_each_pair<true, false>(L, i, s_pack, s_hm, nullptr, packP, hm, nullptr, me.x, me.y, own.x, own.y, body)
-                            : for_each_pair<false, false>(L, i, s_pack, s_hm, nullptr, packP, hm, nullptr, me.x, me.y, own.x, own.y, body);
+    const float scale = uni ? for_each_pair<true, false>(C, W, packP, hm, nullptr, me.x, me.y, own.x, own.y, body)
+                            : for_each_pair<false, false>(C, W, packP, hm, nullptr, me.x, me.y, own.x, own.y, body);
     ax *= scale; ay *= scale;
     const float2 g = gB[i];
     ax -= me.w * g.x;
@@ -260,56 +372,45 @@ k_accel(uint32_t n, NbLists L, const float4* __restrict__ P0, const float4* __re
   }
 }
 
-// loop control of iisph_pressure_iterations after a sweep (simulation.rs:1453-1477)
-__device__ __forceinline__ void solver_decide(SolverCtl& s, unsigned int error_flags, float dt, float rho0, float tol, int max_iters,
-                                              int density_mode) {
-  s.sweeps += 1;
-  const float avg = s.normal > 0 ? s.err_sum / float(s.normal) : __int_as_float(0x7fc00000);
-  s.avg = avg;
-  bool stop;
-  if (density_mode) stop = (s.normal == 0) || (fabsf(avg / rho0) < tol && s.k > 1);
-  else stop = (s.normal == 0) || (fabsf(avg) < tol / dt && s.k > 1);
-  if (stop || s.k == max_iters || (error_flags & ERRF_SOLVER_NONFINITE)) s.done = 1;
-  else s.k += 1;
-}
-
 // ---------------------------------------------------------------------------------------------- K15
-// (Ap)_i = div(a^p)_i; p' = p + ω (s - Ap) / a_ii, clamped at 0; PressureSolverStatistics reduced per block,
-// then by the last block to finish (fixed order => deterministic), which also evaluates the stop rule.
+// Sweep number `sweep`: (Ap)_i = div(a^p)_i; p' = p + ω (s - Ap) / a_ii, clamped at 0; PressureSolverStatistics of the
+// block added to slot sweep % 3 with integer atomics.  gid != nullptr: multi-GPU, ghost particles are skipped (their
+// p' arrives from the owner rank).
 __global__ void __launch_bounds__(kThreads)
 k_jacobi(uint32_t n, NbLists L, const float4* __restrict__ packA, float4* __restrict__ P0, float4* __restrict__ P1,
          const float2* __restrict__ hm, const float4* __restrict__ pconst, const float* __restrict__ rho, StepCtl* ctl,
-         float* __restrict__ blockstats, float omega, float rho0, float tol, int max_iters, int density_mode,
-         const uint32_t* __restrict__ gid) {
+         float omega, int density_mode, const uint32_t* __restrict__ gid, int sweep) {
   if (ctl->solver.done) return;
   __shared__ float4 s_pack[kWin];
   __shared__ float2 s_hm[kWin];
   const bool uni = ctl->hmin == ctl->hmax;
-  stage_window<false>(n, uni, packA, hm, nullptr, s_pack, s_hm, nullptr);
+  PairWindow W;
+  W.issue<false>(n, uni, packA, hm, nullptr, s_pack, s_hm, nullptr);
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const float dt = ctl->dt;
-  const bool odd = (ctl->solver.sweeps & 1) != 0;
+  const bool odd = (sweep & 1) != 0;
   const float4* __restrict__ packP = odd ? P1 : P0;
   float4* __restrict__ packP_next = odd ? P0 : P1;
+  const bool active = i < n && !(gid && (gid[i] & ASPH_GHOST_BIT));
+  float4 me = make_float4(0.f, 0.f, 0.f, 0.f), pc = make_float4(0.f, 0.f, 1.f, 0.f);
+  float2 own = make_float2(1.f, 0.f);
+  float p_old = 0.f, rho_i = 1.f;
+  if (active) { me = packA[i]; pc = pconst[i]; p_old = packP[i].w; rho_i = rho[i]; own = hm[i]; }
+  const bool singular = fabsf(pc.z) < 10e-4f;
+  const PairCol C(L, i, active && !singular);
+  W.wait();
   uint32_t c_normal = 0, c_sing = 0, c_neg = 0;
   float e_sum = 0.f, e_max = 0.f;
   bool bad = false;
-  // gid != nullptr: multi-GPU.  Ghost particles are skipped (their p' arrives from the owner rank) and the stop rule is
-  // applied by k_solver_decide once the statistics of all ranks are summed.
-  if (i < n && !(gid && (gid[i] & ASPH_GHOST_BIT))) {
-    const float4 me = packA[i];
-    const float4 pc = pconst[i];
-    const float p_old = packP[i].w;
+  if (active) {
     float pn = 0.f;
-    const float rho_i = rho[i];
-    if (fabsf(pc.z) < 10e-4f) {
+    if (singular) {
       c_sing = 1;
     } else {
-      const float2 own = hm[i];
       float sum = 0.f;
       auto body = [&](const float4& o, float dx, float dy, float c, float, float) { sum += c * ((o.z - me.z) * dx + (o.w - me.w) * dy); };
-      const float scale = uni ? for_each_pair<true, false>(L, i, s_pack, s_hm, nullptr, packA, hm, nullptr, me.x, me.y, own.x, own.y, body)
-                              : for_each_pair<false, false>(L, i, s_pack, s_hm, nullptr, packA, hm, nullptr, me.x, me.y, own.x, own.y, body);
+      const float scale = uni ? for_each_pair<true, false>(C, W, packA, hm, nullptr, me.x, me.y, own.x, own.y, body)
+                              : for_each_pair<false, false>(C, W, packA, hm, nullptr, me.x, me.y, own.x, own.y, body);
       sum *= scale;
       const float Ap = sum / rho_i - (me.z * pc.x + me.w * pc.y);
       const float resid = pc.w - Ap;
@@ -322,73 +423,36 @@ k_jacobi(uint32_t n, NbLists L, const float4* __restrict__ packA, float4* __rest
     packP_next[i] = make_float4(me.x, me.y, pn / (rho_i * rho_i), pn);
   }
   if (bad) atomicOr(&ctl->error_flags, ERRF_SOLVER_NONFINITE);
-  // block reduction
-  for (int o = 16; o > 0; o >>= 1) {
-    c_normal += __shfl_xor_sync(0xffffffffu, c_normal, o);
-    c_sing += __shfl_xor_sync(0xffffffffu, c_sing, o);
-    c_neg += __shfl_xor_sync(0xffffffffu, c_neg, o);
-    e_sum += __shfl_xor_sync(0xffffffffu, e_sum, o);
-    e_max = fmaxf(e_max, __shfl_xor_sync(0xffffffffu, e_max, o));
-  }
-  __shared__ float sh[5][kThreads];
-  __shared__ bool is_last;
+  // warp totals: counts by redux, the error sum by a fixed-order shuffle tree; then integers only
+  c_normal = __reduce_add_sync(0xffffffffu, c_normal);
+  c_neg = __reduce_add_sync(0xffffffffu, c_neg);
+  c_sing = __reduce_add_sync(0xffffffffu, c_sing);
+  const unsigned int m_enc = __reduce_max_sync(0xffffffffu, __float_as_uint(e_max));  // non-negative floats order like their bits
+  for (int o = 16; o > 0; o >>= 1) e_sum += __shfl_xor_sync(0xffffffffu, e_sum, o);
+  __shared__ unsigned long long sh_cnt[kThreads / 32];
+  __shared__ long long sh_err[kThreads / 32];
+  __shared__ unsigned int sh_sing[kThreads / 32], sh_max[kThreads / 32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) { sh[0][w] = float(c_normal); sh[1][w] = float(c_sing); sh[2][w] = float(c_neg); sh[3][w] = e_sum; sh[4][w] = e_max; }
+  if (lane == 0) {
+    sh_cnt[w] = (unsigned long long)c_normal | ((unsigned long long)c_neg << 32);
+    sh_err[w] = __float2ll_rn(fminf(fmaxf(e_sum, -4096.f), 4096.f) * 4294967296.f);  // 2^-32 fixed point
+    sh_sing[w] = c_sing; sh_max[w] = m_enc;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float a = 0.f, b = 0.f, c = 0.f, d = 0.f, e = 0.f;
-    for (int k = 0; k < kThreads / 32; k++) { a += sh[0][k]; b += sh[1][k]; c += sh[2][k]; d += sh[3][k]; e = fmaxf(e, sh[4][k]); }
-    float* out = blockstats + 5 * size_t(blockIdx.x);
-    out[0] = a; out[1] = b; out[2] = c; out[3] = d; out[4] = e;  // counts <= 256 are exact in fp32
-    __threadfence();
-    const unsigned int t = atomicAdd(&ctl->solver.ticket, 1u);
-    is_last = (t == gridDim.x - 1);
+    unsigned long long cnt = 0;
+    long long err = 0;
+    unsigned int sing = 0, mx = 0;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; k++) { cnt += sh_cnt[k]; err += sh_err[k]; sing += sh_sing[k]; mx = max(mx, sh_max[k]); }
+    SolverCtl& s = ctl->solver;
+    unsigned long long* acc = s.acc[sweep % 3] + 2 * (blockIdx.x % ASPH_ACC_COPIES);
+    if (cnt) atomicAdd(acc, cnt);
+    if (err) atomicAdd(acc + 1, (unsigned long long)err);
+    if (sing) atomicAdd(s.acc[sweep % 3] + 2 * ASPH_ACC_COPIES, (unsigned long long)sing);
+    // e_max >= 0: its bit pattern with the sign bit set is the order-preserving encoding dec_f expects
+    if (mx) atomicMax(&s.maxerr_enc[sweep % 3], mx | 0x80000000u);
   }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  // final reduction in a fixed order: thread t takes blocks t, t+256, ...; then a fixed tree
-  unsigned long long tn = 0, ts = 0, tg = 0;
-  float td = 0.f, te = 0.f;
-  for (uint32_t b = threadIdx.x; b < gridDim.x; b += kThreads) {
-    const float* in = blockstats + 5 * size_t(b);
-    tn += (unsigned long long)__ldcg(in + 0); ts += (unsigned long long)__ldcg(in + 1); tg += (unsigned long long)__ldcg(in + 2);
-    td += __ldcg(in + 3); te = fmaxf(te, __ldcg(in + 4));
-  }
-  __shared__ unsigned long long shn[kThreads], shs[kThreads], shg[kThreads];
-  shn[threadIdx.x] = tn; shs[threadIdx.x] = ts; shg[threadIdx.x] = tg; sh[3][threadIdx.x] = td; sh[4][threadIdx.x] = te;
-  __syncthreads();
-  for (int s = kThreads / 2; s > 0; s >>= 1) {
-    if (threadIdx.x < s) {
-      shn[threadIdx.x] += shn[threadIdx.x + s]; shs[threadIdx.x] += shs[threadIdx.x + s]; shg[threadIdx.x] += shg[threadIdx.x + s];
-      sh[3][threadIdx.x] += sh[3][threadIdx.x + s]; sh[4][threadIdx.x] = fmaxf(sh[4][threadIdx.x], sh[4][threadIdx.x + s]);
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    if (gid) {
-      ctl->solver.partial[0] = double(shn[0]); ctl->solver.partial[1] = double(shs[0]); ctl->solver.partial[2] = double(shg[0]);
-      ctl->solver.partial[3] = double(sh[3][0]);
-      ctl->solver.max_err = sh[4][0];
-      ctl->solver.ticket = 0;
-      return;
-    }
-    SolverCtl s = ctl->solver;
-    s.normal = shn[0]; s.singular = shs[0]; s.negative = shg[0]; s.err_sum = sh[3][0]; s.max_err = sh[4][0];
-    s.ticket = 0;
-    solver_decide(s, ctl->error_flags, dt, rho0, tol, max_iters, density_mode);
-    ctl->solver = s;
-  }
-}
-
-// multi-GPU: the stop rule on the statistics summed over all ranks (every rank computes the same decision)
-__global__ void k_solver_decide(StepCtl* ctl, float rho0, float tol, int max_iters, int density_mode) {
-  SolverCtl s = ctl->solver;
-  if (s.done) return;
-  s.normal = (unsigned long long)s.partial[0]; s.singular = (unsigned long long)s.partial[1]; s.negative = (unsigned long long)s.partial[2];
-  s.err_sum = float(s.partial[3]);
-  solver_decide(s, ctl->error_flags, ctl->dt, rho0, tol, max_iters, density_mode);
-  ctl->solver = s;
 }
 
 NbLists lists_of(asph_sim* sim) {
@@ -415,7 +479,7 @@ int launch_source(asph_sim* sim, int kind) {
   const uint32_t n = sim->n;
   if (n == 0) return ASPH_OK;
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
-  k_solver_reset<<<1, 1, 0, sim->stream>>>(sim->ctl);
+  k_solver_reset<<<1, 64, 0, sim->stream>>>(sim->ctl);
   LAUNCH_CHECK();
   k_source<<<blocks, kThreads, 0, sim->stream>>>(n, lists_of(sim), sim->xv[sim->xv_cur].p, sim->hm.p, sim->rho.p, sim->pconst.p,
                                                  sim->packP[0].p, sim->packA.p, sim->ctl, sim->pp.rest_density, kind);
@@ -432,7 +496,6 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
   *iters_out = 0; *sweeps_out = 0; *avg_out = 0;
   if (n == 0) return ASPH_OK;
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
-  CUDA_TRY(sim->blockstats.ensure(size_t(blocks) * 5 + 8));
   cudaStream_t st = sim->stream;
   const NbLists L = lists_of(sim);
   const uint32_t* gid = sim->dist ? sim->refid[sim->cur].p : nullptr;
@@ -449,7 +512,8 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
       if (time_it) { tm.e0 = kt_event(sim); tm.e1 = kt_event(sim); tm.e1b = kt_event(sim); tm.e2 = kt_event(sim); cudaEventRecord(tm.e0, st); }
       if (launched > 0) {  // sweep 0: a^p = 0 was written by k_source
         k_accel<0><<<blocks, kThreads, 0, st>>>(n, L, sim->packP[0].p, sim->packP[1].p, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, nullptr,
-                                                nullptr, nullptr, 0.f, gid);
+                                                nullptr, nullptr, 0.f, gid, launched, sim->pp.rest_density, max_avg_error, sim->pp.max_iters,
+                                                density_mode ? 1 : 0);
         LAUNCH_CHECK();
         if (time_it) cudaEventRecord(tm.e1, st);
         if (sim->dist) TRY(dist_halo(sim, sim->packA.p, 16));
@@ -458,16 +522,17 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
       }
       if (time_it) cudaEventRecord(tm.e1b, st);
       k_jacobi<<<blocks, kThreads, 0, st>>>(n, L, sim->packA.p, sim->packP[0].p, sim->packP[1].p, sim->hm.p, sim->pconst.p, sim->rho.p,
-                                            sim->ctl, sim->blockstats.p, sim->pp.jacobi_omega, sim->pp.rest_density, max_avg_error,
-                                            sim->pp.max_iters, density_mode ? 1 : 0, gid);
+                                            sim->ctl, sim->pp.jacobi_omega, density_mode ? 1 : 0, gid, launched);
       LAUNCH_CHECK();
       if (time_it) { cudaEventRecord(tm.e2, st); timed.push_back(tm); }
       if (sim->dist) {
-        TRY(dist_solver_reduce(sim));
-        k_solver_decide<<<1, 1, 0, st>>>(sim->ctl, sim->pp.rest_density, max_avg_error, sim->pp.max_iters, density_mode ? 1 : 0);
-        LAUNCH_CHECK();
-        TRY(dist_halo_pressure(sim));
+        TRY(dist_solver_reduce(sim, launched % 3));                       // every rank sees the totals of all ranks
+        TRY(dist_halo(sim, sim->packP[(launched + 1) & 1].p, 16));        // p' of the border particles to their ghosts
       }
+    }
+    if (launched > 0) {  // evaluate the last sweep of the batch (the sweeps before it were evaluated by their successors)
+      k_solver_decide<<<1, 1, 0, st>>>(sim->ctl, launched - 1, sim->pp.rest_density, max_avg_error, sim->pp.max_iters, density_mode ? 1 : 0);
+      LAUNCH_CHECK();
     }
     TRY(sync_ctl(sim));
     const SolverCtl& s = sim->ctl_host->solver;
@@ -511,10 +576,10 @@ int launch_final_accel(asph_sim* sim, int mode) {
   float2* vel = sim->vel[sim->cur].p;
   const uint32_t* gid = sim->dist ? sim->refid[sim->cur].p : nullptr;
   switch (mode) {
-    case 1: k_accel<1><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f, gid); break;
-    case 2: k_accel<2><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, sim->pp.hybrid_factor, gid); break;
-    case 3: k_accel<3><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f, gid); break;
-    default: k_accel<4><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f, gid); break;
+    case 1: k_accel<1><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f, gid, 0, 0.f, 0.f, 0, 0); break;
+    case 2: k_accel<2><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, sim->pp.hybrid_factor, gid, 0, 0.f, 0.f, 0, 0); break;
+    case 3: k_accel<3><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f, gid, 0, 0.f, 0.f, 0, 0); break;
+    default: k_accel<4><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f, gid, 0, 0.f, 0.f, 0, 0); break;
   }
   LAUNCH_CHECK();
   if (sim->dist && mode == 1) TRY(dist_halo(sim, xv, 16));  // the density solve's source term reads the neighbours' new velocities
