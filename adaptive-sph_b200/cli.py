@@ -6,7 +6,8 @@ Mirrors the clap definition of platform/desktop/main_loop.rs:25-103 for the `run
 and its flow (main_loop.rs:105-189, 209-358): read YAML -> optional key-wise overwrite -> init_simulation_params ->
 load split patterns -> init_fluid_sim -> loop { single_step } until the simulated time reaches --max-seconds.
 `image` (Cairo/ffmpeg export) and `generate-split-patterns` (offline optimiser) are out of scope.
-Added: --max-steps, --backend {cuda,oracle} (oracle = the CPU restatement, for comparison only), --dump state.npz.
+Added: --max-steps, --dump state.npz.  The CUDA library is the only backend; `main(argv, lib=...)` lets a test harness
+bind another library exporting the same C ABI.
 """
 import argparse
 import os
@@ -34,7 +35,6 @@ def build_parser():
     run.add_argument("-p", "--statistics-enabled", action="store_true")
     run.add_argument("-w", "--statistics-path", default=None)
     run.add_argument("--max-steps", type=int, default=None)
-    run.add_argument("--backend", choices=["cuda", "oracle"], default="cuda")
     run.add_argument("--split-patterns", default=None, help="default: ./split-patterns.yaml if present, else the shipped file")
     run.add_argument("--dump", default=None, help="write the final state (position, velocity, mass) to this .npz")
     run.add_argument("-q", "--quiet", action="store_true")
@@ -43,7 +43,7 @@ def build_parser():
     return ap
 
 
-def main(argv=None):
+def main(argv=None, lib=None):
     args = build_parser().parse_args(argv)
     if args.command != "run":
         print(f"`{args.command}` is out of scope of this build (rendering / offline pattern optimiser)", file=sys.stderr)
@@ -56,7 +56,8 @@ def main(argv=None):
     params = init_simulation_params(params, scene)
     sp_path = args.split_patterns or ("./split-patterns.yaml" if os.path.exists("./split-patterns.yaml") else None)  # main_loop.rs:225
     split = load_split_patterns_from_file(sp_path)
-    lib = load_library() if args.backend == "cuda" else load_library(os.path.join(ROOT, "oracle", "liboracle_f32.so"))
+    if lib is None:
+        lib = load_library()  # raises when libasph_b200.so is missing: there is no CPU fallback
     stats_on = args.statistics_enabled or args.statistics_path is not None
     sim = init_fluid_sim(params, scene, split, counters_enabled=stats_on, lib=lib)
     rec = StatisticsRecorder()

@@ -1,35 +1,52 @@
-"""`run <config> <scene>` command line (platform/desktop/main_loop.rs:25-103), driven with the CPU oracle backend."""
+"""`run <config> <scene>` command line (platform/desktop/main_loop.rs:25-103).  The host logic (argument parsing, YAML
+overwrite, step loop, statistics) is exercised on CPU by handing `main` the oracle library (same C ABI); the product
+CLI itself only ever binds libasph_b200.so."""
 import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = os.path.join(ROOT, "configs", "default-config.yaml")
+SCENE = os.path.join(ROOT, "configs", "default-scene.yaml")
 
 
-def _run(*args):
-    return subprocess.run([sys.executable, os.path.join(ROOT, "asph_b200.py"), *args], capture_output=True, text=True, timeout=600)
+def _main(asph, lib, *args):
+    import importlib
+    cli = importlib.import_module("adaptive-sph_b200.cli")
+    return cli.main(list(args), lib=lib)
 
 
-def test_run_oracle_backend_with_statistics(tmp_path):
+def test_run_with_statistics(asph, oracle32, tmp_path, capsys):
     stats = tmp_path / "stats.txt"
     over = tmp_path / "over.yaml"
     over.write_text("max_dt: 0.003\n")
-    out = _run("run", os.path.join(ROOT, "configs", "default-config.yaml"), os.path.join(ROOT, "configs", "default-scene.yaml"),
-               "-s", "0.0089", "-c", str(over), "-w", str(stats), "--backend", "oracle")
-    assert out.returncode == 0, out.stderr
-    assert "3 steps" in out.stdout  # 3 * 0.003 >= 0.0089
+    rc = _main(asph, oracle32, "run", CFG, SCENE, "-s", "0.0089", "-c", str(over), "-w", str(stats))
+    assert rc == 0
+    assert "3 steps" in capsys.readouterr().out  # 3 * 0.003 >= 0.0089
     text = stats.read_text()
     for label in ("simulation-step", "neighborhood", "level-estimation", "div-solver", "density-solver", "adaptivity", "particle-count", "dt:"):
         assert label in text
 
 
-def test_unknown_overwrite_key_is_an_error(tmp_path):
+def test_unknown_overwrite_key_is_an_error(asph, oracle32, tmp_path):
     over = tmp_path / "over.yaml"
     over.write_text("not_a_field: 1\n")
-    out = _run("run", os.path.join(ROOT, "configs", "default-config.yaml"), os.path.join(ROOT, "configs", "default-scene.yaml"),
-               "--max-steps", "1", "-c", str(over), "--backend", "oracle")
-    assert out.returncode != 0 and "not able to find attribute" in out.stderr
+    with pytest.raises(Exception, match="not able to find attribute"):
+        _main(asph, oracle32, "run", CFG, SCENE, "--max-steps", "1", "-c", str(over))
 
 
 def test_out_of_scope_subcommands():
-    assert _run("image").returncode == 2
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "asph_b200.py"), "image"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 2
+
+
+@pytest.mark.gpu
+def test_run_product_cli(tmp_path):
+    dump = tmp_path / "state.npz"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "asph_b200.py"), "run", CFG, SCENE, "--max-steps", "5",
+                          "--dump", str(dump), "-p"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    assert "backend cuda-sm100a" in out.stdout and "5 steps" in out.stdout
+    assert dump.exists()
