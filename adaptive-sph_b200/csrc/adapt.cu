@@ -108,7 +108,7 @@ k_mark(AdaptArgs A, const PackedParams P, int merging, uint32_t round, const uin
     atomicMax(&A.stampkey[d], key);
     const float2 xd = A.pos[d];
     const float hd = A.xyhm[d].z, md = A.mass[d];
-    const uint32_t cn = A.L.cnt[d] & 0xffffu;
+    const uint32_t cn = nb_cn(A.L.cnt[d]);
     const NbCol col(A.L, d);
     for (uint32_t k = 0; k < cn; k++) {
       const uint32_t j = col.get(k);
@@ -131,7 +131,7 @@ k_decide(AdaptArgs A, const PackedParams P, int merging, uint32_t round, float d
     const unsigned long long key = stamp_of(round, A.refid[d]);
     const float2 xd = A.pos[d];
     const float hd = A.xyhm[d].z, md = A.mass[d];
-    const uint32_t cn = A.L.cnt[d] & 0xffffu;
+    const uint32_t cn = nb_cn(A.L.cnt[d]);
     const NbCol col(A.L, d);
     bool ready = A.stampkey[d] == key;
     for (uint32_t k = 0; k < cn && ready; k++) {
@@ -181,7 +181,7 @@ k_validate(uint32_t n, AdaptArgs A, uint8_t donor_class, StepCtl* ctl) {
   if (c > 0) {
     if (A.size_class[i] != donor_class || p != DELETE_) ok = false;
     uint32_t c2 = 0;
-    const uint32_t cn = A.L.cnt[i] & 0xffffu;
+    const uint32_t cn = nb_cn(A.L.cnt[i]);
     const NbCol col(A.L, i);
     for (uint32_t k = 0; k < cn; k++) if (A.partner[col.get(k)] == i) c2++;
     if (c2 != c) ok = false;
@@ -320,7 +320,7 @@ __global__ void k_split_apply(uint32_t n, uint32_t cap, const uint8_t* __restric
 AdaptArgs args_of(asph_sim* sim) {
   AdaptArgs A;
   const int c = sim->cur;
-  A.L.pool = sim->nbpool.p; A.L.slice_base = sim->slice_base.p; A.L.cnt = sim->cnt.p; A.xyhm = sim->xyhm.p;
+  A.L.pool = sim->nbpool.p; A.L.slice_base = sim->slice_base.p; A.L.cnt = sim->cnt.p; A.L.cnt_ext = sim->cnt_ext.p; A.xyhm = sim->xyhm.p;
   A.pos = sim->pos[c].p; A.vel = sim->vel[c].p; A.mass = sim->mass[c].p; A.level = sim->level[c].p; A.refid = sim->refid[c].p;
   A.size_class = sim->size_class.p; A.partner = sim->merge_partner.p; A.counter = sim->merge_counter.p;
   A.stampkey = sim->stampkey.p;

@@ -128,7 +128,7 @@ __global__ void k_extract(uint32_t n, int field, const uint32_t* __restrict__ re
     case ASPH_F_PRESSURE_ACCEL: f[2 * r] = packA[i].z; f[2 * r + 1] = packA[i].w; break;
     case ASPH_F_LEVEL: f[r] = level[i]; break;
     case ASPH_F_SIZE_CLASS: ((uint8_t*)out)[r] = size_class[i]; break;
-    case ASPH_F_NEIGHBOR_COUNT: ((uint32_t*)out)[r] = cnt[i] & 0xffffu; break;
+    case ASPH_F_NEIGHBOR_COUNT: ((uint32_t*)out)[r] = nb_cn(cnt[i]); break;
     case ASPH_F_FLAG_SURFACE: ((uint8_t*)out)[r] = flags[i] & 1u; break;
     case ASPH_F_FLAG_INSUFFICIENT: ((uint8_t*)out)[r] = (flags[i] >> 1) & 1u; break;
     case ASPH_F_LAMBDA_SUM: f[r] = lam_sum[i]; break;
@@ -178,7 +178,7 @@ void kt_release(asph_sim* sim, cudaEvent_t e) { sim->kt_pool.push_back(e); }
 int check_error_flags(asph_sim* sim) {
   const unsigned int f = sim->ctl_host->error_flags;
   if (!f) return ASPH_OK;
-  if (f & ERRF_CELL_BUDGET) { sim->last_error = "cell grid does not fit the cell budget"; return ASPH_ERR_CAPACITY; }
+  if (f & ERRF_CELL_BUDGET) { sim->last_error = "cell grid does not fit the cell budget: particle positions are spread over an absurd extent (the simulation has exploded?)"; return ASPH_ERR_CAPACITY; }
   if (f & ERRF_NEIGHBOR_OVERFLOW) { sim->last_error = "exceeded maximum allowed number of 20000 neighbors"; return ASPH_ERR_NEIGHBOR_OVERFLOW; }
   if (f & ERRF_NONFINITE) { sim->last_error = "assert!(is_finite) failed (density / a_ii / position / velocity)"; return ASPH_ERR_NONFINITE; }
   if (f & ERRF_DENSITY) { sim->last_error = "assert!(*p_density > 0.0001) failed"; return ASPH_ERR_DENSITY; }
@@ -472,7 +472,7 @@ void asph_destroy(asph_sim* sim) {
   }
   sim->xyhm.release(); sim->packA.release(); sim->pconst.release(); sim->h_tmp.release(); sim->rho.release(); sim->lam_sum.release();
   sim->nrm.release(); sim->gB.release(); sim->lam_grad.release(); sim->key.release(); sim->cellcount.release(); sim->cellstart.release();
-  sim->order.release(); sim->scan_sums.release(); sim->cnt.release(); sim->slice_base.release();
+  sim->order.release(); sim->scan_sums.release(); sim->cnt.release(); sim->cnt_ext.release(); sim->slice_base.release();
   sim->nbpool.release(); sim->hm.release(); sim->size_class.release(); sim->flags.release(); sim->merge_partner.release();
   sim->cand.release(); for (int k = 0; k < 4; k++) sim->scratch_u[k].release();
   sim->merge_counter.release(); sim->stamp.release(); sim->stampkey.release(); sim->scratch_f.release(); sim->lut.release(); sim->split_pos.release();
@@ -555,7 +555,7 @@ int asph_get_neighbors_csr(asph_sim* sim, uint64_t* offsets, uint32_t* idx, uint
     if (used) CUDA_TRY(cudaMemcpy(pool.data(), sim->nbpool.p, used * sizeof(uint16_t), cudaMemcpyDeviceToHost));
   }
   uint64_t nnz = 0;
-  for (uint32_t i = 0; i < n; i++) nnz += cnt[i] & 0xffffu;
+  for (uint32_t i = 0; i < n; i++) nnz += nb_cn(cnt[i]);
   if (nnz_out) *nnz_out = nnz;
   if (!idx) return ASPH_OK;
   if (cap < nnz || !offsets) return ASPH_ERR_INVALID;
@@ -565,17 +565,11 @@ int asph_get_neighbors_csr(asph_sim* sim, uint64_t* offsets, uint32_t* idx, uint
   for (uint32_t r = 0; r < n; r++) {
     const uint32_t i = where[r];
     offsets[r] = o;
-    const uint32_t c = cnt[i] & 0xffffu;
+    const uint32_t cw = nb_cw(cnt[i]), cf = nb_cf(cnt[i]), c = cw + cf;
     const uint32_t sb = sbase[i >> 5];
     const bool wide = (sb >> 31) != 0;
     const size_t base = size_t(sb & 0x7fffffffu) * 64;
-    const uint32_t lane = i & 31u, bias = nb_bias(i);
-    for (uint32_t k = 0; k < c; k++) {
-      uint32_t j;
-      if (wide) j = reinterpret_cast<const uint32_t*>(pool.data() + base)[(k >> 2) * 128u + lane * 4u + (k & 3u)];
-      else j = bias + uint32_t(pool[base + (k >> 3) * 256u + lane * 8u + (k & 7u)]);
-      idx[o + k] = refid[j];
-    }
+    for (uint32_t k = 0; k < c; k++) idx[o + k] = refid[nb_get(pool.data() + base, wide, i, k, cw, cf)];
     std::sort(idx + o, idx + o + c);
     o += c;
   }

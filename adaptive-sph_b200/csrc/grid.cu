@@ -81,26 +81,37 @@ __global__ void k_make_levels(StepCtl* ctl, float f_search, uint32_t cells_budge
     while (hmax >= bound && nl < ASPH_MAX_LEVELS) { nl++; bound *= 2.f; }
   }
   ctl->nlevels = nl;
+  // A grid that does not fit the cell budget is retried with larger cells (a few stray particles far from the bulk);
+  // beyond ~11x the natural cell size the candidate scans would degenerate to O(N^2), and positions that far apart mean
+  // the simulation has exploded anyway: flag it and leave a 1 x 1 grid that keeps every later kernel in bounds
+  // (k_sort_cells and k_neighbors return at once when the flag is set).
   float scale = 1.f;
-  for (int attempt = 0; attempt < 64; attempt++) {
+  for (int attempt = 0; attempt < 7; attempt++) {
     unsigned long long total = 0;
     float upper = hmin * 2.f;
+    bool ok = true;
     for (int L = 0; L < nl; L++) {
       float hm = (L == nl - 1) ? hmax : fminf(upper, hmax);
       float cell = f_search * hm * ASPH_SLACK * scale;
       GridLevel g;
       g.hmax = hm; g.cell = cell; g.inv_cell = 1.f / cell;
-      g.nx = int(floorf((maxx - minx) * g.inv_cell)) + 1;
-      g.ny = int(floorf((maxy - miny) * g.inv_cell)) + 1;
+      const float fx = floorf((maxx - minx) * g.inv_cell), fy = floorf((maxy - miny) * g.inv_cell);
+      if (!(fx < 4.0e6f) || !(fy < 4.0e6f)) { ok = false; break; }  // also catches inf / NaN extents
+      g.nx = int(fx) + 1;
+      g.ny = int(fy) + 1;
       g.base = uint32_t(total);
       ctl->lv[L] = g;
       total += level_cells(g.nx, g.ny);
       upper *= 2.f;
     }
-    if (total <= cells_budget) { ctl->total_cells = uint32_t(total); return; }
+    if (ok && total <= cells_budget) { ctl->total_cells = uint32_t(total); return; }
     scale *= 1.5f;
   }
-  ctl->total_cells = 0;
+  GridLevel g;
+  g.hmax = hmax; g.cell = 1.f; g.inv_cell = 0.f; g.nx = 1; g.ny = 1; g.base = 0;
+  ctl->lv[0] = g;
+  ctl->nlevels = 1;
+  ctl->total_cells = uint32_t(level_cells(1, 1));
   atomicOr(&ctl->error_flags, ERRF_CELL_BUDGET);
 }
 
@@ -213,6 +224,7 @@ __global__ void k_scatter(uint32_t n, const uint32_t* __restrict__ key, const ui
 // order, the global index makes the sorted order (and with it every fp32 sum) reproducible
 __global__ void k_sort_cells(const StepCtl* __restrict__ ctl, const uint32_t* __restrict__ cellstart, uint32_t* __restrict__ order,
                              const uint32_t* __restrict__ gid) {
+  if (ctl->error_flags & ERRF_CELL_BUDGET) return;  // degenerate 1 x 1 grid (k_make_levels): the step is failing anyway
   const uint32_t total = ctl->total_cells;
   for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < total; c += gridDim.x * blockDim.x) {
     uint32_t s = cellstart[c], e = cellstart[c + 1];
@@ -252,6 +264,7 @@ int sync_ctl(asph_sim* sim) {
   if (sim->dist) TRY(dist_reduce_flags(sim, false));  // every rank sees the same error flags => the same control flow
   CUDA_TRY(cudaMemcpyAsync(sim->ctl_host, sim->ctl, sizeof(StepCtl), cudaMemcpyDeviceToHost, sim->stream));
   CUDA_TRY(cudaStreamSynchronize(sim->stream));
+  sim->ctl_seen = true;
   return ASPH_OK;
 }
 
@@ -297,7 +310,7 @@ int ensure_capacity(asph_sim* sim, uint32_t want) {
   CUDA_TRY(sim->h_tmp.ensure(newcap)); CUDA_TRY(sim->rho.ensure(newcap)); CUDA_TRY(sim->lam_sum.ensure(newcap));
   CUDA_TRY(sim->nrm.ensure(newcap)); CUDA_TRY(sim->gB.ensure(newcap)); CUDA_TRY(sim->lam_grad.ensure(newcap));
   CUDA_TRY(sim->key.ensure(newcap)); CUDA_TRY(sim->order.ensure(newcap));
-  CUDA_TRY(sim->cnt.ensure(newcap));
+  CUDA_TRY(sim->cnt.ensure(newcap)); CUDA_TRY(sim->cnt_ext.ensure(newcap));
   const uint32_t nslices = (newcap + 31) / 32 + 1;
   CUDA_TRY(sim->slice_base.ensure(nslices)); CUDA_TRY(sim->hm.ensure(newcap));
   CUDA_TRY(sim->size_class.ensure(newcap)); CUDA_TRY(sim->flags.ensure(newcap));

@@ -31,8 +31,7 @@ k_surface(uint32_t n, Lists L, const float4* __restrict__ xyhm, const float2* __
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 me = xyhm[i];
-  const uint32_t c = L.cnt[i];
-  const uint32_t ce = c >> 16;
+  const uint32_t ce = L.cnt_ext[i];
   const float2 nr = nrm[i];
   const float s = -(me.w / P.rest_density);
   float nx = s * nr.x, ny = s * nr.y;
@@ -88,7 +87,7 @@ k_expand(Lists L, int t, const uint32_t* __restrict__ front_in, uint32_t* __rest
   }
   for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
     const uint32_t j = front_in[f];
-    const uint32_t ce = L.cnt[j] >> 16;
+    const uint32_t ce = L.cnt_ext[j];
     const NbCol col(L, j);
     for (uint32_t k = 0; k < ce; k++) {
       const uint32_t i = col.get(k);
@@ -111,7 +110,7 @@ k_assign(Lists L, int t, const uint32_t* __restrict__ cand, const float4* __rest
   for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nc; f += gridDim.x * blockDim.x) {
     const uint32_t i = cand[f];
     const float4 me = xyhm[i];
-    const uint32_t ce = L.cnt[i] >> 16;
+    const uint32_t ce = L.cnt_ext[i];
     const NbCol col(L, i);
     float best = -__int_as_float(0x7f800000);
     for (uint32_t k = 0; k < ce; k++) {
@@ -138,7 +137,7 @@ k_smooth(uint32_t n, Lists L, const float2* __restrict__ pos, const float4* __re
   if (i >= n) return;
   const float2 xi = pos[i];
   const float hi = xyhm[i].z;
-  const uint32_t cn = L.cnt[i] & 0xffffu;
+  const uint32_t cn = nb_cn(L.cnt[i]);
   const NbCol col(L, i);
   float num = 0.f, den = 0.f;
   for (uint32_t k = 0; k < cn; k++) {
@@ -166,7 +165,7 @@ int launch_level_estimation(asph_sim* sim) {
   if (n == 0) return ASPH_OK;
   cudaStream_t st = sim->stream;
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
-  Lists L{sim->nbpool.p, sim->slice_base.p, sim->cnt.p};
+  Lists L{sim->nbpool.p, sim->slice_base.p, sim->cnt.p, sim->cnt_ext.p};
   const float cos_threshold = std::cos(50.f * (3.14159265358979323846f / 180.f));
   float* level = sim->level[sim->cur].p;
   k_level_reset<<<1, 1, 0, st>>>(sim->ctl);
@@ -201,7 +200,7 @@ int launch_level_smoothing(asph_sim* sim) {
   if (n == 0) { sim->level_valid = true; return ASPH_OK; }
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
   const int c = sim->cur;
-  Lists L{sim->nbpool.p, sim->slice_base.p, sim->cnt.p};
+  Lists L{sim->nbpool.p, sim->slice_base.p, sim->cnt.p, sim->cnt_ext.p};
   k_smooth<<<blocks, kThreads, 0, sim->stream>>>(n, L, sim->pos[c].p, sim->xyhm.p, sim->rho.p,
                                                  sim->level[c].p, sim->scratch_f.p, sim->pp.maximum_surface_distance, sim->ctl);
   LAUNCH_CHECK();

@@ -1,111 +1,113 @@
-// lists.cuh — the per-step neighbour lists: sliced, chunked ELL of 16-bit relative indices.
+// lists.cuh — the per-step neighbour lists: sliced, chunked ELL of 16-bit entries in three segments per column.
 //
 // A slice is 32 consecutive particles (one warp).  A particle's column is cut into chunks of 8 entries; chunk c of
 // lane l is the 16 bytes at  pool[off + c*256 + l*8 .. +8)  (uint16 units), so ONE 16-byte vector load per lane brings
-// 8 neighbour indices and the warp's loads of a chunk are one contiguous 512 B run.  A whole 2h column (about 14
-// entries) is therefore two load instructions, after which all gathers of the column can be in flight at once.
-// Particles are sorted by grid cell, so a neighbour index j is close to i itself: it is stored as
-// uint16(j - b0 + 32768) with b0 = i rounded down to a multiple of ASPH_PAIR_BLOCK — the first particle of the thread
-// block that consumes the column in the pair passes, so that a stored index minus a compile-time constant IS the
-// position in that block's shared-memory window (solver.cu).  A slice in which some neighbour is further than +-32767 positions away (neighbours in
-// another size level's grid) is stored "wide": plain 32-bit indices, chunks of 4.
-// slice_base[s] = offset in units of 64 uint16 | wide << 31.
-// A column holds first N_2(i) (2h range, what NeighborhoodCache::filter_down keeps, neighborhood_search.rs:56-70):
-// rows 0 .. cnt_near-1, padded with the particle's own index up to the next multiple of 8 (a zero-distance pair
-// contributes nothing to any gradient sum, so the pair loops run whole chunks without per-entry bounds checks); the
-// rest of the extended range used by the level set follows from row pad8(cnt_near) on.  cnt[i] = cnt_near | cnt_ext << 16,
-// both counting real neighbours only (NbCol::get(k), k < cnt_ext, skips the padding).
-// No per-pair coefficient is stored: every pass recomputes dW/dr / r from the gathered positions (pair_g below).
+// 8 entries and the warp's loads of a chunk are one contiguous 512 B run.
+// Particles are sorted by grid cell, so a neighbour index j is close to i itself.  The pair passes (solver.cu) run one
+// block per ASPH_PAIR_BLOCK consecutive particles and stage the WINDOW of particles [b0 - ASPH_PAIR_HALO,
+// b0 + ASPH_PAIR_BLOCK + ASPH_PAIR_HALO), b0 = i rounded down to a multiple of ASPH_PAIR_BLOCK, in shared memory.
+// A column therefore holds
+//   W  rows [0, cw):  the 2h neighbours that lie inside the window, stored as the BYTE OFFSET of their 16-byte window
+//      slot, (j - (b0 - HALO)) * 16, always 16 bits wide — the gather address of the hot loops is one extract away;
+//      padded with the particle's own slot up to a multiple of 8 (a zero-distance pair contributes nothing to any
+//      gradient sum, so the loops run whole chunks without per-entry checks);
+//   F  the cf 2h neighbours outside the window (across a strip edge, or in another size level's grid), starting at the
+//      chunk after W, padded with the particle itself up to a multiple of 4; the pair passes read these from global
+//      memory;
+//   E  the ce - cn remaining neighbours of the extended range used by the level set, right after F.
+// F and E entries are uint16(j - b0 + 32768) in chunks of 8 — unless some F / E neighbour of the slice is further than
+// +-32767 positions away; such a slice is "wide": its F / E entries are plain 32-bit indices in chunks of 4 (the W
+// segment keeps its 16-bit form).  slice_base[s] = offset in units of 64 uint16 | wide << 31.
+// W + F = N_2(i) (what NeighborhoodCache::filter_down keeps, neighborhood_search.rs:56-70), cn = cw + cf.
+// cnt[i] = cw | cf << 12 (cw <= window size < 4096); cnt_ext[i] = ce.  Counts are of real neighbours only.
+// No per-pair coefficient is stored: every pass recomputes dW/dr / r from the gathered positions (PairShape below).
 #pragma once
 #include "sim.cuh"
 
 #define ASPH_PAIR_BLOCK 256u  // threads per block of the pair passes == alignment of the index bias
+#define ASPH_PAIR_HALO 192u   // window slots before / after the block's own particles
+#define ASPH_PAIR_WIN (ASPH_PAIR_BLOCK + 2u * ASPH_PAIR_HALO)
 
 struct NbLists {
   const uint16_t* __restrict__ pool;
   const uint32_t* __restrict__ slice_base;
   const uint32_t* __restrict__ cnt;
+  const uint32_t* __restrict__ cnt_ext;
 };
 
 #ifdef __CUDACC__
 #define ASPH_KNORM 1.81891363533f  // 40 / (7 pi)
-__host__ __device__ __forceinline__ uint32_t nb_bias(uint32_t i) { return (i & ~(ASPH_PAIR_BLOCK - 1u)) - 32768u; }
+__host__ __device__ __forceinline__ uint32_t nb_block0(uint32_t i) { return i & ~(ASPH_PAIR_BLOCK - 1u); }
+__host__ __device__ __forceinline__ uint32_t nb_bias(uint32_t i) { return nb_block0(i) - 32768u; }
+__host__ __device__ __forceinline__ uint32_t nb_win0(uint32_t i) { return nb_block0(i) - ASPH_PAIR_HALO; }  // mod 2^32
+__host__ __device__ __forceinline__ uint32_t nb_cw(uint32_t c) { return c & 0xfffu; }
+__host__ __device__ __forceinline__ uint32_t nb_cf(uint32_t c) { return c >> 12; }
+__host__ __device__ __forceinline__ uint32_t nb_cn(uint32_t c) { return nb_cw(c) + nb_cf(c); }
+__host__ __device__ __forceinline__ uint32_t nb_pad8(uint32_t x) { return (x + 7u) & ~7u; }
+__host__ __device__ __forceinline__ uint32_t nb_pad4(uint32_t x) { return (x + 3u) & ~3u; }
+// 512-byte chunks a column occupies: W in 16-bit form, then F (padded to 4) and E in 16- or 32-bit form
+__host__ __device__ __forceinline__ uint32_t nb_col_chunks(uint32_t cw, uint32_t cf, uint32_t ce, bool wide) {
+  const uint32_t fe = nb_pad4(cf) + (ce - cw - cf);
+  return nb_pad8(cw) / 8u + (wide ? (fe + 3u) / 4u : (fe + 7u) / 8u);
+}
+// position of W row r of lane `lane` (uint16 units from the slice start)
+__host__ __device__ __forceinline__ uint32_t nb_pos_w(uint32_t lane, uint32_t r) { return (r >> 3) * 256u + lane * 8u + (r & 7u); }
+// position of entry k of the F / E region of a column with cw window rows: uint16 units (narrow) / uint32 units (wide)
+__host__ __device__ __forceinline__ uint32_t nb_pos_fe(uint32_t lane, uint32_t cw, bool wide, uint32_t k) {
+  const uint32_t c0 = nb_pad8(cw) >> 3;
+  return wide ? (c0 + (k >> 2)) * 128u + lane * 4u + (k & 3u) : (c0 + (k >> 3)) * 256u + lane * 8u + (k & 7u);
+}
+// k-th real neighbour (k < ce) of particle i (host and device; `slice` = start of the slice in the pool)
+__host__ __device__ __forceinline__ uint32_t nb_get(const uint16_t* slice, bool wide, uint32_t i, uint32_t k, uint32_t cw, uint32_t cf) {
+  const uint32_t lane = i & 31u;
+  if (k < cw) return nb_win0(i) + (uint32_t(slice[nb_pos_w(lane, k)]) >> 4);
+  const uint32_t kk = k < cw + cf ? k - cw : nb_pad4(cf) + (k - cw - cf);
+  const uint32_t pos = nb_pos_fe(lane, cw, wide, kk);
+  return wide ? reinterpret_cast<const uint32_t*>(slice)[pos] : nb_bias(i) + uint32_t(slice[pos]);
+}
+// filling a slice: W rows take a window byte offset, F / E entries an index
+__device__ __forceinline__ void nb_store_w(uint16_t* slice, uint32_t lane, uint32_t r, uint32_t byte_off) {
+  slice[nb_pos_w(lane, r)] = uint16_t(byte_off);
+}
+__device__ __forceinline__ void nb_store_fe(uint16_t* slice, bool wide, uint32_t lane, uint32_t cw, uint32_t k, uint32_t j, uint32_t bias) {
+  const uint32_t pos = nb_pos_fe(lane, cw, wide, k);
+  if (wide) reinterpret_cast<uint32_t*>(slice)[pos] = j;
+  else slice[pos] = uint16_t(j - bias);
+}
+
 struct NbCol {
-  const uint16_t* p16;  // lane's first chunk, narrow view
-  const uint32_t* p32;  // lane's first chunk, wide view
-  uint32_t bias;        // i0 - 32768 (mod 2^32)
-  uint32_t cn, ce;      // real neighbours in the 2h range / in the extended range
+  const uint16_t* slice;  // start of the slice in the pool
+  uint32_t i;
+  uint32_t cw, cf, cn;    // window / far 2h neighbours, cn = cw + cf
   bool wide;
-  __device__ __forceinline__ NbCol() : p16(nullptr), p32(nullptr), bias(0), cn(0), ce(0), wide(false) {}  // empty column
-  __device__ __forceinline__ NbCol(const NbLists& L, uint32_t i) {
+  __device__ __forceinline__ NbCol() : slice(nullptr), i(0), cw(0), cf(0), cn(0), wide(false) {}  // empty column
+  __device__ __forceinline__ NbCol(const NbLists& L, uint32_t i_) : i(i_) {
     const uint32_t sb = __ldg(&L.slice_base[i >> 5]);
     const uint32_t c = __ldg(&L.cnt[i]);
-    cn = c & 0xffffu; ce = c >> 16;
+    cw = nb_cw(c); cf = nb_cf(c); cn = cw + cf;
     wide = (sb >> 31) != 0u;
-    const uint16_t* base = L.pool + size_t(sb & 0x7fffffffu) * 64u;
-    p16 = base + (i & 31u) * 8u;
-    p32 = reinterpret_cast<const uint32_t*>(base) + (i & 31u) * 4u;
-    bias = nb_bias(i);
-  }
-  __device__ __forceinline__ uint32_t row(uint32_t r) const {  // stored row r of the column
-    return wide ? p32[(r >> 2) * 128u + (r & 3u)] : bias + uint32_t(p16[(r >> 3) * 256u + (r & 7u)]);
+    slice = L.pool + size_t(sb & 0x7fffffffu) * 64u;
   }
   // k-th real neighbour, k < ce (cold paths: level set, resampling)
-  __device__ __forceinline__ uint32_t get(uint32_t k) const { return row(k < cn ? k : k - cn + ((cn + 7u) & ~7u)); }
-  // rows [k0, k0 + 8) of the 2h part (k0 a multiple of 8, k0 < cn): real neighbours, then the particle itself as padding.
-  // Streaming loads: list entries are read once per pass and should not displace the gathered packs in L2.
-  __device__ __forceinline__ void get8(uint32_t k0, uint32_t (&j)[8]) const {
+  __device__ __forceinline__ uint32_t get(uint32_t k) const { return nb_get(slice, wide, i, k, cw, cf); }
+  // raw W rows [k0, k0 + 8), k0 a multiple of 8 (8 x uint16 window byte offsets).  Streaming loads: list entries are
+  // read once per pass and should not displace the gathered packs in L2.
+  __device__ __forceinline__ uint4 raw8(uint32_t k0) const {
+    return __ldcs(reinterpret_cast<const uint4*>(slice + (k0 >> 3) * 256u + (i & 31u) * 8u));
+  }
+  // F entries [k0, k0 + 4), k0 a multiple of 4, as particle indices
+  __device__ __forceinline__ void far4(uint32_t k0, uint32_t (&j)[4]) const {
+    const uint32_t pos = nb_pos_fe(i & 31u, cw, wide, k0);
     if (!wide) {
-      const uint4 v = __ldcs(reinterpret_cast<const uint4*>(p16 + (k0 >> 3) * 256u));
-      j[0] = bias + (v.x & 0xffffu); j[1] = bias + (v.x >> 16);
-      j[2] = bias + (v.y & 0xffffu); j[3] = bias + (v.y >> 16);
-      j[4] = bias + (v.z & 0xffffu); j[5] = bias + (v.z >> 16);
-      j[6] = bias + (v.w & 0xffffu); j[7] = bias + (v.w >> 16);
+      const uint2 v = __ldcs(reinterpret_cast<const uint2*>(slice + pos));
+      const uint32_t bias = nb_bias(i);
+      j[0] = bias + (v.x & 0xffffu); j[1] = bias + (v.x >> 16); j[2] = bias + (v.y & 0xffffu); j[3] = bias + (v.y >> 16);
     } else {
-      const uint4 a = __ldcs(reinterpret_cast<const uint4*>(p32 + (k0 >> 2) * 128u));
-      const uint4 b = __ldcs(reinterpret_cast<const uint4*>(p32 + ((k0 >> 2) + 1u) * 128u));
-      j[0] = a.x; j[1] = a.y; j[2] = a.z; j[3] = a.w;
-      j[4] = b.x; j[5] = b.y; j[6] = b.z; j[7] = b.w;
-    }
-  }
-  // raw rows [k0, k0 + 8) of a narrow column (8 x uint16), and their decoding into window offsets
-  __device__ __forceinline__ uint4 raw8(uint32_t k0) const { return __ldcs(reinterpret_cast<const uint4*>(p16 + (k0 >> 3) * 256u)); }
-  static __device__ __forceinline__ void decode8(const uint4& v, uint32_t halo, uint32_t (&off)[8]) {
-    const uint32_t K = 32768u - halo;
-    off[0] = (v.x & 0xffffu) - K; off[1] = (v.x >> 16) - K;
-    off[2] = (v.y & 0xffffu) - K; off[3] = (v.y >> 16) - K;
-    off[4] = (v.z & 0xffffu) - K; off[5] = (v.z >> 16) - K;
-    off[6] = (v.w & 0xffffu) - K; off[7] = (v.w >> 16) - K;
-  }
-  // same rows as window offsets: off = j - wa with wa = b0 - halo (mod 2^32); narrow rows need one subtraction.
-  // WIDE is warp-uniform (a property of the slice), so callers branch on it once outside their loops.
-  template <bool WIDE>
-  __device__ __forceinline__ void get8_off(uint32_t k0, uint32_t halo, uint32_t (&off)[8]) const {
-    if (!WIDE) {
-      const uint32_t K = 32768u - halo;
-      const uint4 v = __ldcs(reinterpret_cast<const uint4*>(p16 + (k0 >> 3) * 256u));
-      off[0] = (v.x & 0xffffu) - K; off[1] = (v.x >> 16) - K;
-      off[2] = (v.y & 0xffffu) - K; off[3] = (v.y >> 16) - K;
-      off[4] = (v.z & 0xffffu) - K; off[5] = (v.z >> 16) - K;
-      off[6] = (v.w & 0xffffu) - K; off[7] = (v.w >> 16) - K;
-    } else {
-      const uint32_t wa = bias + 32768u - halo;
-      const uint4 a = __ldcs(reinterpret_cast<const uint4*>(p32 + (k0 >> 2) * 128u));
-      const uint4 b = __ldcs(reinterpret_cast<const uint4*>(p32 + ((k0 >> 2) + 1u) * 128u));
-      off[0] = a.x - wa; off[1] = a.y - wa; off[2] = a.z - wa; off[3] = a.w - wa;
-      off[4] = b.x - wa; off[5] = b.y - wa; off[6] = b.z - wa; off[7] = b.w - wa;
+      const uint4 v = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(slice) + pos));
+      j[0] = v.x; j[1] = v.y; j[2] = v.z; j[3] = v.w;
     }
   }
 };
-// rows a column with cn near and ce total neighbours occupies
-__device__ __forceinline__ uint32_t nb_col_rows(uint32_t cn, uint32_t ce) { return ((cn + 7u) & ~7u) + (ce - cn); }
-// pool units (64 uint16) a slice of `rows` rows needs
-__device__ __forceinline__ uint32_t nb_slice_units(uint32_t rows, bool wide) { return 4u * (wide ? (rows + 3u) / 4u : (rows + 7u) / 8u); }
-// where entry k of lane `lane` goes when the slice is being filled
-__device__ __forceinline__ void nb_store(uint16_t* slice, bool wide, uint32_t lane, uint32_t k, uint32_t j, uint32_t bias) {
-  if (wide) reinterpret_cast<uint32_t*>(slice)[(k >> 2) * 128u + lane * 4u + (k & 3u)] = j;
-  else slice[(k >> 3) * 256u + lane * 8u + (k & 7u)] = uint16_t(j - bias);
-}
 
 // Single-instruction SFU approximations (2 ulp); flush-to-zero is harmless here: squared distances and smoothing
 // lengths of a simulation are many orders of magnitude above the denormal range.

@@ -4,9 +4,9 @@
 //
 // Neighbour set (bit exact): N_f(i) = { j : |x_ij|^2 < ((h_i+h_j)*0.5*f)^2 }, fp32, no FMA contraction —
 // the final set of build_neighborhood_list_rstar after its symmetrize pass (neighborhood_search.rs:123-185, checked
-// by the reference's own brute-force test at :216-237 and simulation.rs:1810-1863).  Rows 0..cnt_near-1 of a
-// particle's ELL column are N_2 (what NeighborhoodCache::filter_down leaves, neighborhood_search.rs:56-70), rows
-// cnt_near..cnt_ext-1 the rest of N_{f_ext} used only by the level-set estimation.
+// by the reference's own brute-force test at :216-237 and simulation.rs:1810-1863).  The W and F segments of a
+// particle's ELL column (lists.cuh) are N_2 (what NeighborhoodCache::filter_down leaves, neighborhood_search.rs:56-70),
+// the E segment the rest of N_{f_ext} used only by the level-set estimation.
 #include "lists.cuh"
 
 namespace {
@@ -97,19 +97,25 @@ __device__ __forceinline__ void for_each_candidate(float xi, float yi, float hi,
 __global__ void __launch_bounds__(kThreads)
 k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restrict__ ctl_in, StepCtl* ctl,
             const uint32_t* __restrict__ cellstart, const PackedParams P, const float* __restrict__ lut, float f_ext, float f_near,
-            uint32_t pool_cap64, uint16_t* __restrict__ pool, uint32_t* __restrict__ slice_base, uint32_t* __restrict__ cnt,
+            uint32_t pool_cap64, uint16_t* __restrict__ pool, uint32_t* __restrict__ slice_base, uint32_t* __restrict__ cnt, uint32_t* __restrict__ cnt_ext,
             float* __restrict__ rho_out, float2* __restrict__ gB_out, float4* __restrict__ pconst, float* __restrict__ lam_sum_out,
             float2* __restrict__ lam_grad_out, float2* __restrict__ nrm_out, const uint32_t* __restrict__ gid) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t i0 = i & ~(ASPH_PAIR_BLOCK - 1u);  // the index bias is per 256-particle block (lists.cuh)
+  if (ctl_in->error_flags & ERRF_CELL_BUDGET) {  // no usable grid (k_make_levels): empty columns, the host reports the failure
+    if (i < n) { cnt[i] = 0u; cnt_ext[i] = 0u; if (lane == 0) slice_base[i >> 5] = 0u; }
+    return;
+  }
   const bool active = i < n;
   float4 me = make_float4(0.f, 0.f, 1.f, 0.f);
   if (active) me = xyhm[i];
   const float xi = me.x, yi = me.y, hi = me.z;
 
-  // pass 1: counts, and whether every neighbour index fits the 16-bit window around the slice
-  uint32_t cn = 0, ce = 0;
+  // pass 1: counts — 2h neighbours inside / outside the pair passes' shared-memory window (lists.cuh), the extended
+  // range, and whether every index stored outside the window segment fits 16 bits around the block
+  const uint32_t win0 = i0 - ASPH_PAIR_HALO;
+  uint32_t cw = 0, cf = 0, ce = 0;
   bool fits = true;
   if (active) {
     for_each_candidate(xi, yi, hi, ctl_in, cellstart, f_ext, [&](uint32_t j) {
@@ -117,18 +123,22 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
       const float d2 = dist_sq_exact(__fsub_rn(xi, o.x), __fsub_rn(yi, o.y));
       if (d2 < support_sq_exact(hi, o.z, f_ext)) {
         ce++;
-        if (d2 < support_sq_exact(hi, o.z, f_near)) cn++;
-        if (j - i0 + 32768u > 65535u) fits = false;
+        if (d2 < support_sq_exact(hi, o.z, f_near) && j - win0 < ASPH_PAIR_WIN) cw++;
+        else {
+          if (d2 < support_sq_exact(hi, o.z, f_near)) cf++;
+          if (j - i0 + 32768u > 65535u) fits = false;
+        }
       }
     });
   }
-  uint32_t we = nb_col_rows(cn, ce), ce_max = ce;
+  const uint32_t cn = cw + cf;
+  const bool wide = !__all_sync(0xffffffffu, fits);
+  uint32_t chunks = nb_col_chunks(cw, cf, ce, wide), ce_max = ce;
   for (int o = 16; o > 0; o >>= 1) {
-    we = max(we, __shfl_xor_sync(0xffffffffu, we, o));
+    chunks = max(chunks, __shfl_xor_sync(0xffffffffu, chunks, o));
     ce_max = max(ce_max, __shfl_xor_sync(0xffffffffu, ce_max, o));
   }
-  const bool wide = !__all_sync(0xffffffffu, fits);
-  const uint32_t units = nb_slice_units(we, wide);
+  const uint32_t units = 4u * chunks;  // a chunk = 32 lanes x 16 B = 4 pool units of 64 uint16
   uint32_t base64 = 0;
   if (lane == 0) {
     base64 = atomicAdd(&ctl->list_used, units);
@@ -139,24 +149,27 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
   }
   base64 = __shfl_sync(0xffffffffu, base64, 0);
   if (!active) return;
-  if (base64 + units > pool_cap64 || base64 + units < base64) { cnt[i] = 0u; return; }  // empty column: later passes stay in bounds
-  cnt[i] = cn | (ce << 16);
+  if (base64 + units > pool_cap64 || base64 + units < base64) { cnt[i] = 0u; cnt_ext[i] = 0u; return; }  // empty column: later passes stay in bounds
+  cnt[i] = cw | (cf << 12);
+  cnt_ext[i] = ce;
 
-  // pass 2: write the indices (2h neighbours first, then the extended-range rest)
+  // pass 2: write the entries (window segment, far 2h segment, extended-range rest)
   uint16_t* slice = pool + size_t(base64) * 64u;
+  const uint32_t bias = i0 - 32768u;
   {
-    const uint32_t bias = i0 - 32768u;
-    uint32_t kn = 0, ke = (cn + 7u) & ~7u;
+    uint32_t kw = 0, kf = 0, ke = nb_pad4(cf);
     for_each_candidate(xi, yi, hi, ctl_in, cellstart, f_ext, [&](uint32_t j) {
       const float4 o = __ldg(&xyhm[j]);
       const float d2 = dist_sq_exact(__fsub_rn(xi, o.x), __fsub_rn(yi, o.y));
-      uint32_t row;
-      if (d2 < support_sq_exact(hi, o.z, f_near)) row = kn++;
-      else if (d2 < support_sq_exact(hi, o.z, f_ext)) row = ke++;
-      else return;
-      nb_store(slice, wide, lane, row, j, bias);
+      if (d2 < support_sq_exact(hi, o.z, f_near)) {
+        if (j - win0 < ASPH_PAIR_WIN) nb_store_w(slice, lane, kw++, (j - win0) * 16u);
+        else nb_store_fe(slice, wide, lane, cw, kf++, j, bias);
+      } else if (d2 < support_sq_exact(hi, o.z, f_ext)) {
+        nb_store_fe(slice, wide, lane, cw, ke++, j, bias);
+      }
     });
-    for (uint32_t r = cn; r < ((cn + 7u) & ~7u); r++) nb_store(slice, wide, lane, r, i, bias);  // padding: the particle itself
+    for (uint32_t r = cw; r < nb_pad8(cw); r++) nb_store_w(slice, lane, r, (i - win0) * 16u);  // padding: the particle itself
+    for (uint32_t k = cf; k < nb_pad4(cf); k++) nb_store_fe(slice, wide, lane, cw, k, i, bias);
   }
 
   // boundary terms
@@ -166,10 +179,8 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
   // pass 3: pair sums over the thread's own 2h column (all lanes busy, no predicate divergence)
   float rho = 0.f, Sx = 0.f, Sy = 0.f, Q = 0.f, Nx = 0.f, Ny = 0.f;
   {
-    const uint32_t bias = i0 - 32768u;
     for (uint32_t k = 0; k < cn; k++) {
-      const uint32_t j = wide ? reinterpret_cast<const uint32_t*>(slice)[(k >> 2) * 128u + lane * 4u + (k & 3u)]
-                              : bias + uint32_t(slice[(k >> 3) * 256u + lane * 8u + (k & 7u)]);
+      const uint32_t j = nb_get(slice, wide, i, k, cw, cf);
       const float4 o = __ldg(&xyhm[j]);
       const float dx = xi - o.x, dy = yi - o.y;
       float w, g;
@@ -219,7 +230,7 @@ int launch_neighbors(asph_sim* sim, float f_ext, float f_near) {
   }
   const uint32_t cap64 = uint32_t(std::min<size_t>(sim->nbpool.cap / 64, 0x7FFFFFF0u));
   k_neighbors<<<blocks, kThreads, 0, sim->stream>>>(n, sim->xyhm.p, sim->ctl, sim->ctl, sim->cellstart.p, sim->pp, sim->lut.p, f_ext, f_near,
-                                                    cap64, sim->nbpool.p, sim->slice_base.p, sim->cnt.p, sim->rho.p, sim->gB.p,
+                                                    cap64, sim->nbpool.p, sim->slice_base.p, sim->cnt.p, sim->cnt_ext.p, sim->rho.p, sim->gB.p,
                                                     sim->pconst.p, sim->lam_sum.p, sim->lam_grad.p, sim->nrm.p,
                                                     sim->dist ? sim->refid[sim->cur].p : nullptr);
   LAUNCH_CHECK();

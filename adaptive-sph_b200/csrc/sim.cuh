@@ -140,7 +140,7 @@ struct asph_sim {
   DevBuf<float> h_tmp, rho, lam_sum;
   DevBuf<float2> nrm, gB, lam_grad;
   DevBuf<uint32_t> key, cellcount, cellstart, order, scan_sums;
-  DevBuf<uint32_t> cnt, slice_base;
+  DevBuf<uint32_t> cnt, cnt_ext, slice_base;
   DevBuf<uint16_t> nbpool;  // sliced-ELL neighbour lists (lists.cuh)
   DevBuf<float2> hm;        // {h, m} per particle: second gather of the adaptive-h pair passes
   int predicted_sweeps[2] = {1, 1};  // sweeps of the divergence / density solve in the previous step
@@ -177,6 +177,7 @@ struct asph_sim {
   uint64_t pc_calls[ASPH_PC_COUNT] = {0};
   cudaEvent_t ev_begin[ASPH_PC_COUNT], ev_end[ASPH_PC_COUNT];
   int sm_count = 148;
+  bool ctl_seen = false;  // ctl_host holds a control block read back from the device (possibly of the previous step)
   std::string last_error;
   uint64_t kernel_launches = 0;
   // kernel timing (asph_set_kernel_timing)

@@ -14,8 +14,6 @@
 
 namespace {
 
-constexpr int kThreads = 256;
-
 __global__ void k_solver_reset(StepCtl* ctl) {
   SolverCtl& s = ctl->solver;
   if (threadIdx.x == 0) {
@@ -78,30 +76,34 @@ __global__ void k_solver_decide(StepCtl* ctl, int sweep, float rho0, float tol, 
 // ---- shared-memory window ------------------------------------------------------------------------------------
 // Particles are sorted by strip-major cell number (sim.cuh), so almost every 2h neighbour of the kThreads consecutive
 // particles of a block lies within kHalo positions of the block's range.  The block stages that window of the gathered
-// pack (and of {h, m} when h is not uniform) in shared memory with coalesced loads; a neighbour outside the window
-// (across a strip edge, or in another size level's grid) is read from global memory instead.  Correctness never
-// depends on the window, only the speed does.  Slot t of the window holds particle wa + t, wa = block_first - kHalo
-// (mod 2^32: for the first block the slots of "negative" particles stay unused).
-static_assert(kThreads == int(ASPH_PAIR_BLOCK), "the neighbour index bias is aligned to the pair-pass block size");
-constexpr uint32_t kHalo = 192;
-constexpr uint32_t kWin = kThreads + 2 * kHalo;
+// pack (and of {h, m} when h is not uniform) in shared memory with asynchronous coalesced copies.  The neighbour build
+// (neighbors.cu) has already split every column into the entries inside this window — stored as the byte offset of
+// their slot, so a gather is one bit-field extract and one LDS.128 — and the few outside it (across a strip edge, or
+// in another size level's grid), which are read from global memory in a second, short loop.  Slot t of the window
+// holds particle wa + t, wa = block_first - kHalo (mod 2^32: for the first block the slots of "negative" particles
+// stay unused; no column refers to them).
+constexpr int kThreads = int(ASPH_PAIR_BLOCK);
+constexpr uint32_t kHalo = ASPH_PAIR_HALO;
+constexpr uint32_t kWin = ASPH_PAIR_WIN;
+static_assert(kWin * 16u <= 65536u, "window byte offsets are stored in 16 bits");
 
 // Per-block context of a pair pass.  Order inside a kernel: issue() the asynchronous window copy, construct the
 // thread's PairCol (slice header, counts, first two index chunks) and load the thread's own values, then wait() —
 // so the three kinds of global-memory latency overlap instead of following one another.
 struct PairWindow {
-  uint32_t sp, sh, sa;  // shared addresses of the staged pack / {h, m} / aux arrays
+  const float4* wp;  // the staged arrays (shared memory)
+  const float2* wh;
+  const float* wa;
   template <bool AUX>
   __device__ __forceinline__ void issue(uint32_t n, bool uni, const float4* __restrict__ pack, const float2* __restrict__ hm,
                                         const float* __restrict__ aux, float4 (&s_pack)[kWin], float2 (&s_hm)[kWin], float* s_aux) {
-    sp = uint32_t(__cvta_generic_to_shared(&s_pack[0]));
-    sh = uint32_t(__cvta_generic_to_shared(&s_hm[0]));
-    sa = AUX ? uint32_t(__cvta_generic_to_shared(s_aux)) : 0u;
-    // pinned in registers (the compiler would otherwise re-derive them from the CTA id special register at every gather)
-    asm volatile("" : "+r"(sp), "+r"(sh), "+r"(sa));
-    const uint32_t wa = blockIdx.x * kThreads - kHalo;
+    wp = s_pack; wh = s_hm; wa = s_aux;
+    const uint32_t sp = uint32_t(__cvta_generic_to_shared(&s_pack[0]));
+    const uint32_t sh = uint32_t(__cvta_generic_to_shared(&s_hm[0]));
+    const uint32_t sa = AUX ? uint32_t(__cvta_generic_to_shared(s_aux)) : 0u;
+    const uint32_t w0 = blockIdx.x * kThreads - kHalo;
     for (uint32_t t = threadIdx.x; t < kWin; t += kThreads) {
-      const uint32_t g = wa + t;
+      const uint32_t g = w0 + t;
       if (g < n) {
         cp_async16(sp + t * 16u, pack + g);
         if (!uni) cp_async8(sh + t * 8u, hm + g);
@@ -115,16 +117,18 @@ struct PairWindow {
   }
 };
 
-struct PairCol {  // a thread's column header plus its first 16 rows, requested before the window barrier
+// where a pair pass finds {h_j, m_j}: nowhere (h is uniform, m_j = m_i), in the staged window, or in global memory
+enum { HM_UNI = 0, HM_WIN = 1, HM_GLOBAL = 2 };
+
+struct PairCol {  // a thread's column header plus its first 16 window rows, requested before the window barrier
   NbCol col;
   uint4 c0, c1;
+  __device__ __forceinline__ PairCol(const NbCol& c, const uint4& a, const uint4& b) : col(c), c0(a), c1(b) {}
   __device__ __forceinline__ PairCol(const NbLists& L, uint32_t i, bool active) : c0(make_uint4(0, 0, 0, 0)), c1(make_uint4(0, 0, 0, 0)) {
     if (active) {
       col = NbCol(L, i);
-      if (!col.wide) {
-        if (col.cn > 0u) c0 = col.raw8(0);
-        if (col.cn > 8u) c1 = col.raw8(8);
-      }
+      if (col.cw > 0u) c0 = col.raw8(0);
+      if (col.cw > 8u) c1 = col.raw8(8);
     }
   }
 };
@@ -132,69 +136,69 @@ struct PairCol {  // a thread's column header plus its first 16 rows, requested 
 // Σ over N_2(i) of f(pack[j], x_ij, c_ij, h_ij, aux[j]); the caller multiplies its sums by the returned scale:
 //   uniform h (UNI):  c_ij = w'(q)/r un-normalised,   scale = m * 40 / (7 pi (2h)^3)
 //   otherwise:        c_ij = m_j * dW/dr / r,         scale = 1
-// (every f is linear in c).  A column is consumed 8 rows at a time: the gathers (shared memory, or global for the few
-// rows outside the window), then the arithmetic.  Padding rows point at the particle itself (zero distance =>
-// c = 0), so there are no per-entry bounds checks.  The index chunk two iterations ahead is always in flight.
-template <bool UNI, bool AUX, class F>
-__device__ __forceinline__ void pair_chunk(const uint32_t (&off)[8], const PairWindow& W, const float4* __restrict__ pack,
-                                           const float2* __restrict__ hm, const float* __restrict__ aux, float xi, float yi, float hi,
-                                           const PairShape& shape, F& f) {
-  const uint32_t wa = blockIdx.x * kThreads - kHalo;
+// (every f is linear in c).  The window segment of a column is consumed 8 rows at a time — the gathers, then the
+// arithmetic; padding rows point at the particle itself (zero distance => c = 0), so there are no per-entry checks.
+// The index chunk two iterations ahead is always in flight.  The far segment follows 4 rows at a time from global memory.
+template <int HM, bool AUX, class F>
+__device__ __forceinline__ void pair_apply(const float4& o, const float2& t, float a, float xi, float yi, float hi, const PairShape& shape, F& f) {
+  constexpr bool UNI = HM == HM_UNI;
+  const float dx = xi - o.x, dy = yi - o.y;
+  const float d2 = dx * dx + dy * dy;
+  if (UNI) {
+    f(o, dx, dy, shape(d2), hi, a);
+  } else {
+    const float hij = (hi + t.x) * 0.5f;
+    f(o, dx, dy, t.y * pair_g(d2, hij), hij, a);
+  }
+}
+template <int HM, bool AUX, class F>
+__device__ __forceinline__ float for_each_pair(const PairCol& P, const PairWindow& W, const float4* __restrict__ pack,
+                                               const float2* __restrict__ hm, const float* __restrict__ aux, float xi, float yi, float hi,
+                                               float mi, F f) {
+  constexpr bool UNI = HM == HM_UNI;
+  const NbCol& col = P.col;
+  const float inv2h = fast_rcp(2.f * hi);
+  const PairShape shape(inv2h);
+  // ---- window segment
+  uint4 cur = P.c0, nxt = P.c1;
+  for (uint32_t k0 = 0; k0 < col.cw; k0 += 8u) {
+    const uint4 v = cur;
+    cur = nxt;
+    if (k0 + 16u < col.cw) nxt = col.raw8(k0 + 16u);
+    const uint32_t off[8] = {v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16, v.z & 0xffffu, v.z >> 16, v.w & 0xffffu, v.w >> 16};
 #pragma unroll
-  for (int half = 0; half < 2; half++) {
+    for (int half = 0; half < 2; half++) {
+      float4 o[4];
+      float2 t[4];
+      float a[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t of = off[half * 4 + u];
+        o[u] = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(W.wp) + of);
+        if (HM == HM_WIN) t[u] = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(W.wh) + (of >> 1));
+        else if (HM == HM_GLOBAL) t[u] = __ldg(hm + (nb_win0(col.i) + (of >> 4)));
+        else t[u] = make_float2(0.f, 0.f);
+        a[u] = AUX ? *reinterpret_cast<const float*>(reinterpret_cast<const char*>(W.wa) + (of >> 2)) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) pair_apply<HM, AUX>(o[u], t[u], a[u], xi, yi, hi, shape, f);
+    }
+  }
+  // ---- far segment (divergent: most threads have none)
+  for (uint32_t k0 = 0; k0 < col.cf; k0 += 4u) {
+    uint32_t j[4];
+    col.far4(k0, j);
     float4 o[4];
     float2 t[4];
     float a[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      const uint32_t of = off[half * 4 + u];
-      if (of < kWin) {
-        o[u] = lds_f4(W.sp + of * 16u);
-        if (!UNI) t[u] = lds_f2(W.sh + of * 8u);
-        if (AUX) a[u] = lds_f1(W.sa + of * 4u);
-      } else {
-        const uint32_t jj = wa + of;
-        o[u] = __ldg(pack + jj);
-        if (!UNI) t[u] = __ldg(hm + jj);
-        if (AUX) a[u] = __ldg(aux + jj);
-      }
+      o[u] = __ldg(pack + j[u]);
+      t[u] = UNI ? make_float2(0.f, 0.f) : __ldg(hm + j[u]);
+      a[u] = AUX ? __ldg(aux + j[u]) : 0.f;
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const float dx = xi - o[u].x, dy = yi - o[u].y;
-      const float d2 = dx * dx + dy * dy;
-      if (UNI) {
-        f(o[u], dx, dy, shape(d2), hi, AUX ? a[u] : 0.f);
-      } else {
-        const float hij = (hi + t[u].x) * 0.5f;
-        f(o[u], dx, dy, t[u].y * pair_g(d2, hij), hij, AUX ? a[u] : 0.f);
-      }
-    }
-  }
-}
-template <bool UNI, bool AUX, class F>
-__device__ __forceinline__ float for_each_pair(const PairCol& P, const PairWindow& W, const float4* __restrict__ pack,
-                                               const float2* __restrict__ hm, const float* __restrict__ aux, float xi, float yi, float hi,
-                                               float mi, F f) {
-  const NbCol& col = P.col;
-  const float inv2h = fast_rcp(2.f * hi);
-  const PairShape shape(inv2h);
-  if (!col.wide) {
-    uint4 cur = P.c0, nxt = P.c1;
-    for (uint32_t k0 = 0; k0 < col.cn; k0 += 8u) {
-      const uint4 v = cur;
-      cur = nxt;
-      if (k0 + 16u < col.cn) nxt = col.raw8(k0 + 16u);
-      uint32_t off[8];
-      NbCol::decode8(v, kHalo, off);
-      pair_chunk<UNI, AUX>(off, W, pack, hm, aux, xi, yi, hi, shape, f);
-    }
-  } else {
-    for (uint32_t k0 = 0; k0 < col.cn; k0 += 8u) {
-      uint32_t off[8];
-      col.get8_off<true>(k0, kHalo, off);
-      pair_chunk<UNI, AUX>(off, W, pack, hm, aux, xi, yi, hi, shape, f);
-    }
+    for (int u = 0; u < 4; u++) pair_apply<HM, AUX>(o[u], t[u], a[u], xi, yi, hi, shape, f);
   }
   return UNI ? mi * (ASPH_KNORM * inv2h * inv2h * inv2h) : 1.f;
 }
@@ -206,7 +210,7 @@ __device__ __forceinline__ void viscosity_body(uint32_t i, const PairCol& C, con
                                                const PackedParams& P, float dt, float4* __restrict__ xv_out) {
   float ax = 0.f, ay = 0.f;
   if (P.viscosity_type != ASPH_VISC_XSPH && P.viscosity != 0.f) {
-    const float scale = for_each_pair<UNI, true>(C, W, xv_in, hm, rho, me.x, me.y, own.x, own.y,
+    const float scale = for_each_pair<UNI ? HM_UNI : HM_WIN, true>(C, W, xv_in, hm, rho, me.x, me.y, own.x, own.y,
                              [&](const float4& o, float dx, float dy, float c, float hij, float rho_j) {
       const float est = dx * (me.z - o.z) + dy * (me.w - o.w);
       if (est < 0.f) {
@@ -279,8 +283,8 @@ k_source(uint32_t n, NbLists L, const float4* __restrict__ xv, const float2* __r
   if (pairs) {
     float sum = 0.f;
     auto body = [&](const float4& o, float dx, float dy, float c, float, float) { sum += c * ((o.z - me.z) * dx + (o.w - me.w) * dy); };
-    const float scale = uni ? for_each_pair<true, false>(C, W, xv, hm, nullptr, me.x, me.y, own.x, own.y, body)
-                            : for_each_pair<false, false>(C, W, xv, hm, nullptr, me.x, me.y, own.x, own.y, body);
+    const float scale = uni ? for_each_pair<HM_UNI, false>(C, W, xv, hm, nullptr, me.x, me.y, own.x, own.y, body)
+                            : for_each_pair<HM_WIN, false>(C, W, xv, hm, nullptr, me.x, me.y, own.x, own.y, body);
     sum *= scale;
     const float div = sum / rho_i - (me.z * pc.x + me.w * pc.y);
     s = -div / dt;
@@ -339,8 +343,8 @@ k_accel(uint32_t n, NbLists L, const float4* __restrict__ P0, const float4* __re
       const float f = c * (me.z + o.z);
       ax -= f * dx; ay -= f * dy;
     };
-    const float scale = uni ? for_each_pair<true, false>(C, W, packP, hm, nullptr, me.x, me.y, own.x, own.y, body)
-                            : for_each_pair<false, false>(C, W, packP, hm, nullptr, me.x, me.y, own.x, own.y, body);
+    const float scale = uni ? for_each_pair<HM_UNI, false>(C, W, packP, hm, nullptr, me.x, me.y, own.x, own.y, body)
+                            : for_each_pair<HM_WIN, false>(C, W, packP, hm, nullptr, me.x, me.y, own.x, own.y, body);
     ax *= scale; ay *= scale;
     const float2 g = gB[i];
     ax -= me.w * g.x;
@@ -409,8 +413,8 @@ k_jacobi(uint32_t n, NbLists L, const float4* __restrict__ packA, float4* __rest
     } else {
       float sum = 0.f;
       auto body = [&](const float4& o, float dx, float dy, float c, float, float) { sum += c * ((o.z - me.z) * dx + (o.w - me.w) * dy); };
-      const float scale = uni ? for_each_pair<true, false>(C, W, packA, hm, nullptr, me.x, me.y, own.x, own.y, body)
-                              : for_each_pair<false, false>(C, W, packA, hm, nullptr, me.x, me.y, own.x, own.y, body);
+      const float scale = uni ? for_each_pair<HM_UNI, false>(C, W, packA, hm, nullptr, me.x, me.y, own.x, own.y, body)
+                              : for_each_pair<HM_WIN, false>(C, W, packA, hm, nullptr, me.x, me.y, own.x, own.y, body);
       sum *= scale;
       const float Ap = sum / rho_i - (me.z * pc.x + me.w * pc.y);
       const float resid = pc.w - Ap;
@@ -455,9 +459,229 @@ k_jacobi(uint32_t n, NbLists L, const float4* __restrict__ packA, float4* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------- K14 + K15, sweep form
+// The two passes of a Jacobi sweep as PERSISTENT, software-pipelined kernels: a block walks over tiles of kThreads
+// consecutive particles (tile = blockIdx.x, + gridDim.x, ...) and, while it computes tile t out of one shared-memory
+// stage, the asynchronous copies (LDGSTS) of tile t + 1 — the gather window, the threads' own per-particle inputs and
+// the first two index chunks of every column — are already in flight into the other stage; the column headers
+// (counts, slice base) of tile t + 2 travel in registers.  No thread waits for a global load in the steady state except
+// in the short far-segment loop and for columns longer than 16 window rows.
+//   PASS 0 (K14): a^p from p.     own inputs: gB.                    output: packA
+//   PASS 1 (K15): p' from a^p.    own inputs: pconst, rho, p_old.    output: the other pressure pack + statistics
+// HMWIN: the stages have room for the {h, m} window (adaptive h).  The host picks it from the last control block it
+// has seen; if that guess was "uniform" and the step turns out not to be, {h, m} are gathered from global memory.
+template <bool HMWIN>
+struct SweepStage {
+  float4 win[kWin];
+  uint4 chunk[2][kThreads];
+  float4 own4[kThreads];
+  float2 own2[kThreads];
+  float own1[2][kThreads];
+  float2 hmw[HMWIN ? kWin : 1];
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+struct SweepArgs {
+  uint32_t n;
+  NbLists L;
+  const float4* P0; const float4* P1;  // pressure packs {x, y, p/rho^2, p}
+  float4* P0w; float4* P1w;
+  float4* packA;
+  const float2* hm;
+  const float2* gB;
+  const float4* pconst;
+  const float* rho;
+  StepCtl* ctl;
+  const uint32_t* gid;
+  float omega, rho0, tol;
+  int sweep, density_mode, max_iters;
+};
+
+template <int PASS, bool HMWIN>
+__global__ void __launch_bounds__(kThreads, HMWIN ? 3 : 4)
+k_sweep(const SweepArgs A) {
+  extern __shared__ __align__(16) unsigned char sweep_smem[];
+  typedef SweepStage<HMWIN> Stage;
+  Stage* stages = reinterpret_cast<Stage*>(sweep_smem);
+  __shared__ int s_stop;
+  StepCtl* ctl = A.ctl;
+  if (ctl->solver.done) return;
+  const uint32_t n = A.n, tid = threadIdx.x, G = gridDim.x;
+  const uint32_t ntiles = (n + kThreads - 1) / kThreads;
+  const bool odd = (A.sweep & 1) != 0;
+  const float4* __restrict__ packP = odd ? A.P1 : A.P0;
+  float4* __restrict__ packP_next = odd ? A.P0w : A.P1w;
+  const float4* __restrict__ pack = PASS == 0 ? packP : A.packA;  // what the pass gathers
+  const bool uni = ctl->hmin == ctl->hmax;
+  const float dt = ctl->dt;
+
+  // column header of a tile, kept in registers two tiles ahead
+  auto load_hdr = [&](uint32_t t, uint32_t& c, uint32_t& sb) {
+    const uint32_t i = t * kThreads + tid;
+    c = 0u; sb = 0u;
+    if (t < ntiles && i < n) { c = __ldg(&A.L.cnt[i]); sb = __ldg(&A.L.slice_base[i >> 5]); }
+  };
+  // all asynchronous copies of a tile into a stage
+  auto issue = [&](uint32_t t, Stage& S, uint32_t c, uint32_t sb) {
+    const uint32_t w0 = t * kThreads - kHalo;
+    for (uint32_t slot = tid; slot < kWin; slot += kThreads) {
+      const uint32_t g = w0 + slot;
+      if (g < n) {
+        cp_async16(smem_addr(&S.win[slot]), pack + g);
+        if (HMWIN && !uni) cp_async8(smem_addr(&S.hmw[slot]), A.hm + g);
+      }
+    }
+    const uint32_t i = t * kThreads + tid;
+    if (i < n) {
+      const uint32_t cw = nb_cw(c);
+      const uint16_t* col = A.L.pool + size_t(sb & 0x7fffffffu) * 64u + (i & 31u) * 8u;
+      if (cw > 0u) cp_async16(smem_addr(&S.chunk[0][tid]), col);
+      if (cw > 8u) cp_async16(smem_addr(&S.chunk[1][tid]), col + 256);
+      cp_async8(smem_addr(&S.own2[tid]), A.hm + i);
+      if (PASS == 0) {
+        cp_async8(smem_addr(&S.own4[tid]), A.gB + i);
+      } else {
+        cp_async16(smem_addr(&S.own4[tid]), A.pconst + i);
+        cp_async4(smem_addr(&S.own1[0][tid]), A.rho + i);
+        cp_async4(smem_addr(&S.own1[1][tid]), reinterpret_cast<const float*>(packP + i) + 3);
+      }
+    }
+  };
+
+  uint32_t tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  uint32_t c_cur, sb_cur, c_nxt, sb_nxt;
+  load_hdr(tile, c_cur, sb_cur);
+  load_hdr(tile + G, c_nxt, sb_nxt);
+  if (PASS == 0) {
+    if (tid == 0) {
+      // prologue of sweep number `sweep` >= 1: the stop rule for sweep - 1 from its totals, once per block, while the
+      // first headers are in flight; block 0 also records it for the host
+      const SweepTotals t = read_totals(ctl, A.sweep - 1);
+      const bool stop = sweep_stops(t, A.sweep - 1, ctl->error_flags, dt, A.rho0, A.tol, A.max_iters, A.density_mode);
+      if (blockIdx.x == 0) record_sweep(ctl, t, A.sweep - 1, stop);
+      s_stop = stop ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_stop) return;  // the solve ended with the previous sweep
+  }
+  issue(tile, stages[0], c_cur, sb_cur);
+  cp_async_commit();
+
+  uint32_t c_normal = 0, c_sing = 0, c_neg = 0;
+  float e_sum = 0.f, e_max = 0.f;
+  bool bad = false;
+  int s = 0;
+  for (; tile < ntiles; tile += G, s ^= 1) {
+    Stage& S = stages[s];
+    if (tile + G < ntiles) issue(tile + G, stages[s ^ 1], c_nxt, sb_nxt);
+    cp_async_commit();
+    uint32_t c_nn, sb_nn;
+    load_hdr(tile + 2u * G, c_nn, sb_nn);
+    cp_async_wait_1();
+    __syncthreads();
+
+    const uint32_t i = tile * kThreads + tid;
+    const bool active = i < n && !(PASS == 1 && A.gid && (A.gid[i] & ASPH_GHOST_BIT));
+    if (active) {
+      NbCol col;
+      col.i = i; col.cw = nb_cw(c_cur); col.cf = nb_cf(c_cur); col.cn = col.cw + col.cf;
+      col.wide = (sb_cur >> 31) != 0u;
+      col.slice = A.L.pool + size_t(sb_cur & 0x7fffffffu) * 64u;
+      const float4 me = S.win[kHalo + tid];
+      const float2 own = S.own2[tid];
+      PairWindow W;
+      W.wp = S.win; W.wh = S.hmw; W.wa = nullptr;
+      if (PASS == 0) {
+        const PairCol C(col, S.chunk[0][tid], S.chunk[1][tid]);
+        float ax = 0.f, ay = 0.f;
+        auto body = [&](const float4& o, float dx, float dy, float c, float, float) {
+          const float f = c * (me.z + o.z);
+          ax -= f * dx; ay -= f * dy;
+        };
+        const float scale = uni ? for_each_pair<HM_UNI, false>(C, W, pack, A.hm, nullptr, me.x, me.y, own.x, own.y, body)
+                                : for_each_pair<HMWIN ? HM_WIN : HM_GLOBAL, false>(C, W, pack, A.hm, nullptr, me.x, me.y, own.x, own.y, body);
+        const float2 g = *reinterpret_cast<const float2*>(&S.own4[tid]);
+        ax = ax * scale - me.w * g.x;
+        ay = ay * scale - me.w * g.y;
+        A.packA[i] = make_float4(me.x, me.y, ax, ay);
+      } else {
+        const float4 pc = S.own4[tid];
+        const float rho_i = S.own1[0][tid], p_old = S.own1[1][tid];
+        float pn = 0.f;
+        if (fabsf(pc.z) < 10e-4f) {
+          c_sing++;
+        } else {
+          const PairCol C(col, S.chunk[0][tid], S.chunk[1][tid]);
+          float sum = 0.f;
+          auto body = [&](const float4& o, float dx, float dy, float c, float, float) { sum += c * ((o.z - me.z) * dx + (o.w - me.w) * dy); };
+          const float scale = uni ? for_each_pair<HM_UNI, false>(C, W, pack, A.hm, nullptr, me.x, me.y, own.x, own.y, body)
+                                  : for_each_pair<HMWIN ? HM_WIN : HM_GLOBAL, false>(C, W, pack, A.hm, nullptr, me.x, me.y, own.x, own.y, body);
+          sum *= scale;
+          const float Ap = sum / rho_i - (me.z * pc.x + me.w * pc.y);
+          const float resid = pc.w - Ap;
+          pn = p_old + A.omega * resid / pc.z;
+          if (!isfinite(Ap) || !isfinite(pn)) bad = true;
+          const float perr = A.density_mode ? rho_i * dt * dt * resid : dt * resid;
+          if (pn <= 0.f) { pn = 0.f; c_neg++; }
+          else { c_normal++; e_sum += perr; e_max = fmaxf(e_max, fabsf(perr)); }
+        }
+        packP_next[i] = make_float4(me.x, me.y, pn / (rho_i * rho_i), pn);
+      }
+    }
+    __syncthreads();  // every thread is done with stage s before the next iteration refills it
+    c_cur = c_nxt; sb_cur = sb_nxt; c_nxt = c_nn; sb_nxt = sb_nn;
+  }
+
+  if (PASS == 1) {
+    if (bad) atomicOr(&ctl->error_flags, ERRF_SOLVER_NONFINITE);
+    // block totals, once per block: counts by redux, the error sum by a fixed-order shuffle tree; then integers only
+    c_normal = __reduce_add_sync(0xffffffffu, c_normal);
+    c_neg = __reduce_add_sync(0xffffffffu, c_neg);
+    c_sing = __reduce_add_sync(0xffffffffu, c_sing);
+    const unsigned int m_enc = __reduce_max_sync(0xffffffffu, __float_as_uint(e_max));  // non-negative floats order like their bits
+    for (int o = 16; o > 0; o >>= 1) e_sum += __shfl_xor_sync(0xffffffffu, e_sum, o);
+    __shared__ unsigned long long sh_cnt[kThreads / 32];
+    __shared__ long long sh_err[kThreads / 32];
+    __shared__ unsigned int sh_sing[kThreads / 32], sh_max[kThreads / 32];
+    const int lane = tid & 31, w = tid >> 5;
+    if (lane == 0) {
+      sh_cnt[w] = (unsigned long long)c_normal | ((unsigned long long)c_neg << 32);
+      sh_err[w] = __float2ll_rn(fminf(fmaxf(e_sum, -4096.f), 4096.f) * 4294967296.f);  // 2^-32 fixed point
+      sh_sing[w] = c_sing; sh_max[w] = m_enc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long cnt = 0;
+      long long err = 0;
+      unsigned int sing = 0, mx = 0;
+#pragma unroll
+      for (int k = 0; k < kThreads / 32; k++) { cnt += sh_cnt[k]; err += sh_err[k]; sing += sh_sing[k]; mx = max(mx, sh_max[k]); }
+      SolverCtl& sc = ctl->solver;
+      unsigned long long* acc = sc.acc[A.sweep % 3] + 2 * (blockIdx.x % ASPH_ACC_COPIES);
+      if (cnt) atomicAdd(acc, cnt);
+      if (err) atomicAdd(acc + 1, (unsigned long long)err);
+      if (sing) atomicAdd(sc.acc[A.sweep % 3] + 2 * ASPH_ACC_COPIES, (unsigned long long)sing);
+      // e_max >= 0: its bit pattern with the sign bit set is the order-preserving encoding dec_f expects
+      if (mx) atomicMax(&sc.maxerr_enc[A.sweep % 3], mx | 0x80000000u);
+    }
+  }
+}
+
+// grid of a persistent pair pass: every block gets the same number of tiles (the last one possibly fewer)
+inline uint32_t sweep_grid(uint32_t n, int sm_count, int blocks_per_sm) {
+  const uint32_t ntiles = (n + kThreads - 1) / kThreads;
+  const uint32_t slots = uint32_t(std::max(1, sm_count * blocks_per_sm));
+  const uint32_t per = (ntiles + slots - 1) / slots;
+  return (ntiles + per - 1) / per;
+}
+
 NbLists lists_of(asph_sim* sim) {
   NbLists L;
-  L.pool = sim->nbpool.p; L.slice_base = sim->slice_base.p; L.cnt = sim->cnt.p;
+  L.pool = sim->nbpool.p; L.slice_base = sim->slice_base.p; L.cnt = sim->cnt.p; L.cnt_ext = sim->cnt_ext.p;
   return L;
 }
 
@@ -503,6 +727,24 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
   int& predicted = sim->predicted_sweeps[density_mode ? 1 : 0];
   int batch = std::max(1, std::min(predicted, 256));
   const int max_sweeps = sim->pp.max_iters + 1;
+  // stage layout of the persistent sweep kernels: with room for the {h, m} window unless the last control block the
+  // host has seen says h is uniform (a wrong guess only costs speed, see k_sweep)
+  const bool hmwin = !(sim->ctl_seen && sim->ctl_host->hmin == sim->ctl_host->hmax);
+  const size_t smem = 2 * (hmwin ? sizeof(SweepStage<true>) : sizeof(SweepStage<false>));
+  const uint32_t grid = sweep_grid(n, sim->sm_count, hmwin ? 3 : 4);
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(k_sweep<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * sizeof(SweepStage<true>))));
+    CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * sizeof(SweepStage<true>))));
+    CUDA_TRY(cudaFuncSetAttribute(k_sweep<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * sizeof(SweepStage<false>))));
+    CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * sizeof(SweepStage<false>))));
+    attr_done = true;
+  }
+  SweepArgs A;
+  A.n = n; A.L = L; A.P0 = sim->packP[0].p; A.P1 = sim->packP[1].p; A.P0w = sim->packP[0].p; A.P1w = sim->packP[1].p;
+  A.packA = sim->packA.p; A.hm = sim->hm.p; A.gB = sim->gB.p; A.pconst = sim->pconst.p; A.rho = sim->rho.p; A.ctl = sim->ctl; A.gid = gid;
+  A.omega = sim->pp.jacobi_omega; A.rho0 = sim->pp.rest_density; A.tol = max_avg_error;
+  A.density_mode = density_mode ? 1 : 0; A.max_iters = sim->pp.max_iters;
   struct Timed { int sweep; cudaEvent_t e0, e1, e1b, e2; };  // e0..e1: K14; e1b..e2: K15 (halo exchanges excluded)
   std::vector<Timed> timed;
   for (;;) {
@@ -510,10 +752,10 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
       const bool time_it = sim->kt_every > 0 && (launched % sim->kt_every) == 0;
       Timed tm{launched, nullptr, nullptr, nullptr, nullptr};
       if (time_it) { tm.e0 = kt_event(sim); tm.e1 = kt_event(sim); tm.e1b = kt_event(sim); tm.e2 = kt_event(sim); cudaEventRecord(tm.e0, st); }
+      A.sweep = launched;
       if (launched > 0) {  // sweep 0: a^p = 0 was written by k_source
-        k_accel<0><<<blocks, kThreads, 0, st>>>(n, L, sim->packP[0].p, sim->packP[1].p, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, nullptr,
-                                                nullptr, nullptr, 0.f, gid, launched, sim->pp.rest_density, max_avg_error, sim->pp.max_iters,
-                                                density_mode ? 1 : 0);
+        if (hmwin) k_sweep<0, true><<<grid, kThreads, smem, st>>>(A);
+        else k_sweep<0, false><<<grid, kThreads, smem, st>>>(A);
         LAUNCH_CHECK();
         if (time_it) cudaEventRecord(tm.e1, st);
         if (sim->dist) TRY(dist_halo(sim, sim->packA.p, 16));
@@ -521,8 +763,8 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
         cudaEventRecord(tm.e1, st);
       }
       if (time_it) cudaEventRecord(tm.e1b, st);
-      k_jacobi<<<blocks, kThreads, 0, st>>>(n, L, sim->packA.p, sim->packP[0].p, sim->packP[1].p, sim->hm.p, sim->pconst.p, sim->rho.p,
-                                            sim->ctl, sim->pp.jacobi_omega, density_mode ? 1 : 0, gid, launched);
+      if (hmwin) k_sweep<1, true><<<grid, kThreads, smem, st>>>(A);
+      else k_sweep<1, false><<<grid, kThreads, smem, st>>>(A);
       LAUNCH_CHECK();
       if (time_it) { cudaEventRecord(tm.e2, st); timed.push_back(tm); }
       if (sim->dist) {

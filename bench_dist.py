@@ -15,7 +15,7 @@ import numpy as np
 def run(args, A, rank, world):
     import torch
     import torch.distributed as dist
-    from bench import (METRIC, UNIT, SPACING_C2, ClockSampler, dam_break, peaks, pinned, uniform_params)
+    from bench import (METRIC, UNIT, SPACING_C2, ClockSampler, dam_break, peaks, pinned, preroll, uniform_params)
 
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -32,6 +32,7 @@ def run(args, A, rank, world):
         dist.barrier()
         torch.cuda.synchronize()
 
+    pre_steps = preroll(sim, args.preroll_time)   # every rank sees the same global dt, hence the same step count
     for _ in range(W):
         sim.single_step()
     sim.set_kernel_timing(4)
@@ -103,7 +104,9 @@ def run(args, A, rank, world):
             "ms_per_step": dev_ms_max / max(K, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"configs[1] widened {world}x: 2D dam-break, uniform h, {n_global} particles ({n_global // world} per GPU), "
-                                   "HybridDFSPH, x-slab decomposition, NCCL ghost halos per pass",
+                                   "HybridDFSPH, x-slab decomposition, NCCL ghost halos per pass; "
+                                   f"state at t = {args.preroll_time} s (just after the block hits the floor: both pressure solves iterate)",
+                       "preroll_steps": pre_steps, "preroll_time_s": args.preroll_time,
                        "particles": n_global, "owned_per_rank": [int(x.item()) for x in owned_all],
                        "l2": "working set per GPU (~400 MB) exceeds the 126 MB L2; no flush",
                        "avg_div_sweeps": sweeps_div / max(K, 1), "avg_density_sweeps": sweeps_den / max(K, 1),
