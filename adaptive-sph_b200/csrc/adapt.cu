@@ -320,7 +320,7 @@ __global__ void k_split_apply(uint32_t n, uint32_t cap, const uint8_t* __restric
 AdaptArgs args_of(asph_sim* sim) {
   AdaptArgs A;
   const int c = sim->cur;
-  A.L.pool = sim->nbpool.p; A.L.slice_base = sim->slice_base.p; A.L.cnt = sim->cnt.p; A.L.cnt_ext = sim->cnt_ext.p; A.xyhm = sim->xyhm.p;
+  A.L.pool = sim->nbpool.p; A.L.slice_base = sim->slice_base.p; A.L.cnt = sim->cnt.p; A.L.cnt_ext = sim->cnt_ext.p; A.L.far_idx = sim->far_idx.p; A.L.far_cnt = sim->far_cnt.p; A.xyhm = sim->xyhm.p;
   A.pos = sim->pos[c].p; A.vel = sim->vel[c].p; A.mass = sim->mass[c].p; A.level = sim->level[c].p; A.refid = sim->refid[c].p;
   A.size_class = sim->size_class.p; A.partner = sim->merge_partner.p; A.counter = sim->merge_counter.p;
   A.stampkey = sim->stampkey.p;

@@ -472,7 +472,7 @@ void asph_destroy(asph_sim* sim) {
   }
   sim->xyhm.release(); sim->packA.release(); sim->pconst.release(); sim->h_tmp.release(); sim->rho.release(); sim->lam_sum.release();
   sim->nrm.release(); sim->gB.release(); sim->lam_grad.release(); sim->key.release(); sim->cellcount.release(); sim->cellstart.release();
-  sim->order.release(); sim->scan_sums.release(); sim->cnt.release(); sim->cnt_ext.release(); sim->slice_base.release();
+  sim->order.release(); sim->scan_sums.release(); sim->cnt.release(); sim->cnt_ext.release(); sim->far_idx.release(); sim->far_cnt.release(); sim->slice_base.release();
   sim->nbpool.release(); sim->hm.release(); sim->size_class.release(); sim->flags.release(); sim->merge_partner.release();
   sim->cand.release(); for (int k = 0; k < 4; k++) sim->scratch_u[k].release();
   sim->merge_counter.release(); sim->stamp.release(); sim->stampkey.release(); sim->scratch_f.release(); sim->lut.release(); sim->split_pos.release();
@@ -548,11 +548,13 @@ int asph_get_neighbors_csr(asph_sim* sim, uint64_t* offsets, uint32_t* idx, uint
   TRY(sync_ctl(sim));
   const size_t used = size_t(sim->ctl_host->list_used) * 64;  // uint16 units
   std::vector<uint16_t> pool(used);
+  std::vector<uint32_t> far(size_t((n + ASPH_PAIR_BLOCK - 1) / ASPH_PAIR_BLOCK) * ASPH_PAIR_FAR);
   if (n) {
     CUDA_TRY(cudaMemcpy(cnt.data(), sim->cnt.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(refid.data(), sim->refid[sim->cur].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(sbase.data(), sim->slice_base.p, sbase.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if (used) CUDA_TRY(cudaMemcpy(pool.data(), sim->nbpool.p, used * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(far.data(), sim->far_idx.p, far.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   }
   uint64_t nnz = 0;
   for (uint32_t i = 0; i < n; i++) nnz += nb_cn(cnt[i]);
@@ -569,7 +571,7 @@ int asph_get_neighbors_csr(asph_sim* sim, uint64_t* offsets, uint32_t* idx, uint
     const uint32_t sb = sbase[i >> 5];
     const bool wide = (sb >> 31) != 0;
     const size_t base = size_t(sb & 0x7fffffffu) * 64;
-    for (uint32_t k = 0; k < c; k++) idx[o + k] = refid[nb_get(pool.data() + base, wide, i, k, cw, cf)];
+    for (uint32_t k = 0; k < c; k++) idx[o + k] = refid[nb_get(pool.data() + base, far.data(), wide, i, k, cw, cf)];
     std::sort(idx + o, idx + o + c);
     o += c;
   }

@@ -9,7 +9,7 @@
 // support f*(h_i+h_j)/2 <= f*(h_i + hmax_b)/2, so i finds all its level-b neighbours in the cells of grid b that
 // overlap the box of that radius around x_i (neighbors.cu).  With uniform h there is one level whose cell is
 // exactly the support radius.
-#include "sim.cuh"
+#include "lists.cuh"
 
 namespace {
 
@@ -99,19 +99,24 @@ __global__ void k_make_levels(StepCtl* ctl, float f_search, uint32_t cells_budge
       if (!(fx < 4.0e6f) || !(fy < 4.0e6f)) { ok = false; break; }  // also catches inf / NaN extents
       g.nx = int(fx) + 1;
       g.ny = int(fy) + 1;
+      // a cell of edge f * h holds about 1.15 f^2 particles of smoothing length h at rest density (h = 1.9 sqrt(A / pi));
+      // one strip row plus 1.5 cells, with 10 % slack, should fit the halo of the pair passes' window (lists.cuh)
+      const float per_cell = 1.15f * f_search * f_search * scale * scale;
+      g.strip_log2 = 5;
+      while (g.strip_log2 > 2 && (float(1 << g.strip_log2) + 1.5f) * per_cell * 1.1f > float(ASPH_PAIR_HALO)) g.strip_log2--;
       g.base = uint32_t(total);
       ctl->lv[L] = g;
-      total += level_cells(g.nx, g.ny);
+      total += level_cells(g.nx, g.ny, g.strip_log2);
       upper *= 2.f;
     }
     if (ok && total <= cells_budget) { ctl->total_cells = uint32_t(total); return; }
     scale *= 1.5f;
   }
   GridLevel g;
-  g.hmax = hmax; g.cell = 1.f; g.inv_cell = 0.f; g.nx = 1; g.ny = 1; g.base = 0;
+  g.hmax = hmax; g.cell = 1.f; g.inv_cell = 0.f; g.nx = 1; g.ny = 1; g.strip_log2 = 2; g.base = 0;
   ctl->lv[0] = g;
   ctl->nlevels = 1;
-  ctl->total_cells = uint32_t(level_cells(1, 1));
+  ctl->total_cells = uint32_t(level_cells(1, 1, 2));
   atomicOr(&ctl->error_flags, ERRF_CELL_BUDGET);
 }
 
@@ -311,6 +316,10 @@ int ensure_capacity(asph_sim* sim, uint32_t want) {
   CUDA_TRY(sim->nrm.ensure(newcap)); CUDA_TRY(sim->gB.ensure(newcap)); CUDA_TRY(sim->lam_grad.ensure(newcap));
   CUDA_TRY(sim->key.ensure(newcap)); CUDA_TRY(sim->order.ensure(newcap));
   CUDA_TRY(sim->cnt.ensure(newcap)); CUDA_TRY(sim->cnt_ext.ensure(newcap));
+  {
+    const size_t tiles = (size_t(newcap) + ASPH_PAIR_BLOCK - 1) / ASPH_PAIR_BLOCK + 1;
+    CUDA_TRY(sim->far_cnt.ensure(tiles)); CUDA_TRY(sim->far_idx.ensure(tiles * ASPH_PAIR_FAR));
+  }
   const uint32_t nslices = (newcap + 31) / 32 + 1;
   CUDA_TRY(sim->slice_base.ensure(nslices)); CUDA_TRY(sim->hm.ensure(newcap));
   CUDA_TRY(sim->size_class.ensure(newcap)); CUDA_TRY(sim->flags.ensure(newcap));

@@ -165,7 +165,7 @@ int launch_level_estimation(asph_sim* sim) {
   if (n == 0) return ASPH_OK;
   cudaStream_t st = sim->stream;
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
-  Lists L{sim->nbpool.p, sim->slice_base.p, sim->cnt.p, sim->cnt_ext.p};
+  Lists L{sim->nbpool.p, sim->slice_base.p, sim->cnt.p, sim->cnt_ext.p, sim->far_idx.p, sim->far_cnt.p};
   const float cos_threshold = std::cos(50.f * (3.14159265358979323846f / 180.f));
   float* level = sim->level[sim->cur].p;
   k_level_reset<<<1, 1, 0, st>>>(sim->ctl);
@@ -200,7 +200,7 @@ int launch_level_smoothing(asph_sim* sim) {
   if (n == 0) { sim->level_valid = true; return ASPH_OK; }
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
   const int c = sim->cur;
-  Lists L{sim->nbpool.p, sim->slice_base.p, sim->cnt.p, sim->cnt_ext.p};
+  Lists L{sim->nbpool.p, sim->slice_base.p, sim->cnt.p, sim->cnt_ext.p, sim->far_idx.p, sim->far_cnt.p};
   k_smooth<<<blocks, kThreads, 0, sim->stream>>>(n, L, sim->pos[c].p, sim->xyhm.p, sim->rho.p,
                                                  sim->level[c].p, sim->scratch_f.p, sim->pp.maximum_surface_distance, sim->ctl);
   LAUNCH_CHECK();

@@ -11,7 +11,11 @@
 //      slot, (j - (b0 - HALO)) * 16, always 16 bits wide — the gather address of the hot loops is one extract away;
 //      padded with the particle's own slot up to a multiple of 8 (a zero-distance pair contributes nothing to any
 //      gradient sum, so the loops run whole chunks without per-entry checks);
-//   F  the cf 2h neighbours outside the window (across a strip edge, or in another size level's grid), starting at the
+//      the few 2h neighbours outside the contiguous window (across a strip edge, or in another size level's grid) are
+//      W rows as well: each tile of ASPH_PAIR_BLOCK particles owns a FAR TABLE of up to ASPH_PAIR_FAR particle indices
+//      (far_idx[tile * ASPH_PAIR_FAR + s], far_cnt[tile] of them), which the pair passes stage right behind the
+//      contiguous window — slot ASPH_PAIR_WIN + s — by indirect copies;
+//   F  the cf 2h neighbours that found no room in the tile's far table (across a strip edge, or in another size level's grid), starting at the
 //      chunk after W, padded with the particle itself up to a multiple of 4; the pair passes read these from global
 //      memory;
 //   E  the ce - cn remaining neighbours of the extended range used by the level set, right after F.
@@ -27,12 +31,16 @@
 #define ASPH_PAIR_BLOCK 256u  // threads per block of the pair passes == alignment of the index bias
 #define ASPH_PAIR_HALO 192u   // window slots before / after the block's own particles
 #define ASPH_PAIR_WIN (ASPH_PAIR_BLOCK + 2u * ASPH_PAIR_HALO)
+#define ASPH_PAIR_FAR 96u     // far-table slots per tile (staged one per thread; sized so that four blocks of the sweep kernels fit an SM)
+#define ASPH_PAIR_SLOTS (ASPH_PAIR_WIN + ASPH_PAIR_FAR)
 
 struct NbLists {
   const uint16_t* __restrict__ pool;
   const uint32_t* __restrict__ slice_base;
   const uint32_t* __restrict__ cnt;
   const uint32_t* __restrict__ cnt_ext;
+  const uint32_t* __restrict__ far_idx;
+  const uint32_t* __restrict__ far_cnt;
 };
 
 #ifdef __CUDACC__
@@ -58,9 +66,13 @@ __host__ __device__ __forceinline__ uint32_t nb_pos_fe(uint32_t lane, uint32_t c
   return wide ? (c0 + (k >> 2)) * 128u + lane * 4u + (k & 3u) : (c0 + (k >> 3)) * 256u + lane * 8u + (k & 7u);
 }
 // k-th real neighbour (k < ce) of particle i (host and device; `slice` = start of the slice in the pool)
-__host__ __device__ __forceinline__ uint32_t nb_get(const uint16_t* slice, bool wide, uint32_t i, uint32_t k, uint32_t cw, uint32_t cf) {
+__host__ __device__ __forceinline__ uint32_t nb_get(const uint16_t* slice, const uint32_t* far_idx, bool wide, uint32_t i, uint32_t k,
+                                                    uint32_t cw, uint32_t cf) {
   const uint32_t lane = i & 31u;
-  if (k < cw) return nb_win0(i) + (uint32_t(slice[nb_pos_w(lane, k)]) >> 4);
+  if (k < cw) {
+    const uint32_t slot = uint32_t(slice[nb_pos_w(lane, k)]) >> 4;
+    return slot < ASPH_PAIR_WIN ? nb_win0(i) + slot : far_idx[(i / ASPH_PAIR_BLOCK) * ASPH_PAIR_FAR + (slot - ASPH_PAIR_WIN)];
+  }
   const uint32_t kk = k < cw + cf ? k - cw : nb_pad4(cf) + (k - cw - cf);
   const uint32_t pos = nb_pos_fe(lane, cw, wide, kk);
   return wide ? reinterpret_cast<const uint32_t*>(slice)[pos] : nb_bias(i) + uint32_t(slice[pos]);
@@ -77,11 +89,12 @@ __device__ __forceinline__ void nb_store_fe(uint16_t* slice, bool wide, uint32_t
 
 struct NbCol {
   const uint16_t* slice;  // start of the slice in the pool
+  const uint32_t* far_idx;
   uint32_t i;
   uint32_t cw, cf, cn;    // window / far 2h neighbours, cn = cw + cf
   bool wide;
-  __device__ __forceinline__ NbCol() : slice(nullptr), i(0), cw(0), cf(0), cn(0), wide(false) {}  // empty column
-  __device__ __forceinline__ NbCol(const NbLists& L, uint32_t i_) : i(i_) {
+  __device__ __forceinline__ NbCol() : slice(nullptr), far_idx(nullptr), i(0), cw(0), cf(0), cn(0), wide(false) {}  // empty column
+  __device__ __forceinline__ NbCol(const NbLists& L, uint32_t i_) : far_idx(L.far_idx), i(i_) {
     const uint32_t sb = __ldg(&L.slice_base[i >> 5]);
     const uint32_t c = __ldg(&L.cnt[i]);
     cw = nb_cw(c); cf = nb_cf(c); cn = cw + cf;
@@ -89,7 +102,7 @@ struct NbCol {
     slice = L.pool + size_t(sb & 0x7fffffffu) * 64u;
   }
   // k-th real neighbour, k < ce (cold paths: level set, resampling)
-  __device__ __forceinline__ uint32_t get(uint32_t k) const { return nb_get(slice, wide, i, k, cw, cf); }
+  __device__ __forceinline__ uint32_t get(uint32_t k) const { return nb_get(slice, far_idx, wide, i, k, cw, cf); }
   // raw W rows [k0, k0 + 8), k0 a multiple of 8 (8 x uint16 window byte offsets).  Streaming loads: list entries are
   // read once per pass and should not displace the gathered packs in L2.
   __device__ __forceinline__ uint4 raw8(uint32_t k0) const {

@@ -83,10 +83,11 @@ __device__ __forceinline__ void for_each_candidate(float xi, float yi, float hi,
     const int cy0 = max(0, int(floorf((yi - r - oy) * g.inv_cell)));
     const int cy1 = min(g.ny - 1, int(floorf((yi + r - oy) * g.inv_cell)));
     if (cx0 > cx1) continue;
-    // cells are stored strip-major (grid.cu): a row's cells are contiguous inside one strip of ASPH_STRIP columns
+    // cells are stored strip-major (grid.cu): a row's cells are contiguous inside one strip of 2^strip_log2 columns
+    const int sl = g.strip_log2;
     for (int cy = cy0; cy <= cy1; cy++) {
-      for (int st = cx0 >> ASPH_STRIP_LOG2; st <= (cx1 >> ASPH_STRIP_LOG2); st++) {
-        const int ca = max(cx0, st << ASPH_STRIP_LOG2), cb = min(cx1, (st << ASPH_STRIP_LOG2) + ASPH_STRIP - 1);
+      for (int st = cx0 >> sl; st <= (cx1 >> sl); st++) {
+        const int ca = max(cx0, st << sl), cb = min(cx1, (st << sl) + (1 << sl) - 1);
         const uint32_t s = cellstart[cell_index(g, ca, cy)], e = cellstart[cell_index(g, cb, cy) + 1];
         for (uint32_t j = s; j < e; j++) f(j);
       }
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(kThreads)
 k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restrict__ ctl_in, StepCtl* ctl,
             const uint32_t* __restrict__ cellstart, const PackedParams P, const float* __restrict__ lut, float f_ext, float f_near,
             uint32_t pool_cap64, uint16_t* __restrict__ pool, uint32_t* __restrict__ slice_base, uint32_t* __restrict__ cnt, uint32_t* __restrict__ cnt_ext,
+            uint32_t* __restrict__ far_idx, uint32_t* __restrict__ far_cnt,
             float* __restrict__ rho_out, float2* __restrict__ gB_out, float4* __restrict__ pconst, float* __restrict__ lam_sum_out,
             float2* __restrict__ lam_grad_out, float2* __restrict__ nrm_out, const uint32_t* __restrict__ gid) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -116,7 +118,7 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
   // range, and whether every index stored outside the window segment fits 16 bits around the block
   const uint32_t win0 = i0 - ASPH_PAIR_HALO;
   uint32_t cw = 0, cf = 0, ce = 0;
-  bool fits = true;
+  bool fits = true, fits_far = true, fits_ext = true;
   if (active) {
     for_each_candidate(xi, yi, hi, ctl_in, cellstart, f_ext, [&](uint32_t j) {
       const float4 o = __ldg(&xyhm[j]);
@@ -124,13 +126,32 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
       if (d2 < support_sq_exact(hi, o.z, f_ext)) {
         ce++;
         if (d2 < support_sq_exact(hi, o.z, f_near) && j - win0 < ASPH_PAIR_WIN) cw++;
-        else {
-          if (d2 < support_sq_exact(hi, o.z, f_near)) cf++;
-          if (j - i0 + 32768u > 65535u) fits = false;
+        else if (d2 < support_sq_exact(hi, o.z, f_near)) {
+          cf++;
+          if (j - i0 + 32768u > 65535u) fits_far = false;
+        } else if (j - i0 + 32768u > 65535u) {
+          fits_ext = false;
         }
       }
     });
   }
+  // far 2h neighbours become window rows when the tile's far table has room for all of them (lists.cuh)
+  uint32_t far_base = 0xffffffffu;
+  if (cf > 0u) {
+    const uint32_t tile = i / ASPH_PAIR_BLOCK;
+    const uint32_t b = atomicAdd(&far_cnt[tile], cf);
+    if (b + cf <= ASPH_PAIR_FAR) {
+      far_base = b;
+    } else {  // no room: keep them as F entries; slots claimed past the end of the table are never staged, the ones
+              // inside it must still name a valid particle
+      for (uint32_t s = b; s < ASPH_PAIR_FAR; s++) far_idx[tile * ASPH_PAIR_FAR + s] = i;
+    }
+  }
+  const bool in_table = far_base != 0xffffffffu;
+  if (in_table) { cw += cf; cf = 0u; }
+  // the extended-range entries and the F entries that stayed decide whether the slice needs 32-bit entries
+  if (in_table && !fits_ext) fits = false;
+  else if (!in_table && !(fits_ext && fits_far)) fits = false;
   const uint32_t cn = cw + cf;
   const bool wide = !__all_sync(0xffffffffu, fits);
   uint32_t chunks = nb_col_chunks(cw, cf, ce, wide), ce_max = ce;
@@ -157,13 +178,20 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
   uint16_t* slice = pool + size_t(base64) * 64u;
   const uint32_t bias = i0 - 32768u;
   {
-    uint32_t kw = 0, kf = 0, ke = nb_pad4(cf);
+    uint32_t kw = 0, kf = 0, ke = nb_pad4(cf), kt = 0;
     for_each_candidate(xi, yi, hi, ctl_in, cellstart, f_ext, [&](uint32_t j) {
       const float4 o = __ldg(&xyhm[j]);
       const float d2 = dist_sq_exact(__fsub_rn(xi, o.x), __fsub_rn(yi, o.y));
       if (d2 < support_sq_exact(hi, o.z, f_near)) {
-        if (j - win0 < ASPH_PAIR_WIN) nb_store_w(slice, lane, kw++, (j - win0) * 16u);
-        else nb_store_fe(slice, wide, lane, cw, kf++, j, bias);
+        if (j - win0 < ASPH_PAIR_WIN) {
+          nb_store_w(slice, lane, kw++, (j - win0) * 16u);
+        } else if (in_table) {
+          far_idx[(i / ASPH_PAIR_BLOCK) * ASPH_PAIR_FAR + far_base + kt] = j;
+          nb_store_w(slice, lane, kw++, (ASPH_PAIR_WIN + far_base + kt) * 16u);
+          kt++;
+        } else {
+          nb_store_fe(slice, wide, lane, cw, kf++, j, bias);
+        }
       } else if (d2 < support_sq_exact(hi, o.z, f_ext)) {
         nb_store_fe(slice, wide, lane, cw, ke++, j, bias);
       }
@@ -180,7 +208,7 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
   float rho = 0.f, Sx = 0.f, Sy = 0.f, Q = 0.f, Nx = 0.f, Ny = 0.f;
   {
     for (uint32_t k = 0; k < cn; k++) {
-      const uint32_t j = nb_get(slice, wide, i, k, cw, cf);
+      const uint32_t j = nb_get(slice, far_idx, wide, i, k, cw, cf);
       const float4 o = __ldg(&xyhm[j]);
       const float dx = xi - o.x, dy = yi - o.y;
       float w, g;
@@ -229,8 +257,9 @@ int launch_neighbors(asph_sim* sim, float f_ext, float f_near) {
     CUDA_TRY(sim->nbpool.ensure(size_t(sim->cap) * per + 8192));
   }
   const uint32_t cap64 = uint32_t(std::min<size_t>(sim->nbpool.cap / 64, 0x7FFFFFF0u));
+  CUDA_TRY(cudaMemsetAsync(sim->far_cnt.p, 0, (size_t(n + ASPH_PAIR_BLOCK - 1) / ASPH_PAIR_BLOCK) * sizeof(uint32_t), sim->stream));
   k_neighbors<<<blocks, kThreads, 0, sim->stream>>>(n, sim->xyhm.p, sim->ctl, sim->ctl, sim->cellstart.p, sim->pp, sim->lut.p, f_ext, f_near,
-                                                    cap64, sim->nbpool.p, sim->slice_base.p, sim->cnt.p, sim->cnt_ext.p, sim->rho.p, sim->gB.p,
+                                                    cap64, sim->nbpool.p, sim->slice_base.p, sim->cnt.p, sim->cnt_ext.p, sim->far_idx.p, sim->far_cnt.p, sim->rho.p, sim->gB.p,
                                                     sim->pconst.p, sim->lam_sum.p, sim->lam_grad.p, sim->nrm.p,
                                                     sim->dist ? sim->refid[sim->cur].p : nullptr);
   LAUNCH_CHECK();

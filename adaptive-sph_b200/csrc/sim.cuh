@@ -30,23 +30,23 @@ enum {
   ERRF_SPLIT_CHILDREN = 512, ERRF_SOLVER_NONFINITE = 1024, ERRF_PARTNER_VALIDATION = 2048
 };
 
-// Cells of a level are numbered STRIP-MAJOR: the grid is cut into vertical strips of ASPH_STRIP columns; inside a strip
-// cells run row by row.  Particles are sorted by cell number, so the particles of the 3 x 3 (or wider) cell block
-// around a cell lie within a few hundred positions of each other in memory (one strip row = ASPH_STRIP cells), apart
-// from the cells across a strip edge.  The pair passes stage that window in shared memory (solver.cu).
-#define ASPH_STRIP_LOG2 4
-#define ASPH_STRIP (1 << ASPH_STRIP_LOG2)
+// Cells of a level are numbered STRIP-MAJOR: the grid is cut into vertical strips of 2^strip_log2 columns; inside a
+// strip cells run row by row.  Particles are sorted by cell number, so the particles of the 3 x 3 cell block around a
+// cell lie within about one strip row of each other in memory, apart from the cells across a strip edge.  The pair
+// passes stage that window in shared memory (solver.cu); k_make_levels picks the strip width so that one strip row
+// (plus the diagonal cell) fits the window halo at rest density.
 struct GridLevel {
   float cell, inv_cell, hmax;
   int nx, ny;
+  int strip_log2;
   uint32_t base;  // first cell of this level in the concatenated cell array
 };
 __host__ __device__ __forceinline__ uint32_t cell_index(const GridLevel& g, int cx, int cy) {
-  const uint32_t st = uint32_t(cx) >> ASPH_STRIP_LOG2;
-  return g.base + ((st * uint32_t(g.ny) + uint32_t(cy)) << ASPH_STRIP_LOG2) + (uint32_t(cx) & (ASPH_STRIP - 1));
+  const uint32_t st = uint32_t(cx) >> g.strip_log2;
+  return g.base + ((st * uint32_t(g.ny) + uint32_t(cy)) << g.strip_log2) + (uint32_t(cx) & ((1u << g.strip_log2) - 1u));
 }
-__host__ __device__ __forceinline__ unsigned long long level_cells(int nx, int ny) {
-  return (unsigned long long)((nx + ASPH_STRIP - 1) >> ASPH_STRIP_LOG2) * (unsigned long long)ny * ASPH_STRIP;
+__host__ __device__ __forceinline__ unsigned long long level_cells(int nx, int ny, int strip_log2) {
+  return (unsigned long long)((nx + (1 << strip_log2) - 1) >> strip_log2) * (unsigned long long)ny << strip_log2;
 }
 
 // Relaxed-Jacobi solver state.  Sweep number s (0, 1, ...) accumulates its PressureSolverStatistics
@@ -140,7 +140,7 @@ struct asph_sim {
   DevBuf<float> h_tmp, rho, lam_sum;
   DevBuf<float2> nrm, gB, lam_grad;
   DevBuf<uint32_t> key, cellcount, cellstart, order, scan_sums;
-  DevBuf<uint32_t> cnt, cnt_ext, slice_base;
+  DevBuf<uint32_t> cnt, cnt_ext, slice_base, far_idx, far_cnt;
   DevBuf<uint16_t> nbpool;  // sliced-ELL neighbour lists (lists.cuh)
   DevBuf<float2> hm;        // {h, m} per particle: second gather of the adaptive-h pair passes
   int predicted_sweeps[2] = {1, 1};  // sweeps of the divergence / density solve in the previous step

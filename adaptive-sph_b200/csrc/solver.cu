@@ -84,8 +84,11 @@ __global__ void k_solver_decide(StepCtl* ctl, int sweep, float rho0, float tol, 
 // stay unused; no column refers to them).
 constexpr int kThreads = int(ASPH_PAIR_BLOCK);
 constexpr uint32_t kHalo = ASPH_PAIR_HALO;
-constexpr uint32_t kWin = ASPH_PAIR_WIN;
-static_assert(kWin * 16u <= 65536u, "window byte offsets are stored in 16 bits");
+constexpr uint32_t kWin = ASPH_PAIR_WIN;      // contiguous part of the window
+constexpr uint32_t kFar = ASPH_PAIR_FAR;      // slots of the tile's far table, staged behind it
+constexpr uint32_t kSlots = ASPH_PAIR_SLOTS;
+static_assert(kSlots * 16u <= 65536u, "window byte offsets are stored in 16 bits");
+static_assert(kFar <= ASPH_PAIR_BLOCK, "one thread stages one far-table slot");
 
 // Per-block context of a pair pass.  Order inside a kernel: issue() the asynchronous window copy, construct the
 // thread's PairCol (slice header, counts, first two index chunks) and load the thread's own values, then wait() —
@@ -96,7 +99,8 @@ struct PairWindow {
   const float* wa;
   template <bool AUX>
   __device__ __forceinline__ void issue(uint32_t n, bool uni, const float4* __restrict__ pack, const float2* __restrict__ hm,
-                                        const float* __restrict__ aux, float4 (&s_pack)[kWin], float2 (&s_hm)[kWin], float* s_aux) {
+                                        const float* __restrict__ aux, float4 (&s_pack)[kSlots], float2 (&s_hm)[kSlots], float* s_aux,
+                                        const NbLists& L) {
     wp = s_pack; wh = s_hm; wa = s_aux;
     const uint32_t sp = uint32_t(__cvta_generic_to_shared(&s_pack[0]));
     const uint32_t sh = uint32_t(__cvta_generic_to_shared(&s_hm[0]));
@@ -109,6 +113,14 @@ struct PairWindow {
         if (!uni) cp_async8(sh + t * 8u, hm + g);
         if (AUX) cp_async4(sa + t * 4u, aux + g);
       }
+    }
+    // the tile's far table (lists.cuh): particles outside the contiguous window, staged behind it
+    if (threadIdx.x < min(__ldg(&L.far_cnt[blockIdx.x]), kFar)) {
+      const uint32_t g = min(__ldg(&L.far_idx[blockIdx.x * kFar + threadIdx.x]), n - 1u);
+      const uint32_t t = kWin + threadIdx.x;
+      cp_async16(sp + t * 16u, pack + g);
+      if (!uni) cp_async8(sh + t * 8u, hm + g);
+      if (AUX) cp_async4(sa + t * 4u, aux + g);
     }
   }
   __device__ __forceinline__ void wait() const {
@@ -176,7 +188,7 @@ __device__ __forceinline__ float for_each_pair(const PairCol& P, const PairWindo
         const uint32_t of = off[half * 4 + u];
         o[u] = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(W.wp) + of);
         if (HM == HM_WIN) t[u] = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(W.wh) + (of >> 1));
-        else if (HM == HM_GLOBAL) t[u] = __ldg(hm + (nb_win0(col.i) + (of >> 4)));
+        else if (HM == HM_GLOBAL) t[u] = __ldg(hm + ((of >> 4) < kWin ? nb_win0(col.i) + (of >> 4) : __ldg(col.far_idx + (col.i / kThreads) * kFar + ((of >> 4) - kWin))));
         else t[u] = make_float2(0.f, 0.f);
         a[u] = AUX ? *reinterpret_cast<const float*>(reinterpret_cast<const char*>(W.wa) + (of >> 2)) : 0.f;
       }
@@ -237,12 +249,12 @@ __device__ __forceinline__ void viscosity_body(uint32_t i, const PairCol& C, con
 __global__ void __launch_bounds__(kThreads)
 k_viscosity(uint32_t n, NbLists L, const float4* __restrict__ xv_in, const float2* __restrict__ hm, const float* __restrict__ rho,
             const PackedParams P, const StepCtl* __restrict__ ctl, float4* __restrict__ xv_out) {
-  __shared__ float4 s_pack[kWin];
-  __shared__ float2 s_hm[kWin];
-  __shared__ float s_aux[kWin];
+  __shared__ float4 s_pack[kSlots];
+  __shared__ float2 s_hm[kSlots];
+  __shared__ float s_aux[kSlots];
   const bool uni = ctl->hmin == ctl->hmax;
   PairWindow W;
-  W.issue<true>(n, uni, xv_in, hm, rho, s_pack, s_hm, s_aux);
+  W.issue<true>(n, uni, xv_in, hm, rho, s_pack, s_hm, s_aux, L);
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = i < n;
   const PairCol C(L, i, active);
@@ -263,12 +275,12 @@ __global__ void __launch_bounds__(kThreads)
 k_source(uint32_t n, NbLists L, const float4* __restrict__ xv, const float2* __restrict__ hm, const float* __restrict__ rho,
          float4* __restrict__ pconst, float4* __restrict__ packP0, float4* __restrict__ packA, const StepCtl* __restrict__ ctl,
          float rho0, int kind) {
-  __shared__ float4 s_pack[kWin];
-  __shared__ float2 s_hm[kWin];
+  __shared__ float4 s_pack[kSlots];
+  __shared__ float2 s_hm[kSlots];
   const bool uni = ctl->hmin == ctl->hmax;
   const bool pairs = kind != 1;
   PairWindow W;
-  if (pairs) W.issue<false>(n, uni, xv, hm, nullptr, s_pack, s_hm, nullptr);
+  if (pairs) W.issue<false>(n, uni, xv, hm, nullptr, s_pack, s_hm, nullptr, L);
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = i < n;
   const PairCol C(L, i, active && pairs);
@@ -308,8 +320,8 @@ k_accel(uint32_t n, NbLists L, const float4* __restrict__ P0, const float4* __re
         const float2* __restrict__ gB, float4* __restrict__ packA, StepCtl* ctl, float4* __restrict__ xv, float2* __restrict__ pos,
         float2* __restrict__ vel, float hybrid_factor, const uint32_t* __restrict__ gid, int sweep, float rho0, float tol, int max_iters,
         int density_mode) {
-  __shared__ float4 s_pack[kWin];
-  __shared__ float2 s_hm[kWin];
+  __shared__ float4 s_pack[kSlots];
+  __shared__ float2 s_hm[kSlots];
   __shared__ int s_stop;
   if (MODE == 0 && ctl->solver.done) return;
   const int parity = MODE == 0 ? (sweep & 1) : (ctl->solver.sweeps & 1);  // final passes run after k_solver_decide
@@ -319,7 +331,7 @@ k_accel(uint32_t n, NbLists L, const float4* __restrict__ P0, const float4* __re
   const bool pairs = MODE == 0 || ctl->solver.normal != 0;
   const bool uni = ctl->hmin == ctl->hmax;
   PairWindow W;
-  if (pairs) W.issue<false>(n, uni, packP, hm, nullptr, s_pack, s_hm, nullptr);
+  if (pairs) W.issue<false>(n, uni, packP, hm, nullptr, s_pack, s_hm, nullptr, L);
   if (MODE == 0 && threadIdx.x == 0) {
     // prologue of sweep number `sweep` >= 1: the stop rule for sweep - 1 from its totals, once per block, while the
     // window copy is in flight; block 0 also records it for the host
@@ -385,11 +397,11 @@ k_jacobi(uint32_t n, NbLists L, const float4* __restrict__ packA, float4* __rest
          const float2* __restrict__ hm, const float4* __restrict__ pconst, const float* __restrict__ rho, StepCtl* ctl,
          float omega, int density_mode, const uint32_t* __restrict__ gid, int sweep) {
   if (ctl->solver.done) return;
-  __shared__ float4 s_pack[kWin];
-  __shared__ float2 s_hm[kWin];
+  __shared__ float4 s_pack[kSlots];
+  __shared__ float2 s_hm[kSlots];
   const bool uni = ctl->hmin == ctl->hmax;
   PairWindow W;
-  W.issue<false>(n, uni, packA, hm, nullptr, s_pack, s_hm, nullptr);
+  W.issue<false>(n, uni, packA, hm, nullptr, s_pack, s_hm, nullptr, L);
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const float dt = ctl->dt;
   const bool odd = (sweep & 1) != 0;
@@ -472,12 +484,12 @@ k_jacobi(uint32_t n, NbLists L, const float4* __restrict__ packA, float4* __rest
 // has seen; if that guess was "uniform" and the step turns out not to be, {h, m} are gathered from global memory.
 template <bool HMWIN>
 struct SweepStage {
-  float4 win[kWin];
+  float4 win[kSlots];
   uint4 chunk[2][kThreads];
   float4 own4[kThreads];
   float2 own2[kThreads];
   float own1[2][kThreads];
-  float2 hmw[HMWIN ? kWin : 1];
+  float2 hmw[HMWIN ? kSlots : 1];
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -519,13 +531,21 @@ k_sweep(const SweepArgs A) {
   const float dt = ctl->dt;
 
   // column header of a tile, kept in registers two tiles ahead
-  auto load_hdr = [&](uint32_t t, uint32_t& c, uint32_t& sb) {
+  // (the far-table slot this thread stages travels the same way: fj = particle index, or ~0 for none)
+  auto load_hdr = [&](uint32_t t, uint32_t& c, uint32_t& sb, uint32_t& fj) {
     const uint32_t i = t * kThreads + tid;
-    c = 0u; sb = 0u;
-    if (t < ntiles && i < n) { c = __ldg(&A.L.cnt[i]); sb = __ldg(&A.L.slice_base[i >> 5]); }
+    c = 0u; sb = 0u; fj = 0xffffffffu;
+    if (t < ntiles) {
+      if (i < n) { c = __ldg(&A.L.cnt[i]); sb = __ldg(&A.L.slice_base[i >> 5]); }
+      if (tid < min(__ldg(&A.L.far_cnt[t]), kFar)) fj = min(__ldg(&A.L.far_idx[t * kFar + tid]), n - 1u);
+    }
   };
   // all asynchronous copies of a tile into a stage
-  auto issue = [&](uint32_t t, Stage& S, uint32_t c, uint32_t sb) {
+  auto issue = [&](uint32_t t, Stage& S, uint32_t c, uint32_t sb, uint32_t fj) {
+    if (fj != 0xffffffffu) {
+      cp_async16(smem_addr(&S.win[kWin + tid]), pack + fj);
+      if (HMWIN && !uni) cp_async8(smem_addr(&S.hmw[kWin + tid]), A.hm + fj);
+    }
     const uint32_t w0 = t * kThreads - kHalo;
     for (uint32_t slot = tid; slot < kWin; slot += kThreads) {
       const uint32_t g = w0 + slot;
@@ -553,9 +573,9 @@ k_sweep(const SweepArgs A) {
 
   uint32_t tile = blockIdx.x;
   if (tile >= ntiles) return;
-  uint32_t c_cur, sb_cur, c_nxt, sb_nxt;
-  load_hdr(tile, c_cur, sb_cur);
-  load_hdr(tile + G, c_nxt, sb_nxt);
+  uint32_t c_cur, sb_cur, fj_cur, c_nxt, sb_nxt, fj_nxt;
+  load_hdr(tile, c_cur, sb_cur, fj_cur);
+  load_hdr(tile + G, c_nxt, sb_nxt, fj_nxt);
   if (PASS == 0) {
     if (tid == 0) {
       // prologue of sweep number `sweep` >= 1: the stop rule for sweep - 1 from its totals, once per block, while the
@@ -568,8 +588,7 @@ k_sweep(const SweepArgs A) {
     __syncthreads();
     if (s_stop) return;  // the solve ended with the previous sweep
   }
-  issue(tile, stages[0], c_cur, sb_cur);
-  cp_async_commit();
+  issue(tile, stages[0], c_cur, sb_cur, fj_cur);
 
   uint32_t c_normal = 0, c_sing = 0, c_neg = 0;
   float e_sum = 0.f, e_max = 0.f;
@@ -577,18 +596,19 @@ k_sweep(const SweepArgs A) {
   int s = 0;
   for (; tile < ntiles; tile += G, s ^= 1) {
     Stage& S = stages[s];
-    if (tile + G < ntiles) issue(tile + G, stages[s ^ 1], c_nxt, sb_nxt);
-    cp_async_commit();
-    uint32_t c_nn, sb_nn;
-    load_hdr(tile + 2u * G, c_nn, sb_nn);
-    cp_async_wait_1();
+    // tile t's copies (issued one iteration ago) have landed for every thread; the same barrier also says that every
+    // thread is done computing tile t - 1, so its stage can be refilled at once with tile t + 1
+    cp_async_wait_all();
     __syncthreads();
+    if (tile + G < ntiles) issue(tile + G, stages[s ^ 1], c_nxt, sb_nxt, fj_nxt);
+    uint32_t c_nn, sb_nn, fj_nn;
+    load_hdr(tile + 2u * G, c_nn, sb_nn, fj_nn);
 
     const uint32_t i = tile * kThreads + tid;
     const bool active = i < n && !(PASS == 1 && A.gid && (A.gid[i] & ASPH_GHOST_BIT));
     if (active) {
       NbCol col;
-      col.i = i; col.cw = nb_cw(c_cur); col.cf = nb_cf(c_cur); col.cn = col.cw + col.cf;
+      col.far_idx = A.L.far_idx; col.i = i; col.cw = nb_cw(c_cur); col.cf = nb_cf(c_cur); col.cn = col.cw + col.cf;
       col.wide = (sb_cur >> 31) != 0u;
       col.slice = A.L.pool + size_t(sb_cur & 0x7fffffffu) * 64u;
       const float4 me = S.win[kHalo + tid];
@@ -632,8 +652,7 @@ k_sweep(const SweepArgs A) {
         packP_next[i] = make_float4(me.x, me.y, pn / (rho_i * rho_i), pn);
       }
     }
-    __syncthreads();  // every thread is done with stage s before the next iteration refills it
-    c_cur = c_nxt; sb_cur = sb_nxt; c_nxt = c_nn; sb_nxt = sb_nn;
+    c_cur = c_nxt; sb_cur = sb_nxt; c_nxt = c_nn; sb_nxt = sb_nn; fj_nxt = fj_nn;
   }
 
   if (PASS == 1) {
@@ -681,7 +700,7 @@ inline uint32_t sweep_grid(uint32_t n, int sm_count, int blocks_per_sm) {
 
 NbLists lists_of(asph_sim* sim) {
   NbLists L;
-  L.pool = sim->nbpool.p; L.slice_base = sim->slice_base.p; L.cnt = sim->cnt.p; L.cnt_ext = sim->cnt_ext.p;
+  L.pool = sim->nbpool.p; L.slice_base = sim->slice_base.p; L.cnt = sim->cnt.p; L.cnt_ext = sim->cnt_ext.p; L.far_idx = sim->far_idx.p; L.far_cnt = sim->far_cnt.p;
   return L;
 }
 
@@ -731,7 +750,8 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
   // host has seen says h is uniform (a wrong guess only costs speed, see k_sweep)
   const bool hmwin = !(sim->ctl_seen && sim->ctl_host->hmin == sim->ctl_host->hmax);
   const size_t smem = 2 * (hmwin ? sizeof(SweepStage<true>) : sizeof(SweepStage<false>));
-  const uint32_t grid = sweep_grid(n, sim->sm_count, hmwin ? 3 : 4);
+  uint32_t grid = sweep_grid(n, sim->sm_count, hmwin ? 3 : 4);
+  if (const char* e = getenv("ASPH_SWEEP_GRID")) grid = std::max(1u, std::min(grid, uint32_t(atoi(e))));  // test hook: few blocks => many tiles per block
   static bool attr_done = false;
   if (!attr_done) {
     CUDA_TRY(cudaFuncSetAttribute(k_sweep<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * sizeof(SweepStage<true>))));

@@ -84,14 +84,13 @@ def _compare_step_fields(g, o, tol, fields):
     return worst
 
 
-@pytest.mark.parametrize("solver", ["HybridDFSPH", "IISPH", "OnlyDivergence"])
-def test_single_step_uniform(asph, cuda_lib, oracle32, default_params, solver):
+def _single_step_uniform(asph, cuda_lib, oracle32, default_params, solver, spacing=0.02, vel_scale=0.05):
     """One physics step, uniform h, level estimation off (the reference's 'Uniform SPH' recipe,
     media/motivation-video.yaml:42-57): every per-particle quantity against the oracle."""
-    sc = asph.SceneConfig.dam_break(0.02)
+    sc = asph.SceneConfig.dam_break(spacing)
     pos, vel, mass = asph.scene_particles(sc)
     rng = np.random.default_rng(1)
-    vel = (rng.standard_normal(vel.shape) * 0.05).astype(np.float32)
+    vel = (rng.standard_normal(vel.shape) * vel_scale).astype(np.float32)
     params = _uniform_params(default_params, pressure_solver_method=solver)
     b = asph.scene_boundary(sc, "AnalyticOverestimate")
     g, o = _pair(asph, cuda_lib, oracle32, params, pos, vel, mass, b)
@@ -112,6 +111,26 @@ def test_single_step_uniform(asph, cuda_lib, oracle32, default_params, solver):
     vs = max(float(np.abs(o.get_field("velocity")).max()), 1e-3)
     assert _rel(g.get_field("velocity"), o.get_field("velocity"), vs) <= 1e-4, w
     g.close(); o.close()
+
+
+
+@pytest.mark.parametrize("solver", ["HybridDFSPH", "IISPH", "OnlyDivergence"])
+def test_single_step_uniform(asph, cuda_lib, oracle32, default_params, solver):
+    _single_step_uniform(asph, cuda_lib, oracle32, default_params, solver)
+
+
+@pytest.mark.parametrize("solver", ["HybridDFSPH", "IISPH"])
+def test_single_step_uniform_many_tiles_per_block(asph, cuda_lib, oracle32, default_params, solver, monkeypatch):
+    """The same step with the persistent sweep kernels limited to two blocks (ASPH_SWEEP_GRID, a test hook of
+    solver.cu), so that each block walks ~50 tiles through its two-stage copy pipeline."""
+    monkeypatch.setenv("ASPH_SWEEP_GRID", "2")
+    _single_step_uniform(asph, cuda_lib, oracle32, default_params, solver, spacing=0.01)
+
+
+def test_full_size_step_against_oracle(asph, cuda_lib, oracle32, default_params):
+    """BASELINE config[1] at full size (999 292 particles): one HybridDFSPH step with seeded random velocities (both
+    solves iterate) against the CPU oracle — the far tables, 32-column strips and multi-tile pipelines at scale."""
+    _single_step_uniform(asph, cuda_lib, oracle32, default_params, "HybridDFSPH", spacing=1.122e-3, vel_scale=0.02)
 
 
 def test_level_estimation_default_config(asph, cuda_lib, oracle32, default_params):
