@@ -171,12 +171,8 @@ __device__ __forceinline__ float for_each_pair(const PairCol& P, const PairWindo
   const NbCol& col = P.col;
   const float inv2h = fast_rcp(2.f * hi);
   const PairShape shape(inv2h);
-  // ---- window segment
-  uint4 cur = P.c0, nxt = P.c1;
-  for (uint32_t k0 = 0; k0 < col.cw; k0 += 8u) {
-    const uint4 v = cur;
-    cur = nxt;
-    if (k0 + 16u < col.cw) nxt = col.raw8(k0 + 16u);
+  // ---- window segment: the two prefetched chunks, then (long columns only) chunks fetched on demand
+  auto chunk = [&](const uint4& v) {
     const uint32_t off[8] = {v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16, v.z & 0xffffu, v.z >> 16, v.w & 0xffffu, v.w >> 16};
 #pragma unroll
     for (int half = 0; half < 2; half++) {
@@ -194,6 +190,16 @@ __device__ __forceinline__ float for_each_pair(const PairCol& P, const PairWindo
       }
 #pragma unroll
       for (int u = 0; u < 4; u++) pair_apply<HM, AUX>(o[u], t[u], a[u], xi, yi, hi, shape, f);
+    }
+  };
+  if (col.cw > 0u) chunk(P.c0);
+  if (col.cw > 8u) chunk(P.c1);
+  if (col.cw > 16u) {
+    uint4 nxt = col.raw8(16u);
+    for (uint32_t k0 = 16u; k0 < col.cw; k0 += 8u) {
+      const uint4 v = nxt;
+      if (k0 + 8u < col.cw) nxt = col.raw8(k0 + 8u);
+      chunk(v);
     }
   }
   // ---- far segment (divergent: most threads have none)
@@ -310,36 +316,25 @@ k_source(uint32_t n, NbLists L, const float4* __restrict__ xv, const float2* __r
 
 // ---------------------------------------------------------------------------------------------- K14
 // a^p_i = -Σ m_j (P_i + P_j) gradW_ij - p_i * Bc * G_i,  P = p / rho^2.
-// MODE 0: sweep (skipped once the solver is done); 1: final, v += dt a^p into the xv pack; 2: final + HybridDFSPH
-// integration (simulation.rs:2622-2669); 3: final + IISPH integration (simulation.rs:2433-2444); 4: final only.
+// The pass after a solve (the passes inside the sweeps are k_sweep<0> below).  MODE 1: v += dt a^p into the xv pack;
+// 2: + HybridDFSPH integration (simulation.rs:2622-2669); 3: + IISPH integration (simulation.rs:2433-2444); 4: a^p only.
 // P0 / P1: the two pressure packs; the current one is chosen by the parity of the sweeps executed so far, read from
 // the control block, so the launch sequence does not depend on when the solver stops.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 k_accel(uint32_t n, NbLists L, const float4* __restrict__ P0, const float4* __restrict__ P1, const float2* __restrict__ hm,
         const float2* __restrict__ gB, float4* __restrict__ packA, StepCtl* ctl, float4* __restrict__ xv, float2* __restrict__ pos,
-        float2* __restrict__ vel, float hybrid_factor, const uint32_t* __restrict__ gid, int sweep, float rho0, float tol, int max_iters,
-        int density_mode) {
+        float2* __restrict__ vel, float hybrid_factor, const uint32_t* __restrict__ gid) {
   __shared__ float4 s_pack[kSlots];
   __shared__ float2 s_hm[kSlots];
-  __shared__ int s_stop;
-  if (MODE == 0 && ctl->solver.done) return;
-  const int parity = MODE == 0 ? (sweep & 1) : (ctl->solver.sweeps & 1);  // final passes run after k_solver_decide
+  const int parity = ctl->solver.sweeps & 1;  // runs after k_solver_decide
   const float4* __restrict__ packP = parity ? P1 : P0;
   // After a sweep that left no particle with positive pressure (normal == 0: every p' was clamped to 0 or was
   // singular) the whole pressure field is zero and so is a^p; skip the pair sum.
-  const bool pairs = MODE == 0 || ctl->solver.normal != 0;
+  const bool pairs = ctl->solver.normal != 0;
   const bool uni = ctl->hmin == ctl->hmax;
   PairWindow W;
   if (pairs) W.issue<false>(n, uni, packP, hm, nullptr, s_pack, s_hm, nullptr, L);
-  if (MODE == 0 && threadIdx.x == 0) {
-    // prologue of sweep number `sweep` >= 1: the stop rule for sweep - 1 from its totals, once per block, while the
-    // window copy is in flight; block 0 also records it for the host
-    const SweepTotals t = read_totals(ctl, sweep - 1);
-    const bool stop = sweep_stops(t, sweep - 1, ctl->error_flags, ctl->dt, rho0, tol, max_iters, density_mode);
-    if (blockIdx.x == 0) record_sweep(ctl, t, sweep - 1, stop);
-    s_stop = stop ? 1 : 0;
-  }
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = i < n;
   const PairCol C(L, i, active && pairs);
@@ -347,7 +342,6 @@ k_accel(uint32_t n, NbLists L, const float4* __restrict__ P0, const float4* __re
   float2 own = make_float2(1.f, 0.f), g = make_float2(0.f, 0.f);
   if (active) { me = packP[i]; own = hm[i]; g = gB[i]; }
   if (pairs) W.wait();
-  if (MODE == 0 && s_stop) return;  // the solve ended with the previous sweep
   if (!active) return;
   float ax = 0.f, ay = 0.f;
   if (pairs) {
@@ -385,89 +379,6 @@ k_accel(uint32_t n, NbLists L, const float4* __restrict__ P0, const float4* __re
     pos[i] = x; vel[i] = vn;
     if (!(isfinite(x.x) && isfinite(x.y) && isfinite(vn.x) && isfinite(vn.y)) && !(gid && (gid[i] & ASPH_GHOST_BIT)))
       atomicOr(&ctl->error_flags, ERRF_NONFINITE);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------- K15
-// Sweep number `sweep`: (Ap)_i = div(a^p)_i; p' = p + ω (s - Ap) / a_ii, clamped at 0; PressureSolverStatistics of the
-// block added to slot sweep % 3 with integer atomics.  gid != nullptr: multi-GPU, ghost particles are skipped (their
-// p' arrives from the owner rank).
-__global__ void __launch_bounds__(kThreads)
-k_jacobi(uint32_t n, NbLists L, const float4* __restrict__ packA, float4* __restrict__ P0, float4* __restrict__ P1,
-         const float2* __restrict__ hm, const float4* __restrict__ pconst, const float* __restrict__ rho, StepCtl* ctl,
-         float omega, int density_mode, const uint32_t* __restrict__ gid, int sweep) {
-  if (ctl->solver.done) return;
-  __shared__ float4 s_pack[kSlots];
-  __shared__ float2 s_hm[kSlots];
-  const bool uni = ctl->hmin == ctl->hmax;
-  PairWindow W;
-  W.issue<false>(n, uni, packA, hm, nullptr, s_pack, s_hm, nullptr, L);
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const float dt = ctl->dt;
-  const bool odd = (sweep & 1) != 0;
-  const float4* __restrict__ packP = odd ? P1 : P0;
-  float4* __restrict__ packP_next = odd ? P0 : P1;
-  const bool active = i < n && !(gid && (gid[i] & ASPH_GHOST_BIT));
-  float4 me = make_float4(0.f, 0.f, 0.f, 0.f), pc = make_float4(0.f, 0.f, 1.f, 0.f);
-  float2 own = make_float2(1.f, 0.f);
-  float p_old = 0.f, rho_i = 1.f;
-  if (active) { me = packA[i]; pc = pconst[i]; p_old = packP[i].w; rho_i = rho[i]; own = hm[i]; }
-  const bool singular = fabsf(pc.z) < 10e-4f;
-  const PairCol C(L, i, active && !singular);
-  W.wait();
-  uint32_t c_normal = 0, c_sing = 0, c_neg = 0;
-  float e_sum = 0.f, e_max = 0.f;
-  bool bad = false;
-  if (active) {
-    float pn = 0.f;
-    if (singular) {
-      c_sing = 1;
-    } else {
-      float sum = 0.f;
-      auto body = [&](const float4& o, float dx, float dy, float c, float, float) { sum += c * ((o.z - me.z) * dx + (o.w - me.w) * dy); };
-      const float scale = uni ? for_each_pair<HM_UNI, false>(C, W, packA, hm, nullptr, me.x, me.y, own.x, own.y, body)
-                              : for_each_pair<HM_WIN, false>(C, W, packA, hm, nullptr, me.x, me.y, own.x, own.y, body);
-      sum *= scale;
-      const float Ap = sum / rho_i - (me.z * pc.x + me.w * pc.y);
-      const float resid = pc.w - Ap;
-      pn = p_old + omega * resid / pc.z;
-      if (!isfinite(Ap) || !isfinite(pn)) bad = true;
-      const float perr = density_mode ? rho_i * dt * dt * resid : dt * resid;
-      if (pn <= 0.f) { pn = 0.f; c_neg = 1; }
-      else { c_normal = 1; e_sum = perr; e_max = fabsf(perr); }
-    }
-    packP_next[i] = make_float4(me.x, me.y, pn / (rho_i * rho_i), pn);
-  }
-  if (bad) atomicOr(&ctl->error_flags, ERRF_SOLVER_NONFINITE);
-  // warp totals: counts by redux, the error sum by a fixed-order shuffle tree; then integers only
-  c_normal = __reduce_add_sync(0xffffffffu, c_normal);
-  c_neg = __reduce_add_sync(0xffffffffu, c_neg);
-  c_sing = __reduce_add_sync(0xffffffffu, c_sing);
-  const unsigned int m_enc = __reduce_max_sync(0xffffffffu, __float_as_uint(e_max));  // non-negative floats order like their bits
-  for (int o = 16; o > 0; o >>= 1) e_sum += __shfl_xor_sync(0xffffffffu, e_sum, o);
-  __shared__ unsigned long long sh_cnt[kThreads / 32];
-  __shared__ long long sh_err[kThreads / 32];
-  __shared__ unsigned int sh_sing[kThreads / 32], sh_max[kThreads / 32];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) {
-    sh_cnt[w] = (unsigned long long)c_normal | ((unsigned long long)c_neg << 32);
-    sh_err[w] = __float2ll_rn(fminf(fmaxf(e_sum, -4096.f), 4096.f) * 4294967296.f);  // 2^-32 fixed point
-    sh_sing[w] = c_sing; sh_max[w] = m_enc;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long cnt = 0;
-    long long err = 0;
-    unsigned int sing = 0, mx = 0;
-#pragma unroll
-    for (int k = 0; k < kThreads / 32; k++) { cnt += sh_cnt[k]; err += sh_err[k]; sing += sh_sing[k]; mx = max(mx, sh_max[k]); }
-    SolverCtl& s = ctl->solver;
-    unsigned long long* acc = s.acc[sweep % 3] + 2 * (blockIdx.x % ASPH_ACC_COPIES);
-    if (cnt) atomicAdd(acc, cnt);
-    if (err) atomicAdd(acc + 1, (unsigned long long)err);
-    if (sing) atomicAdd(s.acc[sweep % 3] + 2 * ASPH_ACC_COPIES, (unsigned long long)sing);
-    // e_max >= 0: its bit pattern with the sign bit set is the order-preserving encoding dec_f expects
-    if (mx) atomicMax(&s.maxerr_enc[sweep % 3], mx | 0x80000000u);
   }
 }
 
@@ -529,20 +440,24 @@ k_sweep(const SweepArgs A) {
   const float4* __restrict__ pack = PASS == 0 ? packP : A.packA;  // what the pass gathers
   const bool uni = ctl->hmin == ctl->hmax;
   const float dt = ctl->dt;
+  const float err_scale = A.density_mode ? dt * dt : dt;  // predicted density / divergence error per unit of residual
 
   // column header of a tile, kept in registers two tiles ahead
-  // (the far-table slot this thread stages travels the same way: fj = particle index, or ~0 for none)
-  auto load_hdr = [&](uint32_t t, uint32_t& c, uint32_t& sb, uint32_t& fj) {
+  // (the far-table slot this thread stages travels the same way: fj = particle index, fc = slots in use).  Only
+  // independent loads here: a warp issues in order, so nothing in this lambda may consume what it has just requested.
+  auto load_hdr = [&](uint32_t t, uint32_t& c, uint32_t& sb, uint32_t& fj, uint32_t& fc) {
     const uint32_t i = t * kThreads + tid;
-    c = 0u; sb = 0u; fj = 0xffffffffu;
+    c = 0u; sb = 0u; fj = 0u; fc = 0u;
     if (t < ntiles) {
       if (i < n) { c = __ldg(&A.L.cnt[i]); sb = __ldg(&A.L.slice_base[i >> 5]); }
-      if (tid < min(__ldg(&A.L.far_cnt[t]), kFar)) fj = min(__ldg(&A.L.far_idx[t * kFar + tid]), n - 1u);
+      fc = __ldg(&A.L.far_cnt[t]);
+      if (tid < kFar) fj = __ldg(&A.L.far_idx[t * kFar + tid]);
     }
   };
   // all asynchronous copies of a tile into a stage
-  auto issue = [&](uint32_t t, Stage& S, uint32_t c, uint32_t sb, uint32_t fj) {
-    if (fj != 0xffffffffu) {
+  auto issue = [&](uint32_t t, Stage& S, uint32_t c, uint32_t sb, uint32_t fj, uint32_t fc) {
+    if (tid < min(fc, kFar)) {
+      fj = min(fj, n - 1u);  // a slot whose owner gave up on the table (neighbors.cu) may hold anything
       cp_async16(smem_addr(&S.win[kWin + tid]), pack + fj);
       if (HMWIN && !uni) cp_async8(smem_addr(&S.hmw[kWin + tid]), A.hm + fj);
     }
@@ -573,9 +488,9 @@ k_sweep(const SweepArgs A) {
 
   uint32_t tile = blockIdx.x;
   if (tile >= ntiles) return;
-  uint32_t c_cur, sb_cur, fj_cur, c_nxt, sb_nxt, fj_nxt;
-  load_hdr(tile, c_cur, sb_cur, fj_cur);
-  load_hdr(tile + G, c_nxt, sb_nxt, fj_nxt);
+  uint32_t c_cur, sb_cur, fj_cur, fc_cur, c_nxt, sb_nxt, fj_nxt, fc_nxt;
+  load_hdr(tile, c_cur, sb_cur, fj_cur, fc_cur);
+  load_hdr(tile + G, c_nxt, sb_nxt, fj_nxt, fc_nxt);
   if (PASS == 0) {
     if (tid == 0) {
       // prologue of sweep number `sweep` >= 1: the stop rule for sweep - 1 from its totals, once per block, while the
@@ -588,7 +503,7 @@ k_sweep(const SweepArgs A) {
     __syncthreads();
     if (s_stop) return;  // the solve ended with the previous sweep
   }
-  issue(tile, stages[0], c_cur, sb_cur, fj_cur);
+  issue(tile, stages[0], c_cur, sb_cur, fj_cur, fc_cur);
 
   uint32_t c_normal = 0, c_sing = 0, c_neg = 0;
   float e_sum = 0.f, e_max = 0.f;
@@ -600,9 +515,9 @@ k_sweep(const SweepArgs A) {
     // thread is done computing tile t - 1, so its stage can be refilled at once with tile t + 1
     cp_async_wait_all();
     __syncthreads();
-    if (tile + G < ntiles) issue(tile + G, stages[s ^ 1], c_nxt, sb_nxt, fj_nxt);
-    uint32_t c_nn, sb_nn, fj_nn;
-    load_hdr(tile + 2u * G, c_nn, sb_nn, fj_nn);
+    if (tile + G < ntiles) issue(tile + G, stages[s ^ 1], c_nxt, sb_nxt, fj_nxt, fc_nxt);
+    uint32_t c_nn, sb_nn, fj_nn, fc_nn;
+    load_hdr(tile + 2u * G, c_nn, sb_nn, fj_nn, fc_nn);
 
     const uint32_t i = tile * kThreads + tid;
     const bool active = i < n && !(PASS == 1 && A.gid && (A.gid[i] & ASPH_GHOST_BIT));
@@ -631,7 +546,7 @@ k_sweep(const SweepArgs A) {
       } else {
         const float4 pc = S.own4[tid];
         const float rho_i = S.own1[0][tid], p_old = S.own1[1][tid];
-        float pn = 0.f;
+        float pn = 0.f, inv_rho = 0.f;
         if (fabsf(pc.z) < 10e-4f) {
           c_sing++;
         } else {
@@ -640,19 +555,21 @@ k_sweep(const SweepArgs A) {
           auto body = [&](const float4& o, float dx, float dy, float c, float, float) { sum += c * ((o.z - me.z) * dx + (o.w - me.w) * dy); };
           const float scale = uni ? for_each_pair<HM_UNI, false>(C, W, pack, A.hm, nullptr, me.x, me.y, own.x, own.y, body)
                                   : for_each_pair<HMWIN ? HM_WIN : HM_GLOBAL, false>(C, W, pack, A.hm, nullptr, me.x, me.y, own.x, own.y, body);
-          sum *= scale;
-          const float Ap = sum / rho_i - (me.z * pc.x + me.w * pc.y);
+          // reciprocals by the SFU (1 ulp): the relaxed update does not need correctly rounded quotients, and three
+          // IEEE divisions would be a quarter of this thread's instructions outside the pair loop
+          inv_rho = fast_rcp(rho_i);
+          const float Ap = (sum * scale) * inv_rho - (me.z * pc.x + me.w * pc.y);
           const float resid = pc.w - Ap;
-          pn = p_old + A.omega * resid / pc.z;
-          if (!isfinite(Ap) || !isfinite(pn)) bad = true;
-          const float perr = A.density_mode ? rho_i * dt * dt * resid : dt * resid;
+          pn = fmaf(A.omega * resid, fast_rcp(pc.z), p_old);
+          if (!isfinite(pn)) bad = true;  // covers a non-finite Ap as well
+          const float perr = err_scale * (A.density_mode ? rho_i * resid : resid);
           if (pn <= 0.f) { pn = 0.f; c_neg++; }
           else { c_normal++; e_sum += perr; e_max = fmaxf(e_max, fabsf(perr)); }
         }
-        packP_next[i] = make_float4(me.x, me.y, pn / (rho_i * rho_i), pn);
+        packP_next[i] = make_float4(me.x, me.y, pn * (inv_rho * inv_rho), pn);
       }
     }
-    c_cur = c_nxt; sb_cur = sb_nxt; c_nxt = c_nn; sb_nxt = sb_nn; fj_nxt = fj_nn;
+    c_cur = c_nxt; sb_cur = sb_nxt; c_nxt = c_nn; sb_nxt = sb_nn; fj_nxt = fj_nn; fc_nxt = fc_nn;
   }
 
   if (PASS == 1) {
@@ -838,10 +755,10 @@ int launch_final_accel(asph_sim* sim, int mode) {
   float2* vel = sim->vel[sim->cur].p;
   const uint32_t* gid = sim->dist ? sim->refid[sim->cur].p : nullptr;
   switch (mode) {
-    case 1: k_accel<1><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f, gid, 0, 0.f, 0.f, 0, 0); break;
-    case 2: k_accel<2><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, sim->pp.hybrid_factor, gid, 0, 0.f, 0.f, 0, 0); break;
-    case 3: k_accel<3><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f, gid, 0, 0.f, 0.f, 0, 0); break;
-    default: k_accel<4><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f, gid, 0, 0.f, 0.f, 0, 0); break;
+    case 1: k_accel<1><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f, gid); break;
+    case 2: k_accel<2><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, sim->pp.hybrid_factor, gid); break;
+    case 3: k_accel<3><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f, gid); break;
+    default: k_accel<4><<<blocks, kThreads, 0, st>>>(n, L, P0, P1, sim->hm.p, sim->gB.p, sim->packA.p, sim->ctl, xv, pos, vel, 0.f, gid); break;
   }
   LAUNCH_CHECK();
   if (sim->dist && mode == 1) TRY(dist_halo(sim, xv, 16));  // the density solve's source term reads the neighbours' new velocities

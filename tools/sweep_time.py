@@ -15,9 +15,12 @@ sim = A.FluidSimulation(params, pos, vel, mass, A.scene_boundary(scene, "Analyti
 sim.single_step()
 sim.set_kernel_timing(1)
 for k in range(steps):
-    sim.single_step()
+    try:
+        sim.single_step()
+    except Exception as e:
+        print("step failed:", str(e)[:60]); break
 kt = sim.kernel_timing()
 i = sim.step_info()
 out = {k: (v[0] / v[1] * 1e3 if v[1] else None) for k, v in kt.items()}
-print(os.environ.get("ASPH_DEBUG_SWEEP", "0"), "n", len(mass), "sweeps", i["div_sweeps"], i["density_sweeps"],
+print("steps", steps, "n", len(mass), "sweeps", i["div_sweeps"], i["density_sweeps"],
       " ".join(f"{k}={v:.1f}us" for k, v in out.items() if v is not None))
