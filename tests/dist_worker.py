@@ -60,7 +60,9 @@ def main():
             row = {"step": k, "dt": dt, "dt1": dt1, "div": info["div_sweeps"], "div1": i1["div_sweeps"],
                    "den": info["density_sweeps"], "den1": i1["density_sweeps"]}
             report["rows"].append(row)
-            if dt != dt1:
+            # dt is an exact min over the particles, but of velocities that differ in their last bits between the two
+            # runs (different grid origins => different summation orders): equal to an ulp, not bit for bit
+            if abs(dt - dt1) > 2e-6 * dt1:
                 ok = False
     owned = d.num_fluid_particles()
     fields = {}
