@@ -178,6 +178,7 @@ void kt_release(asph_sim* sim, cudaEvent_t e) { sim->kt_pool.push_back(e); }
 int check_error_flags(asph_sim* sim) {
   const unsigned int f = sim->ctl_host->error_flags;
   if (!f) return ASPH_OK;
+  if (f & ERRF_PEER_TIMEOUT) { sim->last_error = "timed out waiting for a neighbour GPU's data (a rank of the job has failed or stopped stepping)"; return ASPH_ERR_NCCL; }
   if (f & ERRF_CELL_BUDGET) { sim->last_error = "cell grid does not fit the cell budget: particle positions are spread over an absurd extent (the simulation has exploded?)"; return ASPH_ERR_CAPACITY; }
   if (f & ERRF_NEIGHBOR_OVERFLOW) { sim->last_error = "exceeded maximum allowed number of 20000 neighbors"; return ASPH_ERR_NEIGHBOR_OVERFLOW; }
   if (f & ERRF_NONFINITE) { sim->last_error = "assert!(is_finite) failed (density / a_ii / position / velocity)"; return ASPH_ERR_NONFINITE; }

@@ -22,7 +22,7 @@
 #include <cmath>
 #include <cstring>
 
-#include "sim.cuh"
+#include "lists.cuh"
 
 namespace {
 
@@ -102,6 +102,20 @@ struct DistState {
   uint32_t* gather_host = nullptr;      // pinned: nranks * W_COUNT words, or the histogram
   bool map_valid = false;
   uint64_t halo_calls = 0, halo_bytes = 0;
+  // peer-memory path (sweeps): see PeerCtl in sim.cuh
+  bool p2p = false;
+  PeerCtl* my_ctl = nullptr;                      // device memory of this rank
+  PeerCtl* peer_ctl[ASPH_MAX_RANKS] = {nullptr};  // every rank's PeerCtl mapped here ([rank] = my_ctl)
+  void* mapped_src[2][3] = {{nullptr}};           // the neighbour's own pointers of packA / packP[0] / packP[1] last mapped ([0] = rank - 1)
+  float4* peer_field[2][3] = {{nullptr}};         // ... and where they are mapped in this process
+  DevBuf<uint32_t> remote_slot;                   // ghost slot on the neighbour of my k-th send-list entry (left part, right part)
+  DevBuf<uint32_t> rslot[2], blocks_done;         // the same per local particle (~0: not a border particle); pass-completion counter
+  DevBuf<unsigned char> tile_border;
+  DevBuf<unsigned char> rec_dev;                  // allgather buffers of P2PRecord: mine, then one per rank
+  unsigned char* rec_host = nullptr;
+  DevBuf<unsigned long long> peer_ctl_dev;        // peer_ctl[] for k_stats_push
+  bool peer_ctl_ready = false;
+  unsigned int halo_seq = 0, stats_seq = 0;       // pushes launched so far
 };
 
 namespace {
@@ -482,6 +496,8 @@ int dist_allreduce_cfl(asph_sim* sim) {
   return ASPH_OK;
 }
 
+static int p2p_refresh(asph_sim* sim);
+
 int dist_after_sort(asph_sim* sim) {
   DistState* D = sim->dist;
   const uint32_t n = sim->n;
@@ -489,6 +505,7 @@ int dist_after_sort(asph_sim* sim) {
   k_build_maps<<<(n + kThreads - 1) / kThreads, kThreads, 0, sim->stream>>>(n, sim->order.p, sim->n_owned, D->n_recv[0], D->slot[0].p, D->slot[1].p,
                                                                            D->n_send[0], D->send_idx.p, D->recv_idx.p);
   LAUNCH_CHECK();
+  TRY(p2p_refresh(sim));
   return ASPH_OK;
 }
 
@@ -539,6 +556,130 @@ int dist_reduce_flags(asph_sim* sim, bool) {
   return ASPH_OK;
 }
 
+// ---- peer-memory path --------------------------------------------------------------------------------------------
+namespace {
+
+struct P2PRecord {  // what every rank tells the others once per step
+  void* ptr[3];                 // its packA, packP[0], packP[1]
+  void* ctl;                    // its PeerCtl
+  cudaIpcMemHandle_t h[3], hc;  // and their IPC handles
+};
+
+// per local particle: the ghost slot of its copy on the left / right neighbour (~0: none), and which tiles have any
+__global__ void k_build_rslot(uint32_t ns0, uint32_t ns1, const uint32_t* __restrict__ send_idx, const uint32_t* __restrict__ remote_slot,
+                              uint32_t* __restrict__ rslot_l, uint32_t* __restrict__ rslot_r, unsigned char* __restrict__ tile_border) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ns0 + ns1) return;
+  const uint32_t i = send_idx[k];
+  (k < ns0 ? rslot_l : rslot_r)[i] = remote_slot[k];
+  tile_border[i / ASPH_PAIR_BLOCK] = 1;
+}
+
+}  // namespace
+
+bool dist_p2p(asph_sim* sim) { return sim->dist && sim->dist->p2p && sim->dist->nranks > 1; }
+
+// Once per step, after the last reallocation the step can cause: every rank publishes the addresses and IPC handles of
+// the three arrays its neighbours write into; a neighbour whose array moved is mapped again.  Also swaps the ghost
+// slot numbers: my k-th send-list entry lands in the neighbour's recv_idx[k].
+static int p2p_refresh(asph_sim* sim) {
+  DistState* D = sim->dist;
+  if (!D->p2p) return ASPH_OK;
+  const int R = D->nranks, r = D->rank;
+  cudaStream_t st = sim->stream;
+  P2PRecord mine;
+  memset(&mine, 0, sizeof mine);
+  mine.ptr[0] = sim->packA.p; mine.ptr[1] = sim->packP[0].p; mine.ptr[2] = sim->packP[1].p; mine.ctl = D->my_ctl;
+  for (int k = 0; k < 3; k++) CUDA_TRY(cudaIpcGetMemHandle(&mine.h[k], mine.ptr[k]));
+  CUDA_TRY(cudaIpcGetMemHandle(&mine.hc, D->my_ctl));
+  CUDA_TRY(cudaMemcpyAsync(D->rec_dev.p, &mine, sizeof mine, cudaMemcpyHostToDevice, st));
+  NCCL_TRY(nccl().AllGather(D->rec_dev.p, D->rec_dev.p + sizeof(P2PRecord), sizeof(P2PRecord), ncclUint8, D->comm, st));
+  CUDA_TRY(cudaMemcpyAsync(D->rec_host, D->rec_dev.p + sizeof(P2PRecord), size_t(R) * sizeof(P2PRecord), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const P2PRecord* all = reinterpret_cast<const P2PRecord*>(D->rec_host);
+  bool ok = true;
+  for (int q = 0; q < R; q++) {  // every rank's PeerCtl, once
+    if (q == r) { D->peer_ctl[q] = D->my_ctl; continue; }
+    if (!D->peer_ctl[q]) {
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[q].hc, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; continue; }
+      D->peer_ctl[q] = static_cast<PeerCtl*>(p);
+    }
+  }
+  for (int side = 0; side < 2; side++) {
+    const int q = side ? r + 1 : r - 1;
+    if (q < 0 || q >= R) continue;
+    for (int k = 0; k < 3; k++) {
+      if (D->mapped_src[side][k] == all[q].ptr[k] && D->peer_field[side][k]) continue;
+      if (D->peer_field[side][k]) { cudaIpcCloseMemHandle(D->peer_field[side][k]); D->peer_field[side][k] = nullptr; }
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[q].h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; continue; }
+      D->peer_field[side][k] = static_cast<float4*>(p);
+      D->mapped_src[side][k] = all[q].ptr[k];
+    }
+  }
+  if (ok && !D->peer_ctl_ready) {
+    CUDA_TRY(cudaMemcpyAsync(D->peer_ctl_dev.p, D->peer_ctl, size_t(R) * sizeof(PeerCtl*), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    D->peer_ctl_ready = true;
+  }
+  if (!ok) {  // this rank cannot reach a peer: every rank must take the same path, so agree through the error-free NCCL route
+    sim->last_error = "cudaIpcOpenMemHandle failed (no peer access between the GPUs of this job?)";
+    return ASPH_ERR_CUDA;
+  }
+  // ghost slot numbers
+  const uint32_t ns = D->n_send[0] + D->n_send[1];
+  CUDA_TRY(D->remote_slot.ensure(std::max<size_t>(size_t(D->cap_h) * 2, ns)));
+  if (ns | (D->n_recv[0] + D->n_recv[1])) {
+    const Nccl& N = nccl();
+    NCCL_TRY(N.GroupStart());
+    if (D->n_recv[0]) NCCL_TRY(N.Send(D->recv_idx.p, D->n_recv[0], ncclUint32, r - 1, D->comm, st));
+    if (D->n_recv[1]) NCCL_TRY(N.Send(D->recv_idx.p + D->n_recv[0], D->n_recv[1], ncclUint32, r + 1, D->comm, st));
+    if (D->n_send[0]) NCCL_TRY(N.Recv(D->remote_slot.p, D->n_send[0], ncclUint32, r - 1, D->comm, st));
+    if (D->n_send[1]) NCCL_TRY(N.Recv(D->remote_slot.p + D->n_send[0], D->n_send[1], ncclUint32, r + 1, D->comm, st));
+    NCCL_TRY(N.GroupEnd());
+  }
+  const size_t tiles = (size_t(sim->cap) + ASPH_PAIR_BLOCK - 1) / ASPH_PAIR_BLOCK + 1;
+  CUDA_TRY(D->rslot[0].ensure(sim->cap)); CUDA_TRY(D->rslot[1].ensure(sim->cap)); CUDA_TRY(D->tile_border.ensure(tiles));
+  CUDA_TRY(cudaMemsetAsync(D->rslot[0].p, 0xFF, size_t(sim->n) * sizeof(uint32_t), st));
+  CUDA_TRY(cudaMemsetAsync(D->rslot[1].p, 0xFF, size_t(sim->n) * sizeof(uint32_t), st));
+  CUDA_TRY(cudaMemsetAsync(D->tile_border.p, 0, tiles, st));
+  if (ns) {
+    k_build_rslot<<<(ns + kThreads - 1) / kThreads, kThreads, 0, st>>>(D->n_send[0], D->n_send[1], D->send_idx.p, D->remote_slot.p, D->rslot[0].p,
+                                                                     D->rslot[1].p, D->tile_border.p);
+    LAUNCH_CHECK();
+  }
+  return ASPH_OK;
+}
+
+PeerArgs dist_peer_args(asph_sim* sim, bool wait_halo, bool wait_stats, int field, bool with_stats) {
+  PeerArgs a;
+  memset(&a, 0, sizeof a);
+  a.nranks = 1;
+  if (!dist_p2p(sim)) return a;
+  DistState* D = sim->dist;
+  a.self = D->my_ctl; a.rank = D->rank; a.nranks = D->nranks;
+  a.halo_seq = wait_halo ? D->halo_seq : 0u;
+  a.stats_seq = wait_stats ? D->stats_seq : 0u;
+  if (field >= 0) {
+    for (int side = 0; side < 2; side++) {
+      const int q = side ? D->rank + 1 : D->rank - 1;
+      const bool has = q >= 0 && q < D->nranks;
+      a.dst[side] = has ? D->peer_field[side][field] : nullptr;
+      a.rslot[side] = D->rslot[side].p;
+      a.nb_ctl[side] = has ? D->peer_ctl[q] : nullptr;
+    }
+    a.tile_border = D->tile_border.p;
+    a.all_ctl = reinterpret_cast<PeerCtl* const*>(D->peer_ctl_dev.p);
+    a.halo_seq_out = ++D->halo_seq;
+    a.stats_seq_out = with_stats ? ++D->stats_seq : 0u;
+    a.blocks_done = D->blocks_done.p;
+    D->halo_calls++;
+    D->halo_bytes += uint64_t(D->n_send[0] + D->n_send[1]) * 16;
+  }
+  return a;
+}
+
 int dist_local_map(asph_sim* sim) {
   DistState* D = sim->dist;
   if (D->map_valid) return ASPH_OK;
@@ -566,6 +707,12 @@ void dist_destroy(asph_sim* sim) {
   D->send_idx.release(); D->recv_idx.release(); D->slot[0].release(); D->slot[1].release();
   D->sendbuf.release(); D->recvbuf.release(); D->words.release(); D->gather.release(); D->hist.release();
   if (D->gather_host) cudaFreeHost(D->gather_host);
+  for (int side = 0; side < 2; side++)
+    for (int k = 0; k < 3; k++) if (D->peer_field[side][k]) cudaIpcCloseMemHandle(D->peer_field[side][k]);
+  for (int q = 0; q < D->nranks && q < ASPH_MAX_RANKS; q++) if (q != D->rank && D->peer_ctl[q]) cudaIpcCloseMemHandle(D->peer_ctl[q]);
+  if (D->my_ctl) cudaFree(D->my_ctl);
+  if (D->rec_host) cudaFreeHost(D->rec_host);
+  D->remote_slot.release(); D->rec_dev.release(); D->peer_ctl_dev.release(); D->rslot[0].release(); D->rslot[1].release(); D->blocks_done.release(); D->tile_border.release();
   delete D;
   sim->dist = nullptr;
 }
@@ -615,6 +762,17 @@ int asph_create_distributed(const asph_params* params, const float* pos, const f
     return fail(ASPH_ERR_CUDA);
   memset(D->gather_host, 0, std::max<size_t>(size_t(n_ranks) * W_COUNT, 16) * sizeof(uint32_t));
   if (ensure_halo_capacity(sim, uint32_t(std::max<uint64_t>(1u << 16, cap / 8))) != ASPH_OK) return fail(ASPH_ERR_CUDA);
+  {  // peer-memory path of the sweeps (ASPH_DIST_P2P=0 keeps them on NCCL send / recv + all-reduce)
+    const char* e = getenv("ASPH_DIST_P2P");
+    D->p2p = n_ranks > 1 && n_ranks <= ASPH_MAX_RANKS && !(e && e[0] == '0');
+    if (D->p2p) {
+      if (cudaMalloc((void**)&D->my_ctl, sizeof(PeerCtl)) != cudaSuccess || cudaMemset(D->my_ctl, 0, sizeof(PeerCtl)) != cudaSuccess ||
+          D->rec_dev.ensure(size_t(n_ranks + 1) * sizeof(P2PRecord)) != cudaSuccess || D->peer_ctl_dev.ensure(ASPH_MAX_RANKS) != cudaSuccess ||
+          D->blocks_done.ensure(4) != cudaSuccess || cudaMemset(D->blocks_done.p, 0, 16) != cudaSuccess ||
+          cudaMallocHost((void**)&D->rec_host, size_t(n_ranks) * sizeof(P2PRecord)) != cudaSuccess)
+        return fail(ASPH_ERR_CUDA);
+    }
+  }
   *out = sim;
   return ASPH_OK;
 }

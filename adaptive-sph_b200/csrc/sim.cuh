@@ -27,7 +27,7 @@
 enum {
   ERRF_NONFINITE = 1, ERRF_NEG_AII = 2, ERRF_DENSITY = 4, ERRF_NEIGHBOR_OVERFLOW = 8, ERRF_LIST_CAPACITY = 16,
   ERRF_PARTICLE_CAPACITY = 32, ERRF_SPLIT_PATTERN = 64, ERRF_LEVEL_WEIGHT = 128, ERRF_CELL_BUDGET = 256,
-  ERRF_SPLIT_CHILDREN = 512, ERRF_SOLVER_NONFINITE = 1024, ERRF_PARTNER_VALIDATION = 2048
+  ERRF_SPLIT_CHILDREN = 512, ERRF_SOLVER_NONFINITE = 1024, ERRF_PARTNER_VALIDATION = 2048, ERRF_PEER_TIMEOUT = 4096
 };
 
 // Cells of a level are numbered STRIP-MAJOR: the grid is cut into vertical strips of 2^strip_log2 columns; inside a
@@ -121,6 +121,36 @@ template <class T> struct DevBuf {
 };
 
 struct DistState;  // dist.cu
+
+// ---- multi-GPU, inside the sweeps: direct peer-memory exchange over NVLink (dist.cu) -------------------------------
+// Every rank owns one PeerCtl in device memory that all other ranks of the node have mapped (CUDA IPC).  A producer
+// (k_push / k_stats_push, launched right after the pass that computed the values) stores border values straight into
+// the neighbour's particle arrays, or its sweep statistics into every rank's stats_in[], fences, and then publishes a
+// sequence number in the consumer's PeerCtl; the consumer's next sweep kernel spins on that number in its prologue.
+// Sequence numbers only grow; all ranks launch the same sequence of passes, so rank r waits for the value its own
+// launch counter has.
+#define ASPH_MAX_RANKS 16
+struct PeerCtl {
+  unsigned int halo_flag[2];                 // [0] written by rank - 1, [1] by rank + 1
+  unsigned int stats_flag[ASPH_MAX_RANKS];   // [r] written by rank r
+  unsigned long long stats_in[ASPH_MAX_RANKS][3][ASPH_ACC_WORDS];  // rank r's SolverCtl::acc[slot] of its own particles
+};
+struct PeerArgs {          // by value into the sweep kernels; self == nullptr: single GPU, or the NCCL path
+  PeerCtl* self;
+  int rank, nranks;
+  unsigned int halo_seq;   // halo_flag value that says the ghosts this pass reads have arrived (from both neighbours)
+  unsigned int stats_seq;  // stats_flag value that says every rank's totals of the previous sweep have arrived
+  // what this pass publishes itself: its border particles' results go straight into the neighbours' arrays as they are
+  // computed; the block that finishes last fences and writes the sequence numbers (and, after the update pass, this
+  // rank's statistics into every rank's PeerCtl)
+  float4* dst[2];               // the pass's output array on rank - 1 / rank + 1 (nullptr: no such neighbour)
+  const uint32_t* rslot[2];     // per local particle: its ghost slot on that neighbour, or ~0
+  const unsigned char* tile_border;  // per tile: does it hold border particles at all?
+  PeerCtl* nb_ctl[2];
+  PeerCtl* const* all_ctl;      // every rank's PeerCtl (device array)
+  unsigned int halo_seq_out, stats_seq_out;  // stats_seq_out == 0: no statistics to publish (acceleration pass)
+  unsigned int* blocks_done;    // counter in this rank's memory, returns to 0 at the end of every pass
+};
 #define ASPH_GHOST_BIT 0x80000000u  // refid of a ghost particle (owned by a neighbouring slab) carries this bit
 
 struct asph_sim {
@@ -249,6 +279,9 @@ int dist_allreduce_cfl(asph_sim* sim);                     // min over ranks of 
 int dist_after_sort(asph_sim* sim);                        // halo index maps in sorted order
 int dist_halo(asph_sim* sim, void* field, int elem_bytes); // owner -> ghost copies of one per-particle field
 int dist_solver_reduce(asph_sim* sim, int slot);           // sum SolverCtl::acc[slot] over ranks
+bool dist_p2p(asph_sim* sim);                              // peer-memory path available (all neighbours mapped)?
+// arguments of the next sweep pass: what it waits for, and (field >= 0) where it publishes: packA (0) / packP[0] (1) / packP[1] (2)
+PeerArgs dist_peer_args(asph_sim* sim, bool wait_halo, bool wait_stats, int field, bool with_stats);
 int dist_reduce_flags(asph_sim* sim, bool with_lists);     // make error flags (and "lists too small") agree on all ranks
 int dist_local_map(asph_sim* sim);                         // scratch_u[3][i] = slot of owned particle i in read-backs, ~0u for ghosts
 void dist_destroy(asph_sim* sim);

@@ -29,9 +29,43 @@ struct SweepTotals {
   unsigned long long normal, negative, singular;
   float err_sum;
 };
-__device__ __forceinline__ SweepTotals read_totals(const StepCtl* ctl, int sweep) {
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Spin until a peer's sequence number has reached `seq` (PeerCtl, sim.cuh).  Bounded: a rank that failed and stopped
+// launching must not hang the others; after 2 s the step is flagged and fails on the host.
+__device__ __forceinline__ void peer_wait(const unsigned int* flag, unsigned int seq, StepCtl* ctl) {
+  unsigned long long t0 = 0;
+  for (unsigned int spins = 0; int(ld_acquire_sys(flag) - seq) < 0; spins++) {
+    if ((spins & 1023u) == 1023u) {
+      if (*reinterpret_cast<volatile unsigned int*>(&ctl->error_flags) & ERRF_PEER_TIMEOUT) return;  // somebody gave up already
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) { atomicOr(&ctl->error_flags, ERRF_PEER_TIMEOUT); return; }
+    }
+    __nanosleep(64);
+  }
+}
+__device__ __forceinline__ void peer_wait_halo(const PeerArgs& P, StepCtl* ctl) {
+  if (!P.self || P.halo_seq == 0u) return;
+  if (P.rank > 0) peer_wait(&P.self->halo_flag[0], P.halo_seq, ctl);
+  if (P.rank + 1 < P.nranks) peer_wait(&P.self->halo_flag[1], P.halo_seq, ctl);
+}
+__device__ __forceinline__ void peer_wait_stats(const PeerArgs& P, StepCtl* ctl) {
+  if (!P.self || P.stats_seq == 0u) return;
+  for (int r = 0; r < P.nranks; r++)
+    if (r != P.rank) peer_wait(&P.self->stats_flag[r], P.stats_seq, ctl);
+}
+// totals of sweep number `sweep` over all particles of all ranks (call peer_wait_stats first)
+__device__ __forceinline__ SweepTotals read_totals(const StepCtl* ctl, int sweep, const PeerArgs& P) {
   const unsigned long long* acc = ctl->solver.acc[sweep % 3];
-  unsigned long long nn = 0, ng = 0;
+  unsigned long long nn = 0, ng = 0, sg = acc[2 * ASPH_ACC_COPIES];
   long long e = 0;
 #pragma unroll
   for (int c = 0; c < ASPH_ACC_COPIES; c++) {
@@ -39,8 +73,20 @@ __device__ __forceinline__ SweepTotals read_totals(const StepCtl* ctl, int sweep
     nn += a & 0xffffffffull; ng += a >> 32;
     e += (long long)b;
   }
+  if (P.self && P.stats_seq != 0u) {  // the other ranks' parts, in rank order (integers: any order gives the same sums)
+    for (int r = 0; r < P.nranks; r++) {
+      if (r == P.rank) continue;
+      const volatile unsigned long long* in = P.self->stats_in[r][sweep % 3];
+      for (int c = 0; c < ASPH_ACC_COPIES; c++) {
+        const unsigned long long a = in[2 * c], b = in[2 * c + 1];
+        nn += a & 0xffffffffull; ng += a >> 32;
+        e += (long long)b;
+      }
+      sg += in[2 * ASPH_ACC_COPIES];
+    }
+  }
   SweepTotals t;
-  t.normal = nn; t.negative = ng; t.singular = acc[2 * ASPH_ACC_COPIES];
+  t.normal = nn; t.negative = ng; t.singular = sg;
   t.err_sum = float(double(e) * (1.0 / 4294967296.0));
   return t;
 }
@@ -67,9 +113,10 @@ __device__ __forceinline__ void record_sweep(StepCtl* ctl, const SweepTotals& t,
   s.maxerr_enc[(sweep + 2) % 3] = 0u;
 }
 // end of a batch of sweeps: evaluate the last one launched (the next batch's first kernel would do the same)
-__global__ void k_solver_decide(StepCtl* ctl, int sweep, float rho0, float tol, int max_iters, int density_mode) {
+__global__ void k_solver_decide(StepCtl* ctl, int sweep, float rho0, float tol, int max_iters, int density_mode, const PeerArgs P) {
   if (ctl->solver.done || ctl->solver.sweeps > sweep) return;
-  const SweepTotals t = read_totals(ctl, sweep);
+  peer_wait_stats(P, ctl);
+  const SweepTotals t = read_totals(ctl, sweep, P);
   record_sweep(ctl, t, sweep, sweep_stops(t, sweep, ctl->error_flags, ctl->dt, rho0, tol, max_iters, density_mode));
 }
 
@@ -421,6 +468,7 @@ struct SweepArgs {
   const uint32_t* gid;
   float omega, rho0, tol;
   int sweep, density_mode, max_iters;
+  PeerArgs peer;  // multi-GPU peer-memory path: what this pass has to wait for
 };
 
 template <int PASS, bool HMWIN>
@@ -431,7 +479,8 @@ k_sweep(const SweepArgs A) {
   Stage* stages = reinterpret_cast<Stage*>(sweep_smem);
   __shared__ int s_stop;
   StepCtl* ctl = A.ctl;
-  if (ctl->solver.done) return;
+  const bool done0 = ctl->solver.done != 0;
+  bool work = !done0;  // (block-uniform) once the solve is over a pass only keeps the ranks' sequence numbers aligned
   const uint32_t n = A.n, tid = threadIdx.x, G = gridDim.x;
   const uint32_t ntiles = (n + kThreads - 1) / kThreads;
   const bool odd = (A.sweep & 1) != 0;
@@ -486,30 +535,46 @@ k_sweep(const SweepArgs A) {
     }
   };
 
+  // multi-GPU: a border particle's result also goes into its ghost copy on the neighbour rank(s), over NVLink
+  auto publish = [&](uint32_t t, uint32_t i, const float4& v) {
+    if (!A.peer.tile_border || !A.peer.tile_border[t]) return;
+    const uint32_t sl = A.peer.rslot[0][i], sr = A.peer.rslot[1][i];
+    if (sl != 0xffffffffu && A.peer.dst[0]) A.peer.dst[0][sl] = v;
+    if (sr != 0xffffffffu && A.peer.dst[1]) A.peer.dst[1][sr] = v;
+  };
+
   uint32_t tile = blockIdx.x;
-  if (tile >= ntiles) return;
-  uint32_t c_cur, sb_cur, fj_cur, fc_cur, c_nxt, sb_nxt, fj_nxt, fc_nxt;
-  load_hdr(tile, c_cur, sb_cur, fj_cur, fc_cur);
-  load_hdr(tile + G, c_nxt, sb_nxt, fj_nxt, fc_nxt);
-  if (PASS == 0) {
+  if (tile >= ntiles) work = false;
+  uint32_t c_cur = 0, sb_cur = 0, fj_cur = 0, fc_cur = 0, c_nxt = 0, sb_nxt = 0, fj_nxt = 0, fc_nxt = 0;
+  if (work) {
+    load_hdr(tile, c_cur, sb_cur, fj_cur, fc_cur);
+    load_hdr(tile + G, c_nxt, sb_nxt, fj_nxt, fc_nxt);
+  }
+  if (PASS == 0 && !done0) {
     if (tid == 0) {
       // prologue of sweep number `sweep` >= 1: the stop rule for sweep - 1 from its totals, once per block, while the
-      // first headers are in flight; block 0 also records it for the host
-      const SweepTotals t = read_totals(ctl, A.sweep - 1);
+      // first headers are in flight; block 0 also records it for the host.  Multi-GPU: the other ranks' totals and the
+      // neighbours' p' of the border particles must have arrived.
+      peer_wait_stats(A.peer, ctl);
+      peer_wait_halo(A.peer, ctl);
+      const SweepTotals t = read_totals(ctl, A.sweep - 1, A.peer);
       const bool stop = sweep_stops(t, A.sweep - 1, ctl->error_flags, dt, A.rho0, A.tol, A.max_iters, A.density_mode);
       if (blockIdx.x == 0) record_sweep(ctl, t, A.sweep - 1, stop);
       s_stop = stop ? 1 : 0;
     }
     __syncthreads();
-    if (s_stop) return;  // the solve ended with the previous sweep
+    if (s_stop) work = false;  // the solve ended with the previous sweep
+  } else if (PASS == 1 && work && A.peer.self && A.peer.halo_seq != 0u) {  // the neighbours' a^p of the border particles
+    if (tid == 0) peer_wait_halo(A.peer, ctl);
+    __syncthreads();
   }
-  issue(tile, stages[0], c_cur, sb_cur, fj_cur, fc_cur);
+  if (work) issue(tile, stages[0], c_cur, sb_cur, fj_cur, fc_cur);
 
   uint32_t c_normal = 0, c_sing = 0, c_neg = 0;
   float e_sum = 0.f, e_max = 0.f;
   bool bad = false;
   int s = 0;
-  for (; tile < ntiles; tile += G, s ^= 1) {
+  for (; work && tile < ntiles; tile += G, s ^= 1) {
     Stage& S = stages[s];
     // tile t's copies (issued one iteration ago) have landed for every thread; the same barrier also says that every
     // thread is done computing tile t - 1, so its stage can be refilled at once with tile t + 1
@@ -520,7 +585,9 @@ k_sweep(const SweepArgs A) {
     load_hdr(tile + 2u * G, c_nn, sb_nn, fj_nn, fc_nn);
 
     const uint32_t i = tile * kThreads + tid;
-    const bool active = i < n && !(PASS == 1 && A.gid && (A.gid[i] & ASPH_GHOST_BIT));
+    // multi-GPU: ghost particles are skipped in both passes — their values arrive from the owner rank, possibly before
+    // this block gets here (peer-memory path), and must not be overwritten with sums over an incomplete neighbourhood
+    const bool active = i < n && !(A.gid && (A.gid[i] & ASPH_GHOST_BIT));
     if (active) {
       NbCol col;
       col.far_idx = A.L.far_idx; col.i = i; col.cw = nb_cw(c_cur); col.cf = nb_cf(c_cur); col.cn = col.cw + col.cf;
@@ -542,7 +609,9 @@ k_sweep(const SweepArgs A) {
         const float2 g = *reinterpret_cast<const float2*>(&S.own4[tid]);
         ax = ax * scale - me.w * g.x;
         ay = ay * scale - me.w * g.y;
-        A.packA[i] = make_float4(me.x, me.y, ax, ay);
+        const float4 out = make_float4(me.x, me.y, ax, ay);
+        A.packA[i] = out;
+        publish(tile, i, out);
       } else {
         const float4 pc = S.own4[tid];
         const float rho_i = S.own1[0][tid], p_old = S.own1[1][tid];
@@ -566,13 +635,15 @@ k_sweep(const SweepArgs A) {
           if (pn <= 0.f) { pn = 0.f; c_neg++; }
           else { c_normal++; e_sum += perr; e_max = fmaxf(e_max, fabsf(perr)); }
         }
-        packP_next[i] = make_float4(me.x, me.y, pn * (inv_rho * inv_rho), pn);
+        const float4 out = make_float4(me.x, me.y, pn * (inv_rho * inv_rho), pn);
+        packP_next[i] = out;
+        publish(tile, i, out);
       }
     }
     c_cur = c_nxt; sb_cur = sb_nxt; c_nxt = c_nn; sb_nxt = sb_nn; fj_nxt = fj_nn; fc_nxt = fc_nn;
   }
 
-  if (PASS == 1) {
+  if (PASS == 1 && work) {
     if (bad) atomicOr(&ctl->error_flags, ERRF_SOLVER_NONFINITE);
     // block totals, once per block: counts by redux, the error sum by a fixed-order shuffle tree; then integers only
     c_normal = __reduce_add_sync(0xffffffffu, c_normal);
@@ -603,6 +674,33 @@ k_sweep(const SweepArgs A) {
       if (sing) atomicAdd(sc.acc[A.sweep % 3] + 2 * ASPH_ACC_COPIES, (unsigned long long)sing);
       // e_max >= 0: its bit pattern with the sign bit set is the order-preserving encoding dec_f expects
       if (mx) atomicMax(&sc.maxerr_enc[A.sweep % 3], mx | 0x80000000u);
+    }
+  }
+  if (A.peer.self && A.peer.halo_seq_out != 0u) {
+    // every block: its remote stores (and its statistics) are complete and visible system-wide; the block that finishes
+    // last tells the neighbours — and, after the update pass, hands this rank's totals to every rank
+    __threadfence_system();
+    __syncthreads();
+    __shared__ unsigned int s_last;
+    if (tid == 0) s_last = atomicAdd(A.peer.blocks_done, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (s_last) {
+      if (A.peer.stats_seq_out != 0u) {
+        const int slot = A.sweep % 3;
+        for (int r = 0; r < A.peer.nranks; r++) {
+          if (r == A.peer.rank) continue;
+          PeerCtl* pc = A.peer.all_ctl[r];
+          if (tid < ASPH_ACC_WORDS) pc->stats_in[A.peer.rank][slot][tid] = *reinterpret_cast<volatile unsigned long long*>(&ctl->solver.acc[slot][tid]);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < uint32_t(A.peer.nranks) && int(tid) != A.peer.rank) st_release_sys(&A.peer.all_ctl[tid]->stats_flag[A.peer.rank], A.peer.stats_seq_out);
+      }
+      if (tid == 0) {
+        *A.peer.blocks_done = 0u;
+        if (A.peer.nb_ctl[0]) st_release_sys(&A.peer.nb_ctl[0]->halo_flag[1], A.peer.halo_seq_out);  // I am my left neighbour's right neighbour
+        if (A.peer.nb_ctl[1]) st_release_sys(&A.peer.nb_ctl[1]->halo_flag[0], A.peer.halo_seq_out);
+      }
     }
   }
 }
@@ -677,6 +775,7 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
     CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * sizeof(SweepStage<false>))));
     attr_done = true;
   }
+  const bool p2p = dist_p2p(sim);
   SweepArgs A;
   A.n = n; A.L = L; A.P0 = sim->packP[0].p; A.P1 = sim->packP[1].p; A.P0w = sim->packP[0].p; A.P1w = sim->packP[1].p;
   A.packA = sim->packA.p; A.hm = sim->hm.p; A.gB = sim->gB.p; A.pconst = sim->pconst.p; A.rho = sim->rho.p; A.ctl = sim->ctl; A.gid = gid;
@@ -691,26 +790,29 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
       if (time_it) { tm.e0 = kt_event(sim); tm.e1 = kt_event(sim); tm.e1b = kt_event(sim); tm.e2 = kt_event(sim); cudaEventRecord(tm.e0, st); }
       A.sweep = launched;
       if (launched > 0) {  // sweep 0: a^p = 0 was written by k_source
+        A.peer = dist_peer_args(sim, true, true, 0, false);  // waits for the previous sweep's p' ghosts and every rank's totals; publishes a^p
         if (hmwin) k_sweep<0, true><<<grid, kThreads, smem, st>>>(A);
         else k_sweep<0, false><<<grid, kThreads, smem, st>>>(A);
         LAUNCH_CHECK();
         if (time_it) cudaEventRecord(tm.e1, st);
-        if (sim->dist) TRY(dist_halo(sim, sim->packA.p, 16));
+        if (!p2p && sim->dist) TRY(dist_halo(sim, sim->packA.p, 16));
       } else if (time_it) {
         cudaEventRecord(tm.e1, st);
       }
       if (time_it) cudaEventRecord(tm.e1b, st);
+      A.peer = dist_peer_args(sim, launched > 0, false, 1 + ((launched + 1) & 1), true);  // waits for the a^p ghosts; publishes p' and the totals
       if (hmwin) k_sweep<1, true><<<grid, kThreads, smem, st>>>(A);
       else k_sweep<1, false><<<grid, kThreads, smem, st>>>(A);
       LAUNCH_CHECK();
       if (time_it) { cudaEventRecord(tm.e2, st); timed.push_back(tm); }
-      if (sim->dist) {
+      if (!p2p && sim->dist) {
         TRY(dist_solver_reduce(sim, launched % 3));                       // every rank sees the totals of all ranks
         TRY(dist_halo(sim, sim->packP[(launched + 1) & 1].p, 16));        // p' of the border particles to their ghosts
       }
     }
     if (launched > 0) {  // evaluate the last sweep of the batch (the sweeps before it were evaluated by their successors)
-      k_solver_decide<<<1, 1, 0, st>>>(sim->ctl, launched - 1, sim->pp.rest_density, max_avg_error, sim->pp.max_iters, density_mode ? 1 : 0);
+      k_solver_decide<<<1, 1, 0, st>>>(sim->ctl, launched - 1, sim->pp.rest_density, max_avg_error, sim->pp.max_iters, density_mode ? 1 : 0,
+                                       dist_peer_args(sim, false, true, -1, false));
       LAUNCH_CHECK();
     }
     TRY(sync_ctl(sim));
@@ -720,6 +822,13 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
       if (tm.sweep < s.sweeps && cudaEventElapsedTime(&a, tm.e0, tm.e1) == cudaSuccess && cudaEventElapsedTime(&b2, tm.e1b, tm.e2) == cudaSuccess) {
         if (tm.sweep > 0) { sim->kt_ms[ASPH_KT_ACCEL_SWEEP] += a; sim->kt_samples[ASPH_KT_ACCEL_SWEEP]++; }  // sweep 0 has no K14 launch
         sim->kt_ms[ASPH_KT_JACOBI_SWEEP] += b2; sim->kt_samples[ASPH_KT_JACOBI_SWEEP]++;
+        static const bool dbg = getenv("ASPH_DEBUG_PUSH") != nullptr;
+        if (dbg) {
+          static double push_ms = 0; static int push_n = 0;
+          float c3 = 0.f;
+          if (tm.sweep > 0 && cudaEventElapsedTime(&c3, tm.e1, tm.e1b) == cudaSuccess) { push_ms += c3; push_n++; }
+          if (push_n == 50) { fprintf(stderr, "[asph] push(packA) interval avg %.2f us over %d samples; accel %.2f us jacobi %.2f us\n", push_ms / push_n * 1e3, push_n, a * 1e3, b2 * 1e3); push_ms = 0; push_n = 0; }
+        }
       }
       kt_release(sim, tm.e0); kt_release(sim, tm.e1); kt_release(sim, tm.e1b); kt_release(sim, tm.e2);
     }

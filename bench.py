@@ -139,7 +139,8 @@ def run_ours(args):
     warm_state = (sim.get_field("position"), sim.get_field("velocity"), sim.get_field("mass"))
     sim.set_state(*warm_state)   # same state again, so the e2e arm and the CPU baseline can start from it too
     sim.set_kernel_timing(4)
-    c0 = sim.counters()["simulation-step"][0]
+    cnt0 = sim.counters()
+    c0 = cnt0["simulation-step"][0]
     l0 = sim.kernel_launches()
     clocks = ClockSampler()
     clocks.start()
@@ -155,7 +156,9 @@ def run_ours(args):
         per_step.append((info["div_sweeps"], info["density_sweeps"], info["dt"]))
     wall = time.perf_counter() - t0
     clk = clocks.stop()
-    dev_ms = sim.counters()["simulation-step"][0] - c0
+    cnt1 = sim.counters()
+    dev_ms = cnt1["simulation-step"][0] - c0
+    phases = {k: (cnt1[k][0] - cnt0[k][0]) / max(K, 1) for k in cnt1}
     launches = sim.kernel_launches() - l0
     kt = sim.kernel_timing()
     sim.set_kernel_timing(0)
@@ -219,7 +222,7 @@ def run_ours(args):
                    "particles": n, "preroll_steps": pre_steps, "preroll_time_s": args.preroll_time, "replay_window_steps": REPLAY_WINDOW, "l2": "working set per step (neighbour lists + SoA, ~400 MB) exceeds the 126 MB L2; no flush",
                    "avg_div_sweeps": sweeps_div / max(K, 1), "avg_density_sweeps": sweeps_den / max(K, 1),
                    "timing": "CUDA events on the library stream around every step (PerformanceCounters 'simulation-step')",
-                   "wall_ms_per_step": wall * 1e3 / max(K, 1)},
+                   "wall_ms_per_step": wall * 1e3 / max(K, 1), "phase_ms_per_step": phases},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
     }
     out.update(extra)

@@ -40,7 +40,8 @@ def run(args, A, rank, world):
     if rank == 0:
         clocks.start()
     fence()
-    c0 = sim.counters()["simulation-step"][0]
+    cnt0 = sim.counters()
+    c0 = cnt0["simulation-step"][0]
     l0 = sim.kernel_launches()
     t0 = time.perf_counter()
     owned_steps, sweeps_div, sweeps_den = 0, 0, 0
@@ -51,7 +52,9 @@ def run(args, A, rank, world):
         sweeps_div += info["div_sweeps"]; sweeps_den += info["density_sweeps"]
     fence()
     wall = time.perf_counter() - t0
-    dev_ms = sim.counters()["simulation-step"][0] - c0
+    cnt1 = sim.counters()
+    dev_ms = cnt1["simulation-step"][0] - c0
+    phases = {k: (cnt1[k][0] - cnt0[k][0]) / max(K, 1) for k in cnt1}
     launches = sim.kernel_launches() - l0
     clk = clocks.stop() if rank == 0 else None
     kt = sim.kernel_timing()
@@ -111,7 +114,9 @@ def run(args, A, rank, world):
                        "l2": "working set per GPU (~400 MB) exceeds the 126 MB L2; no flush",
                        "avg_div_sweeps": sweeps_div / max(K, 1), "avg_density_sweeps": sweeps_den / max(K, 1),
                        "timing": "max over ranks of the CUDA-event time of the K steps on the library stream; barrier + synchronize on both sides",
-                       "wall_ms_per_step": wall_ms_max / max(K, 1)},
+                       "wall_ms_per_step": wall_ms_max / max(K, 1),
+                       "phase_ms_per_step_rank0": phases,
+                       "sweep_kernels_us_rank0": {k: (kt[k][0] / kt[k][1] * 1e3 if kt[k][1] else None) for k in ("accel_sweep", "jacobi_sweep", "neighbors", "sort_grid")}},
             "clocks": clk,
             "e2e": {"value": e2e_total / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_t / max(K, 1)),
                     "d2h_bytes_per_step": int(d2h_t / max(K, 1))},
