@@ -23,7 +23,8 @@
 // +-32767 positions away; such a slice is "wide": its F / E entries are plain 32-bit indices in chunks of 4 (the W
 // segment keeps its 16-bit form).  slice_base[s] = offset in units of 64 uint16 | wide << 31.
 // W + F = N_2(i) (what NeighborhoodCache::filter_down keeps, neighborhood_search.rs:56-70), cn = cw + cf.
-// cnt[i] = cw | cf << 12 (cw <= window size < 4096); cnt_ext[i] = ce.  Counts are of real neighbours only.
+// cnt[i] = cw | cf << 12 | ghost << 31 (cw <= window size < 4096; ghost: the particle is a copy owned by another GPU);
+// cnt_ext[i] = ce.  Counts are of real neighbours only.
 // No per-pair coefficient is stored: every pass recomputes dW/dr / r from the gathered positions (PairShape below).
 #pragma once
 #include "sim.cuh"
@@ -49,7 +50,8 @@ __host__ __device__ __forceinline__ uint32_t nb_block0(uint32_t i) { return i & 
 __host__ __device__ __forceinline__ uint32_t nb_bias(uint32_t i) { return nb_block0(i) - 32768u; }
 __host__ __device__ __forceinline__ uint32_t nb_win0(uint32_t i) { return nb_block0(i) - ASPH_PAIR_HALO; }  // mod 2^32
 __host__ __device__ __forceinline__ uint32_t nb_cw(uint32_t c) { return c & 0xfffu; }
-__host__ __device__ __forceinline__ uint32_t nb_cf(uint32_t c) { return c >> 12; }
+__host__ __device__ __forceinline__ uint32_t nb_cf(uint32_t c) { return (c >> 12) & 0x7ffffu; }
+__host__ __device__ __forceinline__ bool nb_ghost(uint32_t c) { return (c >> 31) != 0u; }
 __host__ __device__ __forceinline__ uint32_t nb_cn(uint32_t c) { return nb_cw(c) + nb_cf(c); }
 __host__ __device__ __forceinline__ uint32_t nb_pad8(uint32_t x) { return (x + 7u) & ~7u; }
 __host__ __device__ __forceinline__ uint32_t nb_pad4(uint32_t x) { return (x + 3u) & ~3u; }

@@ -171,7 +171,7 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
   base64 = __shfl_sync(0xffffffffu, base64, 0);
   if (!active) return;
   if (base64 + units > pool_cap64 || base64 + units < base64) { cnt[i] = 0u; cnt_ext[i] = 0u; return; }  // empty column: later passes stay in bounds
-  cnt[i] = cw | (cf << 12);
+  cnt[i] = cw | (min(cf, 0x7ffffu) << 12) | ((gid && (gid[i] & ASPH_GHOST_BIT)) ? 0x80000000u : 0u);
   cnt_ext[i] = ce;
 
   // pass 2: write the entries (window segment, far 2h segment, extended-range rest)

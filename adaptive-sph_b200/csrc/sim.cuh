@@ -146,6 +146,11 @@ struct PeerArgs {          // by value into the sweep kernels; self == nullptr: 
   float4* dst[2];               // the pass's output array on rank - 1 / rank + 1 (nullptr: no such neighbour)
   const uint32_t* rslot[2];     // per local particle: its ghost slot on that neighbour, or ~0
   const unsigned char* tile_border;  // per tile: does it hold border particles at all?
+  // Tiles with border particles ("edge tiles": the only ones that read ghost values, too) are processed first, and the
+  // sequence number goes to the neighbours as soon as the last of them is done — a whole pass ahead of when the
+  // neighbour needs it, so the handshake latency hides behind the interior tiles.
+  const uint32_t* tile_order;   // permutation of the tiles, edge tiles first; [ntiles] = number of edge tiles
+  unsigned int* edge_done;      // counter, returns to 0 in every pass
   PeerCtl* nb_ctl[2];
   PeerCtl* const* all_ctl;      // every rank's PeerCtl (device array)
   unsigned int halo_seq_out, stats_seq_out;  // stats_seq_out == 0: no statistics to publish (acceleration pass)

@@ -40,17 +40,19 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 // Spin until a peer's sequence number has reached `seq` (PeerCtl, sim.cuh).  Bounded: a rank that failed and stopped
 // launching must not hang the others; after 2 s the step is flagged and fails on the host.
 __device__ __forceinline__ void peer_wait(const unsigned int* flag, unsigned int seq, StepCtl* ctl) {
+  // poll with plain (relaxed) loads of this GPU's own memory — L2 hits — and acquire once the number is there
+  const volatile unsigned int* f = flag;
   unsigned long long t0 = 0;
-  for (unsigned int spins = 0; int(ld_acquire_sys(flag) - seq) < 0; spins++) {
-    if ((spins & 1023u) == 1023u) {
+  for (unsigned int spins = 0; int(*f - seq) < 0; spins++) {
+    if ((spins & 4095u) == 4095u) {
       if (*reinterpret_cast<volatile unsigned int*>(&ctl->error_flags) & ERRF_PEER_TIMEOUT) return;  // somebody gave up already
       unsigned long long now;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
       if (t0 == 0) t0 = now;
       else if (now - t0 > 2000000000ull) { atomicOr(&ctl->error_flags, ERRF_PEER_TIMEOUT); return; }
     }
-    __nanosleep(64);
   }
+  (void)ld_acquire_sys(flag);
 }
 __device__ __forceinline__ void peer_wait_halo(const PeerArgs& P, StepCtl* ctl) {
   if (!P.self || P.halo_seq == 0u) return;
@@ -471,8 +473,8 @@ struct SweepArgs {
   PeerArgs peer;  // multi-GPU peer-memory path: what this pass has to wait for
 };
 
-template <int PASS, bool HMWIN>
-__global__ void __launch_bounds__(kThreads, HMWIN ? 3 : 4)
+template <int PASS, bool HMWIN, bool PEER>
+__global__ void __launch_bounds__(kThreads, (HMWIN || PEER) ? 3 : 4)
 k_sweep(const SweepArgs A) {
   extern __shared__ __align__(16) unsigned char sweep_smem[];
   typedef SweepStage<HMWIN> Stage;
@@ -537,57 +539,69 @@ k_sweep(const SweepArgs A) {
 
   // multi-GPU: a border particle's result also goes into its ghost copy on the neighbour rank(s), over NVLink
   auto publish = [&](uint32_t t, uint32_t i, const float4& v) {
-    if (!A.peer.tile_border || !A.peer.tile_border[t]) return;
+    if (!PEER || !A.peer.tile_border[t]) return;
     const uint32_t sl = A.peer.rslot[0][i], sr = A.peer.rslot[1][i];
     if (sl != 0xffffffffu && A.peer.dst[0]) A.peer.dst[0][sl] = v;
     if (sr != 0xffffffffu && A.peer.dst[1]) A.peer.dst[1][sr] = v;
   };
 
-  uint32_t tile = blockIdx.x;
-  if (tile >= ntiles) work = false;
+  // Tiles are walked in sequence q = blockIdx.x, + G, ...; multi-GPU (peer-memory path): through the permutation that
+  // puts the edge tiles first (sim.cuh), whose entries travel in registers three tiles ahead.
+  const uint32_t* __restrict__ order = PEER ? A.peer.tile_order : nullptr;
+  const uint32_t n_edge = order ? order[ntiles] : 0u;
+  auto ord = [&](uint32_t q) { return order ? (q < ntiles ? __ldg(order + q) : 0xffffffffu) : q; };
+  uint32_t q = blockIdx.x;
+  if (q >= ntiles) work = false;
+  uint32_t tile = 0, t_nxt = 0, t_nn = 0;
   uint32_t c_cur = 0, sb_cur = 0, fj_cur = 0, fc_cur = 0, c_nxt = 0, sb_nxt = 0, fj_nxt = 0, fc_nxt = 0;
   if (work) {
+    tile = ord(q); t_nxt = ord(q + G); t_nn = ord(q + 2u * G);
     load_hdr(tile, c_cur, sb_cur, fj_cur, fc_cur);
-    load_hdr(tile + G, c_nxt, sb_nxt, fj_nxt, fc_nxt);
+    load_hdr(t_nxt, c_nxt, sb_nxt, fj_nxt, fc_nxt);
   }
-  if (PASS == 0 && !done0) {
+  // The stop rule of iisph_pressure_iterations for sweep number sweep - 1, from its totals: evaluated by every block in
+  // the prologue of the next pressure-acceleration pass — or, on the peer-memory path, of the next update pass, so that
+  // the other ranks' totals have a whole pass to arrive (the acceleration pass in between is then executed once too
+  // often at the end of a solve; its output is not used).  Block 0 also records the decision for the host.
+  const bool decides = !done0 && A.sweep > 0 && (PEER ? PASS == 1 : PASS == 0);
+  if (decides || (PEER && work)) {
     if (tid == 0) {
-      // prologue of sweep number `sweep` >= 1: the stop rule for sweep - 1 from its totals, once per block, while the
-      // first headers are in flight; block 0 also records it for the host.  Multi-GPU: the other ranks' totals and the
-      // neighbours' p' of the border particles must have arrived.
-      peer_wait_stats(A.peer, ctl);
-      peer_wait_halo(A.peer, ctl);
-      const SweepTotals t = read_totals(ctl, A.sweep - 1, A.peer);
-      const bool stop = sweep_stops(t, A.sweep - 1, ctl->error_flags, dt, A.rho0, A.tol, A.max_iters, A.density_mode);
-      if (blockIdx.x == 0) record_sweep(ctl, t, A.sweep - 1, stop);
-      s_stop = stop ? 1 : 0;
+      if (PEER) peer_wait_halo(A.peer, ctl);  // the neighbours' border values this pass gathers
+      if (decides) {
+        if (PEER) peer_wait_stats(A.peer, ctl);
+        const SweepTotals t = read_totals(ctl, A.sweep - 1, A.peer);
+        const bool stop = sweep_stops(t, A.sweep - 1, ctl->error_flags, dt, A.rho0, A.tol, A.max_iters, A.density_mode);
+        if (blockIdx.x == 0) record_sweep(ctl, t, A.sweep - 1, stop);
+        s_stop = stop ? 1 : 0;
+      } else {
+        s_stop = 0;
+      }
     }
     __syncthreads();
     if (s_stop) work = false;  // the solve ended with the previous sweep
-  } else if (PASS == 1 && work && A.peer.self && A.peer.halo_seq != 0u) {  // the neighbours' a^p of the border particles
-    if (tid == 0) peer_wait_halo(A.peer, ctl);
-    __syncthreads();
   }
   if (work) issue(tile, stages[0], c_cur, sb_cur, fj_cur, fc_cur);
 
   uint32_t c_normal = 0, c_sing = 0, c_neg = 0;
   float e_sum = 0.f, e_max = 0.f;
   bool bad = false;
+  bool halo_sent = false;  // (block-uniform) the edge tiles of this pass were processed, so their completion sends the number
   int s = 0;
-  for (; work && tile < ntiles; tile += G, s ^= 1) {
+  for (; work && q < ntiles; q += G, s ^= 1) {
     Stage& S = stages[s];
     // tile t's copies (issued one iteration ago) have landed for every thread; the same barrier also says that every
     // thread is done computing tile t - 1, so its stage can be refilled at once with tile t + 1
     cp_async_wait_all();
     __syncthreads();
-    if (tile + G < ntiles) issue(tile + G, stages[s ^ 1], c_nxt, sb_nxt, fj_nxt, fc_nxt);
+    if (q + G < ntiles) issue(t_nxt, stages[s ^ 1], c_nxt, sb_nxt, fj_nxt, fc_nxt);
     uint32_t c_nn, sb_nn, fj_nn, fc_nn;
-    load_hdr(tile + 2u * G, c_nn, sb_nn, fj_nn, fc_nn);
+    load_hdr(t_nn, c_nn, sb_nn, fj_nn, fc_nn);
+    const uint32_t t_n3 = ord(q + 3u * G);
 
     const uint32_t i = tile * kThreads + tid;
     // multi-GPU: ghost particles are skipped in both passes — their values arrive from the owner rank, possibly before
     // this block gets here (peer-memory path), and must not be overwritten with sums over an incomplete neighbourhood
-    const bool active = i < n && !(A.gid && (A.gid[i] & ASPH_GHOST_BIT));
+    const bool active = i < n && !nb_ghost(c_cur);
     if (active) {
       NbCol col;
       col.far_idx = A.L.far_idx; col.i = i; col.cw = nb_cw(c_cur); col.cf = nb_cf(c_cur); col.cn = col.cw + col.cf;
@@ -640,6 +654,19 @@ k_sweep(const SweepArgs A) {
         publish(tile, i, out);
       }
     }
+    if (PEER && n_edge != 0u) {
+      halo_sent = true;
+      if (q < n_edge) {  // an edge tile is complete: the last one of the pass releases the neighbours
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0 && atomicAdd(A.peer.edge_done, 1u) == n_edge - 1u) {
+          *A.peer.edge_done = 0u;
+          if (A.peer.nb_ctl[0]) st_release_sys(&A.peer.nb_ctl[0]->halo_flag[1], A.peer.halo_seq_out);  // I am my left neighbour's right neighbour
+          if (A.peer.nb_ctl[1]) st_release_sys(&A.peer.nb_ctl[1]->halo_flag[0], A.peer.halo_seq_out);
+        }
+      }
+    }
+    tile = t_nxt; t_nxt = t_nn; t_nn = t_n3;
     c_cur = c_nxt; sb_cur = sb_nxt; c_nxt = c_nn; sb_nxt = sb_nn; fj_nxt = fj_nn; fc_nxt = fc_nn;
   }
 
@@ -676,7 +703,7 @@ k_sweep(const SweepArgs A) {
       if (mx) atomicMax(&sc.maxerr_enc[A.sweep % 3], mx | 0x80000000u);
     }
   }
-  if (A.peer.self && A.peer.halo_seq_out != 0u) {
+  if (PEER && A.peer.halo_seq_out != 0u) {
     // every block: its remote stores (and its statistics) are complete and visible system-wide; the block that finishes
     // last tells the neighbours — and, after the update pass, hands this rank's totals to every rank
     __threadfence_system();
@@ -698,8 +725,10 @@ k_sweep(const SweepArgs A) {
       }
       if (tid == 0) {
         *A.peer.blocks_done = 0u;
-        if (A.peer.nb_ctl[0]) st_release_sys(&A.peer.nb_ctl[0]->halo_flag[1], A.peer.halo_seq_out);  // I am my left neighbour's right neighbour
-        if (A.peer.nb_ctl[1]) st_release_sys(&A.peer.nb_ctl[1]->halo_flag[0], A.peer.halo_seq_out);
+        if (!halo_sent) {  // no tile was processed in this pass (the solve is over), or this rank has no edge tiles
+          if (A.peer.nb_ctl[0]) st_release_sys(&A.peer.nb_ctl[0]->halo_flag[1], A.peer.halo_seq_out);
+          if (A.peer.nb_ctl[1]) st_release_sys(&A.peer.nb_ctl[1]->halo_flag[0], A.peer.halo_seq_out);
+        }
       }
     }
   }
@@ -765,14 +794,19 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
   // host has seen says h is uniform (a wrong guess only costs speed, see k_sweep)
   const bool hmwin = !(sim->ctl_seen && sim->ctl_host->hmin == sim->ctl_host->hmax);
   const size_t smem = 2 * (hmwin ? sizeof(SweepStage<true>) : sizeof(SweepStage<false>));
-  uint32_t grid = sweep_grid(n, sim->sm_count, hmwin ? 3 : 4);
+  uint32_t grid = sweep_grid(n, sim->sm_count, (hmwin || dist_p2p(sim)) ? 3 : 4);
   if (const char* e = getenv("ASPH_SWEEP_GRID")) grid = std::max(1u, std::min(grid, uint32_t(atoi(e))));  // test hook: few blocks => many tiles per block
   static bool attr_done = false;
   if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(k_sweep<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * sizeof(SweepStage<true>))));
-    CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * sizeof(SweepStage<true>))));
-    CUDA_TRY(cudaFuncSetAttribute(k_sweep<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * sizeof(SweepStage<false>))));
-    CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * sizeof(SweepStage<false>))));
+    const int big = int(2 * sizeof(SweepStage<true>)), small = int(2 * sizeof(SweepStage<false>));
+    CUDA_TRY(cudaFuncSetAttribute(k_sweep<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(k_sweep<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
+    CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
+    CUDA_TRY(cudaFuncSetAttribute(k_sweep<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(k_sweep<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
+    CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
     attr_done = true;
   }
   const bool p2p = dist_p2p(sim);
@@ -790,9 +824,9 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
       if (time_it) { tm.e0 = kt_event(sim); tm.e1 = kt_event(sim); tm.e1b = kt_event(sim); tm.e2 = kt_event(sim); cudaEventRecord(tm.e0, st); }
       A.sweep = launched;
       if (launched > 0) {  // sweep 0: a^p = 0 was written by k_source
-        A.peer = dist_peer_args(sim, true, true, 0, false);  // waits for the previous sweep's p' ghosts and every rank's totals; publishes a^p
-        if (hmwin) k_sweep<0, true><<<grid, kThreads, smem, st>>>(A);
-        else k_sweep<0, false><<<grid, kThreads, smem, st>>>(A);
+        A.peer = dist_peer_args(sim, true, !p2p, 0, false);  // waits for the previous sweep's p' ghosts; publishes a^p
+        if (p2p) { if (hmwin) k_sweep<0, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, true><<<grid, kThreads, smem, st>>>(A); }
+        else { if (hmwin) k_sweep<0, true, false><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, false><<<grid, kThreads, smem, st>>>(A); }
         LAUNCH_CHECK();
         if (time_it) cudaEventRecord(tm.e1, st);
         if (!p2p && sim->dist) TRY(dist_halo(sim, sim->packA.p, 16));
@@ -800,9 +834,9 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
         cudaEventRecord(tm.e1, st);
       }
       if (time_it) cudaEventRecord(tm.e1b, st);
-      A.peer = dist_peer_args(sim, launched > 0, false, 1 + ((launched + 1) & 1), true);  // waits for the a^p ghosts; publishes p' and the totals
-      if (hmwin) k_sweep<1, true><<<grid, kThreads, smem, st>>>(A);
-      else k_sweep<1, false><<<grid, kThreads, smem, st>>>(A);
+      A.peer = dist_peer_args(sim, launched > 0, p2p && launched > 0, 1 + ((launched + 1) & 1), true);  // waits for the a^p ghosts and the previous sweep's totals; publishes p' and its own
+      if (p2p) { if (hmwin) k_sweep<1, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, true><<<grid, kThreads, smem, st>>>(A); }
+      else { if (hmwin) k_sweep<1, true, false><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, false><<<grid, kThreads, smem, st>>>(A); }
       LAUNCH_CHECK();
       if (time_it) { cudaEventRecord(tm.e2, st); timed.push_back(tm); }
       if (!p2p && sim->dist) {
