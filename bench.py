@@ -37,9 +37,10 @@ SPACING_C2 = 1.122e-3
 # scene to that time is input preparation: it happens before the warm-up steps and is not timed.
 PREROLL_T = 0.1445
 # The timed steps replay a fixed window of the trajectory: after REPLAY_WINDOW steps the state returns to the start of
-# the window.  (About 150 steps later this scene, at this resolution, stops converging within max_iters and the
-# reference's own `a_p.is_finite()` assertion fires; the window stays clear of that.)
-REPLAY_WINDOW = 100
+# the window.  (Some 100-150 steps later this scene, at this resolution, stops converging within max_iters and the
+# reference's own `a_p.is_finite()` assertion fires — when exactly depends on rounding, the impact is chaotic; the
+# window stays clear of that, and should a step fail all the same the window is cut short there and replayed.)
+REPLAY_WINDOW = 40
 REF_SAMPLE_WIDTH = 0.175  # the CPU arm's bounded sample: the same column height and spacing, a quarter of the block's width
 
 
@@ -146,19 +147,32 @@ def run_ours(args):
     clocks.start()
     t0 = time.perf_counter()
     particle_steps, sweeps_div, sweeps_den, per_step = 0, 0, 0, []
-    for k in range(K):
-        if k > 0 and k % REPLAY_WINDOW == 0:
+    window, in_window, restarts, dev_ms, k = REPLAY_WINDOW, 0, 0, 0.0, 0
+    while k < K:
+        if in_window >= window:
             sim.set_state(*warm_state)  # replay the same window (outside the per-step CUDA-event timing)
-        sim.single_step()
+            in_window = 0
+        c_before = sim.counters()["simulation-step"][0]
+        try:
+            sim.single_step()
+        except A.AsphError as e:  # the scene blew up inside the window: shorten the window and replay (not counted)
+            restarts += 1
+            if restarts > 8 or in_window < 3:
+                raise
+            window = max(3, in_window - 2)
+            sim.set_state(*warm_state)
+            in_window = 0
+            continue
+        dev_ms += sim.counters()["simulation-step"][0] - c_before
         info = sim.step_info()
         particle_steps += info["n_particles_begin"]
         sweeps_div += info["div_sweeps"]; sweeps_den += info["density_sweeps"]
         per_step.append((info["div_sweeps"], info["density_sweeps"], info["dt"]))
+        k += 1; in_window += 1
     wall = time.perf_counter() - t0
     clk = clocks.stop()
     cnt1 = sim.counters()
-    dev_ms = cnt1["simulation-step"][0] - c0
-    phases = {k: (cnt1[k][0] - cnt0[k][0]) / max(K, 1) for k in cnt1}
+    phases = {k: (cnt1[k][0] - cnt0[k][0]) / max(K + restarts, 1) for k in cnt1}
     launches = sim.kernel_launches() - l0
     kt = sim.kernel_timing()
     sim.set_kernel_timing(0)
@@ -195,16 +209,25 @@ def run_ours(args):
     sim.set_state(hp, hv, hm); sim.single_step()  # one untimed pass through this path
     hp[:] = warm_state[0]; hv[:] = warm_state[1]; hm[:] = warm_state[2]
     t0 = time.perf_counter()
-    e2e_particle_steps = 0
-    for k in range(K):
-        if k > 0 and k % REPLAY_WINDOW == 0:
+    e2e_particle_steps, in_window, k = 0, 0, 0
+    while k < K:
+        if in_window >= window:
             hp[:] = warm_state[0]; hv[:] = warm_state[1]; hm[:] = warm_state[2]
+            in_window = 0
         sim.set_state(hp, hv, hm)                   # H2D of this step's inputs (x, v, m)
-        sim.single_step()
+        try:
+            sim.single_step()
+        except A.AsphError:
+            if in_window < 3:
+                raise
+            window = max(3, in_window - 2)
+            in_window = window                      # next iteration restarts the window
+            continue
         sim.get_field("position", out=op)           # D2H of the step's result (x, v), reference particle order
         sim.get_field("velocity", out=ov)
         e2e_particle_steps += n
         hp[:] = op; hv[:] = ov                      # next step's input is this step's output
+        k += 1; in_window += 1
     e2e_s = time.perf_counter() - t0
     e2e = {"value": e2e_particle_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * 20), "d2h_bytes_per_step": int(n * 16)}
 
@@ -219,7 +242,7 @@ def run_ours(args):
         "config": {"workload": "configs[1]: 2D dam-break, uniform h, 999292 particles, HybridDFSPH (default-scene-web geometry, "
                                "spacing 1.122e-3; default-config with merging/sharing/splitting off, level_estimation None), "
                                f"state at t = {args.preroll_time} s (just after the block hits the floor: both pressure solves iterate)",
-                   "particles": n, "preroll_steps": pre_steps, "preroll_time_s": args.preroll_time, "replay_window_steps": REPLAY_WINDOW, "l2": "working set per step (neighbour lists + SoA, ~400 MB) exceeds the 126 MB L2; no flush",
+                   "particles": n, "preroll_steps": pre_steps, "preroll_time_s": args.preroll_time, "replay_window_steps": window, "failed_steps_replayed": restarts, "l2": "working set per step (neighbour lists + SoA, ~400 MB) exceeds the 126 MB L2; no flush",
                    "avg_div_sweeps": sweeps_div / max(K, 1), "avg_density_sweeps": sweeps_den / max(K, 1),
                    "timing": "CUDA events on the library stream around every step (PerformanceCounters 'simulation-step')",
                    "wall_ms_per_step": wall * 1e3 / max(K, 1), "phase_ms_per_step": phases},
