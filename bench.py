@@ -181,7 +181,14 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (the Jacobi update pass, K15) -------------------------------------------
     peak, peak_src = peaks()
     roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
-            "kernel": "k_jacobi (K15: x,m,rho,a^p,p,s,a_ii -> p'; 40 B/particle algorithmic)", "peak_source": peak_src}
+            "kernel": "k_sweep<1> (K15, the Jacobi update pass: x,m,rho,a^p,p,s,a_ii -> p'; 40 B/particle algorithmic)", "peak_source": peak_src}
+    try:  # DRAM bytes of one launch of that kernel from the committed ncu capture (profiles/)
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tr = json.load(f)["k_sweep<1> (K15)"]
+        roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        roof["traffic_source"] = "profiles/r1_traffic.json (ncu --set full, per launch, 999292 particles)"
+    except (OSError, KeyError, ValueError):
+        pass
     extra = {}
     if kt["jacobi_sweep"][1] > 0:
         ms_j = kt["jacobi_sweep"][0] / kt["jacobi_sweep"][1]
@@ -191,7 +198,7 @@ def run_ours(args):
         roof["launches_timed"] = int(kt["jacobi_sweep"][1])
     if kt["accel_sweep"][1] > 0:
         ms_a = kt["accel_sweep"][0] / kt["accel_sweep"][1]
-        extra["roofline_accel"] = {"kernel": "k_accel<0> (K14: x,m,rho,p -> a^p; 28 B/particle algorithmic)",
+        extra["roofline_accel"] = {"kernel": "k_sweep<0> (K14, the pressure-acceleration pass: x,m,rho,p -> a^p; 28 B/particle algorithmic)",
                                    "achieved": 28.0 * n / (ms_a * 1e-3) / 1e9, "avg_launch_ms": ms_a,
                                    "frac": 28.0 * n / (ms_a * 1e-3) / 1e9 / peak, "launches_timed": int(kt["accel_sweep"][1])}
     if kt["neighbors"][1] > 0:

@@ -141,7 +141,7 @@ def run(args, A, rank, world):
         peak, peak_src = peaks()
         n_rank = total_steps / max(K, 1) / world
         roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
-                "kernel": "k_jacobi on rank 0 (K15, 40 B/particle algorithmic over owned + ghost particles)", "peak_source": peak_src}
+                "kernel": "k_sweep<1> on rank 0 (K15, the Jacobi update pass incl. its wait for the neighbour GPUs; 40 B/particle algorithmic over owned + ghost particles)", "peak_source": peak_src}
         if kt.get("jacobi_sweep", [0, 0])[1] > 0:
             ms_j = kt["jacobi_sweep"][0] / kt["jacobi_sweep"][1]
             roof["achieved"] = 40.0 * n_rank / (ms_j * 1e-3) / 1e9
