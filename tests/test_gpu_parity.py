@@ -279,3 +279,33 @@ def test_trajectory_c1_resampling(asph, cuda_lib, oracle32, default_params, spli
     assert err <= 1e-5
     assert abs(float(g.get_field("mass").sum()) - float(o.get_field("mass").sum())) < 1e-5
     g.close(); o.close()
+
+
+def test_adaptive_dam_break_mid_size(asph, cuda_lib, oracle32, default_params, split_patterns):
+    """BASELINE config[2] recipe at a size the oracle steps in seconds: dam-break block at spacing 0.004 (77 k particles),
+    particle_radius_fine = the lattice particle's radius, base radius 4x, maximum_surface_distance 0.2, level set and
+    share / merge / split on.  Several size levels, wide slices, far tables and the {h, m} window at scale: particle
+    counts identical every step, positions within the north-star tolerance, mass conserved."""
+    spacing = 0.004
+    sc = asph.SceneConfig.dam_break(spacing)
+    r_f = float(np.sqrt(0.93 / np.pi) * spacing)
+    params = default_params.replace(particle_radius_fine=r_f, particle_radius_base=4.0 * r_f, maximum_surface_distance=0.2)
+    g = asph.init_fluid_sim(params, sc, split_patterns, lib=cuda_lib)
+    o = asph.init_fluid_sim(params, sc, split_patterns, lib=oracle32)
+    m0 = float(o.get_field("mass").astype(np.float64).sum())
+    counts, merged = [], 0
+    for k in range(12):
+        g.single_step(); o.single_step()
+        counts.append((g.num_fluid_particles(), o.num_fluid_particles()))
+        gi, oi = g.step_info(), o.step_info()
+        assert (gi["n_shared"], gi["n_merged"], gi["n_split_parents"]) == (oi["n_shared"], oi["n_merged"], oi["n_split_parents"]), (k, gi, oi)
+        merged += gi["n_merged"]
+    assert all(a == b for a, b in counts), counts
+    assert merged > 0 and counts[-1][0] < counts[0][0]   # the interior really coarsened
+    err = np.abs(g.get_field("position") - o.get_field("position")).max() / 2.0
+    print(f"adaptive dam break: N {counts[0][0]} -> {counts[-1][0]}, |gpu - oracle32| / L = {err:.3e}")
+    assert err <= 1e-5
+    assert abs(float(g.get_field("mass").astype(np.float64).sum()) - m0) < 0.005   # simulation.rs:2791
+    ms = g.get_field("mass")
+    assert ms.max() / ms.min() > 2.25                     # h ~ sqrt(m): more than one size level in play
+    g.close(); o.close()
