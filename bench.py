@@ -30,16 +30,22 @@ if ROOT not in sys.path:
 METRIC = "particle-steps/sec on 2D dam-break at 1/2/4/8 B200; HBM GB/s vs roofline"
 UNIT = "particle-steps/s"
 SPACING_C2 = 1.122e-3
-# The block of the reference's dam-break scene starts 0.1 above the floor.  For its first ~106 steps (0.141 simulated
-# seconds) it is in free fall: no particle has positive pressure, every solve stops after its first sweep and a step is
-# little more than the neighbour build.  The workload is therefore the scene at PREROLL_T simulated seconds, just after
-# the impact, where both pressure solves iterate (sweep counts are reported next to the throughput).  Advancing the
-# scene to that time is input preparation: it happens before the warm-up steps and is not timed.
-PREROLL_T = 0.1445
-# The timed steps replay a fixed window of the trajectory: after REPLAY_WINDOW steps the state returns to the start of
-# the window.  (Some 100-150 steps later this scene, at this resolution, stops converging within max_iters and the
-# reference's own `a_p.is_finite()` assertion fires — when exactly depends on rounding, the impact is chaotic; the
-# window stays clear of that, and should a step fail all the same the window is cut short there and replayed.)
+# The block of the reference's dam-break scene (default-scene-web.yaml) starts 0.1 above the floor, falls freely for
+# ~106 steps (no particle has positive pressure: every solve stops after its first sweep, a step is little more than
+# the neighbour build) and hits the floor at 1.4 m/s.  At 1 M particles the reference's own algorithm does not survive
+# that impact reliably: its Jacobi iteration stops converging within max_iters, the pressures run away and the
+# `a_p.is_finite()` assertion fires — on the CPU oracle as on the GPU, sooner or later depending on rounding (the impact
+# is chaotic), and already during the impact when the block is widened for 4 GPUs.  The benchmark therefore lowers the
+# drop to DROP_GAP = 0.02 (same block, same spacing, same fill ratio): the fluid lands gently (step 21) and the step loop
+# then runs in the regime that matters — divergence solve 3 sweeps, density solve 15-80 sweeps per step — for ~400 steps
+# at 1 M particles, but only for ~65 steps when the block is 4 times as wide (the wider the wetted floor, the sooner the
+# reference's solver loses it; measured on one GPU with the 4x scene, so it is physics, not the decomposition).  The
+# workload is therefore the scene at PREROLL_T = 0.064 simulated seconds, ten steps after the landing; advancing to that
+# time is input preparation (before the warm-up steps, untimed).  Sweep counts per step grow with the width of the
+# block, so next to particle-steps/s the JSON carries particle-sweeps/s, the figure to compare across GPU counts.  The timed steps replay a fixed window: after REPLAY_WINDOW steps the state returns to the
+# start of the window; should a step fail all the same, the window is cut short there and replayed.
+DROP_GAP = 0.02
+PREROLL_T = 0.064
 REPLAY_WINDOW = 40
 REF_SAMPLE_WIDTH = 0.175  # the CPU arm's bounded sample: the same column height and spacing, a quarter of the block's width
 
@@ -49,9 +55,13 @@ def uniform_params(A):
     return p.replace(merging=False, sharing=False, splitting=False, level_estimation_method="None")
 
 
-def dam_break(A, spacing, n_gpus=1, block_width=0.7):
+BLOCK_W, BLOCK_H = [float(v) for v in os.environ.get("ASPH_BENCH_BLOCK", "0.7,1.8").split(",")]
+
+
+def dam_break(A, spacing, n_gpus=1, block_width=None):
     w = 2.0 * n_gpus
-    return A.SceneConfig.dam_break(spacing, pos=(-w / 2 + 0.05, -0.9), size=(block_width * n_gpus, 1.8), width=w, height=2.0)
+    bw = BLOCK_W if block_width is None else block_width
+    return A.SceneConfig.dam_break(spacing, pos=(-w / 2 + 0.05, -1.0 + DROP_GAP), size=(bw * n_gpus, BLOCK_H), width=w, height=2.0)
 
 
 def preroll(sim, t_target, max_steps=2000):
@@ -177,6 +187,7 @@ def run_ours(args):
     kt = sim.kernel_timing()
     sim.set_kernel_timing(0)
     value = particle_steps / (dev_ms * 1e-3)
+    particle_sweeps_per_s = float(n) * (sweeps_div + sweeps_den) / (dev_ms * 1e-3)
 
     # ---- roofline of the dominant kernel (the Jacobi update pass, K15) -------------------------------------------
     peak, peak_src = peaks()
@@ -246,13 +257,14 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": dev_ms / max(K, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: 2D dam-break, uniform h, 999292 particles, HybridDFSPH (default-scene-web geometry, "
-                               "spacing 1.122e-3; default-config with merging/sharing/splitting off, level_estimation None), "
-                               f"state at t = {args.preroll_time} s (just after the block hits the floor: both pressure solves iterate)",
+        "config": {"workload": "configs[1]: 2D dam-break, uniform h, 999292 particles, HybridDFSPH (default-scene-web block at "
+                               f"spacing 1.122e-3, {DROP_GAP} above the floor; default-config with merging/sharing/splitting off, level_estimation None), "
+                               f"state at t = {args.preroll_time} s (the block has landed: both pressure solves iterate)",
                    "particles": n, "preroll_steps": pre_steps, "preroll_time_s": args.preroll_time, "replay_window_steps": window, "failed_steps_replayed": restarts, "l2": "working set per step (neighbour lists + SoA, ~400 MB) exceeds the 126 MB L2; no flush",
                    "avg_div_sweeps": sweeps_div / max(K, 1), "avg_density_sweeps": sweeps_den / max(K, 1),
                    "timing": "CUDA events on the library stream around every step (PerformanceCounters 'simulation-step')",
-                   "wall_ms_per_step": wall * 1e3 / max(K, 1), "phase_ms_per_step": phases},
+                   "wall_ms_per_step": wall * 1e3 / max(K, 1), "phase_ms_per_step": phases,
+                   "particle_sweeps_per_s": particle_sweeps_per_s},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
     }
     out.update(extra)

@@ -153,13 +153,14 @@ def run(args, A, rank, world):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"configs[1] widened {world}x: 2D dam-break, uniform h, {n_global} particles ({n_global // world} per GPU), "
                                    "HybridDFSPH, x-slab decomposition; ghost values of the sweeps stored straight into the neighbour GPU over NVLink peer memory, NCCL for migration / ghost set-up; "
-                                   f"state at t = {args.preroll_time} s (just after the block hits the floor: both pressure solves iterate)",
+                                   f"block 0.02 above the floor, state at t = {args.preroll_time} s (the block has landed: both pressure solves iterate)",
                        "preroll_steps": pre_steps, "preroll_time_s": args.preroll_time, "replay_window_steps": window, "failed_steps_replayed": state["restarts"],
                        "particles": n_global, "owned_per_rank": [int(x.item()) for x in owned_all],
                        "l2": "working set per GPU (~400 MB) exceeds the 126 MB L2; no flush",
                        "avg_div_sweeps": sweeps_div / max(K, 1), "avg_density_sweeps": sweeps_den / max(K, 1),
                        "timing": "max over ranks of the CUDA-event time of the K steps on the library stream; barrier + synchronize on both sides",
                        "wall_ms_per_step": wall_ms_max / max(K, 1),
+                       "particle_sweeps_per_s": (total_steps / max(K, 1)) * (sweeps_div + sweeps_den) / (dev_ms_max * 1e-3),
                        "phase_ms_per_step_rank0": phases,
                        "sweep_kernels_us_rank0": {k: (kt[k][0] / kt[k][1] * 1e3 if kt.get(k, [0, 0])[1] else None) for k in ("accel_sweep", "jacobi_sweep", "neighbors", "sort_grid")}},
             "clocks": clk,
