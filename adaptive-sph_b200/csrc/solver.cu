@@ -2,10 +2,12 @@
 // (K12), PPE source terms (K13), the relaxed-Jacobi pressure sweeps (K14 + K15) with their device-side stop rule,
 // and the integrators (K16).
 //
-// Every pass is one thread per particle.  A warp reads row k of its slice's 16-bit index column as one coalesced
-// 64 B line, gathers ONE float4 per neighbour (plus {h, m} when h is not uniform) and recomputes
+// Every pass is one thread per particle.  A thread reads its column 8 rows at a time (one 16 B load of 16-bit window
+// byte offsets; the warp's loads of a chunk are one 512 B run), gathers ONE float4 per neighbour from the block's
+// shared-memory window (plus {h, m} when h is not uniform) and recomputes
 //   m_j * gradW_ij = m_j * pair_g(|x_ij|^2, h_ij) * x_ij
-// in registers (lists.cuh), so a sweep streams 2 B per neighbour from HBM instead of 8.
+// in registers (lists.cuh), so a sweep streams 2 B per neighbour from HBM instead of 8.  The two passes of a Jacobi
+// sweep are persistent, software-pipelined kernels (k_sweep); on several GPUs they also carry the ghost exchange.
 //
 // Reference: simulation.rs:931-1005 (non-pressure accel), :1552-1592 (divergence operator), :1633-1748 (sources),
 // :1751-1808 (pressure accel), :1207-1322 (Jacobi sweep + PressureSolverStatistics), :1378-1516 (loop control),
