@@ -63,30 +63,53 @@ __device__ __forceinline__ void peer_wait_halo(const PeerArgs& P, StepCtl* ctl) 
 }
 __device__ __forceinline__ void peer_wait_stats(const PeerArgs& P, StepCtl* ctl) {
   if (!P.self || P.stats_seq == 0u) return;
+  // all ranks' numbers are requested together (one L2 round trip per polling round, not one per rank)
+  const volatile unsigned int* f = P.self->stats_flag;
+  unsigned long long t0 = 0;
+  for (unsigned int spins = 0;; spins++) {
+    unsigned int v[ASPH_MAX_RANKS];
+#pragma unroll
+    for (int r = 0; r < ASPH_MAX_RANKS; r++) v[r] = (r < P.nranks && r != P.rank) ? f[r] : P.stats_seq;
+    bool all = true;
+#pragma unroll
+    for (int r = 0; r < ASPH_MAX_RANKS; r++) all = all && int(v[r] - P.stats_seq) >= 0;
+    if (all) break;
+    if ((spins & 1023u) == 1023u) {
+      if (*reinterpret_cast<volatile unsigned int*>(&ctl->error_flags) & ERRF_PEER_TIMEOUT) return;
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) { atomicOr(&ctl->error_flags, ERRF_PEER_TIMEOUT); return; }
+    }
+  }
   for (int r = 0; r < P.nranks; r++)
-    if (r != P.rank) peer_wait(&P.self->stats_flag[r], P.stats_seq, ctl);
+    if (r != P.rank) { (void)ld_acquire_sys(&P.self->stats_flag[r]); break; }  // one acquire orders the mailbox reads below
 }
 // totals of sweep number `sweep` over all particles of all ranks (call peer_wait_stats first)
 __device__ __forceinline__ SweepTotals read_totals(const StepCtl* ctl, int sweep, const PeerArgs& P) {
   const unsigned long long* acc = ctl->solver.acc[sweep % 3];
-  unsigned long long nn = 0, ng = 0, sg = acc[2 * ASPH_ACC_COPIES];
+  unsigned long long w[ASPH_ACC_WORDS];
+#pragma unroll
+  for (int c = 0; c < ASPH_ACC_WORDS; c++) w[c] = __ldcg(acc + c);  // written by an earlier kernel; all loads in flight together
+  unsigned long long nn = 0, ng = 0, sg = w[2 * ASPH_ACC_COPIES];
   long long e = 0;
 #pragma unroll
   for (int c = 0; c < ASPH_ACC_COPIES; c++) {
-    const unsigned long long a = acc[2 * c], b = acc[2 * c + 1];  // written by an earlier kernel: ordinary cached loads
-    nn += a & 0xffffffffull; ng += a >> 32;
-    e += (long long)b;
+    nn += w[2 * c] & 0xffffffffull; ng += w[2 * c] >> 32;
+    e += (long long)w[2 * c + 1];
   }
-  if (P.self && P.stats_seq != 0u) {  // the other ranks' parts, in rank order (integers: any order gives the same sums)
+  if (P.self && P.stats_seq != 0u) {  // the other ranks' parts (integers: any order gives the same sums)
     for (int r = 0; r < P.nranks; r++) {
       if (r == P.rank) continue;
-      const volatile unsigned long long* in = P.self->stats_in[r][sweep % 3];
+      const unsigned long long* in = P.self->stats_in[r][sweep % 3];
+#pragma unroll
+      for (int c = 0; c < ASPH_ACC_WORDS; c++) w[c] = __ldcg(in + c);  // L2 is where the peer's stores landed
+#pragma unroll
       for (int c = 0; c < ASPH_ACC_COPIES; c++) {
-        const unsigned long long a = in[2 * c], b = in[2 * c + 1];
-        nn += a & 0xffffffffull; ng += a >> 32;
-        e += (long long)b;
+        nn += w[2 * c] & 0xffffffffull; ng += w[2 * c] >> 32;
+        e += (long long)w[2 * c + 1];
       }
-      sg += in[2 * ASPH_ACC_COPIES];
+      sg += w[2 * ASPH_ACC_COPIES];
     }
   }
   SweepTotals t;
