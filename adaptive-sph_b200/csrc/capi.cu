@@ -45,6 +45,28 @@ int pack_params(asph_sim* sim, const asph_params* p) {
   q.fail_on_missing_split_pattern = p->fail_on_missing_split_pattern;
   q.n_planes = sim->boundary.kind == ASPH_BND_PLANES ? sim->boundary.n_planes : 0;
   for (int s = 0; s < q.n_planes; s++) for (int k = 0; k < 3; k++) q.planes[s][k] = sim->boundary.planes[s][k];
+  // Sdf2DConnectedComponents::from_points (sdf/sdf2d.rs:37-71): normalised edge directions and vertex pseudo-normals, fp32
+  q.n_poly = 0;
+  if (sim->boundary.kind == ASPH_BND_POLYGON) {
+    const int np = sim->boundary.n_poly;
+    if (np < 3 || np > ASPH_POLY_DEV) { sim->last_error = "polygon boundary: 3..16 vertices"; return ASPH_ERR_INVALID; }
+    q.n_poly = np;
+    for (int i = 0; i < np; i++) { q.poly_pt[i][0] = sim->boundary.poly[i][0]; q.poly_pt[i][1] = sim->boundary.poly[i][1]; }
+    for (int i = 0; i < np; i++) {
+      const int j = (i + 1) % np;
+      volatile float dx = q.poly_pt[j][0] - q.poly_pt[i][0], dy = q.poly_pt[j][1] - q.poly_pt[i][1];
+      volatile float xx = dx * dx, yy = dy * dy;  // volatile: no contraction on the host either
+      volatile float n2 = xx + yy;
+      if (!(n2 > 0.00001f)) { sim->last_error = "polygon boundary: degenerate edge"; return ASPH_ERR_INVALID; }
+      const float n = std::sqrt(n2);
+      q.poly_dir[i][0] = dx / n; q.poly_dir[i][1] = dy / n;
+    }
+    for (int i = 0; i < np; i++) {
+      const int a = i == 0 ? np - 1 : i - 1;
+      q.poly_pn[i][0] = -q.poly_dir[a][1] + -q.poly_dir[i][1];
+      q.poly_pn[i][1] = q.poly_dir[a][0] + q.poly_dir[i][0];
+    }
+  }
 
   auto unsupported = [&](const char* what) { sim->last_error = std::string(what) + " is not implemented yet (SURVEY.md §8f)"; return ASPH_ERR_UNSUPPORTED; };
   if (p->support_length_estimation != ASPH_H_FROM_MASS) return unsupported("support_length_estimation != FromMass");
@@ -53,7 +75,6 @@ int pack_params(asph_sim* sim, const asph_params* p) {
   if (p->operator_discretization == ASPH_OP_WINCHENBACH2020) return unsupported("operator_discretization Winchenbach2020");
   if (p->pressure_solver_method == ASPH_SOLVER_IISPH2) return unsupported("pressure_solver_method IISPH2");
   if (p->viscosity_type == ASPH_VISC_XSPH) return unsupported("viscosity_type XSPH (todo!() in the reference)");
-  if (sim->boundary.kind == ASPH_BND_POLYGON) return unsupported("AnalyticUnderestimate polygon boundary");
   if (p->level_estimation_after_advection) return unsupported("level_estimation_after_advection");
   return ASPH_OK;
 }

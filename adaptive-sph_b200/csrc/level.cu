@@ -44,8 +44,7 @@ k_surface(uint32_t n, Lists L, const float4* __restrict__ xyhm, const float2* __
     interior = true;
   } else {
     float dmin = __int_as_float(0x7f800000);
-    for (int p = 0; p < P.n_planes; p++)
-      dmin = fminf(dmin, __fadd_rn(__fadd_rn(__fmul_rn(P.planes[p][0], me.x), __fmul_rn(P.planes[p][1], me.y)), P.planes[p][2]));
+    for (int p = 0; p < sdf_count(P); p++) dmin = fminf(dmin, sdf_probe(P, p, me.x, me.y));
     if (!P.boundary_is_fluid_surface && dmin < me.z * 1.5f) {
       interior = true;
     } else {

@@ -23,10 +23,6 @@ __device__ __forceinline__ float lut_get(const float* __restrict__ data, float x
   return __fadd_rn(__fmul_rn(data[idx], __fsub_rn(1.f, t)), __fmul_rn(data[idx + 1], t));
 }
 
-__device__ __forceinline__ float plane_probe(const float* pl, float x, float y) {  // SdfPlane::probe sdf_plane.rs:36-38
-  return __fadd_rn(__fadd_rn(__fmul_rn(pl[0], x), __fmul_rn(pl[1], y)), pl[2]);
-}
-
 // BoundaryWinchenbach2020::update_after_advect (boundary_winchenbach2020.rs:58-152): Σ λ·penalty and Σ ∇(λ·penalty)
 __device__ __forceinline__ void boundary_terms(const PackedParams& P, const float* __restrict__ lut, float x, float y, float h,
                                                float& lam_sum, float& gx_sum, float& gy_sum) {
@@ -34,13 +30,13 @@ __device__ __forceinline__ void boundary_terms(const PackedParams& P, const floa
   const float sr = __fmul_rn(h, 2.f);
   const float eps = P.sdf_gradient_eps;
   const float inv_2eps = __fdiv_rn(1.f, __fmul_rn(2.f, eps));
-  for (int s = 0; s < P.n_planes; s++) {
-    const float* pl = P.planes[s];
-    float d = __fdiv_rn(plane_probe(pl, x, y), sr);
+  const int ns = sdf_count(P);
+  for (int s = 0; s < ns; s++) {
+    float d = __fdiv_rn(sdf_probe(P, s, x, y), sr);
     if (!(d < 1.f)) continue;
     // finite_diff_gradient sdf.rs:50-62
-    float gx = __fmul_rn(__fsub_rn(plane_probe(pl, __fadd_rn(x, eps), y), plane_probe(pl, __fsub_rn(x, eps), y)), inv_2eps);
-    float gy = __fmul_rn(__fsub_rn(plane_probe(pl, x, __fadd_rn(y, eps)), plane_probe(pl, x, __fsub_rn(y, eps))), inv_2eps);
+    float gx = __fmul_rn(__fsub_rn(sdf_probe(P, s, __fadd_rn(x, eps), y), sdf_probe(P, s, __fsub_rn(x, eps), y)), inv_2eps);
+    float gy = __fmul_rn(__fsub_rn(sdf_probe(P, s, x, __fadd_rn(y, eps)), sdf_probe(P, s, x, __fsub_rn(y, eps))), inv_2eps);
     float gn = __fsqrt_rn(dist_sq_exact(gx, gy));
     if (gn < 0.00001f) continue;
     gx = __fdiv_rn(gx, gn); gy = __fdiv_rn(gy, gn);

@@ -17,6 +17,7 @@
 #include "../../include/asph.h"
 
 #define ASPH_MAX_LEVELS 12
+#define ASPH_POLY_DEV 16  // polygon vertices the device code takes (a box has 4)
 #define ASPH_RETRY_LISTS 1000  // internal: the neighbour pool was too small; grow it and redo the step from the neighbour pass
 #define ASPH_SLACK 1.00390625f  // 1 + 1/256: cell / search-radius safety factor against fp32 binning error
 
@@ -104,6 +105,9 @@ struct PackedParams {  // SimulationParams rounded once to fp32 (what serde does
       allow_merge_size_diff, fail_on_missing_split_pattern;
   int n_planes;
   float planes[ASPH_MAX_PLANES][3];
+  // AnalyticUnderestimate: one polygon SDF (Sdf2D with one connected component, sdf/sdf2d.rs); 0 vertices = planes
+  int n_poly;
+  float poly_pt[ASPH_POLY_DEV][2], poly_dir[ASPH_POLY_DEV][2], poly_pn[ASPH_POLY_DEV][2];
 };
 
 template <class T> struct DevBuf {
@@ -317,6 +321,40 @@ __device__ __forceinline__ float h_from_mass(float m, float rho0) {
 }
 // strict predicate |x_ij|^2 < ((h_i + h_j) * 0.5 * f)^2 without FMA contraction
 // (neighborhood_search.rs:141-146, 63-67)
+// Boundary SDFs of the semi-analytic handler.  Planes: SdfPlane::probe (sdf/sdf_plane.rs:36-38).  Polygon: Sdf2D::probe
+// (sdf/sdf2d.rs:73-141, 179-210) — nearest edge or vertex, positive on the air side; same operation order as the
+// reference and the oracle, no contraction.
+__device__ __forceinline__ int sdf_count(const PackedParams& P) { return P.n_poly > 0 ? 1 : P.n_planes; }
+__device__ __forceinline__ float sdf_probe(const PackedParams& P, int s, float x, float y) {
+  if (P.n_poly == 0) {
+    const float* pl = P.planes[s];
+    return __fadd_rn(__fadd_rn(__fmul_rn(pl[0], x), __fmul_rn(pl[1], y)), pl[2]);
+  }
+  const int np = P.n_poly;
+  float min_dist_sq = __int_as_float(0x7f800000);
+  bool is_line = false;
+  float line_dist = 0.f, pdx_c = 0.f, pdy_c = 0.f, pdist_sq = 0.f;
+  int pidx = 0;
+  for (int k = 0; k < np; k++) {
+    const int k1 = k + 1 == np ? 0 : k + 1;
+    const float lx = __fsub_rn(P.poly_pt[k1][0], P.poly_pt[k][0]), ly = __fsub_rn(P.poly_pt[k1][1], P.poly_pt[k][1]);
+    const float len_sq = __fadd_rn(__fmul_rn(lx, lx), __fmul_rn(ly, ly));
+    const float dx = P.poly_dir[k][0], dy = P.poly_dir[k][1];
+    const float px = __fsub_rn(x, P.poly_pt[k][0]), py = __fsub_rn(y, P.poly_pt[k][1]);
+    const float proj = __fadd_rn(__fmul_rn(px, dx), __fmul_rn(py, dy));
+    if (proj > 0.f && __fmul_rn(proj, proj) < len_sq) {
+      const float dl = __fadd_rn(__fmul_rn(px, -dy), __fmul_rn(py, dx));  // dot with the left normal (-dy, dx)
+      const float dl2 = __fmul_rn(dl, dl);
+      if (dl2 < min_dist_sq) { is_line = true; line_dist = dl; min_dist_sq = dl2; }
+    }
+    const float c = __fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py));
+    if (c < min_dist_sq) { is_line = false; pidx = k; pdx_c = px; pdy_c = py; pdist_sq = c; min_dist_sq = c; }
+  }
+  if (is_line) return line_dist;
+  const float sg = __fadd_rn(__fmul_rn(P.poly_pn[pidx][0], pdx_c), __fmul_rn(P.poly_pn[pidx][1], pdy_c)) >= 0.f ? 1.f : -1.f;
+  return __fmul_rn(__fsqrt_rn(pdist_sq), sg);
+}
+
 __device__ __forceinline__ float dist_sq_exact(float dx, float dy) {
   return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
 }

@@ -84,15 +84,16 @@ def _compare_step_fields(g, o, tol, fields):
     return worst
 
 
-def _single_step_uniform(asph, cuda_lib, oracle32, default_params, solver, spacing=0.02, vel_scale=0.05):
+def _single_step_uniform(asph, cuda_lib, oracle32, default_params, solver, spacing=0.02, vel_scale=0.05,
+                         boundary_kind="AnalyticOverestimate", block_pos=(-0.95, -0.9)):
     """One physics step, uniform h, level estimation off (the reference's 'Uniform SPH' recipe,
     media/motivation-video.yaml:42-57): every per-particle quantity against the oracle."""
-    sc = asph.SceneConfig.dam_break(spacing)
+    sc = asph.SceneConfig.dam_break(spacing, pos=block_pos)
     pos, vel, mass = asph.scene_particles(sc)
     rng = np.random.default_rng(1)
     vel = (rng.standard_normal(vel.shape) * vel_scale).astype(np.float32)
-    params = _uniform_params(default_params, pressure_solver_method=solver)
-    b = asph.scene_boundary(sc, "AnalyticOverestimate")
+    params = _uniform_params(default_params, pressure_solver_method=solver, init_boundary_handler=boundary_kind)
+    b = asph.scene_boundary(sc, boundary_kind)
     g, o = _pair(asph, cuda_lib, oracle32, params, pos, vel, mass, b)
     dg = g.single_step_without_adaptivity(); do = o.single_step_without_adaptivity()
     assert dg == do  # dt is an exact min-reduction
@@ -125,6 +126,30 @@ def test_single_step_uniform_many_tiles_per_block(asph, cuda_lib, oracle32, defa
     solver.cu), so that each block walks ~50 tiles through its two-stage copy pipeline."""
     monkeypatch.setenv("ASPH_SWEEP_GRID", "2")
     _single_step_uniform(asph, cuda_lib, oracle32, default_params, solver, spacing=0.01)
+
+
+@pytest.mark.parametrize("solver", ["HybridDFSPH", "IISPH"])
+def test_single_step_polygon_boundary(asph, cuda_lib, oracle32, default_params, solver):
+    """`init_boundary_handler: AnalyticUnderestimate` (sdf/sdf2d.rs: one polygon SDF instead of four planes; used by
+    media/video-viscosity.yaml): the block sits in the corner, within the support radius of the floor and the wall, so
+    edges and the corner vertex both decide λ, ∇λ and through them every other field."""
+    _single_step_uniform(asph, cuda_lib, oracle32, default_params, solver, spacing=0.02, boundary_kind="AnalyticUnderestimate",
+                         block_pos=(-0.985, -0.985))
+
+
+def test_trajectory_polygon_boundary_with_resampling(asph, cuda_lib, oracle32, default_params, split_patterns):
+    """C1 (default-config + default-scene, level set and resampling on) with the polygon boundary, 20 steps."""
+    sc = _scene(asph, "default-scene.yaml")
+    params = default_params.replace(init_boundary_handler="AnalyticUnderestimate")
+    g = asph.init_fluid_sim(params, sc, split_patterns, lib=cuda_lib)
+    o = asph.init_fluid_sim(params, sc, split_patterns, lib=oracle32)
+    for k in range(20):
+        g.single_step(); o.single_step()
+        assert g.num_fluid_particles() == o.num_fluid_particles(), k
+    err = np.abs(g.get_field("position") - o.get_field("position")).max() / 2.0
+    print(f"C1 polygon boundary, 20 steps: N = {g.num_fluid_particles()}, |gpu - oracle32| / L = {err:.3e}")
+    assert err <= 1e-5
+    g.close(); o.close()
 
 
 def test_full_size_step_against_oracle(asph, cuda_lib, oracle32, default_params):
