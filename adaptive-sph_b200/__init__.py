@@ -11,9 +11,11 @@ from .scene import (SceneConfig, add_fluid_block, init_simulation_params, scene_
 from .distributed import (DistributedFluidSimulation, broadcast_unique_id, gather_by_global_index, owner_of, share_range,
                           slab_bounds_from_histogram)
 from .split_patterns import SplitPatterns, load_split_patterns_from_file
+from .vtk import VtkExporter, init_fluid_sim_from_vtk, read_vtk_file, write_vtk_file, write_vtk_file2
 
 __all__ = ["AsphError", "FluidSimulation", "StatisticsRecorder", "init_fluid_sim", "load_library", "FIELDS",
            "LEVEL_INTERIOR", "PRODUCT_LIB", "SimulationParams", "merge_overwrite", "SceneConfig", "add_fluid_block",
            "init_simulation_params", "scene_boundary", "scene_particles", "scene_particle_count", "SplitPatterns",
            "load_split_patterns_from_file", "DistributedFluidSimulation", "broadcast_unique_id", "gather_by_global_index",
-           "owner_of", "share_range", "slab_bounds_from_histogram"]
+           "owner_of", "share_range", "slab_bounds_from_histogram", "VtkExporter", "init_fluid_sim_from_vtk", "read_vtk_file",
+           "write_vtk_file", "write_vtk_file2"]

