@@ -216,6 +216,7 @@ struct asph_sim {
   uint64_t pc_calls[ASPH_PC_COUNT] = {0};
   cudaEvent_t ev_begin[ASPH_PC_COUNT], ev_end[ASPH_PC_COUNT];
   int sm_count = 148;
+  bool sweep_attr_done = false;  // dynamic shared-memory limit of the sweep kernels raised on this handle's device
   bool ctl_seen = false;  // ctl_host holds a control block read back from the device (possibly of the previous step)
   std::string last_error;
   uint64_t kernel_launches = 0;

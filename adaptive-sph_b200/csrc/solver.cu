@@ -821,8 +821,7 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
   const size_t smem = 2 * (hmwin ? sizeof(SweepStage<true>) : sizeof(SweepStage<false>));
   uint32_t grid = sweep_grid(n, sim->sm_count, (hmwin || dist_p2p(sim)) ? 3 : 4);
   if (const char* e = getenv("ASPH_SWEEP_GRID")) grid = std::max(1u, std::min(grid, uint32_t(atoi(e))));  // test hook: few blocks => many tiles per block
-  static bool attr_done = false;
-  if (!attr_done) {
+  if (!sim->sweep_attr_done) {  // per handle: function attributes belong to the device the handle lives on
     const int big = int(2 * sizeof(SweepStage<true>)), small = int(2 * sizeof(SweepStage<false>));
     CUDA_TRY(cudaFuncSetAttribute(k_sweep<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -832,7 +831,7 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
     CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(k_sweep<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
     CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
-    attr_done = true;
+    sim->sweep_attr_done = true;
   }
   const bool p2p = dist_p2p(sim);
   SweepArgs A;
