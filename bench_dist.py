@@ -97,7 +97,6 @@ def run(args, A, rank, world):
     n_own = sim.num_fluid_particles()
     cap = int(n_own * 1.25) + 65536
     hp, _a = pinned((cap, 2)); hv, _b = pinned((cap, 2)); hm, _c = pinned((cap,))
-    op, _d = pinned((cap, 2)); ov, _e = pinned((cap, 2)); om, _f = pinned((cap,))
     sim.get_field("position", out=hp[:n_own]); sim.get_field("velocity", out=hv[:n_own]); sim.get_field("mass", out=hm[:n_own])
     fence()
     e2e_s, e2e_owned, h2d, d2h, in_window, k = 0.0, 0, 0, 0, 0, 0
@@ -119,10 +118,10 @@ def run(args, A, rank, world):
             in_window = window
             continue
         n_own = sim.num_fluid_particles()                        # migration may have changed the owned set
-        sim.get_field("position", out=op[:n_own]); sim.get_field("velocity", out=ov[:n_own]); sim.get_field("mass", out=om[:n_own])
+        # D2H of the result into the same host buffers: this step's output is the next step's input
+        sim.get_field("position", out=hp[:n_own]); sim.get_field("velocity", out=hv[:n_own]); sim.get_field("mass", out=hm[:n_own])
         e2e_s += time.perf_counter() - t1
         h2d += n_in * 20; d2h += n_own * 20; e2e_owned += n_in
-        hp[:n_own] = op[:n_own]; hv[:n_own] = ov[:n_own]; hm[:n_own] = om[:n_own]
         k += 1; in_window += 1
     fence()
 
