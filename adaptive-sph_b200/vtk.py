@@ -20,7 +20,6 @@ Added: `read_vtk_file` and `init_fluid_sim_from_vtk` — the persistent state of
 (SURVEY.md §8a), all three are in a snapshot as exact fp32, so a snapshot is a checkpoint: a simulation restarted from
 it continues bit for bit like the uninterrupted one (tests/test_vtk.py).  The reference has no checkpoint / resume.
 """
-import json
 import os
 
 import numpy as np

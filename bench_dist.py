@@ -11,7 +11,7 @@ import json
 import os
 import time
 
-import numpy as np
+
 
 
 def run(args, A, rank, world):
