@@ -304,6 +304,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # all host threads the process may use: torchrun pins OMP_NUM_THREADS to 1 for its workers, which would turn the
+    # reference arm into a single-core run (the OpenMP runtime reads the variable when the oracle library is loaded)
+    try:
+        os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import asph_b200 as A
     oracle_path = os.path.join(ROOT, "oracle", "liboracle_f32.so")
     if not os.path.exists(oracle_path):
