@@ -11,6 +11,7 @@ from .scene import (SceneConfig, add_fluid_block, init_simulation_params, scene_
 from .distributed import (DistributedFluidSimulation, broadcast_unique_id, gather_by_global_index, owner_of, share_range,
                           slab_bounds_from_histogram)
 from .split_patterns import SplitPatterns, load_split_patterns_from_file
+from .export_jobs import ImageExportConfig, JobError, export_simulation_image, load_job_file, resolve_job, run_job
 from .vtk import VtkExporter, init_fluid_sim_from_vtk, read_vtk_file, write_vtk_file, write_vtk_file2
 
 __all__ = ["AsphError", "FluidSimulation", "StatisticsRecorder", "init_fluid_sim", "load_library", "FIELDS",
@@ -18,4 +19,5 @@ __all__ = ["AsphError", "FluidSimulation", "StatisticsRecorder", "init_fluid_sim
            "init_simulation_params", "scene_boundary", "scene_particles", "scene_particle_count", "SplitPatterns",
            "load_split_patterns_from_file", "DistributedFluidSimulation", "broadcast_unique_id", "gather_by_global_index",
            "owner_of", "share_range", "slab_bounds_from_histogram", "VtkExporter", "init_fluid_sim_from_vtk", "read_vtk_file",
-           "write_vtk_file", "write_vtk_file2"]
+           "write_vtk_file", "write_vtk_file2", "ImageExportConfig", "JobError", "export_simulation_image", "load_job_file",
+           "resolve_job", "run_job"]

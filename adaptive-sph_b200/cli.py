@@ -5,7 +5,8 @@ Mirrors the clap definition of platform/desktop/main_loop.rs:25-103 for the `run
                                      [-w/--statistics-path F]
 and its flow (main_loop.rs:105-189, 209-358): read YAML -> optional key-wise overwrite -> init_simulation_params ->
 load split patterns -> init_fluid_sim -> loop { single_step } until the simulated time reaches --max-seconds.
-`image` (Cairo/ffmpeg export) and `generate-split-patterns` (offline optimiser) are out of scope.
+`image JOB.yaml...` runs the reference's batch export jobs (animation/mod.rs:28-288) with VTK snapshots in place of the
+Cairo/ffmpeg rendering (export_jobs.py); `generate-split-patterns` (offline optimiser) is out of scope.
 Added: --max-steps, --dump state.npz.  The CUDA library is the only backend; `main(argv, lib=...)` lets a test harness
 bind another library exporting the same C ABI.
 """
@@ -42,15 +43,33 @@ def build_parser():
     run.add_argument("--vtk-every", type=int, default=1, help="snapshot every n-th step")
     run.add_argument("--restart-vtk", default=None, help="start from this VTK snapshot instead of the scene's blocks (the scene still gives the boundary)")
     run.add_argument("-q", "--quiet", action="store_true")
-    for name in ("image", "generate-split-patterns"):
-        sub.add_parser(name, help="not available in the headless B200 build")
+    img = sub.add_parser("image", help="Run batch export jobs (VTK snapshots instead of rendered images)")
+    img.add_argument("job_files", metavar="JOB_FILE", nargs="+")
+    img.add_argument("--out-dir", default=None, help="default: next to the job file, as the reference does")
+    img.add_argument("--only", type=int, action="append", default=None, help="run only job number K of each file (repeatable)")
+    img.add_argument("--max-steps", type=int, default=None, help="stop every job after n steps (regression runs)")
+    img.add_argument("--split-patterns", default=None)
+    img.add_argument("-q", "--quiet", action="store_true")
+    sub.add_parser("generate-split-patterns", help="not available in the headless B200 build")
     return ap
 
 
 def main(argv=None, lib=None):
     args = build_parser().parse_args(argv)
+    if args.command == "image":
+        from .export_jobs import JobError, export_simulation_image
+        if lib is None:
+            lib = load_library()
+        try:
+            done = export_simulation_image(args.job_files, lib, out_dir=args.out_dir, only=args.only, max_steps=args.max_steps,
+                                           quiet=args.quiet, split_patterns_path=args.split_patterns)
+        except JobError as e:
+            print(f"job failed: {e}", file=sys.stderr)
+            return 1
+        print(f"{len(done)} job(s), {sum(1 for m in done if m['finished'])} reached their export time")
+        return 0
     if args.command != "run":
-        print(f"`{args.command}` is out of scope of this build (rendering / offline pattern optimiser)", file=sys.stderr)
+        print(f"`{args.command}` is out of scope of this build (offline pattern optimiser)", file=sys.stderr)
         return 2
     if args.max_seconds is None and args.max_steps is None:
         print("headless run needs --max-seconds or --max-steps", file=sys.stderr)

@@ -116,10 +116,11 @@ def distance_to_boundary(boundary, pos):
     return out.astype(np.float32)
 
 
-def write_vtk_file(path, sim, params=None):
+def write_vtk_file(path, sim, params=None, positions=None):
     """vtk_exporter.rs:81-167 for a FluidSimulation (binding.py).  Call it where the reference's exporter does: after
     `single_step_without_adaptivity`, before `single_step_adaptivity` (platform/desktop/animation/mod.rs:138-273) —
-    the per-step fields describe the particle set of the physics step."""
+    the per-step fields describe the particle set of the physics step.  `positions` replaces the point coordinates
+    (the batch exporter's interpolated frame positions, animation/mod.rs:193-210)."""
     from .binding import AsphError
 
     def opt(name):
@@ -128,7 +129,7 @@ def write_vtk_file(path, sim, params=None):
         except AsphError:
             return None
 
-    pos = sim.get_field("position")
+    pos = sim.get_field("position") if positions is None else np.asarray(positions, np.float32)
     n = len(pos)
     data_ft, data_vec, data_u8 = [], [], []
     for vtk_name, field in (("density", "density"), ("density_error", "density_error"), ("density_error2", None),

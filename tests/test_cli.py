@@ -38,7 +38,7 @@ def test_unknown_overwrite_key_is_an_error(asph, oracle32, tmp_path):
 
 
 def test_out_of_scope_subcommands():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "asph_b200.py"), "image"], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "asph_b200.py"), "generate-split-patterns"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 2
 
 
