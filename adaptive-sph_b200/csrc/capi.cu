@@ -72,7 +72,11 @@ int pack_params(asph_sim* sim, const asph_params* p) {
   if (p->support_length_estimation != ASPH_H_FROM_MASS) return unsupported("support_length_estimation != FromMass");
   if (p->constrain_neighborhood_count) return unsupported("constrain_neighborhood_count");
   if (p->level_estimation_method == ASPH_LEVEL_CENTER_DIFF) return unsupported("level_estimation_method CenterDiff");
-  if (p->operator_discretization == ASPH_OP_WINCHENBACH2020) return unsupported("operator_discretization Winchenbach2020");
+  // Modes whose kernels were written after the GPU budget of the round ran out and have not passed their parity tests
+  // on hardware yet (tests/test_zz_unverified_modes.py) stay off unless the caller asks for them explicitly.
+  const bool unverified = getenv("ASPH_UNVERIFIED_MODES") != nullptr && atoi(getenv("ASPH_UNVERIFIED_MODES")) != 0;
+  if (p->operator_discretization == ASPH_OP_WINCHENBACH2020 && !unverified)
+    return unsupported("operator_discretization Winchenbach2020 (kernels not yet verified on hardware; ASPH_UNVERIFIED_MODES=1 enables them)");
   if (p->pressure_solver_method == ASPH_SOLVER_IISPH2) return unsupported("pressure_solver_method IISPH2");
   if (p->viscosity_type == ASPH_VISC_XSPH) return unsupported("viscosity_type XSPH (todo!() in the reference)");
   if (p->level_estimation_after_advection) return unsupported("level_estimation_after_advection");
@@ -495,7 +499,7 @@ void asph_destroy(asph_sim* sim) {
   sim->xyhm.release(); sim->packA.release(); sim->pconst.release(); sim->h_tmp.release(); sim->rho.release(); sim->lam_sum.release();
   sim->nrm.release(); sim->gB.release(); sim->lam_grad.release(); sim->key.release(); sim->cellcount.release(); sim->cellstart.release();
   sim->order.release(); sim->scan_sums.release(); sim->cnt.release(); sim->cnt_ext.release(); sim->far_idx.release(); sim->far_cnt.release(); sim->slice_base.release();
-  sim->nbpool.release(); sim->hm.release(); sim->size_class.release(); sim->flags.release(); sim->merge_partner.release();
+  sim->nbpool.release(); sim->hm.release(); sim->hv.release(); sim->size_class.release(); sim->flags.release(); sim->merge_partner.release();
   sim->cand.release(); for (int k = 0; k < 4; k++) sim->scratch_u[k].release();
   sim->merge_counter.release(); sim->stamp.release(); sim->stampkey.release(); sim->scratch_f.release(); sim->lut.release(); sim->split_pos.release();
   sim->split_off.release(); sim->blockstats.release();

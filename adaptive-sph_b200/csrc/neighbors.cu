@@ -229,8 +229,10 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
   const float ax = Sx / rho2 + Bc * Gx, ay = Sy / rho2 + Bc * Gy;
   const float bx = Sx / rho + rho0 * Gx / rho, by = Sy / rho + rho0 * Gy / rho;
   const float aii = (ax * bx + ay * by) + (me.w * Q) / (rho2 * rho);
-  if (!isfinite(aii)) err |= ERRF_NONFINITE;
-  else if (aii < 0.f) err |= ERRF_NEG_AII;
+  if (P.opdisc != ASPH_OP_WINCHENBACH2020) {  // that operator's diagonal needs the neighbours' densities: k_aii_w2020
+    if (!isfinite(aii)) err |= ERRF_NONFINITE;
+    else if (aii < 0.f) err |= ERRF_NEG_AII;
+  }
   if (err && !(gid && (gid[i] & ASPH_GHOST_BIT))) atomicOr(&ctl->error_flags, err);  // a ghost's neighbourhood is incomplete by design
   rho_out[i] = rho;
   gB_out[i] = make_float2(Bc * Gx, Bc * Gy);
@@ -238,6 +240,46 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
   lam_sum_out[i] = lam;
   lam_grad_out[i] = make_float2(Gx, Gy);
   nrm_out[i] = make_float2(Nx, Ny);  // Σ_j ∇W_ij; K3 scales it by -(m_i/ρ0)
+}
+
+// Winchenbach2020 operator.  Its divergence weights every neighbour with m_j / rho_j instead of
+// m_j / rho_i (simulation.rs:1571-1575) and drops rho_b / rho_i from the boundary term (boundary_winchenbach2020.rs:
+// 207-213), so the diagonal (boundary_winchenbach2020.rs:236-269)
+//   a_ii = (S / rho_i^2 + rho_b G / rho_i^2) . (T + G) + m_i U / rho_i^2,
+//   S = sum m_j gradW,  T = sum (m_j / rho_j) gradW,  U = sum (m_j / rho_j) |gradW|^2
+// needs the neighbours' densities: a second pass over the 2h columns after the density pass.  It also writes
+// hv = {h, m / rho}, which the divergence passes (K13, K15) gather in place of {h, m}, and pconst.xy = G.
+__global__ void __launch_bounds__(kThreads)
+k_aii_w2020(uint32_t n, NbLists L, const float4* __restrict__ xyhm, const float* __restrict__ rho, const float2* __restrict__ lam_grad,
+            float rho0, float4* __restrict__ pconst, float2* __restrict__ hv, StepCtl* ctl, const uint32_t* __restrict__ gid) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 me = xyhm[i];
+  const float rho_i = rho[i];
+  hv[i] = make_float2(me.z, me.w / rho_i);
+  const NbCol col(L, i);
+  float Sx = 0.f, Sy = 0.f, Tx = 0.f, Ty = 0.f, U = 0.f;
+  for (uint32_t k = 0; k < col.cn; k++) {
+    const uint32_t j = col.get(k);
+    const float4 o = __ldg(&xyhm[j]);
+    const float dx = me.x - o.x, dy = me.y - o.y;
+    const float d2 = dx * dx + dy * dy;
+    float w, g;
+    pair_wg(d2, (me.z + o.z) * 0.5f, w, g);
+    const float c = o.w * g, v = o.w / __ldg(&rho[j]);
+    Sx += c * dx; Sy += c * dy;
+    Tx += (v * g) * dx; Ty += (v * g) * dy;
+    U += v * (g * g * d2);
+  }
+  const float2 G = lam_grad[i];
+  const float rho2 = rho_i * rho_i;
+  const float ax = Sx / rho2 + (rho0 / rho2) * G.x, ay = Sy / rho2 + (rho0 / rho2) * G.y;
+  const float aii = (ax * (Tx + G.x) + ay * (Ty + G.y)) + (me.w * U) / rho2;
+  unsigned int err = 0;
+  if (!isfinite(aii)) err |= ERRF_NONFINITE;
+  else if (aii < 0.f) err |= ERRF_NEG_AII;
+  if (err && !(gid && (gid[i] & ASPH_GHOST_BIT))) atomicOr(&ctl->error_flags, err);
+  pconst[i] = make_float4(G.x, G.y, aii, 0.f);
 }
 
 }  // namespace
@@ -260,6 +302,14 @@ int launch_neighbors(asph_sim* sim, float f_ext, float f_near) {
                                                     sim->dist ? sim->refid[sim->cur].p : nullptr);
   LAUNCH_CHECK();
   if (sim->dist) TRY(dist_halo(sim, sim->rho.p, 4));  // K12 / K17 read the neighbours' densities
+  if (op_w2020(sim)) {
+    CUDA_TRY(sim->hv.ensure(sim->cap));
+    NbLists L;
+    L.pool = sim->nbpool.p; L.slice_base = sim->slice_base.p; L.cnt = sim->cnt.p; L.cnt_ext = sim->cnt_ext.p; L.far_idx = sim->far_idx.p; L.far_cnt = sim->far_cnt.p;
+    k_aii_w2020<<<blocks, kThreads, 0, sim->stream>>>(n, L, sim->xyhm.p, sim->rho.p, sim->lam_grad.p, sim->pp.rest_density, sim->pconst.p,
+                                                      sim->hv.p, sim->ctl, sim->dist ? sim->refid[sim->cur].p : nullptr);
+    LAUNCH_CHECK();
+  }
   sim->lists_valid = true;  // provisional: the caller checks ERRF_LIST_CAPACITY at its next synchronisation (neighbors_grow)
   return ASPH_OK;
 }

@@ -182,6 +182,7 @@ struct asph_sim {
   DevBuf<uint32_t> cnt, cnt_ext, slice_base, far_idx, far_cnt;
   DevBuf<uint16_t> nbpool;  // sliced-ELL neighbour lists (lists.cuh)
   DevBuf<float2> hm;        // {h, m} per particle: second gather of the adaptive-h pair passes
+  DevBuf<float2> hv;        // {h, m / rho}: what the divergence passes gather instead under the Winchenbach2020 operator
   int predicted_sweeps[2] = {1, 1};  // sweeps of the divergence / density solve in the previous step
   DevBuf<uint8_t> size_class, flags;  // flags: bit0 surface, bit1 insufficient neighbours
   DevBuf<uint32_t> merge_partner, front[2], cand, work[2], scratch_u[4];
@@ -272,6 +273,7 @@ int launch_exclusive_scan(asph_sim* sim, const uint32_t* in, uint32_t* out, cons
                           uint32_t n_max);  // out[i] = sum(in[0..i)) for i < *n_dev + n_add
 // neighbors.cu
 int launch_neighbors(asph_sim* sim, float f_ext, float f_near);
+inline bool op_w2020(const asph_sim* sim) { return sim->pp.opdisc == ASPH_OP_WINCHENBACH2020; }
 int neighbors_grow(asph_sim* sim);
 // solver.cu
 int launch_viscosity(asph_sim* sim);

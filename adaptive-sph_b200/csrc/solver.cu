@@ -354,10 +354,12 @@ k_viscosity(uint32_t n, NbLists L, const float4* __restrict__ xv_in, const float
 __global__ void __launch_bounds__(kThreads)
 k_source(uint32_t n, NbLists L, const float4* __restrict__ xv, const float2* __restrict__ hm, const float* __restrict__ rho,
          float4* __restrict__ pconst, float4* __restrict__ packP0, float4* __restrict__ packA, const StepCtl* __restrict__ ctl,
-         float rho0, int kind) {
+         float rho0, int kind, int w2020) {
   __shared__ float4 s_pack[kSlots];
   __shared__ float2 s_hm[kSlots];
-  const bool uni = ctl->hmin == ctl->hmax;
+  // Winchenbach2020 operator: `hm` is {h, m / rho} (k_aii_w2020), every pair carries its own weight m_j / rho_j, and
+  // neither the pair sum nor the boundary term (pconst.xy = G) is divided by rho_i (simulation.rs:1571-1575)
+  const bool uni = ctl->hmin == ctl->hmax && !w2020;
   const bool pairs = kind != 1;
   PairWindow W;
   if (pairs) W.issue<false>(n, uni, xv, hm, nullptr, s_pack, s_hm, nullptr, L);
@@ -378,10 +380,10 @@ k_source(uint32_t n, NbLists L, const float4* __restrict__ xv, const float2* __r
     const float scale = uni ? for_each_pair<HM_UNI, false>(C, W, xv, hm, nullptr, me.x, me.y, own.x, own.y, body)
                             : for_each_pair<HM_WIN, false>(C, W, xv, hm, nullptr, me.x, me.y, own.x, own.y, body);
     sum *= scale;
-    const float div = sum / rho_i - (me.z * pc.x + me.w * pc.y);
+    const float div = (w2020 ? sum : sum / rho_i) - (me.z * pc.x + me.w * pc.y);
     s = -div / dt;
   }
-  if (kind != 0) s += -(rho0 - rho_i) / (rho_i * dt * dt);
+  if (kind != 0) s += -(rho0 - rho_i) / ((w2020 ? rho0 : rho_i) * dt * dt);  // next_density_estimate, simulation.rs:1633-1748
   pc.w = s;
   pconst[i] = pc;
   packP0[i] = make_float4(me.x, me.y, 0.f, 0.f);
@@ -498,9 +500,12 @@ struct SweepArgs {
   PeerArgs peer;  // multi-GPU peer-memory path: what this pass has to wait for
 };
 
-template <int PASS, bool HMWIN, bool PEER>
+// W2020 (update pass under the Winchenbach2020 operator): `hm` is {h, m / rho} (k_aii_w2020), so
+// every pair carries its own weight m_j / rho_j, and the pair sum is not divided by rho_i (simulation.rs:1571-1575).
+template <int PASS, bool HMWIN, bool PEER, bool W2020 = false>
 __global__ void __launch_bounds__(kThreads, (HMWIN || PEER) ? 3 : 4)
 k_sweep(const SweepArgs A) {
+  static_assert(!W2020 || (PASS == 1 && HMWIN), "the Winchenbach2020 variant is an update pass with the {h, m / rho} window");
   extern __shared__ __align__(16) unsigned char sweep_smem[];
   typedef SweepStage<HMWIN> Stage;
   Stage* stages = reinterpret_cast<Stage*>(sweep_smem);
@@ -514,7 +519,7 @@ k_sweep(const SweepArgs A) {
   const float4* __restrict__ packP = odd ? A.P1 : A.P0;
   float4* __restrict__ packP_next = odd ? A.P0w : A.P1w;
   const float4* __restrict__ pack = PASS == 0 ? packP : A.packA;  // what the pass gathers
-  const bool uni = ctl->hmin == ctl->hmax;
+  const bool uni = !W2020 && ctl->hmin == ctl->hmax;
   const float dt = ctl->dt;
   const float err_scale = A.density_mode ? dt * dt : dt;  // predicted density / divergence error per unit of residual
 
@@ -666,7 +671,7 @@ k_sweep(const SweepArgs A) {
           // reciprocals by the SFU (1 ulp): the relaxed update does not need correctly rounded quotients, and three
           // IEEE divisions would be a quarter of this thread's instructions outside the pair loop
           inv_rho = fast_rcp(rho_i);
-          const float Ap = (sum * scale) * inv_rho - (me.z * pc.x + me.w * pc.y);
+          const float Ap = (sum * scale) * (W2020 ? 1.f : inv_rho) - (me.z * pc.x + me.w * pc.y);
           const float resid = pc.w - Ap;
           pn = fmaf(A.omega * resid, fast_rcp(pc.z), p_old);
           if (!isfinite(pn)) bad = true;  // covers a non-finite Ap as well
@@ -793,8 +798,9 @@ int launch_source(asph_sim* sim, int kind) {
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
   k_solver_reset<<<1, 64, 0, sim->stream>>>(sim->ctl);
   LAUNCH_CHECK();
-  k_source<<<blocks, kThreads, 0, sim->stream>>>(n, lists_of(sim), sim->xv[sim->xv_cur].p, sim->hm.p, sim->rho.p, sim->pconst.p,
-                                                 sim->packP[0].p, sim->packA.p, sim->ctl, sim->pp.rest_density, kind);
+  const bool w2020 = op_w2020(sim);
+  k_source<<<blocks, kThreads, 0, sim->stream>>>(n, lists_of(sim), sim->xv[sim->xv_cur].p, w2020 ? sim->hv.p : sim->hm.p, sim->rho.p, sim->pconst.p,
+                                                 sim->packP[0].p, sim->packA.p, sim->ctl, sim->pp.rest_density, kind, w2020 ? 1 : 0);
   LAUNCH_CHECK();
   sim->p_cur = 0;
   return ASPH_OK;
@@ -817,7 +823,8 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
   const int max_sweeps = sim->pp.max_iters + 1;
   // stage layout of the persistent sweep kernels: with room for the {h, m} window unless the last control block the
   // host has seen says h is uniform (a wrong guess only costs speed, see k_sweep)
-  const bool hmwin = !(sim->ctl_seen && sim->ctl_host->hmin == sim->ctl_host->hmax);
+  const bool w2020 = op_w2020(sim);  // its update pass always gathers {h, m / rho}
+  const bool hmwin = w2020 || !(sim->ctl_seen && sim->ctl_host->hmin == sim->ctl_host->hmax);
   const size_t smem = 2 * (hmwin ? sizeof(SweepStage<true>) : sizeof(SweepStage<false>));
   uint32_t grid = sweep_grid(n, sim->sm_count, (hmwin || dist_p2p(sim)) ? 3 : 4);
   if (const char* e = getenv("ASPH_SWEEP_GRID")) grid = std::max(1u, std::min(grid, uint32_t(atoi(e))));  // test hook: few blocks => many tiles per block
@@ -831,6 +838,8 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
     CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(k_sweep<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
     CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
+    CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
+    CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
     sim->sweep_attr_done = true;
   }
   const bool p2p = dist_p2p(sim);
@@ -848,6 +857,7 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
       if (time_it) { tm.e0 = kt_event(sim); tm.e1 = kt_event(sim); tm.e1b = kt_event(sim); tm.e2 = kt_event(sim); cudaEventRecord(tm.e0, st); }
       A.sweep = launched;
       if (launched > 0) {  // sweep 0: a^p = 0 was written by k_source
+        A.hm = sim->hm.p;
         A.peer = dist_peer_args(sim, true, !p2p, 0, false);  // waits for the previous sweep's p' ghosts; publishes a^p
         if (p2p) { if (hmwin) k_sweep<0, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, true><<<grid, kThreads, smem, st>>>(A); }
         else { if (hmwin) k_sweep<0, true, false><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, false><<<grid, kThreads, smem, st>>>(A); }
@@ -858,8 +868,10 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
         cudaEventRecord(tm.e1, st);
       }
       if (time_it) cudaEventRecord(tm.e1b, st);
+      A.hm = w2020 ? sim->hv.p : sim->hm.p;
       A.peer = dist_peer_args(sim, launched > 0, p2p && launched > 0, 1 + ((launched + 1) & 1), true);  // waits for the a^p ghosts and the previous sweep's totals; publishes p' and its own
-      if (p2p) { if (hmwin) k_sweep<1, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, true><<<grid, kThreads, smem, st>>>(A); }
+      if (w2020) { if (p2p) k_sweep<1, true, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, true, false, true><<<grid, kThreads, smem, st>>>(A); }
+      else if (p2p) { if (hmwin) k_sweep<1, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, true><<<grid, kThreads, smem, st>>>(A); }
       else { if (hmwin) k_sweep<1, true, false><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, false><<<grid, kThreads, smem, st>>>(A); }
       LAUNCH_CHECK();
       if (time_it) { cudaEventRecord(tm.e2, st); timed.push_back(tm); }

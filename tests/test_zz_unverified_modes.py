@@ -1,0 +1,77 @@
+"""GPU parity tests of modes whose CUDA kernels were written AFTER the GPU budget of round 1 was spent.
+
+They have never run on hardware.  The library keeps answering ASPH_ERR_UNSUPPORTED for these modes unless
+ASPH_UNVERIFIED_MODES=1 is set (capi.cu), which these tests do; they are `xfail(strict=False)` so that the first GPU
+run reports them as XPASS / xfail without turning the suite red, and they are named to run last.  Once a mode passes on a
+B200 its test moves to test_gpu_parity.py and the switch goes away.
+
+  * operator_discretization: Winchenbach2020 (simulation.rs:1571-1579, boundary_winchenbach2020.rs:207-213, 236-269;
+    5 of the reference's media jobs) — k_aii_w2020 (neighbors.cu), k_source / k_sweep<1, ., ., W2020> (solver.cu).
+"""
+import numpy as np
+import pytest
+
+from test_gpu_parity import _compare_step_fields, _pair, _rel, _scene, _uniform_params
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
+              pytest.mark.xfail(strict=False, reason="kernels written after the round's GPU budget was spent: first run on hardware pending")]
+
+
+@pytest.fixture(autouse=True)
+def _enable_unverified(monkeypatch):
+    monkeypatch.setenv("ASPH_UNVERIFIED_MODES", "1")
+
+
+def _one_step(asph, cuda_lib, oracle32, params, pos, vel, mass, boundary):
+    g, o = _pair(asph, cuda_lib, oracle32, params, pos, vel, mass, boundary)
+    dg = g.single_step_without_adaptivity(); do = o.single_step_without_adaptivity()
+    assert dg == do
+    gi, oi = g.step_info(), o.step_info()
+    assert (gi["div_sweeps"], gi["density_sweeps"]) == (oi["div_sweeps"], oi["density_sweeps"]), (gi, oi)
+    pmax = max(float(np.abs(o.get_field("pressure")).max()), 1e-6)
+    amax = max(float(np.abs(o.get_field("pressure_accel")).max()), 1e-6)
+    w = _compare_step_fields(g, o, 2e-4, [("density", 1.0), ("aii", None), ("ppe_source_term", None), ("pressure", pmax),
+                                          ("pressure_accel", amax)])
+    assert _rel(g.get_field("position"), o.get_field("position"), 2.0) <= 1e-6, w
+    vs = max(float(np.abs(o.get_field("velocity")).max()), 1e-3)
+    assert _rel(g.get_field("velocity"), o.get_field("velocity"), vs) <= 1e-4, w
+    g.close(); o.close()
+
+
+@pytest.mark.parametrize("solver", ["HybridDFSPH", "IISPH", "OnlyDivergence"])
+def test_winchenbach2020_single_step_uniform(asph, cuda_lib, oracle32, default_params, solver):
+    """One physics step, uniform h, block in the corner (boundary terms active), every per-particle field."""
+    sc = asph.SceneConfig.dam_break(0.02)
+    pos, vel, mass = asph.scene_particles(sc)
+    vel = (np.random.default_rng(1).standard_normal(vel.shape) * 0.05).astype(np.float32)
+    params = _uniform_params(default_params, pressure_solver_method=solver, operator_discretization="Winchenbach2020")
+    _one_step(asph, cuda_lib, oracle32, params, pos, vel, mass, asph.scene_boundary(sc, "AnalyticOverestimate"))
+
+
+def test_winchenbach2020_single_step_mixed_sizes(asph, cuda_lib, oracle32, default_params):
+    """Jittered cloud with masses spread over 4:1 around the lattice mass (two size levels, far tables), polygon boundary."""
+    sc = asph.SceneConfig.dam_break(0.02)
+    pos, vel, mass = asph.scene_particles(sc)
+    rng = np.random.default_rng(2)
+    pos = (pos + rng.uniform(-0.2, 0.2, pos.shape).astype(np.float32) * np.float32(0.02)).astype(np.float32)
+    mass = (mass * np.exp(rng.uniform(-np.log(2.0), np.log(2.0), mass.shape))).astype(np.float32)
+    vel = (rng.standard_normal(vel.shape) * 0.05).astype(np.float32)
+    params = _uniform_params(default_params, operator_discretization="Winchenbach2020", init_boundary_handler="AnalyticUnderestimate")
+    _one_step(asph, cuda_lib, oracle32, params, pos, vel, mass, asph.scene_boundary(sc, "AnalyticUnderestimate"))
+
+
+def test_winchenbach2020_default_scene_with_resampling(asph, cuda_lib, oracle32, default_params, split_patterns):
+    """C1 (default config + scene) under the Winchenbach2020 operator, 15 full steps: identical particle counts and
+    resampling statistics every step, positions within 1e-5 of the domain size."""
+    sc = _scene(asph, "default-scene.yaml")
+    params = default_params.replace(operator_discretization="Winchenbach2020")
+    g = asph.init_fluid_sim(params, sc, split_patterns, lib=cuda_lib)
+    o = asph.init_fluid_sim(params, sc, split_patterns, lib=oracle32)
+    for step in range(15):
+        g.single_step(); o.single_step()
+        gi, oi = g.step_info(), o.step_info()
+        for k in ("n_particles_end", "n_shared", "n_merged", "n_split_parents", "div_sweeps", "density_sweeps"):
+            assert gi[k] == oi[k], (step, k, gi, oi)
+    assert _rel(g.get_field("position"), o.get_field("position"), 2.0) <= 1e-5
+    assert abs(float(g.get_field("mass").sum()) - float(o.get_field("mass").sum())) < 1e-5
+    g.close(); o.close()
