@@ -36,6 +36,10 @@ int asph_set_state(asph_sim* sim, const float* pos, const float* vel, const floa
     s.level_estimation[i] = Level<FT>();
     s.neighs[i].clear();
     s.lambda[i].clear();
+    // FluidSimulation::new (sim.rs:505-520): h2 = 0, h2_next = h from mass at INIT_REST_DENSITY = 1
+    s.h2[i] = 0;
+    s.h2_next[i] = h_from_mass<FT>(s.mass[i], FT(1));
+    s.size_class[i] = ASPH_CLASS_OPTIMAL;
   }
   return ASPH_OK;
 }
@@ -179,6 +183,12 @@ int oracle_build_neighbors_bruteforce(asph_sim* sim, const asph_params* params, 
 double oracle_aii_inefficient(asph_sim* sim, const asph_params* params, uint64_t i) {
   Params<FT> P(*params);
   return double(sim->s.aii_inefficient(i, P));
+}
+// oracle-only: the IISPH2 correction factors of the last step (sim.rs:2263-2311), for the numpy cross-check in tests/
+int oracle_get_omega(asph_sim* sim, double* out, uint64_t n) {
+  if (n != sim->s.n()) return ASPH_ERR_INVALID;
+  for (uint64_t i = 0; i < n; i++) out[i] = double(sim->s.omega[i]);
+  return ASPH_OK;
 }
 // oracle-only: run phases of the adaptivity separately for per-phase parity
 int oracle_set_level(asph_sim* sim, const float* level, uint64_t n) {

@@ -277,6 +277,8 @@ template <class FT> struct Sim {
   std::vector<FT> mass;
   std::vector<V> position, velocity, velocity_temp, pressure_accel;
   std::vector<FT> density, ppe_source_term, pressure, pressure_next_iter, aii, density_error, h2, constant_field;
+  std::vector<FT> h2_next, omega;  // FromDistribution* / constrain_neighborhood_count state (sim.rs:309-311); IISPH2 (sim.rs:307)
+  std::vector<uint8_t> flag_neighborhood_reduced;
   std::vector<Level<FT>> level_estimation, level_estimation_temp;
   std::vector<uint8_t> size_class, flag_is_fluid_surface, flag_insufficient_neighs;
   std::vector<uint32_t> merge_partner;
@@ -305,7 +307,8 @@ template <class FT> struct Sim {
   void resize_all(size_t N) {
     mass.resize(N); position.resize(N); velocity.resize(N); velocity_temp.resize(N); pressure_accel.resize(N);
     density.resize(N); ppe_source_term.resize(N); pressure.resize(N); pressure_next_iter.resize(N); aii.resize(N);
-    density_error.resize(N); h2.resize(N); constant_field.resize(N);
+    density_error.resize(N); h2.resize(N); constant_field.resize(N); h2_next.resize(N); omega.resize(N);
+    flag_neighborhood_reduced.resize(N);
     level_estimation.resize(N); level_estimation_temp.resize(N);
     size_class.resize(N, ASPH_CLASS_OPTIMAL); flag_is_fluid_surface.resize(N); flag_insufficient_neighs.resize(N);
     merge_partner.resize(N); merge_counter.resize(N);
@@ -610,9 +613,14 @@ template <class FT> struct Sim {
       } else {
         interior = false;
         normal = normal / normal.norm();  // normalize_mut
+        // is_neighbor_in_level_estimation_range (sim.rs:698-723): only FromDistribution / FromDistribution2 cut the range
+        const bool cut = P.raw.support_length_estimation == ASPH_H_FROM_DISTRIBUTION ||
+                         P.raw.support_length_estimation == ASPH_H_FROM_DISTRIBUTION2;
+        const FT particle_radius = volume_to_radius<FT>(mass[i] / P.rest_density);
+        const FT cut_r = particle_radius * FT(P.raw.maximum_range);
         for (uint32_t j : neighs[i]) {
-          // is_neighbor_in_level_estimation_range is a no-op under FromMass (sim.rs:698-723)
           V xji = position[j] - position[i];
+          if (cut && xji.norm_squared() > cut_r * cut_r) continue;
           xji = xji / (xji.norm() + FT(0.000001));
           if (xji.dot(normal) > threshold) { interior = true; break; }
         }
@@ -620,6 +628,32 @@ template <class FT> struct Sim {
       level_estimation[i].surface = !interior;
       level_estimation[i].v = 0;
       flag_is_fluid_surface[i] = interior ? 0 : 1;
+    }
+  }
+  void surface_detection_by_center_diff(const Params<FT>& P) {  // sim.rs:631-695
+    const size_t N = n();
+#pragma omp parallel for schedule(static)
+    for (int64_t ii = 0; ii < int64_t(N); ii++) {
+      size_t i = size_t(ii);
+      FT weight_sum = 0, avg_radius = 0;
+      V avg_center;
+      int num_neighbors = 0;
+      for (uint32_t j : neighs[i]) {
+        FT vol = mass[j] / P.rest_density;
+        FT rad = volume_to_radius<FT>(vol);
+        FT weight = kernelh<FT>(position[i] - position[j], hij(i, j)) * vol;
+        avg_center += position[j] * weight;
+        avg_radius += rad * weight;
+        weight_sum += weight;
+        num_neighbors++;
+      }
+      avg_radius /= weight_sum;
+      FT surface_level = FT(-0.85) * avg_radius;
+      FT phi;
+      if (num_neighbors < 5) phi = surface_level;
+      else { avg_center = avg_center / weight_sum; phi = (position[i] - avg_center).norm() - avg_radius; }
+      if (phi >= surface_level) { level_estimation[i].surface = true; level_estimation[i].v = phi; flag_is_fluid_surface[i] = 1; }
+      else { level_estimation[i].surface = false; level_estimation[i].v = 0; flag_is_fluid_surface[i] = 0; }
     }
   }
   int propagate_level_set(const Params<FT>&) {  // sim.rs:729-801
@@ -677,8 +711,9 @@ template <class FT> struct Sim {
     switch (P.raw.level_estimation_method) {
       case ASPH_LEVEL_NONE: return true;
       case ASPH_LEVEL_EMPTY_ANGLE: surface_detection_by_empty_angle(P); break;
-      default: err = {ASPH_ERR_UNSUPPORTED, "CenterDiff level estimation (SURVEY §8f rank 3)"}; return false;
+      default: surface_detection_by_center_diff(P); break;
     }
+    (void)err;
     info.level_sweeps = propagate_level_set(P);
     return true;
   }
@@ -789,7 +824,7 @@ template <class FT> struct Sim {
   FT next_density_estimate(size_t i, const Params<FT>& P) const {
     return P.raw.operator_discretization == ASPH_OP_WINCHENBACH2020 ? P.rest_density : density[i];
   }
-  enum SourceKind { SRC_DIVERGENCE, SRC_ONLY_DENSITY, SRC_FULL };
+  enum SourceKind { SRC_DIVERGENCE, SRC_ONLY_DENSITY, SRC_FULL, SRC_FULL_WITH_OMEGA };
   void prepare_ppe(SourceKind kind, const Params<FT>& P, FT dt) {  // sim.rs:1127-1204, 1633-1748
     const size_t N = n();
     auto vf = [&](size_t j) { return velocity[j]; };
@@ -803,9 +838,12 @@ template <class FT> struct Sim {
         s = -div / dt;
       } else if (kind == SRC_ONLY_DENSITY) {
         s = -(P.rest_density - density[i]) / (next_density_estimate(i, P) * dt * dt);
-      } else {
+      } else if (kind == SRC_FULL) {
         FT div = divergence_iisph(i, vf, V(), P);
         s = -(P.rest_density - density[i]) / (next_density_estimate(i, P) * dt * dt) - div / dt;
+      } else {  // calculate_source_term_full_with_omega sim.rs:1678-1710: next_density_estimate is the rest density
+        FT div = divergence_iisph(i, vf, V(), P);
+        s = -(P.rest_density - density[i]) / (P.rest_density * dt * dt) - div / (dt * omega[i]);
       }
       ppe_source_term[i] = s;
     }
@@ -896,19 +934,102 @@ template <class FT> struct Sim {
     return divergence_iisph(check_i, af, V(), P);
   }
 
+  // support length from the particle distribution, sim.rs:1873-1971 ("Constrained Neighbor Lists for SPH-based Fluid
+  // Simulations" eq. 3-4), and the neighbour-count constraint, sim.rs:2145-2177.  lambda_sum is the boundary handler's
+  // state of the PREVIOUS step (update_after_advect runs afterwards, sim.rs:2179).
+  bool estimate_support_lengths(const Params<FT>& P, StepError& err) {
+    const size_t N = n();
+    const int mode = P.raw.support_length_estimation;
+    if (mode != ASPH_H_FROM_MASS) {
+      int bad = 0;
+#pragma omp parallel for schedule(static) reduction(max : bad)
+      for (int64_t ii = 0; ii < int64_t(N); ii++) {
+        size_t i = size_t(ii);
+        const FT w = FT(0.5);
+        FT volume_estimate;
+        if (mode == ASPH_H_FROM_DISTRIBUTION2) {
+          FT v_w_sum = 0;
+          for (uint32_t j : neighs[i]) v_w_sum += (mass[j] / P.rest_density) * kernelh<FT>(position[i] - position[j], hij(i, j));
+          FT vi = mass[i] / P.rest_density;
+          volume_estimate = vi / (v_w_sum + lambda_sum(i));
+        } else {
+          FT w_sum = 0;
+          for (uint32_t j : neighs[i]) w_sum += kernelh<FT>(position[i] - position[j], hij(i, j));
+          volume_estimate = (FT(1) - std::min(lambda_sum(i), FT(0.5))) / w_sum;
+        }
+        if (!(volume_estimate >= FT(0))) { bad = 1; continue; }
+        FT h_new = FT(ETA) * volume_to_radius<FT>(volume_estimate);
+        FT hn = w * h_new + (FT(1) - w) * h2[i];
+        if (mode == ASPH_H_FROM_DISTRIBUTION_CLAMPED1) hn = std::min(hn, FT(1) * h_from_mass<FT>(mass[i], P.rest_density));
+        if (mode == ASPH_H_FROM_DISTRIBUTION_CLAMPED2) hn = std::min(hn, FT(2) * h_from_mass<FT>(mass[i], P.rest_density));
+        h2_next[i] = hn;
+      }
+      if (bad) { err = {ASPH_ERR_INVALID, "assert!(volume_estimate >= 0.)"}; return false; }
+    }
+    if (P.raw.constrain_neighborhood_count) {
+      const size_t target = size_t(FT(ETA * 2) * FT(ETA * 2)) + 5;  // optimal_neighbor_number (sim.rs:386) as usize + 5
+      int bad = 0;
+#pragma omp parallel for schedule(static) reduction(max : bad)
+      for (int64_t ii = 0; ii < int64_t(N); ii++) {
+        size_t i = size_t(ii);
+        const size_t cnt = neighs[i].size();
+        if (cnt > target) {
+          std::vector<FT> fringe;
+          fringe.reserve(cnt);
+          for (uint32_t j : neighs[i]) fringe.push_back(FT(2) * (position[i] - position[j]).norm() - h2[j] * FT(2));
+          std::sort(fringe.begin(), fringe.end(), [](FT a, FT b) { return a > b; });
+          FT hn = fringe[cnt - target];
+          if (!(hn < h2[i]) || !(hn >= FT(0))) { bad = 1; continue; }
+          h2_next[i] = hn;
+          flag_neighborhood_reduced[i] = 1;
+        } else {
+          h2_next[i] = h2[i];
+          flag_neighborhood_reduced[i] = 0;
+        }
+      }
+      if (bad) { err = {ASPH_ERR_INVALID, "constrain_neighborhood_count: assert!(*p_h_next < h) / assert!(*p_h_next >= 0.)"}; return false; }
+      std::swap(h2, h2_next);
+    }
+    return true;
+  }
+  // IISPH2 correction factor, sim.rs:2263-2311
+  void compute_omega(const Params<FT>& P) {
+    const size_t N = n();
+    auto dwdh = [](FT d, FT H) {
+      FT q = d / H;
+      FT cd = FT(40) / (FT(7) * Consts<FT>::PI);
+      FT w = cubic_unnorm<FT>(q), wd = cubic_unnorm_deriv<FT>(q);
+      return cd * -FT(2) / (H * H * H) * w + cd / (H * H) * wd * (-d / (H * H));
+    };
+    (void)P;
+    for (size_t i = 0; i < N; i++) {
+      FT om = 1;
+      const FT H_i = h2[i] * FT(2);
+      if (size_class[i] == ASPH_CLASS_LARGE) {
+        om += H_i / (FT(3) * density[i]) * mass[i] * dwdh(FT(0), h2[i] * FT(2));
+      } else {
+        for (uint32_t j : neighs[i]) {
+          FT d = (position[i] - position[j]).norm();
+          om += H_i / (FT(3) * density[i]) * mass[j] * dwdh(d, hij(i, j) * FT(2));
+        }
+      }
+      omega[i] = std::min(FT(2.5), std::max(om, FT(0.125)));
+    }
+  }
+
   // ---------------------------------------------------------------- the step, sim.rs:1980-2730
   bool step_physics(const Params<FT>& P, FT& dt_out, StepError& err) {
     const size_t N = n();
     info = asph_step_info();
     info.n_particles_begin = N;
     pc.begin(ASPH_PC_SIMULATION_STEP);
-    if (P.raw.support_length_estimation != ASPH_H_FROM_MASS) {
-      err = {ASPH_ERR_UNSUPPORTED, "support_length_estimation != FromMass (SURVEY §8f rank 3)"}; return false;
-    }
-    if (P.raw.constrain_neighborhood_count) { err = {ASPH_ERR_UNSUPPORTED, "constrain_neighborhood_count"}; return false; }
-    // 1: h from mass, sim.rs:1865-1871
+    // 1: kernel support, sim.rs:1998-2016: from mass (sim.rs:1865-1871), or the length estimated in the last step
+    if (P.raw.support_length_estimation == ASPH_H_FROM_MASS) {
 #pragma omp parallel for schedule(static)
-    for (int64_t ii = 0; ii < int64_t(N); ii++) h2[size_t(ii)] = h_from_mass<FT>(mass[size_t(ii)], P.rest_density);
+      for (int64_t ii = 0; ii < int64_t(N); ii++) h2[size_t(ii)] = h_from_mass<FT>(mass[size_t(ii)], P.rest_density);
+    } else {
+      std::swap(h2, h2_next);
+    }
 
     if (!P.raw.level_estimation_after_advection) {  // sim.rs:2018-2058
       if (!P.raw.use_extended_range_for_level_estimation || P.raw.level_estimation_method == ASPH_LEVEL_CENTER_DIFF) {
@@ -928,7 +1049,8 @@ template <class FT> struct Sim {
       if (!build_neighbors(FT(2), err)) return false;
       pc.end(ASPH_PC_NEIGHBORHOOD);
     }
-    boundary_update_after_advect(P);  // sim.rs:2179
+    if (!estimate_support_lengths(P, err)) return false;  // sim.rs:2090-2177
+    boundary_update_after_advect(P);                      // sim.rs:2179
     // CFL, sim.rs:2182-2191
     FT min_cfl = std::numeric_limits<FT>::infinity();
     for (size_t i = 0; i < N; i++) {
@@ -1000,7 +1122,24 @@ template <class FT> struct Sim {
         }
         break;
       }
-      default: err = {ASPH_ERR_UNSUPPORTED, "pressure_solver_method IISPH2 (SURVEY §8f rank 3)"}; return false;
+      default: {  // IISPH2, sim.rs:2262-2387
+        compute_omega(P);
+        update_velocity_with_non_pressure_accel(P, dt);
+        prepare_ppe(SRC_FULL_WITH_OMEGA, P, dt);
+        pc.begin(ASPH_PC_DENSITY_SOLVER);
+        if (!pressure_iterations(P.iisph_max_avg_density_error, true, P, dt, iters, info.last_avg_error_density, err)) return false;
+        pc.end(ASPH_PC_DENSITY_SOLVER);
+        info.density_iterations = iters; info.density_sweeps = iters + 1;
+        for (size_t i = 0; i < N; i++) pressure[i] /= std::sqrt(omega[i]);
+        calculate_pressure_accels(pressure, P);
+#pragma omp parallel for schedule(static)
+        for (int64_t ii = 0; ii < int64_t(N); ii++) {
+          size_t i = size_t(ii);
+          velocity[i] += dt * pressure_accel[i];
+          position[i] += dt * velocity[i];
+        }
+        break;
+      }
     }
     for (size_t i = 0; i < N; i++)
       if (!position[i].finite() || !velocity[i].finite()) { err = {ASPH_ERR_NONFINITE, "position/velocity not finite"}; return false; }
@@ -1118,6 +1257,7 @@ template <class FT> struct Sim {
       velocity[i] = (mass_i * velocity[i] + mass_n * velocity[j]) / m;
       position[i] = (mass_i * position[i] + mass_n * position[j]) / m;
       mass[i] = m;
+      h2_next[i] = h_from_mass<FT>(m, P.rest_density);  // particle_sharing.rs:206, particle_merging.rs:323
     }
   }
   void share_particles(const Params<FT>& P, FT dt) {  // particle_sharing.rs:152-240
@@ -1126,6 +1266,7 @@ template <class FT> struct Sim {
       if (merge_partner[i] != ASPH_MERGE_PARTNER_DELETE) continue;
       if (int(merge_counter[i]) < P.raw.minimum_share_partners) continue;
       mass[i] -= dropped_mass_sharing(i, mass[i], dt, P);
+      h2_next[i] = h_from_mass<FT>(mass[i], P.rest_density);  // particle_sharing.rs:238
     }
   }
   void swap_particles(size_t a, size_t b) {  // ParticleVec::swap sim.rs:249-253 (+ neighs, boundary)
@@ -1134,7 +1275,8 @@ template <class FT> struct Sim {
     std::swap(density[a], density[b]); std::swap(ppe_source_term[a], ppe_source_term[b]);
     std::swap(pressure[a], pressure[b]); std::swap(pressure_next_iter[a], pressure_next_iter[b]);
     std::swap(aii[a], aii[b]); std::swap(density_error[a], density_error[b]); std::swap(h2[a], h2[b]);
-    std::swap(constant_field[a], constant_field[b]);
+    std::swap(constant_field[a], constant_field[b]); std::swap(h2_next[a], h2_next[b]); std::swap(omega[a], omega[b]);
+    std::swap(flag_neighborhood_reduced[a], flag_neighborhood_reduced[b]);
     std::swap(level_estimation[a], level_estimation[b]); std::swap(level_estimation_temp[a], level_estimation_temp[b]);
     std::swap(size_class[a], size_class[b]);
     std::swap(flag_is_fluid_surface[a], flag_is_fluid_surface[b]);
@@ -1177,6 +1319,7 @@ template <class FT> struct Sim {
       const float* pat = &split_pos[2 * size_t(split_offset[nc - 2])];
       FT radius = volume_to_radius<FT>(mass[i] / FT(1));  // INIT_REST_DENSITY
       FT child_mass = mass[i] / FT(nc);
+      FT child_h = h_from_mass<FT>(child_mass, P.rest_density);
       V ov = velocity[i], op = position[i];
       Level<FT> ol = level_estimation[i];
       resize_all(n() + nc - 1);
@@ -1184,6 +1327,7 @@ template <class FT> struct Sim {
         V off = V(FT(pat[2 * c]), FT(pat[2 * c + 1])) * radius;
         size_t t = (c == 0) ? i : new_id++;
         mass[t] = child_mass; velocity[t] = ov; position[t] = op + off; level_estimation[t] = ol;
+        h2[i] = child_h; h2_next[t] = child_h;  // splitting.rs:65-74: h2 of an appended child stays 0 until the next step
       }
       parents++;
     }
