@@ -254,6 +254,9 @@ k_aii_w2020(uint32_t n, NbLists L, const float4* __restrict__ xyhm, const float*
             float rho0, float4* __restrict__ pconst, float2* __restrict__ hv, StepCtl* ctl, const uint32_t* __restrict__ gid) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  // The neighbour pass gave up on some slices (pool too small: the step is redone from that pass after neighbors_grow)
+  // or had no grid at all: their densities were never written, and flagging "non-finite" for them would outlive the retry.
+  if (ctl->error_flags & (ERRF_LIST_CAPACITY | ERRF_CELL_BUDGET)) return;
   const float4 me = xyhm[i];
   const float rho_i = rho[i];
   hv[i] = make_float2(me.z, me.w / rho_i);

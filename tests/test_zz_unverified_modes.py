@@ -1,9 +1,11 @@
-"""GPU parity tests of modes whose CUDA kernels were written AFTER the GPU budget of round 1 was spent.
+"""GPU parity tests of modes whose CUDA kernels were written when the GPU budget of round 1 was (all but) spent.
 
-They have never run on hardware.  The library keeps answering ASPH_ERR_UNSUPPORTED for these modes unless
-ASPH_UNVERIFIED_MODES=1 is set (capi.cu), which these tests do; they are `xfail(strict=False)` so that the first GPU
-run reports them as XPASS / xfail without turning the suite red, and they are named to run last.  Once a mode passes on a
-B200 its test moves to test_gpu_parity.py and the switch goes away.
+The library keeps answering ASPH_ERR_UNSUPPORTED for these modes unless ASPH_UNVERIFIED_MODES=1 is set (capi.cu), which
+these tests do.  The last GPU seconds of the round went into one run of this file (profiles/r1_w2020_first_hw_run.txt):
+the four single-step tests passed on a B200; the multi-step run with resampling failed on a stale error flag of the
+list-pool retry path, fixed since but not re-run — that test stays `xfail(strict=False)` (it reports XPASS / xfail without
+turning the suite red) and the file is named to run last.  Once it passes the tests move to test_gpu_parity.py and the
+switch goes away.
 
   * operator_discretization: Winchenbach2020 (simulation.rs:1571-1579, boundary_winchenbach2020.rs:207-213, 236-269;
     5 of the reference's media jobs) — k_aii_w2020 (neighbors.cu), k_source / k_sweep<1, ., ., W2020> (solver.cu).
@@ -13,8 +15,8 @@ import pytest
 
 from test_gpu_parity import _compare_step_fields, _pair, _rel, _scene, _uniform_params
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
-              pytest.mark.xfail(strict=False, reason="kernels written after the round's GPU budget was spent: first run on hardware pending")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+pending = pytest.mark.xfail(strict=False, reason="failed in its only hardware run (stale flag after a list-pool retry); fixed, re-run pending")
 
 
 @pytest.fixture(autouse=True)
@@ -60,6 +62,7 @@ def test_winchenbach2020_single_step_mixed_sizes(asph, cuda_lib, oracle32, defau
     _one_step(asph, cuda_lib, oracle32, params, pos, vel, mass, asph.scene_boundary(sc, "AnalyticUnderestimate"))
 
 
+@pending
 def test_winchenbach2020_default_scene_with_resampling(asph, cuda_lib, oracle32, default_params, split_patterns):
     """C1 (default config + scene) under the Winchenbach2020 operator, 15 full steps: identical particle counts and
     resampling statistics every step, positions within 1e-5 of the domain size."""
