@@ -317,6 +317,52 @@ __global__ void k_split_apply(uint32_t n, uint32_t cap, const uint8_t* __restric
   }
 }
 
+// ---- support_length_estimation != FromMass: h2_next and the boundary handler's lambda follow the particles ---------
+// Receivers and sharing donors get the length of their new mass (particle_sharing.rs:206,238, particle_merging.rs:323).
+// Runs after k_apply_receivers / k_share_donors (the masses are the new ones, partner / counter still say who changed).
+__global__ void __launch_bounds__(kThreads)
+k_hnext_after_transfer(uint32_t n, AdaptArgs A, const PackedParams P, int merging, float* __restrict__ hnext) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t j = A.partner[i];
+  const int minp = merging ? P.min_merge_partners : P.min_share_partners;
+  bool changed;
+  if (j == AVAILABLE) changed = false;
+  else if (j == DELETE_) changed = !merging && int(A.counter[i]) >= minp;  // sharing donor; a merging donor is deleted
+  else changed = int(A.counter[j]) >= minp;                                // receiver
+  if (changed) hnext[i] = h_from_mass(A.mass[i], P.rest_density);
+}
+// same destinations as k_compact
+__global__ void k_compact_extra(uint32_t n, const uint32_t* __restrict__ keep_scan, const float* __restrict__ hnext, const float* __restrict__ lamprev,
+                                float* __restrict__ hnext_o, float* __restrict__ lamprev_o) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (keep_scan[i + 1] == keep_scan[i]) return;
+  const uint32_t o = keep_scan[i];
+  hnext_o[o] = hnext[i]; lamprev_o[o] = lamprev[i];
+}
+// same targets as k_split_apply, launched BEFORE it (it needs the parents' unsplit masses): every child gets the length
+// of the child mass (splitting.rs:50,66,74); appended children start with empty lambda lists (boundary_handler.extend)
+__global__ void k_split_extra(uint32_t n, uint32_t cap, const uint8_t* __restrict__ size_class, const uint32_t* __restrict__ extra_scan,
+                              const PackedParams P, int max_children, const float* __restrict__ mass, const float* __restrict__ level,
+                              const uint32_t* __restrict__ refid, float* __restrict__ hnext, float* __restrict__ lamprev) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (size_class[i] != ASPH_CLASS_TOO_LARGE) return;
+  unsigned int err = 0;
+  const float m = mass[i];
+  const uint32_t nc = split_children(level[i], m, P, max_children, &err);
+  if (nc < 2u) return;
+  const float child_h = h_from_mass(m / float(nc), P.rest_density);
+  const uint32_t first = n + extra_scan[refid[i]];
+  for (uint32_t c = 0; c < nc; c++) {
+    const uint32_t t = (c == 0) ? i : first + (c - 1u);
+    if (t >= cap) return;
+    hnext[t] = child_h;
+    if (c > 0) lamprev[t] = 0.f;
+  }
+}
+
 AdaptArgs args_of(asph_sim* sim) {
   AdaptArgs A;
   const int c = sim->cur;
@@ -404,6 +450,10 @@ int launch_adaptivity(asph_sim* sim, float dt) {
     LAUNCH_CHECK();
     k_share_donors<<<blocks, kThreads, 0, st>>>(sim->n, A, P, dt);
     LAUNCH_CHECK();
+    if (sim->hdist_valid) {
+      k_hnext_after_transfer<<<blocks, kThreads, 0, st>>>(sim->n, A, P, 0, sim->hnext[sim->cur].p);
+      LAUNCH_CHECK();
+    }
   }
   if (sim->step_number % 2 == 0) {
     if (sim->merge_enabled) {  // simulation.rs:2760-2774
@@ -416,6 +466,10 @@ int launch_adaptivity(asph_sim* sim, float dt) {
       const AdaptArgs A = args_of(sim);
       k_apply_receivers<<<blocks, kThreads, 0, st>>>(n, A, P, 1, dt);
       LAUNCH_CHECK();
+      if (sim->hdist_valid) {
+        k_hnext_after_transfer<<<blocks, kThreads, 0, st>>>(n, A, P, 1, sim->hnext[sim->cur].p);
+        LAUNCH_CHECK();
+      }
       uint32_t* del_ref = sim->scratch_u[0].p;   // n + 1
       uint32_t* keep = sim->scratch_u[1].p;      // n + 1
       uint32_t* holes = sim->scratch_u[2].p;
@@ -430,6 +484,10 @@ int launch_adaptivity(asph_sim* sim, float dt) {
                                              sim->refid[c].p, sim->pos[1 - c].p, sim->vel[1 - c].p, sim->mass[1 - c].p, sim->level[1 - c].p,
                                              sim->refid[1 - c].p, sim->ctl);
       LAUNCH_CHECK();
+      if (sim->hdist_valid) {
+        k_compact_extra<<<blocks, kThreads, 0, st>>>(n, keep, sim->hnext[c].p, sim->lamprev[c].p, sim->hnext[1 - c].p, sim->lamprev[1 - c].p);
+        LAUNCH_CHECK();
+      }
       TRY(sync_ctl(sim));
       TRY(check_error_flags(sim));
       const uint32_t n_new = sim->ctl_host->n_new;
@@ -465,6 +523,11 @@ int launch_adaptivity(asph_sim* sim, float dt) {
     }
     if (n_new != n) {
       const int cc = sim->cur;
+      if (sim->hdist_valid) {
+        k_split_extra<<<blocks, kThreads, 0, st>>>(n, sim->cap, sim->size_class.p, sim->scratch_u[0].p, P, sim->max_children, sim->mass[cc].p,
+                                                   sim->level[cc].p, sim->refid[cc].p, sim->hnext[cc].p, sim->lamprev[cc].p);
+        LAUNCH_CHECK();
+      }
       k_split_apply<<<blocks, kThreads, 0, st>>>(n, sim->cap, sim->size_class.p, sim->scratch_u[0].p, P, sim->max_children,
                                                  sim->split_off.p, sim->split_pos.p, sim->pos[cc].p, sim->vel[cc].p, sim->mass[cc].p,
                                                  sim->level[cc].p, sim->refid[cc].p);

@@ -37,6 +37,8 @@ int pack_params(asph_sim* sim, const asph_params* p) {
   q.solver = p->pressure_solver_method; q.density_source = p->hybrid_dfsph_density_source_term;
   q.np_before_div = p->hybrid_dfsph_non_pressure_accel_before_divergence_free; q.penalty = p->boundary_penalty_term;
   q.sizing = p->sizing_function; q.opdisc = p->operator_discretization;
+  q.h_mode = p->support_length_estimation;
+  q.level_cut = (q.h_mode == ASPH_H_FROM_DISTRIBUTION || q.h_mode == ASPH_H_FROM_DISTRIBUTION2) ? float(p->maximum_range) : 0.f;
   q.boundary_is_fluid_surface = p->boundary_is_fluid_surface;
   q.max_iters = int(std::min<int64_t>(p->max_iters, 1 << 28));
   q.min_share_partners = p->minimum_share_partners; q.min_merge_partners = p->minimum_merge_partners;
@@ -69,7 +71,6 @@ int pack_params(asph_sim* sim, const asph_params* p) {
   }
 
   auto unsupported = [&](const char* what) { sim->last_error = std::string(what) + " is not implemented yet (SURVEY.md §8f)"; return ASPH_ERR_UNSUPPORTED; };
-  if (p->support_length_estimation != ASPH_H_FROM_MASS) return unsupported("support_length_estimation != FromMass");
   if (p->constrain_neighborhood_count) return unsupported("constrain_neighborhood_count");
   if (p->level_estimation_method == ASPH_LEVEL_CENTER_DIFF) return unsupported("level_estimation_method CenterDiff");
   // Modes whose kernels were written after the GPU budget of the round ran out and have not passed their parity tests
@@ -77,6 +78,10 @@ int pack_params(asph_sim* sim, const asph_params* p) {
   const bool unverified = getenv("ASPH_UNVERIFIED_MODES") != nullptr && atoi(getenv("ASPH_UNVERIFIED_MODES")) != 0;
   if (p->operator_discretization == ASPH_OP_WINCHENBACH2020 && !unverified)
     return unsupported("operator_discretization Winchenbach2020 (kernels not yet verified on hardware; ASPH_UNVERIFIED_MODES=1 enables them)");
+  if (p->support_length_estimation != ASPH_H_FROM_MASS) {
+    if (!unverified) return unsupported("support_length_estimation != FromMass (kernels not yet verified on hardware; ASPH_UNVERIFIED_MODES=1 enables them)");
+    if (sim->dist) return unsupported("support_length_estimation != FromMass across GPU slabs");
+  }
   if (p->pressure_solver_method == ASPH_SOLVER_IISPH2) return unsupported("pressure_solver_method IISPH2");
   if (p->viscosity_type == ASPH_VISC_XSPH) return unsupported("viscosity_type XSPH (todo!() in the reference)");
   if (p->level_estimation_after_advection) return unsupported("level_estimation_after_advection");
@@ -431,6 +436,7 @@ int asph_set_state(asph_sim* sim, const float* pos, const float* vel, const floa
   }
   CUDA_TRY(cudaStreamSynchronize(sim->stream));
   sim->lists_valid = false; sim->level_valid = false; sim->step_fields_valid = false;
+  sim->hdist_valid = false;  // h2_next restarts from the masses, as in FluidSimulation::new (simulation.rs:505-520)
   return ASPH_OK;
 }
 
@@ -499,6 +505,7 @@ void asph_destroy(asph_sim* sim) {
   sim->xyhm.release(); sim->packA.release(); sim->pconst.release(); sim->h_tmp.release(); sim->rho.release(); sim->lam_sum.release();
   sim->nrm.release(); sim->gB.release(); sim->lam_grad.release(); sim->key.release(); sim->cellcount.release(); sim->cellstart.release();
   sim->order.release(); sim->scan_sums.release(); sim->cnt.release(); sim->cnt_ext.release(); sim->far_idx.release(); sim->far_cnt.release(); sim->slice_base.release();
+  for (int b = 0; b < 2; b++) { sim->hnext[b].release(); sim->lamprev[b].release(); }
   sim->nbpool.release(); sim->hm.release(); sim->hv.release(); sim->size_class.release(); sim->flags.release(); sim->merge_partner.release();
   sim->cand.release(); for (int k = 0; k < 4; k++) sim->scratch_u[k].release();
   sim->merge_counter.release(); sim->stamp.release(); sim->stampkey.release(); sim->scratch_f.release(); sim->lut.release(); sim->split_pos.release();

@@ -34,13 +34,15 @@ __device__ __forceinline__ float warp_max(float v) {
 // K1 + K8 + bounding box.  h is bit-exact (neighbour predicate); the CFL term follows simulation.rs:2184-2186
 // operation by operation ((2h)^2 / (v.v + 0.01)), and min is order independent, so dt is bit-exact too.
 __global__ void k_prepare(uint32_t n, const float2* __restrict__ pos, const float2* __restrict__ vel,
-                          const float* __restrict__ mass, float rho0, float* __restrict__ h_out, StepCtl* ctl) {
+                          const float* __restrict__ mass, float rho0, const float* __restrict__ h_in, float* __restrict__ h_out,
+                          StepCtl* ctl) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const float inf = __int_as_float(0x7f800000);
   float hmin = inf, hmax = -inf, minx = inf, miny = inf, maxx = -inf, maxy = -inf, cfl = inf;
   if (i < n) {
     float2 x = pos[i], v = vel[i];
-    float h = h_from_mass(mass[i], rho0);
+    // FromMass (simulation.rs:1865-1871), or the length the previous step left in h2_next (simulation.rs:2005-2014)
+    float h = h_in ? h_in[i] : h_from_mass(mass[i], rho0);
     h_out[i] = h;
     hmin = hmax = h;
     minx = maxx = x.x; miny = maxy = x.y;
@@ -263,6 +265,21 @@ __global__ void k_reorder(uint32_t n, const uint32_t* __restrict__ order, const 
   hm[s] = make_float2(h[src], m);
 }
 
+// support_length_estimation != FromMass: the per-particle state besides x, v, m (sim.cuh)
+__global__ void k_hdist_init(uint32_t n, const float* __restrict__ mass, float* __restrict__ hnext, float* __restrict__ lamprev) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  hnext[i] = h_from_mass(mass[i], 1.0f);  // INIT_REST_DENSITY, simulation.rs:505-520
+  lamprev[i] = 0.f;                       // the boundary handler starts with empty lambda lists
+}
+__global__ void k_reorder_extra(uint32_t n, const uint32_t* __restrict__ order, const float* __restrict__ hnext, const float* __restrict__ lamprev,
+                                float* __restrict__ hnext_o, float* __restrict__ lamprev_o) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const uint32_t src = order[s];
+  hnext_o[s] = hnext[src]; lamprev_o[s] = lamprev[src];
+}
+
 }  // namespace
 
 int sync_ctl(asph_sim* sim) {
@@ -309,6 +326,21 @@ int ensure_capacity(asph_sim* sim, uint32_t want) {
       CUDA_TRY(sim->level[b].ensure(newcap)); CUDA_TRY(sim->refid[b].ensure(newcap));
     }
   }
+  if (sim->hdist_valid) {  // support_length_estimation != FromMass: two more persistent arrays
+    for (int b = 0; b < 2; b++) {
+      if (b == sim->cur && old_n > 0) {
+        DevBuf<float> h2, l2;
+        CUDA_TRY(h2.ensure(newcap)); CUDA_TRY(l2.ensure(newcap));
+        CUDA_TRY(cudaMemcpyAsync(h2.p, sim->hnext[b].p, old_n * sizeof(float), cudaMemcpyDeviceToDevice, sim->stream));
+        CUDA_TRY(cudaMemcpyAsync(l2.p, sim->lamprev[b].p, old_n * sizeof(float), cudaMemcpyDeviceToDevice, sim->stream));
+        CUDA_TRY(cudaStreamSynchronize(sim->stream));
+        sim->hnext[b].release(); sim->lamprev[b].release();
+        sim->hnext[b] = h2; sim->lamprev[b] = l2;
+      } else {
+        CUDA_TRY(sim->hnext[b].ensure(newcap)); CUDA_TRY(sim->lamprev[b].ensure(newcap));
+      }
+    }
+  }
   CUDA_TRY(sim->xyhm.ensure(newcap)); CUDA_TRY(sim->xv[0].ensure(newcap)); CUDA_TRY(sim->xv[1].ensure(newcap));
   CUDA_TRY(sim->packP[0].ensure(newcap)); CUDA_TRY(sim->packP[1].ensure(newcap)); CUDA_TRY(sim->packA.ensure(newcap));
   CUDA_TRY(sim->pconst.ensure(newcap));
@@ -348,7 +380,16 @@ int launch_sort_and_grid(asph_sim* sim, float f_search) {
   if (n == 0) return ASPH_OK;
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
   const int c = sim->cur;
-  k_prepare<<<blocks, kThreads, 0, st>>>(n, sim->pos[c].p, sim->vel[c].p, sim->mass[c].p, sim->pp.rest_density, sim->h_tmp.p, sim->ctl);
+  const bool hdist = h_from_distribution(sim);
+  if (hdist && !sim->hdist_valid) {  // first step in this mode (or after asph_set_state): h2_next = h of the masses
+    for (int b = 0; b < 2; b++) { CUDA_TRY(sim->hnext[b].ensure(sim->cap)); CUDA_TRY(sim->lamprev[b].ensure(sim->cap)); }
+    k_hdist_init<<<blocks, kThreads, 0, st>>>(n, sim->mass[c].p, sim->hnext[c].p, sim->lamprev[c].p);
+    LAUNCH_CHECK();
+    sim->hdist_valid = true;
+  }
+  if (!hdist) sim->hdist_valid = false;  // a FromMass step does not maintain h2_next
+  k_prepare<<<blocks, kThreads, 0, st>>>(n, sim->pos[c].p, sim->vel[c].p, sim->mass[c].p, sim->pp.rest_density,
+                                         hdist ? sim->hnext[c].p : nullptr, sim->h_tmp.p, sim->ctl);
   LAUNCH_CHECK();
   if (sim->dist) TRY(dist_allreduce_cfl(sim));  // dt is global: min over all ranks
   k_make_levels<<<1, 1, 0, st>>>(sim->ctl, f_search, sim->cells_budget, sim->pp.max_dt, sim->pp.cfl_factor);
@@ -369,6 +410,10 @@ int launch_sort_and_grid(asph_sim* sim, float f_search) {
                                          sim->level[c].p, sim->h_tmp.p, sim->pos[1 - c].p, sim->vel[1 - c].p, sim->mass[1 - c].p,
                                          sim->refid[1 - c].p, sim->level[1 - c].p, sim->xyhm.p, sim->xv[0].p, sim->hm.p);
   LAUNCH_CHECK();
+  if (hdist) {
+    k_reorder_extra<<<blocks, kThreads, 0, st>>>(n, sim->order.p, sim->hnext[c].p, sim->lamprev[c].p, sim->hnext[1 - c].p, sim->lamprev[1 - c].p);
+    LAUNCH_CHECK();
+  }
   sim->cur = 1 - c;
   if (sim->dist) TRY(dist_after_sort(sim));
   return ASPH_OK;

@@ -52,10 +52,14 @@ k_surface(uint32_t n, Lists L, const float4* __restrict__ xyhm, const float2* __
       const float nn = sqrtf(nx * nx + ny * ny);
       nx /= nn; ny /= nn;
       const NbCol col(L, i);
+      // is_neighbor_in_level_estimation_range (simulation.rs:698-723): FromDistribution / FromDistribution2 only
+      const float cut = P.level_cut * sqrtf((me.w / P.rest_density) * ASPH_FRAC_1_PI_F);
+      const float cut2 = P.level_cut > 0.f ? cut * cut : __int_as_float(0x7f800000);
       for (uint32_t k = 0; k < ce; k++) {
         const uint32_t j = col.get(k);
         const float4 o = __ldg(&xyhm[j]);
         const float dx = o.x - me.x, dy = o.y - me.y;
+        if (dx * dx + dy * dy > cut2) continue;
         const float inv = 1.f / (sqrtf(dx * dx + dy * dy) + 0.000001f);
         if ((dx * inv) * nx + (dy * inv) * ny > cos_threshold) { interior = true; break; }
       }

@@ -285,6 +285,48 @@ k_aii_w2020(uint32_t n, NbLists L, const float4* __restrict__ xyhm, const float*
   pconst[i] = make_float4(G.x, G.y, aii, 0.f);
 }
 
+// Support length from the particle distribution (simulation.rs:1873-1971; "Constrained Neighbor Lists for SPH-based Fluid
+// Simulations" eq. 3-4), after the 2h lists of the step exist and before the boundary terms of the step replace the
+// previous ones (simulation.rs:2090-2143, 2179):
+//   FromDistribution / Clamped1 / Clamped2:  V = (1 - min(Lambda_prev, 0.5)) / sum_j W(x_ij, h_ij)
+//   FromDistribution2:                       V = (m_i / rho0) / (sum_j (m_j / rho0) W(x_ij, h_ij) + Lambda_prev)
+//   h_next = 0.5 * ETA * sqrt(V / pi) + 0.5 * h_i   [clamped to 1x / 2x the length from the mass]
+// W in the reference's operation order (sph_kernels.rs:49-52) so that the only difference to the CPU is the summation order.
+__global__ void __launch_bounds__(kThreads)
+k_estimate_h(uint32_t n, NbLists L, const float4* __restrict__ xyhm, const float* __restrict__ lam_sum, int mode, float rho0,
+             float* __restrict__ hnext, float* __restrict__ lamprev, StepCtl* ctl) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (ctl->error_flags & (ERRF_LIST_CAPACITY | ERRF_CELL_BUDGET)) return;  // void attempt: the step is redone / fails (hnext untouched)
+  const float4 me = xyhm[i];
+  const NbCol col(L, i);
+  float sum = 0.f;
+  for (uint32_t k = 0; k < col.cn; k++) {
+    const float4 o = __ldg(&xyhm[col.get(k)]);
+    const float r = __fsqrt_rn(dist_sq_exact(__fsub_rn(me.x, o.x), __fsub_rn(me.y, o.y)));
+    const float hij = __fmul_rn(__fadd_rn(me.z, o.z), 0.5f);
+    // cubic_kernel_2d: (10 / (7 pi (h h))) * w(r / (2 h))
+    const float q = __fdiv_rn(r, __fmul_rn(2.f, hij));
+    float w;
+    if (q < 0.5f) w = __fadd_rn(__fmul_rn(6.f, __fsub_rn(__fmul_rn(__fmul_rn(q, q), q), __fmul_rn(q, q))), 1.f);
+    else if (q < 1.f) { const float v = __fsub_rn(1.f, q); w = __fmul_rn(2.f, __fmul_rn(__fmul_rn(v, v), v)); }
+    else w = 0.f;
+    const float W = __fmul_rn(__fdiv_rn(10.f, __fmul_rn(__fmul_rn(7.f, ASPH_PI_F), __fmul_rn(hij, hij))), w);
+    sum = __fadd_rn(sum, mode == ASPH_H_FROM_DISTRIBUTION2 ? __fmul_rn(__fdiv_rn(o.w, rho0), W) : W);
+  }
+  const float lp = lamprev[i];
+  float vol;
+  if (mode == ASPH_H_FROM_DISTRIBUTION2) vol = __fdiv_rn(__fdiv_rn(me.w, rho0), __fadd_rn(sum, lp));
+  else vol = __fdiv_rn(__fsub_rn(1.f, fminf(lp, 0.5f)), sum);
+  if (!(vol >= 0.f)) { atomicOr(&ctl->error_flags, ERRF_NONFINITE); return; }  // assert!(volume_estimate >= 0.)
+  const float h_new = __fmul_rn(1.9f, __fsqrt_rn(__fmul_rn(vol, ASPH_FRAC_1_PI_F)));
+  float hn = __fadd_rn(__fmul_rn(0.5f, h_new), __fmul_rn(0.5f, me.z));
+  if (mode == ASPH_H_FROM_DISTRIBUTION_CLAMPED1) hn = fminf(hn, __fmul_rn(1.f, h_from_mass(me.w, rho0)));
+  if (mode == ASPH_H_FROM_DISTRIBUTION_CLAMPED2) hn = fminf(hn, __fmul_rn(2.f, h_from_mass(me.w, rho0)));
+  hnext[i] = hn;
+  lamprev[i] = lam_sum[i];  // this step's boundary terms (k_neighbors) are what the next step's estimate sees
+}
+
 }  // namespace
 
 int launch_neighbors(asph_sim* sim, float f_ext, float f_near) {
@@ -305,6 +347,13 @@ int launch_neighbors(asph_sim* sim, float f_ext, float f_near) {
                                                     sim->dist ? sim->refid[sim->cur].p : nullptr);
   LAUNCH_CHECK();
   if (sim->dist) TRY(dist_halo(sim, sim->rho.p, 4));  // K12 / K17 read the neighbours' densities
+  if (h_from_distribution(sim)) {
+    NbLists L;
+    L.pool = sim->nbpool.p; L.slice_base = sim->slice_base.p; L.cnt = sim->cnt.p; L.cnt_ext = sim->cnt_ext.p; L.far_idx = sim->far_idx.p; L.far_cnt = sim->far_cnt.p;
+    k_estimate_h<<<blocks, kThreads, 0, sim->stream>>>(n, L, sim->xyhm.p, sim->lam_sum.p, sim->pp.h_mode, sim->pp.rest_density,
+                                                       sim->hnext[sim->cur].p, sim->lamprev[sim->cur].p, sim->ctl);
+    LAUNCH_CHECK();
+  }
   if (op_w2020(sim)) {
     CUDA_TRY(sim->hv.ensure(sim->cap));
     NbLists L;

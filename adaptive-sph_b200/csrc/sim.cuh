@@ -108,6 +108,10 @@ struct PackedParams {  // SimulationParams rounded once to fp32 (what serde does
   // AnalyticUnderestimate: one polygon SDF (Sdf2D with one connected component, sdf/sdf2d.rs); 0 vertices = planes
   int n_poly;
   float poly_pt[ASPH_POLY_DEV][2], poly_dir[ASPH_POLY_DEV][2], poly_pn[ASPH_POLY_DEV][2];
+  // support_length_estimation (ASPH_H_*); level_cut = maximum_range for FromDistribution / FromDistribution2 (the surface
+  // detector ignores neighbours beyond particle_radius * maximum_range, simulation.rs:698-723), 0 = no cut
+  int h_mode;
+  float level_cut;
 };
 
 template <class T> struct DevBuf {
@@ -183,6 +187,12 @@ struct asph_sim {
   DevBuf<uint16_t> nbpool;  // sliced-ELL neighbour lists (lists.cuh)
   DevBuf<float2> hm;        // {h, m} per particle: second gather of the adaptive-h pair passes
   DevBuf<float2> hv;        // {h, m / rho}: what the divergence passes gather instead under the Winchenbach2020 operator
+  // support_length_estimation != FromMass: the two per-particle values that survive a step besides
+  // x, v, m — h2_next (the smoothing length of the NEXT step: this step's estimate, or h from the new mass where
+  // resampling changed a particle) and the boundary handler's lambda sum of this step (read by the next step's estimate).
+  // Double buffered like `mass`; carried through the reorder, the merge compaction and the split.
+  DevBuf<float> hnext[2], lamprev[2];
+  bool hdist_valid = false;
   int predicted_sweeps[2] = {1, 1};  // sweeps of the divergence / density solve in the previous step
   DevBuf<uint8_t> size_class, flags;  // flags: bit0 surface, bit1 insufficient neighbours
   DevBuf<uint32_t> merge_partner, front[2], cand, work[2], scratch_u[4];
@@ -269,6 +279,7 @@ float asph_host_lut_get(const std::vector<float>& data, float x);
 int ensure_capacity(asph_sim* sim, uint32_t n_particles);
 int sync_ctl(asph_sim* sim);  // copies the control block to the pinned mirror and synchronises the stream
 int launch_sort_and_grid(asph_sim* sim, float f_search);
+inline bool h_from_distribution(const asph_sim* sim) { return sim->pp.h_mode != ASPH_H_FROM_MASS; }
 int launch_exclusive_scan(asph_sim* sim, const uint32_t* in, uint32_t* out, const uint32_t* n_dev, uint32_t n_add,
                           uint32_t n_max);  // out[i] = sum(in[0..i)) for i < *n_dev + n_add
 // neighbors.cu

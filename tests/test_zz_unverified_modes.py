@@ -9,6 +9,7 @@ switch goes away.
 
   * operator_discretization: Winchenbach2020 (simulation.rs:1571-1579, boundary_winchenbach2020.rs:207-213, 236-269;
     5 of the reference's media jobs) — k_aii_w2020 (neighbors.cu), k_source / k_sweep<1, ., ., W2020> (solver.cu).
+  * support_length_estimation: FromDistribution* (second half of this file) — never run on hardware.
 """
 import numpy as np
 import pytest
@@ -77,4 +78,50 @@ def test_winchenbach2020_default_scene_with_resampling(asph, cuda_lib, oracle32,
             assert gi[k] == oi[k], (step, k, gi, oi)
     assert _rel(g.get_field("position"), o.get_field("position"), 2.0) <= 1e-5
     assert abs(float(g.get_field("mass").sum()) - float(o.get_field("mass").sum())) < 1e-5
+    g.close(); o.close()
+
+
+# ---- support_length_estimation != FromMass (simulation.rs:1873-1971, 1998-2016): k_estimate_h (neighbors.cu), the h2_next /
+# lambda state carried through the reorder (grid.cu) and the resampling kernels (adapt.cu).  Never run on hardware.
+never_run = pytest.mark.xfail(strict=False, reason="kernels written after the round's GPU budget was spent: first run on hardware pending")
+H_MODES = ["FromDistribution", "FromDistributionClamped1", "FromDistributionClamped2", "FromDistribution2"]
+
+
+@never_run
+@pytest.mark.parametrize("mode", H_MODES)
+def test_support_length_from_distribution_physics(asph, cuda_lib, oracle32, default_params, mode):
+    """Four physics steps of C1 with the level set on: h of every step (the previous step's estimate; W summed in list
+    order instead of index order, so a few ulp apart), neighbour counts, surface flags, positions."""
+    sc = _scene(asph, "default-scene.yaml")
+    params = default_params.replace(support_length_estimation=mode, merging=False, sharing=False, splitting=False)
+    g = asph.init_fluid_sim(params, sc, None, lib=cuda_lib)
+    o = asph.init_fluid_sim(params, sc, None, lib=oracle32)
+    for step in range(4):
+        dg = g.single_step_without_adaptivity(); do = o.single_step_without_adaptivity()
+        assert abs(dg - do) <= 1e-6 * do, step
+        hg, ho = g.get_field("h"), o.get_field("h")
+        assert np.allclose(hg, ho, rtol=3e-6, atol=0), (step, np.abs(hg / ho - 1).max())
+        same = g.get_field("neighbor_count") == o.get_field("neighbor_count")
+        assert same.mean() > 0.995, (step, same.mean())  # a pair exactly at the support edge may flip with an ulp of h
+        assert (g.get_field("flag_is_fluid_surface") == o.get_field("flag_is_fluid_surface")).mean() > 0.995, step
+    assert _rel(g.get_field("position"), o.get_field("position"), 2.0) <= 1e-5
+    g.close(); o.close()
+
+
+@never_run
+@pytest.mark.parametrize("mode", ["FromDistributionClamped1", "FromDistribution"])
+def test_support_length_from_distribution_with_resampling(asph, cuda_lib, oracle32, default_params, split_patterns, mode):
+    """C1 with share / merge / split, 12 full steps: h2_next follows the particles through the resampling kernels —
+    same particle counts and resampling statistics every step, masses conserved, positions close."""
+    sc = _scene(asph, "default-scene.yaml")
+    params = default_params.replace(support_length_estimation=mode)
+    g = asph.init_fluid_sim(params, sc, split_patterns, lib=cuda_lib)
+    o = asph.init_fluid_sim(params, sc, split_patterns, lib=oracle32)
+    for step in range(12):
+        g.single_step(); o.single_step()
+        gi, oi = g.step_info(), o.step_info()
+        for k in ("n_particles_end", "n_shared", "n_merged", "n_split_parents"):
+            assert gi[k] == oi[k], (step, k, gi, oi)
+    assert abs(float(g.get_field("mass").sum()) - float(o.get_field("mass").sum())) < 1e-5
+    assert _rel(g.get_field("position"), o.get_field("position"), 2.0) <= 1e-4
     g.close(); o.close()
