@@ -363,6 +363,21 @@ __global__ void k_split_extra(uint32_t n, uint32_t cap, const uint8_t* __restric
   }
 }
 
+// ---- IISPH2: particle_size_class outlives the step (the omega pass of the next step reads it) -------------------------
+__global__ void k_cls_copy(uint32_t n, const uint8_t* __restrict__ size_class, uint8_t* __restrict__ cls) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cls[i] = size_class[i];
+}
+__global__ void k_cls_compact(uint32_t n, const uint32_t* __restrict__ keep_scan, const uint8_t* __restrict__ size_class, uint8_t* __restrict__ cls_o) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (keep_scan[i + 1] != keep_scan[i]) cls_o[keep_scan[i]] = size_class[i];
+}
+__global__ void k_cls_fill(uint32_t first, uint32_t n, uint8_t v, uint8_t* __restrict__ cls) {  // appended children: ParticleVec::extend default
+  const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cls[i] = v;
+}
+
 AdaptArgs args_of(asph_sim* sim) {
   AdaptArgs A;
   const int c = sim->cur;
@@ -438,6 +453,11 @@ int launch_adaptivity(asph_sim* sim, float dt) {
   TRY(total_mass(sim, &m1));
   sim->adapt_rounds = 0;
   const PackedParams& P = sim->pp;
+  // IISPH2 reads the classes of the last resampling phase in the next step's omega pass
+  const bool track_cls = solver_iisph2(sim);
+  bool cls_done = false;
+  const bool classified = sim->share_enabled || (sim->step_number % 2 == 0 ? sim->merge_enabled : sim->split_enabled);
+  if (track_cls) { for (int b = 0; b < 2; b++) CUDA_TRY(sim->cls[b].ensure(sim->cap)); }
 
   if (sim->share_enabled) {  // simulation.rs:2747-2758
     TRY(classify(sim));
@@ -488,6 +508,11 @@ int launch_adaptivity(asph_sim* sim, float dt) {
         k_compact_extra<<<blocks, kThreads, 0, st>>>(n, keep, sim->hnext[c].p, sim->lamprev[c].p, sim->hnext[1 - c].p, sim->lamprev[1 - c].p);
         LAUNCH_CHECK();
       }
+      if (track_cls) {
+        k_cls_compact<<<blocks, kThreads, 0, st>>>(n, keep, sim->size_class.p, sim->cls[1 - c].p);
+        LAUNCH_CHECK();
+        cls_done = true;
+      }
       TRY(sync_ctl(sim));
       TRY(check_error_flags(sim));
       const uint32_t n_new = sim->ctl_host->n_new;
@@ -534,8 +559,21 @@ int launch_adaptivity(asph_sim* sim, float dt) {
       LAUNCH_CHECK();
       sim->lists_valid = false; sim->step_fields_valid = false;
       sim->n = n_new; sim->n_owned = n_new;
+      if (track_cls) {  // parents keep their class, appended children are Optimal
+        if (!sim->cls_valid) { for (int b = 0; b < 2; b++) CUDA_TRY(sim->cls[b].ensure(sim->cap)); }  // the capacity may just have grown
+        k_cls_copy<<<blocks, kThreads, 0, st>>>(n, sim->size_class.p, sim->cls[cc].p);
+        LAUNCH_CHECK();
+        k_cls_fill<<<(n_new - n + kThreads - 1) / kThreads, kThreads, 0, st>>>(n, n_new, ASPH_CLASS_OPTIMAL, sim->cls[cc].p);
+        LAUNCH_CHECK();
+        cls_done = true;
+      }
     }
   }
+  if (track_cls && !cls_done && classified) {  // same particle set as the last classify
+    k_cls_copy<<<(sim->n + kThreads - 1) / kThreads, kThreads, 0, st>>>(sim->n, sim->size_class.p, sim->cls[sim->cur].p);
+    LAUNCH_CHECK();
+  }
+  if (track_cls && (cls_done || classified)) sim->cls_valid = true;
   TRY(sync_ctl(sim));
   TRY(check_error_flags(sim));
   TRY(total_mass(sim, &m2));

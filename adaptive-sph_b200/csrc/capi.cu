@@ -82,7 +82,10 @@ int pack_params(asph_sim* sim, const asph_params* p) {
     if (!unverified) return unsupported("support_length_estimation != FromMass (kernels not yet verified on hardware; ASPH_UNVERIFIED_MODES=1 enables them)");
     if (sim->dist) return unsupported("support_length_estimation != FromMass across GPU slabs");
   }
-  if (p->pressure_solver_method == ASPH_SOLVER_IISPH2) return unsupported("pressure_solver_method IISPH2");
+  if (p->pressure_solver_method == ASPH_SOLVER_IISPH2) {
+    if (!unverified) return unsupported("pressure_solver_method IISPH2 (kernels not yet verified on hardware; ASPH_UNVERIFIED_MODES=1 enables them)");
+    if (sim->dist) return unsupported("pressure_solver_method IISPH2 across GPU slabs");
+  }
   if (p->viscosity_type == ASPH_VISC_XSPH) return unsupported("viscosity_type XSPH (todo!() in the reference)");
   if (p->level_estimation_after_advection) return unsupported("level_estimation_after_advection");
   return ASPH_OK;
@@ -259,6 +262,14 @@ static int physics_after_sort(asph_sim* sim, bool lvl, float f_ext) {
       return r;
     };
     switch (P.solver) {
+      case ASPH_SOLVER_IISPH2:  // simulation.rs:2262-2387
+        if (!guard(launch_omega(sim)) || !guard(launch_viscosity(sim)) || !guard(launch_source(sim, 3))) break;
+        pc_begin(sim, ASPH_PC_DENSITY_SOLVER);
+        if (!guard(solve(true, P.max_avg_density_error_iisph, &sim->info.last_avg_error_density))) break;
+        sim->info.density_iterations = iters; sim->info.density_sweeps = sweeps;
+        if (!guard(launch_scale_pressure(sim)) || !guard(launch_final_accel(sim, 3))) break;
+        pc_end(sim, ASPH_PC_DENSITY_SOLVER);
+        break;
       case ASPH_SOLVER_IISPH:  // simulation.rs:2389-2446
         if (!guard(launch_viscosity(sim)) || !guard(launch_source(sim, 2))) break;
         pc_begin(sim, ASPH_PC_DENSITY_SOLVER);
@@ -437,6 +448,7 @@ int asph_set_state(asph_sim* sim, const float* pos, const float* vel, const floa
   CUDA_TRY(cudaStreamSynchronize(sim->stream));
   sim->lists_valid = false; sim->level_valid = false; sim->step_fields_valid = false;
   sim->hdist_valid = false;  // h2_next restarts from the masses, as in FluidSimulation::new (simulation.rs:505-520)
+  sim->cls_valid = false;    // every particle Optimal (ParticleVec default)
   return ASPH_OK;
 }
 
@@ -505,7 +517,8 @@ void asph_destroy(asph_sim* sim) {
   sim->xyhm.release(); sim->packA.release(); sim->pconst.release(); sim->h_tmp.release(); sim->rho.release(); sim->lam_sum.release();
   sim->nrm.release(); sim->gB.release(); sim->lam_grad.release(); sim->key.release(); sim->cellcount.release(); sim->cellstart.release();
   sim->order.release(); sim->scan_sums.release(); sim->cnt.release(); sim->cnt_ext.release(); sim->far_idx.release(); sim->far_cnt.release(); sim->slice_base.release();
-  for (int b = 0; b < 2; b++) { sim->hnext[b].release(); sim->lamprev[b].release(); }
+  for (int b = 0; b < 2; b++) { sim->hnext[b].release(); sim->lamprev[b].release(); sim->cls[b].release(); }
+  sim->omega.release();
   sim->nbpool.release(); sim->hm.release(); sim->hv.release(); sim->size_class.release(); sim->flags.release(); sim->merge_partner.release();
   sim->cand.release(); for (int k = 0; k < 4; k++) sim->scratch_u[k].release();
   sim->merge_counter.release(); sim->stamp.release(); sim->stampkey.release(); sim->scratch_f.release(); sim->lut.release(); sim->split_pos.release();

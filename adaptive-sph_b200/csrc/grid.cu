@@ -280,6 +280,11 @@ __global__ void k_reorder_extra(uint32_t n, const uint32_t* __restrict__ order, 
   hnext_o[s] = hnext[src]; lamprev_o[s] = lamprev[src];
 }
 
+__global__ void k_reorder_cls(uint32_t n, const uint32_t* __restrict__ order, const uint8_t* __restrict__ cls, uint8_t* __restrict__ cls_o) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) cls_o[s] = cls[order[s]];
+}
+
 }  // namespace
 
 int sync_ctl(asph_sim* sim) {
@@ -338,6 +343,20 @@ int ensure_capacity(asph_sim* sim, uint32_t want) {
         sim->hnext[b] = h2; sim->lamprev[b] = l2;
       } else {
         CUDA_TRY(sim->hnext[b].ensure(newcap)); CUDA_TRY(sim->lamprev[b].ensure(newcap));
+      }
+    }
+  }
+  if (sim->cls_valid) {
+    for (int b = 0; b < 2; b++) {
+      if (b == sim->cur && old_n > 0) {
+        DevBuf<uint8_t> c2;
+        CUDA_TRY(c2.ensure(newcap));
+        CUDA_TRY(cudaMemcpyAsync(c2.p, sim->cls[b].p, old_n, cudaMemcpyDeviceToDevice, sim->stream));
+        CUDA_TRY(cudaStreamSynchronize(sim->stream));
+        sim->cls[b].release();
+        sim->cls[b] = c2;
+      } else {
+        CUDA_TRY(sim->cls[b].ensure(newcap));
       }
     }
   }
@@ -412,6 +431,10 @@ int launch_sort_and_grid(asph_sim* sim, float f_search) {
   LAUNCH_CHECK();
   if (hdist) {
     k_reorder_extra<<<blocks, kThreads, 0, st>>>(n, sim->order.p, sim->hnext[c].p, sim->lamprev[c].p, sim->hnext[1 - c].p, sim->lamprev[1 - c].p);
+    LAUNCH_CHECK();
+  }
+  if (sim->cls_valid) {  // IISPH2: the size classes of the last resampling phase follow the particles
+    k_reorder_cls<<<blocks, kThreads, 0, st>>>(n, sim->order.p, sim->cls[c].p, sim->cls[1 - c].p);
     LAUNCH_CHECK();
   }
   sim->cur = 1 - c;

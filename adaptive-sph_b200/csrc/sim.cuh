@@ -193,6 +193,11 @@ struct asph_sim {
   // Double buffered like `mass`; carried through the reorder, the merge compaction and the split.
   DevBuf<float> hnext[2], lamprev[2];
   bool hdist_valid = false;
+  // IISPH2 (simulation.rs:2262-2387): the correction factors of the step, and the size classes the LAST resampling phase
+  // assigned (particle_size_class outlives the step in the reference; the omega pass reads it), carried like hnext
+  DevBuf<float> omega;
+  DevBuf<uint8_t> cls[2];
+  bool cls_valid = false;
   int predicted_sweeps[2] = {1, 1};  // sweeps of the divergence / density solve in the previous step
   DevBuf<uint8_t> size_class, flags;  // flags: bit0 surface, bit1 insufficient neighbours
   DevBuf<uint32_t> merge_partner, front[2], cand, work[2], scratch_u[4];
@@ -288,7 +293,10 @@ inline bool op_w2020(const asph_sim* sim) { return sim->pp.opdisc == ASPH_OP_WIN
 int neighbors_grow(asph_sim* sim);
 // solver.cu
 int launch_viscosity(asph_sim* sim);
-int launch_source(asph_sim* sim, int kind);  // 0 divergence, 1 only density, 2 full
+int launch_source(asph_sim* sim, int kind);  // 0 divergence, 1 only density, 2 full, 3 full with the IISPH2 omega factors
+int launch_omega(asph_sim* sim);             // IISPH2: omega_i (simulation.rs:2263-2311)
+int launch_scale_pressure(asph_sim* sim);    // IISPH2: p /= sqrt(omega) after the solve (simulation.rs:2358-2360)
+inline bool solver_iisph2(const asph_sim* sim) { return sim->pp.solver == ASPH_SOLVER_IISPH2; }
 int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* iters_out, int* sweeps_out, double* avg_out);
 int launch_final_accel(asph_sim* sim, int mode);  // 1: v += dt a (xv pack); 2: hybrid integrate; 3: IISPH integrate
 // level.cu

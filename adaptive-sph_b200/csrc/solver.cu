@@ -354,7 +354,7 @@ k_viscosity(uint32_t n, NbLists L, const float4* __restrict__ xv_in, const float
 __global__ void __launch_bounds__(kThreads)
 k_source(uint32_t n, NbLists L, const float4* __restrict__ xv, const float2* __restrict__ hm, const float* __restrict__ rho,
          float4* __restrict__ pconst, float4* __restrict__ packP0, float4* __restrict__ packA, const StepCtl* __restrict__ ctl,
-         float rho0, int kind, int w2020) {
+         float rho0, int kind, int w2020, const float* __restrict__ omega) {
   __shared__ float4 s_pack[kSlots];
   __shared__ float2 s_hm[kSlots];
   // Winchenbach2020 operator: `hm` is {h, m / rho} (k_aii_w2020), every pair carries its own weight m_j / rho_j, and
@@ -381,13 +381,54 @@ k_source(uint32_t n, NbLists L, const float4* __restrict__ xv, const float2* __r
                             : for_each_pair<HM_WIN, false>(C, W, xv, hm, nullptr, me.x, me.y, own.x, own.y, body);
     sum *= scale;
     const float div = (w2020 ? sum : sum / rho_i) - (me.z * pc.x + me.w * pc.y);
-    s = -div / dt;
+    s = omega ? -div / (dt * omega[i]) : -div / dt;  // calculate_source_term_full_with_omega, simulation.rs:1678-1710
   }
-  if (kind != 0) s += -(rho0 - rho_i) / ((w2020 ? rho0 : rho_i) * dt * dt);  // next_density_estimate, simulation.rs:1633-1748
+  if (kind != 0) s += -(rho0 - rho_i) / (((w2020 || omega) ? rho0 : rho_i) * dt * dt);  // next_density_estimate, simulation.rs:1633-1748
   pc.w = s;
   pconst[i] = pc;
   packP0[i] = make_float4(me.x, me.y, 0.f, 0.f);
   packA[i] = make_float4(me.x, me.y, 0.f, 0.f);  // a^p of the first sweep: p = 0 everywhere => exactly zero (simulation.rs:1792-1807)
+}
+
+// ---------------------------------------------------------------------------------------------- IISPH2
+// omega_i = clamp(1 + H_i / (3 rho_i) * sum_j m_j dW/dH(|x_ij|, H_ij), 0.125, 2.5), H = 2h the support radius; a particle
+// classified Large by the last resampling phase uses its own term only (simulation.rs:2263-2311).
+__device__ __forceinline__ float dwdh(float d, float H) {
+  const float q = d / H;
+  const float cd = 40.f / (7.f * ASPH_PI_F);
+  return cd * -2.f / (H * H * H) * cubic_w(q) + cd / (H * H) * cubic_dw(q) * (-d / (H * H));
+}
+__global__ void __launch_bounds__(kThreads)
+k_omega(uint32_t n, NbLists L, const float4* __restrict__ xyhm, const float* __restrict__ rho, const uint8_t* __restrict__ cls,
+        float* __restrict__ omega) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 me = xyhm[i];
+  const float Hi = me.z * 2.f;
+  const float pre = Hi / (3.f * rho[i]);
+  float om = 1.f;
+  if (cls && cls[i] == ASPH_CLASS_LARGE) {
+    om += pre * me.w * dwdh(0.f, me.z * 2.f);
+  } else {
+    const NbCol col(L, i);
+    for (uint32_t k = 0; k < col.cn; k++) {
+      const float4 o = __ldg(&xyhm[col.get(k)]);
+      const float dx = me.x - o.x, dy = me.y - o.y;
+      om += pre * o.w * dwdh(sqrtf(dx * dx + dy * dy), ((me.z + o.z) * 0.5f) * 2.f);
+    }
+  }
+  omega[i] = fminf(2.5f, fmaxf(om, 0.125f));
+}
+// p /= sqrt(omega) on the pack that holds the solve's result (chosen like in k_accel)
+__global__ void __launch_bounds__(kThreads)
+k_scale_pressure(uint32_t n, float4* __restrict__ P0, float4* __restrict__ P1, const StepCtl* __restrict__ ctl, const float* __restrict__ omega) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4* pack = (ctl->solver.sweeps & 1) ? P1 : P0;
+  float4 v = pack[i];
+  const float s = sqrtf(omega[i]);
+  v.z /= s; v.w /= s;
+  pack[i] = v;
 }
 
 // ---------------------------------------------------------------------------------------------- K14
@@ -792,6 +833,24 @@ int launch_viscosity(asph_sim* sim) {
   return ASPH_OK;
 }
 
+int launch_omega(asph_sim* sim) {
+  const uint32_t n = sim->n;
+  if (n == 0) return ASPH_OK;
+  CUDA_TRY(sim->omega.ensure(sim->cap));
+  k_omega<<<(n + kThreads - 1) / kThreads, kThreads, 0, sim->stream>>>(n, lists_of(sim), sim->xyhm.p, sim->rho.p,
+                                                                       sim->cls_valid ? sim->cls[sim->cur].p : nullptr, sim->omega.p);
+  LAUNCH_CHECK();
+  return ASPH_OK;
+}
+
+int launch_scale_pressure(asph_sim* sim) {
+  const uint32_t n = sim->n;
+  if (n == 0) return ASPH_OK;
+  k_scale_pressure<<<(n + kThreads - 1) / kThreads, kThreads, 0, sim->stream>>>(n, sim->packP[0].p, sim->packP[1].p, sim->ctl, sim->omega.p);
+  LAUNCH_CHECK();
+  return ASPH_OK;
+}
+
 int launch_source(asph_sim* sim, int kind) {
   const uint32_t n = sim->n;
   if (n == 0) return ASPH_OK;
@@ -799,8 +858,10 @@ int launch_source(asph_sim* sim, int kind) {
   k_solver_reset<<<1, 64, 0, sim->stream>>>(sim->ctl);
   LAUNCH_CHECK();
   const bool w2020 = op_w2020(sim);
+  const float* omega = kind == 3 ? sim->omega.p : nullptr;
+  if (kind == 3) kind = 2;
   k_source<<<blocks, kThreads, 0, sim->stream>>>(n, lists_of(sim), sim->xv[sim->xv_cur].p, w2020 ? sim->hv.p : sim->hm.p, sim->rho.p, sim->pconst.p,
-                                                 sim->packP[0].p, sim->packA.p, sim->ctl, sim->pp.rest_density, kind, w2020 ? 1 : 0);
+                                                 sim->packP[0].p, sim->packA.p, sim->ctl, sim->pp.rest_density, kind, w2020 ? 1 : 0, omega);
   LAUNCH_CHECK();
   sim->p_cur = 0;
   return ASPH_OK;

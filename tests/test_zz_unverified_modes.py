@@ -9,7 +9,7 @@ switch goes away.
 
   * operator_discretization: Winchenbach2020 (simulation.rs:1571-1579, boundary_winchenbach2020.rs:207-213, 236-269;
     5 of the reference's media jobs) — k_aii_w2020 (neighbors.cu), k_source / k_sweep<1, ., ., W2020> (solver.cu).
-  * support_length_estimation: FromDistribution* (second half of this file) — never run on hardware.
+  * support_length_estimation: FromDistribution* and pressure_solver_method: IISPH2 (rest of this file) — never run on hardware.
 """
 import numpy as np
 import pytest
@@ -124,4 +124,31 @@ def test_support_length_from_distribution_with_resampling(asph, cuda_lib, oracle
             assert gi[k] == oi[k], (step, k, gi, oi)
     assert abs(float(g.get_field("mass").sum()) - float(o.get_field("mass").sum())) < 1e-5
     assert _rel(g.get_field("position"), o.get_field("position"), 2.0) <= 1e-4
+    g.close(); o.close()
+
+
+# ---- pressure_solver_method: IISPH2 (simulation.rs:2262-2387): k_omega, the omega-scaled source, k_scale_pressure (solver.cu),
+# the size classes of the last resampling phase carried to the next step (grid.cu, adapt.cu).  Never run on hardware.
+@never_run
+def test_iisph2_single_step_uniform(asph, cuda_lib, oracle32, default_params):
+    sc = asph.SceneConfig.dam_break(0.02)
+    pos, vel, mass = asph.scene_particles(sc)
+    vel = (np.random.default_rng(1).standard_normal(vel.shape) * 0.05).astype(np.float32)
+    params = _uniform_params(default_params, pressure_solver_method="IISPH2")
+    _one_step(asph, cuda_lib, oracle32, params, pos, vel, mass, asph.scene_boundary(sc, "AnalyticOverestimate"))
+
+
+@never_run
+def test_iisph2_default_scene_with_resampling(asph, cuda_lib, oracle32, default_params, split_patterns):
+    """C1, 12 full steps: the Large particles of each resampling phase take the single-term omega in the next step."""
+    sc = _scene(asph, "default-scene.yaml")
+    params = default_params.replace(pressure_solver_method="IISPH2")
+    g = asph.init_fluid_sim(params, sc, split_patterns, lib=cuda_lib)
+    o = asph.init_fluid_sim(params, sc, split_patterns, lib=oracle32)
+    for step in range(12):
+        g.single_step(); o.single_step()
+        gi, oi = g.step_info(), o.step_info()
+        for k in ("n_particles_end", "n_shared", "n_merged", "n_split_parents", "density_sweeps"):
+            assert gi[k] == oi[k], (step, k, gi, oi)
+    assert _rel(g.get_field("position"), o.get_field("position"), 2.0) <= 1e-5
     g.close(); o.close()
