@@ -70,7 +70,13 @@ int pack_params(asph_sim* sim, const asph_params* p) {
     }
   }
 
-  auto unsupported = [&](const char* what) { sim->last_error = std::string(what) + " is not implemented yet (SURVEY.md §8f)"; return ASPH_ERR_UNSUPPORTED; };
+  // A refused mode must not leak into the calls that go on after ASPH_ERR_UNSUPPORTED (asph_create, asph_build_neighbors
+  // only need the neighbour pass): the packed copy falls back to the plain variants of everything mode dependent.
+  auto unsupported = [&](const char* what) {
+    sim->last_error = std::string(what) + " is not implemented yet (SURVEY.md §8f)";
+    q.h_mode = ASPH_H_FROM_MASS; q.level_cut = 0.f; q.opdisc = ASPH_OP_CONSISTENT_SIMPLE_GRADIENT; q.solver = ASPH_SOLVER_HYBRID_DFSPH;
+    return ASPH_ERR_UNSUPPORTED;
+  };
   if (p->constrain_neighborhood_count) return unsupported("constrain_neighborhood_count");
   if (p->level_estimation_method == ASPH_LEVEL_CENTER_DIFF) return unsupported("level_estimation_method CenterDiff");
   // Modes whose kernels were written after the GPU budget of the round ran out and have not passed their parity tests

@@ -126,3 +126,27 @@ def test_every_media_job_of_the_reference_resolves(asph):
     # default-config.yaml (`.unwrap_or_else(|| panic!("not able to find attribute {}"))`, animation/mod.rs:96)
     assert sorted(stale) == ["constant-field.yaml", "density.yaml", "distance-to-neighbor.yaml", "render-test.yaml", "surface-distance.yaml"]
     assert all("visualization_params" in v or "fill_stash_with" in v for v in stale.values())
+
+
+@pytest.mark.gpu
+def test_jobs_on_the_gpu_match_the_oracle(asph, cuda_lib, oracle32, tmp_path):
+    """A still and a video job through the product library: same steps, same frame count, snapshot positions within
+    1e-6 of the domain size of the oracle's."""
+    still = {"time": 0.0055, "config_path": CFG, "scene": SMALL_SCENE, "png_file": "still.png", "output_stats": True,
+             "visualization_params": {"visualized_attribute": "Density"}, "update_attributes": {"max_dt": 0.002}}
+    clip = {"time": 0.005, "video_start_time": 0, "video_fps": 1000, "config_path": CFG, "scene": SMALL_SCENE, "png_file": "clip.mp4",
+            "visualization_params": {"visualized_attribute": "Velocity"}, "update_attributes": {"max_dt": 0.002}}
+    path = _write_jobs(tmp_path, [still, clip])
+    mg = asph.export_simulation_image([path], cuda_lib, out_dir=str(tmp_path / "gpu"))
+    mo = asph.export_simulation_image([path], oracle32, out_dir=str(tmp_path / "cpu"))
+    for a, b in zip(mg, mo):
+        assert a["backend"] == "cuda-sm100a" and b["backend"] == "oracle-f32"
+        for k in ("finished", "steps", "frames", "particles_first_step", "particles_end"):
+            assert a[k] == b[k], (k, a, b)
+    files = ["still.png.vtk"] + [os.path.join("clip.mp4.frames", os.path.basename(f))
+                                 for f in sorted(glob.glob(str(tmp_path / "cpu" / "clip.mp4.frames" / "file-*.vtk")))]
+    for f in files:
+        g = asph.read_vtk_file(str(tmp_path / "gpu" / f)); o = asph.read_vtk_file(str(tmp_path / "cpu" / f))
+        assert np.abs(g["position"] - o["position"]).max() <= 2e-6, f
+        assert np.allclose(g["mass"], o["mass"], rtol=1e-6), f
+    assert "simulation-step" in (tmp_path / "gpu" / "still.png.stat").read_text()
