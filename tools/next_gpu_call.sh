@@ -1,0 +1,14 @@
+#!/bin/bash
+# First GPU call of the next round (run as: gpurun --timeout 900 -- 'bash tools/next_gpu_call.sh').
+# 1. the parity tests that have not run on hardware yet, with their real outcomes (--runxfail shows tracebacks);
+# 2. the whole GPU suite as the driver runs it;
+# 3. one short bench line.
+# Everything lands in gpurun_out/ (merged back into the repo's gpurun_out/ by gpurun).
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+timeout 300 python -m pytest tests/test_zz_unverified_modes.py -q --runxfail --tb=short -p no:cacheprovider > gpurun_out/pending_modes.log 2>&1
+echo "pending modes: rc=$?"; tail -15 gpurun_out/pending_modes.log
+timeout 500 python -m pytest tests -q -m gpu -x -rxX -p no:cacheprovider > gpurun_out/gpu_suite.log 2>&1
+echo "gpu suite: rc=$?"; tail -8 gpurun_out/gpu_suite.log
+timeout 200 python bench.py --steps 8 --warmup 3 > gpurun_out/bench_short.json 2> gpurun_out/bench_short.err
+echo "bench: rc=$?"; cut -c1-600 gpurun_out/bench_short.json
