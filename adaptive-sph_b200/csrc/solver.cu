@@ -521,8 +521,6 @@ struct SweepStage {
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 struct SweepArgs {
   uint32_t n;
@@ -874,7 +872,6 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
   const uint32_t n = sim->n;
   *iters_out = 0; *sweeps_out = 0; *avg_out = 0;
   if (n == 0) return ASPH_OK;
-  const uint32_t blocks = (n + kThreads - 1) / kThreads;
   cudaStream_t st = sim->stream;
   const NbLists L = lists_of(sim);
   const uint32_t* gid = sim->dist ? sim->refid[sim->cur].p : nullptr;
