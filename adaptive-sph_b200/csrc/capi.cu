@@ -37,6 +37,7 @@ int pack_params(asph_sim* sim, const asph_params* p) {
   q.solver = p->pressure_solver_method; q.density_source = p->hybrid_dfsph_density_source_term;
   q.np_before_div = p->hybrid_dfsph_non_pressure_accel_before_divergence_free; q.penalty = p->boundary_penalty_term;
   q.sizing = p->sizing_function; q.opdisc = p->operator_discretization;
+  q.self_last = sim->rows4 ? 1 : 0;
   q.h_mode = p->support_length_estimation;
   q.level_cut = (q.h_mode == ASPH_H_FROM_DISTRIBUTION || q.h_mode == ASPH_H_FROM_DISTRIBUTION2) ? float(p->maximum_range) : 0.f;
   q.boundary_is_fluid_surface = p->boundary_is_fluid_surface;
@@ -481,6 +482,7 @@ int asph_create(const asph_params* params, const float* pos, const float* vel, c
   if (cudaMallocHost((void**)&sim->ctl_host, sizeof(StepCtl)) != cudaSuccess) return fail(ASPH_ERR_CUDA);
   memset(sim->ctl_host, 0, sizeof(StepCtl));
   sim->counters = counters_enabled != 0;
+  if (const char* e = getenv("ASPH_ROWS4")) sim->rows4 = atoi(e) != 0;
   if (boundary) sim->boundary = *boundary; else memset(&sim->boundary, 0, sizeof(sim->boundary));
   {  // λ / λ′ lookup tables (BoundaryWinchenbach2020::new, boundary_winchenbach2020.rs:33-45)
     std::vector<float> lam, dlam;

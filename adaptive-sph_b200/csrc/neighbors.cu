@@ -180,7 +180,7 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
       const float d2 = dist_sq_exact(__fsub_rn(xi, o.x), __fsub_rn(yi, o.y));
       if (d2 < support_sq_exact(hi, o.z, f_near)) {
         if (j - win0 < ASPH_PAIR_WIN) {
-          nb_store_w(slice, lane, kw++, (j - win0) * 16u);
+          if (!(P.self_last && j == i)) nb_store_w(slice, lane, kw++, (j - win0) * 16u);
         } else if (in_table) {
           far_idx[(i / ASPH_PAIR_BLOCK) * ASPH_PAIR_FAR + far_base + kt] = j;
           nb_store_w(slice, lane, kw++, (ASPH_PAIR_WIN + far_base + kt) * 16u);
@@ -192,6 +192,7 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
         nb_store_fe(slice, wide, lane, cw, ke++, j, bias);
       }
     });
+    if (P.self_last) nb_store_w(slice, lane, kw++, (i - win0) * 16u);  // the particle's own row closes the W segment (solver.cu, R4)
     for (uint32_t r = cw; r < nb_pad8(cw); r++) nb_store_w(slice, lane, r, (i - win0) * 16u);  // padding: the particle itself
     for (uint32_t k = cf; k < nb_pad4(cf); k++) nb_store_fe(slice, wide, lane, cw, k, i, bias);
   }

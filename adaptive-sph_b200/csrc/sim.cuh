@@ -112,6 +112,9 @@ struct PackedParams {  // SimulationParams rounded once to fp32 (what serde does
   // detector ignores neighbours beyond particle_radius * maximum_range, simulation.rs:698-723), 0 = no cut
   int h_mode;
   float level_cut;
+  // experiment (ASPH_ROWS4=1): the neighbour pass writes a particle's own W row LAST, so that the sweep kernels can stop
+  // one row early and in steps of 4 rows instead of 8 (solver.cu, R4)
+  int self_last;
 };
 
 template <class T> struct DevBuf {
@@ -232,6 +235,7 @@ struct asph_sim {
   uint64_t pc_calls[ASPH_PC_COUNT] = {0};
   cudaEvent_t ev_begin[ASPH_PC_COUNT], ev_end[ASPH_PC_COUNT];
   int sm_count = 148;
+  bool rows4 = false;  // ASPH_ROWS4=1 at asph_create: self row last + 4-row granularity in the sweep kernels (not the default yet)
   bool sweep_attr_done = false;  // dynamic shared-memory limit of the sweep kernels raised on this handle's device
   bool ctl_seen = false;  // ctl_host holds a control block read back from the device (possibly of the previous step)
   std::string last_error;

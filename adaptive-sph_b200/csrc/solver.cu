@@ -237,7 +237,10 @@ __device__ __forceinline__ void pair_apply(const float4& o, const float2& t, flo
     f(o, dx, dy, t.y * pair_g(d2, hij), hij, a);
   }
 }
-template <int HM, bool AUX, class F>
+// R4 (experiment, ASPH_ROWS4=1): the neighbour pass wrote the particle's own row last in the W segment; it contributes
+// nothing to any gradient sum, so the loop stops one row early, and it runs in steps of 4 rows instead of 8 — on the resting
+// lattice (12 neighbours + self) that is 12 rows per particle instead of 16.
+template <int HM, bool AUX, bool R4 = false, class F>
 __device__ __forceinline__ float for_each_pair(const PairCol& P, const PairWindow& W, const float4* __restrict__ pack,
                                                const float2* __restrict__ hm, const float* __restrict__ aux, float xi, float yi, float hi,
                                                float mi, F f) {
@@ -246,10 +249,11 @@ __device__ __forceinline__ float for_each_pair(const PairCol& P, const PairWindo
   const float inv2h = fast_rcp(2.f * hi);
   const PairShape shape(inv2h);
   // ---- window segment: the two prefetched chunks, then (long columns only) chunks fetched on demand
-  auto chunk = [&](const uint4& v) {
+  auto chunk = [&](const uint4& v, uint32_t rows_left) {
     const uint32_t off[8] = {v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16, v.z & 0xffffu, v.z >> 16, v.w & 0xffffu, v.w >> 16};
 #pragma unroll
     for (int half = 0; half < 2; half++) {
+      if (R4 && half == 1 && rows_left <= 4u) break;
       float4 o[4];
       float2 t[4];
       float a[4];
@@ -266,14 +270,15 @@ __device__ __forceinline__ float for_each_pair(const PairCol& P, const PairWindo
       for (int u = 0; u < 4; u++) pair_apply<HM, AUX>(o[u], t[u], a[u], xi, yi, hi, shape, f);
     }
   };
-  if (col.cw > 0u) chunk(P.c0);
-  if (col.cw > 8u) chunk(P.c1);
-  if (col.cw > 16u) {
+  const uint32_t cw = R4 ? (col.cw > 0u ? col.cw - 1u : 0u) : col.cw;  // rows to process
+  if (cw > 0u) chunk(P.c0, cw);
+  if (cw > 8u) chunk(P.c1, cw - 8u);
+  if (cw > 16u) {
     uint4 nxt = col.raw8(16u);
-    for (uint32_t k0 = 16u; k0 < col.cw; k0 += 8u) {
+    for (uint32_t k0 = 16u; k0 < cw; k0 += 8u) {
       const uint4 v = nxt;
-      if (k0 + 8u < col.cw) nxt = col.raw8(k0 + 8u);
-      chunk(v);
+      if (k0 + 8u < cw) nxt = col.raw8(k0 + 8u);
+      chunk(v, cw - k0);
     }
   }
   // ---- far segment (divergent: most threads have none)
@@ -541,10 +546,11 @@ struct SweepArgs {
 
 // W2020 (update pass under the Winchenbach2020 operator): `hm` is {h, m / rho} (k_aii_w2020), so
 // every pair carries its own weight m_j / rho_j, and the pair sum is not divided by rho_i (simulation.rs:1571-1575).
-template <int PASS, bool HMWIN, bool PEER, bool W2020 = false>
+template <int PASS, bool HMWIN, bool PEER, bool W2020 = false, bool R4 = false>
 __global__ void __launch_bounds__(kThreads, (HMWIN || PEER) ? 3 : 4)
 k_sweep(const SweepArgs A) {
   static_assert(!W2020 || (PASS == 1 && HMWIN), "the Winchenbach2020 variant is an update pass with the {h, m / rho} window");
+  static_assert(!R4 || (!PEER && !W2020), "the 4-row variant exists for the single-GPU default operator only");
   extern __shared__ __align__(16) unsigned char sweep_smem[];
   typedef SweepStage<HMWIN> Stage;
   Stage* stages = reinterpret_cast<Stage*>(sweep_smem);
@@ -687,8 +693,8 @@ k_sweep(const SweepArgs A) {
           const float f = c * (me.z + o.z);
           ax -= f * dx; ay -= f * dy;
         };
-        const float scale = uni ? for_each_pair<HM_UNI, false>(C, W, pack, A.hm, nullptr, me.x, me.y, own.x, own.y, body)
-                                : for_each_pair<HMWIN ? HM_WIN : HM_GLOBAL, false>(C, W, pack, A.hm, nullptr, me.x, me.y, own.x, own.y, body);
+        const float scale = uni ? for_each_pair<HM_UNI, false, R4>(C, W, pack, A.hm, nullptr, me.x, me.y, own.x, own.y, body)
+                                : for_each_pair<HMWIN ? HM_WIN : HM_GLOBAL, false, R4>(C, W, pack, A.hm, nullptr, me.x, me.y, own.x, own.y, body);
         const float2 g = *reinterpret_cast<const float2*>(&S.own4[tid]);
         ax = ax * scale - me.w * g.x;
         ay = ay * scale - me.w * g.y;
@@ -705,8 +711,8 @@ k_sweep(const SweepArgs A) {
           const PairCol C(col, S.chunk[0][tid], S.chunk[1][tid]);
           float sum = 0.f;
           auto body = [&](const float4& o, float dx, float dy, float c, float, float) { sum += c * ((o.z - me.z) * dx + (o.w - me.w) * dy); };
-          const float scale = uni ? for_each_pair<HM_UNI, false>(C, W, pack, A.hm, nullptr, me.x, me.y, own.x, own.y, body)
-                                  : for_each_pair<HMWIN ? HM_WIN : HM_GLOBAL, false>(C, W, pack, A.hm, nullptr, me.x, me.y, own.x, own.y, body);
+          const float scale = uni ? for_each_pair<HM_UNI, false, R4>(C, W, pack, A.hm, nullptr, me.x, me.y, own.x, own.y, body)
+                                  : for_each_pair<HMWIN ? HM_WIN : HM_GLOBAL, false, R4>(C, W, pack, A.hm, nullptr, me.x, me.y, own.x, own.y, body);
           // reciprocals by the SFU (1 ulp): the relaxed update does not need correctly rounded quotients, and three
           // IEEE divisions would be a quarter of this thread's instructions outside the pair loop
           inv_rho = fast_rcp(rho_i);
@@ -896,11 +902,16 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
     CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(k_sweep<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
     CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
+    CUDA_TRY((cudaFuncSetAttribute(k_sweep<0, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
+    CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
+    CUDA_TRY((cudaFuncSetAttribute(k_sweep<0, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small)));
+    CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small)));
     CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
     CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
     sim->sweep_attr_done = true;
   }
   const bool p2p = dist_p2p(sim);
+  const bool r4 = sim->rows4 && !sim->dist && !w2020;  // the lists were written self-last (pack_params: self_last)
   SweepArgs A;
   A.n = n; A.L = L; A.P0 = sim->packP[0].p; A.P1 = sim->packP[1].p; A.P0w = sim->packP[0].p; A.P1w = sim->packP[1].p;
   A.packA = sim->packA.p; A.hm = sim->hm.p; A.gB = sim->gB.p; A.pconst = sim->pconst.p; A.rho = sim->rho.p; A.ctl = sim->ctl; A.gid = gid;
@@ -917,7 +928,8 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
       if (launched > 0) {  // sweep 0: a^p = 0 was written by k_source
         A.hm = sim->hm.p;
         A.peer = dist_peer_args(sim, true, !p2p, 0, false);  // waits for the previous sweep's p' ghosts; publishes a^p
-        if (p2p) { if (hmwin) k_sweep<0, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, true><<<grid, kThreads, smem, st>>>(A); }
+        if (r4) { if (hmwin) k_sweep<0, true, false, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, false, false, true><<<grid, kThreads, smem, st>>>(A); }
+        else if (p2p) { if (hmwin) k_sweep<0, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, true><<<grid, kThreads, smem, st>>>(A); }
         else { if (hmwin) k_sweep<0, true, false><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, false><<<grid, kThreads, smem, st>>>(A); }
         LAUNCH_CHECK();
         if (time_it) cudaEventRecord(tm.e1, st);
@@ -928,7 +940,8 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
       if (time_it) cudaEventRecord(tm.e1b, st);
       A.hm = w2020 ? sim->hv.p : sim->hm.p;
       A.peer = dist_peer_args(sim, launched > 0, p2p && launched > 0, 1 + ((launched + 1) & 1), true);  // waits for the a^p ghosts and the previous sweep's totals; publishes p' and its own
-      if (w2020) { if (p2p) k_sweep<1, true, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, true, false, true><<<grid, kThreads, smem, st>>>(A); }
+      if (r4) { if (hmwin) k_sweep<1, true, false, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, false, false, true><<<grid, kThreads, smem, st>>>(A); }
+      else if (w2020) { if (p2p) k_sweep<1, true, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, true, false, true><<<grid, kThreads, smem, st>>>(A); }
       else if (p2p) { if (hmwin) k_sweep<1, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, true><<<grid, kThreads, smem, st>>>(A); }
       else { if (hmwin) k_sweep<1, true, false><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, false><<<grid, kThreads, smem, st>>>(A); }
       LAUNCH_CHECK();

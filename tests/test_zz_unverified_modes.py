@@ -152,3 +152,56 @@ def test_iisph2_default_scene_with_resampling(asph, cuda_lib, oracle32, default_
             assert gi[k] == oi[k], (step, k, gi, oi)
     assert _rel(g.get_field("position"), o.get_field("position"), 2.0) <= 1e-5
     g.close(); o.close()
+
+
+# ---- experiment ASPH_ROWS4=1 (not a mode of the reference: a faster row schedule for the sweep kernels):
+# the neighbour pass writes the particle's own row last, k_sweep<., ., ., ., R4> stops one row early and in steps of 4 rows.
+# Never run on hardware; results must stay within the tolerances of the default schedule.
+@pytest.fixture
+def rows4(monkeypatch):
+    monkeypatch.setenv("ASPH_ROWS4", "1")
+    monkeypatch.delenv("ASPH_UNVERIFIED_MODES", raising=False)
+
+
+@never_run
+def test_rows4_neighbor_sets_bit_exact(asph, cuda_lib, oracle32, default_params, rows4):
+    from test_gpu_parity import _point_clouds
+    b = asph.scene_boundary(_scene(asph, "default-scene.yaml"), "AnalyticOverestimate")
+    for name, (pos, mass) in _point_clouds(asph).items():
+        g, o = _pair(asph, cuda_lib, oracle32, default_params, pos, np.zeros_like(pos), mass, b)
+        g.build_neighbors(np.float32(2.0)); o.build_neighbors(np.float32(2.0))
+        go, gi = g.neighbors_csr(); oo, oi = o.neighbors_csr()
+        assert np.array_equal(go, oo) and np.array_equal(gi, oi), name
+        g.close(); o.close()
+
+
+@never_run
+@pytest.mark.parametrize("solver", ["HybridDFSPH", "IISPH"])
+def test_rows4_single_step_uniform(asph, cuda_lib, oracle32, default_params, solver, rows4):
+    from test_gpu_parity import _single_step_uniform
+    _single_step_uniform(asph, cuda_lib, oracle32, default_params, solver)
+
+
+@never_run
+def test_rows4_single_step_mixed_sizes(asph, cuda_lib, oracle32, default_params, rows4):
+    sc = asph.SceneConfig.dam_break(0.02)
+    pos, vel, mass = asph.scene_particles(sc)
+    rng = np.random.default_rng(2)
+    pos = (pos + rng.uniform(-0.2, 0.2, pos.shape).astype(np.float32) * np.float32(0.02)).astype(np.float32)
+    mass = (mass * np.exp(rng.uniform(-np.log(2.0), np.log(2.0), mass.shape))).astype(np.float32)
+    vel = (rng.standard_normal(vel.shape) * 0.05).astype(np.float32)
+    _one_step(asph, cuda_lib, oracle32, _uniform_params(default_params), pos, vel, mass, asph.scene_boundary(sc, "AnalyticOverestimate"))
+
+
+@never_run
+def test_rows4_default_scene_with_resampling(asph, cuda_lib, oracle32, default_params, split_patterns, rows4):
+    sc = _scene(asph, "default-scene.yaml")
+    g = asph.init_fluid_sim(default_params, sc, split_patterns, lib=cuda_lib)
+    o = asph.init_fluid_sim(default_params, sc, split_patterns, lib=oracle32)
+    for step in range(20):
+        g.single_step(); o.single_step()
+        gi, oi = g.step_info(), o.step_info()
+        for k in ("n_particles_end", "n_shared", "n_merged", "n_split_parents", "div_sweeps", "density_sweeps"):
+            assert gi[k] == oi[k], (step, k, gi, oi)
+    assert _rel(g.get_field("position"), o.get_field("position"), 2.0) <= 1e-5
+    g.close(); o.close()
