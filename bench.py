@@ -264,7 +264,8 @@ def run_ours(args):
                    "avg_div_sweeps": sweeps_div / max(K, 1), "avg_density_sweeps": sweeps_den / max(K, 1),
                    "timing": "CUDA events on the library stream around every step (PerformanceCounters 'simulation-step')",
                    "wall_ms_per_step": wall * 1e3 / max(K, 1), "phase_ms_per_step": phases,
-                   "particle_sweeps_per_s": particle_sweeps_per_s},
+                   "particle_sweeps_per_s": particle_sweeps_per_s,
+                   "switches": {k: os.environ[k] for k in ("ASPH_ROWS4", "ASPH_SWEEP_GRID", "ASPH_UNVERIFIED_MODES") if k in os.environ}},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
     }
     out.update(extra)
