@@ -150,3 +150,65 @@ def test_run_on_the_gpu(exe, tmp_path):
     assert "5 steps" in out.stdout and "backend cuda-sm100a" in out.stdout
     pos, vel, mass = _read_dump(dump)
     assert len(mass) > 1035 and np.all(np.isfinite(pos))
+
+
+def _same_snapshot(asph, a, b, exact=True):
+    sa, sb = asph.read_vtk_file(a), asph.read_vtk_file(b)
+    assert set(sa) == set(sb), (sorted(sa), sorted(sb))
+    for k in sa:
+        if k == "distances" or not exact:
+            assert np.allclose(sa[k], sb[k], rtol=1e-6, atol=1e-7), k
+        else:
+            assert np.array_equal(sa[k], sb[k]), k
+
+
+def test_vtk_snapshots_equal_the_python_exporter(asph, oracle32, exe, tmp_path):
+    """`run --vtk-dir`: same files, same arrays as the Python VtkExporter on the same run (polygon boundary: lines,
+    distances and lambda arrays included)."""
+    import importlib
+    cli = importlib.import_module("adaptive-sph_b200.cli")
+    over = tmp_path / "over.yaml"
+    over.write_text("init_boundary_handler: AnalyticUnderestimate\n")
+    out = _run(exe, "run", CFG, SCENE, "--max-steps", "3", "-c", str(over), "--vtk-dir", str(tmp_path / "cpp"), "--lib", ORACLE, "-q")
+    assert out.returncode == 0, out.stderr
+    assert cli.main(["run", CFG, SCENE, "--max-steps", "3", "-c", str(over), "--vtk-dir", str(tmp_path / "py"), "-q"], lib=oracle32) == 0
+    names = sorted(os.listdir(tmp_path / "py"))
+    assert sorted(os.listdir(tmp_path / "cpp")) == names == ["my-sph-00001.vtk", "my-sph-00002.vtk", "my-sph-00003.vtk", "my-sph.vtk.series"]
+    for n in names[:3]:
+        _same_snapshot(asph, str(tmp_path / "cpp" / n), str(tmp_path / "py" / n))
+        assert os.path.getsize(tmp_path / "cpp" / n) == os.path.getsize(tmp_path / "py" / n)
+    sc, sp = json.load(open(tmp_path / "cpp" / names[3])), json.load(open(tmp_path / "py" / names[3]))
+    assert [f["name"] for f in sc["files"]] == [f["name"] for f in sp["files"]]
+    assert np.allclose([f["time"] for f in sc["files"]], [f["time"] for f in sp["files"]], rtol=1e-6)
+
+
+def test_image_jobs_equal_the_python_exporter(asph, oracle32, exe, tmp_path):
+    small = {"boundary": {"type": "box", "width": 2, "height": 2},
+             "blocks": [{"pos": [-0.9, -0.9], "size": [0.4, 0.5], "spacing": 0.03, "volume_fill_ratio": 0.93, "velocity": [0, 0]}]}
+    still = {"time": 0.0055, "config_path": CFG, "scene": small, "png_file": "still.png", "output_stats": True,
+             "visualization_params": {"visualized_attribute": "Density"}, "update_attributes": {"max_dt": 0.002}}
+    clip = {"time": 0.005, "video_start_time": 0, "video_fps": 1000, "config_path": CFG, "scene_file": SCENE, "png_file": "sub/clip.mp4",
+            "visualization_params": {"visualized_attribute": "Velocity"}, "update_attributes": {"max_dt": 0.002, "splitting": False}}
+    jobs = tmp_path / "jobs.yaml"
+    jobs.write_text(yaml.safe_dump([still, clip]))
+    out = _run(exe, "image", str(jobs), "--out-dir", str(tmp_path / "cpp"), "--lib", ORACLE, "-q")
+    assert out.returncode == 0, out.stderr
+    assert "2 job(s), 2 reached their export time" in out.stdout
+    man = asph.export_simulation_image([str(jobs)], oracle32, out_dir=str(tmp_path / "py"), log=lambda *a: None)
+    _same_snapshot(asph, str(tmp_path / "cpp" / "still.png.vtk"), str(tmp_path / "py" / "still.png.vtk"))
+    fc = sorted(glob.glob(str(tmp_path / "cpp" / "sub" / "clip.mp4.frames" / "file-*.vtk")))
+    fp = sorted(glob.glob(str(tmp_path / "py" / "sub" / "clip.mp4.frames" / "file-*.vtk")))
+    assert len(fc) == len(fp) == man[1]["frames"]
+    for a, b in zip(fc, fp):
+        _same_snapshot(asph, a, b)
+    mc = json.load(open(tmp_path / "cpp" / "still.png.job.json"))
+    assert mc["finished"] and mc["steps"] == man[0]["steps"] and mc["particles_end"] == man[0]["particles_end"]
+    assert "simulation-step" in (tmp_path / "cpp" / "still.png.stat").read_text()
+    # the reference's panics
+    bad = tmp_path / "bad.yaml"
+    bad.write_text(yaml.safe_dump([dict(still, update_attributes={"nope": 1})]))
+    out = _run(exe, "image", str(bad), "--out-dir", str(tmp_path / "x"), "--lib", ORACLE)
+    assert out.returncode == 1 and "not able to find attribute nope" in out.stderr
+    bad.write_text(yaml.safe_dump([dict(still, scene_file=SCENE)]))
+    out = _run(exe, "image", str(bad), "--out-dir", str(tmp_path / "x"), "--lib", ORACLE)
+    assert out.returncode == 1 and "Not both" in out.stderr
