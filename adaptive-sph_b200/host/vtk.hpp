@@ -2,7 +2,7 @@
 // (platform/desktop/vtk_exporter.rs:17-167, 256-367): legacy VTK 4.2, BINARY (big endian), DATASET
 // POLYDATA with POINTS (z = 0; the end points of the boundary lines appended), VERTICES, LINES and one SCALARS array per
 // field (float x 1, float x 3 for vectors, unsigned_char for flags), plus the `<basename>.vtk.series` index.  Same bytes as
-// adaptive-sph_b200/vtk.py writes (tests/test_cpp_host.py reads both back).
+// adaptive-sph_b200/vtk.py writes (tests/test_native_host.py reads both back).
 #pragma once
 #include <algorithm>
 #include <cmath>

@@ -4,7 +4,7 @@
 // block mappings and block sequences by indentation (including "- key: value" items, nested "- - x" sequences and
 // sequences at the indentation of their key), flow sequences "[a, b]" and flow mappings "{a: b}", plain / single- /
 // double-quoted scalars, "#" comments, "---" document markers.  Not supported (and not used by those files): anchors,
-// tags, multi-line scalars, multiple documents.  tests/test_cpp_host.py compares the parse of every shipped file — and,
+// tags, multi-line scalars, multiple documents.  tests/test_native_host.py compares the parse of every shipped file — and,
 // in the build container, of every YAML file of the reference — with PyYAML.
 #pragma once
 #include <cstdlib>
