@@ -550,7 +550,7 @@ template <int PASS, bool HMWIN, bool PEER, bool W2020 = false, bool R4 = false>
 __global__ void __launch_bounds__(kThreads, (HMWIN || PEER) ? 3 : 4)
 k_sweep(const SweepArgs A) {
   static_assert(!W2020 || (PASS == 1 && HMWIN), "the Winchenbach2020 variant is an update pass with the {h, m / rho} window");
-  static_assert(!R4 || (!PEER && !W2020), "the 4-row variant exists for the single-GPU default operator only");
+  static_assert(!R4 || !W2020, "the 4-row variant exists for the default operators only");
   extern __shared__ __align__(16) unsigned char sweep_smem[];
   typedef SweepStage<HMWIN> Stage;
   Stage* stages = reinterpret_cast<Stage*>(sweep_smem);
@@ -906,12 +906,16 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
     CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
     CUDA_TRY((cudaFuncSetAttribute(k_sweep<0, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small)));
     CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small)));
+    CUDA_TRY((cudaFuncSetAttribute(k_sweep<0, true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
+    CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
+    CUDA_TRY((cudaFuncSetAttribute(k_sweep<0, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small)));
+    CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small)));
     CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
     CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
     sim->sweep_attr_done = true;
   }
   const bool p2p = dist_p2p(sim);
-  const bool r4 = sim->rows4 && !sim->dist && !w2020;  // the lists were written self-last (pack_params: self_last)
+  const bool r4 = sim->rows4 && !w2020;  // the lists were written self-last (pack_params: self_last)
   SweepArgs A;
   A.n = n; A.L = L; A.P0 = sim->packP[0].p; A.P1 = sim->packP[1].p; A.P0w = sim->packP[0].p; A.P1w = sim->packP[1].p;
   A.packA = sim->packA.p; A.hm = sim->hm.p; A.gB = sim->gB.p; A.pconst = sim->pconst.p; A.rho = sim->rho.p; A.ctl = sim->ctl; A.gid = gid;
@@ -928,7 +932,8 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
       if (launched > 0) {  // sweep 0: a^p = 0 was written by k_source
         A.hm = sim->hm.p;
         A.peer = dist_peer_args(sim, true, !p2p, 0, false);  // waits for the previous sweep's p' ghosts; publishes a^p
-        if (r4) { if (hmwin) k_sweep<0, true, false, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, false, false, true><<<grid, kThreads, smem, st>>>(A); }
+        if (r4 && p2p) { if (hmwin) k_sweep<0, true, true, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, true, false, true><<<grid, kThreads, smem, st>>>(A); }
+        else if (r4) { if (hmwin) k_sweep<0, true, false, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, false, false, true><<<grid, kThreads, smem, st>>>(A); }
         else if (p2p) { if (hmwin) k_sweep<0, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, true><<<grid, kThreads, smem, st>>>(A); }
         else { if (hmwin) k_sweep<0, true, false><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, false><<<grid, kThreads, smem, st>>>(A); }
         LAUNCH_CHECK();
@@ -940,7 +945,8 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
       if (time_it) cudaEventRecord(tm.e1b, st);
       A.hm = w2020 ? sim->hv.p : sim->hm.p;
       A.peer = dist_peer_args(sim, launched > 0, p2p && launched > 0, 1 + ((launched + 1) & 1), true);  // waits for the a^p ghosts and the previous sweep's totals; publishes p' and its own
-      if (r4) { if (hmwin) k_sweep<1, true, false, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, false, false, true><<<grid, kThreads, smem, st>>>(A); }
+      if (r4 && p2p) { if (hmwin) k_sweep<1, true, true, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, true, false, true><<<grid, kThreads, smem, st>>>(A); }
+      else if (r4) { if (hmwin) k_sweep<1, true, false, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, false, false, true><<<grid, kThreads, smem, st>>>(A); }
       else if (w2020) { if (p2p) k_sweep<1, true, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, true, false, true><<<grid, kThreads, smem, st>>>(A); }
       else if (p2p) { if (hmwin) k_sweep<1, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, true><<<grid, kThreads, smem, st>>>(A); }
       else { if (hmwin) k_sweep<1, true, false><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, false><<<grid, kThreads, smem, st>>>(A); }

@@ -156,6 +156,7 @@ def run(args, A, rank, world):
                        "preroll_steps": pre_steps, "preroll_time_s": args.preroll_time, "replay_window_steps": window, "failed_steps_replayed": state["restarts"],
                        "particles": n_global, "owned_per_rank": [int(x.item()) for x in owned_all],
                        "l2": "working set per GPU (~400 MB) exceeds the 126 MB L2; no flush",
+                       "switches": {k: os.environ[k] for k in ("ASPH_ROWS4", "ASPH_DIST_P2P", "ASPH_P2P_EDGE_FIRST", "ASPH_SWEEP_GRID") if k in os.environ},
                        "avg_div_sweeps": sweeps_div / max(K, 1), "avg_density_sweeps": sweeps_den / max(K, 1),
                        "timing": "max over ranks of the CUDA-event time of the K steps on the library stream; barrier + synchronize on both sides",
                        "wall_ms_per_step": wall_ms_max / max(K, 1),

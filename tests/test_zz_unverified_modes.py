@@ -205,3 +205,16 @@ def test_rows4_default_scene_with_resampling(asph, cuda_lib, oracle32, default_p
             assert gi[k] == oi[k], (step, k, gi, oi)
     assert _rel(g.get_field("position"), o.get_field("position"), 2.0) <= 1e-5
     g.close(); o.close()
+
+
+@never_run
+def test_rows4_two_gpu_pressure_solve_matches_single_gpu(monkeypatch):
+    """The PEER instantiations of the 4-row sweep kernels (needs 2 GPUs; the single-GPU reference run inside the worker
+    uses the 4-row kernels as well)."""
+    import test_dist_gpu as D
+    if D._gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("ASPH_ROWS4", "1")
+    rep = D._run(2, 4, "HybridDFSPH", mode="random")
+    D._check(rep, 1e-6)
+    assert rep["sweeps_equal"], rep
