@@ -80,8 +80,8 @@ def write_scene(src, dst, title):
            f"boundary: {{type: {b['type']}, width: {scalar(b['width'])}, height: {scalar(b['height'])}}}", "blocks:"]
     for blk in m["blocks"]:
         vec = lambda v: "[" + ", ".join(scalar(x) for x in v) + "]"
-        out.append(f"  - {{pos: {vec(blk['pos'])}, size: {vec(blk['size'])}, spacing: {scalar(blk['spacing'])}, "
-                   f"volume_fill_ratio: {scalar(blk['volume_fill_ratio'])}, velocity: {vec(blk['velocity'])}}}")
+        out.append(f"  - {{spacing: {scalar(blk['spacing'])}, volume_fill_ratio: {scalar(blk['volume_fill_ratio'])}, pos: {vec(blk['pos'])}, "
+                   f"size: {vec(blk['size'])}, velocity: {vec(blk['velocity'])}}}")
     with open(dst, "w") as f:
         f.write("\n".join(out) + "\n")
 
