@@ -16,7 +16,7 @@ import pytest
 
 from test_gpu_parity import _compare_step_fields, _pair, _rel, _scene, _uniform_params
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(90)]
 pending = pytest.mark.xfail(strict=False, reason="failed in its only hardware run (stale flag after a list-pool retry); fixed, re-run pending")
 
 
