@@ -154,6 +154,18 @@ __device__ __forceinline__ float pair_g(float d2, float hij) {
   const float inv2h = fast_rcp(2.f * hij);
   return (ASPH_KNORM * inv2h * inv2h * inv2h) * PairShape(inv2h)(d2);
 }
+// The same value from h_i + h_j = 2 h_ij with the four per-pair constants of PairShape folded away (the experimental 4-row
+// sweep kernels, solver.cu R4): i = 1 / (h_i + h_j);  q < 1/2: i (18 q - 12);  q >= 1/2: i (12 - 6 q) - 6 / r.
+__device__ __forceinline__ float pair_g_sum(float d2, float hsum) {
+  const float i = fast_rcp(hsum);
+  const float inv_r = fast_rsqrt(d2);
+  const float q = (d2 * inv_r) * i;
+  const float s = q < 0.5f ? fmaf(q, 18.f, -12.f) : fmaf(q, -6.f, 12.f);
+  float g = s * i;
+  if (!(q < 0.5f)) g = fmaf(inv_r, -6.f, g);
+  g = q > 1.0e-5f ? g : 0.f;
+  return ((ASPH_KNORM * i) * (i * i)) * g;
+}
 // 16-byte / 8-byte / 4-byte shared-memory loads by 32-bit shared address (one LEA + LDS per gather)
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   float4 v;

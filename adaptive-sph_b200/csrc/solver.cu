@@ -225,13 +225,15 @@ struct PairCol {  // a thread's column header plus its first 16 window rows, req
 // (every f is linear in c).  The window segment of a column is consumed 8 rows at a time — the gathers, then the
 // arithmetic; padding rows point at the particle itself (zero distance => c = 0), so there are no per-entry checks.
 // The index chunk two iterations ahead is always in flight.  The far segment follows 4 rows at a time from global memory.
-template <int HM, bool AUX, class F>
+template <int HM, bool AUX, bool R4 = false, class F>
 __device__ __forceinline__ void pair_apply(const float4& o, const float2& t, float a, float xi, float yi, float hi, const PairShape& shape, F& f) {
   constexpr bool UNI = HM == HM_UNI;
   const float dx = xi - o.x, dy = yi - o.y;
   const float d2 = dx * dx + dy * dy;
   if (UNI) {
     f(o, dx, dy, shape(d2), hi, a);
+  } else if (R4) {  // the sweep bodies use neither h_ij nor the aux value
+    f(o, dx, dy, t.y * pair_g_sum(d2, hi + t.x), 0.f, a);
   } else {
     const float hij = (hi + t.x) * 0.5f;
     f(o, dx, dy, t.y * pair_g(d2, hij), hij, a);
@@ -267,7 +269,7 @@ __device__ __forceinline__ float for_each_pair(const PairCol& P, const PairWindo
         a[u] = AUX ? *reinterpret_cast<const float*>(reinterpret_cast<const char*>(W.wa) + (of >> 2)) : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 4; u++) pair_apply<HM, AUX>(o[u], t[u], a[u], xi, yi, hi, shape, f);
+      for (int u = 0; u < 4; u++) pair_apply<HM, AUX, R4>(o[u], t[u], a[u], xi, yi, hi, shape, f);
     }
   };
   const uint32_t cw = R4 ? (col.cw > 0u ? col.cw - 1u : 0u) : col.cw;  // rows to process
@@ -295,7 +297,7 @@ __device__ __forceinline__ float for_each_pair(const PairCol& P, const PairWindo
       a[u] = AUX ? __ldg(aux + j[u]) : 0.f;
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++) pair_apply<HM, AUX>(o[u], t[u], a[u], xi, yi, hi, shape, f);
+    for (int u = 0; u < 4; u++) pair_apply<HM, AUX, R4>(o[u], t[u], a[u], xi, yi, hi, shape, f);
   }
   return UNI ? mi * (ASPH_KNORM * inv2h * inv2h * inv2h) : 1.f;
 }
