@@ -549,7 +549,7 @@ struct SweepArgs {
 // W2020 (update pass under the Winchenbach2020 operator): `hm` is {h, m / rho} (k_aii_w2020), so
 // every pair carries its own weight m_j / rho_j, and the pair sum is not divided by rho_i (simulation.rs:1571-1575).
 template <int PASS, bool HMWIN, bool PEER, bool W2020 = false, bool R4 = false>
-__global__ void __launch_bounds__(kThreads, (HMWIN || PEER) ? 3 : 4)
+__global__ void __launch_bounds__(kThreads, (HMWIN || (PEER && !R4)) ? 3 : 4)
 k_sweep(const SweepArgs A) {
   static_assert(!W2020 || (PASS == 1 && HMWIN), "the Winchenbach2020 variant is an update pass with the {h, m / rho} window");
   static_assert(!R4 || !W2020, "the 4-row variant exists for the default operators only");
@@ -892,7 +892,10 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
   const bool w2020 = op_w2020(sim);  // its update pass always gathers {h, m / rho}
   const bool hmwin = w2020 || !(sim->ctl_seen && sim->ctl_host->hmin == sim->ctl_host->hmax);
   const size_t smem = 2 * (hmwin ? sizeof(SweepStage<true>) : sizeof(SweepStage<false>));
-  uint32_t grid = sweep_grid(n, sim->sm_count, (hmwin || dist_p2p(sim)) ? 3 : 4);
+  // blocks per SM as in the kernels' launch bounds: 3 with the {h, m} window or the peer-memory exchange — except that the
+  // experimental 4-row peer kernels (ASPH_ROWS4) fit 64 registers without spills and run at 4
+  const bool r4_early = sim->rows4 && !w2020;
+  uint32_t grid = sweep_grid(n, sim->sm_count, (hmwin || (dist_p2p(sim) && !r4_early)) ? 3 : 4);
   if (const char* e = getenv("ASPH_SWEEP_GRID")) grid = std::max(1u, std::min(grid, uint32_t(atoi(e))));  // test hook: few blocks => many tiles per block
   if (!sim->sweep_attr_done) {  // per handle: function attributes belong to the device the handle lives on
     const int big = int(2 * sizeof(SweepStage<true>)), small = int(2 * sizeof(SweepStage<false>));
