@@ -84,3 +84,33 @@ def test_list_layout_round_trip(tmp_path):
                           stdout=subprocess.DEVNULL)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout + out.stderr
+
+
+def test_rows4_schedule_covers_every_row_but_the_own_one():
+    """The row schedule of the experimental sweep kernels (solver.cu, for_each_pair<., ., R4>; ASPH_ROWS4=1), restated: with
+    the particle's own row last in the W segment, every other row is visited exactly once, in groups of 4, and no visit
+    goes beyond the 8-row padding of the column."""
+    def visited(cw_real):
+        out = []
+
+        def chunk(base, rows_left):
+            for half in range(2):
+                if half == 1 and rows_left <= 4:
+                    break
+                out.extend(range(base + 4 * half, base + 4 * half + 4))
+        cw = cw_real - 1 if cw_real > 0 else 0
+        if cw > 0:
+            chunk(0, cw)
+        if cw > 8:
+            chunk(8, cw - 8)
+        k0 = 16
+        while cw > 16 and k0 < cw:
+            chunk(k0, cw - k0)
+            k0 += 8
+        return out
+    for cw in range(0, 200):
+        rows = visited(cw)
+        assert len(rows) == len(set(rows))
+        assert set(range(max(cw - 1, 0))) <= set(rows)
+        assert all(r < (cw + 7) // 8 * 8 for r in rows)
+        assert len(rows) == (max(cw - 1, 0) + 3) // 4 * 4
