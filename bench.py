@@ -269,11 +269,36 @@ def run_ours(args):
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
     }
     out.update(extra)
+    if not args.no_experiments and "ASPH_ROWS4" not in os.environ:
+        out["experiments"] = {"rows4": experiment_rows4(args, out)}
     log = os.environ.get("ASPH_BENCH_LOG")
     if log:
         with open(log, "w") as f:
             json.dump({"per_step": per_step}, f)
     print(json.dumps(out))
+
+
+def experiment_rows4(args, base):
+    """A/B of the experimental sweep schedule (ASPH_ROWS4=1): the same workload in a separate process, after
+    the measurement above is complete, so that whatever happens there cannot touch the reported numbers.  Reported beside
+    them under "experiments", never as `value`."""
+    k = max(4, min(args.steps, 32))
+    cmd = [sys.executable, os.path.abspath(__file__), "--steps", str(k), "--warmup", str(args.warmup), "--cpu-budget", "0",
+           "--preroll-time", str(args.preroll_time), "--no-experiments"]
+    try:
+        run = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, ASPH_ROWS4="1"), cwd=ROOT)
+        line = [l for l in run.stdout.splitlines() if l.startswith("{")]
+        if run.returncode != 0 or not line:
+            return {"error": (run.stderr or run.stdout)[-300:], "returncode": run.returncode}
+        r = json.loads(line[-1])
+        return {"what": "own row last in the neighbour lists, sweep kernels in steps of 4 rows (not the default: no parity run on hardware yet)",
+                "value": r["value"], "ms_per_step": r["ms_per_step"], "steps": r["steps"],
+                "avg_div_sweeps": r["config"]["avg_div_sweeps"], "avg_density_sweeps": r["config"]["avg_density_sweeps"],
+                "particle_sweeps_per_s": r["config"]["particle_sweeps_per_s"], "jacobi_pass_ms": r["roofline"].get("avg_launch_ms"), "accel_pass_ms": (r.get("roofline_accel") or {}).get("avg_launch_ms"),
+                "baseline_jacobi_pass_ms": base["roofline"].get("avg_launch_ms"),
+                "baseline_particle_sweeps_per_s": base["config"]["particle_sweeps_per_s"]}
+    except Exception as e:  # a time-out or a malformed line must not cost the bench its result
+        return {"error": repr(e)[:300]}
 
 
 def cpu_baseline_from(A, params, boundary, state, budget_s):
@@ -369,6 +394,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU time for the cpu_baseline leg")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="time cap of the reference arm's timed steps")
     ap.add_argument("--preroll-time", type=float, default=PREROLL_T, help="simulated seconds the scene is advanced before warm-up (0 = the initial lattice)")
+    ap.add_argument("--no-experiments", action="store_true", help="skip the A/B legs reported under \"experiments\"")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
