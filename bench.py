@@ -273,8 +273,8 @@ def run_ours(args):
         t_exp = time.perf_counter()
         out["experiments"] = {"rows4": experiment_rows4(args, out)}
         # the adaptive workloads of BASELINE.json that the headline metric is not quoted on (default kernels; one GPU)
-        for key, spacing, warm, steps, limit in (("adaptive_4m_configs2", 5.612e-4, 60, 40, 240), ("adaptive_16m_north_star", 2.806e-4, 20, 10, 300)):
-            if time.perf_counter() - t_exp > 360:
+        for key, spacing, warm, steps, limit in (("adaptive_4m_configs2", 5.612e-4, 60, 40, 150), ("adaptive_16m_north_star", 2.806e-4, 20, 10, 200)):
+            if time.perf_counter() - t_exp > 200:
                 out["experiments"][key] = {"skipped": "experiment time budget used up"}
                 continue
             out["experiments"][key] = experiment_adaptive(spacing, warm, steps, limit)
@@ -293,7 +293,7 @@ def experiment_rows4(args, base):
     cmd = [sys.executable, os.path.abspath(__file__), "--steps", str(k), "--warmup", str(args.warmup), "--cpu-budget", "0",
            "--preroll-time", str(args.preroll_time), "--no-experiments"]
     try:
-        run = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, ASPH_ROWS4="1"), cwd=ROOT)
+        run = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env=dict(os.environ, ASPH_ROWS4="1"), cwd=ROOT)
         line = [l for l in run.stdout.splitlines() if l.startswith("{")]
         if run.returncode != 0 or not line:
             return {"error": (run.stderr or run.stdout)[-300:], "returncode": run.returncode}
