@@ -20,3 +20,9 @@ timeout 600 python tools/bench_adaptive.py --spacing 5.612e-4 --warmup 60 --step
 echo "adaptive 4M: rc=$?"; cut -c1-700 gpurun_out/adaptive_4m.json
 timeout 900 python tools/bench_adaptive.py --spacing 2.806e-4 --warmup 40 --steps 20 > gpurun_out/adaptive_16m.json 2> gpurun_out/adaptive_16m.err
 echo "adaptive 16M: rc=$?"; cut -c1-700 gpurun_out/adaptive_16m.json
+# 5. launch lists (per-kernel durations, cold and serialised under ncu: shares only) of the default and the 4-row schedule
+for v in 0 1; do
+  ASPH_ROWS4=$v timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_rows4_$v.csv \
+    python tools/profile_step.py 1.122e-3 2 > gpurun_out/profile_rows4_$v.log 2>&1
+  echo "ncu launch list ROWS4=$v: rc=$?"
+done
