@@ -212,3 +212,47 @@ def test_image_jobs_equal_the_python_exporter(asph, oracle32, exe, tmp_path):
     bad.write_text(yaml.safe_dump([dict(still, scene_file=SCENE)]))
     out = _run(exe, "image", str(bad), "--out-dir", str(tmp_path / "x"), "--lib", ORACLE)
     assert out.returncode == 1 and "Not both" in out.stderr
+
+
+def test_yaml_subset_parser_edge_cases(exe, tmp_path):
+    """Constructs the shipped files do not exercise together: quoted scalars with '#' and ':', comments after values,
+    sequences at the indentation of their key, nested flow collections, empty values, '- - x' items, blank lines."""
+    doc = '''# leading comment
+title: "Particle count #p: now"   # trailing comment
+path: 'a: b'
+empty:
+nothing: ~
+flag: true
+num: -3.5e-05
+list_same_indent:
+- 1
+- [2, 3, [4, 5]]
+- {a: 1, b: [x, y], c: {d: e}}
+nested:
+  deeper:
+    - - 0.5
+      - -0.25
+    - - 1
+      - 2
+
+  after_blank: ok
+jobs:
+  - time: 3
+    update_attributes:
+      viscosity: 0.001
+      level_estimation_method: None
+    scene:
+      blocks:
+        - pos: [0, 1]
+          size: [1, 1]
+  - time: 4
+'''
+    p = tmp_path / "edge.yaml"
+    p.write_text(doc)
+    out = _run(exe, "yaml-dump", str(p))
+    assert out.returncode == 0, out.stderr
+    _same(yaml.safe_load(doc), json.loads(out.stdout))
+    bad = tmp_path / "bad.yaml"
+    bad.write_text("a: [1, 2\n")
+    out = _run(exe, "yaml-dump", str(bad))
+    assert out.returncode == 1 and "unterminated flow collection" in out.stderr
