@@ -2,7 +2,7 @@
 //
 //   asph_run run SIMULATION_CONFIG SCENE_CONFIG [-s|--max-seconds S] [-c|--overwrite-config-file F] [-p|--statistics-enabled]
 //                [-w|--statistics-path F] [--max-steps N] [--split-patterns F] [--dump F] [--vtk-dir D [--vtk-every N]]
-//                [--lib LIBRARY] [-q]
+//                [--restart-vtk SNAPSHOT] [--lib LIBRARY] [-q]
 //   asph_run image JOB_FILE... [--out-dir D] [--only K]... [--max-steps N] [--split-patterns F] [--lib LIBRARY] [-q]
 //
 // mirrors the clap definition and the flow of platform/desktop/main_loop.rs:25-189, 209-358 for `run`: read the YAML files,
@@ -229,7 +229,7 @@ int cmd_image(const std::vector<std::string>& a) {
 int usage() {
   std::fprintf(stderr,
                "usage: asph_run run SIMULATION_CONFIG SCENE_CONFIG [-s SECONDS] [-c OVERWRITE.yaml] [-p] [-w STATS_FILE]\n"
-               "                    [--max-steps N] [--split-patterns FILE] [--dump FILE] [--vtk-dir DIR [--vtk-every N]] [--lib LIBRARY] [-q]\n"
+               "                    [--max-steps N] [--split-patterns FILE] [--dump FILE] [--vtk-dir DIR [--vtk-every N]] [--restart-vtk FILE] [--lib LIBRARY] [-q]\n"
                "       asph_run image JOB_FILE... [--out-dir DIR] [--only K] [--max-steps N] [--lib LIBRARY] [-q]\n");
   return 2;
 }
@@ -238,7 +238,7 @@ int cmd_run(const std::vector<std::string>& a) {
   std::vector<std::string> positional;
   double max_seconds = -1;
   long max_steps = -1;
-  std::string overwrite, stats_path, split_path, dump, lib_path, vtk_dir;
+  std::string overwrite, stats_path, split_path, dump, lib_path, vtk_dir, restart_vtk;
   long vtk_every = 1;
   bool stats = false, quiet = false;
   for (size_t i = 0; i < a.size(); i++) {
@@ -256,6 +256,7 @@ int cmd_run(const std::vector<std::string>& a) {
     else if (s == "--dump") dump = value();
     else if (s == "--vtk-dir") vtk_dir = value();
     else if (s == "--vtk-every") vtk_every = std::max(1L, std::atol(value().c_str()));
+    else if (s == "--restart-vtk") restart_vtk = value();
     else if (s == "--lib") lib_path = value();
     else if (s == "-q" || s == "--quiet") quiet = true;
     else if (!s.empty() && s[0] == '-') throw std::runtime_error("unknown option " + s);
@@ -274,7 +275,15 @@ int cmd_run(const std::vector<std::string>& a) {
   host::split_patterns_from_yaml(yaml_lite::parse_file(split_path), split);
   if (lib_path.empty()) lib_path = exe_dir() + "/../csrc/libasph_b200.so";
   host::Library lib(lib_path);
-  const host::Particles particles = host::scene_particles(scene);
+  host::Particles particles;
+  if (restart_vtk.empty()) {
+    particles = host::scene_particles(scene);
+  } else {  // restart: the particles come from a snapshot (x, v, m = the whole persistent state); the scene gives the boundary
+    const host::VtkSnapshot snap = host::read_vtk_file(restart_vtk);
+    particles.pos = snap.position; particles.vel = snap.get("velocity"); particles.mass = snap.get("mass");
+    if (particles.vel.size() != particles.pos.size() || 2 * particles.mass.size() != particles.pos.size())
+      throw std::runtime_error("snapshot arrays have inconsistent lengths: " + restart_vtk);
+  }
   const asph_boundary boundary = host::scene_boundary(scene, params.init_boundary_handler);
   host::FluidSimulation sim(lib, params, particles, boundary, &split, stats);  // init_fluid_sim, simulation.rs:3074
 

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <limits>
+#include <sstream>
 #include <string>
 #include <utility>
 #include <vector>
@@ -163,6 +164,97 @@ inline void write_vtk_file(const std::string& path, FluidSimulation& sim, const 
     try_float("lambda", ASPH_F_LAMBDA_SUM, 1);
   }
   write_vtk_file2(path, pos, fields, boundary_lines(boundary));
+}
+
+// Reads what write_vtk_file2 writes, as far as a restart needs it: the positions of the n particles (VERTICES count) and the
+// float arrays, cut back to the particles.  The persistent state of the step loop is exactly (x, v, m), all
+// three are in a snapshot as exact fp32, so a snapshot is a checkpoint (the reference has no checkpoint / resume).
+struct VtkSnapshot {
+  std::vector<float> position;                                   // [2n]
+  std::vector<std::pair<std::string, std::vector<float>>> arrays;  // name -> n (scalars) or 2n (vectors) values
+  const std::vector<float>& get(const std::string& name) const {
+    for (auto& a : arrays) if (a.first == name) return a.second;
+    throw std::runtime_error("snapshot has no array `" + name + "`");
+  }
+};
+inline VtkSnapshot read_vtk_file(const std::string& path) {
+  FILE* fp = std::fopen(path.c_str(), "rb");
+  if (!fp) throw std::runtime_error("cannot read " + path);
+  std::vector<unsigned char> raw;
+  unsigned char buf[1 << 16];
+  for (size_t k; (k = std::fread(buf, 1, sizeof(buf), fp)) > 0;) raw.insert(raw.end(), buf, buf + k);
+  std::fclose(fp);
+  size_t at = 0;
+  auto line = [&]() {
+    size_t e = at;
+    while (e < raw.size() && raw[e] != '\n') e++;
+    std::string s(raw.begin() + long(at), raw.begin() + long(e));
+    at = std::min(raw.size(), e + 1);
+    return s;
+  };
+  auto words = [](const std::string& s) {
+    std::vector<std::string> w;
+    std::istringstream in(s);
+    for (std::string t; in >> t;) w.push_back(t);
+    return w;
+  };
+  auto be_float = [&](size_t off) {
+    const uint32_t u = (uint32_t(raw[off]) << 24) | (uint32_t(raw[off + 1]) << 16) | (uint32_t(raw[off + 2]) << 8) | uint32_t(raw[off + 3]);
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+  };
+  auto skip = [&](size_t nbytes) {
+    if (at + nbytes > raw.size()) throw std::runtime_error("truncated VTK file " + path);
+    at += nbytes;
+    if (at < raw.size() && raw[at] == '\n') at++;
+  };
+  if (line().compare(0, 22, "# vtk DataFile Version") != 0) throw std::runtime_error("not a legacy VTK file: " + path);
+  line();
+  if (words(line()) != std::vector<std::string>{"BINARY"} || words(line()) != std::vector<std::string>{"DATASET", "POLYDATA"})
+    throw std::runtime_error("expected BINARY / DATASET POLYDATA: " + path);
+  VtkSnapshot snap;
+  size_t n_pts = 0, n = size_t(-1), pts_at = 0;
+  while (at < raw.size()) {
+    const std::vector<std::string> head = words(line());
+    if (head.empty()) continue;
+    if (head[0] == "POINTS") {
+      if (head.size() < 3 || head[2] != "float") throw std::runtime_error("POINTS: expected float");
+      n_pts = size_t(std::stoull(head[1]));
+      pts_at = at;
+      skip(12 * n_pts);
+    } else if (head[0] == "VERTICES") {
+      n = size_t(std::stoull(head[1]));
+      skip(4 * size_t(std::stoull(head[2])));
+    } else if (head[0] == "LINES") {
+      skip(4 * size_t(std::stoull(head[2])));
+    } else if (head[0] == "POINT_DATA") {
+      if (size_t(std::stoull(head[1])) != n_pts) throw std::runtime_error("POINT_DATA count differs from POINTS");
+    } else if (head[0] == "SCALARS") {
+      const int comps = head.size() > 3 ? std::stoi(head[3]) : 1;
+      line();  // LOOKUP_TABLE default
+      const size_t keep = std::min(n, n_pts);
+      if (head[2] == "float") {
+        std::vector<float> a;
+        const int take = comps == 3 ? 2 : comps;
+        a.reserve(keep * size_t(take));
+        for (size_t i = 0; i < keep; i++)
+          for (int c = 0; c < take; c++) a.push_back(be_float(at + 4 * (i * size_t(comps) + size_t(c))));
+        snap.arrays.push_back({head[1], std::move(a)});
+        skip(4 * n_pts * size_t(comps));
+      } else if (head[2] == "unsigned_char") {
+        skip(n_pts * size_t(comps));
+      } else {
+        throw std::runtime_error("unsupported array type " + head[2]);
+      }
+    } else {
+      throw std::runtime_error("unexpected section " + head[0]);
+    }
+  }
+  const size_t keep = std::min(n, n_pts);
+  snap.position.reserve(2 * keep);
+  for (size_t i = 0; i < keep; i++) { snap.position.push_back(be_float(pts_at + 12 * i)); snap.position.push_back(be_float(pts_at + 12 * i + 4)); }
+  return snap;
 }
 
 // VtkExporter, vtk_exporter.rs:17-79: `<folder>/<basename>-00001.vtk`, ... and `<folder>/<basename>.vtk.series`
