@@ -1,0 +1,158 @@
+"""One whole physics step of the oracle against an independent numpy restatement of the step semantics (SURVEY.md
+Appendix A, written from the formulas, not from oracle/): h, N_2 by brute force, boundary lambda terms from the closed
+forms, CFL dt, density, a_ii, non-pressure acceleration, PPE sources, the relaxed-Jacobi update, pressure acceleration and
+the integrators of HybridDFSPH / IISPH / OnlyDivergence.  `max_iters: 0` makes every solve exactly one sweep (p = 0 -> a^p = 0
+-> p' = max(0, omega * s / a_ii)), so the whole step is a closed expression.  fp64 oracle, tolerance 1e-9 of the field scale:
+what differs is only the order of the sums.  (The reference itself cannot be run here)"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ETA = 1.9
+
+
+def _w(r, h):
+    q = r / (2 * h)
+    w = np.where(q < 0.5, 6 * (q ** 3 - q ** 2) + 1, np.where(q < 1, 2 * (1 - q) ** 3, 0.0))
+    return 10.0 / (7 * np.pi * h * h) * w
+
+
+def _gradw(dx, h):
+    """cubic_kernel_2d_deriv (A1): zero for q <= 1e-5"""
+    r = np.linalg.norm(dx, axis=-1)
+    q = r / (2 * h)
+    dw = np.where(q < 0.5, 18 * q * q - 12 * q, np.where(q < 1, -6 * (1 - q) ** 2, 0.0))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        g = (10.0 / (7 * np.pi * h * h) * dw / (2 * h))[..., None] * dx / r[..., None]
+    return np.where((q > 1e-5)[..., None], g, 0.0)
+
+
+class Restatement:
+    def __init__(self, lib, params, pos, vel, mass, planes):
+        v = params.values
+        self.rho0, self.nu, self.g, self.omega = float(v["rest_density"]), float(v["viscosity"]), float(v["gravity"]), float(v["jacobi_omega"])
+        self.cfl, self.max_dt, self.hyb = float(v["cfl_factor"]), float(v["max_dt"]), float(v["hybrid_dfsph_factor"])
+        self.eps = float(v["sdf_gradient_eps"])
+        self.x, self.v, self.m = pos.astype(np.float64), vel.astype(np.float64), mass.astype(np.float64)
+        n = len(self.m)
+        self.h = ETA * np.sqrt(self.m / self.rho0 / np.pi)
+        d = self.x[:, None, :] - self.x[None, :, :]
+        hij = 0.5 * (self.h[:, None] + self.h[None, :])
+        self.nb = (d ** 2).sum(-1) < (2 * hij) ** 2            # A3, f = 2, strict, self included
+        self.W = np.where(self.nb, _w(np.sqrt((d ** 2).sum(-1)), hij), 0.0)
+        self.G = np.where(self.nb[..., None], _gradw(d, hij), 0.0)   # gradW_ij, [n, n, 2]
+        self.d = d
+        self.hij = hij
+        # boundary terms (A6), Quadratic1 penalty, lambda from the closed forms the Maxima tables pin
+        lib.asph_lambda.restype = C.c_double; lib.asph_lambda.argtypes = [C.c_double]
+        lib.asph_dlambda.restype = C.c_double; lib.asph_dlambda.argtypes = [C.c_double]
+        self.Lam = np.zeros(n); self.GLam = np.zeros((n, 2))
+        for (nx, ny, dl) in planes:
+            probe = nx * self.x[:, 0] + ny * self.x[:, 1] + dl
+            sr = 2 * self.h
+            dd = probe / sr
+            for i in np.nonzero(dd < 1)[0]:
+                di = dd[i]
+                pen, pder = (1.0, 0.0) if di > 0 else ((0.5 * di * di + 1, di) if di > -1 else (0.5 - di, -1.0))
+                lam, lamd = (1.0, 0.0) if di <= -1 else (lib.asph_lambda(di), lib.asph_dlambda(di))
+                self.Lam[i] += lam * pen
+                self.GLam[i] += np.array([nx, ny]) / sr[i] * (pder * lam + pen * lamd)   # plane normals are unit: g_hat = n
+
+    def dt(self):
+        c = (2 * self.h) ** 2 / ((self.v ** 2).sum(1) + 0.01)
+        return min(self.max_dt, self.cfl * np.sqrt(c.min()))
+
+    def density(self):
+        return (self.m[None, :] * self.W).sum(1) + self.Lam
+
+    def aii(self, rho):
+        S = (self.m[None, :, None] * self.G).sum(1)
+        Q = (self.m[None, :] * (self.G ** 2).sum(-1)).sum(1)
+        B = self.rho0 * self.GLam / (rho ** 2)[:, None]
+        return ((S / (rho ** 2)[:, None] + B) * (S / rho[:, None] + self.rho0 * self.GLam / rho[:, None])).sum(1) + self.m * Q / rho ** 3
+
+    def non_pressure(self, v, rho):
+        vij = v[:, None, :] - v[None, :, :]
+        xv = (self.d * vij).sum(-1)
+        rho_ij = 0.5 * (rho[:, None] + rho[None, :])
+        coef = 8.0 * (self.m[None, :] / rho_ij) * xv / ((self.d ** 2).sum(-1) + 0.01 * self.hij ** 2)
+        coef = np.where(self.nb & (xv < 0), coef, 0.0)
+        a = self.nu * (coef[..., None] * self.G).sum(1)
+        a[:, 1] += self.g
+        return a
+
+    def divergence(self, q, rho):
+        dq = q[None, :, :] - q[:, None, :]
+        s = ((self.m[None, :] / rho[:, None]) * (dq * self.G).sum(-1)).sum(1)
+        return s + (self.rho0 / rho) * ((0.0 - q) * self.GLam).sum(1)
+
+    def pressure_accel(self, p, rho):
+        P = p / rho ** 2
+        a = -((self.m[None, :] * (P[:, None] + P[None, :]))[..., None] * self.G).sum(1)
+        return a - (self.rho0 * P)[:, None] * self.GLam
+
+    def one_sweep(self, s, aii):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            p = np.where(np.abs(aii) < 10e-4, 0.0, self.omega * s / aii)
+        return np.maximum(p, 0.0)
+
+    def step(self, solver):
+        dt = self.dt()
+        rho = self.density()
+        aii = self.aii(rho)
+        v = self.v + dt * self.non_pressure(self.v, rho)
+        out = {"dt": dt, "density": rho, "aii": aii}
+        if solver == "HybridDFSPH":
+            p = self.one_sweep(-self.divergence(v, rho) / dt, aii)
+            v = v + dt * self.pressure_accel(p, rho)
+            s = -(self.rho0 - rho) / (rho * dt * dt) - self.divergence(v, rho) / dt
+            p = self.one_sweep(s, aii)
+            ap = self.pressure_accel(p, rho)
+            x = self.x + dt * v + dt * dt * ap
+            v = v + dt * ap * min(dt * self.hyb, 1.0)
+        else:
+            s = -self.divergence(v, rho) / dt
+            if solver == "IISPH":
+                s = s - (self.rho0 - rho) / (rho * dt * dt)
+            p = self.one_sweep(s, aii)
+            ap = self.pressure_accel(p, rho)
+            v = v + dt * ap
+            x = self.x + dt * v
+        out.update(ppe_source_term=s, pressure=p, pressure_accel=ap, position=x, velocity=v)
+        return out
+
+
+@pytest.mark.parametrize("solver", ["HybridDFSPH", "IISPH", "OnlyDivergence"])
+@pytest.mark.parametrize("where", ["corner", "middle"])
+def test_one_step_equals_the_numpy_restatement(asph, oracle64, default_params, solver, where):
+    rng = np.random.default_rng(7)
+    sp = 0.05
+    corner = where == "corner"  # in the corner two walls contribute lambda terms; in the middle none does
+    sc = asph.SceneConfig.dam_break(sp, pos=(-0.999, -0.999) if corner else (-0.3, -0.3), size=(0.6, 0.5))
+    pos, vel, mass = asph.scene_particles(sc)
+    pos = (pos + rng.uniform(-0.15, 0.15, pos.shape) * sp).astype(np.float32)
+    if corner:
+        pos = np.maximum(pos, np.float32(-0.999))
+    mass = (mass * np.exp(rng.uniform(-0.4, 0.4, mass.shape))).astype(np.float32)   # mixed smoothing lengths
+    vel = (rng.standard_normal(vel.shape) * 0.2).astype(np.float32)
+    params = default_params.replace(merging=False, sharing=False, splitting=False, level_estimation_method="None", max_iters=0,
+                                    pressure_solver_method=solver, hybrid_dfsph_factor=30.0)
+    b = asph.scene_boundary(sc, "AnalyticOverestimate")
+    planes = [tuple(float(b.planes[k][c]) for c in range(3)) for k in range(b.n_planes)]
+    sim = asph.FluidSimulation(params, pos, vel, mass, b, lib=oracle64)
+    dt = sim.single_step_without_adaptivity()
+    ref = Restatement(oracle64, params, pos, vel, mass, planes).step(solver)
+    assert abs(dt - ref["dt"]) <= 1e-7 * ref["dt"]            # the ABI reports dt as a float
+    if corner:
+        assert np.abs(sim.get_field("lambda_sum")).max() > 0.05   # the walls are really felt
+    info = sim.step_info()
+    assert info["density_sweeps"] in (0, 1) and info["div_sweeps"] in (0, 1)
+    for name in ("density", "aii", "ppe_source_term", "pressure", "pressure_accel", "position", "velocity"):
+        got = sim.get_field(name).astype(np.float64)
+        scale = max(np.abs(ref[name]).max(), 1e-12)
+        # fields come back through the float ABI: 1e-7 relative; the lambda LUT adds ~1e-8 near the walls
+        assert np.abs(got - ref[name]).max() <= 3e-7 * scale, (name, np.abs(got - ref[name]).max() / scale)
+    sim.close()
