@@ -156,3 +156,76 @@ def test_one_step_equals_the_numpy_restatement(asph, oracle64, default_params, s
         # fields come back through the float ABI: 1e-7 relative; the lambda LUT adds ~1e-8 near the walls
         assert np.abs(got - ref[name]).max() <= 3e-7 * scale, (name, np.abs(got - ref[name]).max() / scale)
     sim.close()
+
+
+def test_level_set_equals_the_numpy_restatement(asph, oracle64, default_params):
+    """EmptyAngle surface detection (A4), propagation by Jacobi sweeps (A5) and the smoothing pass (sim.rs:804-857) on the
+    two-resolution scene, against numpy: surface flags, sweep count and the final level field."""
+    sc = asph.SceneConfig.from_yaml(os.path.join(ROOT, "configs", "default-scene.yaml"))
+    pos, vel, mass = asph.scene_particles(sc)
+    rng = np.random.default_rng(3)
+    pos = (pos + rng.uniform(-0.1, 0.1, pos.shape) * 0.03).astype(np.float32)   # break the lattice ties of the cone test
+    params = default_params.replace(merging=False, sharing=False, splitting=False)
+    b = asph.scene_boundary(sc, "AnalyticOverestimate")
+    sim = asph.FluidSimulation(params, pos, vel, mass, b, lib=oracle64)
+    sim.single_step_without_adaptivity()
+    x, m = pos.astype(np.float64), mass.astype(np.float64)
+    rho0, D = 1.0, float(params["maximum_surface_distance"])
+    h = ETA * np.sqrt(m / rho0 / np.pi)
+    d = x[:, None, :] - x[None, :, :]
+    r = np.sqrt((d ** 2).sum(-1))
+    hij = 0.5 * (h[:, None] + h[None, :])
+    f1 = float(np.float64(params["level_estimation_range"])) / ETA
+    N1 = r ** 2 < (hij * f1) ** 2
+    G = np.where(N1[..., None], _gradw(d, hij), 0.0)
+    normal = -(m / rho0)[:, None] * G.sum(1)
+    planes = [tuple(float(b.planes[k][c]) for c in range(3)) for k in range(b.n_planes)]
+    wall = np.min([nx * x[:, 0] + ny * x[:, 1] + dl for nx, ny, dl in planes], axis=0)
+    cos50 = np.cos(np.deg2rad(50.0))
+    n = len(m)
+    surface = np.zeros(n, bool)
+    margin = np.full(n, np.inf)   # distance of the deciding comparison from its threshold (fp32 inputs: skip exact ties)
+    for i in range(n):
+        js = np.nonzero(N1[i])[0]
+        nn = (normal[i] ** 2).sum()
+        if len(js) < 3:
+            surface[i] = True
+        elif nn < 1e-5:
+            surface[i] = False; margin[i] = abs(nn - 1e-5)
+        elif wall[i] < 1.5 * h[i]:          # boundary_is_fluid_surface: false
+            surface[i] = False; margin[i] = abs(wall[i] - 1.5 * h[i])
+        else:
+            nh = normal[i] / np.sqrt(nn)
+            xji = x[js] - x[i]
+            c = (xji / (np.linalg.norm(xji, axis=1) + 1e-6)[:, None]) @ nh
+            surface[i] = not np.any(c > cos50)
+            margin[i] = np.abs(c - cos50).min()
+    flags = sim.get_field("flag_is_fluid_surface").astype(bool)
+    clear = margin > 1e-6
+    assert clear.mean() > 0.99 and np.array_equal(flags[clear], surface[clear])
+    surface = flags.copy()   # continue from the oracle's flags so that a tie cannot shift the distance field
+    # A5: Jacobi sweeps until nothing changes
+    has = surface.copy(); phi = np.zeros(n)
+    sweeps = 0
+    while True:
+        sweeps += 1
+        new_has, new_phi, changed = has.copy(), phi.copy(), False
+        for i in np.nonzero(~has)[0]:
+            js = np.nonzero(N1[i] & has)[0]
+            if len(js):
+                new_phi[i] = np.max(phi[js] - r[i, js]); new_has[i] = True; changed = True
+        has, phi = new_has, new_phi
+        if not changed:
+            break
+    assert sim.step_info()["level_sweeps"] == sweeps
+    # smoothing: post-advection positions, N_2 of the step, the step's densities
+    x2 = sim.get_field("position").astype(np.float64); rho = sim.get_field("density").astype(np.float64)
+    N2 = r ** 2 < (2 * hij) ** 2
+    d2 = x2[:, None, :] - x2[None, :, :]
+    W = np.where(N2, _w(np.sqrt((d2 ** 2).sum(-1)), hij), 0.0)
+    dist = np.where(has, np.maximum(phi, -D), -D)
+    vw = (m / rho)[None, :] * W
+    level = (vw * dist[None, :]).sum(1) / vw.sum(1)
+    got = sim.get_field("level").astype(np.float64)
+    assert np.abs(got - level).max() <= 1e-6 * max(np.abs(level).max(), 1e-9), np.abs(got - level).max()
+    sim.close()
