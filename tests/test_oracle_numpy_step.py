@@ -229,3 +229,151 @@ def test_level_set_equals_the_numpy_restatement(asph, oracle64, default_params):
     got = sim.get_field("level").astype(np.float64)
     assert np.abs(got - level).max() <= 1e-6 * max(np.abs(level).max(), 1e-9), np.abs(got - level).max()
     sim.close()
+
+
+AVAILABLE, DELETE = 0xFFFFFFFF, 0xFFFFFFFE
+
+
+def _resample(params, split_patterns, x, v, m, level, h, rows, dt, step_number):
+    """single_step_adaptivity restated from SURVEY.md A16-A20 in plain Python (serial greedy searches, swap-with-last
+    deletion, append-at-end splitting).  Arrays are float64 copies; returns the new (x, v, m) and (shared, merged, split)."""
+    P = params.values
+    rho0, D = float(P["rest_density"]), float(P["maximum_surface_distance"])
+    r_f, r_b = float(P["particle_radius_fine"]), float(P["particle_radius_base"])
+    m_base = np.pi * r_b * r_b * rho0
+    x, v, m, level = x.copy(), v.copy(), m.copy(), level.copy()
+
+    def target(i):
+        t = max(level[i], -D) / -D
+        tr = r_f * (1 - t) + r_b * t
+        return np.pi * tr * tr * rho0          # sizing_function: Radius
+
+    def classes():
+        out = []
+        for i in range(len(m)):
+            q = m[i] / target(i)
+            out.append(0 if q <= 0.5 else 1 if q <= 1 / 1.1 else 2 if q < 1.1 else 3 if q < 2 else 4)
+        return out
+
+    def drop_share(i):
+        tm = target(i)
+        return min(m[i] - tm, tm * float(P["max_mass_transfer_sharing"]) * dt)
+
+    def search(merging, cls):
+        n = len(m)
+        partner, counter, claims = [AVAILABLE] * n, [0] * n, 0
+        factor = float(P["max_merge_distance"] if merging else P["max_share_distance"])
+        for i in range(n):
+            counter[i] = 0
+            if cls[i] != (0 if merging else 3):
+                continue
+            for j in rows[i]:
+                j = int(j)
+                if j == i:
+                    continue
+                if merging:
+                    ok = {3: False, 4: False, 2: bool(P["allow_merge_with_optimal_particle"])}.get(cls[j], True)
+                    if P["allow_merge_on_size_difference"] and m[j] > 5 * m[i]:
+                        ok = True
+                else:
+                    ok = {1: True, 0: bool(P["allow_share_with_too_small_particle"]), 2: bool(P["allow_share_with_optimal_particle"])}.get(cls[j], False)
+                if not ok:
+                    continue
+                dx = x[i] - x[j]
+                md = 0.5 * (h[i] + h[j]) * factor
+                if dx @ dx > md * md:
+                    continue
+                dropped = m[i] if merging else drop_share(i)
+                nm = m[j] + dropped / (counter[i] + 1)
+                if nm >= target(j) * 1.1 or nm > m_base or partner[j] != AVAILABLE:
+                    continue
+                if counter[i] == 0:
+                    if partner[i] != AVAILABLE:
+                        continue
+                    partner[i] = DELETE
+                partner[j] = i
+                counter[i] += 1
+                claims += 1
+        return partner, counter, claims
+
+    def receive(merging, partner, counter, minp):
+        donors_drop = {d: (m[d] if merging else drop_share(d)) for d in range(len(m)) if partner[d] == DELETE}
+        m_old, x_old, v_old = m.copy(), x.copy(), v.copy()
+        for i in range(len(m)):
+            d = partner[i]
+            if d in (AVAILABLE, DELETE) or counter[d] < minp:
+                continue
+            mu = donors_drop[d] / counter[d]
+            tot = m_old[i] + mu
+            v[i] = (m_old[i] * v_old[i] + mu * v_old[d]) / tot
+            x[i] = (m_old[i] * x_old[i] + mu * x_old[d]) / tot
+            m[i] = tot
+        return donors_drop
+
+    stats = [0, 0, 0]
+    if P["sharing"]:
+        partner, counter, stats[0] = search(False, classes())
+        drops = receive(False, partner, counter, int(P["minimum_share_partners"]))
+        for d, dr in drops.items():
+            if counter[d] >= int(P["minimum_share_partners"]):
+                m[d] -= dr
+    if step_number % 2 == 0:
+        if P["merging"]:
+            partner, counter, stats[1] = search(True, classes())
+            receive(True, partner, counter, int(P["minimum_merge_partners"]))
+            order = list(range(len(m)))      # swap-with-last compaction on an index list
+            i, last = 0, len(order) - 1
+            while i <= last:
+                k = order[i]
+                if partner[k] == DELETE and counter[k] >= int(P["minimum_merge_partners"]):   # its whole mass was handed out
+                    order[i], order[last] = order[last], order[i]
+                    last -= 1
+                    continue
+                i += 1
+            keep = order[:last + 1]
+            x, v, m = x[keep], v[keep], m[keep]
+    elif P["splitting"]:
+        cls = classes()
+        nx, nv, nm = [], [], []
+        for i in range(len(cls)):
+            if cls[i] != 4:
+                continue
+            nc = min(int(np.floor(m[i] / target(i) + 0.5)), split_patterns.max_children)
+            pat = split_patterns.get(nc).astype(np.float64)
+            rad = np.sqrt(m[i] / 1.0 / np.pi)
+            cm, ov, ox = m[i] / nc, v[i].copy(), x[i].copy()
+            for c in range(nc):
+                px = ox + pat[c] * rad
+                if c == 0:
+                    m[i], v[i], x[i] = cm, ov, px
+                else:
+                    nx.append(px); nv.append(ov); nm.append(cm)
+            stats[2] += 1
+        if nm:
+            x, v, m = np.concatenate([x, np.array(nx)]), np.concatenate([v, np.array(nv)]), np.concatenate([m, np.array(nm)])
+    return x, v, m, tuple(stats)
+
+
+def test_resampling_equals_the_python_restatement(asph, oracle64, default_params, split_patterns):
+    """Six full steps of C1 (split on odd steps, merge on even ones, share always): after every physics step the resampling
+    phase of the oracle is compared with the restatement above, started from the oracle's own post-physics state."""
+    sc = asph.SceneConfig.from_yaml(os.path.join(ROOT, "configs", "default-scene.yaml"))
+    params = default_params.replace(max_mass_transfer_sharing=40.0)   # partial hand-overs too, not only whole excesses
+    sim = asph.init_fluid_sim(params, sc, split_patterns, lib=oracle64)
+    seen = [0, 0, 0]
+    for step in range(1, 7):
+        dt = sim.single_step_without_adaptivity(params)
+        f = {k: sim.get_field(k).astype(np.float64) for k in ("position", "velocity", "mass", "level", "h")}
+        off, idx = sim.neighbors_csr()
+        rows = [idx[int(off[i]):int(off[i + 1])] for i in range(len(off) - 1)]
+        x, v, m, stats = _resample(params, split_patterns, f["position"], f["velocity"], f["mass"], f["level"], f["h"], rows, float(dt), step)
+        sim.single_step_adaptivity(params, dt)
+        info = sim.step_info()
+        assert (info["n_shared"], info["n_merged"], info["n_split_parents"]) == stats, (step, info, stats)
+        assert sim.num_fluid_particles() == len(m), step
+        for name, ref in (("position", x), ("velocity", v), ("mass", m)):
+            got = sim.get_field(name).astype(np.float64)
+            assert np.abs(got - ref).max() <= 2e-7 * max(np.abs(ref).max(), 1e-12), (step, name)   # float read-back
+        seen = [a + b for a, b in zip(seen, stats)]
+    assert all(s > 0 for s in seen), seen   # every phase really happened
+    sim.close()
