@@ -31,7 +31,7 @@ def _gradw(dx, h):
 
 
 class Restatement:
-    def __init__(self, lib, params, pos, vel, mass, planes):
+    def __init__(self, lib, params, pos, vel, mass, probes):
         v = params.values
         self.rho0, self.nu, self.g, self.omega = float(v["rest_density"]), float(v["viscosity"]), float(v["gravity"]), float(v["jacobi_omega"])
         self.cfl, self.max_dt, self.hyb = float(v["cfl_factor"]), float(v["max_dt"]), float(v["hybrid_dfsph_factor"])
@@ -50,16 +50,21 @@ class Restatement:
         lib.asph_lambda.restype = C.c_double; lib.asph_lambda.argtypes = [C.c_double]
         lib.asph_dlambda.restype = C.c_double; lib.asph_dlambda.argtypes = [C.c_double]
         self.Lam = np.zeros(n); self.GLam = np.zeros((n, 2))
-        for (nx, ny, dl) in planes:
-            probe = nx * self.x[:, 0] + ny * self.x[:, 1] + dl
+        for probe in probes:   # signed distance functions, positive inside the tank (sdf/sdf_plane.rs, sdf/sdf2d.rs)
             sr = 2 * self.h
-            dd = probe / sr
-            for i in np.nonzero(dd < 1)[0]:
-                di = dd[i]
+            for i in range(n):
+                di = probe(self.x[i]) / sr[i]
+                if not di < 1:
+                    continue
+                ex, ey = np.array([self.eps, 0.0]), np.array([0.0, self.eps])   # central differences, sdf/sdf.rs:50-62
+                g = np.array([probe(self.x[i] + ex) - probe(self.x[i] - ex), probe(self.x[i] + ey) - probe(self.x[i] - ey)]) / (2 * self.eps)
+                if np.linalg.norm(g) < 1e-5:
+                    continue
+                g = g / np.linalg.norm(g)
                 pen, pder = (1.0, 0.0) if di > 0 else ((0.5 * di * di + 1, di) if di > -1 else (0.5 - di, -1.0))
                 lam, lamd = (1.0, 0.0) if di <= -1 else (lib.asph_lambda(di), lib.asph_dlambda(di))
                 self.Lam[i] += lam * pen
-                self.GLam[i] += np.array([nx, ny]) / sr[i] * (pder * lam + pen * lamd)   # plane normals are unit: g_hat = n
+                self.GLam[i] += g / sr[i] * (pder * lam + pen * lamd)
 
     def dt(self):
         c = (2 * self.h) ** 2 / ((self.v ** 2).sum(1) + 0.01)
@@ -125,12 +130,38 @@ class Restatement:
         return out
 
 
+def _polygon_probe(pts):
+    """Sdf2D of a closed polygon (sdf/sdf2d.rs:73-141): distance to the nearest edge or vertex, positive on the left of the
+    edges (inside a counter-clockwise tank); at a vertex the sign comes from the sum of the two edge normals."""
+    pts = np.asarray(pts, np.float64)
+    nxt = np.roll(pts, -1, axis=0)
+    edir = (nxt - pts) / np.linalg.norm(nxt - pts, axis=1)[:, None]
+    elen2 = ((nxt - pts) ** 2).sum(1)
+    prev = np.roll(edir, 1, axis=0)
+    pn = np.stack([-prev[:, 1] - edir[:, 1], prev[:, 0] + edir[:, 0]], axis=1)
+
+    def probe(x):
+        best, out = np.inf, 0.0
+        for k in range(len(pts)):
+            pd = x - pts[k]
+            proj = pd @ edir[k]
+            dl = pd[0] * -edir[k, 1] + pd[1] * edir[k, 0]
+            if proj > 0 and proj * proj < elen2[k] and dl * dl < best:
+                best, out = dl * dl, dl
+            c = pd @ pd
+            if c < best:
+                best, out = c, np.sqrt(c) * (1.0 if pd @ pn[k] >= 0 else -1.0)
+        return out
+    return probe
+
+
 @pytest.mark.parametrize("solver", ["HybridDFSPH", "IISPH", "OnlyDivergence"])
-@pytest.mark.parametrize("where", ["corner", "middle"])
+@pytest.mark.parametrize("where", ["corner", "middle", "polygon-corner"])
 def test_one_step_equals_the_numpy_restatement(asph, oracle64, default_params, solver, where):
     rng = np.random.default_rng(7)
     sp = 0.05
-    corner = where == "corner"  # in the corner two walls contribute lambda terms; in the middle none does
+    corner = where != "middle"  # in the corner two walls contribute lambda terms; in the middle none does
+    kind = "AnalyticUnderestimate" if where == "polygon-corner" else "AnalyticOverestimate"
     sc = asph.SceneConfig.dam_break(sp, pos=(-0.999, -0.999) if corner else (-0.3, -0.3), size=(0.6, 0.5))
     pos, vel, mass = asph.scene_particles(sc)
     pos = (pos + rng.uniform(-0.15, 0.15, pos.shape) * sp).astype(np.float32)
@@ -139,12 +170,15 @@ def test_one_step_equals_the_numpy_restatement(asph, oracle64, default_params, s
     mass = (mass * np.exp(rng.uniform(-0.4, 0.4, mass.shape))).astype(np.float32)   # mixed smoothing lengths
     vel = (rng.standard_normal(vel.shape) * 0.2).astype(np.float32)
     params = default_params.replace(merging=False, sharing=False, splitting=False, level_estimation_method="None", max_iters=0,
-                                    pressure_solver_method=solver, hybrid_dfsph_factor=30.0)
-    b = asph.scene_boundary(sc, "AnalyticOverestimate")
-    planes = [tuple(float(b.planes[k][c]) for c in range(3)) for k in range(b.n_planes)]
+                                    pressure_solver_method=solver, hybrid_dfsph_factor=30.0, init_boundary_handler=kind)
+    b = asph.scene_boundary(sc, kind)
+    if kind == "AnalyticOverestimate":
+        probes = [(lambda x, k=k: float(b.planes[k][0]) * x[0] + float(b.planes[k][1]) * x[1] + float(b.planes[k][2])) for k in range(b.n_planes)]
+    else:
+        probes = [_polygon_probe([(float(b.poly[k][0]), float(b.poly[k][1])) for k in range(b.n_poly)])]
     sim = asph.FluidSimulation(params, pos, vel, mass, b, lib=oracle64)
     dt = sim.single_step_without_adaptivity()
-    ref = Restatement(oracle64, params, pos, vel, mass, planes).step(solver)
+    ref = Restatement(oracle64, params, pos, vel, mass, probes).step(solver)
     assert abs(dt - ref["dt"]) <= 1e-7 * ref["dt"]            # the ABI reports dt as a float
     if corner:
         assert np.abs(sim.get_field("lambda_sum")).max() > 0.05   # the walls are really felt
