@@ -104,6 +104,44 @@ class Restatement:
             p = np.where(np.abs(aii) < 10e-4, 0.0, self.omega * s / aii)
         return np.maximum(p, 0.0)
 
+    def solve(self, s, aii, rho, dt, tol, density_mode, max_iters):
+        """iisph_pressure_iterations (A13, sim.rs:1378-1516): relaxed Jacobi from p = 0; returns (p, iterations k)."""
+        p = np.zeros(len(s))
+        k = 0
+        while True:
+            ap = self.pressure_accel(p, rho)
+            Ap = self.divergence(ap, rho)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                pn = p + self.omega * (s - Ap) / aii
+            singular = np.abs(aii) < 10e-4
+            perr = (rho * dt * dt if density_mode else dt) * (s - Ap)
+            normal = ~singular & (pn > 0)
+            p = np.where(normal, pn, 0.0)
+            avg = perr[normal].sum() / normal.sum() if normal.any() else np.nan
+            if not normal.any():
+                break
+            if k > 1 and (abs(avg / self.rho0) < tol if density_mode else abs(avg) < tol / dt):
+                break
+            if k == max_iters:
+                break
+            k += 1
+        return p, k
+
+    def step_converged(self, params):
+        """HybridDFSPH with the full solver loops (default tolerances)."""
+        v0 = params.values
+        dt = self.dt()
+        rho = self.density()
+        aii = self.aii(rho)
+        v = self.v + dt * self.non_pressure(self.v, rho)
+        p, k_div = self.solve(-self.divergence(v, rho) / dt, aii, rho, dt, float(v0["hybrid_dfsph_max_avg_divergence_error"]), False, int(v0["max_iters"]))
+        v = v + dt * self.pressure_accel(p, rho)
+        s = -(self.rho0 - rho) / (rho * dt * dt) - self.divergence(v, rho) / dt
+        p, k_den = self.solve(s, aii, rho, dt, float(v0["hybrid_dfsph_max_avg_density_error"]), True, int(v0["max_iters"]))
+        ap = self.pressure_accel(p, rho)
+        return {"position": self.x + dt * v + dt * dt * ap, "velocity": v + dt * ap * min(dt * self.hyb, 1.0), "pressure": p,
+                "div_iterations": k_div, "density_iterations": k_den}
+
     def step(self, solver):
         dt = self.dt()
         rho = self.density()
@@ -189,6 +227,29 @@ def test_one_step_equals_the_numpy_restatement(asph, oracle64, default_params, s
         scale = max(np.abs(ref[name]).max(), 1e-12)
         # fields come back through the float ABI: 1e-7 relative; the lambda LUT adds ~1e-8 near the walls
         assert np.abs(got - ref[name]).max() <= 3e-7 * scale, (name, np.abs(got - ref[name]).max() / scale)
+    sim.close()
+
+
+def test_solver_loops_equal_the_numpy_restatement(asph, oracle64, default_params):
+    """The relaxed-Jacobi loops with their stop rules (A13): same iteration counts, same pressures, same end state."""
+    rng = np.random.default_rng(11)
+    sp = 0.05
+    sc = asph.SceneConfig.dam_break(sp, pos=(-0.999, -0.999), size=(0.6, 0.5))
+    pos, vel, mass = asph.scene_particles(sc)
+    pos = np.maximum((pos + rng.uniform(-0.15, 0.15, pos.shape) * sp).astype(np.float32), np.float32(-0.999))
+    vel = (rng.standard_normal(vel.shape) * 0.2).astype(np.float32)
+    params = default_params.replace(merging=False, sharing=False, splitting=False, level_estimation_method="None")
+    b = asph.scene_boundary(sc, "AnalyticOverestimate")
+    probes = [(lambda x, k=k: float(b.planes[k][0]) * x[0] + float(b.planes[k][1]) * x[1] + float(b.planes[k][2])) for k in range(b.n_planes)]
+    sim = asph.FluidSimulation(params, pos, vel, mass, b, lib=oracle64)
+    sim.single_step_without_adaptivity()
+    ref = Restatement(oracle64, params, pos, vel, mass, probes).step_converged(params)
+    info = sim.step_info()
+    assert (info["div_iterations"], info["density_iterations"]) == (ref["div_iterations"], ref["density_iterations"]), (info, ref)
+    assert info["density_iterations"] > 3   # the loop really iterated
+    for name in ("pressure", "position", "velocity"):
+        got = sim.get_field(name).astype(np.float64)
+        assert np.abs(got - ref[name]).max() <= 1e-6 * max(np.abs(ref[name]).max(), 1e-12), name
     sim.close()
 
 
