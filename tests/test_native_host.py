@@ -276,3 +276,26 @@ def test_restart_from_a_snapshot_continues_bit_for_bit(asph, exe, tmp_path):
         assert np.array_equal(x, y)
     snap = asph.read_vtk_file(str(part / "my-sph-00003.vtk"))
     assert len(snap["mass"]) == len(a[2])
+
+
+def test_yaml_subset_parser_on_generated_documents(exe, tmp_path):
+    """Random nested documents in both of PyYAML's dump styles (block and flow) parse like PyYAML parses them."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    keys = st.text("abcdefghijklmnopqrstuvwxyz_", min_size=1, max_size=8)
+    words = st.text("abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ", min_size=1, max_size=10).filter(
+        lambda s: s.lower() not in ("null", "true", "false", "yes", "no", "on", "off", "y", "n", "nan", "inf"))
+    tricky = st.sampled_from(["a b", "x: y", "# c", "a #b", "k:v", "- d", "[e", "1.5.2", "Particle count #p", "../default-config.yaml"])
+    scalars = st.one_of(tricky, st.integers(-10 ** 6, 10 ** 6), st.floats(-1e6, 1e6, allow_nan=False, allow_infinity=False, width=32), st.booleans(), words, st.none())
+    docs = st.recursive(scalars, lambda ch: st.one_of(st.lists(ch, min_size=1, max_size=4), st.dictionaries(keys, ch, min_size=1, max_size=4)), max_leaves=20)
+    path = tmp_path / "gen.yaml"
+
+    @settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(doc=st.dictionaries(keys, docs, min_size=1, max_size=5), flow=st.sampled_from([False, None]))
+    def check(doc, flow):
+        text = yaml.safe_dump(doc, default_flow_style=flow, width=10 ** 6)
+        path.write_text(text)
+        out = _run(exe, "yaml-dump", str(path))
+        assert out.returncode == 0, (text, out.stderr)
+        _same(yaml.safe_load(text), json.loads(out.stdout))
+
+    check()
