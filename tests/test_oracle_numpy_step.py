@@ -472,3 +472,33 @@ def test_resampling_equals_the_python_restatement(asph, oracle64, default_params
         seen = [a + b for a, b in zip(seen, stats)]
     assert all(s > 0 for s in seen), seen   # every phase really happened
     sim.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent (max_iters = 0 has not run on hardware): first run pending")
+@pytest.mark.parametrize("solver", ["HybridDFSPH", "IISPH"])
+def test_cuda_step_equals_the_numpy_restatement(asph, cuda_lib, default_params, solver):
+    """The CUDA path against the numpy restatement directly (no oracle in between): one-sweep step in the corner of the
+    tank, fp32 tolerances of tests/test_gpu_parity.py."""
+    rng = np.random.default_rng(7)
+    sp = 0.05
+    sc = asph.SceneConfig.dam_break(sp, pos=(-0.999, -0.999), size=(0.6, 0.5))
+    pos, vel, mass = asph.scene_particles(sc)
+    pos = np.maximum((pos + rng.uniform(-0.15, 0.15, pos.shape) * sp).astype(np.float32), np.float32(-0.999))
+    mass = (mass * np.exp(rng.uniform(-0.4, 0.4, mass.shape))).astype(np.float32)
+    vel = (rng.standard_normal(vel.shape) * 0.2).astype(np.float32)
+    params = default_params.replace(merging=False, sharing=False, splitting=False, level_estimation_method="None", max_iters=0,
+                                    pressure_solver_method=solver, hybrid_dfsph_factor=30.0)
+    b = asph.scene_boundary(sc, "AnalyticOverestimate")
+    probes = [(lambda x, k=k: float(b.planes[k][0]) * x[0] + float(b.planes[k][1]) * x[1] + float(b.planes[k][2])) for k in range(b.n_planes)]
+    sim = asph.FluidSimulation(params, pos, vel, mass, b, lib=cuda_lib)
+    sim.single_step_without_adaptivity()
+    ref = Restatement(cuda_lib, params, pos, vel, mass, probes).step(solver)   # asph_lambda / asph_dlambda: host helpers of the library
+    for name in ("density", "aii", "ppe_source_term", "pressure", "pressure_accel"):
+        got = sim.get_field(name).astype(np.float64)
+        scale = max(np.abs(ref[name]).max(), 1e-12)
+        assert np.abs(got - ref[name]).max() <= 2e-4 * scale, (name, np.abs(got - ref[name]).max() / scale)
+    assert np.abs(sim.get_field("position") - ref["position"]).max() <= 2e-6
+    vs = max(np.abs(ref["velocity"]).max(), 1e-3)
+    assert np.abs(sim.get_field("velocity") - ref["velocity"]).max() <= 1e-4 * vs
+    sim.close()
