@@ -16,6 +16,7 @@ import argparse
 import ctypes as C
 import json
 import os
+import signal
 import subprocess
 import sys
 import threading
@@ -269,34 +270,81 @@ def run_ours(args):
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
     }
     out.update(extra)
-    if not args.no_experiments and "ASPH_ROWS4" not in os.environ:
-        t_exp = time.perf_counter()
-        out["experiments"] = {"rows4": experiment_rows4(args, out)}
-        # the adaptive workloads of BASELINE.json that the headline metric is not quoted on (default kernels; one GPU)
-        for key, spacing, warm, steps, limit in (("adaptive_4m_configs2", 5.612e-4, 60, 40, 150), ("adaptive_16m_north_star", 2.806e-4, 20, 10, 200)):
-            if time.perf_counter() - t_exp > 200:
-                out["experiments"][key] = {"skipped": "experiment time budget used up"}
-                continue
-            out["experiments"][key] = experiment_adaptive(spacing, warm, steps, limit)
     log = os.environ.get("ASPH_BENCH_LOG")
     if log:
         with open(log, "w") as f:
             json.dump({"per_step": per_step}, f)
-    print(json.dumps(out))
+    if not args.no_experiments and "ASPH_ROWS4" not in os.environ:
+        run_experiments(args, out)
+    print(json.dumps(out), flush=True)
+
+
+_children = []
+
+
+def _run_child(cmd, limit_s, env=None):
+    """A child process in its own process group, killed as a group when its time is up (a hung kernel must not outlive it)."""
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=ROOT, start_new_session=True)
+    _children.append(p)
+    try:
+        so, se = p.communicate(timeout=limit_s)
+    except subprocess.TimeoutExpired:
+        _kill_group(p)
+        so, se = p.communicate()
+        return None, so, (se or "") + f"\n[killed after {limit_s} s]"
+    finally:
+        _children.remove(p)
+    return p.returncode, so, se
+
+
+def _kill_group(p):
+    try:
+        os.killpg(p.pid, signal.SIGKILL)
+    except (OSError, ProcessLookupError):
+        pass
+
+
+def run_experiments(args, out):
+    """The legs reported under "experiments": they start after the measurement proper is complete and run in child
+    processes, so nothing that happens there can change the reported numbers; should the bench itself be told to stop
+    (SIGTERM / SIGINT from an impatient caller) while one of them runs, the measured line is printed at once."""
+    out["experiments"] = exp = {}
+
+    def bail(signum, _frame):
+        for p in list(_children):
+            _kill_group(p)
+        exp["interrupted"] = f"signal {signum} during the experiment legs; the measurement above was complete"
+        sys.stdout.write(json.dumps(out) + "\n")
+        sys.stdout.flush()
+        os._exit(0)
+
+    old = {s: signal.signal(s, bail) for s in (signal.SIGTERM, signal.SIGINT)}
+    try:
+        t_exp = time.perf_counter()
+        exp["rows4"] = experiment_rows4(args, out)
+        # the adaptive workloads of BASELINE.json that the headline metric is not quoted on (default kernels; one GPU)
+        for key, spacing, warm, steps, limit in (("adaptive_4m_configs2", 5.612e-4, 60, 40, 120), ("adaptive_16m_north_star", 2.806e-4, 20, 10, 150)):
+            if time.perf_counter() - t_exp > 150:
+                exp[key] = {"skipped": "experiment time budget used up"}
+                continue
+            exp[key] = experiment_adaptive(spacing, warm, steps, limit)
+        exp["seconds"] = time.perf_counter() - t_exp
+    finally:
+        for s, h in old.items():
+            signal.signal(s, h)
 
 
 def experiment_rows4(args, base):
     """A/B of the experimental sweep schedule (ASPH_ROWS4=1): the same workload in a separate process, after
-    the measurement above is complete, so that whatever happens there cannot touch the reported numbers.  Reported beside
-    them under "experiments", never as `value`."""
+    the measurement above is complete.  Reported beside it under "experiments", never as `value`."""
     k = max(4, min(args.steps, 32))
     cmd = [sys.executable, os.path.abspath(__file__), "--steps", str(k), "--warmup", str(args.warmup), "--cpu-budget", "0",
            "--preroll-time", str(args.preroll_time), "--no-experiments"]
     try:
-        run = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env=dict(os.environ, ASPH_ROWS4="1"), cwd=ROOT)
-        line = [l for l in run.stdout.splitlines() if l.startswith("{")]
-        if run.returncode != 0 or not line:
-            return {"error": (run.stderr or run.stdout)[-300:], "returncode": run.returncode}
+        rc, so, se = _run_child(cmd, 90, env=dict(os.environ, ASPH_ROWS4="1"))
+        line = [l for l in (so or "").splitlines() if l.startswith("{")]
+        if rc != 0 or not line:
+            return {"error": (se or so or "")[-300:], "returncode": rc}
         r = json.loads(line[-1])
         return {"what": "own row last in the neighbour lists, sweep kernels in steps of 4 rows (not the default: no parity run on hardware yet)",
                 "value": r["value"], "ms_per_step": r["ms_per_step"], "steps": r["steps"],
@@ -304,7 +352,7 @@ def experiment_rows4(args, base):
                 "particle_sweeps_per_s": r["config"]["particle_sweeps_per_s"], "jacobi_pass_ms": r["roofline"].get("avg_launch_ms"), "accel_pass_ms": (r.get("roofline_accel") or {}).get("avg_launch_ms"),
                 "baseline_jacobi_pass_ms": base["roofline"].get("avg_launch_ms"),
                 "baseline_particle_sweeps_per_s": base["config"]["particle_sweeps_per_s"]}
-    except Exception as e:  # a time-out or a malformed line must not cost the bench its result
+    except Exception as e:  # a malformed line must not cost the bench its result
         return {"error": repr(e)[:300]}
 
 
@@ -312,10 +360,10 @@ def experiment_adaptive(spacing, warmup, steps, limit_s):
     """tools/bench_adaptive.py in a separate process: the adaptive dam break (level set + share / merge / split every step)."""
     cmd = [sys.executable, os.path.join(ROOT, "tools", "bench_adaptive.py"), "--spacing", repr(spacing), "--warmup", str(warmup), "--steps", str(steps)]
     try:
-        run = subprocess.run(cmd, capture_output=True, text=True, timeout=limit_s, cwd=ROOT)
-        line = [l for l in run.stdout.splitlines() if l.startswith("{")]
+        rc, so, se = _run_child(cmd, limit_s)
+        line = [l for l in (so or "").splitlines() if l.startswith("{")]
         if not line:
-            return {"error": (run.stderr or run.stdout)[-300:], "returncode": run.returncode}
+            return {"error": (se or so or "")[-300:], "returncode": rc}
         return json.loads(line[-1])
     except Exception as e:
         return {"error": repr(e)[:300]}
