@@ -11,6 +11,36 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "isolated(timeout): run the test body in a child pytest process (kernels that have never run on hardware)")
+
+
+@pytest.hookimpl(tryfirst=True)
+def pytest_pyfunc_call(pyfuncitem):
+    """Tests marked `isolated` exercise kernels that have had no hardware run yet.  Their bodies run in a child pytest
+    process (own CUDA context, own process group, hard time limit), so a hung kernel or a sticky CUDA error there costs one
+    test, not the rest of the suite.  The child's verdict is the test's verdict."""
+    mark = pyfuncitem.get_closest_marker("isolated")
+    if mark is None or os.environ.get("ASPH_TEST_CHILD"):
+        return None
+    limit = float(mark.kwargs.get("timeout", mark.args[0] if mark.args else 75))
+    node = f"{pyfuncitem.path}::{pyfuncitem.name}"
+    cmd = [sys.executable, "-m", "pytest", node, "-q", "-x", "--runxfail", "--tb=short", "-p", "no:cacheprovider"]
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=ROOT, start_new_session=True,
+                         env=dict(os.environ, ASPH_TEST_CHILD="1"))
+    try:
+        out, _ = p.communicate(timeout=limit)
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(p.pid, 9)
+        except OSError:
+            pass
+        out, _ = p.communicate()
+        pytest.fail(f"isolated test killed after {limit:.0f} s\n{(out or '')[-1500:]}", pytrace=False)
+    if p.returncode == 5 or " skipped" in (out or "") and " passed" not in (out or "") and p.returncode == 0:
+        pytest.skip((out or "").strip().splitlines()[-1] if out else "skipped in the child")
+    if p.returncode != 0:
+        pytest.fail(f"isolated test failed in its child process (rc {p.returncode})\n{(out or '')[-3000:]}", pytrace=False)
+    return True
 
 
 @pytest.fixture(scope="session")
