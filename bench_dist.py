@@ -1,7 +1,9 @@
 """Multi-GPU arm of bench.py (N > 1, one rank per GPU under torchrun): slab decomposition along x, NCCL halos.
 
-Weak scaling: the tank and the fluid block of BASELINE configs[1] are widened N-fold, so every GPU owns about 999 292
-particles; the physics per column is unchanged (same spacing, same column height => same sweep counts as at N = 1).
+Weak scaling: the tank is N times as wide and holds N times the fluid of BASELINE configs[1], so every GPU owns about
+999 292 particles — by default as N dam-break columns side by side whose middles the slab faces cut through (bench.py
+`dam_break`, "columns": the sweep counts of the 1-GPU scene), or as one N-fold wider block (`ASPH_BENCH_SCENE=wide`; also
+the fallback should the default scene fail to reach the timed window).
 Each rank generates only its own share of the lattice.  Timing: barrier + synchronize on both sides of the K timed
 steps; per rank the CUDA-event time of the steps on the library's stream; the job's time is the MAX over ranks.
 The timed steps replay a window of REPLAY_WINDOW steps after the pre-roll (bench.py explains why): at the end of a
@@ -17,17 +19,16 @@ import time
 def run(args, A, rank, world):
     import torch
     import torch.distributed as dist
-    from bench import (METRIC, UNIT, SPACING_C2, ClockSampler, dam_break, peaks, pinned, preroll, uniform_params)
+    from bench import (METRIC, UNIT, SPACING_C2, SCENE_KIND, ClockSampler, dam_break, peaks, pinned, preroll, uniform_params)
 
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = A.load_library()
     params = uniform_params(A)
-    scene = dam_break(A, SPACING_C2, n_gpus=world)
     from bench import REPLAY_WINDOW
     K, W = args.steps, args.warmup
-    state = {"pre_steps": 0, "restarts": 0}
+    state = {"pre_steps": 0, "restarts": 0, "scene": None, "kind": None, "fallback_reason": None}
 
     def fence():
         torch.cuda.synchronize()
@@ -37,14 +38,32 @@ def run(args, A, rank, world):
     def fresh():
         """A simulation at the start of the timed window: the scene advanced to PREROLL_T plus W warm-up steps (untimed).
         Every rank sees the same global dt and the same error flags, so all ranks take the same number of steps."""
-        sim = A.DistributedFluidSimulation.from_scene(params, scene, counters_enabled=True, lib=lib, rank=rank, world=world, device=local)
+        sim = A.DistributedFluidSimulation.from_scene(params, state["scene"], counters_enabled=True, lib=lib, rank=rank, world=world, device=local)
         state["pre_steps"] = preroll(sim, args.preroll_time)
         for _ in range(W):
             sim.single_step()
         sim.set_kernel_timing(4)
         return sim
 
-    sim = fresh()
+    # The scene: the default kind, or — should it not reach the timed window on this machine (every rank sees the same
+    # error flags; the ranks agree on the outcome) — the one wide block the first measurements of the round were taken on.
+    sim = None
+    for kind in ([SCENE_KIND] if SCENE_KIND == "wide" else [SCENE_KIND, "wide"]):
+        state["scene"], state["kind"] = dam_break(A, SPACING_C2, n_gpus=world, kind=kind), kind
+        ok, why = 1, None
+        try:
+            sim = fresh()
+        except A.AsphError as e:
+            ok, why, sim = 0, str(e), None
+        agree = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if int(agree.item()) == 1:
+            break
+        if sim is not None:
+            sim.close(); sim = None
+        state["fallback_reason"] = f"scene '{kind}' failed before the timed window: {why or 'on another rank'}"
+    if sim is None:
+        raise RuntimeError(state["fallback_reason"])
     n_global = sim.n_global
     clocks = ClockSampler(local)
     if rank == 0:
@@ -150,10 +169,11 @@ def run(args, A, rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms_max / max(K, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"configs[1] widened {world}x: 2D dam-break, uniform h, {n_global} particles ({n_global // world} per GPU), "
+            "config": {"workload": (f"configs[1] x {world}: {world} dam-break columns of the configs[1] block side by side in a {2 * world} m tank (half columns against the side walls, slab faces through the middle of the others), "
+                                    if state["kind"] != "wide" else f"configs[1] widened {world}x (one block): ") + f"2D dam-break, uniform h, {n_global} particles ({n_global // world} per GPU), "
                                    "HybridDFSPH, x-slab decomposition; ghost values of the sweeps stored straight into the neighbour GPU over NVLink peer memory, NCCL for migration / ghost set-up; "
                                    f"block 0.02 above the floor, state at t = {args.preroll_time} s (the block has landed: both pressure solves iterate)",
-                       "preroll_steps": pre_steps, "preroll_time_s": args.preroll_time, "replay_window_steps": window, "failed_steps_replayed": state["restarts"],
+                       "scene": state["kind"], "scene_fallback": state["fallback_reason"], "preroll_steps": pre_steps, "preroll_time_s": args.preroll_time, "replay_window_steps": window, "failed_steps_replayed": state["restarts"],
                        "particles": n_global, "owned_per_rank": [int(x.item()) for x in owned_all],
                        "l2": "working set per GPU (~400 MB) exceeds the 126 MB L2; no flush",
                        "switches": {k: os.environ[k] for k in ("ASPH_ROWS4", "ASPH_DIST_P2P", "ASPH_P2P_EDGE_FIRST", "ASPH_SWEEP_GRID") if k in os.environ},

@@ -70,3 +70,30 @@ def test_measured_line_survives_sigterm_during_experiments(tmp_path):
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["value"] == 1.0 and "interrupted" in d["experiments"]
+
+
+def test_weak_scaling_scene_columns():
+    """bench.py's N-GPU scene: N x the fluid of configs[1] as dam-break columns whose middles the equal-count slab faces
+    (host mirror of dist.cu `rebalance`) cut through, about the same number of particles on every GPU."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import asph_b200 as A
+    import bench
+    one = A.scene_particle_count(bench.dam_break(A, bench.SPACING_C2))
+    assert one == 999292
+    for n in (2, 4, 8):
+        sc = bench.dam_break(A, bench.SPACING_C2, n_gpus=n, kind="columns")
+        assert len(sc.blocks) == n + 1 and abs(A.scene_particle_count(sc) / (n * one) - 1) < 2e-3
+        assert A.scene_particle_count(bench.dam_break(A, bench.SPACING_C2, n_gpus=n, kind="wide")) >= n * one
+        coarse = bench.dam_break(A, 8e-3, n_gpus=n, kind="columns")
+        pos, _, _ = A.scene_particles(coarse)
+        x = pos[:, 0].astype(np.float64)
+        assert np.all(np.diff(x) >= 0)   # reference order is already sorted by x: contiguous index shares are x-slabs
+        hist, _ = np.histogram(x, bins=8192, range=(x.min(), x.max()))
+        faces = A.slab_bounds_from_histogram(hist, x.min(), x.max(), n)[1:-1]
+        centres = [-n + 2.0 * k for k in range(1, n)]
+        assert len(faces) == n - 1
+        for f, c in zip(faces, centres):
+            assert abs(f - c) < 0.05, (n, faces, centres)   # through the middle of a full column (0.7 wide)
+        owned = np.histogram(x, bins=[-np.inf] + list(faces) + [np.inf])[0]
+        assert owned.max() / owned.min() < 1.03, owned
