@@ -6,7 +6,7 @@ import asph_b200 as A
 from bench import uniform_params, dam_break, SPACING_C2
 n_gpus = int(sys.argv[1]); steps = int(sys.argv[2])
 params = uniform_params(A)
-scene = dam_break(A, SPACING_C2, n_gpus=n_gpus)
+scene = dam_break(A, SPACING_C2, n_gpus=n_gpus, kind="wide")
 pos, vel, mass = A.scene_particles(scene)
 sim = A.FluidSimulation(params, pos, vel, mass, A.scene_boundary(scene, "AnalyticOverestimate"))
 for k in range(steps):
