@@ -32,10 +32,19 @@ def main():
     # "random": seeded random velocities => compression somewhere from the first step, the pressure solver iterates
     #           (the recipe of test_single_step_uniform); few steps, because an SPH impact amplifies rounding noise
     # "drift":  the block moves to the right in free fall => particles migrate between slabs every step
-    scene = A.SceneConfig.dam_break(spacing, pos=(-0.9, -0.6), size=(1.2, 0.5))
+    # "columns": the benchmark's weak-scaling scene in small (bench.py `dam_break`): separate fluid columns with empty
+    #           space between them, slab faces through the middle of a column, random velocities as in "random"
+    if mode == "columns":
+        tank = 2.0 * world
+        spans = [(-tank / 2 + 0.05, 0.3)] + [(-tank / 2 + 2.0 * k - 0.3, 0.6) for k in range(1, world)] + [(tank / 2 - 0.35, 0.3)]
+        scene = A.SceneConfig({"boundary": {"type": "box", "width": tank, "height": 2.0},
+                               "blocks": [{"pos": [x0, -0.98], "size": [w, 0.5], "spacing": spacing, "volume_fill_ratio": 0.93,
+                                           "velocity": [0, 0]} for x0, w in spans]})
+    else:
+        scene = A.SceneConfig.dam_break(spacing, pos=(-0.9, -0.6), size=(1.2, 0.5))
     pos, vel, mass = A.scene_particles(scene)
     rng = np.random.default_rng(7)
-    if mode == "random":
+    if mode in ("random", "columns"):
         vel = (rng.standard_normal(vel.shape) * 0.05).astype(np.float32)
     else:
         vel = (rng.standard_normal(vel.shape) * 0.002).astype(np.float32)

@@ -53,6 +53,17 @@ def test_two_gpu_pressure_solve_matches_single_gpu(solver):
     assert rep["err"]["pressure"] < 1e-3 and rep["err"]["velocity"] < 1e-4, rep
 
 
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: first run on hardware pending")
+def test_two_gpu_separate_columns_match_single_gpu():
+    """The benchmark's weak-scaling scene in small: fluid columns with empty space between them, the slab face through the
+    middle of one (added when the round's GPU time was spent; first run on hardware pending)."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rep = _run(2, 4, "HybridDFSPH", mode="columns")
+    _check(rep, 1e-6)
+    assert rep["sweeps_equal"], rep
+
+
 def test_two_gpu_migration():
     """The block drifts to the right: particles change owner every step; ownership stays a partition and the trajectory
     equals the single-GPU one."""

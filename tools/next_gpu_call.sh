@@ -6,7 +6,7 @@
 # Everything lands in gpurun_out/ (merged back into the repo's gpurun_out/ by gpurun).
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-timeout 300 python -m pytest tests/test_zz_unverified_modes.py tests/test_oracle_numpy_step.py -m gpu -q --runxfail --tb=short -p no:cacheprovider > gpurun_out/pending_modes.log 2>&1
+timeout 600 python -m pytest tests/test_zz_unverified_modes.py tests/test_oracle_numpy_step.py tests/test_dist_gpu.py -m gpu -q --runxfail --tb=short -p no:cacheprovider > gpurun_out/pending_modes.log 2>&1
 echo "pending modes: rc=$?"; tail -15 gpurun_out/pending_modes.log
 timeout 500 python -m pytest tests -q -m gpu -x -rxX -p no:cacheprovider > gpurun_out/gpu_suite.log 2>&1
 echo "gpu suite: rc=$?"; tail -8 gpurun_out/gpu_suite.log
