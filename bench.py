@@ -60,16 +60,17 @@ def uniform_params(A):
 
 BLOCK_W, BLOCK_H = [float(v) for v in os.environ.get("ASPH_BENCH_BLOCK", "0.7,1.8").split(",")]
 # Weak scaling (N > 1 GPUs), the tank is N times as wide and holds N times the fluid of configs[1]:
-#   "columns" (default): N dam-break columns of the configs[1] width side by side, one per 2 m of tank — a half-width column
-#             against either side wall and N - 1 full ones between them, so that the equal-count slab faces of the
-#             decomposition cut through the middle of the full columns (every GPU owns two half columns and exchanges a halo
-#             through fluid).  Every column is the 1-GPU problem again: the pressure solves need the sweeps of the 1-GPU
-#             scene (oracle, 2 x 1 M particles: 3 + 19.9 per step against 3 + 18.9), so particle-steps/s is comparable
-#             across GPU counts.
-#   "wide":   ONE block N times as wide (the scene of the first measurements of this round).  The wider the wetted floor, the
-#             more Jacobi sweeps a step needs (23 / 35 / 55 density sweeps at 2 / 4 / 8 GPUs) and the sooner the reference's
-#             solver loses the scene, so particle-steps/s then mixes the scaling of the code with the physics of the scene.
-SCENE_KIND = os.environ.get("ASPH_BENCH_SCENE", "columns")
+#   "wide" (default): ONE block N times as wide — the scene every multi-GPU number of this round was measured on.  The wider
+#             the wetted floor, the more Jacobi sweeps a step needs (23 / 35 / 55 density sweeps at 2 / 4 / 8 GPUs against
+#             19 at one) and the sooner the reference's solver loses the scene, so particle-steps/s mixes the scaling of
+#             the code with the physics of the scene; particle-sweeps/s (in `config`) is the like-for-like figure.
+#   "columns" (ASPH_BENCH_SCENE=columns; exploratory): N dam-break columns of the configs[1] width side by side, one per 2 m
+#             of tank — a half-width column against either side wall and N - 1 full ones between them, so that the
+#             equal-count slab faces cut through the middle of the full columns.  On the CPU oracle 2 x 1 M particles need
+#             3 + 21.0 sweeps per step in the benchmark window (wide: 3 + 22.5), but 4 x 1 M particles run into solves that
+#             do not converge within max_iters a few steps after the landing (steps 30, 31 of the pre-roll): more separate
+#             impacts, more chances for the reference's solver to lose one.  Not the default; no hardware run yet.
+SCENE_KIND = os.environ.get("ASPH_BENCH_SCENE", "wide")
 
 
 def dam_break(A, spacing, n_gpus=1, block_width=None, kind=None):

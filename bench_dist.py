@@ -1,9 +1,9 @@
 """Multi-GPU arm of bench.py (N > 1, one rank per GPU under torchrun): slab decomposition along x, NCCL halos.
 
 Weak scaling: the tank is N times as wide and holds N times the fluid of BASELINE configs[1], so every GPU owns about
-999 292 particles — by default as N dam-break columns side by side whose middles the slab faces cut through (bench.py
-`dam_break`, "columns": the sweep counts of the 1-GPU scene), or as one N-fold wider block (`ASPH_BENCH_SCENE=wide`; also
-the fallback should the default scene fail to reach the timed window).
+999 292 particles — as one N-fold wider block (the physics per column is not quite unchanged: the wider the wetted floor,
+the more sweeps a step needs, see bench.py) or, with `ASPH_BENCH_SCENE=columns`, as N separate dam-break columns whose
+middles the slab faces cut through (exploratory; falls back to the wide block should it fail to reach the timed window).
 Each rank generates only its own share of the lattice.  Timing: barrier + synchronize on both sides of the K timed
 steps; per rank the CUDA-event time of the steps on the library's stream; the job's time is the MAX over ranks.
 The timed steps replay a window of REPLAY_WINDOW steps after the pre-roll (bench.py explains why): at the end of a
