@@ -292,7 +292,7 @@ def run_ours(args):
     if log:
         with open(log, "w") as f:
             json.dump({"per_step": per_step}, f)
-    if not args.no_experiments and "ASPH_ROWS4" not in os.environ:
+    if not args.no_experiments and "ASPH_ROWS4" not in os.environ and "ASPH_SWEEP_GRID" not in os.environ:
         run_experiments(args, out)
     print(json.dumps(out), flush=True)
 
@@ -340,6 +340,9 @@ def run_experiments(args, out):
     try:
         t_exp = time.perf_counter()
         exp["rows4"] = experiment_rows4(args, out)
+        for per_sm in (2, 3):
+            if time.perf_counter() - t_exp < 100:
+                exp[f"sweep_grid_{per_sm}_per_sm"] = experiment_occupancy(args, out, per_sm)
         # the adaptive workloads of BASELINE.json that the headline metric is not quoted on (default kernels; one GPU)
         for key, spacing, warm, steps, limit in (("adaptive_4m_configs2", 5.612e-4, 60, 40, 120), ("adaptive_16m_north_star", 2.806e-4, 20, 10, 150)):
             if time.perf_counter() - t_exp > 150:
@@ -352,19 +355,19 @@ def run_experiments(args, out):
             signal.signal(s, h)
 
 
-def experiment_rows4(args, base):
-    """A/B of the experimental sweep schedule (ASPH_ROWS4=1): the same workload in a separate process, after
-    the measurement above is complete.  Reported beside it under "experiments", never as `value`."""
-    k = max(4, min(args.steps, 32))
+def experiment_switch(args, base, env, what, steps=None, limit_s=90):
+    """The same workload in a separate process with library switches set in its environment, after the measurement above
+    is complete.  Reported beside it under "experiments", never as `value`."""
+    k = steps or max(4, min(args.steps, 32))
     cmd = [sys.executable, os.path.abspath(__file__), "--steps", str(k), "--warmup", str(args.warmup), "--cpu-budget", "0",
            "--preroll-time", str(args.preroll_time), "--no-experiments"]
     try:
-        rc, so, se = _run_child(cmd, 90, env=dict(os.environ, ASPH_ROWS4="1"))
+        rc, so, se = _run_child(cmd, limit_s, env=dict(os.environ, **env))
         line = [l for l in (so or "").splitlines() if l.startswith("{")]
         if rc != 0 or not line:
             return {"error": (se or so or "")[-300:], "returncode": rc}
         r = json.loads(line[-1])
-        return {"what": "own row last in the neighbour lists, sweep kernels in steps of 4 rows (not the default: no parity run on hardware yet)",
+        return {"what": what, "switches": env,
                 "value": r["value"], "ms_per_step": r["ms_per_step"], "steps": r["steps"],
                 "avg_div_sweeps": r["config"]["avg_div_sweeps"], "avg_density_sweeps": r["config"]["avg_density_sweeps"],
                 "particle_sweeps_per_s": r["config"]["particle_sweeps_per_s"], "jacobi_pass_ms": r["roofline"].get("avg_launch_ms"), "accel_pass_ms": (r.get("roofline_accel") or {}).get("avg_launch_ms"),
@@ -372,6 +375,26 @@ def experiment_rows4(args, base):
                 "baseline_particle_sweeps_per_s": base["config"]["particle_sweeps_per_s"]}
     except Exception as e:  # a malformed line must not cost the bench its result
         return {"error": repr(e)[:300]}
+
+
+def experiment_rows4(args, base):
+    """A/B of the experimental sweep schedule (ASPH_ROWS4=1)."""
+    return experiment_switch(args, base, {"ASPH_ROWS4": "1"},
+                             "own row last in the neighbour lists, sweep kernels in steps of 4 rows (not the default: no parity run on hardware yet)")
+
+
+def experiment_occupancy(args, base, blocks_per_sm):
+    """Sensitivity of the default sweep kernels to resident blocks per SM (ASPH_SWEEP_GRID caps the persistent grid; the
+    default is 4 per SM with uniform h): how much of a pass is latency hidden by occupancy — an input for the next kernel
+    design, not a candidate default."""
+    sm = 148
+    try:
+        import torch
+        sm = torch.cuda.get_device_properties(0).multi_processor_count
+    except Exception:
+        pass
+    return experiment_switch(args, base, {"ASPH_SWEEP_GRID": str(sm * blocks_per_sm)},
+                             f"default sweep kernels with the persistent grid capped at {blocks_per_sm} blocks per SM ({sm} SMs)", steps=8, limit_s=60)
 
 
 def experiment_adaptive(spacing, warmup, steps, limit_s):
