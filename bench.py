@@ -341,11 +341,11 @@ def run_experiments(args, out):
         t_exp = time.perf_counter()
         exp["rows4"] = experiment_rows4(args, out)
         for per_sm in (2, 3):
-            if time.perf_counter() - t_exp < 100:
+            if time.perf_counter() - t_exp < 45 + 30 * (per_sm - 2):
                 exp[f"sweep_grid_{per_sm}_per_sm"] = experiment_occupancy(args, out, per_sm)
         # the adaptive workloads of BASELINE.json that the headline metric is not quoted on (default kernels; one GPU)
         for key, spacing, warm, steps, limit in (("adaptive_4m_configs2", 5.612e-4, 60, 40, 120), ("adaptive_16m_north_star", 2.806e-4, 20, 10, 150)):
-            if time.perf_counter() - t_exp > 150:
+            if time.perf_counter() - t_exp > 120:
                 exp[key] = {"skipped": "experiment time budget used up"}
                 continue
             exp[key] = experiment_adaptive(spacing, warm, steps, limit)
