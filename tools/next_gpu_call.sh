@@ -26,3 +26,8 @@ for v in 0 1; do
     python tools/profile_step.py 1.122e-3 2 > gpurun_out/profile_rows4_$v.log 2>&1
   echo "ncu launch list ROWS4=$v: rc=$?"
 done
+# 6. (separate call, `gpurun --gpus 2`): the 2-GPU parity tests incl. the columns layout and the 4-row peer kernels, then the
+#    two weak-scaling scenes side by side:
+#      python -m pytest tests/test_dist_gpu.py tests/test_zz_unverified_modes.py -m gpu -q --runxfail -k "two_gpu"
+#      for s in wide columns; do ASPH_BENCH_SCENE=$s python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
+#        --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 16 --warmup 3; done
