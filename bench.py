@@ -102,6 +102,22 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def issue_roofline(n, launch_ms, sm_count, sm_mhz, warp_instructions, hbm_peak_gbs):
+    """Second reading of the Jacobi update pass: it executes ~590 instructions per particle for its 40
+    algorithmic bytes (13 pairs x ~21 instructions + the tile pipeline), about 2.6 x the chip's instruction-to-byte balance,
+    so its ceiling is the issue rate (4 warp instructions / clock / SM), reported beside the contract's HBM roofline.
+    `warp_instructions` per launch comes from the committed ncu capture (profiles/r1_traffic.json)."""
+    peak = 4.0 * sm_count * sm_mhz * 1e6
+    achieved = warp_instructions / (launch_ms * 1e-3)
+    floor_s = warp_instructions / peak                      # duration with every issue slot filled
+    return {"bound": "issue", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "G warp-instructions/s", "frac": achieved / peak,
+            "sm_count": int(sm_count), "sm_mhz": float(sm_mhz), "instructions_per_launch": float(warp_instructions),
+            "instructions_per_particle": 32.0 * warp_instructions / n,
+            "instructions_source": "profiles/r1_traffic.json (ncu smsp__inst_executed.sum, same kernel and workload)",
+            # the contract's HBM fraction (40 B x particles / time / peak) this instruction mix would reach at full issue
+            "hbm_frac_at_full_issue": 40.0 * n / floor_s / 1e9 / hbm_peak_gbs}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -228,6 +244,13 @@ def run_ours(args):
         roof["frac"] = roof["achieved"] / peak
         roof["avg_launch_ms"] = ms_j
         roof["launches_timed"] = int(kt["jacobi_sweep"][1])
+        if "ASPH_ROWS4" not in os.environ:
+            try:
+                import torch
+                extra["roofline_issue"] = issue_roofline(n, ms_j, torch.cuda.get_device_properties(0).multi_processor_count,
+                                                         clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965.0, tr["warp_instructions"], peak)
+            except Exception as e:  # informational: never at the cost of the line
+                extra["roofline_issue"] = {"error": repr(e)[:200]}
     if kt["accel_sweep"][1] > 0:
         ms_a = kt["accel_sweep"][0] / kt["accel_sweep"][1]
         extra["roofline_accel"] = {"kernel": "k_sweep<0> (K14, the pressure-acceleration pass: x,m,rho,p -> a^p; 28 B/particle algorithmic)",

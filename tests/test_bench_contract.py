@@ -97,3 +97,14 @@ def test_weak_scaling_scene_columns():
             assert abs(f - c) < 0.05, (n, faces, centres)   # through the middle of a full column (0.7 wide)
         owned = np.histogram(x, bins=[-np.inf] + list(faces) + [np.inf])[0]
         assert owned.max() / owned.min() < 1.03, owned
+
+
+def test_issue_roofline_arithmetic():
+    """The second (issue-slot) reading of the Jacobi update pass next to the contract's HBM roofline: numbers of the round's
+    measurement (36.5 us per launch, 18.4 M warp instructions, 148 SMs at 1965 MHz, 6456.8 GB/s)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    r = bench.issue_roofline(999292, 0.0365, 148, 1965.0, 18.40e6, 6456.8)
+    assert abs(r["peak"] - 4 * 148 * 1.965) < 1e-6 and r["unit"] == "G warp-instructions/s"
+    assert abs(r["frac"] - 0.4334) < 1e-3 and abs(r["instructions_per_particle"] - 589.2) < 0.1
+    assert abs(r["hbm_frac_at_full_issue"] - 0.391) < 1e-3   # the HBM fraction is capped at 39 % by the instruction count
