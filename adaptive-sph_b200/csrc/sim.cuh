@@ -235,6 +235,7 @@ struct asph_sim {
   uint64_t pc_calls[ASPH_PC_COUNT] = {0};
   cudaEvent_t ev_begin[ASPH_PC_COUNT], ev_end[ASPH_PC_COUNT];
   int sm_count = 148;
+  bool bulk = false;   // ASPH_BULK=1 at asph_create: bulk-copy stage fill of the sweep kernels (experiment, solver.cu; not the default)
   bool rows4 = false;  // ASPH_ROWS4=1 at asph_create: self row last + 4-row granularity in the sweep kernels (not the default yet)
   bool sweep_attr_done = false;  // dynamic shared-memory limit of the sweep kernels raised on this handle's device
   bool ctl_seen = false;  // ctl_host holds a control block read back from the device (possibly of the previous step)

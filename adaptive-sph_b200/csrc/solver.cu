@@ -548,268 +548,46 @@ struct SweepArgs {
 
 // W2020 (update pass under the Winchenbach2020 operator): `hm` is {h, m / rho} (k_aii_w2020), so
 // every pair carries its own weight m_j / rho_j, and the pair sum is not divided by rho_i (simulation.rs:1571-1575).
-template <int PASS, bool HMWIN, bool PEER, bool W2020 = false, bool R4 = false>
-__global__ void __launch_bounds__(kThreads, (HMWIN || (PEER && !R4)) ? 3 : 4)
-k_sweep(const SweepArgs A) {
-  static_assert(!W2020 || (PASS == 1 && HMWIN), "the Winchenbach2020 variant is an update pass with the {h, m / rho} window");
-  static_assert(!R4 || !W2020, "the 4-row variant exists for the default operators only");
-  extern __shared__ __align__(16) unsigned char sweep_smem[];
-  typedef SweepStage<HMWIN> Stage;
-  Stage* stages = reinterpret_cast<Stage*>(sweep_smem);
-  __shared__ int s_stop;
-  StepCtl* ctl = A.ctl;
-  const bool done0 = ctl->solver.done != 0;
-  bool work = !done0;  // (block-uniform) once the solve is over a pass only keeps the ranks' sequence numbers aligned
-  const uint32_t n = A.n, tid = threadIdx.x, G = gridDim.x;
-  const uint32_t ntiles = (n + kThreads - 1) / kThreads;
-  const bool odd = (A.sweep & 1) != 0;
-  const float4* __restrict__ packP = odd ? A.P1 : A.P0;
-  float4* __restrict__ packP_next = odd ? A.P0w : A.P1w;
-  const float4* __restrict__ pack = PASS == 0 ? packP : A.packA;  // what the pass gathers
-  const bool uni = !W2020 && ctl->hmin == ctl->hmax;
-  const float dt = ctl->dt;
-  const float err_scale = A.density_mode ? dt * dt : dt;  // predicted density / divergence error per unit of residual
+#define SWEEP_BULK 0
+#define SWEEP_KERNEL_NAME k_sweep
+#include "sweep_kernel.inc"
+#undef SWEEP_BULK
+#undef SWEEP_KERNEL_NAME
 
-  // column header of a tile, kept in registers two tiles ahead
-  // (the far-table slot this thread stages travels the same way: fj = particle index, fc = slots in use).  Only
-  // independent loads here: a warp issues in order, so nothing in this lambda may consume what it has just requested.
-  auto load_hdr = [&](uint32_t t, uint32_t& c, uint32_t& sb, uint32_t& fj, uint32_t& fc) {
-    const uint32_t i = t * kThreads + tid;
-    c = 0u; sb = 0u; fj = 0u; fc = 0u;
-    if (t < ntiles) {
-      if (i < n) { c = __ldg(&A.L.cnt[i]); sb = __ldg(&A.L.slice_base[i >> 5]); }
-      fc = __ldg(&A.L.far_cnt[t]);
-      if (tid < kFar) fj = __ldg(&A.L.far_idx[t * kFar + tid]);
-    }
-  };
-  // all asynchronous copies of a tile into a stage
-  auto issue = [&](uint32_t t, Stage& S, uint32_t c, uint32_t sb, uint32_t fj, uint32_t fc) {
-    if (tid < min(fc, kFar)) {
-      fj = min(fj, n - 1u);  // a slot whose owner gave up on the table (neighbors.cu) may hold anything
-      cp_async16(smem_addr(&S.win[kWin + tid]), pack + fj);
-      if (HMWIN && !uni) cp_async8(smem_addr(&S.hmw[kWin + tid]), A.hm + fj);
-    }
-    const uint32_t w0 = t * kThreads - kHalo;
-    for (uint32_t slot = tid; slot < kWin; slot += kThreads) {
-      const uint32_t g = w0 + slot;
-      if (g < n) {
-        cp_async16(smem_addr(&S.win[slot]), pack + g);
-        if (HMWIN && !uni) cp_async8(smem_addr(&S.hmw[slot]), A.hm + g);
-      }
-    }
-    const uint32_t i = t * kThreads + tid;
-    if (i < n) {
-      const uint32_t cw = nb_cw(c);
-      const uint16_t* col = A.L.pool + size_t(sb & 0x7fffffffu) * 64u + (i & 31u) * 8u;
-      if (cw > 0u) cp_async16(smem_addr(&S.chunk[0][tid]), col);
-      if (cw > 8u) cp_async16(smem_addr(&S.chunk[1][tid]), col + 256);
-      cp_async8(smem_addr(&S.own2[tid]), A.hm + i);
-      if (PASS == 0) {
-        cp_async8(smem_addr(&S.own4[tid]), A.gB + i);
-      } else {
-        cp_async16(smem_addr(&S.own4[tid]), A.pconst + i);
-        cp_async4(smem_addr(&S.own1[0][tid]), A.rho + i);
-        cp_async4(smem_addr(&S.own1[1][tid]), reinterpret_cast<const float*>(packP + i) + 3);
-      }
-    }
-  };
-
-  // multi-GPU: a border particle's result also goes into its ghost copy on the neighbour rank(s), over NVLink
-  auto publish = [&](uint32_t t, uint32_t i, const float4& v) {
-    if (!PEER || !A.peer.tile_border[t]) return;
-    const uint32_t sl = A.peer.rslot[0][i], sr = A.peer.rslot[1][i];
-    if (sl != 0xffffffffu && A.peer.dst[0]) A.peer.dst[0][sl] = v;
-    if (sr != 0xffffffffu && A.peer.dst[1]) A.peer.dst[1][sr] = v;
-  };
-
-  // Tiles are walked in sequence q = blockIdx.x, + G, ...; multi-GPU (peer-memory path): through the permutation that
-  // puts the edge tiles first (sim.cuh), whose entries travel in registers three tiles ahead.
-  const uint32_t* __restrict__ order = PEER ? A.peer.tile_order : nullptr;
-  const uint32_t n_edge = order ? order[ntiles] : 0u;
-  auto ord = [&](uint32_t q) { return order ? (q < ntiles ? __ldg(order + q) : 0xffffffffu) : q; };
-  uint32_t q = blockIdx.x;
-  if (q >= ntiles) work = false;
-  uint32_t tile = 0, t_nxt = 0, t_nn = 0;
-  uint32_t c_cur = 0, sb_cur = 0, fj_cur = 0, fc_cur = 0, c_nxt = 0, sb_nxt = 0, fj_nxt = 0, fc_nxt = 0;
-  if (work) {
-    tile = ord(q); t_nxt = ord(q + G); t_nn = ord(q + 2u * G);
-    load_hdr(tile, c_cur, sb_cur, fj_cur, fc_cur);
-    load_hdr(t_nxt, c_nxt, sb_nxt, fj_nxt, fc_nxt);
-  }
-  // The stop rule of iisph_pressure_iterations for sweep number sweep - 1, from its totals: evaluated by every block in
-  // the prologue of the next pressure-acceleration pass — or, on the peer-memory path, of the next update pass, so that
-  // the other ranks' totals have a whole pass to arrive (the acceleration pass in between is then executed once too
-  // often at the end of a solve; its output is not used).  Block 0 also records the decision for the host.
-  const bool decides = !done0 && A.sweep > 0 && (PEER ? PASS == 1 : PASS == 0);
-  if (decides || (PEER && work)) {
-    if (tid == 0) {
-      if (PEER) peer_wait_halo(A.peer, ctl);  // the neighbours' border values this pass gathers
-      if (decides) {
-        if (PEER) peer_wait_stats(A.peer, ctl);
-        const SweepTotals t = read_totals(ctl, A.sweep - 1, A.peer);
-        const bool stop = sweep_stops(t, A.sweep - 1, ctl->error_flags, dt, A.rho0, A.tol, A.max_iters, A.density_mode);
-        if (blockIdx.x == 0) record_sweep(ctl, t, A.sweep - 1, stop);
-        s_stop = stop ? 1 : 0;
-      } else {
-        s_stop = 0;
-      }
-    }
-    __syncthreads();
-    if (s_stop) work = false;  // the solve ended with the previous sweep
-  }
-  if (work) issue(tile, stages[0], c_cur, sb_cur, fj_cur, fc_cur);
-
-  uint32_t c_normal = 0, c_sing = 0, c_neg = 0;
-  float e_sum = 0.f, e_max = 0.f;
-  bool bad = false;
-  bool halo_sent = false;  // (block-uniform) the edge tiles of this pass were processed, so their completion sends the number
-  int s = 0;
-  for (; work && q < ntiles; q += G, s ^= 1) {
-    Stage& S = stages[s];
-    // tile t's copies (issued one iteration ago) have landed for every thread; the same barrier also says that every
-    // thread is done computing tile t - 1, so its stage can be refilled at once with tile t + 1
-    cp_async_wait_all();
-    __syncthreads();
-    if (q + G < ntiles) issue(t_nxt, stages[s ^ 1], c_nxt, sb_nxt, fj_nxt, fc_nxt);
-    uint32_t c_nn, sb_nn, fj_nn, fc_nn;
-    load_hdr(t_nn, c_nn, sb_nn, fj_nn, fc_nn);
-    const uint32_t t_n3 = ord(q + 3u * G);
-
-    const uint32_t i = tile * kThreads + tid;
-    // multi-GPU: ghost particles are skipped in both passes — their values arrive from the owner rank, possibly before
-    // this block gets here (peer-memory path), and must not be overwritten with sums over an incomplete neighbourhood
-    const bool active = i < n && !nb_ghost(c_cur);
-    if (active) {
-      NbCol col;
-      col.far_idx = A.L.far_idx; col.i = i; col.cw = nb_cw(c_cur); col.cf = nb_cf(c_cur); col.cn = col.cw + col.cf;
-      col.wide = (sb_cur >> 31) != 0u;
-      col.slice = A.L.pool + size_t(sb_cur & 0x7fffffffu) * 64u;
-      const float4 me = S.win[kHalo + tid];
-      const float2 own = S.own2[tid];
-      PairWindow W;
-      W.wp = S.win; W.wh = S.hmw; W.wa = nullptr;
-      if (PASS == 0) {
-        const PairCol C(col, S.chunk[0][tid], S.chunk[1][tid]);
-        float ax = 0.f, ay = 0.f;
-        auto body = [&](const float4& o, float dx, float dy, float c, float, float) {
-          const float f = c * (me.z + o.z);
-          ax -= f * dx; ay -= f * dy;
-        };
-        const float scale = uni ? for_each_pair<HM_UNI, false, R4>(C, W, pack, A.hm, nullptr, me.x, me.y, own.x, own.y, body)
-                                : for_each_pair<HMWIN ? HM_WIN : HM_GLOBAL, false, R4>(C, W, pack, A.hm, nullptr, me.x, me.y, own.x, own.y, body);
-        const float2 g = *reinterpret_cast<const float2*>(&S.own4[tid]);
-        ax = ax * scale - me.w * g.x;
-        ay = ay * scale - me.w * g.y;
-        const float4 out = make_float4(me.x, me.y, ax, ay);
-        A.packA[i] = out;
-        publish(tile, i, out);
-      } else {
-        const float4 pc = S.own4[tid];
-        const float rho_i = S.own1[0][tid], p_old = S.own1[1][tid];
-        float pn = 0.f, inv_rho = 0.f;
-        if (fabsf(pc.z) < 10e-4f) {
-          c_sing++;
-        } else {
-          const PairCol C(col, S.chunk[0][tid], S.chunk[1][tid]);
-          float sum = 0.f;
-          auto body = [&](const float4& o, float dx, float dy, float c, float, float) { sum += c * ((o.z - me.z) * dx + (o.w - me.w) * dy); };
-          const float scale = uni ? for_each_pair<HM_UNI, false, R4>(C, W, pack, A.hm, nullptr, me.x, me.y, own.x, own.y, body)
-                                  : for_each_pair<HMWIN ? HM_WIN : HM_GLOBAL, false, R4>(C, W, pack, A.hm, nullptr, me.x, me.y, own.x, own.y, body);
-          // reciprocals by the SFU (1 ulp): the relaxed update does not need correctly rounded quotients, and three
-          // IEEE divisions would be a quarter of this thread's instructions outside the pair loop
-          inv_rho = fast_rcp(rho_i);
-          const float Ap = (sum * scale) * (W2020 ? 1.f : inv_rho) - (me.z * pc.x + me.w * pc.y);
-          const float resid = pc.w - Ap;
-          pn = fmaf(A.omega * resid, fast_rcp(pc.z), p_old);
-          if (!isfinite(pn)) bad = true;  // covers a non-finite Ap as well
-          const float perr = err_scale * (A.density_mode ? rho_i * resid : resid);
-          if (pn <= 0.f) { pn = 0.f; c_neg++; }
-          else { c_normal++; e_sum += perr; e_max = fmaxf(e_max, fabsf(perr)); }
-        }
-        const float4 out = make_float4(me.x, me.y, pn * (inv_rho * inv_rho), pn);
-        packP_next[i] = out;
-        publish(tile, i, out);
-      }
-    }
-    if (PEER && n_edge != 0u) {
-      halo_sent = true;
-      if (q < n_edge) {  // an edge tile is complete: the last one of the pass releases the neighbours
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0 && atomicAdd(A.peer.edge_done, 1u) == n_edge - 1u) {
-          *A.peer.edge_done = 0u;
-          if (A.peer.nb_ctl[0]) st_release_sys(&A.peer.nb_ctl[0]->halo_flag[1], A.peer.halo_seq_out);  // I am my left neighbour's right neighbour
-          if (A.peer.nb_ctl[1]) st_release_sys(&A.peer.nb_ctl[1]->halo_flag[0], A.peer.halo_seq_out);
-        }
-      }
-    }
-    tile = t_nxt; t_nxt = t_nn; t_nn = t_n3;
-    c_cur = c_nxt; sb_cur = sb_nxt; c_nxt = c_nn; sb_nxt = sb_nn; fj_nxt = fj_nn; fc_nxt = fc_nn;
-  }
-
-  if (PASS == 1 && work) {
-    if (bad) atomicOr(&ctl->error_flags, ERRF_SOLVER_NONFINITE);
-    // block totals, once per block: counts by redux, the error sum by a fixed-order shuffle tree; then integers only
-    c_normal = __reduce_add_sync(0xffffffffu, c_normal);
-    c_neg = __reduce_add_sync(0xffffffffu, c_neg);
-    c_sing = __reduce_add_sync(0xffffffffu, c_sing);
-    const unsigned int m_enc = __reduce_max_sync(0xffffffffu, __float_as_uint(e_max));  // non-negative floats order like their bits
-    for (int o = 16; o > 0; o >>= 1) e_sum += __shfl_xor_sync(0xffffffffu, e_sum, o);
-    __shared__ unsigned long long sh_cnt[kThreads / 32];
-    __shared__ long long sh_err[kThreads / 32];
-    __shared__ unsigned int sh_sing[kThreads / 32], sh_max[kThreads / 32];
-    const int lane = tid & 31, w = tid >> 5;
-    if (lane == 0) {
-      sh_cnt[w] = (unsigned long long)c_normal | ((unsigned long long)c_neg << 32);
-      sh_err[w] = __float2ll_rn(fminf(fmaxf(e_sum, -4096.f), 4096.f) * 4294967296.f);  // 2^-32 fixed point
-      sh_sing[w] = c_sing; sh_max[w] = m_enc;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      unsigned long long cnt = 0;
-      long long err = 0;
-      unsigned int sing = 0, mx = 0;
-#pragma unroll
-      for (int k = 0; k < kThreads / 32; k++) { cnt += sh_cnt[k]; err += sh_err[k]; sing += sh_sing[k]; mx = max(mx, sh_max[k]); }
-      SolverCtl& sc = ctl->solver;
-      unsigned long long* acc = sc.acc[A.sweep % 3] + 2 * (blockIdx.x % ASPH_ACC_COPIES);
-      if (cnt) atomicAdd(acc, cnt);
-      if (err) atomicAdd(acc + 1, (unsigned long long)err);
-      if (sing) atomicAdd(sc.acc[A.sweep % 3] + 2 * ASPH_ACC_COPIES, (unsigned long long)sing);
-      // e_max >= 0: its bit pattern with the sign bit set is the order-preserving encoding dec_f expects
-      if (mx) atomicMax(&sc.maxerr_enc[A.sweep % 3], mx | 0x80000000u);
-    }
-  }
-  if (PEER && A.peer.halo_seq_out != 0u) {
-    // every block: its remote stores (and its statistics) are complete and visible system-wide; the block that finishes
-    // last tells the neighbours — and, after the update pass, hands this rank's totals to every rank
-    __threadfence_system();
-    __syncthreads();
-    __shared__ unsigned int s_last;
-    if (tid == 0) s_last = atomicAdd(A.peer.blocks_done, 1u) == gridDim.x - 1u;
-    __syncthreads();
-    if (s_last) {
-      if (A.peer.stats_seq_out != 0u) {
-        const int slot = A.sweep % 3;
-        for (int r = 0; r < A.peer.nranks; r++) {
-          if (r == A.peer.rank) continue;
-          PeerCtl* pc = A.peer.all_ctl[r];
-          if (tid < ASPH_ACC_WORDS) pc->stats_in[A.peer.rank][slot][tid] = *reinterpret_cast<volatile unsigned long long*>(&ctl->solver.acc[slot][tid]);
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (tid < uint32_t(A.peer.nranks) && int(tid) != A.peer.rank) st_release_sys(&A.peer.all_ctl[tid]->stats_flag[A.peer.rank], A.peer.stats_seq_out);
-      }
-      if (tid == 0) {
-        *A.peer.blocks_done = 0u;
-        if (!halo_sent) {  // no tile was processed in this pass (the solve is over), or this rank has no edge tiles
-          if (A.peer.nb_ctl[0]) st_release_sys(&A.peer.nb_ctl[0]->halo_flag[1], A.peer.halo_seq_out);
-          if (A.peer.nb_ctl[1]) st_release_sys(&A.peer.nb_ctl[1]->halo_flag[0], A.peer.halo_seq_out);
-        }
-      }
-    }
+// ---- experiment ASPH_BULK=1: the stage fill of an interior tile as bulk asynchronous copies.  Everything a
+// tile stages except the far-table slots, gB and the own particles' p is a contiguous range of global memory, so one
+// thread (and lane 0 of every warp for its list chunks) issues cp.async.bulk copies that complete on one mbarrier per
+// stage, in place of ~8 LDGSTS per thread with their address arithmetic.  Tiles clipped by either end of the particle
+// range keep the per-thread copies.  The kernel body lives in sweep_kernel.inc and is compiled twice.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0u;
+}
+// bounded (about 4 s): a byte count that never arrives must end in an error flag, not in a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, StepCtl* ctl) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000ll) { atomicOr(&ctl->error_flags, ERRF_PEER_TIMEOUT); return; }
   }
 }
+
+#define SWEEP_BULK 1
+#define SWEEP_KERNEL_NAME k_sweep_bulk
+#include "sweep_kernel.inc"
+#undef SWEEP_BULK
+#undef SWEEP_KERNEL_NAME
+
 
 // grid of a persistent pair pass: every block gets the same number of tiles (the last one possibly fewer)
 inline uint32_t sweep_grid(uint32_t n, int sm_count, int blocks_per_sm) {
@@ -915,12 +693,17 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
     CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
     CUDA_TRY((cudaFuncSetAttribute(k_sweep<0, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small)));
     CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small)));
+    CUDA_TRY((cudaFuncSetAttribute(k_sweep_bulk<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big + 16)));
+    CUDA_TRY((cudaFuncSetAttribute(k_sweep_bulk<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big + 16)));
+    CUDA_TRY((cudaFuncSetAttribute(k_sweep_bulk<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small + 16)));
+    CUDA_TRY((cudaFuncSetAttribute(k_sweep_bulk<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small + 16)));
     CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
     CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
     sim->sweep_attr_done = true;
   }
   const bool p2p = dist_p2p(sim);
   const bool r4 = sim->rows4 && !w2020;  // the lists were written self-last (pack_params: self_last)
+  const bool bulk = sim->bulk && !p2p && !w2020 && !r4;  // experiment ASPH_BULK=1: bulk-copy stage fill (single GPU, default operators)
   SweepArgs A;
   A.n = n; A.L = L; A.P0 = sim->packP[0].p; A.P1 = sim->packP[1].p; A.P0w = sim->packP[0].p; A.P1w = sim->packP[1].p;
   A.packA = sim->packA.p; A.hm = sim->hm.p; A.gB = sim->gB.p; A.pconst = sim->pconst.p; A.rho = sim->rho.p; A.ctl = sim->ctl; A.gid = gid;
@@ -937,7 +720,8 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
       if (launched > 0) {  // sweep 0: a^p = 0 was written by k_source
         A.hm = sim->hm.p;
         A.peer = dist_peer_args(sim, true, !p2p, 0, false);  // waits for the previous sweep's p' ghosts; publishes a^p
-        if (r4 && p2p) { if (hmwin) k_sweep<0, true, true, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, true, false, true><<<grid, kThreads, smem, st>>>(A); }
+        if (bulk) { if (hmwin) k_sweep_bulk<0, true, false><<<grid, kThreads, smem + 16, st>>>(A); else k_sweep_bulk<0, false, false><<<grid, kThreads, smem + 16, st>>>(A); }
+        else if (r4 && p2p) { if (hmwin) k_sweep<0, true, true, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, true, false, true><<<grid, kThreads, smem, st>>>(A); }
         else if (r4) { if (hmwin) k_sweep<0, true, false, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, false, false, true><<<grid, kThreads, smem, st>>>(A); }
         else if (p2p) { if (hmwin) k_sweep<0, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, true><<<grid, kThreads, smem, st>>>(A); }
         else { if (hmwin) k_sweep<0, true, false><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, false><<<grid, kThreads, smem, st>>>(A); }
@@ -950,7 +734,8 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
       if (time_it) cudaEventRecord(tm.e1b, st);
       A.hm = w2020 ? sim->hv.p : sim->hm.p;
       A.peer = dist_peer_args(sim, launched > 0, p2p && launched > 0, 1 + ((launched + 1) & 1), true);  // waits for the a^p ghosts and the previous sweep's totals; publishes p' and its own
-      if (r4 && p2p) { if (hmwin) k_sweep<1, true, true, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, true, false, true><<<grid, kThreads, smem, st>>>(A); }
+      if (bulk) { if (hmwin) k_sweep_bulk<1, true, false><<<grid, kThreads, smem + 16, st>>>(A); else k_sweep_bulk<1, false, false><<<grid, kThreads, smem + 16, st>>>(A); }
+      else if (r4 && p2p) { if (hmwin) k_sweep<1, true, true, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, true, false, true><<<grid, kThreads, smem, st>>>(A); }
       else if (r4) { if (hmwin) k_sweep<1, true, false, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, false, false, true><<<grid, kThreads, smem, st>>>(A); }
       else if (w2020) { if (p2p) k_sweep<1, true, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, true, false, true><<<grid, kThreads, smem, st>>>(A); }
       else if (p2p) { if (hmwin) k_sweep<1, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, true><<<grid, kThreads, smem, st>>>(A); }

@@ -244,7 +244,7 @@ def run_ours(args):
         roof["frac"] = roof["achieved"] / peak
         roof["avg_launch_ms"] = ms_j
         roof["launches_timed"] = int(kt["jacobi_sweep"][1])
-        if "ASPH_ROWS4" not in os.environ:
+        if "ASPH_ROWS4" not in os.environ and "ASPH_BULK" not in os.environ:
             try:
                 import torch
                 extra["roofline_issue"] = issue_roofline(n, ms_j, torch.cuda.get_device_properties(0).multi_processor_count,
@@ -307,7 +307,7 @@ def run_ours(args):
                    "timing": "CUDA events on the library stream around every step (PerformanceCounters 'simulation-step')",
                    "wall_ms_per_step": wall * 1e3 / max(K, 1), "phase_ms_per_step": phases,
                    "particle_sweeps_per_s": particle_sweeps_per_s,
-                   "switches": {k: os.environ[k] for k in ("ASPH_ROWS4", "ASPH_SWEEP_GRID", "ASPH_UNVERIFIED_MODES") if k in os.environ}},
+                   "switches": {k: os.environ[k] for k in ("ASPH_ROWS4", "ASPH_BULK", "ASPH_SWEEP_GRID", "ASPH_UNVERIFIED_MODES") if k in os.environ}},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
     }
     out.update(extra)
@@ -315,7 +315,7 @@ def run_ours(args):
     if log:
         with open(log, "w") as f:
             json.dump({"per_step": per_step}, f)
-    if not args.no_experiments and "ASPH_ROWS4" not in os.environ and "ASPH_SWEEP_GRID" not in os.environ:
+    if not args.no_experiments and not any(k in os.environ for k in ("ASPH_ROWS4", "ASPH_SWEEP_GRID", "ASPH_BULK")):
         run_experiments(args, out)
     print(json.dumps(out), flush=True)
 
@@ -363,8 +363,12 @@ def run_experiments(args, out):
     try:
         t_exp = time.perf_counter()
         exp["rows4"] = experiment_rows4(args, out)
+        if time.perf_counter() - t_exp < 45:
+            exp["bulk"] = experiment_switch(args, out, {"ASPH_BULK": "1"},
+                                            "interior tiles of the sweep kernels staged by cp.async.bulk + mbarrier (k_sweep_bulk; not the default: no parity run on hardware yet)",
+                                            steps=16, limit_s=60)
         for per_sm in (2, 3):
-            if time.perf_counter() - t_exp < 45 + 30 * (per_sm - 2):
+            if time.perf_counter() - t_exp < 60 + 25 * (per_sm - 2):
                 exp[f"sweep_grid_{per_sm}_per_sm"] = experiment_occupancy(args, out, per_sm)
         # the adaptive workloads of BASELINE.json that the headline metric is not quoted on (default kernels; one GPU)
         for key, spacing, warm, steps, limit in (("adaptive_4m_configs2", 5.612e-4, 60, 40, 120), ("adaptive_16m_north_star", 2.806e-4, 20, 10, 150)):

@@ -227,3 +227,55 @@ def test_rows4_two_gpu_pressure_solve_matches_single_gpu(monkeypatch):
     rep = D._run(2, 4, "HybridDFSPH", mode="random")
     D._check(rep, 1e-6)
     assert rep["sweeps_equal"], rep
+
+
+# ---- experiment ASPH_BULK=1: interior tiles of the sweep kernels staged by cp.async.bulk + mbarrier
+# (k_sweep_bulk, sweep_kernel.inc).  Never run on hardware; results must equal the default kernels' (same arithmetic, same order).
+@pytest.fixture
+def bulk(monkeypatch):
+    monkeypatch.setenv("ASPH_BULK", "1")
+    monkeypatch.delenv("ASPH_UNVERIFIED_MODES", raising=False)
+    monkeypatch.delenv("ASPH_ROWS4", raising=False)
+
+
+@never_run
+@pytest.mark.parametrize("solver", ["HybridDFSPH", "IISPH"])
+def test_bulk_single_step_uniform(asph, cuda_lib, oracle32, default_params, solver, bulk):
+    from test_gpu_parity import _single_step_uniform
+    _single_step_uniform(asph, cuda_lib, oracle32, default_params, solver)
+
+
+@never_run
+def test_bulk_single_step_mixed_sizes(asph, cuda_lib, oracle32, default_params, bulk):
+    """{h, m} window variant: masses spread over 4:1."""
+    sc = asph.SceneConfig.dam_break(0.02)
+    pos, vel, mass = asph.scene_particles(sc)
+    rng = np.random.default_rng(2)
+    pos = (pos + rng.uniform(-0.2, 0.2, pos.shape).astype(np.float32) * np.float32(0.02)).astype(np.float32)
+    mass = (mass * np.exp(rng.uniform(-np.log(2.0), np.log(2.0), mass.shape))).astype(np.float32)
+    vel = (rng.standard_normal(vel.shape) * 0.05).astype(np.float32)
+    _one_step(asph, cuda_lib, oracle32, _uniform_params(default_params), pos, vel, mass, asph.scene_boundary(sc, "AnalyticOverestimate"))
+
+
+@never_run
+def test_bulk_equals_default_kernels_bit_for_bit(asph, cuda_lib, default_params, monkeypatch):
+    """Same arithmetic in the same order: 10 steps of a 78 k-particle uniform dam break (about 300 interior tiles) end in
+    the bit-identical state with and without the switch."""
+    sc = asph.SceneConfig.dam_break(0.004)
+    pos, vel, mass = asph.scene_particles(sc)
+    vel = (np.random.default_rng(3).standard_normal(vel.shape) * 0.05).astype(np.float32)
+    params = _uniform_params(default_params)
+    b = asph.scene_boundary(sc, "AnalyticOverestimate")
+    out = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("ASPH_BULK", flag)
+        g = asph.FluidSimulation(params, pos, vel, mass, b, lib=cuda_lib)
+        sweeps = []
+        for _ in range(10):
+            g.single_step(); i = g.step_info(); sweeps.append((i["div_sweeps"], i["density_sweeps"]))
+        out.append((sweeps, g.get_field("position"), g.get_field("velocity"), g.get_field("pressure")))
+        g.close()
+    assert out[0][0] == out[1][0]
+    for k in (1, 2, 3):
+        assert np.array_equal(out[0][k], out[1][k]), k
+
