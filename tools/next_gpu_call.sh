@@ -15,6 +15,9 @@ echo "bench: rc=$?"; cut -c1-600 gpurun_out/bench_short.json
 # 3b. A/B of the 4-row schedule of the sweep kernels
 ASPH_ROWS4=1 timeout 200 python bench.py --steps 8 --warmup 3 > gpurun_out/bench_short_rows4.json 2> gpurun_out/bench_short_rows4.err
 echo "bench ROWS4: rc=$?"; cut -c1-600 gpurun_out/bench_short_rows4.json
+# 3c. A/B of the bulk-copy stage fill
+ASPH_BULK=1 timeout 200 python bench.py --steps 8 --warmup 3 > gpurun_out/bench_short_bulk.json 2> gpurun_out/bench_short_bulk.err
+echo "bench BULK: rc=$?"; cut -c1-600 gpurun_out/bench_short_bulk.json
 # 4. the adaptive workloads that have no number yet: BASELINE configs[2] (4 M particles) and the 16 M north-star case
 timeout 600 python tools/bench_adaptive.py --spacing 5.612e-4 --warmup 60 --steps 40 > gpurun_out/adaptive_4m.json 2> gpurun_out/adaptive_4m.err
 echo "adaptive 4M: rc=$?"; cut -c1-700 gpurun_out/adaptive_4m.json
