@@ -693,6 +693,10 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
     CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
     CUDA_TRY((cudaFuncSetAttribute(k_sweep<0, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small)));
     CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small)));
+    CUDA_TRY((cudaFuncSetAttribute(k_sweep_bulk<0, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big + 16)));
+    CUDA_TRY((cudaFuncSetAttribute(k_sweep_bulk<1, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big + 16)));
+    CUDA_TRY((cudaFuncSetAttribute(k_sweep_bulk<0, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small + 16)));
+    CUDA_TRY((cudaFuncSetAttribute(k_sweep_bulk<1, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small + 16)));
     CUDA_TRY((cudaFuncSetAttribute(k_sweep_bulk<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big + 16)));
     CUDA_TRY((cudaFuncSetAttribute(k_sweep_bulk<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big + 16)));
     CUDA_TRY((cudaFuncSetAttribute(k_sweep_bulk<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small + 16)));
@@ -703,7 +707,7 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
   }
   const bool p2p = dist_p2p(sim);
   const bool r4 = sim->rows4 && !w2020;  // the lists were written self-last (pack_params: self_last)
-  const bool bulk = sim->bulk && !p2p && !w2020 && !r4;  // experiment ASPH_BULK=1: bulk-copy stage fill (single GPU, default operators)
+  const bool bulk = sim->bulk && !p2p && !w2020;  // experiment ASPH_BULK=1: bulk-copy stage fill (single GPU, default operators; with or without ASPH_ROWS4)
   SweepArgs A;
   A.n = n; A.L = L; A.P0 = sim->packP[0].p; A.P1 = sim->packP[1].p; A.P0w = sim->packP[0].p; A.P1w = sim->packP[1].p;
   A.packA = sim->packA.p; A.hm = sim->hm.p; A.gB = sim->gB.p; A.pconst = sim->pconst.p; A.rho = sim->rho.p; A.ctl = sim->ctl; A.gid = gid;
@@ -720,7 +724,8 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
       if (launched > 0) {  // sweep 0: a^p = 0 was written by k_source
         A.hm = sim->hm.p;
         A.peer = dist_peer_args(sim, true, !p2p, 0, false);  // waits for the previous sweep's p' ghosts; publishes a^p
-        if (bulk) { if (hmwin) k_sweep_bulk<0, true, false><<<grid, kThreads, smem + 16, st>>>(A); else k_sweep_bulk<0, false, false><<<grid, kThreads, smem + 16, st>>>(A); }
+        if (bulk && r4) { if (hmwin) k_sweep_bulk<0, true, false, false, true><<<grid, kThreads, smem + 16, st>>>(A); else k_sweep_bulk<0, false, false, false, true><<<grid, kThreads, smem + 16, st>>>(A); }
+        else if (bulk) { if (hmwin) k_sweep_bulk<0, true, false><<<grid, kThreads, smem + 16, st>>>(A); else k_sweep_bulk<0, false, false><<<grid, kThreads, smem + 16, st>>>(A); }
         else if (r4 && p2p) { if (hmwin) k_sweep<0, true, true, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, true, false, true><<<grid, kThreads, smem, st>>>(A); }
         else if (r4) { if (hmwin) k_sweep<0, true, false, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, false, false, true><<<grid, kThreads, smem, st>>>(A); }
         else if (p2p) { if (hmwin) k_sweep<0, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, true><<<grid, kThreads, smem, st>>>(A); }
@@ -734,7 +739,8 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
       if (time_it) cudaEventRecord(tm.e1b, st);
       A.hm = w2020 ? sim->hv.p : sim->hm.p;
       A.peer = dist_peer_args(sim, launched > 0, p2p && launched > 0, 1 + ((launched + 1) & 1), true);  // waits for the a^p ghosts and the previous sweep's totals; publishes p' and its own
-      if (bulk) { if (hmwin) k_sweep_bulk<1, true, false><<<grid, kThreads, smem + 16, st>>>(A); else k_sweep_bulk<1, false, false><<<grid, kThreads, smem + 16, st>>>(A); }
+      if (bulk && r4) { if (hmwin) k_sweep_bulk<1, true, false, false, true><<<grid, kThreads, smem + 16, st>>>(A); else k_sweep_bulk<1, false, false, false, true><<<grid, kThreads, smem + 16, st>>>(A); }
+      else if (bulk) { if (hmwin) k_sweep_bulk<1, true, false><<<grid, kThreads, smem + 16, st>>>(A); else k_sweep_bulk<1, false, false><<<grid, kThreads, smem + 16, st>>>(A); }
       else if (r4 && p2p) { if (hmwin) k_sweep<1, true, true, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, true, false, true><<<grid, kThreads, smem, st>>>(A); }
       else if (r4) { if (hmwin) k_sweep<1, true, false, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, false, false, true><<<grid, kThreads, smem, st>>>(A); }
       else if (w2020) { if (p2p) k_sweep<1, true, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, true, false, true><<<grid, kThreads, smem, st>>>(A); }

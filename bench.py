@@ -367,8 +367,10 @@ def run_experiments(args, out):
             exp["bulk"] = experiment_switch(args, out, {"ASPH_BULK": "1"},
                                             "interior tiles of the sweep kernels staged by cp.async.bulk + mbarrier (k_sweep_bulk; not the default: no parity run on hardware yet)",
                                             steps=16, limit_s=60)
+        if time.perf_counter() - t_exp < 60 and "error" not in exp.get("bulk", {"error": 1}) and "error" not in exp["rows4"]:
+            exp["rows4_bulk"] = experiment_switch(args, out, {"ASPH_ROWS4": "1", "ASPH_BULK": "1"}, "both experiments together", steps=16, limit_s=60)
         for per_sm in (2, 3):
-            if time.perf_counter() - t_exp < 60 + 25 * (per_sm - 2):
+            if time.perf_counter() - t_exp < 75 + 20 * (per_sm - 2):
                 exp[f"sweep_grid_{per_sm}_per_sm"] = experiment_occupancy(args, out, per_sm)
         # the adaptive workloads of BASELINE.json that the headline metric is not quoted on (default kernels; one GPU)
         for key, spacing, warm, steps, limit in (("adaptive_4m_configs2", 5.612e-4, 60, 40, 120), ("adaptive_16m_north_star", 2.806e-4, 20, 10, 150)):

@@ -279,3 +279,20 @@ def test_bulk_equals_default_kernels_bit_for_bit(asph, cuda_lib, default_params,
     for k in (1, 2, 3):
         assert np.array_equal(out[0][k], out[1][k]), k
 
+
+@never_run
+def test_rows4_with_bulk_default_scene_with_resampling(asph, cuda_lib, oracle32, default_params, split_patterns, monkeypatch):
+    """Both experiments together (k_sweep_bulk<., ., ., ., R4>): C1 with level set + resampling, 12 steps."""
+    monkeypatch.setenv("ASPH_ROWS4", "1"); monkeypatch.setenv("ASPH_BULK", "1")
+    monkeypatch.delenv("ASPH_UNVERIFIED_MODES", raising=False)
+    sc = _scene(asph, "default-scene.yaml")
+    g = asph.init_fluid_sim(default_params, sc, split_patterns, lib=cuda_lib)
+    o = asph.init_fluid_sim(default_params, sc, split_patterns, lib=oracle32)
+    for step in range(12):
+        g.single_step(); o.single_step()
+        gi, oi = g.step_info(), o.step_info()
+        for k in ("n_particles_end", "n_shared", "n_merged", "n_split_parents", "div_sweeps", "density_sweeps"):
+            assert gi[k] == oi[k], (step, k, gi, oi)
+    assert _rel(g.get_field("position"), o.get_field("position"), 2.0) <= 1e-5
+    g.close(); o.close()
+
