@@ -578,6 +578,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, StepCtl
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (*reinterpret_cast<volatile unsigned int*>(&ctl->error_flags) & ERRF_PEER_TIMEOUT) return;  // somebody gave up already: do not wait again
     if (clock64() - t0 > 8000000000ll) { atomicOr(&ctl->error_flags, ERRF_PEER_TIMEOUT); return; }
   }
 }
