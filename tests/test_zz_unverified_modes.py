@@ -18,7 +18,7 @@ from test_gpu_parity import _compare_step_fields, _pair, _rel, _scene, _uniform_
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(90)]
 _xf_pending = pytest.mark.xfail(strict=False, reason="failed in its only hardware run (stale flag after a list-pool retry); fixed, re-run pending")
-_iso = pytest.mark.isolated(timeout=75)  # body in a child pytest process (tests/conftest.py): a hang or a sticky CUDA error costs this test only
+_iso = pytest.mark.isolated(timeout=60)  # body in a child pytest process (tests/conftest.py): a hang or a sticky CUDA error costs this test only
 
 
 def pending(f):
