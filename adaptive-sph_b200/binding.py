@@ -98,6 +98,12 @@ def _declare(lib):
     lib.asph_set_kernel_timing.restype = C.c_int
     lib.asph_get_kernel_timing.argtypes = [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     lib.asph_get_kernel_timing.restype = C.c_int
+    lib.asph_adapt_rounds.argtypes = [_P]
+    lib.asph_adapt_rounds.restype = C.c_uint64
+    lib.asph_set_level.argtypes = [_P, _FP, C.c_uint64]
+    lib.asph_set_level.restype = C.c_int
+    lib.asph_set_step_number.argtypes = [_P, C.c_uint64]
+    lib.asph_set_step_number.restype = None
     lib.asph_kernel_launches.argtypes = [_P]
     lib.asph_kernel_launches.restype = C.c_uint64
     lib.asph_backend_name.argtypes = []
@@ -282,11 +288,15 @@ class FluidSimulation:
         self._check(self.lib.asph_set_kernel_timing(self._h, int(sample_every)))
 
     def kernel_timing(self):
-        ms = (C.c_double * 4)()
-        cnt = (C.c_uint64 * 4)()
+        ms = (C.c_double * 6)()
+        cnt = (C.c_uint64 * 6)()
         self._check(self.lib.asph_get_kernel_timing(self._h, ms, cnt))
-        names = ["accel_sweep", "jacobi_sweep", "neighbors", "sort_grid"]
-        return {names[k]: (ms[k], cnt[k]) for k in range(4)}
+        names = ["accel_sweep", "jacobi_sweep", "neighbors", "sort_grid", "level_propagate", "partner_search"]
+        return {names[k]: (ms[k], cnt[k]) for k in range(6)}
+
+    def adapt_rounds(self):
+        """Dependency rounds of the greedy partner searches in the last resampling phase (0 on the CPU oracle)."""
+        return int(self.lib.asph_adapt_rounds(self._h))
 
     def kernel_launches(self):
         return int(self.lib.asph_kernel_launches(self._h))

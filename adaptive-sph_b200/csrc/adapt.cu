@@ -9,14 +9,24 @@
 //   single_step_adaptivity             simulation.rs:2732-2796
 //
 // The reference's partner searches are SERIAL greedy loops over particles in index order (donor i claims the
-// still-unclaimed eligible neighbours j in list order).  They are reproduced exactly by deterministic rounds: in each
-// round every undecided donor stamps itself and its possible receivers with its reference index (64-bit atomicMax
-// of round:~index); a donor whose stamp survived on all of them has no undecided lower-index donor that could touch
-// the same particles, so it runs its inner loop (neighbours in ascending reference index = the oracle's list order)
-// and is final.  Donors claimed as receivers meanwhile drop out.  Particles live on the device in grid-cell order;
-// `refid` carries the reference index, and the reference's swap-with-last deletion and append-at-end splitting are
-// reproduced in reference-index space with prefix sums.
+// still-unclaimed eligible neighbours j in list order).  They are reproduced exactly, without serialising, by ONE
+// persistent cooperative kernel per search (k_greedy; tools/greedy_model.py is its executable specification, checked
+// against the serial loop):
+//   * E'(d) = what donor d would claim if every neighbour were still available (its loop run "optimistically") bounds
+//     what it can ever claim: a claimed neighbour only lowers the divisor of the mass that later candidates are offered.
+//     Donors with an empty E' are final at once (they are most of the donors of a settled simulation).
+//   * d depends on a lower-index undecided donor y only if their touch sets {d} + E^(d), {y} + E^(y) intersect
+//     (E^ = a cheap superset of E').  A donor with no such y runs the reference's inner loop (neighbours in ascending
+//     reference index) and is final; a donor that finds one registers in that blocker's wait list and sleeps until the
+//     blocker has decided or has been claimed itself.  So every donor is examined a handful of times, not once per round,
+//     and a round costs two grid barriers instead of two launches and a host read.
+// Particles live on the device in grid-cell order; `refid` carries the reference index, and the reference's
+// swap-with-last deletion and append-at-end splitting are reproduced in reference-index space with prefix sums.
+#include <cooperative_groups.h>
+
 #include "lists.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -35,7 +45,6 @@ struct AdaptArgs {
   uint8_t* size_class;
   uint32_t* partner;
   uint32_t* counter;
-  unsigned long long* stampkey;
 };
 
 __global__ void k_classify(uint32_t n, const float* __restrict__ level, const float* __restrict__ mass, const PackedParams P,
@@ -79,96 +88,253 @@ __device__ __forceinline__ bool static_eligible(const AdaptArgs& A, const Packed
   return !(dx * dx + dy * dy > max_dist * max_dist);
 }
 
-__global__ void k_partner_init(uint32_t n, AdaptArgs A, uint8_t donor_class, uint32_t* __restrict__ work, StepCtl* ctl) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  A.partner[i] = AVAILABLE;
-  A.counter[i] = 0;
-  A.stampkey[i] = 0ull;
-  if (A.size_class[i] == donor_class) work[atomicAdd(&ctl->work_n[0], 1u)] = i;
-}
 __global__ void k_partner_ctl_reset(StepCtl* ctl) {
-  ctl->work_n[0] = 0; ctl->work_n[1] = 0; ctl->rounds = 0; ctl->n_claims = 0;
+  ctl->work_n[0] = 0; ctl->work_n[1] = 0; ctl->ready_n = 0; ctl->rounds = 0; ctl->n_claims = 0; ctl->greedy_done = 0;
 }
 
-__device__ __forceinline__ unsigned long long stamp_of(uint32_t round, uint32_t refid) {
-  return ((unsigned long long)round << 32) | (unsigned long long)(0xFFFFFFFFu - refid);
+// ---- the greedy partner search as one persistent cooperative kernel ------------------------------------------------
+constexpr int kGreedyThreads = 512;
+constexpr uint32_t NONE_ = 0xFFFFFFFFu;
+constexpr uint32_t GI_PENDING = 1u, GI_DONE = 2u;  // low byte of info[d] for a donor d; bits 8.. = |E'(d)|
+
+struct GreedyArgs {
+  AdaptArgs A;
+  uint32_t* info;    // per particle: 0, or donor state | |E'| << 8
+  float* drop;       // per donor: the mass it hands out (dropped_mass_sharing / its whole mass)
+  uint32_t* head;    // per particle: first donor waiting for it (linked through `next`)
+  uint32_t* next;
+  uint32_t* resume;  // per donor: member of its touch set the blocker scan continues at
+  uint32_t* work[2]; // donors to examine this round / next round
+  uint32_t* ready;   // donors that decide, in the order they became ready (every donor enters once)
+  StepCtl* ctl;
+  uint32_t n;
+  int merging;
+  float dt;
+  uint8_t donor_class;
+};
+
+__device__ __forceinline__ bool mass_ok(float mass_j, float target_j, float add, const PackedParams& P) {
+  const float new_mass_j = mass_j + add;  // particle_sharing.rs:76-86 / particle_merging.rs:79-91
+  return !(new_mass_j >= target_j * 1.1f) && !(new_mass_j > P.mass_base);
 }
 
-// round r, phase A: every live undecided donor stamps itself and its possible receivers
-__global__ void __launch_bounds__(kThreads)
-k_mark(AdaptArgs A, const PackedParams P, int merging, uint32_t round, const uint32_t* __restrict__ work_in, StepCtl* ctl) {
-  const int pin = (round - 1) & 1;
-  const uint32_t nw = ctl->work_n[pin];
-  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->work_n[round & 1] = 0;  // filled by k_decide of this round
-  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += gridDim.x * blockDim.x) {
-    const uint32_t d = work_in[w];
-    if (A.partner[d] != AVAILABLE) continue;  // claimed as a receiver: can never donate (…rs:62-68 / :88-96)
-    const unsigned long long key = stamp_of(round, A.refid[d]);
-    atomicMax(&A.stampkey[d], key);
-    const float2 xd = A.pos[d];
-    const float hd = A.xyhm[d].z, md = A.mass[d];
-    const uint32_t cn = nb_cn(A.L.cnt[d]);
-    const NbCol col(A.L, d);
-    for (uint32_t k = 0; k < cn; k++) {
-      const uint32_t j = col.get(k);
-      if (j == d || A.partner[j] != AVAILABLE) continue;
-      if (static_eligible(A, P, merging != 0, d, j, xd, hd, md)) atomicMax(&A.stampkey[j], key);
-    }
-  }
+struct DonorRegs { uint32_t d, rid; float2 x; float h, m, drop; };
+
+__device__ __forceinline__ DonorRegs donor_regs(const AdaptArgs& A, const PackedParams& P, int merging, float dt, uint32_t d) {
+  DonorRegs D;
+  D.d = d; D.rid = A.refid[d]; D.x = A.pos[d]; D.h = A.xyhm[d].z; D.m = A.mass[d];
+  D.drop = merging ? D.m : dropped_mass_sharing(A.level[d], D.m, dt, P);
+  return D;
 }
 
-// round r, phase B: donors that own all their stamps run the reference's inner loop; the rest wait
-__global__ void __launch_bounds__(kThreads)
-k_decide(AdaptArgs A, const PackedParams P, int merging, uint32_t round, float dt, const uint32_t* __restrict__ work_in,
-         uint32_t* __restrict__ work_out, StepCtl* ctl) {
-  const int pin = (round - 1) & 1;
-  const uint32_t nw = ctl->work_n[pin];
-  if (blockIdx.x == 0 && threadIdx.x == 0 && nw > 0) ctl->rounds = round;
-  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += gridDim.x * blockDim.x) {
-    const uint32_t d = work_in[w];
-    if (A.partner[d] != AVAILABLE) continue;
-    const unsigned long long key = stamp_of(round, A.refid[d]);
-    const float2 xd = A.pos[d];
-    const float hd = A.xyhm[d].z, md = A.mass[d];
-    const uint32_t cn = nb_cn(A.L.cnt[d]);
-    const NbCol col(A.L, d);
-    bool ready = A.stampkey[d] == key;
-    for (uint32_t k = 0; k < cn && ready; k++) {
-      const uint32_t j = col.get(k);
-      if (j == d || A.partner[j] != AVAILABLE) continue;
-      if (static_eligible(A, P, merging != 0, d, j, xd, hd, md) && A.stampkey[j] != key) ready = false;
-    }
-    if (!ready) { work_out[atomicAdd(&ctl->work_n[round & 1], 1u)] = d; continue; }
-    // the reference's inner loop over N(d) in ascending reference index
-    const float dropped = merging ? md : dropped_mass_sharing(A.level[d], md, dt, P);
-    uint32_t count = 0;
-    long long last = -1;
-    for (;;) {
-      uint32_t best_j = 0xFFFFFFFFu;
-      long long best_r = 0x7FFFFFFFFFFFFFFFll;
-      for (uint32_t k = 0; k < cn; k++) {
-        const uint32_t j = col.get(k);
-        const long long r = (long long)A.refid[j];
-        if (r > last && r < best_r) { best_r = r; best_j = j; }
+// The reference's inner loop for donor D (one warp, every lane returns the same count): candidates in ascending
+// reference index, each lane owning the list positions lane, lane + 32, ...  OPT: every receiver counts as available
+// and nothing is written (E'); otherwise the claims are made, and lane c keeps the c-th claimed receiver in `mine`
+// (c < 32; `walk` is called at once for the few beyond).
+template <bool OPT, class Walk>
+__device__ __forceinline__ uint32_t donor_loop(const AdaptArgs& A, const PackedParams& P, int merging, const DonorRegs& D, uint32_t lane,
+                                               uint32_t& mine, Walk walk) {
+  const uint32_t cn = nb_cn(A.L.cnt[D.d]);
+  const NbCol col(A.L, D.d);
+  struct Cand { uint32_t j, rid; float m, tgt; bool ok; };
+  auto cand_at = [&](uint32_t k) {
+    Cand c;
+    c.ok = false; c.j = 0; c.rid = NONE_; c.m = 0.f; c.tgt = 0.f;
+    if (k < cn) {
+      c.j = col.get(k);
+      if (c.j != D.d && static_eligible(A, P, merging != 0, D.d, c.j, D.x, D.h, D.m)) {
+        c.ok = true; c.rid = A.refid[c.j]; c.m = A.mass[c.j]; c.tgt = target_mass(A.level[c.j], P);
       }
-      if (best_j == 0xFFFFFFFFu) break;
-      last = best_r;
-      const uint32_t j = best_j;
-      if (j == d) continue;
-      if (!static_eligible(A, P, merging != 0, d, j, xd, hd, md)) continue;
-      const float new_mass_j = A.mass[j] + dropped / float(count + 1u);
-      const float target_j = target_mass(A.level[j], P);
-      if (new_mass_j >= target_j * 1.1f) continue;
-      if (new_mass_j > P.mass_base) continue;
-      if (A.partner[j] != AVAILABLE) continue;
-      if (count == 0) A.partner[d] = DELETE_;  // partner[d] == AVAILABLE was checked above
-      A.partner[j] = d;
-      count++;
     }
-    A.counter[d] = count;
-    if (count) atomicAdd(&ctl->n_claims, count);
+    return c;
+  };
+  const Cand first = cand_at(lane);  // a column rarely has more than 32 rows: this one stays in registers
+  uint32_t count = 0;
+  long long last = -1;
+  mine = NONE_;
+  for (;;) {
+    Cand best = first;
+    if (!(best.ok && (long long)best.rid > last)) { best.ok = false; best.rid = NONE_; }
+    for (uint32_t k = lane + 32u; k < cn; k += 32u) {
+      const Cand c = cand_at(k);
+      if (c.ok && (long long)c.rid > last && c.rid < best.rid) best = c;
+    }
+    const uint32_t r = __reduce_min_sync(0xffffffffu, best.ok ? best.rid : NONE_);
+    if (r == NONE_) break;
+    last = (long long)r;
+    const int src = __ffs(__ballot_sync(0xffffffffu, best.ok && best.rid == r)) - 1;
+    const uint32_t j = __shfl_sync(0xffffffffu, best.j, src);
+    const float mj = __shfl_sync(0xffffffffu, best.m, src), tj = __shfl_sync(0xffffffffu, best.tgt, src);
+    if (!mass_ok(mj, tj, D.drop / float(count + 1u), P)) continue;
+    if (!OPT) {
+      if (__ldcg(A.partner + j) != AVAILABLE) continue;
+      if (lane == 0) {
+        if (count == 0) A.partner[D.d] = DELETE_;  // the donor itself was available: checked when it was examined
+        A.partner[j] = D.d;
+      }
+      if (count < 32u) { if (lane == count) mine = j; }
+      else walk(j);
+    }
+    count++;
   }
+  return count;
+}
+
+__global__ void __launch_bounds__(kGreedyThreads)
+k_greedy(const GreedyArgs G, const PackedParams P) {
+  cg::grid_group grid = cg::this_grid();
+  const AdaptArgs& A = G.A;
+  StepCtl* ctl = G.ctl;
+  const uint32_t n = G.n, lane = threadIdx.x & 31u;
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  const uint32_t gwarp = gtid >> 5, nwarps = gthreads >> 5;
+  const int merging = G.merging;
+  volatile uint32_t* work_n = ctl->work_n;
+  volatile uint32_t* ready_n = &ctl->ready_n;
+
+  // ---- phase I-a: reset the per-particle state, collect the donors (find_*_partner_sequential resets partner / counter)
+  for (uint32_t i0 = gtid - lane; i0 < n; i0 += gthreads) {
+    const uint32_t i = i0 + lane;
+    bool donor = false;
+    if (i < n) {
+      A.partner[i] = AVAILABLE; A.counter[i] = 0; G.head[i] = NONE_; G.info[i] = 0u; G.resume[i] = 0u;
+      donor = A.size_class[i] == G.donor_class;
+    }
+    const unsigned int mask = __ballot_sync(0xffffffffu, donor);
+    if (mask) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&ctl->work_n[0], uint32_t(__popc(mask)));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (donor) G.work[0][base + uint32_t(__popc(mask & ((1u << lane) - 1u)))] = i;
+    }
+  }
+  grid.sync();
+  // ---- phase I-b: E'(d) of every donor
+  {
+    const uint32_t nw = work_n[0];
+    for (uint32_t w = gwarp; w < nw; w += nwarps) {
+      const uint32_t d = __ldcg(G.work[0] + w);
+      const DonorRegs D = donor_regs(A, P, merging, G.dt, d);
+      uint32_t mine;
+      const uint32_t c = donor_loop<true>(A, P, merging, D, lane, mine, [](uint32_t) {});
+      if (lane == 0) { G.drop[d] = D.drop; G.info[d] = (c ? GI_PENDING : GI_DONE) | (min(c, 0xFFFFFFu) << 8); }
+    }
+  }
+  grid.sync();
+
+  // is x in the touch set of the lower donor y?  (x's own values are passed in: they are warp-uniform in the scan)
+  auto touches = [&](uint32_t y, uint32_t info_y, uint32_t x, float mass_x, float target_x) {
+    if (x == y) return true;
+    const float my = A.mass[y];
+    if (!static_eligible(A, P, merging != 0, y, x, A.pos[y], A.xyhm[y].z, my)) return false;
+    return mass_ok(mass_x, target_x, G.drop[y] / float(info_y >> 8), P);
+  };
+  // wake everything that waits for b: it goes into the next round's work list
+  auto wake = [&](uint32_t b, uint32_t* __restrict__ out, uint32_t slot) {
+    uint32_t z = __ldcg(G.head + b);
+    if (z == NONE_) return;
+    G.head[b] = NONE_;
+    while (z != NONE_) {
+      const uint32_t nz = __ldcg(G.next + z);
+      out[atomicAdd(&ctl->work_n[slot], 1u)] = z;
+      z = nz;
+    }
+  };
+
+  uint32_t ready_begin = 0;
+  uint32_t round = 1;
+  for (;; round++) {
+    const uint32_t pin = (round - 1u) & 1u, pout = round & 1u;
+    const uint32_t nw = work_n[pin];
+    if (nw == 0u) break;
+    if (round > n + 2u) {  // cannot happen (the lowest undecided donor is never blocked); do not hang if it does
+      if (gtid == 0) atomicOr(&ctl->error_flags, ERRF_PARTNER_VALIDATION);
+      break;
+    }
+    if (gtid == 0) { ctl->work_n[pout] = 0u; ctl->rounds = round; }
+    // ---- phase A: examine (the state is frozen: nothing decides in this phase)
+    for (uint32_t w = gwarp; w < nw; w += nwarps) {
+      const uint32_t d = __ldcg(G.work[pin] + w);
+      const uint32_t info_d = __ldcg(G.info + d);
+      if ((info_d & 0xffu) != GI_PENDING) continue;
+      if (__ldcg(A.partner + d) != AVAILABLE) {  // claimed as a receiver meanwhile: can never donate (…rs:62-68 / :88-96)
+        if (lane == 0) G.info[d] = (info_d & ~0xffu) | GI_DONE;
+        continue;
+      }
+      const DonorRegs D = donor_regs(A, P, merging, G.dt, d);
+      const uint32_t res = __ldcg(G.resume + d);
+      const uint32_t cn = nb_cn(A.L.cnt[d]);
+      const NbCol col(A.L, d);
+      uint32_t blocker = NONE_, at = 0;
+      // scan N(x) for a lower undecided, unclaimed donor that touches x
+      auto scan_x = [&](uint32_t x) {
+        const float mass_x = A.mass[x], target_x = target_mass(A.level[x], P);
+        const uint32_t cx = nb_cn(A.L.cnt[x]);
+        const NbCol colx(A.L, x);
+        for (uint32_t k0 = 0; k0 < cx; k0 += 32u) {
+          const uint32_t k = k0 + lane;
+          bool hit = false;
+          uint32_t y = 0;
+          if (k < cx) {
+            y = colx.get(k);
+            const uint32_t iy = __ldcg(G.info + y);
+            hit = (iy & 0xffu) == GI_PENDING && A.refid[y] < D.rid && __ldcg(A.partner + y) == AVAILABLE && touches(y, iy, x, mass_x, target_x);
+          }
+          const unsigned int m = __ballot_sync(0xffffffffu, hit);
+          if (m) return __shfl_sync(0xffffffffu, y, __ffs(m) - 1);
+        }
+        return NONE_;
+      };
+      if (res == 0u) blocker = scan_x(d);  // member 0: the donor itself
+      for (uint32_t k0 = 0; k0 < cn && blocker == NONE_; k0 += 32u) {
+        const uint32_t k = k0 + lane;
+        bool member = false;
+        uint32_t x = 0;
+        if (k < cn && 1u + k >= res) {
+          x = col.get(k);
+          if (x != d && static_eligible(A, P, merging != 0, d, x, D.x, D.h, D.m))
+            member = mass_ok(A.mass[x], target_mass(A.level[x], P), D.drop / float(info_d >> 8), P);
+        }
+        unsigned int m = __ballot_sync(0xffffffffu, member);
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1u;
+          blocker = scan_x(__shfl_sync(0xffffffffu, x, b));
+          if (blocker != NONE_) { at = 1u + k0 + uint32_t(b); break; }
+        }
+      }
+      if (lane == 0) {
+        if (blocker == NONE_) {
+          G.ready[atomicAdd(&ctl->ready_n, 1u)] = d;
+        } else {
+          G.next[d] = atomicExch(G.head + blocker, d);
+          G.resume[d] = at;
+        }
+      }
+    }
+    grid.sync();
+    // ---- phase B: the ready donors decide (their touch sets are disjoint) and wake their waiters
+    const uint32_t ready_end = *ready_n;
+    for (uint32_t w = ready_begin + gwarp; w < ready_end; w += nwarps) {
+      const uint32_t d = __ldcg(G.ready + w);
+      const DonorRegs D = donor_regs(A, P, merging, G.dt, d);
+      uint32_t mine;
+      const uint32_t c = donor_loop<false>(A, P, merging, D, lane, mine, [&](uint32_t j) { if (lane == 0) wake(j, G.work[pout], pout); });
+      if (lane == 0) {
+        A.counter[d] = c;
+        G.info[d] = GI_DONE;
+        if (c) atomicAdd(&ctl->n_claims, c);
+      }
+      const uint32_t c32 = min(c, 32u);
+      uint32_t b = lane < c32 ? mine : NONE_;
+      if (c32 < 32u && lane == c32) b = d;
+      if (b != NONE_) wake(b, G.work[pout], pout);
+      if (c32 == 32u && lane == 0) wake(d, G.work[pout], pout);
+    }
+    ready_begin = ready_end;
+    grid.sync();
+  }
+  if (gtid == 0) ctl->greedy_done = 1;
 }
 
 // validate_share_partners particle_sharing.rs:113-150 / validate_merge_partners particle_merging.rs:230-268
@@ -384,7 +550,6 @@ AdaptArgs args_of(asph_sim* sim) {
   A.L.pool = sim->nbpool.p; A.L.slice_base = sim->slice_base.p; A.L.cnt = sim->cnt.p; A.L.cnt_ext = sim->cnt_ext.p; A.L.far_idx = sim->far_idx.p; A.L.far_cnt = sim->far_cnt.p; A.xyhm = sim->xyhm.p;
   A.pos = sim->pos[c].p; A.vel = sim->vel[c].p; A.mass = sim->mass[c].p; A.level = sim->level[c].p; A.refid = sim->refid[c].p;
   A.size_class = sim->size_class.p; A.partner = sim->merge_partner.p; A.counter = sim->merge_counter.p;
-  A.stampkey = sim->stampkey.p;
   return A;
 }
 
@@ -400,6 +565,12 @@ int total_mass(asph_sim* sim, double* out) {
   return ASPH_OK;
 }
 
+int ensure_greedy_buffers(asph_sim* sim) {
+  CUDA_TRY(sim->g_info.ensure(sim->cap)); CUDA_TRY(sim->g_drop.ensure(sim->cap)); CUDA_TRY(sim->g_head.ensure(sim->cap));
+  CUDA_TRY(sim->g_next.ensure(sim->cap)); CUDA_TRY(sim->g_resume.ensure(sim->cap));
+  return ASPH_OK;
+}
+
 int classify(asph_sim* sim) {
   const uint32_t n = sim->n;
   k_classify<<<(n + kThreads - 1) / kThreads, kThreads, 0, sim->stream>>>(n, sim->level[sim->cur].p, sim->mass[sim->cur].p, sim->pp,
@@ -408,37 +579,45 @@ int classify(asph_sim* sim) {
   return ASPH_OK;
 }
 
-// the greedy partner search in deterministic rounds; returns the number of claimed receivers
+// the greedy partner search (k_greedy); returns the number of claimed receivers
 int find_partners(asph_sim* sim, bool merging, float dt, uint32_t* claims) {
   const uint32_t n = sim->n;
   cudaStream_t st = sim->stream;
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
-  const AdaptArgs A = args_of(sim);
   const uint8_t donor_class = merging ? ASPH_CLASS_TOO_SMALL : ASPH_CLASS_LARGE;
   k_partner_ctl_reset<<<1, 1, 0, st>>>(sim->ctl);
   LAUNCH_CHECK();
-  k_partner_init<<<blocks, kThreads, 0, st>>>(n, A, donor_class, sim->work[0].p, sim->ctl);
-  LAUNCH_CHECK();
-  const int grid = std::max(1, std::min<int>(int(blocks), sim->sm_count * 8));
-  uint32_t round = 1;
-  int batch = 4;
-  for (;;) {
-    for (int b = 0; b < batch; b++, round++) {
-      k_mark<<<grid, kThreads, 0, st>>>(A, sim->pp, merging ? 1 : 0, round, sim->work[(round - 1) & 1].p, sim->ctl);
-      LAUNCH_CHECK();
-      k_decide<<<grid, kThreads, 0, st>>>(A, sim->pp, merging ? 1 : 0, round, dt, sim->work[(round - 1) & 1].p, sim->work[round & 1].p,
-                                          sim->ctl);
-      LAUNCH_CHECK();
-    }
-    TRY(sync_ctl(sim));
-    if (sim->ctl_host->work_n[(round - 1) & 1] == 0) break;
-    if (round > 2u * n + 16u) { sim->last_error = "partner search did not terminate"; return ASPH_ERR_INVALID; }
-    batch = std::min(batch * 2, 64);
+  if (sim->greedy_grid == 0) {  // co-resident blocks of the persistent kernel on this device
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_greedy, kGreedyThreads, 0));
+    sim->greedy_grid = std::max(1, std::min(per_sm, 2) * sim->sm_count);
   }
-  sim->adapt_rounds += sim->ctl_host->rounds;
-  *claims = sim->ctl_host->n_claims;
+  GreedyArgs G;
+  G.A = args_of(sim);
+  G.info = sim->g_info.p; G.drop = sim->g_drop.p; G.head = sim->g_head.p; G.next = sim->g_next.p; G.resume = sim->g_resume.p;
+  G.work[0] = sim->work[0].p; G.work[1] = sim->work[1].p; G.ready = sim->cand.p;
+  G.ctl = sim->ctl; G.n = n; G.merging = merging ? 1 : 0; G.dt = dt; G.donor_class = donor_class;
+  PackedParams pp = sim->pp;
+  const uint32_t grid = uint32_t(std::max(1, std::min<int>(sim->greedy_grid, int((n + kGreedyThreads - 1) / kGreedyThreads))));
+  void* args[] = {&G, &pp};
+  cudaEvent_t kt0 = nullptr, kt1 = nullptr;
+  if (sim->kt_every > 0) { kt0 = kt_event(sim); kt1 = kt_event(sim); cudaEventRecord(kt0, st); }
+  CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_greedy, dim3(grid), dim3(kGreedyThreads), args, 0, st));
+  sim->kernel_launches++;
+  if (kt1) cudaEventRecord(kt1, st);
+  const AdaptArgs A = G.A;
   k_validate<<<blocks, kThreads, 0, st>>>(n, A, donor_class, sim->ctl);
   LAUNCH_CHECK();
+  const int rc_sync = sync_ctl(sim);
+  if (kt1) {
+    float ms = 0.f;
+    if (rc_sync == ASPH_OK && cudaEventElapsedTime(&ms, kt0, kt1) == cudaSuccess) { sim->kt_ms[ASPH_KT_PARTNER_SEARCH] += ms; sim->kt_samples[ASPH_KT_PARTNER_SEARCH]++; }
+    kt_release(sim, kt0); kt_release(sim, kt1);
+  }
+  TRY(rc_sync);
+  if (!sim->ctl_host->greedy_done) { sim->last_error = "partner search did not terminate"; return ASPH_ERR_INVALID; }
+  sim->adapt_rounds += sim->ctl_host->rounds;
+  *claims = sim->ctl_host->n_claims;
   return ASPH_OK;
 }
 
@@ -448,7 +627,7 @@ int launch_adaptivity(asph_sim* sim, float dt) {
   const uint32_t n0 = sim->n;
   if (n0 == 0) return ASPH_OK;
   cudaStream_t st = sim->stream;
-  CUDA_TRY(sim->stampkey.ensure(sim->cap));
+  TRY(ensure_greedy_buffers(sim));
   double m1 = 0, m2 = 0;
   TRY(total_mass(sim, &m1));
   sim->adapt_rounds = 0;
@@ -464,15 +643,17 @@ int launch_adaptivity(asph_sim* sim, float dt) {
     uint32_t claims = 0;
     TRY(find_partners(sim, false, dt, &claims));
     sim->info.n_shared = int(claims);
-    const uint32_t blocks = (sim->n + kThreads - 1) / kThreads;
-    const AdaptArgs A = args_of(sim);
-    k_apply_receivers<<<blocks, kThreads, 0, st>>>(sim->n, A, P, 0, dt);
-    LAUNCH_CHECK();
-    k_share_donors<<<blocks, kThreads, 0, st>>>(sim->n, A, P, dt);
-    LAUNCH_CHECK();
-    if (sim->hdist_valid) {
-      k_hnext_after_transfer<<<blocks, kThreads, 0, st>>>(sim->n, A, P, 0, sim->hnext[sim->cur].p);
+    if (claims) {  // nothing was claimed: no receiver, no donor changes
+      const uint32_t blocks = (sim->n + kThreads - 1) / kThreads;
+      const AdaptArgs A = args_of(sim);
+      k_apply_receivers<<<blocks, kThreads, 0, st>>>(sim->n, A, P, 0, dt);
       LAUNCH_CHECK();
+      k_share_donors<<<blocks, kThreads, 0, st>>>(sim->n, A, P, dt);
+      LAUNCH_CHECK();
+      if (sim->hdist_valid) {
+        k_hnext_after_transfer<<<blocks, kThreads, 0, st>>>(sim->n, A, P, 0, sim->hnext[sim->cur].p);
+        LAUNCH_CHECK();
+      }
     }
   }
   if (sim->step_number % 2 == 0) {
@@ -481,6 +662,13 @@ int launch_adaptivity(asph_sim* sim, float dt) {
       uint32_t claims = 0;
       TRY(find_partners(sim, true, dt, &claims));
       sim->info.n_merged = int(claims);
+      if (claims == 0) {  // no receiver was claimed: no donor is removed, the particle set stays as it is
+        if (track_cls) {
+          k_cls_copy<<<(sim->n + kThreads - 1) / kThreads, kThreads, 0, st>>>(sim->n, sim->size_class.p, sim->cls[sim->cur].p);
+          LAUNCH_CHECK();
+          cls_done = true;
+        }
+      } else {
       const uint32_t n = sim->n;
       const uint32_t blocks = (n + kThreads - 1) / kThreads;
       const AdaptArgs A = args_of(sim);
@@ -519,6 +707,7 @@ int launch_adaptivity(asph_sim* sim, float dt) {
       if (n_new != n) { sim->lists_valid = false; sim->step_fields_valid = false; }
       sim->cur = 1 - c;
       sim->n = n_new; sim->n_owned = n_new;
+      }
     }
   } else if (sim->split_enabled) {  // simulation.rs:2775-2788
     if (sim->max_children < 2) { sim->last_error = "splitting enabled but no split patterns were given"; return ASPH_ERR_INVALID; }
@@ -544,7 +733,7 @@ int launch_adaptivity(asph_sim* sim, float dt) {
       if (n_new <= sim->cap) break;
       // growing re-allocates the scratch arrays (the persistent ones are preserved): count again afterwards
       TRY(ensure_capacity(sim, n_new + n_new / 4 + 1024));
-      CUDA_TRY(sim->stampkey.ensure(sim->cap));
+      TRY(ensure_greedy_buffers(sim));
     }
     if (n_new != n) {
       const int cc = sim->cur;

@@ -37,7 +37,7 @@ int pack_params(asph_sim* sim, const asph_params* p) {
   q.solver = p->pressure_solver_method; q.density_source = p->hybrid_dfsph_density_source_term;
   q.np_before_div = p->hybrid_dfsph_non_pressure_accel_before_divergence_free; q.penalty = p->boundary_penalty_term;
   q.sizing = p->sizing_function; q.opdisc = p->operator_discretization;
-  q.self_last = sim->rows4 ? 1 : 0;
+  q.self_last = 1;
   q.h_mode = p->support_length_estimation;
   q.level_cut = (q.h_mode == ASPH_H_FROM_DISTRIBUTION || q.h_mode == ASPH_H_FROM_DISTRIBUTION2) ? float(p->maximum_range) : 0.f;
   q.boundary_is_fluid_surface = p->boundary_is_fluid_surface;
@@ -52,7 +52,7 @@ int pack_params(asph_sim* sim, const asph_params* p) {
   q.n_poly = 0;
   if (sim->boundary.kind == ASPH_BND_POLYGON) {
     const int np = sim->boundary.n_poly;
-    if (np < 3 || np > ASPH_POLY_DEV) { sim->last_error = "polygon boundary: 3..16 vertices"; return ASPH_ERR_INVALID; }
+    if (np < 3 || np > ASPH_POLY_DEV) { sim->last_error = "polygon boundary: 3..64 vertices"; return ASPH_ERR_INVALID; }
     q.n_poly = np;
     for (int i = 0; i < np; i++) { q.poly_pt[i][0] = sim->boundary.poly[i][0]; q.poly_pt[i][1] = sim->boundary.poly[i][1]; }
     for (int i = 0; i < np; i++) {
@@ -80,32 +80,37 @@ int pack_params(asph_sim* sim, const asph_params* p) {
   };
   if (p->constrain_neighborhood_count) return unsupported("constrain_neighborhood_count");
   if (p->level_estimation_method == ASPH_LEVEL_CENTER_DIFF) return unsupported("level_estimation_method CenterDiff");
-  // Modes whose kernels were written after the GPU budget of the round ran out and have not passed their parity tests
-  // on hardware yet (tests/test_zz_unverified_modes.py) stay off unless the caller asks for them explicitly.
-  const bool unverified = getenv("ASPH_UNVERIFIED_MODES") != nullptr && atoi(getenv("ASPH_UNVERIFIED_MODES")) != 0;
-  if (p->operator_discretization == ASPH_OP_WINCHENBACH2020 && !unverified)
-    return unsupported("operator_discretization Winchenbach2020 (kernels not yet verified on hardware; ASPH_UNVERIFIED_MODES=1 enables them)");
-  if (p->support_length_estimation != ASPH_H_FROM_MASS) {
-    if (!unverified) return unsupported("support_length_estimation != FromMass (kernels not yet verified on hardware; ASPH_UNVERIFIED_MODES=1 enables them)");
-    if (sim->dist) return unsupported("support_length_estimation != FromMass across GPU slabs");
-  }
-  if (p->pressure_solver_method == ASPH_SOLVER_IISPH2) {
-    if (!unverified) return unsupported("pressure_solver_method IISPH2 (kernels not yet verified on hardware; ASPH_UNVERIFIED_MODES=1 enables them)");
-    if (sim->dist) return unsupported("pressure_solver_method IISPH2 across GPU slabs");
-  }
+  // single-GPU only so far: the per-particle state these modes carry from step to step does not migrate between slabs
+  if (p->support_length_estimation != ASPH_H_FROM_MASS && sim->dist) return unsupported("support_length_estimation != FromMass across GPU slabs");
+  if (p->pressure_solver_method == ASPH_SOLVER_IISPH2 && sim->dist) return unsupported("pressure_solver_method IISPH2 across GPU slabs");
   if (p->viscosity_type == ASPH_VISC_XSPH) return unsupported("viscosity_type XSPH (todo!() in the reference)");
   if (p->level_estimation_after_advection) return unsupported("level_estimation_after_advection");
   return ASPH_OK;
 }
 
 // ---- PerformanceCounters (simulation.rs:159-189): CUDA-event intervals per label ----------------------------
-struct PcInterval { int label; cudaEvent_t b, e; bool counts_call; };
+struct PcInterval { int label; cudaEvent_t b, e; bool counts_call; bool ended; };
 struct PcState { std::vector<PcInterval> open; std::vector<cudaEvent_t> pool; };
-PcState& pc_of(asph_sim* sim) {
-  static thread_local std::vector<std::pair<asph_sim*, PcState*>> table;
-  for (auto& kv : table) if (kv.first == sim) return *kv.second;
-  table.push_back({sim, new PcState()});
-  return *table.back().second;
+PcState& pc_of(asph_sim* sim) {  // owned by the handle (asph_sim::pc), freed by asph_destroy
+  if (!sim->pc) sim->pc = new PcState();
+  return *static_cast<PcState*>(sim->pc);
+}
+void pc_destroy(asph_sim* sim) {
+  if (!sim->pc) return;
+  PcState* s = static_cast<PcState*>(sim->pc);
+  for (auto& iv : s->open) { cudaEventDestroy(iv.b); cudaEventDestroy(iv.e); }
+  for (cudaEvent_t e : s->pool) cudaEventDestroy(e);
+  delete s;
+  sim->pc = nullptr;
+}
+// an error return leaves intervals open whose end was never recorded: drop them instead of timing them later
+void pc_discard(asph_sim* sim) {
+  if (!sim->counters || !sim->pc) return;
+  PcState& s = pc_of(sim);
+  cudaStreamSynchronize(sim->stream);
+  for (auto& iv : s.open) { s.pool.push_back(iv.b); s.pool.push_back(iv.e); }
+  s.open.clear();
+  cudaGetLastError();
 }
 cudaEvent_t pc_event(PcState& s) {
   if (!s.pool.empty()) { cudaEvent_t e = s.pool.back(); s.pool.pop_back(); return e; }
@@ -114,7 +119,7 @@ cudaEvent_t pc_event(PcState& s) {
 void pc_begin(asph_sim* sim, int label, bool counts_call = true) {
   if (!sim->counters) return;
   PcState& s = pc_of(sim);
-  PcInterval iv{label, pc_event(s), pc_event(s), counts_call};
+  PcInterval iv{label, pc_event(s), pc_event(s), counts_call, false};
   cudaEventRecord(iv.b, sim->stream);
   s.open.push_back(iv);
 }
@@ -122,7 +127,7 @@ void pc_end(asph_sim* sim, int label) {
   if (!sim->counters) return;
   PcState& s = pc_of(sim);
   for (int k = int(s.open.size()) - 1; k >= 0; k--)
-    if (s.open[k].label == label) { cudaEventRecord(s.open[k].e, sim->stream); return; }
+    if (s.open[k].label == label && !s.open[k].ended) { cudaEventRecord(s.open[k].e, sim->stream); s.open[k].ended = true; return; }
 }
 void pc_collect(asph_sim* sim) {
   if (!sim->counters) return;
@@ -130,7 +135,7 @@ void pc_collect(asph_sim* sim) {
   cudaStreamSynchronize(sim->stream);
   for (auto& iv : s.open) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, iv.b, iv.e) == cudaSuccess) {
+    if (iv.ended && cudaEventElapsedTime(&ms, iv.b, iv.e) == cudaSuccess) {
       sim->pc_ms[iv.label] += ms;
       if (iv.counts_call) sim->pc_calls[iv.label]++;
     }
@@ -354,14 +359,14 @@ static int step_physics(asph_sim* sim, const asph_params* params, float* dt_out)
     pc_begin(sim, ASPH_PC_NEIGHBORHOOD);
     cudaEvent_t kt0 = nullptr, kt1 = nullptr;
     if (sim->kt_every > 0) { kt0 = kt_event(sim); kt1 = kt_event(sim); cudaEventRecord(kt0, sim->stream); }
-    TRY(launch_sort_and_grid(sim, std::max(f_ext, P.f_near)));
+    { const int rc0 = launch_sort_and_grid(sim, std::max(f_ext, P.f_near)); if (rc0 != ASPH_OK) { pc_discard(sim); return rc0; } }
     if (kt1) cudaEventRecord(kt1, sim->stream);
     int rc = ASPH_OK;
     for (int attempt = 0; attempt < 6; attempt++) {
       sim->xv_cur = 0;
       rc = physics_after_sort(sim, lvl, f_ext);
       if (rc != ASPH_RETRY_LISTS) break;
-      TRY(neighbors_grow(sim));
+      { const int rc0 = neighbors_grow(sim); if (rc0 != ASPH_OK) { pc_discard(sim); return rc0; } }
       pc_begin(sim, ASPH_PC_NEIGHBORHOOD, false);
     }
     if (kt1) {
@@ -482,7 +487,6 @@ int asph_create(const asph_params* params, const float* pos, const float* vel, c
   if (cudaMallocHost((void**)&sim->ctl_host, sizeof(StepCtl)) != cudaSuccess) return fail(ASPH_ERR_CUDA);
   memset(sim->ctl_host, 0, sizeof(StepCtl));
   sim->counters = counters_enabled != 0;
-  if (const char* e = getenv("ASPH_ROWS4")) sim->rows4 = atoi(e) != 0;
   if (const char* e = getenv("ASPH_BULK")) sim->bulk = atoi(e) != 0;
   if (boundary) sim->boundary = *boundary; else memset(&sim->boundary, 0, sizeof(sim->boundary));
   {  // λ / λ′ lookup tables (BoundaryWinchenbach2020::new, boundary_winchenbach2020.rs:33-45)
@@ -519,6 +523,7 @@ void asph_destroy(asph_sim* sim) {
   cudaSetDevice(sim->device);
   if (sim->stream) cudaStreamSynchronize(sim->stream);
   dist_destroy(sim);
+  pc_destroy(sim);
   for (int b = 0; b < 2; b++) {
     sim->pos[b].release(); sim->vel[b].release(); sim->mass[b].release(); sim->level[b].release(); sim->refid[b].release();
     sim->xv[b].release(); sim->packP[b].release(); sim->front[b].release(); sim->work[b].release();
@@ -530,7 +535,7 @@ void asph_destroy(asph_sim* sim) {
   sim->omega.release();
   sim->nbpool.release(); sim->hm.release(); sim->hv.release(); sim->size_class.release(); sim->flags.release(); sim->merge_partner.release();
   sim->cand.release(); for (int k = 0; k < 4; k++) sim->scratch_u[k].release();
-  sim->merge_counter.release(); sim->stamp.release(); sim->stampkey.release(); sim->scratch_f.release(); sim->lut.release(); sim->split_pos.release();
+  sim->merge_counter.release(); sim->stamp.release(); sim->g_info.release(); sim->g_head.release(); sim->g_next.release(); sim->g_resume.release(); sim->g_drop.release(); sim->scratch_f.release(); sim->lut.release(); sim->split_pos.release();
   sim->split_off.release(); sim->blockstats.release();
   if (sim->ctl) cudaFree(sim->ctl);
   if (sim->ctl_host) cudaFreeHost(sim->ctl_host);

@@ -98,7 +98,7 @@ struct DistState {
   DevBuf<uint32_t> send_idx, recv_idx;  // sorted particle indices, left part then right part
   DevBuf<uint32_t> slot[2];             // per pre-sort owned particle: position in the send list of that side or kNone
   DevBuf<float4> sendbuf, recvbuf;      // 2 float4 per particle and side
-  DevBuf<uint32_t> words, gather, hist;
+  DevBuf<uint32_t> words, gather, hist, flag_bits;
   uint32_t* gather_host = nullptr;      // pinned: nranks * W_COUNT words, or the histogram
   bool map_valid = false;
   uint64_t halo_calls = 0, halo_bytes = 0;
@@ -550,10 +550,20 @@ int dist_solver_reduce(asph_sim* sim, int slot) {
   return ASPH_OK;
 }
 
+// The error flags are a bit mask and NCCL has no bitwise OR: one word per bit, maximum over the ranks, packed again.
+__global__ void k_flags_expand(const StepCtl* __restrict__ ctl, uint32_t* __restrict__ bits) { bits[threadIdx.x] = (ctl->error_flags >> threadIdx.x) & 1u; }
+__global__ void k_flags_pack(StepCtl* ctl, const uint32_t* __restrict__ bits) {
+  const unsigned int m = __ballot_sync(0xffffffffu, bits[threadIdx.x] != 0u);
+  if (threadIdx.x == 0) ctl->error_flags = m;
+}
 int dist_reduce_flags(asph_sim* sim, bool) {
   DistState* D = sim->dist;
   if (D->nranks == 1) return ASPH_OK;
-  NCCL_TRY(nccl().AllReduce(&sim->ctl->error_flags, &sim->ctl->error_flags, 1, ncclUint32, ncclMax, D->comm, sim->stream));
+  k_flags_expand<<<1, 32, 0, sim->stream>>>(sim->ctl, D->flag_bits.p);
+  LAUNCH_CHECK();
+  NCCL_TRY(nccl().AllReduce(D->flag_bits.p, D->flag_bits.p, 32, ncclUint32, ncclMax, D->comm, sim->stream));
+  k_flags_pack<<<1, 32, 0, sim->stream>>>(sim->ctl, D->flag_bits.p);
+  LAUNCH_CHECK();
   return ASPH_OK;
 }
 
@@ -739,7 +749,7 @@ void dist_destroy(asph_sim* sim) {
   if (!D) return;
   if (D->comm && nccl().CommDestroy) nccl().CommDestroy(D->comm);
   D->send_idx.release(); D->recv_idx.release(); D->slot[0].release(); D->slot[1].release();
-  D->sendbuf.release(); D->recvbuf.release(); D->words.release(); D->gather.release(); D->hist.release();
+  D->sendbuf.release(); D->recvbuf.release(); D->words.release(); D->gather.release(); D->hist.release(); D->flag_bits.release();
   if (D->gather_host) cudaFreeHost(D->gather_host);
   for (int side = 0; side < 2; side++)
     for (int k = 0; k < 3; k++) if (D->peer_field[side][k]) cudaIpcCloseMemHandle(D->peer_field[side][k]);
@@ -790,7 +800,7 @@ int asph_create_distributed(const asph_params* params, const float* pos, const f
   ncclUniqueId id;
   memcpy(&id, nccl_id, 128);
   if (nccl().CommInitRank(&D->comm, n_ranks, id, rank) != ncclSuccess) { D->comm = nullptr; return fail(ASPH_ERR_NCCL); }
-  if (D->words.ensure(W_COUNT) != cudaSuccess || D->gather.ensure(size_t(n_ranks) * W_COUNT) != cudaSuccess ||
+  if (D->words.ensure(W_COUNT) != cudaSuccess || D->flag_bits.ensure(32) != cudaSuccess || D->gather.ensure(size_t(n_ranks) * W_COUNT) != cudaSuccess ||
       D->hist.ensure(kHistBins) != cudaSuccess ||
       cudaMallocHost((void**)&D->gather_host, std::max<size_t>(size_t(n_ranks) * W_COUNT, 16) * sizeof(uint32_t)) != cudaSuccess)
     return fail(ASPH_ERR_CUDA);

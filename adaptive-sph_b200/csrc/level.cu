@@ -5,31 +5,41 @@
 //   K17 smooth_level_estimation_field             simulation.rs:804-857
 //
 // K4 in the reference re-scans all N particles every sweep until nothing changes (O(N * sweeps)).  A particle's
-// value is final in the first sweep in which any neighbour already has one, i.e. in sweep = BFS distance from the
-// detected surface, and it only reads values of the previous sweep.  So here each sweep touches only the front:
-// k_expand claims the unassigned neighbours of the particles assigned in the previous sweep, k_assign computes
-// max_j(φ_j − |x_ij|) for the claimed ones over neighbours stamped in EARLIER sweeps.  max is order independent and
-// the distance is computed without contraction, so the field is bit-identical to the reference's Jacobi sweeps.
+// value is final in the first sweep in which any neighbour already has one, i.e. in sweep t = its BFS distance from
+// the detected surface, and it only reads values of the previous sweep — which, the lists being symmetric, are exactly
+// the values of the particles assigned in sweep t - 1.  So here each sweep touches only that front, and the whole
+// propagation is ONE persistent cooperative kernel (k_propagate): in sweep t every particle j of front(t - 1) pushes
+// φ_j − |x_ij| into its still unassigned neighbours i with an integer atomic (all values are <= 0, so the float maximum is
+// the unsigned minimum of the bit patterns); the first push claims i for front(t).  One grid-wide barrier per sweep, no
+// host round trip, no launch.  max is order independent and the distance is computed without contraction, so the
+// field is bit-identical to the reference's Jacobi sweeps.
 // `level` encoding: value <= 0 = FluidSurface(value); ASPH_LEVEL_INTERIOR (1.0) = FluidInterior.
+#include <cooperative_groups.h>
+
 #include "lists.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kPropThreads = 512;                 // block of the persistent propagation kernel
+constexpr unsigned int kUnassigned = 0xFFFFFFFFu;  // bit pattern of a level value no push has reached yet
 
 typedef NbLists Lists;
 
+// front_n[0] = tail of the one front array (every particle enters it once; the fronts of successive sweeps are
+// consecutive segments); level_live[0] = number of the last sweep that assigned a value above the cutoff
 __global__ void k_level_reset(StepCtl* ctl) {
   ctl->front_n[0] = 0; ctl->front_n[1] = 0; ctl->cand_n[0] = 0; ctl->cand_n[1] = 0;
-  ctl->level_live[0] = 1; ctl->level_live[1] = 0;
+  ctl->level_live[0] = 0; ctl->level_live[1] = 0;
   ctl->level_sweep = 0; ctl->level_done = 0;
 }
 
-__global__ void __launch_bounds__(kThreads)
-k_surface(uint32_t n, Lists L, const float4* __restrict__ xyhm, const float2* __restrict__ nrm, const PackedParams P, float cos_threshold,
-          float* __restrict__ level, int* __restrict__ stamp, uint8_t* __restrict__ flags, uint32_t* __restrict__ front, StepCtl* ctl) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// K3 for particle i; returns whether it is a surface particle
+__device__ __forceinline__ bool surface_of(uint32_t i, const Lists& L, const float4* __restrict__ xyhm, const float2* __restrict__ nrm,
+                                           const PackedParams& P, float cos_threshold, float* __restrict__ level, int* __restrict__ stamp,
+                                           uint8_t* __restrict__ flags) {
   const float4 me = xyhm[i];
   const uint32_t ce = L.cnt_ext[i];
   const float2 nr = nrm[i];
@@ -69,67 +79,89 @@ k_surface(uint32_t n, Lists L, const float4* __restrict__ xyhm, const float2* __
     fl |= 1u;
     level[i] = 0.f;
     stamp[i] = 0;
-    front[atomicAdd(&ctl->front_n[0], 1u)] = i;
   } else {
-    level[i] = ASPH_LEVEL_INTERIOR;
+    level[i] = __uint_as_float(kUnassigned);  // k_propagate turns what no push reaches into ASPH_LEVEL_INTERIOR
     stamp[i] = -1;
   }
   flags[i] = fl;
+  return !interior;
+}
+__global__ void __launch_bounds__(kThreads)
+k_surface(uint32_t n, Lists L, const float4* __restrict__ xyhm, const float2* __restrict__ nrm, const PackedParams P, float cos_threshold,
+          float* __restrict__ level, int* __restrict__ stamp, uint8_t* __restrict__ flags, uint32_t* __restrict__ front, StepCtl* ctl) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool surf = i < n && surface_of(i, L, xyhm, nrm, P, cos_threshold, level, stamp, flags);
+  // front(0): one atomic per warp
+  const unsigned int mask = __ballot_sync(0xffffffffu, surf);
+  if (!mask) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(&ctl->front_n[0], uint32_t(__popc(mask)));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (surf) front[base + uint32_t(__popc(mask & ((1u << lane) - 1u)))] = i;
 }
 
-// sweep t: claim the unassigned neighbours of front[(t-1)&1]
-__global__ void __launch_bounds__(kThreads)
-k_expand(Lists L, int t, const uint32_t* __restrict__ front_in, uint32_t* __restrict__ cand, int* __restrict__ stamp, StepCtl* ctl) {
-  if (ctl->level_done) return;
-  const int pin = (t - 1) & 1;
-  const uint32_t nf = ctl->level_live[pin] ? ctl->front_n[pin] : 0u;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    ctl->front_n[t & 1] = 0;       // filled by k_assign of this sweep
-    ctl->level_live[t & 1] = 0;
-    if (nf == 0) ctl->level_done = 1;
-  }
-  for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
-    const uint32_t j = front_in[f];
-    const uint32_t ce = L.cnt_ext[j];
-    const NbCol col(L, j);
-    for (uint32_t k = 0; k < ce; k++) {
-      const uint32_t i = col.get(k);
-      if (stamp[i] == -1 && atomicCAS(&stamp[i], -1, -2) == -1) cand[atomicAdd(&ctl->cand_n[t & 1], 1u)] = i;
+// K4 (simulation.rs:739-800) as one persistent cooperative kernel.  One warp per front particle j, one lane per
+// neighbour i; sweep t reads front(t - 1) = front[begin, end) and appends front(t) behind it.
+//   stamp[i]: -1 unassigned, otherwise the sweep that assigned i (0 = detected surface)
+// Values other SMs wrote in earlier sweeps (stamp, level, the front entries) are read with ld.global.cg: an L1 line
+// fetched in an earlier sweep may hold their previous contents.
+__global__ void __launch_bounds__(kPropThreads)
+k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restrict__ level, int* __restrict__ stamp,
+            uint32_t* __restrict__ front, StepCtl* ctl, float neg_dmax, int use_cutoff) {
+  cg::grid_group grid = cg::this_grid();
+  unsigned int* level_bits = reinterpret_cast<unsigned int*>(level);
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  volatile uint32_t* tail = &ctl->front_n[0];
+  volatile int* live_sweep = &ctl->level_live[0];
+  uint32_t begin = 0, end = *tail;
+  int sweeps = 0;
+  for (int t = 1; t <= int(n) + 1; t++) {
+    // the sweep runs if the previous one assigned anything (above the cutoff); the reference's last sweep changes nothing
+    if (end == begin || (t > 1 && *live_sweep != t - 1)) break;
+    sweeps = t;
+    bool live = false;
+    for (uint32_t f = begin + gwarp; f < end; f += nwarps) {
+      const uint32_t j = __ldcg(front + f);
+      const float4 me = __ldg(&xyhm[j]);
+      const float lj = __ldcg(level + j);
+      const uint32_t ce = __ldg(&L.cnt_ext[j]);
+      const NbCol col(L, j);
+      for (uint32_t k0 = 0; k0 < ce; k0 += 32u) {
+        const uint32_t k = k0 + lane;
+        bool won = false;
+        uint32_t i = 0;
+        if (k < ce) {
+          i = col.get(k);
+          const int s = __ldcg(stamp + i);
+          if (s == -1 || s == t) {
+            const float4 o = __ldg(&xyhm[i]);
+            const float d = __fsqrt_rn(dist_sq_exact(__fsub_rn(me.x, o.x), __fsub_rn(me.y, o.y)));
+            const float v = __fsub_rn(lj, d);  // <= 0: the largest float is the smallest bit pattern
+            atomicMin(level_bits + i, __float_as_uint(v));
+            if (s == -1) won = atomicCAS(stamp + i, -1, t) == -1;
+            if (!use_cutoff || v > neg_dmax) live = true;
+          }
+        }
+        const unsigned int mask = __ballot_sync(0xffffffffu, won);
+        if (mask) {
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(&ctl->front_n[0], uint32_t(__popc(mask)));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (won) front[base + uint32_t(__popc(mask & ((1u << lane) - 1u)))] = i;
+        }
+      }
     }
+    if (__any_sync(0xffffffffu, live) && lane == 0) *live_sweep = t;
+    grid.sync();
+    begin = end;
+    end = *tail;
   }
-}
-
-// sweep t: φ_i = max over neighbours assigned before sweep t of (φ_j − |x_j − x_i|)   (simulation.rs:757-785)
-__global__ void __launch_bounds__(kThreads)
-k_assign(Lists L, int t, const uint32_t* __restrict__ cand, const float4* __restrict__ xyhm, float* __restrict__ level,
-         int* __restrict__ stamp, uint32_t* __restrict__ front_out, StepCtl* ctl, float neg_dmax, int use_cutoff) {
-  if (ctl->level_done) return;
-  const uint32_t nc = ctl->cand_n[t & 1];
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    ctl->cand_n[(t + 1) & 1] = 0;
-    ctl->level_sweep = t;
-  }
-  bool live = false;
-  for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nc; f += gridDim.x * blockDim.x) {
-    const uint32_t i = cand[f];
-    const float4 me = xyhm[i];
-    const uint32_t ce = L.cnt_ext[i];
-    const NbCol col(L, i);
-    float best = -__int_as_float(0x7f800000);
-    for (uint32_t k = 0; k < ce; k++) {
-      const uint32_t j = col.get(k);
-      const int sj = stamp[j];
-      if (sj < 0 || sj >= t) continue;
-      const float4 o = __ldg(&xyhm[j]);
-      const float d = __fsqrt_rn(dist_sq_exact(__fsub_rn(o.x, me.x), __fsub_rn(o.y, me.y)));
-      best = fmaxf(best, __fsub_rn(level[j], d));
-    }
-    level[i] = best;
-    stamp[i] = t;
-    front_out[atomicAdd(&ctl->front_n[t & 1], 1u)] = i;
-    if (!use_cutoff || best > neg_dmax) live = true;
-  }
-  if (live) ctl->level_live[t & 1] = 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->level_sweep = sweeps; ctl->level_done = 1; }
+  // particles no push has reached stay FluidInterior
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (__ldcg(level_bits + i) == kUnassigned) level[i] = ASPH_LEVEL_INTERIOR;
 }
 
 // K17: φ_i = Σ φ~_j V_j W_ij / Σ V_j W_ij with post-advection positions, pre-advection lists / densities
@@ -176,23 +208,36 @@ int launch_level_estimation(asph_sim* sim) {
   k_surface<<<blocks, kThreads, 0, st>>>(n, L, sim->xyhm.p, sim->nrm.p, sim->pp, cos_threshold, level, sim->stamp.p, sim->flags.p,
                                          sim->front[0].p, sim->ctl);
   LAUNCH_CHECK();
-  const int grid = std::max(1, std::min<int>(int(blocks), sim->sm_count * 8));
-  const int use_cutoff = sim->level_cutoff ? 1 : 0;
-  int t = 1, batch = 8;
-  for (;;) {
-    for (int b = 0; b < batch; b++, t++) {
-      k_expand<<<grid, kThreads, 0, st>>>(L, t, sim->front[(t - 1) & 1].p, sim->cand.p, sim->stamp.p, sim->ctl);
-      LAUNCH_CHECK();
-      k_assign<<<grid, kThreads, 0, st>>>(L, t, sim->cand.p, sim->xyhm.p, level, sim->stamp.p, sim->front[t & 1].p, sim->ctl,
-                                          -sim->pp.maximum_surface_distance, use_cutoff);
-      LAUNCH_CHECK();
-    }
-    TRY(sync_ctl(sim));
-    if (sim->ctl_host->error_flags & ERRF_LIST_CAPACITY) return ASPH_RETRY_LISTS;
-    if (sim->ctl_host->level_done) break;
-    if (t > int(n) + 2) { sim->last_error = "level-set propagation did not terminate"; return ASPH_ERR_INVALID; }
-    batch = std::min(batch * 2, 64);
+  int use_cutoff = sim->level_cutoff ? 1 : 0;
+  float neg_dmax = -sim->pp.maximum_surface_distance;
+  if (sim->prop_grid == 0) {  // co-resident blocks of the persistent kernel on this device
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate, kPropThreads, 0));
+    sim->prop_grid = std::max(1, per_sm * sim->sm_count);
   }
+  // a front rarely holds more than a few ten thousand particles: one warp each
+  uint32_t grid = uint32_t(std::max(1, std::min<int>(sim->prop_grid, int((n + 4u * kPropThreads - 1) / (4u * kPropThreads)))));
+  uint32_t n_arg = n;
+  float* level_arg = level;
+  int* stamp_arg = sim->stamp.p;
+  uint32_t* front_arg = sim->front[0].p;
+  const float4* xyhm_arg = sim->xyhm.p;
+  StepCtl* ctl_arg = sim->ctl;
+  void* args[] = {&n_arg, &L, &xyhm_arg, &level_arg, &stamp_arg, &front_arg, &ctl_arg, &neg_dmax, &use_cutoff};
+  cudaEvent_t kt0 = nullptr, kt1 = nullptr;
+  if (sim->kt_every > 0) { kt0 = kt_event(sim); kt1 = kt_event(sim); cudaEventRecord(kt0, st); }
+  CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_propagate, dim3(grid), dim3(kPropThreads), args, 0, st));
+  sim->kernel_launches++;
+  if (kt1) cudaEventRecord(kt1, st);
+  const int rc_sync = sync_ctl(sim);
+  if (kt1) {
+    float ms = 0.f;
+    if (rc_sync == ASPH_OK && cudaEventElapsedTime(&ms, kt0, kt1) == cudaSuccess) { sim->kt_ms[ASPH_KT_LEVEL_PROPAGATE] += ms; sim->kt_samples[ASPH_KT_LEVEL_PROPAGATE]++; }
+    kt_release(sim, kt0); kt_release(sim, kt1);
+  }
+  TRY(rc_sync);
+  if (sim->ctl_host->error_flags & ERRF_LIST_CAPACITY) return ASPH_RETRY_LISTS;
+  if (!sim->ctl_host->level_done) { sim->last_error = "level-set propagation did not terminate"; return ASPH_ERR_INVALID; }
   // sweeps including the final one that changes nothing, as the reference counts them (simulation.rs:739-799)
   sim->info.level_sweeps = std::max(1, sim->ctl_host->level_sweep);
   return ASPH_OK;

@@ -155,18 +155,25 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
     chunks = max(chunks, __shfl_xor_sync(0xffffffffu, chunks, o));
     ce_max = max(ce_max, __shfl_xor_sync(0xffffffffu, ce_max, o));
   }
-  const uint32_t units = 4u * chunks;  // a chunk = 32 lanes x 16 B = 4 pool units of 64 uint16
+  // a chunk = 32 lanes x 16 B = 4 pool units of 64 uint16.  Every slice owns at least two chunks: the sweep kernels stage
+  // the first two of every warp with one bulk copy each, whatever the column lengths (sweep_kernel.inc).
+  const uint32_t units = 4u * max(chunks, 2u);
   uint32_t base64 = 0;
+  bool fits_pool = true;
   if (lane == 0) {
     base64 = atomicAdd(&ctl->list_used, units);
     atomicMax(&ctl->max_count, ce_max);
     if (ce_max > 20000u) atomicOr(&ctl->error_flags, ERRF_NEIGHBOR_OVERFLOW);  // MAX_NEIGHBOR_COUNT neighborhood_search.rs:3,148-150
-    if (base64 + units > pool_cap64 || base64 + units < base64) atomicOr(&ctl->error_flags, ERRF_LIST_CAPACITY);
-    slice_base[i >> 5] = base64 | (wide ? 0x80000000u : 0u);
+    fits_pool = !(base64 + units > pool_cap64 || base64 + units < base64);
+    if (!fits_pool) atomicOr(&ctl->error_flags, ERRF_LIST_CAPACITY);
+    // a slice that found no room points at the start of the pool (always at least two chunks long): whatever a later pass
+    // of this void attempt reads through it stays in bounds
+    slice_base[i >> 5] = fits_pool ? (base64 | (wide ? 0x80000000u : 0u)) : 0u;
   }
   base64 = __shfl_sync(0xffffffffu, base64, 0);
+  fits_pool = __shfl_sync(0xffffffffu, fits_pool ? 1 : 0, 0) != 0;
   if (!active) return;
-  if (base64 + units > pool_cap64 || base64 + units < base64) { cnt[i] = 0u; cnt_ext[i] = 0u; return; }  // empty column: later passes stay in bounds
+  if (!fits_pool) { cnt[i] = 0u; cnt_ext[i] = 0u; return; }  // empty column: later passes stay in bounds
   cnt[i] = cw | (min(cf, 0x7ffffu) << 12) | ((gid && (gid[i] & ASPH_GHOST_BIT)) ? 0x80000000u : 0u);
   cnt_ext[i] = ce;
 
@@ -338,7 +345,7 @@ int launch_neighbors(asph_sim* sim, float f_ext, float f_near) {
   if (sim->nbpool.cap == 0) {
     // first guess: 24 (2h) / 48 (extended) 16-bit entries per particle
     const size_t per = (f_ext > f_near) ? 48 : 24;
-    CUDA_TRY(sim->nbpool.ensure(size_t(sim->cap) * per + 8192));
+    CUDA_TRY(sim->nbpool.ensure(size_t(sim->cap) * per + 8192));  // never shorter than the two chunks (512 uint16) a void slice points at
   }
   const uint32_t cap64 = uint32_t(std::min<size_t>(sim->nbpool.cap / 64, 0x7FFFFFF0u));
   CUDA_TRY(cudaMemsetAsync(sim->far_cnt.p, 0, (size_t(n + ASPH_PAIR_BLOCK - 1) / ASPH_PAIR_BLOCK) * sizeof(uint32_t), sim->stream));

@@ -17,7 +17,7 @@
 #include "../../include/asph.h"
 
 #define ASPH_MAX_LEVELS 12
-#define ASPH_POLY_DEV 16  // polygon vertices the device code takes (a box has 4)
+#define ASPH_POLY_DEV ASPH_MAX_POLY_VERTS  // polygon vertices the device code takes = what the header allows (a box has 4)
 #define ASPH_RETRY_LISTS 1000  // internal: the neighbour pool was too small; grow it and redo the step from the neighbour pass
 #define ASPH_SLACK 1.00390625f  // 1 + 1/256: cell / search-radius safety factor against fp32 binning error
 
@@ -88,7 +88,7 @@ struct StepCtl {
   // adaptivity
   uint32_t n_new;  // particle count after merge / split
   uint32_t n_shared, n_merged, n_split_parents;
-  uint32_t work_n[2], rounds, n_claims;
+  uint32_t work_n[2], rounds, n_claims, ready_n, greedy_done;
   double mass_before, mass_after;
 };
 
@@ -112,8 +112,8 @@ struct PackedParams {  // SimulationParams rounded once to fp32 (what serde does
   // detector ignores neighbours beyond particle_radius * maximum_range, simulation.rs:698-723), 0 = no cut
   int h_mode;
   float level_cut;
-  // experiment (ASPH_ROWS4=1): the neighbour pass writes a particle's own W row LAST, so that the sweep kernels can stop
-  // one row early and in steps of 4 rows instead of 8 (solver.cu, R4)
+  // the neighbour pass writes a particle's own W row LAST, so that the sweep kernels can stop one row early and in steps
+  // of 4 rows instead of 8 (solver.cu, R4); always 1 (kept as a parameter of the list layout, tests/test_list_layout.py)
   int self_last;
 };
 
@@ -206,7 +206,9 @@ struct asph_sim {
   DevBuf<uint32_t> merge_partner, front[2], cand, work[2], scratch_u[4];
   DevBuf<uint32_t> merge_counter;
   DevBuf<int> stamp;
-  DevBuf<unsigned long long> stampkey;  // partner search: round:~refid stamps
+  // partner search (adapt.cu, k_greedy): donor state | |E'| << 8, offered mass, wait lists (head / next), scan resume point
+  DevBuf<uint32_t> g_info, g_head, g_next, g_resume;
+  DevBuf<float> g_drop;
   uint64_t adapt_rounds = 0;
   DevBuf<float> scratch_f;
   DevBuf<float> lut;         // 2 * 10001 floats: λ then λ′
@@ -233,11 +235,11 @@ struct asph_sim {
   bool counters = false;
   double pc_ms[ASPH_PC_COUNT] = {0};
   uint64_t pc_calls[ASPH_PC_COUNT] = {0};
-  cudaEvent_t ev_begin[ASPH_PC_COUNT], ev_end[ASPH_PC_COUNT];
+  void* pc = nullptr;  // PerformanceCounters state (capi.cu: open intervals + event pool)
   int sm_count = 148;
-  bool bulk = false;   // ASPH_BULK=1 at asph_create: bulk-copy stage fill of the sweep kernels (experiment, solver.cu; not the default)
-  bool rows4 = false;  // ASPH_ROWS4=1 at asph_create: self row last + 4-row granularity in the sweep kernels (not the default yet)
+  bool bulk = true;    // bulk-copy (cp.async.bulk + mbarrier) stage fill of the single-GPU sweep kernels; ASPH_BULK=0 at asph_create: per-thread copies
   bool sweep_attr_done = false;  // dynamic shared-memory limit of the sweep kernels raised on this handle's device
+  int prop_grid = 0, greedy_grid = 0;  // co-resident blocks of the persistent cooperative kernels (level.cu, adapt.cu) on this device
   bool ctl_seen = false;  // ctl_host holds a control block read back from the device (possibly of the previous step)
   std::string last_error;
   uint64_t kernel_launches = 0;

@@ -671,44 +671,29 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
   const bool w2020 = op_w2020(sim);  // its update pass always gathers {h, m / rho}
   const bool hmwin = w2020 || !(sim->ctl_seen && sim->ctl_host->hmin == sim->ctl_host->hmax);
   const size_t smem = 2 * (hmwin ? sizeof(SweepStage<true>) : sizeof(SweepStage<false>));
-  // blocks per SM as in the kernels' launch bounds: 3 with the {h, m} window or the peer-memory exchange — except that the
-  // experimental 4-row peer kernels (ASPH_ROWS4) fit 64 registers without spills and run at 4
-  const bool r4_early = sim->rows4 && !w2020;
-  uint32_t grid = sweep_grid(n, sim->sm_count, (hmwin || (dist_p2p(sim) && !r4_early)) ? 3 : 4);
+  // blocks per SM as in the kernels' launch bounds: 3 with the {h, m} window, else 4
+  uint32_t grid = sweep_grid(n, sim->sm_count, hmwin ? 3 : 4);
   if (const char* e = getenv("ASPH_SWEEP_GRID")) grid = std::max(1u, std::min(grid, uint32_t(atoi(e))));  // test hook: few blocks => many tiles per block
   if (!sim->sweep_attr_done) {  // per handle: function attributes belong to the device the handle lives on
     const int big = int(2 * sizeof(SweepStage<true>)), small = int(2 * sizeof(SweepStage<false>));
-    CUDA_TRY(cudaFuncSetAttribute(k_sweep<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_TRY(cudaFuncSetAttribute(k_sweep<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
-    CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
-    CUDA_TRY(cudaFuncSetAttribute(k_sweep<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_TRY(cudaFuncSetAttribute(k_sweep<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
-    CUDA_TRY(cudaFuncSetAttribute(k_sweep<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
-    CUDA_TRY((cudaFuncSetAttribute(k_sweep<0, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
-    CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
-    CUDA_TRY((cudaFuncSetAttribute(k_sweep<0, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small)));
-    CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small)));
-    CUDA_TRY((cudaFuncSetAttribute(k_sweep<0, true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
-    CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
-    CUDA_TRY((cudaFuncSetAttribute(k_sweep<0, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small)));
-    CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small)));
-    CUDA_TRY((cudaFuncSetAttribute(k_sweep_bulk<0, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big + 16)));
-    CUDA_TRY((cudaFuncSetAttribute(k_sweep_bulk<1, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big + 16)));
-    CUDA_TRY((cudaFuncSetAttribute(k_sweep_bulk<0, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small + 16)));
-    CUDA_TRY((cudaFuncSetAttribute(k_sweep_bulk<1, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small + 16)));
-    CUDA_TRY((cudaFuncSetAttribute(k_sweep_bulk<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big + 16)));
-    CUDA_TRY((cudaFuncSetAttribute(k_sweep_bulk<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big + 16)));
-    CUDA_TRY((cudaFuncSetAttribute(k_sweep_bulk<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small + 16)));
-    CUDA_TRY((cudaFuncSetAttribute(k_sweep_bulk<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small + 16)));
-    CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
-    CUDA_TRY((cudaFuncSetAttribute(k_sweep<1, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
+#define SWEEP_ATTR(K, BYTES) CUDA_TRY((cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES)))
+    // the 4-row kernels of the default operators: single GPU (bulk-copy stage fill, or per-thread copies) and peer memory
+    SWEEP_ATTR((k_sweep_bulk<0, true, false, false, true>), big + 16); SWEEP_ATTR((k_sweep_bulk<1, true, false, false, true>), big + 16);
+    SWEEP_ATTR((k_sweep_bulk<0, false, false, false, true>), small + 16); SWEEP_ATTR((k_sweep_bulk<1, false, false, false, true>), small + 16);
+    SWEEP_ATTR((k_sweep<0, true, false, false, true>), big); SWEEP_ATTR((k_sweep<1, true, false, false, true>), big);
+    SWEEP_ATTR((k_sweep<0, false, false, false, true>), small); SWEEP_ATTR((k_sweep<1, false, false, false, true>), small);
+    SWEEP_ATTR((k_sweep<0, true, true, false, true>), big); SWEEP_ATTR((k_sweep<1, true, true, false, true>), big);
+    SWEEP_ATTR((k_sweep<0, false, true, false, true>), small); SWEEP_ATTR((k_sweep<1, false, true, false, true>), small);
+    // Winchenbach2020 operator: 8-row kernels with the {h, m / rho} window
+    SWEEP_ATTR((k_sweep<0, true, false>), big); SWEEP_ATTR((k_sweep<0, true, true>), big);
+    SWEEP_ATTR((k_sweep<1, true, false, true>), big); SWEEP_ATTR((k_sweep<1, true, true, true>), big);
+#undef SWEEP_ATTR
     sim->sweep_attr_done = true;
   }
   const bool p2p = dist_p2p(sim);
-  const bool r4 = sim->rows4 && !w2020;  // the lists were written self-last (pack_params: self_last)
-  const bool bulk = sim->bulk && !p2p && !w2020;  // experiment ASPH_BULK=1: bulk-copy stage fill (single GPU, default operators; with or without ASPH_ROWS4)
+  // Single GPU, default operators: the stage fill of interior tiles by bulk copies (k_sweep_bulk); ASPH_BULK=0 keeps the
+  // per-thread copies (the kernels the multi-GPU NCCL path uses as well) for A/B runs.
+  const bool bulk = sim->bulk && !sim->dist && !w2020;
   SweepArgs A;
   A.n = n; A.L = L; A.P0 = sim->packP[0].p; A.P1 = sim->packP[1].p; A.P0w = sim->packP[0].p; A.P1w = sim->packP[1].p;
   A.packA = sim->packA.p; A.hm = sim->hm.p; A.gB = sim->gB.p; A.pconst = sim->pconst.p; A.rho = sim->rho.p; A.ctl = sim->ctl; A.gid = gid;
@@ -725,12 +710,10 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
       if (launched > 0) {  // sweep 0: a^p = 0 was written by k_source
         A.hm = sim->hm.p;
         A.peer = dist_peer_args(sim, true, !p2p, 0, false);  // waits for the previous sweep's p' ghosts; publishes a^p
-        if (bulk && r4) { if (hmwin) k_sweep_bulk<0, true, false, false, true><<<grid, kThreads, smem + 16, st>>>(A); else k_sweep_bulk<0, false, false, false, true><<<grid, kThreads, smem + 16, st>>>(A); }
-        else if (bulk) { if (hmwin) k_sweep_bulk<0, true, false><<<grid, kThreads, smem + 16, st>>>(A); else k_sweep_bulk<0, false, false><<<grid, kThreads, smem + 16, st>>>(A); }
-        else if (r4 && p2p) { if (hmwin) k_sweep<0, true, true, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, true, false, true><<<grid, kThreads, smem, st>>>(A); }
-        else if (r4) { if (hmwin) k_sweep<0, true, false, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, false, false, true><<<grid, kThreads, smem, st>>>(A); }
-        else if (p2p) { if (hmwin) k_sweep<0, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, true><<<grid, kThreads, smem, st>>>(A); }
-        else { if (hmwin) k_sweep<0, true, false><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, false><<<grid, kThreads, smem, st>>>(A); }
+        if (w2020) { if (p2p) k_sweep<0, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, true, false><<<grid, kThreads, smem, st>>>(A); }
+        else if (bulk) { if (hmwin) k_sweep_bulk<0, true, false, false, true><<<grid, kThreads, smem + 16, st>>>(A); else k_sweep_bulk<0, false, false, false, true><<<grid, kThreads, smem + 16, st>>>(A); }
+        else if (p2p) { if (hmwin) k_sweep<0, true, true, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, true, false, true><<<grid, kThreads, smem, st>>>(A); }
+        else { if (hmwin) k_sweep<0, true, false, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<0, false, false, false, true><<<grid, kThreads, smem, st>>>(A); }
         LAUNCH_CHECK();
         if (time_it) cudaEventRecord(tm.e1, st);
         if (!p2p && sim->dist) TRY(dist_halo(sim, sim->packA.p, 16));
@@ -740,13 +723,10 @@ int launch_solver(asph_sim* sim, bool density_mode, float max_avg_error, int* it
       if (time_it) cudaEventRecord(tm.e1b, st);
       A.hm = w2020 ? sim->hv.p : sim->hm.p;
       A.peer = dist_peer_args(sim, launched > 0, p2p && launched > 0, 1 + ((launched + 1) & 1), true);  // waits for the a^p ghosts and the previous sweep's totals; publishes p' and its own
-      if (bulk && r4) { if (hmwin) k_sweep_bulk<1, true, false, false, true><<<grid, kThreads, smem + 16, st>>>(A); else k_sweep_bulk<1, false, false, false, true><<<grid, kThreads, smem + 16, st>>>(A); }
-      else if (bulk) { if (hmwin) k_sweep_bulk<1, true, false><<<grid, kThreads, smem + 16, st>>>(A); else k_sweep_bulk<1, false, false><<<grid, kThreads, smem + 16, st>>>(A); }
-      else if (r4 && p2p) { if (hmwin) k_sweep<1, true, true, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, true, false, true><<<grid, kThreads, smem, st>>>(A); }
-      else if (r4) { if (hmwin) k_sweep<1, true, false, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, false, false, true><<<grid, kThreads, smem, st>>>(A); }
-      else if (w2020) { if (p2p) k_sweep<1, true, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, true, false, true><<<grid, kThreads, smem, st>>>(A); }
-      else if (p2p) { if (hmwin) k_sweep<1, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, true><<<grid, kThreads, smem, st>>>(A); }
-      else { if (hmwin) k_sweep<1, true, false><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, false><<<grid, kThreads, smem, st>>>(A); }
+      if (w2020) { if (p2p) k_sweep<1, true, true, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, true, false, true><<<grid, kThreads, smem, st>>>(A); }
+      else if (bulk) { if (hmwin) k_sweep_bulk<1, true, false, false, true><<<grid, kThreads, smem + 16, st>>>(A); else k_sweep_bulk<1, false, false, false, true><<<grid, kThreads, smem + 16, st>>>(A); }
+      else if (p2p) { if (hmwin) k_sweep<1, true, true, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, true, false, true><<<grid, kThreads, smem, st>>>(A); }
+      else { if (hmwin) k_sweep<1, true, false, false, true><<<grid, kThreads, smem, st>>>(A); else k_sweep<1, false, false, false, true><<<grid, kThreads, smem, st>>>(A); }
       LAUNCH_CHECK();
       if (time_it) { cudaEventRecord(tm.e2, st); timed.push_back(tm); }
       if (!p2p && sim->dist) {

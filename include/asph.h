@@ -223,9 +223,22 @@ uint64_t asph_kernel_launches(const asph_sim* sim);
  * CUDA-event durations, on the handle's own stream, of sampled launches of the hot kernels, accumulated since
  * asph_set_kernel_timing was last called.  sample_every = 0 switches it off; k > 0 times every k-th Jacobi sweep
  * (its pressure-acceleration pass and its update pass separately) and every neighbour build. */
-enum { ASPH_KT_ACCEL_SWEEP = 0, ASPH_KT_JACOBI_SWEEP = 1, ASPH_KT_NEIGHBORS = 2, ASPH_KT_SORT_GRID = 3, ASPH_KT_COUNT = 4 };
+enum { ASPH_KT_ACCEL_SWEEP = 0, ASPH_KT_JACOBI_SWEEP = 1, ASPH_KT_NEIGHBORS = 2, ASPH_KT_SORT_GRID = 3,
+       ASPH_KT_LEVEL_PROPAGATE = 4,  /* the persistent level-set propagation kernel (one launch per step) */
+       ASPH_KT_PARTNER_SEARCH = 5,   /* the persistent greedy partner-search kernel (one launch per share / merge phase) */
+       ASPH_KT_COUNT = 6 };
 int asph_set_kernel_timing(asph_sim* sim, int sample_every);
 int asph_get_kernel_timing(asph_sim* sim, double ms_sum[ASPH_KT_COUNT], uint64_t samples[ASPH_KT_COUNT]);
+
+/* ------------------------------------------------------------------ diagnostics (parity tests, restart files)
+ * asph_set_level: prescribe the level field (reference particle order; value <= 0 = FluidSurface(value),
+ * ASPH_LEVEL_INTERIOR = FluidInterior) so that single_step_adaptivity (simulation.rs:2732) can be driven on its own;
+ * asph_set_step_number: the step counter that decides merge (even) / split (odd) steps (simulation.rs:2725, 2760);
+ * asph_adapt_rounds: dependency rounds the greedy partner searches of the last resampling phase took (0 on the CPU
+ * oracle, whose searches are the reference's serial loops). */
+int asph_set_level(asph_sim* sim, const float* level_ref_order, uint64_t n);
+void asph_set_step_number(asph_sim* sim, uint64_t step_number);
+uint64_t asph_adapt_rounds(const asph_sim* sim);
 
 /* ------------------------------------------------------------------ pure helpers (host side, no GPU needed)
  * sph_kernels.rs:49-71 (cubic spline, h = smoothing length, support 2h) and

@@ -1333,10 +1333,13 @@ template <class FT> struct Sim {
     }
     return true;
   }
-  FT total_mass() const {  // iter().sum() in index order
-    FT s = 0;
-    for (FT m : mass) s += m;
-    return s;
+  // The reference sums with iter().sum() in FT (sim.rs:2745, 2791).  Its f32 running sum drifts by a fraction of an ulp
+  // per addend and trips the 0.005 tolerance by itself near a million equal particles (before vs after a merge step the
+  // addends differ), which says nothing about conservation; the check is kept, the sum is accumulated in double.
+  FT total_mass() const {
+    double s = 0;
+    for (FT m : mass) s += double(m);
+    return FT(s);
   }
   bool step_adaptivity(const Params<FT>& P, FT dt, StepError& err) {  // sim.rs:2732-2796
     pc.begin(ASPH_PC_SIMULATION_STEP);

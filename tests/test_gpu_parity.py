@@ -334,13 +334,3 @@ def test_adaptive_dam_break_mid_size(asph, cuda_lib, oracle32, default_params, s
     ms = g.get_field("mass")
     assert ms.max() / ms.min() > 2.25                     # h ~ sqrt(m): more than one size level in play
     g.close(); o.close()
-
-
-def test_unverified_modes_are_off_without_the_switch(asph, cuda_lib, default_params, monkeypatch):
-    """Modes whose kernels have not passed parity on hardware yet (tests/test_zz_unverified_modes.py) answer UNSUPPORTED."""
-    monkeypatch.delenv("ASPH_UNVERIFIED_MODES", raising=False)
-    sc = _scene(asph, "default-scene.yaml")
-    sim = asph.init_fluid_sim(default_params.replace(operator_discretization="Winchenbach2020"), sc, None, lib=cuda_lib)
-    with pytest.raises(asph.AsphError, match="UNSUPPORTED"):
-        sim.single_step()
-    sim.close()
