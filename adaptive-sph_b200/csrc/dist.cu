@@ -106,8 +106,8 @@ struct DistState {
   bool p2p = false;
   PeerCtl* my_ctl = nullptr;                      // device memory of this rank
   PeerCtl* peer_ctl[ASPH_MAX_RANKS] = {nullptr};  // every rank's PeerCtl mapped here ([rank] = my_ctl)
-  void* mapped_src[2][3] = {{nullptr}};           // the neighbour's own pointers of packA / packP[0] / packP[1] last mapped ([0] = rank - 1)
-  float4* peer_field[2][3] = {{nullptr}};         // ... and where they are mapped in this process
+  void* mapped_src[2][4] = {{nullptr}};           // the neighbour's own pointers of packA / packP[0] / packP[1] / mailboxes last mapped ([0] = rank - 1)
+  float4* peer_field[2][4] = {{nullptr}};         // ... and where they are mapped in this process
   DevBuf<uint32_t> remote_slot;                   // ghost slot on the neighbour of my k-th send-list entry (left part, right part)
   DevBuf<uint32_t> rslot[2], blocks_done;         // the same per local particle (~0: not a border particle); pass-completion counter
   DevBuf<unsigned char> tile_border;
@@ -117,6 +117,12 @@ struct DistState {
   DevBuf<unsigned long long> peer_ctl_dev;        // peer_ctl[] for k_stats_push
   bool peer_ctl_ready = false;
   unsigned int halo_seq = 0, stats_seq = 0;       // pushes launched so far
+  // persistent cooperative kernels (CoopPeer, sim.cuh)
+  DevBuf<uint2> mbox;                             // this rank's mailboxes: 2 parities x 2 sides x cap_h messages
+  uint32_t mbox_cap = 0;
+  DevBuf<uint32_t> owner_slot, owner_tmp;         // per local particle: a ghost's index on its owner rank (~0 otherwise)
+  DevBuf<unsigned int> verdict;
+  unsigned int coop_seq = 0;                      // cross-GPU barriers run so far (the same on every rank)
 };
 
 namespace {
@@ -570,10 +576,11 @@ int dist_reduce_flags(asph_sim* sim, bool) {
 // ---- peer-memory path --------------------------------------------------------------------------------------------
 namespace {
 
+constexpr int kPeerFields = 4;
 struct P2PRecord {  // what every rank tells the others once per step
-  void* ptr[3];                 // its packA, packP[0], packP[1]
-  void* ctl;                    // its PeerCtl
-  cudaIpcMemHandle_t h[3], hc;  // and their IPC handles
+  void* ptr[kPeerFields];                 // its packA, packP[0], packP[1], mailboxes
+  void* ctl;                              // its PeerCtl
+  cudaIpcMemHandle_t h[kPeerFields], hc;  // and their IPC handles
 };
 
 // tiles in processing order: the ones with border particles first (one block; a few thousand tiles)
@@ -609,6 +616,11 @@ __global__ void k_build_rslot(uint32_t ns0, uint32_t ns1, const uint32_t* __rest
   tile_border[i / ASPH_PAIR_BLOCK] = 1;
 }
 
+__global__ void k_scatter_words(uint32_t count, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ src, uint32_t* __restrict__ dst) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < count) dst[idx[k]] = src[k];
+}
+
 }  // namespace
 
 bool dist_p2p(asph_sim* sim) { return sim->dist && sim->dist->p2p && sim->dist->nranks > 1; }
@@ -623,8 +635,12 @@ static int p2p_refresh(asph_sim* sim) {
   cudaStream_t st = sim->stream;
   P2PRecord mine;
   memset(&mine, 0, sizeof mine);
-  mine.ptr[0] = sim->packA.p; mine.ptr[1] = sim->packP[0].p; mine.ptr[2] = sim->packP[1].p; mine.ctl = D->my_ctl;
-  for (int k = 0; k < 3; k++) CUDA_TRY(cudaIpcGetMemHandle(&mine.h[k], mine.ptr[k]));
+  if (D->mbox_cap != D->cap_h || !D->mbox.p) {  // cap_h is the same on every rank (ensure_halo_capacity decisions are global)
+    CUDA_TRY(D->mbox.ensure(size_t(4) * D->cap_h));
+    D->mbox_cap = D->cap_h;
+  }
+  mine.ptr[0] = sim->packA.p; mine.ptr[1] = sim->packP[0].p; mine.ptr[2] = sim->packP[1].p; mine.ptr[3] = D->mbox.p; mine.ctl = D->my_ctl;
+  for (int k = 0; k < kPeerFields; k++) CUDA_TRY(cudaIpcGetMemHandle(&mine.h[k], mine.ptr[k]));
   CUDA_TRY(cudaIpcGetMemHandle(&mine.hc, D->my_ctl));
   CUDA_TRY(cudaMemcpyAsync(D->rec_dev.p, &mine, sizeof mine, cudaMemcpyHostToDevice, st));
   NCCL_TRY(nccl().AllGather(D->rec_dev.p, D->rec_dev.p + sizeof(P2PRecord), sizeof(P2PRecord), ncclUint8, D->comm, st));
@@ -643,7 +659,7 @@ static int p2p_refresh(asph_sim* sim) {
   for (int side = 0; side < 2; side++) {
     const int q = side ? r + 1 : r - 1;
     if (q < 0 || q >= R) continue;
-    for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < kPeerFields; k++) {
       if (D->mapped_src[side][k] == all[q].ptr[k] && D->peer_field[side][k]) continue;
       if (D->peer_field[side][k]) { cudaIpcCloseMemHandle(D->peer_field[side][k]); D->peer_field[side][k] = nullptr; }
       void* p = nullptr;
@@ -672,6 +688,24 @@ static int p2p_refresh(asph_sim* sim) {
     if (D->n_send[0]) NCCL_TRY(N.Recv(D->remote_slot.p, D->n_send[0], ncclUint32, r - 1, D->comm, st));
     if (D->n_send[1]) NCCL_TRY(N.Recv(D->remote_slot.p + D->n_send[0], D->n_send[1], ncclUint32, r + 1, D->comm, st));
     NCCL_TRY(N.GroupEnd());
+  }
+  // ... and the other way round: the k-th ghost I received is particle send_idx[k] on its owner
+  const uint32_t nr = D->n_recv[0] + D->n_recv[1];
+  CUDA_TRY(D->owner_tmp.ensure(std::max<size_t>(size_t(D->cap_h) * 2, nr)));
+  CUDA_TRY(D->owner_slot.ensure(sim->cap));
+  if (ns | nr) {
+    const Nccl& N = nccl();
+    NCCL_TRY(N.GroupStart());
+    if (D->n_send[0]) NCCL_TRY(N.Send(D->send_idx.p, D->n_send[0], ncclUint32, r - 1, D->comm, st));
+    if (D->n_send[1]) NCCL_TRY(N.Send(D->send_idx.p + D->n_send[0], D->n_send[1], ncclUint32, r + 1, D->comm, st));
+    if (D->n_recv[0]) NCCL_TRY(N.Recv(D->owner_tmp.p, D->n_recv[0], ncclUint32, r - 1, D->comm, st));
+    if (D->n_recv[1]) NCCL_TRY(N.Recv(D->owner_tmp.p + D->n_recv[0], D->n_recv[1], ncclUint32, r + 1, D->comm, st));
+    NCCL_TRY(N.GroupEnd());
+  }
+  CUDA_TRY(cudaMemsetAsync(D->owner_slot.p, 0xFF, size_t(sim->n) * sizeof(uint32_t), st));
+  if (nr) {
+    k_scatter_words<<<(nr + kThreads - 1) / kThreads, kThreads, 0, st>>>(nr, D->recv_idx.p, D->owner_tmp.p, D->owner_slot.p);
+    LAUNCH_CHECK();
   }
   const size_t tiles = (size_t(sim->cap) + ASPH_PAIR_BLOCK - 1) / ASPH_PAIR_BLOCK + 1;
   CUDA_TRY(D->rslot[0].ensure(sim->cap)); CUDA_TRY(D->rslot[1].ensure(sim->cap)); CUDA_TRY(D->tile_border.ensure(tiles));
@@ -724,6 +758,34 @@ PeerArgs dist_peer_args(asph_sim* sim, bool wait_halo, bool wait_stats, int fiel
   return a;
 }
 
+CoopPeer dist_coop_peer(asph_sim* sim) {
+  CoopPeer c;
+  memset(&c, 0, sizeof c);
+  c.nranks = 1;
+  if (!dist_p2p(sim)) return c;
+  DistState* D = sim->dist;
+  c.self = D->my_ctl; c.all_ctl = reinterpret_cast<PeerCtl* const*>(D->peer_ctl_dev.p);
+  c.rank = D->rank; c.nranks = D->nranks; c.seq0 = D->coop_seq;
+  c.mbox = D->mbox.p; c.mbox_cap = D->mbox_cap;
+  for (int side = 0; side < 2; side++) {
+    const int q = side ? D->rank + 1 : D->rank - 1;
+    const bool has = q >= 0 && q < D->nranks;
+    c.nb_ctl[side] = has ? D->peer_ctl[q] : nullptr;
+    c.nb_mbox[side] = has ? reinterpret_cast<uint2*>(D->peer_field[side][3]) : nullptr;
+    c.rslot[side] = D->rslot[side].p;
+  }
+  c.owner_slot = D->owner_slot.p;
+  c.verdict = D->verdict.p;
+  return c;
+}
+void dist_coop_advance(asph_sim* sim, unsigned int barriers) { if (sim->dist) sim->dist->coop_seq += barriers; }
+int dist_halo_words(asph_sim* sim, void* field) { return halo_impl(sim, field, field, nullptr, 4); }
+const uint32_t* dist_ghost_index(asph_sim* sim, uint32_t* count) {
+  DistState* D = sim->dist;
+  *count = D ? D->n_recv[0] + D->n_recv[1] : 0u;
+  return D ? D->recv_idx.p : nullptr;
+}
+
 int dist_local_map(asph_sim* sim) {
   DistState* D = sim->dist;
   if (D->map_valid) return ASPH_OK;
@@ -752,11 +814,11 @@ void dist_destroy(asph_sim* sim) {
   D->sendbuf.release(); D->recvbuf.release(); D->words.release(); D->gather.release(); D->hist.release(); D->flag_bits.release();
   if (D->gather_host) cudaFreeHost(D->gather_host);
   for (int side = 0; side < 2; side++)
-    for (int k = 0; k < 3; k++) if (D->peer_field[side][k]) cudaIpcCloseMemHandle(D->peer_field[side][k]);
+    for (int k = 0; k < 4; k++) if (D->peer_field[side][k]) cudaIpcCloseMemHandle(D->peer_field[side][k]);
   for (int q = 0; q < D->nranks && q < ASPH_MAX_RANKS; q++) if (q != D->rank && D->peer_ctl[q]) cudaIpcCloseMemHandle(D->peer_ctl[q]);
   if (D->my_ctl) cudaFree(D->my_ctl);
   if (D->rec_host) cudaFreeHost(D->rec_host);
-  D->remote_slot.release(); D->rec_dev.release(); D->peer_ctl_dev.release(); D->rslot[0].release(); D->rslot[1].release(); D->blocks_done.release(); D->tile_border.release();
+  D->mbox.release(); D->owner_slot.release(); D->owner_tmp.release(); D->verdict.release(); D->remote_slot.release(); D->rec_dev.release(); D->peer_ctl_dev.release(); D->rslot[0].release(); D->rslot[1].release(); D->blocks_done.release(); D->tile_border.release();
   delete D;
   sim->dist = nullptr;
 }
@@ -812,7 +874,7 @@ int asph_create_distributed(const asph_params* params, const float* pos, const f
     if (D->p2p) {
       if (cudaMalloc((void**)&D->my_ctl, sizeof(PeerCtl)) != cudaSuccess || cudaMemset(D->my_ctl, 0, sizeof(PeerCtl)) != cudaSuccess ||
           D->rec_dev.ensure(size_t(n_ranks + 1) * sizeof(P2PRecord)) != cudaSuccess || D->peer_ctl_dev.ensure(ASPH_MAX_RANKS) != cudaSuccess ||
-          D->blocks_done.ensure(4) != cudaSuccess || cudaMemset(D->blocks_done.p, 0, 16) != cudaSuccess ||
+          D->blocks_done.ensure(4) != cudaSuccess || cudaMemset(D->blocks_done.p, 0, 16) != cudaSuccess || D->verdict.ensure(4) != cudaSuccess ||
           cudaMallocHost((void**)&D->rec_host, size_t(n_ranks) * sizeof(P2PRecord)) != cudaSuccess)
         return fail(ASPH_ERR_CUDA);
     }

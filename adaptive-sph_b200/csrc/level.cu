@@ -28,8 +28,8 @@ constexpr unsigned int kUnassigned = 0xFFFFFFFFu;  // bit pattern of a level val
 
 typedef NbLists Lists;
 
-// front_n[0] = tail of the one front array (every particle enters it once; the fronts of successive sweeps are
-// consecutive segments); level_live[0] = number of the last sweep that assigned a value above the cutoff
+// front_n[p] = tail of the front array of the sweeps of parity p; level_live[p] = the last sweep of parity p that assigned
+// a value above the cutoff (k_propagate)
 __global__ void k_level_reset(StepCtl* ctl) {
   ctl->front_n[0] = 0; ctl->front_n[1] = 0; ctl->cand_n[0] = 0; ctl->cand_n[1] = 0;
   ctl->level_live[0] = 0; ctl->level_live[1] = 0;
@@ -90,7 +90,9 @@ __global__ void __launch_bounds__(kThreads)
 k_surface(uint32_t n, Lists L, const float4* __restrict__ xyhm, const float2* __restrict__ nrm, const PackedParams P, float cos_threshold,
           float* __restrict__ level, int* __restrict__ stamp, uint8_t* __restrict__ flags, uint32_t* __restrict__ front, StepCtl* ctl) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool surf = i < n && surface_of(i, L, xyhm, nrm, P, cos_threshold, level, stamp, flags);
+  bool surf = i < n && surface_of(i, L, xyhm, nrm, P, cos_threshold, level, stamp, flags);
+  // multi-GPU: a ghost's neighbourhood is incomplete here; its state arrives from the rank that owns it (k_ghost_front)
+  if (surf && nb_ghost(__ldg(&L.cnt[i]))) surf = false;
   // front(0): one atomic per warp
   const unsigned int mask = __ballot_sync(0xffffffffu, surf);
   if (!mask) return;
@@ -101,62 +103,160 @@ k_surface(uint32_t n, Lists L, const float4* __restrict__ xyhm, const float2* __
   if (surf) front[base + uint32_t(__popc(mask & ((1u << lane) - 1u)))] = i;
 }
 
+// multi-GPU, after the owners' level / stamp values of the ghosts have arrived: ghosts on the detected surface join front(0)
+__global__ void k_ghost_front(uint32_t count, const uint32_t* __restrict__ ghost_idx, const int* __restrict__ stamp, uint32_t* __restrict__ front,
+                              StepCtl* ctl) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const uint32_t i = ghost_idx[k];
+  if (stamp[i] == 0) front[atomicAdd(&ctl->front_n[0], 1u)] = i;
+}
+
 // K4 (simulation.rs:739-800) as one persistent cooperative kernel.  One warp per front particle j, one lane per
-// neighbour i; sweep t reads front(t - 1) = front[begin, end) and appends front(t) behind it.
+// neighbour i; sweep t reads front(t - 1) and appends front(t).
 //   stamp[i]: -1 unassigned, otherwise the sweep that assigned i (0 = detected surface)
+// The fronts of even sweeps live in front0, those of odd sweeps in front1, each array filled once from the start
+// (front_n[p] = its tail), and level_live[p] = the last sweep of parity p that assigned a value above the cutoff: what
+// sweep t reads is complete when the barrier before it falls, and nothing a block may already write in sweep t
+// (parity t) touches what a slower block still has to read at the top of sweep t (parity t - 1).
 // Values other SMs wrote in earlier sweeps (stamp, level, the front entries) are read with ld.global.cg: an L1 line
 // fetched in an earlier sweep may hold their previous contents.
+// PEER (several GPUs, x-slabs with ghost copies of the neighbours' border particles): ghosts are never assigned here —
+// their neighbourhoods are incomplete; the owner's value comes in.  After the pushes of sweep t every newly assigned
+// border particle is mailed to its ghost copies (CoopPeer, sim.cuh), the GPUs meet in a barrier that also tells every
+// rank whether any of them assigned anything (above the cutoff), and the mail — slot, value — joins the local front(t).
+template <bool PEER>
 __global__ void __launch_bounds__(kPropThreads)
 k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restrict__ level, int* __restrict__ stamp,
-            uint32_t* __restrict__ front, StepCtl* ctl, float neg_dmax, int use_cutoff) {
+            uint32_t* __restrict__ front0, uint32_t* __restrict__ front1, StepCtl* ctl, float neg_dmax, int use_cutoff, const CoopPeer P) {
   cg::grid_group grid = cg::this_grid();
   unsigned int* level_bits = reinterpret_cast<unsigned int*>(level);
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  volatile uint32_t* tail = &ctl->front_n[0];
-  volatile int* live_sweep = &ctl->level_live[0];
-  uint32_t begin = 0, end = *tail;
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  const uint32_t gwarp = gtid >> 5, nwarps = gthreads >> 5;
+  volatile uint32_t* tail = ctl->front_n;
+  volatile int* live_sweep = ctl->level_live;
+  uint32_t consumed[2] = {0u, 0u};  // how much of each parity's array earlier sweeps have read
+  uint32_t exported[2] = {0u, 0u};  // PEER: how much of it has been looked at for mail (front(0) needs none: the halo exchange did it)
+  if (PEER) exported[0] = tail[0];
+  bool go = true;                   // PEER: the verdict of the last barrier
   int sweeps = 0;
-  for (int t = 1; t <= int(n) + 1; t++) {
+  for (int t = 1; t < (1 << 30); t++) {
+    const int pin = (t - 1) & 1, pout = t & 1;
+    const uint32_t begin = consumed[pin], end = tail[pin];
     // the sweep runs if the previous one assigned anything (above the cutoff); the reference's last sweep changes nothing
-    if (end == begin || (t > 1 && *live_sweep != t - 1)) break;
+    if (PEER ? !go : (end == begin || (t > 1 && live_sweep[pin] != t - 1) || t > int(n) + 1)) break;
+    consumed[pin] = end;
     sweeps = t;
+    const uint32_t* __restrict__ fin = pin ? front1 : front0;
+    uint32_t* __restrict__ fout = pout ? front1 : front0;
     bool live = false;
-    for (uint32_t f = begin + gwarp; f < end; f += nwarps) {
-      const uint32_t j = __ldcg(front + f);
-      const float4 me = __ldg(&xyhm[j]);
-      const float lj = __ldcg(level + j);
-      const uint32_t ce = __ldg(&L.cnt_ext[j]);
-      const NbCol col(L, j);
-      for (uint32_t k0 = 0; k0 < ce; k0 += 32u) {
-        const uint32_t k = k0 + lane;
-        bool won = false;
-        uint32_t i = 0;
-        if (k < ce) {
-          i = col.get(k);
-          const int s = __ldcg(stamp + i);
-          if (s == -1 || s == t) {
-            const float4 o = __ldg(&xyhm[i]);
-            const float d = __fsqrt_rn(dist_sq_exact(__fsub_rn(me.x, o.x), __fsub_rn(me.y, o.y)));
+    // Eight lanes per front particle, four front particles per warp, and up to four neighbours per lane requested
+    // together: a sweep is a chain of dependent memory round trips (front entry -> column header -> list entry ->
+    // stamp -> atomics), so what counts is how many of them are in flight at once, not how many lanes are busy.
+    const uint32_t sub = lane & 7u, grp = lane >> 3;
+    for (uint32_t f0 = begin + gwarp * 4u; f0 < end; f0 += nwarps * 4u) {
+      const uint32_t f = f0 + grp;
+      const bool have = f < end;
+      uint32_t j = 0, ce = 0;
+      float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+      float lj = 0.f;
+      NbCol col;
+      if (have) {
+        j = __ldcg(fin + f);
+        me = __ldg(&xyhm[j]);
+        lj = __ldcg(level + j);
+        ce = __ldg(&L.cnt_ext[j]);
+        col = NbCol(L, j);
+      }
+      uint32_t ce_max = ce;
+      for (int o = 16; o >= 8; o >>= 1) ce_max = max(ce_max, __shfl_xor_sync(0xffffffffu, ce_max, o));
+      for (uint32_t k0 = 0; k0 < ce_max; k0 += 32u) {
+        uint32_t iu[4];
+        int su[4];
+        bool cand[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const uint32_t k = k0 + sub + 8u * uint32_t(u);
+          cand[u] = k < ce;
+          iu[u] = cand[u] ? col.get(k) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) su[u] = cand[u] ? __ldcg(stamp + iu[u]) : 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          cand[u] = cand[u] && (su[u] == -1 || su[u] == t) && !(PEER && nb_ghost(__ldg(&L.cnt[iu[u]])));
+        }
+        float4 ou[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) ou[u] = cand[u] ? __ldg(&xyhm[iu[u]]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bool won[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          won[u] = false;
+          if (cand[u]) {
+            const float d = __fsqrt_rn(dist_sq_exact(__fsub_rn(me.x, ou[u].x), __fsub_rn(me.y, ou[u].y)));
             const float v = __fsub_rn(lj, d);  // <= 0: the largest float is the smallest bit pattern
-            atomicMin(level_bits + i, __float_as_uint(v));
-            if (s == -1) won = atomicCAS(stamp + i, -1, t) == -1;
+            atomicMin(level_bits + iu[u], __float_as_uint(v));
+            if (su[u] == -1) won[u] = atomicCAS(stamp + iu[u], -1, t) == -1;
             if (!use_cutoff || v > neg_dmax) live = true;
           }
         }
-        const unsigned int mask = __ballot_sync(0xffffffffu, won);
-        if (mask) {
-          uint32_t base = 0;
-          if (lane == 0) base = atomicAdd(&ctl->front_n[0], uint32_t(__popc(mask)));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (won) front[base + uint32_t(__popc(mask & ((1u << lane) - 1u)))] = i;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const unsigned int mask = __ballot_sync(0xffffffffu, won[u]);
+          if (mask) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&ctl->front_n[pout], uint32_t(__popc(mask)));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (won[u]) fout[base + uint32_t(__popc(mask & ((1u << lane) - 1u)))] = iu[u];
+          }
         }
       }
     }
-    if (__any_sync(0xffffffffu, live) && lane == 0) *live_sweep = t;
+    if (__any_sync(0xffffffffu, live) && lane == 0) live_sweep[pout] = t;
     grid.sync();
-    begin = end;
-    end = *tail;
+    if (PEER) {
+      const unsigned int seq = P.seq0 + unsigned(t), par = seq & 1u;
+      // mail the border particles assigned in this sweep to their ghost copies
+      const uint32_t e0 = exported[pout], e1 = tail[pout];
+      for (uint32_t f = e0 + gtid; f < e1; f += gthreads) {
+        const uint32_t i = __ldcg(fout + f);
+        const unsigned int bits = __ldcg(level_bits + i);
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+          const uint32_t sl = __ldg(&P.rslot[side][i]);
+          if (sl == 0xffffffffu || !P.nb_mbox[side]) continue;
+          const uint32_t k = atomicAdd_system(&P.nb_ctl[side]->mbox_n[par][1 - side], 1u);  // I am that neighbour's other side
+          if (k < P.mbox_cap) P.nb_mbox[side][size_t(par * 2u + uint32_t(1 - side)) * P.mbox_cap + k] = make_uint2(sl, bits);
+        }
+      }
+      __threadfence_system();
+      grid.sync();
+      if (gtid == 0) {
+        const unsigned int mine = (e1 > e0 ? 1u : 0u) | (live_sweep[pout] == t ? 2u : 0u);
+        const unsigned int all = coop_barrier(P, seq, mine, ctl);
+        *P.verdict = ((all & 3u) == 3u && !(all & 0x80000000u) && t <= (1 << 29)) ? 1u : 0u;
+        __threadfence();
+      }
+      grid.sync();
+      go = *reinterpret_cast<volatile unsigned int*>(P.verdict) != 0u;
+      // the mail of this sweep: the ghosts' values and their place in front(t)
+#pragma unroll
+      for (int side = 0; side < 2; side++) {
+        const uint32_t n_in = min(*reinterpret_cast<volatile unsigned int*>(&P.self->mbox_n[par][side]), P.mbox_cap);
+        const uint2* __restrict__ box = P.mbox + size_t(par * 2u + uint32_t(side)) * P.mbox_cap;
+        for (uint32_t e = gtid; e < n_in; e += gthreads) {
+          const uint2 m = __ldcg(box + e);
+          level_bits[m.x] = m.y;
+          stamp[m.x] = t;
+          fout[atomicAdd(&ctl->front_n[pout], 1u)] = m.x;
+        }
+      }
+      grid.sync();
+      if (gtid == 0) { P.self->mbox_n[par][0] = 0u; P.self->mbox_n[par][1] = 0u; }  // next written two barriers from now
+      exported[pout] = tail[pout];
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->level_sweep = sweeps; ctl->level_done = 1; }
   // particles no push has reached stay FluidInterior
@@ -208,12 +308,25 @@ int launch_level_estimation(asph_sim* sim) {
   k_surface<<<blocks, kThreads, 0, st>>>(n, L, sim->xyhm.p, sim->nrm.p, sim->pp, cos_threshold, level, sim->stamp.p, sim->flags.p,
                                          sim->front[0].p, sim->ctl);
   LAUNCH_CHECK();
+  const bool peer = dist_p2p(sim);
+  if (sim->dist && !peer) { sim->last_error = "level estimation across GPU slabs needs the peer-memory path (ASPH_DIST_P2P)"; return ASPH_ERR_UNSUPPORTED; }
+  if (peer) {  // the owners' verdict on the ghosts (their own neighbourhoods are incomplete here), then front(0) with them
+    TRY(dist_halo_words(sim, level));
+    TRY(dist_halo_words(sim, sim->stamp.p));
+    uint32_t n_ghost = 0;
+    const uint32_t* ghost_idx = dist_ghost_index(sim, &n_ghost);
+    if (n_ghost) {
+      k_ghost_front<<<(n_ghost + kThreads - 1) / kThreads, kThreads, 0, st>>>(n_ghost, ghost_idx, sim->stamp.p, sim->front[0].p, sim->ctl);
+      LAUNCH_CHECK();
+    }
+  }
   int use_cutoff = sim->level_cutoff ? 1 : 0;
   float neg_dmax = -sim->pp.maximum_surface_distance;
   if (sim->prop_grid == 0) {  // co-resident blocks of the persistent kernel on this device
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate, kPropThreads, 0));
-    sim->prop_grid = std::max(1, per_sm * sim->sm_count);
+    int per_sm = 0, per_sm_peer = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<false>, kPropThreads, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_peer, k_propagate<true>, kPropThreads, 0));
+    sim->prop_grid = std::max(1, std::min(std::min(per_sm, per_sm_peer), 2) * sim->sm_count);  // more blocks only make the barrier dearer
   }
   // a front rarely holds more than a few ten thousand particles: one warp each
   uint32_t grid = uint32_t(std::max(1, std::min<int>(sim->prop_grid, int((n + 4u * kPropThreads - 1) / (4u * kPropThreads)))));
@@ -221,12 +334,14 @@ int launch_level_estimation(asph_sim* sim) {
   float* level_arg = level;
   int* stamp_arg = sim->stamp.p;
   uint32_t* front_arg = sim->front[0].p;
+  uint32_t* front1_arg = sim->front[1].p;
   const float4* xyhm_arg = sim->xyhm.p;
   StepCtl* ctl_arg = sim->ctl;
-  void* args[] = {&n_arg, &L, &xyhm_arg, &level_arg, &stamp_arg, &front_arg, &ctl_arg, &neg_dmax, &use_cutoff};
+  CoopPeer coop = dist_coop_peer(sim);
+  void* args[] = {&n_arg, &L, &xyhm_arg, &level_arg, &stamp_arg, &front_arg, &front1_arg, &ctl_arg, &neg_dmax, &use_cutoff, &coop};
   cudaEvent_t kt0 = nullptr, kt1 = nullptr;
   if (sim->kt_every > 0) { kt0 = kt_event(sim); kt1 = kt_event(sim); cudaEventRecord(kt0, st); }
-  CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_propagate, dim3(grid), dim3(kPropThreads), args, 0, st));
+  CUDA_TRY(cudaLaunchCooperativeKernel(peer ? (void*)k_propagate<true> : (void*)k_propagate<false>, dim3(grid), dim3(kPropThreads), args, 0, st));
   sim->kernel_launches++;
   if (kt1) cudaEventRecord(kt1, st);
   const int rc_sync = sync_ctl(sim);
@@ -236,6 +351,8 @@ int launch_level_estimation(asph_sim* sim) {
     kt_release(sim, kt0); kt_release(sim, kt1);
   }
   TRY(rc_sync);
+  if (peer) dist_coop_advance(sim, unsigned(std::max(0, sim->ctl_host->level_sweep)));  // one barrier per sweep run, on every rank alike
+  if (sim->ctl_host->error_flags & ERRF_PEER_TIMEOUT) return check_error_flags(sim);
   if (sim->ctl_host->error_flags & ERRF_LIST_CAPACITY) return ASPH_RETRY_LISTS;
   if (!sim->ctl_host->level_done) { sim->last_error = "level-set propagation did not terminate"; return ASPH_ERR_INVALID; }
   // sweeps including the final one that changes nothing, as the reference counts them (simulation.rs:739-799)
@@ -249,10 +366,12 @@ int launch_level_smoothing(asph_sim* sim) {
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
   const int c = sim->cur;
   Lists L{sim->nbpool.p, sim->slice_base.p, sim->cnt.p, sim->cnt_ext.p, sim->far_idx.p, sim->far_cnt.p};
+  if (sim->dist) TRY(dist_halo(sim, sim->pos[c].p, 8));  // K17 reads the neighbours' advected positions: the ghosts' come from their owners
   k_smooth<<<blocks, kThreads, 0, sim->stream>>>(n, L, sim->pos[c].p, sim->xyhm.p, sim->rho.p,
                                                  sim->level[c].p, sim->scratch_f.p, sim->pp.maximum_surface_distance, sim->ctl);
   LAUNCH_CHECK();
   CUDA_TRY(cudaMemcpyAsync(sim->level[c].p, sim->scratch_f.p, size_t(n) * sizeof(float), cudaMemcpyDeviceToDevice, sim->stream));
+  if (sim->dist) TRY(dist_halo_words(sim, sim->level[c].p));  // a ghost's own sum runs over an incomplete neighbourhood
   sim->level_valid = true;
   return ASPH_OK;
 }

@@ -145,6 +145,26 @@ struct PeerCtl {
   unsigned int halo_flag[2];                 // [0] written by rank - 1, [1] by rank + 1
   unsigned int stats_flag[ASPH_MAX_RANKS];   // [r] written by rank r
   unsigned long long stats_in[ASPH_MAX_RANKS][3][ASPH_ACC_WORDS];  // rank r's SolverCtl::acc[slot] of its own particles
+  // the persistent cooperative kernels (level.cu, adapt.cu): barriers across all GPUs with a 4-bit payload per rank, and
+  // mailboxes the two neighbour ranks append to; both double buffered by the parity of the barrier number
+  unsigned int coop_flag[2][ASPH_MAX_RANKS];  // [parity][from rank] = barrier number << 4 | payload
+  unsigned int mbox_n[2][2];                  // [parity][from side (0 = rank - 1)] entries waiting in this rank's mailbox
+};
+// What a persistent cooperative kernel needs to talk to the other GPUs (by value; self == nullptr: single GPU).
+// A message is a uint2 {ghost slot on the receiving rank, payload}: a border particle's new value travels to its ghost
+// copy as one 8-byte store into the neighbour's mailbox over NVLink, after one system-scope atomic for the position.
+struct CoopPeer {
+  PeerCtl* self;
+  PeerCtl* const* all_ctl;   // every rank's PeerCtl (device array)
+  PeerCtl* nb_ctl[2];
+  int rank, nranks;
+  unsigned int seq0;         // barriers completed before this launch (same on every rank)
+  uint2* mbox;               // this rank's mailboxes: entry k of [parity][side] at ((parity * 2 + side) * mbox_cap + k)
+  uint2* nb_mbox[2];         // the neighbours' mailboxes (peer mappings)
+  uint32_t mbox_cap;
+  const uint32_t* rslot[2];  // per local particle: its ghost slot on that neighbour, or ~0
+  const uint32_t* owner_slot;  // per local particle: for a ghost, its index on the rank that owns it (else ~0)
+  unsigned int* verdict;     // device word (this rank) in which the thread that ran the barrier leaves the combined payload
 };
 struct PeerArgs {          // by value into the sweep kernels; self == nullptr: single GPU, or the NCCL path
   PeerCtl* self;
@@ -321,6 +341,10 @@ bool dist_p2p(asph_sim* sim);                              // peer-memory path a
 // arguments of the next sweep pass: what it waits for, and (field >= 0) where it publishes: packA (0) / packP[0] (1) / packP[1] (2)
 PeerArgs dist_peer_args(asph_sim* sim, bool wait_halo, bool wait_stats, int field, bool with_stats);
 int dist_reduce_flags(asph_sim* sim, bool with_lists);     // make error flags (and "lists too small") agree on all ranks
+CoopPeer dist_coop_peer(asph_sim* sim);                    // arguments of a persistent cooperative kernel (self == nullptr when single GPU)
+void dist_coop_advance(asph_sim* sim, unsigned int barriers);  // the launch ran that many cross-GPU barriers
+int dist_halo_words(asph_sim* sim, void* field);           // dist_halo of a 4-byte field whatever its type
+const uint32_t* dist_ghost_index(asph_sim* sim, uint32_t* count);  // sorted indices of the ghost particles of this step
 int dist_local_map(asph_sim* sim);                         // scratch_u[3][i] = slot of owned particle i in read-backs, ~0u for ghosts
 void dist_destroy(asph_sim* sim);
 // capi.cu
@@ -333,6 +357,41 @@ void kt_release(asph_sim* sim, cudaEvent_t e);
 // ------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 #define ASPH_PI_F 3.14159265358979323846f
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Barrier number `seq` across the persistent kernels of all ranks, called by ONE thread of each after its own grid has
+// synchronised and fenced (system scope): every rank leaves seq << 4 | payload with every other rank and waits for
+// theirs; returns the OR of all payloads, or 0x80000000 if a rank did not show up within about 2 s (the step then fails
+// on the host instead of hanging).  A rank can be at most one barrier ahead of another, hence two flag sets.
+__device__ __forceinline__ unsigned int coop_barrier(const CoopPeer& P, unsigned int seq, unsigned int payload, StepCtl* ctl) {
+  const unsigned int par = seq & 1u, word = (seq << 4) | (payload & 15u);
+  for (int q = 0; q < P.nranks; q++)
+    if (q != P.rank) st_release_sys(&P.all_ctl[q]->coop_flag[par][P.rank], word);
+  unsigned int acc = payload & 15u;
+  unsigned long long t0 = 0;
+  for (int q = 0; q < P.nranks; q++) {
+    if (q == P.rank) continue;
+    const volatile unsigned int* f = &P.self->coop_flag[par][q];
+    unsigned int w;
+    for (unsigned int spins = 0; ((w = *f) >> 4) != (seq & 0x0fffffffu); spins++) {
+      if ((spins & 1023u) == 1023u) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 2000000000ull) { atomicOr(&ctl->error_flags, ERRF_PEER_TIMEOUT); return 0x80000000u; }
+      }
+    }
+    acc |= w & 15u;
+  }
+  (void)ld_acquire_sys(&P.self->coop_flag[par][P.rank == 0 ? 1 : 0]);  // orders the reads of what the peers stored before their flag
+  return acc;
+}
 #define ASPH_FRAC_1_PI_F 0.318309886183790671538f
 
 __device__ __forceinline__ unsigned int enc_f(float f) {
@@ -423,7 +482,9 @@ __device__ __forceinline__ float target_mass(float level, const PackedParams& P)
     float tr = P.particle_radius_fine * (1.f - t) + P.particle_radius_base * t;
     return radius_to_volume(tr) * P.rest_density;
   }
-  float st = powf(t, 0.5f);
+  // t.powf(0.5) in the reference: libm's powf is correctly rounded here (CUDA's powf is not), and the correctly rounded
+  // square root is what it returns
+  float st = __fsqrt_rn(t);
   float tr = P.particle_radius_fine * (1.f - st) + P.particle_radius_base * st;
   return radius_to_volume(tr) * P.rest_density;
 }

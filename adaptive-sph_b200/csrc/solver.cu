@@ -31,14 +31,6 @@ struct SweepTotals {
   unsigned long long normal, negative, singular;
   float err_sum;
 };
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 // Spin until a peer's sequence number has reached `seq` (PeerCtl, sim.cuh).  Bounded: a rank that failed and stopped
 // launching must not hang the others; after 2 s the step is flagged and fails on the host.
 __device__ __forceinline__ void peer_wait(const unsigned int* flag, unsigned int seq, StepCtl* ctl) {

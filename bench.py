@@ -6,17 +6,25 @@
                                                                kind "port" — the Rust reference cannot be built
                                                                in this image) on all host cores
 
-Workload at N = 1: BASELINE.json configs[1] — 2-D dam break, uniform h, 999 292 particles, HybridDFSPH
-(`default-scene-web.yaml` geometry at spacing 1.122e-3, default-config with the reference's "Uniform SPH" overrides
-of media/motivation-video.yaml:42-57).  At N > 1 the tank and the block are widened N-fold (weak scaling: 999 292
-particles per GPU) and split into N vertical slabs.
-A "step" is one FluidSimulation::single_step over the whole particle set.  value = Σ_steps N_step / device time.
+Workload (every N): the north star's case — 2-D dam break, 15 996 516 initial particles (`default-scene-web.yaml`
+block at spacing 2.806e-4), adaptive h with radius ratio 4:1, HybridDFSPH, EmptyAngle level set and share / merge /
+split every step (SURVEY.md §8d C3 recipe: particle_radius_fine = the radius of a lattice particle,
+particle_radius_base = 4x, maximum_surface_distance 0.2, default-config otherwise).  The scene is advanced by
+PREROLL_STEPS untimed steps first (input preparation): the interior coarsens towards the base size, the particle
+count settles near 5 M, the block lands.  During the first RAMP_STEPS of them particle_radius_base grows linearly
+from the fine radius to its final value — parameters are passed by value every step, as in the reference
+(main_loop.rs:280) — because merging two thirds of 16 M particles in ONE step, which the plain recipe does, throws
+thousands of surface particles off at 10-20 m/s in the reference algorithm (CPU oracle and GPU alike) and the CFL
+rule then holds the whole simulation at dt ~ 1e-5.
+A "step" is one FluidSimulation::single_step (physics + resampling) over the whole particle set.
+value = sum over the timed steps of N_step / device time of those steps (CUDA events on the library stream).
+At N > 1 the SAME scene is cut into N x-slabs (strong scaling): bench_dist.py.
 """
 import argparse
 import ctypes as C
 import json
+import math
 import os
-import signal
 import subprocess
 import sys
 import threading
@@ -30,54 +38,63 @@ if ROOT not in sys.path:
 
 METRIC = "particle-steps/sec on 2D dam-break at 1/2/4/8 B200; HBM GB/s vs roofline"
 UNIT = "particle-steps/s"
-SPACING_C2 = 1.122e-3
-# The block of the reference's dam-break scene (default-scene-web.yaml) starts 0.1 above the floor, falls freely for
-# ~106 steps (no particle has positive pressure: every solve stops after its first sweep, a step is little more than
-# the neighbour build) and hits the floor at 1.4 m/s.  At 1 M particles the reference's own algorithm does not survive
-# that impact reliably: its Jacobi iteration stops converging within max_iters, the pressures run away and the
-# `a_p.is_finite()` assertion fires — on the CPU oracle as on the GPU, sooner or later depending on rounding (the impact
-# is chaotic), and already during the impact when the block is widened for 4 GPUs.  The benchmark therefore lowers the
-# drop to DROP_GAP = 0.02 (same block, same spacing, same fill ratio): the fluid lands gently (step 21) and the step loop
-# then runs in the regime that matters — divergence solve 3 sweeps, density solve 15-80 sweeps per step — for ~400 steps
-# at 1 M particles, but only for ~65 steps when the block is 4 times as wide (the wider the wetted floor, the sooner the
-# reference's solver loses it; measured on one GPU with the 4x scene, so it is physics, not the decomposition).  The
-# workload is therefore the scene at PREROLL_T = 0.064 simulated seconds, ten steps after the landing; advancing to that
-# time is input preparation (before the warm-up steps, untimed).  Sweep counts per step grow with the width of the
-# block, so next to particle-steps/s the JSON carries particle-sweeps/s, the figure to compare across GPU counts.
-# The timed steps replay a fixed, short window (the 8-GPU scene lasts only ~25 steps past the pre-roll): after
-# REPLAY_WINDOW steps the state returns to the start of the window; should a step fail all the same, the window is cut
-# short there and replayed.
+SPACING_1M = 1.122e-3     # BASELINE configs[1]:   623 x 1604 =    999 292 particles
+SPACING_4M = 5.612e-4     # BASELINE configs[2]:  1247 x 3207 =  3 999 129
+SPACING_16M = 2.806e-4    # north star:           2494 x 6414 = 15 996 516
+SPACING_C2 = SPACING_1M   # (name used by tests / tools for the configs[1] spacing)
+SPACING = float(os.environ.get("ASPH_BENCH_SPACING", SPACING_16M))  # smaller scenes for dry runs of this script
+RATIO = 4.0
+DMAX = 0.2
+# The block of the reference's dam-break scene (default-scene-web.yaml) starts 0.1 above the floor and hits it at
+# 1.4 m/s, an impact the reference's Jacobi solver does not survive reliably at a million particles and more (CPU oracle
+# and GPU alike: DESIGN.md §5); the benchmark lowers the drop to DROP_GAP (same block, spacing, fill ratio).
 DROP_GAP = 0.02
-PREROLL_T = 0.064
-REPLAY_WINDOW = 16
-REF_SAMPLE_WIDTH = 0.175  # the CPU arm's bounded sample: the same column height and spacing, a quarter of the block's width
+PREROLL_T = 0.064         # uniform configs[1] line: simulated time the scene is advanced to (ten steps after the landing)
+PREROLL_STEPS = int(os.environ.get("ASPH_BENCH_PREROLL", 120))
+RAMP_STEPS = 60
+BLOCK_W, BLOCK_H = 0.7, 1.8
+
+# algorithmic bytes per particle and launch of the kernels that are timed one by one
+KERNEL_BYTES = {
+    "neighbors": (20.0, "k_neighbors (K2+K7+K9+K11: neighbour lists + density + a_ii partials; x,h,m -> rho,a_ii: 20 B/particle algorithmic)"),
+    "accel_sweep": (28.0, "k_sweep<0> (K14, pressure-acceleration pass: x,m,rho,p -> a^p; 28 B/particle algorithmic)"),
+    "jacobi_sweep": (40.0, "k_sweep<1> (K15, Jacobi update pass: x,m,rho,a^p,p,s,a_ii -> p'; 40 B/particle algorithmic)"),
+    "level_propagate": (20.0, "k_propagate (K4, level-set propagation, one persistent launch per step; 20 B/particle algorithmic in total)"),
+    "partner_search": (32.0, "k_greedy (K19/K20 partner search, one persistent launch per share / merge phase; x,m,level,class in, partner out: 32 B/particle)"),
+}
+
+
+def default_params(A):
+    return A.SimulationParams.from_yaml(os.path.join(ROOT, "configs", "default-config.yaml"))
 
 
 def uniform_params(A):
-    p = A.SimulationParams.from_yaml(os.path.join(ROOT, "configs", "default-config.yaml"))
-    return p.replace(merging=False, sharing=False, splitting=False, level_estimation_method="None")
+    """The reference's "Uniform SPH" recipe (media/motivation-video.yaml:42-57): BASELINE configs[1]."""
+    return default_params(A).replace(merging=False, sharing=False, splitting=False, level_estimation_method="None")
 
 
-BLOCK_W, BLOCK_H = [float(v) for v in os.environ.get("ASPH_BENCH_BLOCK", "0.7,1.8").split(",")]
-# Weak scaling (N > 1 GPUs), the tank is N times as wide and holds N times the fluid of configs[1]:
-#   "wide" (default): ONE block N times as wide — the scene every multi-GPU number of this round was measured on.  The wider
-#             the wetted floor, the more Jacobi sweeps a step needs (23 / 35 / 55 density sweeps at 2 / 4 / 8 GPUs against
-#             19 at one) and the sooner the reference's solver loses the scene, so particle-steps/s mixes the scaling of
-#             the code with the physics of the scene; particle-sweeps/s (in `config`) is the like-for-like figure.
-#   "columns" (ASPH_BENCH_SCENE=columns; exploratory): N dam-break columns of the configs[1] width side by side, one per 2 m
-#             of tank — a half-width column against either side wall and N - 1 full ones between them, so that the
-#             equal-count slab faces cut through the middle of the full columns.  On the CPU oracle 2 x 1 M particles need
-#             3 + 21.0 sweeps per step in the benchmark window (wide: 3 + 22.5), but 4 x 1 M particles run into solves that
-#             do not converge within max_iters a few steps after the landing (steps 30, 31 of the pre-roll): more separate
-#             impacts, more chances for the reference's solver to lose one.  Not the default; no hardware run yet.
-SCENE_KIND = os.environ.get("ASPH_BENCH_SCENE", "wide")
+def fine_radius(spacing):
+    return math.sqrt(0.93 / math.pi) * spacing  # radius of a lattice particle: volume_fill_ratio * spacing^2 = pi r^2
+
+
+def adaptive_params(A, spacing, ratio=RATIO):
+    r_f = fine_radius(spacing)
+    return default_params(A).replace(particle_radius_fine=r_f, particle_radius_base=ratio * r_f, maximum_surface_distance=DMAX)
+
+
+def ramped(params, spacing, step, ratio=RATIO, ramp_steps=RAMP_STEPS):
+    """Parameters of pre-roll step number `step`: the base radius on its way from the fine radius to ratio x fine."""
+    f = min(1.0, (step + 1) / float(ramp_steps))
+    return params.replace(particle_radius_base=(1.0 + (ratio - 1.0) * f) * fine_radius(spacing))
 
 
 def dam_break(A, spacing, n_gpus=1, block_width=None, kind=None):
+    """The dam-break block DROP_GAP above the floor.  (n_gpus / kind: the widened tanks of the round-1 weak-scaling runs,
+    kept for tools/ and the tests of their geometry; the benchmark itself uses the one 2 m tank at every N.)"""
     w = 2.0 * n_gpus
     bw = BLOCK_W if block_width is None else block_width
     y0 = -1.0 + DROP_GAP
-    if n_gpus == 1 or (kind or SCENE_KIND) == "wide":
+    if n_gpus == 1 or (kind or "wide") == "wide":
         return A.SceneConfig.dam_break(spacing, pos=(-w / 2 + 0.05, y0), size=(bw * n_gpus, BLOCK_H), width=w, height=2.0)
     spans = [(-w / 2 + 0.05, bw / 2)] + [(-w / 2 + 2.0 * k - bw / 2, bw) for k in range(1, n_gpus)] + [(w / 2 - 0.05 - bw / 2, bw / 2)]
     return A.SceneConfig({"boundary": {"type": "box", "width": w, "height": 2.0},
@@ -85,13 +102,27 @@ def dam_break(A, spacing, n_gpus=1, block_width=None, kind=None):
                                       "velocity": [0, 0]} for x0, width in spans]})
 
 
+def workload_name(n0):
+    return (f"north star: 2D dam-break, {n0} initial particles (default-scene-web block at spacing {SPACING:g}, {DROP_GAP} above the floor), adaptive h "
+            f"radius ratio {RATIO:g}:1 (particle_radius_fine = lattice particle radius, maximum_surface_distance {DMAX}), HybridDFSPH, EmptyAngle level set, "
+            f"share / merge / split every step; state after {PREROLL_STEPS} untimed steps (base radius ramped up over the first {RAMP_STEPS})")
+
+
 def preroll(sim, t_target, max_steps=2000):
-    """Advance the scene to simulated time t_target (input preparation, untimed).  Returns the steps taken."""
+    """Advance a scene to simulated time t_target (input preparation, untimed).  Returns the steps taken."""
     k = 0
     while sim.time < t_target and k < max_steps:
         sim.single_step()
         k += 1
     return k
+
+
+def preroll_adaptive(sim, A, base, spacing, steps=None):
+    """The adaptive scene's input preparation: `steps` untimed steps, base radius ramped up over the first RAMP_STEPS."""
+    steps = PREROLL_STEPS if steps is None else steps
+    for s in range(steps):
+        sim.single_step(ramped(base, spacing, s))
+    return steps
 
 
 def peaks():
@@ -103,38 +134,36 @@ def peaks():
 
 
 def issue_roofline(n, launch_ms, sm_count, sm_mhz, warp_instructions, hbm_peak_gbs):
-    """Second reading of the Jacobi update pass: it executes ~590 instructions per particle for its 40
-    algorithmic bytes (13 pairs x ~21 instructions + the tile pipeline), about 2.6 x the chip's instruction-to-byte balance,
-    so its ceiling is the issue rate (4 warp instructions / clock / SM), reported beside the contract's HBM roofline.
-    `warp_instructions` per launch comes from the committed ncu capture (profiles/r1_traffic.json)."""
+    """Second reading of a pair pass: its ceiling is the issue rate (4 warp instructions / clock / SM), reported
+    beside the contract's HBM roofline.  `warp_instructions` per launch comes from a committed ncu capture (profiles/)."""
     peak = 4.0 * sm_count * sm_mhz * 1e6
     achieved = warp_instructions / (launch_ms * 1e-3)
     floor_s = warp_instructions / peak                      # duration with every issue slot filled
     return {"bound": "issue", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "G warp-instructions/s", "frac": achieved / peak,
             "sm_count": int(sm_count), "sm_mhz": float(sm_mhz), "instructions_per_launch": float(warp_instructions),
             "instructions_per_particle": 32.0 * warp_instructions / n,
-            "instructions_source": "profiles/r1_traffic.json (ncu smsp__inst_executed.sum, same kernel and workload)",
             # the contract's HBM fraction (40 B x particles / time / peak) this instruction mix would reach at full issue
             "hbm_frac_at_full_issue": 40.0 * n / floor_s / 1e9 / hbm_peak_gbs}
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_throttle_reasons.hw_slowdown,clocks_throttle_reasons.hw_thermal_slowdown," \
+        "clocks_throttle_reasons.sw_thermal_slowdown,clocks_throttle_reasons.sw_power_cap"
 
     def __init__(self, device=0):
-        self.rows, self.proc, self.device = [], None, device
+        self.device, self.rows, self.proc, self.thread = device, [], None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
 
     def _read(self):
         for line in self.proc.stdout:
@@ -164,307 +193,245 @@ def pinned(shape, dtype=np.float32):
     return t.numpy(), t
 
 
+class StepLog:
+    """What a run of steps did: the figures throughput is meaningless without."""
+    KEYS = ("div_sweeps", "density_sweeps", "level_sweeps", "n_shared", "n_merged", "n_split_parents")
+
+    def __init__(self):
+        self.n, self.rows, self.rounds, self.dt = [], [], [], []
+
+    def add(self, sim):
+        i = sim.step_info()
+        self.n.append(int(i["n_particles_begin"]))
+        self.rows.append([int(i[k]) for k in self.KEYS])
+        self.rounds.append(sim.adapt_rounds())
+        self.dt.append(float(i["dt"]))
+
+    def summary(self):
+        a = np.asarray(self.rows, dtype=np.float64).reshape(-1, len(self.KEYS))
+        out = {"avg_" + k: float(a[:, j].mean()) for j, k in enumerate(self.KEYS)} if len(a) else {}
+        out.update({"particles_first": self.n[0] if self.n else None, "particles_last": self.n[-1] if self.n else None,
+                    "avg_greedy_rounds": float(np.mean(self.rounds)) if self.rounds else None,
+                    "max_greedy_rounds": int(max(self.rounds)) if self.rounds else None,
+                    "avg_dt": float(np.mean(self.dt)) if self.dt else None})
+        return out
+
+
+def kernel_table(kt, K, n_avg, peak):
+    """Per timed kernel class: average launch, launches and milliseconds per step, algorithmic GB/s and roofline fraction."""
+    tab = {}
+    for name, (ms, cnt) in kt.items():
+        if cnt == 0:
+            continue
+        row = {"avg_launch_ms": ms / cnt, "launches_per_step": cnt / max(K, 1), "ms_per_step": ms / max(K, 1)}
+        if name in KERNEL_BYTES:
+            gbs = KERNEL_BYTES[name][0] * n_avg / (ms / cnt * 1e-3) / 1e9
+            row.update({"algorithmic_bytes_per_particle": KERNEL_BYTES[name][0], "achieved_gbs": gbs, "frac": gbs / peak})
+        tab[name] = row
+    return tab
+
+
 def run_ours(args):
     import asph_b200 as A
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
-        return run_ours_distributed(args, A, rank, world)
+        from bench_dist import run  # multi-GPU arm: the same scene in N x-slabs
+        return run(args, A, rank, world)
+    t_start = time.perf_counter()
     lib = A.load_library()
-    params = uniform_params(A)
-    scene = dam_break(A, SPACING_C2)
-    pos, vel, mass = A.scene_particles(scene)
-    boundary = A.scene_boundary(scene, "AnalyticOverestimate")
-    n = len(mass)
-    sim = A.FluidSimulation(params, pos, vel, mass, boundary, counters_enabled=True, lib=lib)
+    base = adaptive_params(A, SPACING)
+    scene = dam_break(A, SPACING)
+    base = A.init_simulation_params(base, scene)
+    split = A.load_split_patterns_from_file()
+    sim = A.init_fluid_sim(base, scene, split, counters_enabled=True, lib=lib)
     assert sim.backend() == "cuda-sm100a"
+    boundary = A.scene_boundary(scene, base["init_boundary_handler"])
+    n0 = sim.num_fluid_particles()
     K, W = args.steps, args.warmup
 
-    # ---- device-resident arm: W warm-up steps, K timed steps; time = CUDA-event time of the step counter -------
-    pre_steps = preroll(sim, args.preroll_time)
+    # ---- input preparation (untimed), warm-up ------------------------------------------------------------------
+    t_pre = time.perf_counter()
+    preroll_adaptive(sim, A, base, SPACING)
+    t_pre = time.perf_counter() - t_pre
     for _ in range(W):
-        sim.single_step()
+        sim.single_step(base)
     warm_state = (sim.get_field("position"), sim.get_field("velocity"), sim.get_field("mass"))
-    sim.set_state(*warm_state)   # same state again, so the e2e arm and the CPU baseline can start from it too
-    sim.set_kernel_timing(4)
+    warm_step_number = sim.step_number
+    print(f"[bench] input prepared: {n0} -> {len(warm_state[2])} particles in {t_pre:.1f} s; {sim.kernel_launches()} kernel launches before the timed region",
+          file=sys.stderr, flush=True)
+
+    # ---- device-resident arm: K timed steps; time = CUDA events around every step on the library stream ---------
+    sim.set_kernel_timing(1)
     cnt0 = sim.counters()
-    c0 = cnt0["simulation-step"][0]
     l0 = sim.kernel_launches()
     clocks = ClockSampler()
     clocks.start()
     t0 = time.perf_counter()
-    particle_steps, sweeps_div, sweeps_den, per_step = 0, 0, 0, []
-    window, in_window, restarts, dev_ms, k = REPLAY_WINDOW, 0, 0, 0.0, 0
-    while k < K:
-        if in_window >= window:
-            sim.set_state(*warm_state)  # replay the same window (outside the per-step CUDA-event timing)
-            in_window = 0
+    log = StepLog()
+    dev_ms = 0.0
+    for _ in range(K):
         c_before = sim.counters()["simulation-step"][0]
-        try:
-            sim.single_step()
-        except A.AsphError as e:  # the scene blew up inside the window: shorten the window and replay (not counted)
-            restarts += 1
-            if restarts > 8 or in_window < 3:
-                raise
-            window = max(3, in_window - 2)
-            sim.set_state(*warm_state)
-            in_window = 0
-            continue
+        sim.single_step(base)
         dev_ms += sim.counters()["simulation-step"][0] - c_before
-        info = sim.step_info()
-        particle_steps += info["n_particles_begin"]
-        sweeps_div += info["div_sweeps"]; sweeps_den += info["density_sweeps"]
-        per_step.append((info["div_sweeps"], info["density_sweeps"], info["dt"]))
-        k += 1; in_window += 1
+        log.add(sim)
     wall = time.perf_counter() - t0
     clk = clocks.stop()
     cnt1 = sim.counters()
-    phases = {k: (cnt1[k][0] - cnt0[k][0]) / max(K + restarts, 1) for k in cnt1}
+    phases = {k: (cnt1[k][0] - cnt0[k][0]) / max(K, 1) for k in cnt1}
     launches = sim.kernel_launches() - l0
     kt = sim.kernel_timing()
     sim.set_kernel_timing(0)
+    particle_steps = float(sum(log.n))
+    n_avg = particle_steps / max(K, 1)
     value = particle_steps / (dev_ms * 1e-3)
-    particle_sweeps_per_s = float(n) * (sweeps_div + sweeps_den) / (dev_ms * 1e-3)
+    sm = log.summary()
 
-    # ---- roofline of the dominant kernel (the Jacobi update pass, K15) -------------------------------------------
+    # ---- rooflines: the dominant kernel (largest share of the step among the kernels timed one by one), the step ----
     peak, peak_src = peaks()
-    roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
-            "kernel": "k_sweep<1> (K15, the Jacobi update pass: x,m,rho,a^p,p,s,a_ii -> p'; 40 B/particle algorithmic)", "peak_source": peak_src}
-    try:  # DRAM bytes of one launch of that kernel from the committed ncu capture (profiles/)
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            tr = json.load(f)["k_sweep<1> (K15)"]
-        roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-        roof["traffic_source"] = "profiles/r1_traffic.json (ncu --set full, per launch, 999292 particles)"
-    except (OSError, KeyError, ValueError):
-        pass
-    extra = {}
-    if kt["jacobi_sweep"][1] > 0:
-        ms_j = kt["jacobi_sweep"][0] / kt["jacobi_sweep"][1]
-        roof["achieved"] = 40.0 * n / (ms_j * 1e-3) / 1e9
-        roof["frac"] = roof["achieved"] / peak
-        roof["avg_launch_ms"] = ms_j
-        roof["launches_timed"] = int(kt["jacobi_sweep"][1])
-        if "ASPH_ROWS4" not in os.environ and "ASPH_BULK" not in os.environ:
-            try:
-                import torch
-                extra["roofline_issue"] = issue_roofline(n, ms_j, torch.cuda.get_device_properties(0).multi_processor_count,
-                                                         clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965.0, tr["warp_instructions"], peak)
-            except Exception as e:  # informational: never at the cost of the line
-                extra["roofline_issue"] = {"error": repr(e)[:200]}
-    if kt["accel_sweep"][1] > 0:
-        ms_a = kt["accel_sweep"][0] / kt["accel_sweep"][1]
-        extra["roofline_accel"] = {"kernel": "k_sweep<0> (K14, the pressure-acceleration pass: x,m,rho,p -> a^p; 28 B/particle algorithmic)",
-                                   "achieved": 28.0 * n / (ms_a * 1e-3) / 1e9, "avg_launch_ms": ms_a,
-                                   "frac": 28.0 * n / (ms_a * 1e-3) / 1e9 / peak, "launches_timed": int(kt["accel_sweep"][1])}
-    if kt["neighbors"][1] > 0:
-        extra["neighbors_ms"] = kt["neighbors"][0] / kt["neighbors"][1]
-        extra["sort_grid_ms"] = kt["sort_grid"][0] / kt["sort_grid"][1]
-    # whole step against SURVEY.md §8d: B = 260 + 68 (S_div + S_den) bytes per particle-step
-    b_step = 260.0 + 68.0 * (sweeps_div + sweeps_den) / max(K, 1)
-    extra["step_roofline"] = {"bytes_per_particle_step": b_step, "achieved": b_step * value / 1e9,
-                              "frac": b_step * value / 1e9 / peak}
+    tab = kernel_table(kt, K, n_avg, peak)
+    single = {k: v for k, v in tab.items() if k in KERNEL_BYTES}
+    dom = max(single, key=lambda k: single[k]["ms_per_step"]) if single else None
+    roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src}
+    if dom:
+        roof.update({"kernel": KERNEL_BYTES[dom][1], "achieved": single[dom]["achieved_gbs"], "frac": single[dom]["frac"],
+                     "avg_launch_ms": single[dom]["avg_launch_ms"], "share_of_step": single[dom]["ms_per_step"] / (dev_ms / max(K, 1)),
+                     "particles_per_launch": n_avg})
+        try:  # DRAM bytes of one launch of that kernel from the committed ncu capture of this workload (profiles/)
+            with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+                tr = json.load(f)[dom]
+            roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            roof["traffic_source"] = tr.get("source", "profiles/r2_traffic.json (ncu --set full, per launch)")
+        except (OSError, KeyError, ValueError):
+            pass
+    s_div, s_den = sm.get("avg_div_sweeps", 0.0), sm.get("avg_density_sweeps", 0.0)
+    b_step = 388.0 + 68.0 * (s_div + s_den)  # SURVEY.md §8d: adaptive DFSPH, B = 388 + 68 (S_div + S_den) bytes per particle-step
+    step_roof = {"bytes_per_particle_step": b_step, "achieved": b_step * value / 1e9, "frac": b_step * value / 1e9 / peak, "unit": "GB/s"}
 
     # ---- e2e arm: host buffers in, host buffers out, every step (same K steps from the same warm state) ---------
-    hp, _tp = pinned((n, 2)); hv, _tv = pinned((n, 2)); hm, _tm = pinned((n,))
-    hp[:] = warm_state[0]; hv[:] = warm_state[1]; hm[:] = warm_state[2]
-    sim.set_state(hp, hv, hm); sim.single_step()  # one untimed pass through this path
-    hp[:] = warm_state[0]; hv[:] = warm_state[1]; hm[:] = warm_state[2]
+    cap = int(len(warm_state[2]) * 1.1) + 4096
+    hp, _tp = pinned((cap, 2)); hv, _tv = pinned((cap, 2)); hm, _tm = pinned((cap,))
+
+    def load_warm():
+        n = len(warm_state[2])
+        hp[:n] = warm_state[0]; hv[:n] = warm_state[1]; hm[:n] = warm_state[2]
+        sim.lib.asph_set_step_number(sim._h, warm_step_number)
+        return n
+
+    n_cur = load_warm()
+    sim.set_state(hp[:n_cur], hv[:n_cur], hm[:n_cur]); sim.single_step(base)  # one untimed pass through this path
+    n_cur = load_warm()
+    e2e_log = StepLog()
+    h2d = d2h = 0
     t0 = time.perf_counter()
-    e2e_particle_steps, in_window, k = 0, 0, 0
-    while k < K:
-        if in_window >= window:
-            hp[:] = warm_state[0]; hv[:] = warm_state[1]; hm[:] = warm_state[2]
-            in_window = 0
-        sim.set_state(hp, hv, hm)                   # H2D of this step's inputs (x, v, m) from pinned host memory
-        try:
-            sim.single_step()
-        except A.AsphError:
-            if in_window < 3:
-                raise
-            window = max(3, in_window - 2)
-            in_window = window                      # next iteration restarts the window
-            continue
-        sim.get_field("position", out=hp)           # D2H of the step's result (x, v), reference particle order, into the
-        sim.get_field("velocity", out=hv)           # same host buffers: this step's output is the next step's input
-        e2e_particle_steps += n
-        k += 1; in_window += 1
+    for _ in range(K):
+        sim.set_state(hp[:n_cur], hv[:n_cur], hm[:n_cur])    # H2D of this step's inputs (x, v, m) from pinned host memory
+        sim.single_step(base)
+        e2e_log.add(sim)
+        h2d += n_cur * 20
+        n_cur = sim.num_fluid_particles()                      # resampling changes the particle count
+        sim.get_field("position", out=hp[:n_cur])              # D2H of the step's result (x, v, m), reference particle order,
+        sim.get_field("velocity", out=hv[:n_cur])              # into the same host buffers: this step's output is the next
+        sim.get_field("mass", out=hm[:n_cur])                  # step's input
+        d2h += n_cur * 20
     e2e_s = time.perf_counter() - t0
-    e2e = {"value": e2e_particle_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * 20), "d2h_bytes_per_step": int(n * 16)}
+    e2e = {"value": float(sum(e2e_log.n)) / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d / max(K, 1)), "d2h_bytes_per_step": int(d2h / max(K, 1)),
+           "ms_per_step": e2e_s * 1e3 / max(K, 1), "work": e2e_log.summary()}
+    same_work = all(abs(e2e["work"].get(k, 0) - sm.get(k, 0)) <= 1.0 for k in ("avg_div_sweeps", "avg_density_sweeps", "avg_level_sweeps"))
+    e2e["same_work_as_device_arm"] = bool(same_work)
+    sim_time = sim.time
+    sim.close()
+    if not same_work:
+        raise SystemExit(f"bench: the e2e arm did not do the work of the device arm: {e2e['work']} vs {sm}")
 
     # ---- CPU baseline: the oracle (port of the reference) from the same warm state, bounded sample -----------------
-    cpu = cpu_baseline_from(A, params, boundary, warm_state, budget_s=args.cpu_budget)
-    sim.close()
+    cpu = cpu_baseline_from(A, base, boundary, split, warm_state, warm_step_number, budget_s=args.cpu_budget) if args.cpu_budget > 0 else None
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
-        "ms_per_step": dev_ms / max(K, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dev_ms / max(K, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: 2D dam-break, uniform h, 999292 particles, HybridDFSPH (default-scene-web block at "
-                               f"spacing 1.122e-3, {DROP_GAP} above the floor; default-config with merging/sharing/splitting off, level_estimation None), "
-                               f"state at t = {args.preroll_time} s (the block has landed: both pressure solves iterate)",
-                   "particles": n, "preroll_steps": pre_steps, "preroll_time_s": args.preroll_time, "replay_window_steps": window, "failed_steps_replayed": restarts, "l2": "working set per step (neighbour lists + SoA, ~400 MB) exceeds the 126 MB L2; no flush",
-                   "avg_div_sweeps": sweeps_div / max(K, 1), "avg_density_sweeps": sweeps_den / max(K, 1),
-                   "timing": "CUDA events on the library stream around every step (PerformanceCounters 'simulation-step')",
-                   "wall_ms_per_step": wall * 1e3 / max(K, 1), "phase_ms_per_step": phases,
-                   "particle_sweeps_per_s": particle_sweeps_per_s,
-                   "switches": {k: os.environ[k] for k in ("ASPH_ROWS4", "ASPH_BULK", "ASPH_SWEEP_GRID", "ASPH_UNVERIFIED_MODES") if k in os.environ}},
-        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+        "config": dict({"workload": workload_name(n0), "particles_initial": n0, "preroll_steps": PREROLL_STEPS, "preroll_wall_s": t_pre,
+                        "l2": "working set per step (neighbour lists + SoA, > 1 GB) exceeds the 126 MB L2; no flush",
+                        "timing": "CUDA events on the library stream around every step (PerformanceCounters 'simulation-step': physics + resampling)",
+                        "wall_ms_per_step": wall * 1e3 / max(K, 1), "phase_ms_per_step": phases, "simulated_time": sim_time,
+                        "kernels": tab, "switches": {k: os.environ[k] for k in ("ASPH_BULK", "ASPH_SWEEP_GRID", "ASPH_BENCH_SPACING", "ASPH_BENCH_PREROLL") if k in os.environ}}, **sm),
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "step_roofline": step_roof, "cpu_baseline": cpu,
     }
-    out.update(extra)
-    log = os.environ.get("ASPH_BENCH_LOG")
-    if log:
-        with open(log, "w") as f:
-            json.dump({"per_step": per_step}, f)
-    if not args.no_experiments and not any(k in os.environ for k in ("ASPH_ROWS4", "ASPH_SWEEP_GRID", "ASPH_BULK")):
-        run_experiments(args, out)
+    if not args.no_secondary:
+        try:
+            out["secondary"] = {"configs1_uniform_1m": uniform_line(A, lib, peak)}
+        except Exception as e:  # informational: never at the cost of the line
+            out["secondary"] = {"configs1_uniform_1m": {"error": repr(e)[:300]}}
+    out["bench_wall_s"] = time.perf_counter() - t_start
     print(json.dumps(out), flush=True)
 
 
-_children = []
+def uniform_line(A, lib, peak, steps=12, warmup=3):
+    """BASELINE configs[1] (2-D dam break, uniform h, 999 292 particles, HybridDFSPH; the headline of round 1) beside the
+    headline: the regime in which both pressure solves iterate, i.e. the sweep kernels' own numbers."""
+    params = uniform_params(A)
+    scene = dam_break(A, SPACING_1M)
+    pos, vel, mass = A.scene_particles(scene)
+    n = len(mass)
+    sim = A.FluidSimulation(params, pos, vel, mass, A.scene_boundary(scene, "AnalyticOverestimate"), counters_enabled=True, lib=lib)
+    pre = preroll(sim, PREROLL_T)
+    for _ in range(warmup):
+        sim.single_step()
+    sim.set_kernel_timing(1)
+    dev_ms, log = 0.0, StepLog()
+    for _ in range(steps):
+        c0 = sim.counters()["simulation-step"][0]
+        sim.single_step()
+        dev_ms += sim.counters()["simulation-step"][0] - c0
+        log.add(sim)
+    kt = sim.kernel_timing()
+    sim.close()
+    sm = log.summary()
+    value = n * steps / (dev_ms * 1e-3)
+    b_step = 260.0 + 68.0 * (sm["avg_div_sweeps"] + sm["avg_density_sweeps"])
+    return {"workload": f"configs[1]: 2D dam-break, uniform h, {n} particles, HybridDFSPH, state at t = {PREROLL_T} s ({pre} untimed steps)",
+            "value": value, "unit": UNIT, "ms_per_step": dev_ms / steps, "steps": steps, "avg_div_sweeps": sm["avg_div_sweeps"],
+            "avg_density_sweeps": sm["avg_density_sweeps"], "particle_sweeps_per_s": value * (sm["avg_div_sweeps"] + sm["avg_density_sweeps"]),
+            "kernels": kernel_table(kt, steps, n, peak),
+            "step_roofline": {"bytes_per_particle_step": b_step, "achieved": b_step * value / 1e9, "frac": b_step * value / 1e9 / peak}}
 
 
-def _run_child(cmd, limit_s, env=None):
-    """A child process in its own process group, killed as a group when its time is up (a hung kernel must not outlive it)."""
-    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=ROOT, start_new_session=True)
-    _children.append(p)
-    try:
-        so, se = p.communicate(timeout=limit_s)
-    except subprocess.TimeoutExpired:
-        _kill_group(p)
-        so, se = p.communicate()
-        return None, so, (se or "") + f"\n[killed after {limit_s} s]"
-    finally:
-        _children.remove(p)
-    return p.returncode, so, se
-
-
-def _kill_group(p):
-    try:
-        os.killpg(p.pid, signal.SIGKILL)
-    except (OSError, ProcessLookupError):
-        pass
-
-
-def run_experiments(args, out):
-    """The legs reported under "experiments": they start after the measurement proper is complete and run in child
-    processes, so nothing that happens there can change the reported numbers; should the bench itself be told to stop
-    (SIGTERM / SIGINT from an impatient caller) while one of them runs, the measured line is printed at once."""
-    out["experiments"] = exp = {}
-
-    def bail(signum, _frame):
-        for p in list(_children):
-            _kill_group(p)
-        exp["interrupted"] = f"signal {signum} during the experiment legs; the measurement above was complete"
-        sys.stdout.write(json.dumps(out) + "\n")
-        sys.stdout.flush()
-        os._exit(0)
-
-    old = {s: signal.signal(s, bail) for s in (signal.SIGTERM, signal.SIGINT)}
-    try:
-        t_exp = time.perf_counter()
-        exp["rows4"] = experiment_rows4(args, out)
-        if time.perf_counter() - t_exp < 45:
-            exp["bulk"] = experiment_switch(args, out, {"ASPH_BULK": "1"},
-                                            "interior tiles of the sweep kernels staged by cp.async.bulk + mbarrier (k_sweep_bulk; not the default: no parity run on hardware yet)",
-                                            steps=16, limit_s=60)
-        if time.perf_counter() - t_exp < 60 and "error" not in exp.get("bulk", {"error": 1}) and "error" not in exp["rows4"]:
-            exp["rows4_bulk"] = experiment_switch(args, out, {"ASPH_ROWS4": "1", "ASPH_BULK": "1"}, "both experiments together", steps=16, limit_s=60)
-        for per_sm in (2, 3):
-            if time.perf_counter() - t_exp < 75 + 20 * (per_sm - 2):
-                exp[f"sweep_grid_{per_sm}_per_sm"] = experiment_occupancy(args, out, per_sm)
-        # the adaptive workloads of BASELINE.json that the headline metric is not quoted on (default kernels; one GPU)
-        for key, spacing, warm, steps, limit in (("adaptive_4m_configs2", 5.612e-4, 60, 40, 120), ("adaptive_16m_north_star", 2.806e-4, 20, 10, 150)):
-            if time.perf_counter() - t_exp > 120:
-                exp[key] = {"skipped": "experiment time budget used up"}
-                continue
-            exp[key] = experiment_adaptive(spacing, warm, steps, limit)
-        exp["seconds"] = time.perf_counter() - t_exp
-    finally:
-        for s, h in old.items():
-            signal.signal(s, h)
-
-
-def experiment_switch(args, base, env, what, steps=None, limit_s=90):
-    """The same workload in a separate process with library switches set in its environment, after the measurement above
-    is complete.  Reported beside it under "experiments", never as `value`."""
-    k = steps or max(4, min(args.steps, 32))
-    cmd = [sys.executable, os.path.abspath(__file__), "--steps", str(k), "--warmup", str(args.warmup), "--cpu-budget", "0",
-           "--preroll-time", str(args.preroll_time), "--no-experiments"]
-    try:
-        rc, so, se = _run_child(cmd, limit_s, env=dict(os.environ, **env))
-        line = [l for l in (so or "").splitlines() if l.startswith("{")]
-        if rc != 0 or not line:
-            return {"error": (se or so or "")[-300:], "returncode": rc}
-        r = json.loads(line[-1])
-        return {"what": what, "switches": env,
-                "value": r["value"], "ms_per_step": r["ms_per_step"], "steps": r["steps"],
-                "avg_div_sweeps": r["config"]["avg_div_sweeps"], "avg_density_sweeps": r["config"]["avg_density_sweeps"],
-                "particle_sweeps_per_s": r["config"]["particle_sweeps_per_s"], "jacobi_pass_ms": r["roofline"].get("avg_launch_ms"), "accel_pass_ms": (r.get("roofline_accel") or {}).get("avg_launch_ms"),
-                "baseline_jacobi_pass_ms": base["roofline"].get("avg_launch_ms"),
-                "baseline_particle_sweeps_per_s": base["config"]["particle_sweeps_per_s"]}
-    except Exception as e:  # a malformed line must not cost the bench its result
-        return {"error": repr(e)[:300]}
-
-
-def experiment_rows4(args, base):
-    """A/B of the experimental sweep schedule (ASPH_ROWS4=1)."""
-    return experiment_switch(args, base, {"ASPH_ROWS4": "1"},
-                             "own row last in the neighbour lists, sweep kernels in steps of 4 rows (not the default: no parity run on hardware yet)")
-
-
-def experiment_occupancy(args, base, blocks_per_sm):
-    """Sensitivity of the default sweep kernels to resident blocks per SM (ASPH_SWEEP_GRID caps the persistent grid; the
-    default is 4 per SM with uniform h): how much of a pass is latency hidden by occupancy — an input for the next kernel
-    design, not a candidate default."""
-    sm = 148
-    try:
-        import torch
-        sm = torch.cuda.get_device_properties(0).multi_processor_count
-    except Exception:
-        pass
-    return experiment_switch(args, base, {"ASPH_SWEEP_GRID": str(sm * blocks_per_sm)},
-                             f"default sweep kernels with the persistent grid capped at {blocks_per_sm} blocks per SM ({sm} SMs)", steps=8, limit_s=60)
-
-
-def experiment_adaptive(spacing, warmup, steps, limit_s):
-    """tools/bench_adaptive.py in a separate process: the adaptive dam break (level set + share / merge / split every step)."""
-    cmd = [sys.executable, os.path.join(ROOT, "tools", "bench_adaptive.py"), "--spacing", repr(spacing), "--warmup", str(warmup), "--steps", str(steps)]
-    try:
-        rc, so, se = _run_child(cmd, limit_s)
-        line = [l for l in (so or "").splitlines() if l.startswith("{")]
-        if not line:
-            return {"error": (se or so or "")[-300:], "returncode": rc}
-        return json.loads(line[-1])
-    except Exception as e:
-        return {"error": repr(e)[:300]}
-
-
-def cpu_baseline_from(A, params, boundary, state, budget_s):
+def load_oracle(A):
     oracle_path = os.path.join(ROOT, "oracle", "liboracle_f32.so")
     if not os.path.exists(oracle_path):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j", "2"], stdout=subprocess.DEVNULL)
     olib = A.load_library(oracle_path)
     olib.oracle_max_threads.restype = C.c_int
-    cores = int(olib.oracle_max_threads())
-    o = A.FluidSimulation(params, state[0], state[1], state[2], boundary, lib=olib)
+    return olib, int(olib.oracle_max_threads())
+
+
+def cpu_baseline_from(A, params, boundary, split, state, step_number, budget_s, max_steps=200):
+    """The CPU oracle stepping the SAME state with the same parameters: whole steps until the time budget is used."""
+    olib, cores = load_oracle(A)
+    o = A.FluidSimulation(params, state[0], state[1], state[2], boundary, split, lib=olib)
+    o.lib.asph_set_step_number(o._h, step_number)
     t0 = time.perf_counter()
-    ps, steps = 0, 0
-    while steps < 2 or (time.perf_counter() - t0) < budget_s:
-        o.single_step()
-        ps += o.step_info()["n_particles_begin"]
-        steps += 1
-        if steps >= 200:
-            break
+    log = StepLog()
+    while len(log.n) < 1 or ((time.perf_counter() - t0) < budget_s and len(log.n) < max_steps):
+        o.single_step(params)
+        log.add(o)
     el = time.perf_counter() - t0
     o.close()
-    return {"value": ps / el, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{steps} steps of the same 999292-particle workload from the post-warm-up state ({el:.1f} s of CPU time, "
-                      f"OpenMP over particles, serial phases as in the reference)"}
+    sm = log.summary()
+    return {"value": float(sum(log.n)) / el, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(log.n)} whole steps of the same {len(state[2])}-particle state (post-warm-up), same parameters: {el:.1f} s of CPU time, "
+                      f"OpenMP over particles, serial phases as in the reference; sweeps div {sm['avg_div_sweeps']:.1f} density {sm['avg_density_sweeps']:.1f} "
+                      f"level {sm['avg_level_sweeps']:.0f}",
+            "work": sm}
 
 
 def run_reference(args):
-    """The reference arm: the reference's CPU implementation of the path.  The Rust crate cannot be built here
-    (no cargo/rustc), so this is the oracle port (kind 'port'), all host threads, on a bounded sample."""
+    """The reference arm: the reference's CPU implementation of the path on the SAME workload.  The Rust crate cannot be
+    built here (no cargo/rustc), so this is the oracle port (kind 'port') with all host threads.  Its input state — the
+    scene after the untimed pre-roll and the warm-up steps — is prepared exactly as in our arm (input preparation runs on
+    the GPU library when a GPU is present: 120 steps of 16 M particles take the CPU hours; nothing of it is timed);
+    the timed steps are whole steps of that state, as many of the K asked for as fit --ref-budget seconds."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -475,64 +442,71 @@ def run_reference(args):
     except AttributeError:
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import asph_b200 as A
-    oracle_path = os.path.join(ROOT, "oracle", "liboracle_f32.so")
-    if not os.path.exists(oracle_path):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j", "2"], stdout=subprocess.DEVNULL)
-    olib = A.load_library(oracle_path)
-    olib.oracle_max_threads.restype = C.c_int
-    cores = int(olib.oracle_max_threads())
-    params = uniform_params(A)
-    scene = dam_break(A, SPACING_C2, block_width=REF_SAMPLE_WIDTH)
-    pos, vel, mass = A.scene_particles(scene)
-    boundary = A.scene_boundary(scene, "AnalyticOverestimate")
-    o = A.FluidSimulation(params, pos, vel, mass, boundary, lib=olib)
+    olib, cores = load_oracle(A)
+    split = A.load_split_patterns_from_file()
+    spacing, prepared_by = SPACING, None
+    try:
+        lib = A.load_library()
+        base = adaptive_params(A, spacing)
+        scene = dam_break(A, spacing)
+        base = A.init_simulation_params(base, scene)
+        sim = A.init_fluid_sim(base, scene, split, lib=lib)
+        prepared_by = "the CUDA library (untimed input preparation, as in our arm)"
+    except Exception as e:  # no GPU: a scene the CPU can prepare itself in minutes (the configs[1] spacing)
+        spacing = max(SPACING, SPACING_1M)
+        base = adaptive_params(A, spacing)
+        scene = dam_break(A, spacing)
+        base = A.init_simulation_params(base, scene)
+        sim = A.init_fluid_sim(base, scene, split, lib=olib)
+        prepared_by = f"the CPU oracle itself at spacing {spacing:g} (no usable GPU for the full-size preparation: {str(e)[:80]})"
+    n0 = sim.num_fluid_particles()
     t_pre = time.perf_counter()
-    pre_steps = preroll(o, args.preroll_time)
-    t_pre = time.perf_counter() - t_pre
+    preroll_adaptive(sim, A, base, spacing)
     for _ in range(args.warmup):
-        o.single_step()
+        sim.single_step(base)
+    t_pre = time.perf_counter() - t_pre
+    state = (sim.get_field("position"), sim.get_field("velocity"), sim.get_field("mass"))
+    step_number = sim.step_number
+    boundary = A.scene_boundary(scene, base["init_boundary_handler"])
+    sim.close()
+    o = A.FluidSimulation(base, state[0], state[1], state[2], boundary, split, lib=olib)
+    o.lib.asph_set_step_number(o._h, step_number)
+    log = StepLog()
     t0 = time.perf_counter()
-    ps, done, sw_div, sw_den = 0, 0, 0, 0
     for _ in range(args.steps):
-        o.single_step()
-        info = o.step_info()
-        ps += info["n_particles_begin"]
-        sw_div += info["div_sweeps"]; sw_den += info["density_sweeps"]
-        done += 1
+        o.single_step(base)
+        log.add(o)
         if time.perf_counter() - t0 > args.ref_budget:
             break
     el = time.perf_counter() - t0
-    value = ps / el
-    sample = (f"{done} steps (of {args.steps} asked) of a {REF_SAMPLE_WIDTH}-wide slice of the same dam-break block (same spacing {SPACING_C2}, same "
-              f"column height; {len(mass)} particles = 1/4 of the GPU arm's), uniform h, HybridDFSPH, from t = {args.preroll_time} s "
-              f"({pre_steps} untimed pre-roll steps, {t_pre:.0f} s) + {args.warmup} warm-up steps; avg sweeps div {sw_div / max(done, 1):.1f} density {sw_den / max(done, 1):.1f}")
+    o.close()
+    done = len(log.n)
+    value = float(sum(log.n)) / el
+    sm = log.summary()
+    same = spacing == SPACING
+    sample = (f"{done} whole steps (of {args.steps} asked) of the {len(state[2])}-particle state the workload is in after {PREROLL_STEPS} pre-roll + {args.warmup} warm-up steps "
+              f"({n0} initial particles; prepared in {t_pre:.0f} s by {prepared_by}); all host threads, OpenMP over particles, serial phases as in the reference; "
+              f"sweeps div {sm['avg_div_sweeps']:.1f} density {sm['avg_density_sweeps']:.1f} level {sm['avg_level_sweeps']:.0f}")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done, "warmup": args.warmup,
-        "ms_per_step": el * 1e3 / max(done, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": el * 1e3 / max(done, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "configs[1] dam-break, bounded CPU sample (quarter-width slice of the block)", "particles": int(len(mass)),
-                   "preroll_steps": pre_steps, "preroll_time_s": args.preroll_time,
-                   "avg_div_sweeps": sw_div / max(done, 1), "avg_density_sweeps": sw_den / max(done, 1)},
+        "config": dict({"workload": workload_name(n0) if same else f"the same recipe at spacing {spacing:g} ({n0} initial particles): CPU-only box",
+                        "particles_initial": n0, "preroll_steps": PREROLL_STEPS, "same_config_as_our_arm": same}, **sm),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def run_ours_distributed(args, A, rank, world):
-    from bench_dist import run  # multi-GPU arm (slab decomposition + NCCL halos)
-    return run(args, A, rank, world)
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU time for the cpu_baseline leg")
-    ap.add_argument("--ref-budget", type=float, default=150.0, help="time cap of the reference arm's timed steps")
-    ap.add_argument("--preroll-time", type=float, default=PREROLL_T, help="simulated seconds the scene is advanced before warm-up (0 = the initial lattice)")
-    ap.add_argument("--no-experiments", action="store_true", help="skip the A/B legs reported under \"experiments\"")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU time for the cpu_baseline leg (0 = skip)")
+    ap.add_argument("--ref-budget", type=float, default=120.0, help="time cap of the reference arm's timed steps")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs[1] (uniform h, 1 M particles) line reported under \"secondary\"")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

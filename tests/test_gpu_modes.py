@@ -310,22 +310,30 @@ def test_bulk_copy_kernels_equal_per_thread_copy_kernels_bit_for_bit(asph, cuda_
         assert np.array_equal(out[0][k], out[1][k]), k
 
 
-def test_bulk_copy_kernels_adaptive_bit_for_bit(asph, cuda_lib, default_params, split_patterns, monkeypatch):
-    """The {h, m}-window instantiations: 8 steps of the adaptive mid-size dam break, with and without the bulk copies."""
+def test_bulk_copy_kernels_adaptive(asph, cuda_lib, default_params, split_patterns, monkeypatch):
+    """The {h, m}-window instantiations: 8 steps of the adaptive mid-size dam break, with and without the bulk copies.
+    With several size levels a step is not bit-reproducible from run to run (which columns get the slots of a crowded far
+    table is decided by the arrival order of an atomic, and with it the order of a few fp32 sums), so the two stage fills
+    are compared the way the step is compared with the oracle: same particle counts and resampling statistics every step,
+    positions within 1e-6 of the domain size."""
     spacing = 0.004
     sc = asph.SceneConfig.dam_break(spacing)
     r_f = float(np.sqrt(0.93 / np.pi) * spacing)
     params = default_params.replace(particle_radius_fine=r_f, particle_radius_base=4.0 * r_f, maximum_surface_distance=0.2)
     out = []
-    for flag in ("0", "1"):
+    for flag in ("1", "0"):
         monkeypatch.setenv("ASPH_BULK", flag)
         g = asph.init_fluid_sim(params, sc, split_patterns, lib=cuda_lib)
+        stats = []
         for _ in range(8):
             g.single_step()
-        out.append((g.num_fluid_particles(), g.get_field("position"), g.get_field("mass")))
+            i = g.step_info()
+            stats.append(tuple(i[k] for k in RESAMPLING_KEYS + ("div_sweeps", "density_sweeps", "level_sweeps")))
+        out.append((stats, g.get_field("position"), g.get_field("mass")))
         g.close()
     assert out[0][0] == out[1][0]
-    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+    assert _rel(out[0][1], out[1][1], 2.0) <= 1e-6
+    assert _rel(out[0][2], out[1][2]) <= 1e-6
 
 
 # ---- north star: 1e-5 relative after 100 steps ------------------------------------------------------------------------------
