@@ -53,9 +53,10 @@ __global__ void k_classify(uint32_t n, const float* __restrict__ level, const fl
   if (i < n) size_class[i] = classify_particle(level[i], mass[i], P);
 }
 
-__global__ void k_mass_sum(uint32_t n, const float* __restrict__ mass, double* out) {
+__global__ void k_mass_sum(uint32_t n, const float* __restrict__ mass, const uint32_t* __restrict__ refid, double* out) {
   double s = 0.0;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += double(mass[i]);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (!(refid[i] & ASPH_GHOST_BIT)) s += double(mass[i]);  // ghosts (multi-GPU) are counted by their owners
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
 }
@@ -90,6 +91,7 @@ __device__ __forceinline__ bool static_eligible(const AdaptArgs& A, const Packed
 
 __global__ void k_partner_ctl_reset(StepCtl* ctl) {
   ctl->work_n[0] = 0; ctl->work_n[1] = 0; ctl->ready_n = 0; ctl->rounds = 0; ctl->n_claims = 0; ctl->greedy_done = 0;
+  ctl->mail_sent = 0; ctl->greedy_barriers = 0; ctl->validate_why = 0;
 }
 
 // ---- the greedy partner search as one persistent cooperative kernel ------------------------------------------------
@@ -143,7 +145,7 @@ __device__ __forceinline__ uint32_t donor_loop(const AdaptArgs& A, const PackedP
     if (k < cn) {
       c.j = col.get(k);
       if (c.j != D.d && static_eligible(A, P, merging != 0, D.d, c.j, D.x, D.h, D.m)) {
-        c.ok = true; c.rid = A.refid[c.j]; c.m = A.mass[c.j]; c.tgt = target_mass(A.level[c.j], P);
+        c.ok = true; c.rid = A.refid[c.j] & ~ASPH_GHOST_BIT; c.m = A.mass[c.j]; c.tgt = target_mass(A.level[c.j], P);
       }
     }
     return c;
@@ -180,8 +182,23 @@ __device__ __forceinline__ uint32_t donor_loop(const AdaptArgs& A, const PackedP
   return count;
 }
 
+// ---- several GPUs (PEER): the search runs over the slabs of all ranks at once --------------------------------------
+// Every rank examines and decides the donors it OWNS; its ghost zone is two pair supports wide (capi.cu), so the touch
+// set of an owned donor and every donor that can touch it are present, as owned particles or as ghosts.  What a rank
+// decides about a border particle is mailed to the ghost copies (CoopPeer, sim.cuh): the donor state and offered mass
+// after phase I-b, and after every round's phase B the decided donors (state, partner, counter) and the claimed
+// receivers; a claim on a ghost goes to the rank that owns the receiver, which also wakes the donors waiting for it.
+// One cross-GPU barrier per round delivers the mail and tells every rank whether any rank has work or mail left.
+// A donor blocked by a ghost cannot sleep on it (the wake-up would come from another GPU): it is examined again next round.
+enum { MAIL_INFO = 0, MAIL_DROP = 1, MAIL_PARTNER = 2, MAIL_COUNTER = 3, MAIL_CLAIM = 4 };
+constexpr uint32_t CLAIMED_ELSEWHERE = 0xFFFFFFFDu;  // partner of a ghost whose donor is not present on this rank
+constexpr uint32_t kSlotMask = 0x0FFFFFFFu;
+
+__device__ __forceinline__ uint32_t rid_of(const AdaptArgs& A, uint32_t i) { return A.refid[i] & ~ASPH_GHOST_BIT; }
+
+template <bool PEER>
 __global__ void __launch_bounds__(kGreedyThreads)
-k_greedy(const GreedyArgs G, const PackedParams P) {
+k_greedy(const GreedyArgs G, const PackedParams P, const CoopPeer C) {
   cg::grid_group grid = cg::this_grid();
   const AdaptArgs& A = G.A;
   StepCtl* ctl = G.ctl;
@@ -191,6 +208,25 @@ k_greedy(const GreedyArgs G, const PackedParams P) {
   const int merging = G.merging;
   volatile uint32_t* work_n = ctl->work_n;
   volatile uint32_t* ready_n = &ctl->ready_n;
+  unsigned int bar = C.seq0 + 1u;  // PEER: number of the next cross-GPU barrier; mail posted before it uses its parity
+
+  auto is_ghost = [&](uint32_t i) { return PEER && nb_ghost(__ldg(&A.L.cnt[i])); };
+  // one message to the neighbour on `side` (0 = rank - 1)
+  auto mail = [&](int side, uint32_t slot, uint32_t kind, uint32_t payload) {
+    const uint32_t par = bar & 1u;
+    const uint32_t k = atomicAdd_system(&C.nb_ctl[side]->mbox_n[par][1 - side], 1u);
+    if (k < C.mbox_cap) C.nb_mbox[side][size_t(par * 2u + uint32_t(1 - side)) * C.mbox_cap + k] = make_uint2(slot | (kind << 28), payload);
+    else atomicOr(&ctl->error_flags, ERRF_PEER_TIMEOUT);
+    ctl->mail_sent = bar;
+  };
+  // what the ghost copies of owned particle i have to hear
+  auto mail_copies = [&](uint32_t i, uint32_t kind, uint32_t payload) {
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+      const uint32_t sl = __ldg(&C.rslot[side][i]);
+      if (sl != 0xffffffffu && C.nb_mbox[side]) mail(side, sl, kind, payload);
+    }
+  };
 
   // ---- phase I-a: reset the per-particle state, collect the donors (find_*_partner_sequential resets partner / counter)
   for (uint32_t i0 = gtid - lane; i0 < n; i0 += gthreads) {
@@ -198,7 +234,8 @@ k_greedy(const GreedyArgs G, const PackedParams P) {
     bool donor = false;
     if (i < n) {
       A.partner[i] = AVAILABLE; A.counter[i] = 0; G.head[i] = NONE_; G.info[i] = 0u; G.resume[i] = 0u;
-      donor = A.size_class[i] == G.donor_class;
+      donor = A.size_class[i] == G.donor_class && !is_ghost(i);
+      if (PEER && A.size_class[i] == G.donor_class && !donor) G.info[i] = GI_PENDING;  // a ghost donor: pending until its owner says otherwise
     }
     const unsigned int mask = __ballot_sync(0xffffffffu, donor);
     if (mask) {
@@ -217,17 +254,20 @@ k_greedy(const GreedyArgs G, const PackedParams P) {
       const DonorRegs D = donor_regs(A, P, merging, G.dt, d);
       uint32_t mine;
       const uint32_t c = donor_loop<true>(A, P, merging, D, lane, mine, [](uint32_t) {});
-      if (lane == 0) { G.drop[d] = D.drop; G.info[d] = (c ? GI_PENDING : GI_DONE) | (min(c, 0xFFFFFFu) << 8); }
+      if (lane == 0) {
+        const uint32_t info = (c ? GI_PENDING : GI_DONE) | (min(c, 0xFFFFFFu) << 8);
+        G.drop[d] = D.drop; G.info[d] = info;
+        if (PEER) { mail_copies(d, MAIL_INFO, info); if (c) mail_copies(d, MAIL_DROP, __float_as_uint(D.drop)); }
+      }
     }
   }
-  grid.sync();
 
   // is x in the touch set of the lower donor y?  (x's own values are passed in: they are warp-uniform in the scan)
   auto touches = [&](uint32_t y, uint32_t info_y, uint32_t x, float mass_x, float target_x) {
     if (x == y) return true;
     const float my = A.mass[y];
     if (!static_eligible(A, P, merging != 0, y, x, A.pos[y], A.xyhm[y].z, my)) return false;
-    return mass_ok(mass_x, target_x, G.drop[y] / float(info_y >> 8), P);
+    return mass_ok(mass_x, target_x, (PEER ? __ldcg(G.drop + y) : G.drop[y]) / float(info_y >> 8), P);
   };
   // wake everything that waits for b: it goes into the next round's work list
   auto wake = [&](uint32_t b, uint32_t* __restrict__ out, uint32_t slot) {
@@ -240,18 +280,59 @@ k_greedy(const GreedyArgs G, const PackedParams P) {
       z = nz;
     }
   };
+  // PEER: fence, meet the other GPUs, take in their mail; returns whether any rank has work or mail outstanding
+  auto exchange = [&](uint32_t pout) {
+    __threadfence_system();
+    grid.sync();
+    if (gtid == 0) {
+      const unsigned int mine = (work_n[pout] > 0u ? 1u : 0u) | (*reinterpret_cast<volatile unsigned int*>(&ctl->mail_sent) == bar ? 2u : 0u);
+      const unsigned int all = coop_barrier(C, bar, mine, ctl);
+      *C.verdict = ((all & 3u) != 0u && !(all & 0x80000000u)) ? 1u : 0u;
+      __threadfence();
+    }
+    grid.sync();
+    const bool go = *reinterpret_cast<volatile unsigned int*>(C.verdict) != 0u;
+    const uint32_t par = bar & 1u;
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+      const uint32_t n_in = min(*reinterpret_cast<volatile unsigned int*>(&C.self->mbox_n[par][side]), C.mbox_cap);
+      const uint2* __restrict__ box = C.mbox + size_t(par * 2u + uint32_t(side)) * C.mbox_cap;
+      for (uint32_t e = gtid; e < n_in; e += gthreads) {
+        const uint2 m = __ldcg(box + e);
+        const uint32_t slot = m.x & kSlotMask;
+        switch (m.x >> 28) {
+          case MAIL_INFO: G.info[slot] = m.y; break;
+          case MAIL_DROP: G.drop[slot] = __uint_as_float(m.y); break;
+          case MAIL_PARTNER: A.partner[slot] = m.y; break;
+          case MAIL_COUNTER: A.counter[slot] = m.y; break;
+          case MAIL_CLAIM:  // one of my particles was claimed by a donor of the neighbour rank (m.y = that donor's ghost here)
+            A.partner[slot] = m.y;
+            wake(slot, G.work[pout], pout);
+            break;
+        }
+      }
+    }
+    grid.sync();
+    if (gtid == 0) { C.self->mbox_n[par][0] = 0u; C.self->mbox_n[par][1] = 0u; }  // next written two barriers from now
+    bar++;
+    return go;
+  };
+
+  bool go = true;
+  if (PEER) go = exchange(0u);  // the ghosts' donor states and offered masses; work list 0 is the first round's
+  else grid.sync();
 
   uint32_t ready_begin = 0;
   uint32_t round = 1;
   for (;; round++) {
     const uint32_t pin = (round - 1u) & 1u, pout = round & 1u;
     const uint32_t nw = work_n[pin];
-    if (nw == 0u) break;
-    if (round > n + 2u) {  // cannot happen (the lowest undecided donor is never blocked); do not hang if it does
+    if (PEER ? !go : nw == 0u) break;
+    if (round > (PEER ? 0x3fffffffu : n + 2u)) {  // cannot happen (the lowest undecided donor is never blocked); do not hang if it does
       if (gtid == 0) atomicOr(&ctl->error_flags, ERRF_PARTNER_VALIDATION);
       break;
     }
-    if (gtid == 0) { ctl->work_n[pout] = 0u; ctl->rounds = round; }
+    if (gtid == 0) ctl->rounds = round;
     // ---- phase A: examine (the state is frozen: nothing decides in this phase)
     for (uint32_t w = gwarp; w < nw; w += nwarps) {
       const uint32_t d = __ldcg(G.work[pin] + w);
@@ -262,6 +343,7 @@ k_greedy(const GreedyArgs G, const PackedParams P) {
         continue;
       }
       const DonorRegs D = donor_regs(A, P, merging, G.dt, d);
+      const uint32_t rid_d = D.rid & ~ASPH_GHOST_BIT;
       const uint32_t res = __ldcg(G.resume + d);
       const uint32_t cn = nb_cn(A.L.cnt[d]);
       const NbCol col(A.L, d);
@@ -278,7 +360,7 @@ k_greedy(const GreedyArgs G, const PackedParams P) {
           if (k < cx) {
             y = colx.get(k);
             const uint32_t iy = __ldcg(G.info + y);
-            hit = (iy & 0xffu) == GI_PENDING && A.refid[y] < D.rid && __ldcg(A.partner + y) == AVAILABLE && touches(y, iy, x, mass_x, target_x);
+            hit = (iy & 0xffu) == GI_PENDING && rid_of(A, y) < rid_d && __ldcg(A.partner + y) == AVAILABLE && touches(y, iy, x, mass_x, target_x);
           }
           const unsigned int m = __ballot_sync(0xffffffffu, hit);
           if (m) return __shfl_sync(0xffffffffu, y, __ffs(m) - 1);
@@ -307,55 +389,84 @@ k_greedy(const GreedyArgs G, const PackedParams P) {
         if (blocker == NONE_) {
           G.ready[atomicAdd(&ctl->ready_n, 1u)] = d;
         } else {
-          G.next[d] = atomicExch(G.head + blocker, d);
           G.resume[d] = at;
+          if (is_ghost(blocker)) G.work[pout][atomicAdd(&ctl->work_n[pout], 1u)] = d;  // no wake-up crosses GPUs: look again next round
+          else G.next[d] = atomicExch(G.head + blocker, d);
         }
       }
     }
     grid.sync();
     // ---- phase B: the ready donors decide (their touch sets are disjoint) and wake their waiters
     const uint32_t ready_end = *ready_n;
+    // a claimed receiver: its waiters wake up; on several GPUs its other copies hear of it
+    auto claimed = [&](uint32_t j, uint32_t d) {
+      wake(j, G.work[pout], pout);
+      if (!PEER) return;
+      if (is_ghost(j)) {  // to the owner: partner = this donor's ghost over there
+        const uint32_t os = __ldg(&C.owner_slot[j]);
+        const int side = int(os >> 31);
+        mail(side, os & kSlotMask, MAIL_CLAIM, __ldg(&C.rslot[side][d]));
+      } else {
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+          const uint32_t sl = __ldg(&C.rslot[side][j]);
+          if (sl == 0xffffffffu || !C.nb_mbox[side]) continue;
+          const uint32_t dd = __ldg(&C.rslot[side][d]);
+          mail(side, sl, MAIL_PARTNER, dd != 0xffffffffu ? dd : CLAIMED_ELSEWHERE);
+        }
+      }
+    };
     for (uint32_t w = ready_begin + gwarp; w < ready_end; w += nwarps) {
       const uint32_t d = __ldcg(G.ready + w);
       const DonorRegs D = donor_regs(A, P, merging, G.dt, d);
       uint32_t mine;
-      const uint32_t c = donor_loop<false>(A, P, merging, D, lane, mine, [&](uint32_t j) { if (lane == 0) wake(j, G.work[pout], pout); });
+      const uint32_t c = donor_loop<false>(A, P, merging, D, lane, mine, [&](uint32_t j) { if (lane == 0) claimed(j, d); });
       if (lane == 0) {
         A.counter[d] = c;
         G.info[d] = GI_DONE;
         if (c) atomicAdd(&ctl->n_claims, c);
+        if (PEER) {
+          mail_copies(d, MAIL_INFO, GI_DONE);
+          if (c) { mail_copies(d, MAIL_PARTNER, DELETE_); mail_copies(d, MAIL_COUNTER, c); }
+        }
       }
       const uint32_t c32 = min(c, 32u);
-      uint32_t b = lane < c32 ? mine : NONE_;
-      if (c32 < 32u && lane == c32) b = d;
-      if (b != NONE_) wake(b, G.work[pout], pout);
-      if (c32 == 32u && lane == 0) wake(d, G.work[pout], pout);
+      if (lane < c32) claimed(mine, d);
+      if (lane == (c32 & 31u)) wake(d, G.work[pout], pout);
     }
     ready_begin = ready_end;
-    grid.sync();
+    if (gtid == 0) ctl->work_n[pin] = 0u;  // consumed in phase A; it is the work list the round after next fills
+    if (PEER) go = exchange(pout);
+    else grid.sync();
   }
-  if (gtid == 0) ctl->greedy_done = 1;
+  if (gtid == 0) { ctl->greedy_done = 1; ctl->greedy_barriers = bar - (C.seq0 + 1u); }
 }
 
 // validate_share_partners particle_sharing.rs:113-150 / validate_merge_partners particle_merging.rs:230-268
 __global__ void __launch_bounds__(kThreads)
 k_validate(uint32_t n, AdaptArgs A, uint8_t donor_class, StepCtl* ctl) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  bool ok = true;
+  if (i >= n || nb_ghost(A.L.cnt[i])) return;  // a ghost's bookkeeping is its owner's business
+  int why = 0;  // which invariant broke (reported with the first offender: diagnostics only)
+  uint32_t seen = 0;
   const uint32_t c = A.counter[i], p = A.partner[i];
   if (c > 0) {
-    if (A.size_class[i] != donor_class || p != DELETE_) ok = false;
+    if (A.size_class[i] != donor_class) why = 1;
+    else if (p != DELETE_) why = 2;
     uint32_t c2 = 0;
     const uint32_t cn = nb_cn(A.L.cnt[i]);
     const NbCol col(A.L, i);
     for (uint32_t k = 0; k < cn; k++) if (A.partner[col.get(k)] == i) c2++;
-    if (c2 != c) ok = false;
+    if (c2 != c && !why) { why = 3; seen = c2; }
   } else {
-    if (p == DELETE_) ok = false;
-    else if (p != AVAILABLE && A.partner[p] != DELETE_) ok = false;
+    if (p == DELETE_) why = 4;
+    else if (p != AVAILABLE && p != 0xFFFFFFFDu && A.partner[p] != DELETE_) { why = 5; seen = A.partner[p]; }
   }
-  if (!ok) atomicOr(&ctl->error_flags, ERRF_PARTNER_VALIDATION);
+  if (why) {
+    if (atomicOr(&ctl->error_flags, ERRF_PARTNER_VALIDATION) == 0u || true) {
+      if (atomicCAS(&ctl->validate_why, 0u, uint32_t(why)) == 0u) { ctl->validate_at[0] = i; ctl->validate_at[1] = c; ctl->validate_at[2] = p; ctl->validate_at[3] = seen; }
+    }
+  }
 }
 
 // receivers absorb their share (particle_sharing.rs:164-211, particle_merging.rs:282-324).  A receiver has exactly one
@@ -363,7 +474,7 @@ k_validate(uint32_t n, AdaptArgs A, uint8_t donor_class, StepCtl* ctl) {
 __global__ void __launch_bounds__(kThreads)
 k_apply_receivers(uint32_t n, AdaptArgs A, const PackedParams P, int merging, float dt) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n || nb_ghost(A.L.cnt[i])) return;  // (the donor may be a ghost: its state arrived with the mail of the search)
   const uint32_t j = A.partner[i];
   if (j == AVAILABLE || j == DELETE_) return;
   const uint32_t cj = A.counter[j];
@@ -380,7 +491,7 @@ k_apply_receivers(uint32_t n, AdaptArgs A, const PackedParams P, int merging, fl
 __global__ void __launch_bounds__(kThreads)
 k_share_donors(uint32_t n, AdaptArgs A, const PackedParams P, float dt) {  // particle_sharing.rs:213-240
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n || nb_ghost(A.L.cnt[i])) return;
   if (A.partner[i] != DELETE_ || int(A.counter[i]) < P.min_share_partners) return;
   const float m = A.mass[i];
   A.mass[i] = m - dropped_mass_sharing(A.level[i], m, dt, P);
@@ -410,27 +521,27 @@ __global__ void k_holes(uint32_t n, const uint32_t* __restrict__ del_scan, uint3
   if (r < n_new && del_scan[r + 1] != del_scan[r]) holes[del_scan[r]] = r;
 }
 // survivors: those with reference index >= n_new fill the holes, highest index first; then compact in device order
-__global__ void k_compact(uint32_t n, const uint32_t* __restrict__ del_scan, const uint32_t* __restrict__ holes,
+// (n particles on this device, n_ref reference indices in all: the same number unless the fluid is spread over several GPUs)
+__global__ void k_compact(uint32_t n, uint32_t n_ref, const uint32_t* __restrict__ del_scan, const uint32_t* __restrict__ holes,
                           const uint32_t* __restrict__ keep_scan, const float2* __restrict__ pos, const float2* __restrict__ vel,
                           const float* __restrict__ mass, const float* __restrict__ level, const uint32_t* __restrict__ refid,
                           float2* __restrict__ pos_o, float2* __restrict__ vel_o, float* __restrict__ mass_o, float* __restrict__ level_o,
                           uint32_t* __restrict__ refid_o, StepCtl* ctl) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (i == 0) ctl->n_new = keep_scan[n];
   if (keep_scan[i + 1] == keep_scan[i]) return;
-  const uint32_t total_del = del_scan[n];
-  const uint32_t n_new = n - total_del;
-  uint32_t r = refid[i];
+  const uint32_t total_del = del_scan[n_ref];
+  const uint32_t n_new = n_ref - total_del;
+  uint32_t r = refid[i] & ~ASPH_GHOST_BIT;
   if (r >= n_new) {
-    const uint32_t k = (n - 1u - r) - (total_del - del_scan[r + 1]);  // survivors with a higher reference index
+    const uint32_t k = (n_ref - 1u - r) - (total_del - del_scan[r + 1]);  // survivors with a higher reference index
     r = holes[k];
   }
   const uint32_t o = keep_scan[i];
   pos_o[o] = pos[i]; vel_o[o] = vel[i]; mass_o[o] = mass[i]; level_o[o] = level[i]; refid_o[o] = r;
-  if (i == 0 || o == 0) ctl->n_new = n_new;
 }
 
-// ---- splitting (splitting.rs:19-81) ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t split_children(float level, float m, const PackedParams& P, int max_children, unsigned int* err) {
   const float tm = target_mass(level, P);
   const float rr = roundf(m / tm);
@@ -442,6 +553,65 @@ __device__ __forceinline__ uint32_t split_children(float level, float m, const P
   if (nc < 2u) { *err |= ERRF_SPLIT_CHILDREN; nc = 1u; }
   return nc;
 }
+// ---- several GPUs: the reference index space is shared by all ranks.  Every rank lists what it deletes / splits, the
+// lists are gathered (dist_allgather_list), and the dense per-index arrays above are built identically on every rank.
+__global__ void k_mark_deleted_dist(uint32_t n, AdaptArgs A, int min_partners, uint32_t* __restrict__ list, uint32_t* __restrict__ keep, StepCtl* ctl) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (i == 0) keep[n] = 0u;
+  if (nb_ghost(A.L.cnt[i])) { keep[i] = 0u; return; }  // the compaction drops this step's ghosts as well
+  const bool del = A.partner[i] == DELETE_ && int(A.counter[i]) >= min_partners;  // dropped_mass_merging == mass: nothing is left
+  keep[i] = del ? 0u : 1u;
+  if (del) list[atomicAdd(&ctl->list_n, 1u)] = A.refid[i];
+}
+// gathered[q * stride + k], k < counts[q] * words: `words` 32-bit words per entry, the first is a reference index
+__global__ void k_scatter_gathered(int ranks, uint32_t stride, int words, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ gathered,
+                                   uint32_t* __restrict__ dense) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t per = stride / uint32_t(words);
+  const uint32_t q = e / per, k = e - q * per;
+  if (q >= uint32_t(ranks) || k >= counts[q]) return;
+  const uint32_t* ent = gathered + size_t(q) * stride + size_t(k) * words;
+  dense[ent[0]] = words == 1 ? 1u : ent[1];
+}
+__global__ void k_split_count_dist(uint32_t n, AdaptArgs A, const PackedParams P, int max_children, uint32_t* __restrict__ list, StepCtl* ctl) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || nb_ghost(A.L.cnt[i]) || A.size_class[i] != ASPH_CLASS_TOO_LARGE) return;
+  unsigned int err = 0;
+  const uint32_t extra = split_children(A.level[i], A.mass[i], P, max_children, &err) - 1u;
+  if (err) atomicOr(&ctl->error_flags, err);
+  atomicAdd(&ctl->n_split_parents, 1u);
+  atomicAdd(&ctl->local_extra, extra);
+  const uint32_t k = atomicAdd(&ctl->list_n, 1u);
+  list[2 * k] = A.refid[i]; list[2 * k + 1] = extra;
+}
+// children of an owned parent: stored behind this rank's particles (any order: the next step sorts by cell and reference
+// index), numbered n_ref + (children of all parents with a lower reference index) + c - 1 as in the reference
+__global__ void k_split_apply_dist(uint32_t n, uint32_t n_ref, uint32_t cap, AdaptArgs A, const uint32_t* __restrict__ extra_scan, const PackedParams P,
+                                   int max_children, const int* __restrict__ split_off, const float* __restrict__ split_pos, float* __restrict__ level,
+                                   uint32_t* __restrict__ refid, StepCtl* ctl) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || nb_ghost(A.L.cnt[i]) || A.size_class[i] != ASPH_CLASS_TOO_LARGE) return;
+  unsigned int err = 0;
+  const float m = A.mass[i], lv = level[i];
+  const uint32_t nc = split_children(lv, m, P, max_children, &err);
+  if (nc < 2u) return;
+  const float* pat = split_pos + 2 * size_t(split_off[nc - 2u]);
+  const float radius = sqrtf((m / 1.0f) * ASPH_FRAC_1_PI_F);
+  const float child_mass = m / float(nc);
+  const float2 op = A.pos[i], ov = A.vel[i];
+  const uint32_t first_ref = n_ref + extra_scan[refid[i]];
+  const uint32_t base = atomicAdd(&ctl->n_new, nc - 1u);
+  for (uint32_t c = 0; c < nc; c++) {
+    const uint32_t t = (c == 0) ? i : base + (c - 1u);
+    if (t >= cap) return;
+    A.mass[t] = child_mass; A.vel[t] = ov; level[t] = lv;
+    A.pos[t] = make_float2(op.x + pat[2 * c] * radius, op.y + pat[2 * c + 1] * radius);
+    if (c > 0) refid[t] = first_ref + (c - 1u);
+  }
+}
+
+// ---- splitting (splitting.rs:19-81) ---------------------------------------------------------------------------------
 __global__ void k_split_count(uint32_t n, const uint8_t* __restrict__ size_class, const float* __restrict__ level,
                               const float* __restrict__ mass, const uint32_t* __restrict__ refid, const PackedParams P, int max_children,
                               uint32_t* __restrict__ extra_ref, StepCtl* ctl) {
@@ -557,11 +727,12 @@ int total_mass(asph_sim* sim, double* out) {
   double* acc = (double*)sim->scratch_f.p;
   CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(double), sim->stream));
   if (sim->n) {
-    k_mass_sum<<<std::max(1, sim->sm_count * 4), kThreads, 0, sim->stream>>>(sim->n, sim->mass[sim->cur].p, acc);
+    k_mass_sum<<<std::max(1, sim->sm_count * 4), kThreads, 0, sim->stream>>>(sim->n, sim->mass[sim->cur].p, sim->refid[sim->cur].p, acc);
     LAUNCH_CHECK();
   }
   CUDA_TRY(cudaMemcpyAsync(out, acc, sizeof(double), cudaMemcpyDeviceToHost, sim->stream));
   CUDA_TRY(cudaStreamSynchronize(sim->stream));
+  if (sim->dist) TRY(dist_allreduce_host(sim, out, 1, 1));  // the whole fluid, not this slab's share
   return ASPH_OK;
 }
 
@@ -587,10 +758,13 @@ int find_partners(asph_sim* sim, bool merging, float dt, uint32_t* claims) {
   const uint8_t donor_class = merging ? ASPH_CLASS_TOO_SMALL : ASPH_CLASS_LARGE;
   k_partner_ctl_reset<<<1, 1, 0, st>>>(sim->ctl);
   LAUNCH_CHECK();
-  if (sim->greedy_grid == 0) {  // co-resident blocks of the persistent kernel on this device
+  const bool peer = dist_p2p(sim);
+  int& co_resident = peer ? sim->greedy_grid_peer : sim->greedy_grid;
+  if (co_resident == 0) {  // co-resident blocks of the persistent kernel on this device
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_greedy, kGreedyThreads, 0));
-    sim->greedy_grid = std::max(1, std::min(per_sm, 2) * sim->sm_count);
+    if (peer) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_greedy<true>, kGreedyThreads, 0));
+    else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_greedy<false>, kGreedyThreads, 0));
+    co_resident = std::max(1, std::min(per_sm, 2) * sim->sm_count);
   }
   GreedyArgs G;
   G.A = args_of(sim);
@@ -598,11 +772,12 @@ int find_partners(asph_sim* sim, bool merging, float dt, uint32_t* claims) {
   G.work[0] = sim->work[0].p; G.work[1] = sim->work[1].p; G.ready = sim->cand.p;
   G.ctl = sim->ctl; G.n = n; G.merging = merging ? 1 : 0; G.dt = dt; G.donor_class = donor_class;
   PackedParams pp = sim->pp;
-  const uint32_t grid = uint32_t(std::max(1, std::min<int>(sim->greedy_grid, int((n + kGreedyThreads - 1) / kGreedyThreads))));
-  void* args[] = {&G, &pp};
+  CoopPeer coop = dist_coop_peer(sim);
+  const uint32_t grid = uint32_t(std::max(1, std::min<int>(co_resident, int((n + kGreedyThreads - 1) / kGreedyThreads))));
+  void* args[] = {&G, &pp, &coop};
   cudaEvent_t kt0 = nullptr, kt1 = nullptr;
   if (sim->kt_every > 0) { kt0 = kt_event(sim); kt1 = kt_event(sim); cudaEventRecord(kt0, st); }
-  CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_greedy, dim3(grid), dim3(kGreedyThreads), args, 0, st));
+  CUDA_TRY(cudaLaunchCooperativeKernel(peer ? (void*)k_greedy<true> : (void*)k_greedy<false>, dim3(grid), dim3(kGreedyThreads), args, 0, st));
   sim->kernel_launches++;
   if (kt1) cudaEventRecord(kt1, st);
   const AdaptArgs A = G.A;
@@ -615,9 +790,110 @@ int find_partners(asph_sim* sim, bool merging, float dt, uint32_t* claims) {
     kt_release(sim, kt0); kt_release(sim, kt1);
   }
   TRY(rc_sync);
+  if (peer) dist_coop_advance(sim, sim->ctl_host->greedy_barriers);  // the same number on every rank
+  if (sim->ctl_host->error_flags & ERRF_PEER_TIMEOUT) return check_error_flags(sim);
   if (!sim->ctl_host->greedy_done) { sim->last_error = "partner search did not terminate"; return ASPH_ERR_INVALID; }
   sim->adapt_rounds += sim->ctl_host->rounds;
-  *claims = sim->ctl_host->n_claims;
+  unsigned long long c = sim->ctl_host->n_claims;
+  if (sim->dist) TRY(dist_allreduce_host(sim, &c, 1, 0));  // every rank reports (and branches on) the claims of the whole fluid
+  *claims = uint32_t(c);
+  return ASPH_OK;
+}
+
+// ---- several GPUs: deletion and splitting in the reference-index space all ranks share ------------------------------
+int merge_compact_dist(asph_sim* sim, const AdaptArgs& A, int min_partners) {
+  cudaStream_t st = sim->stream;
+  const uint32_t n = sim->n, blocks = (n + kThreads - 1) / kThreads;
+  const uint32_t n_ref = uint32_t(dist_n_global(sim));
+  uint32_t* list = sim->scratch_u[0].p;   // reference indices this rank deletes
+  uint32_t* keep = sim->scratch_u[1].p;   // n + 1
+  CUDA_TRY(cudaMemsetAsync(&sim->ctl->list_n, 0, sizeof(uint32_t), st));
+  k_mark_deleted_dist<<<blocks, kThreads, 0, st>>>(n, A, min_partners, list, keep, sim->ctl);
+  LAUNCH_CHECK();
+  TRY(sync_ctl(sim));
+  const uint32_t* gathered = nullptr; const uint32_t* counts = nullptr;
+  uint32_t stride = 0; unsigned long long total = 0;
+  TRY(dist_allgather_list(sim, list, sim->ctl_host->list_n, 1, &gathered, &counts, &stride, &total));
+  if (total == 0) return ASPH_OK;  // every donor found fewer partners than minimum_merge_partners: nothing is removed anywhere
+  uint32_t *del_ref = nullptr, *holes = nullptr;
+  TRY(dist_ref_buffers(sim, size_t(n_ref) + 1, &del_ref, &holes));
+  CUDA_TRY(cudaMemsetAsync(del_ref, 0, (size_t(n_ref) + 1) * sizeof(uint32_t), st));
+  const int R = dist_ranks(sim);
+  k_scatter_gathered<<<(uint32_t(R) * stride + kThreads - 1) / kThreads, kThreads, 0, st>>>(R, stride, 1, counts, gathered, del_ref);
+  LAUNCH_CHECK();
+  CUDA_TRY(cudaMemcpyAsync(&sim->ctl->n_new, &n_ref, sizeof(uint32_t), cudaMemcpyHostToDevice, st));  // scan lengths
+  TRY(launch_exclusive_scan(sim, del_ref, del_ref, &sim->ctl->n_new, 1, n_ref + 1));
+  CUDA_TRY(cudaMemcpyAsync(&sim->ctl->n_new, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  TRY(launch_exclusive_scan(sim, keep, keep, &sim->ctl->n_new, 1, n + 1));
+  k_holes<<<(n_ref + kThreads - 1) / kThreads, kThreads, 0, st>>>(n_ref, del_ref, holes);
+  LAUNCH_CHECK();
+  const int c = sim->cur;
+  k_compact<<<blocks, kThreads, 0, st>>>(n, n_ref, del_ref, holes, keep, sim->pos[c].p, sim->vel[c].p, sim->mass[c].p, sim->level[c].p,
+                                         sim->refid[c].p, sim->pos[1 - c].p, sim->vel[1 - c].p, sim->mass[1 - c].p, sim->level[1 - c].p,
+                                         sim->refid[1 - c].p, sim->ctl);
+  LAUNCH_CHECK();
+  TRY(sync_ctl(sim));
+  TRY(check_error_flags(sim));
+  sim->lists_valid = false; sim->step_fields_valid = false;  // this step's ghosts are gone as well
+  sim->cur = 1 - c;
+  sim->n = sim->ctl_host->n_new; sim->n_owned = sim->n;
+  dist_set_n_global(sim, uint64_t(n_ref) - total);
+  return ASPH_OK;
+}
+
+int split_dist(asph_sim* sim) {
+  cudaStream_t st = sim->stream;
+  const PackedParams& P = sim->pp;
+  const uint32_t n = sim->n, blocks = (n + kThreads - 1) / kThreads;
+  const uint32_t n_ref = uint32_t(dist_n_global(sim));
+  uint32_t* list = sim->scratch_u[0].p;  // (reference index, extra children) per parent: 2 words, at most n / 2 parents fit... a parent is one of n particles
+  TRY(classify(sim));
+  CUDA_TRY(cudaMemsetAsync(&sim->ctl->n_split_parents, 0, sizeof(uint32_t), st));
+  CUDA_TRY(cudaMemsetAsync(&sim->ctl->list_n, 0, sizeof(uint32_t), st));
+  CUDA_TRY(cudaMemsetAsync(&sim->ctl->local_extra, 0, sizeof(uint32_t), st));
+  {
+    const AdaptArgs A = args_of(sim);
+    k_split_count_dist<<<blocks, kThreads, 0, st>>>(n, A, P, sim->max_children, reinterpret_cast<uint32_t*>(sim->scratch_f.p), sim->ctl);
+    LAUNCH_CHECK();
+  }
+  TRY(sync_ctl(sim));
+  TRY(check_error_flags(sim));
+  unsigned long long parents = sim->ctl_host->n_split_parents;
+  TRY(dist_allreduce_host(sim, &parents, 1, 0));
+  sim->info.n_split_parents = int(parents);
+  const uint32_t local_extra = sim->ctl_host->local_extra, n_parents_local = sim->ctl_host->list_n;
+  (void)list;
+  const uint32_t* gathered = nullptr; const uint32_t* counts = nullptr;
+  uint32_t stride = 0; unsigned long long total = 0;
+  TRY(dist_allgather_list(sim, reinterpret_cast<uint32_t*>(sim->scratch_f.p), n_parents_local, 2, &gathered, &counts, &stride, &total));
+  if (total == 0) return ASPH_OK;
+  // the gathered buffers and the dense arrays live in the distributed state: growing the particle arrays keeps them
+  if (uint64_t(n) + local_extra > sim->cap) {
+    TRY(ensure_capacity(sim, uint32_t(std::min<uint64_t>(uint64_t(n) + local_extra + (uint64_t(n) + local_extra) / 4 + 1024, 0x7FFFFFF0ull))));
+    TRY(ensure_greedy_buffers(sim));
+    TRY(classify(sim));  // size_class was reallocated
+  }
+  uint32_t *extra_ref = nullptr, *unused = nullptr;
+  TRY(dist_ref_buffers(sim, size_t(n_ref) + 1, &extra_ref, &unused));
+  CUDA_TRY(cudaMemsetAsync(extra_ref, 0, (size_t(n_ref) + 1) * sizeof(uint32_t), st));
+  const int R = dist_ranks(sim);
+  k_scatter_gathered<<<(uint32_t(R) * (stride / 2u) + kThreads - 1) / kThreads, kThreads, 0, st>>>(R, stride, 2, counts, gathered, extra_ref);
+  LAUNCH_CHECK();
+  CUDA_TRY(cudaMemcpyAsync(&sim->ctl->n_new, &n_ref, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  TRY(launch_exclusive_scan(sim, extra_ref, extra_ref, &sim->ctl->n_new, 1, n_ref + 1));
+  CUDA_TRY(cudaMemcpyAsync(&sim->ctl->n_new, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, st));  // children are stored from here on
+  const int c = sim->cur;
+  const AdaptArgs A = args_of(sim);
+  k_split_apply_dist<<<blocks, kThreads, 0, st>>>(n, n_ref, sim->cap, A, extra_ref, P, sim->max_children, sim->split_off.p, sim->split_pos.p,
+                                                  sim->level[c].p, sim->refid[c].p, sim->ctl);
+  LAUNCH_CHECK();
+  uint32_t total_extra = 0;
+  CUDA_TRY(cudaMemcpyAsync(&total_extra, extra_ref + n_ref, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  TRY(sync_ctl(sim));
+  TRY(check_error_flags(sim));
+  sim->lists_valid = false; sim->step_fields_valid = false;
+  sim->n = sim->ctl_host->n_new; sim->n_owned += local_extra;
+  dist_set_n_global(sim, uint64_t(n_ref) + total_extra);
   return ASPH_OK;
 }
 
@@ -628,6 +904,8 @@ int launch_adaptivity(asph_sim* sim, float dt) {
   if (n0 == 0) return ASPH_OK;
   cudaStream_t st = sim->stream;
   TRY(ensure_greedy_buffers(sim));
+  // several GPUs: the ghosts' advected velocities (their positions came with the level smoothing's halo, level.cu)
+  if (sim->dist) TRY(dist_halo(sim, sim->vel[sim->cur].p, 8));
   double m1 = 0, m2 = 0;
   TRY(total_mass(sim, &m1));
   sim->adapt_rounds = 0;
@@ -668,6 +946,11 @@ int launch_adaptivity(asph_sim* sim, float dt) {
           LAUNCH_CHECK();
           cls_done = true;
         }
+      } else if (sim->dist) {
+        const AdaptArgs A = args_of(sim);
+        k_apply_receivers<<<(sim->n + kThreads - 1) / kThreads, kThreads, 0, st>>>(sim->n, A, P, 1, dt);
+        LAUNCH_CHECK();
+        TRY(merge_compact_dist(sim, A, P.min_merge_partners));
       } else {
       const uint32_t n = sim->n;
       const uint32_t blocks = (n + kThreads - 1) / kThreads;
@@ -688,7 +971,7 @@ int launch_adaptivity(asph_sim* sim, float dt) {
       k_holes<<<blocks, kThreads, 0, st>>>(n, del_ref, holes);
       LAUNCH_CHECK();
       const int c = sim->cur;
-      k_compact<<<blocks, kThreads, 0, st>>>(n, del_ref, holes, keep, sim->pos[c].p, sim->vel[c].p, sim->mass[c].p, sim->level[c].p,
+      k_compact<<<blocks, kThreads, 0, st>>>(n, n, del_ref, holes, keep, sim->pos[c].p, sim->vel[c].p, sim->mass[c].p, sim->level[c].p,
                                              sim->refid[c].p, sim->pos[1 - c].p, sim->vel[1 - c].p, sim->mass[1 - c].p, sim->level[1 - c].p,
                                              sim->refid[1 - c].p, sim->ctl);
       LAUNCH_CHECK();
@@ -711,6 +994,9 @@ int launch_adaptivity(asph_sim* sim, float dt) {
     }
   } else if (sim->split_enabled) {  // simulation.rs:2775-2788
     if (sim->max_children < 2) { sim->last_error = "splitting enabled but no split patterns were given"; return ASPH_ERR_INVALID; }
+    if (sim->dist) {
+      TRY(split_dist(sim));
+    } else {
     const uint32_t n = sim->n;
     const uint32_t blocks = (n + kThreads - 1) / kThreads;
     uint32_t n_new = n;
@@ -756,6 +1042,7 @@ int launch_adaptivity(asph_sim* sim, float dt) {
         LAUNCH_CHECK();
         cls_done = true;
       }
+    }
     }
   }
   if (track_cls && !cls_done && classified) {  // same particle set as the last classify

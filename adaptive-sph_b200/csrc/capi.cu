@@ -234,7 +234,13 @@ int check_error_flags(asph_sim* sim) {
   if (f & ERRF_PARTICLE_CAPACITY) { sim->last_error = "particle capacity exhausted by splitting"; return ASPH_ERR_CAPACITY; }
   if (f & ERRF_SPLIT_PATTERN) { sim->last_error = "no split pattern for a 1-to-n split"; return ASPH_ERR_INVALID; }
   if (f & ERRF_SPLIT_CHILDREN) { sim->last_error = "assert!(num_children > 1)"; return ASPH_ERR_INVALID; }
-  if (f & ERRF_PARTNER_VALIDATION) { sim->last_error = "validate_share_partners / validate_merge_partners failed"; return ASPH_ERR_INVALID; }
+  if (f & ERRF_PARTNER_VALIDATION) {
+    const StepCtl& c = *sim->ctl_host;
+    sim->last_error = "validate_share_partners / validate_merge_partners failed (invariant " + std::to_string(c.validate_why) + " at particle " +
+                      std::to_string(c.validate_at[0]) + ": counter " + std::to_string(c.validate_at[1]) + ", partner " + std::to_string(c.validate_at[2]) +
+                      ", found " + std::to_string(c.validate_at[3]) + "; rounds " + std::to_string(c.rounds) + ", n " + std::to_string(sim->n) + ")";
+    return ASPH_ERR_INVALID;
+  }
   sim->last_error = "device error flag " + std::to_string(f);
   return ASPH_ERR_INVALID;
 }
@@ -343,8 +349,11 @@ static int step_physics(asph_sim* sim, const asph_params* params, float* dt_out)
   // simulation.rs:2034-2057), so only N_2 is built.
   const float f_ext = lvl ? P.f_ext : P.f_near;
   if (sim->dist) {
-    if (lvl) { sim->last_error = "level estimation across GPU slabs"; return ASPH_ERR_UNSUPPORTED; }
-    int rc = dist_begin_step(sim, std::max(f_ext, P.f_near));  // migration + ghost exchange; sim->n = owned + ghosts
+    // Ghost zone: one support of the widest lists — two pair supports (4 h_max) when the step ends with share / merge: an
+    // owned donor must see every donor that can touch its touch set (adapt.cu, k_greedy)
+    float f_ghost = std::max(f_ext, P.f_near);
+    if (lvl && (params->sharing || params->merging)) f_ghost = std::max(f_ghost, 4.0f);
+    int rc = dist_begin_step(sim, f_ghost);  // migration + ghost exchange; sim->n = owned + ghosts
     if (rc != ASPH_OK) { pc_collect(sim); return rc; }
     sim->info.n_particles_begin = sim->n_owned;
     if (sim->n_owned == 0) {  // every collective below assumes all ranks take part
@@ -401,7 +410,7 @@ static int step_adaptivity(asph_sim* sim, const asph_params* params, float dt) {
     return ASPH_ERR_INVALID;
   }
   if (!any) return ASPH_OK;
-  if (sim->dist) { sim->last_error = "resampling across GPU slabs"; return ASPH_ERR_UNSUPPORTED; }
+  if (sim->dist && dist_ranks(sim) > 1 && !dist_p2p(sim)) { sim->last_error = "resampling across GPU slabs needs the peer-memory path (ASPH_DIST_P2P)"; return ASPH_ERR_UNSUPPORTED; }
   if (!sim->lists_valid || !sim->level_valid) {
     sim->last_error = "single_step_adaptivity needs the neighbour lists and level field of the preceding physics step";
     return ASPH_ERR_INVALID;
@@ -413,7 +422,7 @@ static int step_adaptivity(asph_sim* sim, const asph_params* params, float dt) {
   pc_end(sim, ASPH_PC_ADAPTIVITY);
   pc_end(sim, ASPH_PC_SIMULATION_STEP);
   pc_collect(sim);
-  sim->info.n_particles_end = sim->n;
+  sim->info.n_particles_end = sim->dist ? sim->n_owned : sim->n;
   return rc;
 }
 

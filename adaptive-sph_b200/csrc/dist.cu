@@ -123,6 +123,9 @@ struct DistState {
   DevBuf<uint32_t> owner_slot, owner_tmp;         // per local particle: a ghost's index on its owner rank (~0 otherwise)
   DevBuf<unsigned int> verdict;
   unsigned int coop_seq = 0;                      // cross-GPU barriers run so far (the same on every rank)
+  // resampling: lists gathered over all ranks, arrays over the shared reference index space
+  DevBuf<uint32_t> ag_send, ag_recv, ag_counts, ref_a, ref_b;
+  DevBuf<unsigned long long> red;
 };
 
 namespace {
@@ -616,9 +619,10 @@ __global__ void k_build_rslot(uint32_t ns0, uint32_t ns1, const uint32_t* __rest
   tile_border[i / ASPH_PAIR_BLOCK] = 1;
 }
 
-__global__ void k_scatter_words(uint32_t count, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ src, uint32_t* __restrict__ dst) {
+// owner_slot[ghost] = its index on the owning rank | side << 31 (side 1: the owner is rank + 1); ghosts arrive left part first
+__global__ void k_scatter_owner(uint32_t count, uint32_t n_left, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ src, uint32_t* __restrict__ dst) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < count) dst[idx[k]] = src[k];
+  if (k < count) dst[idx[k]] = src[k] | (k < n_left ? 0u : 0x80000000u);
 }
 
 }  // namespace
@@ -635,9 +639,10 @@ static int p2p_refresh(asph_sim* sim) {
   cudaStream_t st = sim->stream;
   P2PRecord mine;
   memset(&mine, 0, sizeof mine);
-  if (D->mbox_cap != D->cap_h || !D->mbox.p) {  // cap_h is the same on every rank (ensure_halo_capacity decisions are global)
-    CUDA_TRY(D->mbox.ensure(size_t(4) * D->cap_h));
-    D->mbox_cap = D->cap_h;
+  if (D->mbox_cap != 4u * D->cap_h || !D->mbox.p) {  // cap_h is the same on every rank (ensure_halo_capacity decisions are global)
+    D->mbox.release();                               // a round of the partner search mails at most four words per border particle
+    CUDA_TRY(D->mbox.ensure(size_t(4) * 4u * D->cap_h));
+    D->mbox_cap = 4u * D->cap_h;
   }
   mine.ptr[0] = sim->packA.p; mine.ptr[1] = sim->packP[0].p; mine.ptr[2] = sim->packP[1].p; mine.ptr[3] = D->mbox.p; mine.ctl = D->my_ctl;
   for (int k = 0; k < kPeerFields; k++) CUDA_TRY(cudaIpcGetMemHandle(&mine.h[k], mine.ptr[k]));
@@ -704,7 +709,7 @@ static int p2p_refresh(asph_sim* sim) {
   }
   CUDA_TRY(cudaMemsetAsync(D->owner_slot.p, 0xFF, size_t(sim->n) * sizeof(uint32_t), st));
   if (nr) {
-    k_scatter_words<<<(nr + kThreads - 1) / kThreads, kThreads, 0, st>>>(nr, D->recv_idx.p, D->owner_tmp.p, D->owner_slot.p);
+    k_scatter_owner<<<(nr + kThreads - 1) / kThreads, kThreads, 0, st>>>(nr, D->n_recv[0], D->recv_idx.p, D->owner_tmp.p, D->owner_slot.p);
     LAUNCH_CHECK();
   }
   const size_t tiles = (size_t(sim->cap) + ASPH_PAIR_BLOCK - 1) / ASPH_PAIR_BLOCK + 1;
@@ -786,6 +791,53 @@ const uint32_t* dist_ghost_index(asph_sim* sim, uint32_t* count) {
   return D ? D->recv_idx.p : nullptr;
 }
 
+int dist_ranks(asph_sim* sim) { return sim->dist ? sim->dist->nranks : 1; }
+uint64_t dist_n_global(asph_sim* sim) { return sim->dist ? sim->dist->n_global : sim->n; }
+void dist_set_n_global(asph_sim* sim, uint64_t n) { if (sim->dist) sim->dist->n_global = n; }
+
+int dist_allreduce_host(asph_sim* sim, void* host_values, int count, int is_double) {
+  DistState* D = sim->dist;
+  if (!D || D->nranks == 1) return ASPH_OK;
+  CUDA_TRY(D->red.ensure(size_t(std::max(count, 8))));
+  cudaStream_t st = sim->stream;
+  CUDA_TRY(cudaMemcpyAsync(D->red.p, host_values, size_t(count) * 8, cudaMemcpyHostToDevice, st));
+  NCCL_TRY(nccl().AllReduce(D->red.p, D->red.p, size_t(count), is_double ? ncclDouble : ncclUint64, ncclSum, D->comm, st));
+  CUDA_TRY(cudaMemcpyAsync(host_values, D->red.p, size_t(count) * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return ASPH_OK;
+}
+
+int dist_allgather_list(asph_sim* sim, const uint32_t* list, uint32_t n_entries, int words, const uint32_t** gathered, const uint32_t** counts,
+                        uint32_t* stride, unsigned long long* total) {
+  DistState* D = sim->dist;
+  const int R = D->nranks;
+  cudaStream_t st = sim->stream;
+  CUDA_TRY(D->ag_counts.ensure(size_t(R) + 1));
+  CUDA_TRY(cudaMemcpyAsync(D->ag_counts.p + R, &n_entries, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  NCCL_TRY(nccl().AllGather(D->ag_counts.p + R, D->ag_counts.p, 1, ncclUint32, D->comm, st));
+  std::vector<uint32_t> cnt_h(static_cast<size_t>(R));
+  CUDA_TRY(cudaMemcpyAsync(cnt_h.data(), D->ag_counts.p, size_t(R) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  uint32_t mx = 0;
+  unsigned long long tot = 0;
+  for (int q = 0; q < R; q++) { mx = std::max(mx, cnt_h[static_cast<size_t>(q)]); tot += cnt_h[static_cast<size_t>(q)]; }
+  *total = tot; *counts = D->ag_counts.p; *stride = mx * uint32_t(words); *gathered = nullptr;
+  if (tot == 0) return ASPH_OK;
+  const size_t per = size_t(mx) * size_t(words);
+  CUDA_TRY(D->ag_send.ensure(per)); CUDA_TRY(D->ag_recv.ensure(per * size_t(R)));
+  if (n_entries) CUDA_TRY(cudaMemcpyAsync(D->ag_send.p, list, size_t(n_entries) * words * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  NCCL_TRY(nccl().AllGather(D->ag_send.p, D->ag_recv.p, per, ncclUint32, D->comm, st));
+  *gathered = D->ag_recv.p;
+  return ASPH_OK;
+}
+
+int dist_ref_buffers(asph_sim* sim, size_t n, uint32_t** a, uint32_t** b) {
+  DistState* D = sim->dist;
+  CUDA_TRY(D->ref_a.ensure(n + n / 8 + 1024)); CUDA_TRY(D->ref_b.ensure(n + n / 8 + 1024));
+  *a = D->ref_a.p; *b = D->ref_b.p;
+  return ASPH_OK;
+}
+
 int dist_local_map(asph_sim* sim) {
   DistState* D = sim->dist;
   if (D->map_valid) return ASPH_OK;
@@ -818,7 +870,7 @@ void dist_destroy(asph_sim* sim) {
   for (int q = 0; q < D->nranks && q < ASPH_MAX_RANKS; q++) if (q != D->rank && D->peer_ctl[q]) cudaIpcCloseMemHandle(D->peer_ctl[q]);
   if (D->my_ctl) cudaFree(D->my_ctl);
   if (D->rec_host) cudaFreeHost(D->rec_host);
-  D->mbox.release(); D->owner_slot.release(); D->owner_tmp.release(); D->verdict.release(); D->remote_slot.release(); D->rec_dev.release(); D->peer_ctl_dev.release(); D->rslot[0].release(); D->rslot[1].release(); D->blocks_done.release(); D->tile_border.release();
+  D->ag_send.release(); D->ag_recv.release(); D->ag_counts.release(); D->ref_a.release(); D->ref_b.release(); D->red.release(); D->mbox.release(); D->owner_slot.release(); D->owner_tmp.release(); D->verdict.release(); D->remote_slot.release(); D->rec_dev.release(); D->peer_ctl_dev.release(); D->rslot[0].release(); D->rslot[1].release(); D->blocks_done.release(); D->tile_border.release();
   delete D;
   sim->dist = nullptr;
 }

@@ -130,8 +130,11 @@ __global__ void __launch_bounds__(kPropThreads)
 k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restrict__ level, int* __restrict__ stamp,
             uint32_t* __restrict__ front0, uint32_t* __restrict__ front1, StepCtl* ctl, float neg_dmax, int use_cutoff, const CoopPeer P) {
   cg::grid_group grid = cg::this_grid();
+  constexpr uint32_t kStage = 192;
+  __shared__ uint32_t s_stage[kPropThreads / 32][kStage];
+  __shared__ uint32_t s_count[kPropThreads / 32], s_base;
   unsigned int* level_bits = reinterpret_cast<unsigned int*>(level);
-  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
   const uint32_t gwarp = gtid >> 5, nwarps = gthreads >> 5;
   volatile uint32_t* tail = ctl->front_n;
@@ -155,6 +158,7 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
     // together: a sweep is a chain of dependent memory round trips (front entry -> column header -> list entry ->
     // stamp -> atomics), so what counts is how many of them are in flight at once, not how many lanes are busy.
     const uint32_t sub = lane & 7u, grp = lane >> 3;
+    uint32_t wcount = 0;  // claims staged by this warp in this sweep (warp-uniform)
     for (uint32_t f0 = begin + gwarp * 4u; f0 < end; f0 += nwarps * 4u) {
       const uint32_t f = f0 + grp;
       const bool have = f < end;
@@ -202,17 +206,40 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
             if (!use_cutoff || v > neg_dmax) live = true;
           }
         }
+        // the newly claimed particles go into this warp's staging buffer: the tail of front(t) is ONE word, and an atomic per
+        // warp and batch on it (some ten thousand per sweep, all to the same address) was most of a sweep's time
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const unsigned int mask = __ballot_sync(0xffffffffu, won[u]);
           if (mask) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&ctl->front_n[pout], uint32_t(__popc(mask)));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (won[u]) fout[base + uint32_t(__popc(mask & ((1u << lane) - 1u)))] = iu[u];
+            const uint32_t cnt = uint32_t(__popc(mask));
+            if (wcount + cnt > kStage) {  // full (a sweep rarely claims more than a few dozen per warp): to the front right away
+              uint32_t base = 0;
+              if (lane == 0) base = atomicAdd(&ctl->front_n[pout], wcount);
+              base = __shfl_sync(0xffffffffu, base, 0);
+              for (uint32_t e = lane; e < wcount; e += 32u) fout[base + e] = s_stage[wid][e];
+              __syncwarp();
+              wcount = 0;
+            }
+            if (won[u]) s_stage[wid][wcount + uint32_t(__popc(mask & ((1u << lane) - 1u)))] = iu[u];
+            wcount += cnt;
           }
         }
       }
+    }
+    // one atomic per block: the warps' staged claims behind one another at the tail of front(t)
+    __syncwarp();
+    if (lane == 0) s_count[wid] = wcount;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t total = 0;
+      for (int w = 0; w < kPropThreads / 32; w++) { const uint32_t c = s_count[w]; s_count[w] = total; total += c; }
+      s_base = total ? atomicAdd(&ctl->front_n[pout], total) : 0u;
+    }
+    __syncthreads();
+    {
+      const uint32_t base = s_base + s_count[wid];
+      for (uint32_t e = lane; e < wcount; e += 32u) fout[base + e] = s_stage[wid][e];
     }
     if (__any_sync(0xffffffffu, live) && lane == 0) live_sweep[pout] = t;
     grid.sync();
@@ -309,7 +336,7 @@ int launch_level_estimation(asph_sim* sim) {
                                          sim->front[0].p, sim->ctl);
   LAUNCH_CHECK();
   const bool peer = dist_p2p(sim);
-  if (sim->dist && !peer) { sim->last_error = "level estimation across GPU slabs needs the peer-memory path (ASPH_DIST_P2P)"; return ASPH_ERR_UNSUPPORTED; }
+  if (sim->dist && dist_ranks(sim) > 1 && !peer) { sim->last_error = "level estimation across GPU slabs needs the peer-memory path (ASPH_DIST_P2P)"; return ASPH_ERR_UNSUPPORTED; }
   if (peer) {  // the owners' verdict on the ghosts (their own neighbourhoods are incomplete here), then front(0) with them
     TRY(dist_halo_words(sim, level));
     TRY(dist_halo_words(sim, sim->stamp.p));

@@ -89,6 +89,9 @@ struct StepCtl {
   uint32_t n_new;  // particle count after merge / split
   uint32_t n_shared, n_merged, n_split_parents;
   uint32_t work_n[2], rounds, n_claims, ready_n, greedy_done;
+  uint32_t mail_sent, greedy_barriers;  // several GPUs: number of the last barrier mail was posted for; barriers a search ran
+  uint32_t validate_why, validate_at[4];  // first broken partner invariant: which, particle, counter, partner, what was found
+  uint32_t list_n, local_extra;         // several GPUs: entries in this rank's delete / split list; children this rank appends
   double mass_before, mass_after;
 };
 
@@ -259,7 +262,7 @@ struct asph_sim {
   int sm_count = 148;
   bool bulk = true;    // bulk-copy (cp.async.bulk + mbarrier) stage fill of the single-GPU sweep kernels; ASPH_BULK=0 at asph_create: per-thread copies
   bool sweep_attr_done = false;  // dynamic shared-memory limit of the sweep kernels raised on this handle's device
-  int prop_grid = 0, greedy_grid = 0;  // co-resident blocks of the persistent cooperative kernels (level.cu, adapt.cu) on this device
+  int prop_grid = 0, greedy_grid = 0, greedy_grid_peer = 0;  // co-resident blocks of the persistent cooperative kernels (level.cu, adapt.cu) on this device
   bool ctl_seen = false;  // ctl_host holds a control block read back from the device (possibly of the previous step)
   std::string last_error;
   uint64_t kernel_launches = 0;
@@ -345,6 +348,15 @@ CoopPeer dist_coop_peer(asph_sim* sim);                    // arguments of a per
 void dist_coop_advance(asph_sim* sim, unsigned int barriers);  // the launch ran that many cross-GPU barriers
 int dist_halo_words(asph_sim* sim, void* field);           // dist_halo of a 4-byte field whatever its type
 const uint32_t* dist_ghost_index(asph_sim* sim, uint32_t* count);  // sorted indices of the ghost particles of this step
+int dist_ranks(asph_sim* sim);
+uint64_t dist_n_global(asph_sim* sim);                     // particles of the whole fluid (the reference index space)
+void dist_set_n_global(asph_sim* sim, uint64_t n);
+int dist_allreduce_host(asph_sim* sim, void* host_values, int count, int is_double);  // sum over ranks of host-side uint64 / double values
+// every rank's list (entries of `words` 32-bit words) on every rank: gathered[q * stride + ...], counts[q] entries of rank q (device
+// pointers owned by the distributed state, valid until the next call); *total = entries of all ranks
+int dist_allgather_list(asph_sim* sim, const uint32_t* list, uint32_t n_entries, int words, const uint32_t** gathered, const uint32_t** counts,
+                        uint32_t* stride, unsigned long long* total);
+int dist_ref_buffers(asph_sim* sim, size_t n, uint32_t** a, uint32_t** b);  // two arrays over the reference index space
 int dist_local_map(asph_sim* sim);                         // scratch_u[3][i] = slot of owned particle i in read-backs, ~0u for ghosts
 void dist_destroy(asph_sim* sim);
 // capi.cu

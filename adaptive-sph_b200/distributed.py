@@ -82,7 +82,7 @@ class DistributedFluidSimulation(FluidSimulation):
     (reference-order) indices; the library migrates particles to their owner slab at the first step."""
 
     def __init__(self, params, pos, vel, mass, global_index, n_global, boundary=None, counters_enabled=False,
-                 capacity=0, lib=None, rank=None, world=None, device=None):
+                 capacity=0, lib=None, rank=None, world=None, device=None, split_patterns=None):
         import torch.distributed as dist
         lib = lib if lib is not None else load_library()
         rank = dist.get_rank() if rank is None else rank
@@ -91,7 +91,7 @@ class DistributedFluidSimulation(FluidSimulation):
             device = int(os.environ.get("LOCAL_RANK", rank))
         self.rank, self.world, self.n_global = rank, world, int(n_global)
         nccl_id = broadcast_unique_id(lib, rank)
-        super().__init__(params, pos, vel, mass, boundary, None, counters_enabled, capacity, lib,
+        super().__init__(params, pos, vel, mass, boundary, split_patterns, counters_enabled, capacity, lib,
                          distributed=dict(global_index=global_index, nccl_id=nccl_id, n_global=n_global, rank=rank,
                                           n_ranks=world, device=device))
 
@@ -106,6 +106,13 @@ class DistributedFluidSimulation(FluidSimulation):
         gidx = np.arange(lo, hi, dtype=np.uint32)
         return cls(params, pos, vel, mass, gidx, n_global, scene_boundary(scene, params["init_boundary_handler"]), **kw)
 
+    def num_global_particles(self):
+        """Particles of the whole fluid now (resampling changes the count): the sum of what the ranks own."""
+        import torch.distributed as dist
+        counts = [None] * self.world
+        dist.all_gather_object(counts, self.num_fluid_particles())
+        return int(sum(counts))
+
     def gather_field(self, name):
         """Field of ALL particles in reference order, assembled on every rank."""
-        return gather_by_global_index(self.get_field(name), self.global_index(), self.n_global)
+        return gather_by_global_index(self.get_field(name), self.global_index(), self.num_global_particles())

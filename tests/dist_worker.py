@@ -29,6 +29,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     params = A.SimulationParams.from_yaml(os.path.join(ROOT, "configs", "default-config.yaml")).replace(
         merging=False, sharing=False, splitting=False, level_estimation_method="None", pressure_solver_method=solver)
+    if mode in ("adaptive", "levelset"):
+        return adaptive(A, dist, rank, world, steps, spacing, mode)
     # "random": seeded random velocities => compression somewhere from the first step, the pressure solver iterates
     #           (the recipe of test_single_step_uniform); few steps, because an SPH impact amplifies rounding noise
     # "drift":  the block moves to the right in free fall => particles migrate between slabs every step
@@ -94,6 +96,71 @@ def main():
         report["owned_first"] = [c[0] for c in counts]
         report["owned"] = [c[1] for c in counts]
         report["rows"] = report["rows"][-3:]
+        print("DIST_REPORT " + json.dumps(report))
+    d.close()
+    if single is not None:
+        single.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def adaptive(A, dist, rank, world, steps, spacing, mode):
+    """BASELINE configs[2] recipe in small (tests/test_gpu_parity.py::test_adaptive_dam_break_mid_size): level set and, in mode
+    "adaptive", share / merge / split across the slabs.  Every step: the particle count, the level sweeps and the resampling
+    statistics of the N-GPU run equal the 1-GPU run's; at the end the fields, gathered by reference index, agree."""
+    r_f = float(np.sqrt(0.93 / np.pi) * spacing)
+    params = A.SimulationParams.from_yaml(os.path.join(ROOT, "configs", "default-config.yaml")).replace(
+        particle_radius_fine=r_f, particle_radius_base=4.0 * r_f, maximum_surface_distance=0.2)
+    if mode == "levelset":
+        params = params.replace(merging=False, sharing=False, splitting=False)
+    split = A.load_split_patterns_from_file()
+    scene = A.SceneConfig.dam_break(spacing, pos=(-0.9, -0.9), size=(1.2, 0.8))
+    pos, vel, mass = A.scene_particles(scene)
+    n_global = len(mass)
+    lo, hi = A.share_range(n_global, rank, world)
+    boundary = A.scene_boundary(scene, "AnalyticOverestimate")
+    d = A.DistributedFluidSimulation(params, pos[lo:hi], vel[lo:hi], mass[lo:hi], np.arange(lo, hi, dtype=np.uint32), n_global,
+                                     boundary, counters_enabled=True, split_patterns=split)
+    single = A.FluidSimulation(params, pos, vel, mass, boundary, split) if rank == 0 else None
+    keys = ("div_sweeps", "density_sweeps", "level_sweeps", "n_shared", "n_merged", "n_split_parents")
+    report = {"world": world, "steps": steps, "n_global": n_global, "mode": mode, "rows": [], "mismatch": []}
+    for k in range(steps):
+        dt = d.single_step()
+        info = d.step_info()
+        n_now = d.num_global_particles()
+        if single is not None:
+            dt1 = single.single_step()
+            i1 = single.step_info()
+            row = {"step": k, "n": n_now, "n1": single.num_fluid_particles(), "dt": dt, "dt1": dt1}
+            for key in keys:
+                row[key] = [int(info[key]), int(i1[key])]
+                if int(info[key]) != int(i1[key]):
+                    report["mismatch"].append((k, key, int(info[key]), int(i1[key])))
+            if row["n"] != row["n1"]:
+                report["mismatch"].append((k, "n", row["n"], row["n1"]))
+            if abs(dt - dt1) > 2e-6 * dt1:
+                report["mismatch"].append((k, "dt", dt, dt1))
+            report["rows"].append(row)
+    fields = {name: d.gather_field(name) for name in ("position", "velocity", "mass", "level")}
+    owned = d.num_fluid_particles()
+    counts = [None] * world
+    dist.all_gather_object(counts, owned)
+    if rank == 0:
+        err = {}
+        for name, scale in (("position", 2.0), ("velocity", None), ("mass", None), ("level", 1.0)):
+            a, b = fields[name].astype(np.float64), single.get_field(name).astype(np.float64)
+            if a.shape != b.shape:
+                err[name] = float("inf")
+                continue
+            s = scale if scale is not None else max(np.abs(b).max(), 1e-30)
+            err[name] = float(np.abs(a - b).max() / s)
+        report["err"] = err
+        report["owned"] = counts
+        report["n_end"] = [int(len(fields["mass"])), single.num_fluid_particles()]
+        report["merged_total"] = int(sum(r["n_merged"][1] for r in report["rows"]))
+        report["split_total"] = int(sum(r["n_split_parents"][1] for r in report["rows"]))
+        report["shared_total"] = int(sum(r["n_shared"][1] for r in report["rows"]))
+        report["rows"] = report["rows"][-2:]
         print("DIST_REPORT " + json.dumps(report))
     d.close()
     if single is not None:

@@ -53,10 +53,8 @@ def test_two_gpu_pressure_solve_matches_single_gpu(solver):
     assert rep["err"]["pressure"] < 1e-3 and rep["err"]["velocity"] < 1e-4, rep
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: first run on hardware pending")
 def test_two_gpu_separate_columns_match_single_gpu():
-    """The benchmark's weak-scaling scene in small: fluid columns with empty space between them, the slab face through the
-    middle of one (added when the round's GPU time was spent; first run on hardware pending)."""
+    """Fluid columns with empty space between them, the slab face through the middle of one."""
     if _gpu_count() < 2:
         pytest.skip("needs 2 GPUs")
     rep = _run(2, 4, "HybridDFSPH", mode="columns")
@@ -80,3 +78,33 @@ def test_four_gpu_step_matches_single_gpu():
     rep = _run(4, 4, "HybridDFSPH", "0.004", mode="random")
     _check(rep, 1e-6)
     assert rep["sweeps_equal"], rep
+
+
+def _check_adaptive(rep, tol_x=1e-5):
+    assert not rep["mismatch"], rep
+    assert rep["n_end"][0] == rep["n_end"][1], rep
+    assert sum(rep["owned"]) == rep["n_end"][1], rep       # ownership is a partition of the resampled particle set
+    assert rep["err"]["mass"] <= 1e-6, rep                  # same donors, same receivers, same children
+    assert rep["err"]["position"] < tol_x, rep
+    assert rep["err"]["level"] < 1e-4, rep
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_level_set_across_slabs(world):
+    """EmptyAngle detection + propagation + smoothing with the fluid cut into x-slabs: the fronts cross the slab faces through
+    the mailboxes of the persistent propagation kernel; sweep counts and the level field equal the single-GPU run's."""
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    rep = _run(world, 6, "HybridDFSPH", "0.006", mode="levelset")
+    _check_adaptive(rep, 1e-6)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_adaptive_dam_break_across_slabs(world):
+    """BASELINE configs[2] recipe in small, share / merge / split across the slabs: every step the same particle count and
+    the same shared / merged / split statistics as on one GPU, and at the end the same particles (by reference index)."""
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    rep = _run(world, 14, "HybridDFSPH", "0.006", mode="adaptive")
+    _check_adaptive(rep)
+    assert rep["merged_total"] > 0 and rep["n_end"][1] < rep["n_global"], rep   # the interior really coarsened
