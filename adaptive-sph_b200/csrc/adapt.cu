@@ -932,6 +932,10 @@ int launch_adaptivity(asph_sim* sim, float dt) {
         k_hnext_after_transfer<<<blocks, kThreads, 0, st>>>(sim->n, A, P, 0, sim->hnext[sim->cur].p);
         LAUNCH_CHECK();
       }
+      if (sim->dist) {  // the merge search of this step reads the shared particles' new x, v, m: their ghost copies follow
+        const int c = sim->cur;
+        TRY(dist_halo(sim, sim->pos[c].p, 8)); TRY(dist_halo(sim, sim->vel[c].p, 8)); TRY(dist_halo_words(sim, sim->mass[c].p));
+      }
     }
   }
   if (sim->step_number % 2 == 0) {

@@ -711,14 +711,20 @@ float asph_dlambda_lut(float d) { return asph_host_lut_get(host_lut(1), d); }
 
 // ---- diagnostics used by the parity tests: drive single_step_adaptivity from a prescribed level field / step parity
 int asph_set_level(asph_sim* sim, const float* level_ref_order, uint64_t n) {
-  if (!sim || !level_ref_order || n != sim->n || sim->dist) return ASPH_ERR_INVALID;
+  // several GPUs: the array covers the whole fluid (indexed by reference index); this rank picks its particles' and its ghosts' values
+  if (!sim || !level_ref_order || n != (sim->dist ? dist_n_global(sim) : uint64_t(sim->n))) return ASPH_ERR_INVALID;
   CUDA_TRY(cudaSetDevice(sim->device));
-  std::vector<uint32_t> refid(n);
-  std::vector<float> lv(n);
-  if (n) {
-    CUDA_TRY(cudaMemcpy(refid.data(), sim->refid[sim->cur].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    for (uint64_t i = 0; i < n; i++) lv[i] = level_ref_order[refid[i]];
-    CUDA_TRY(cudaMemcpy(sim->level[sim->cur].p, lv.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+  const uint64_t nl = sim->n;
+  std::vector<uint32_t> refid(nl);
+  std::vector<float> lv(nl);
+  if (nl) {
+    CUDA_TRY(cudaMemcpy(refid.data(), sim->refid[sim->cur].p, nl * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < nl; i++) {
+      const uint32_t r = refid[i] & ~ASPH_GHOST_BIT;
+      if (r >= n) return ASPH_ERR_INVALID;
+      lv[i] = level_ref_order[r];
+    }
+    CUDA_TRY(cudaMemcpy(sim->level[sim->cur].p, lv.data(), nl * sizeof(float), cudaMemcpyHostToDevice));
   }
   sim->level_valid = true;
   return ASPH_OK;

@@ -31,6 +31,8 @@ def main():
         merging=False, sharing=False, splitting=False, level_estimation_method="None", pressure_solver_method=solver)
     if mode in ("adaptive", "levelset"):
         return adaptive(A, dist, rank, world, steps, spacing, mode)
+    if mode.startswith("resample"):
+        return resample(A, dist, rank, world, steps, mode)
     # "random": seeded random velocities => compression somewhere from the first step, the pressure solver iterates
     #           (the recipe of test_single_step_uniform); few steps, because an SPH impact amplifies rounding noise
     # "drift":  the block moves to the right in free fall => particles migrate between slabs every step
@@ -104,6 +106,75 @@ def main():
     dist.destroy_process_group()
 
 
+def resample(A, dist, rank, world, seed, mode):
+    """single_step_adaptivity across the slabs on prescribed inputs (the recipe of test_resampling_phase_parity): a jittered
+    lattice with masses spread over all five size classes of a prescribed level field, so that donors and receivers sit on
+    both sides of every slab face.  After one physics step (lists, ghosts) both runs get the SAME level field and run the
+    resampling phase alone: same statistics, bit-identical masses, by reference index."""
+    import ctypes as C
+    phase = mode.split(":", 1)[1] if ":" in mode else "share+merge"
+    rng = np.random.default_rng(seed)
+    sp = np.float32(0.01)
+    blk = dict(pos=(np.float32(-0.8), np.float32(-0.5)), size=(np.float32(1.601), np.float32(0.801)), spacing=sp,
+               volume_fill_ratio=np.float32(0.93), velocity=(np.float32(0), np.float32(0)))
+    pos, vel, mass = A.add_fluid_block(blk)
+    pos = (pos + rng.uniform(-0.25, 0.25, pos.shape).astype(np.float32) * sp).astype(np.float32)
+    vel = (rng.standard_normal(pos.shape) * 0.01).astype(np.float32)
+    mass = (mass * rng.uniform(0.3, 2.6, mass.shape)).astype(np.float32)
+    level = np.minimum((-(0.35 - pos[:, 1]) * 0.5).astype(np.float32), np.float32(0.0))
+    r0 = float(np.sqrt(0.93e-4 / np.pi))
+    params = A.SimulationParams.from_yaml(os.path.join(ROOT, "configs", "default-config.yaml")).replace(
+        particle_radius_fine=r0, particle_radius_base=2.0 * r0, maximum_surface_distance=0.2,
+        sharing="share" in phase, merging="merge" in phase, splitting="split" in phase,
+        max_dt=1e-5, max_iters=3)  # the physics step only has to build the lists and the ghosts: the masses are far from rest
+    split = A.load_split_patterns_from_file()
+    scene = A.SceneConfig({"boundary": {"type": "box", "width": 2.0, "height": 2.0}, "blocks": []})
+    boundary = A.scene_boundary(scene, "AnalyticOverestimate")
+    n_global = len(mass)
+    order = np.argsort(pos[:, 0], kind="stable")     # the shares are x-slabs; the reference index stays the lattice index
+    lo, hi = A.share_range(n_global, rank, world)
+    mine = np.sort(order[lo:hi])
+    d = A.DistributedFluidSimulation(params, pos[mine], vel[mine], mass[mine], mine.astype(np.uint32), n_global, boundary,
+                                     split_patterns=split)
+    single = A.FluidSimulation(params, pos, vel, mass, boundary, split) if rank == 0 else None
+    dt = d.single_step_without_adaptivity()
+    lp = level.ctypes.data_as(C.POINTER(C.c_float))
+    step_number = 2 if "merge" in phase else 3
+    assert d.lib.asph_set_level(d._h, lp, n_global) == 0
+    d.lib.asph_set_step_number(d._h, step_number)
+    d.single_step_adaptivity(dt=0.002)
+    info = d.step_info()
+    report = {"world": world, "mode": mode, "seed": seed, "n_global": n_global, "mismatch": []}
+    n_now = d.num_global_particles()
+    fields = {name: d.gather_field(name) for name in ("mass", "position", "velocity")}
+    if single is not None:
+        dt1 = single.single_step_without_adaptivity()
+        assert single.lib.asph_set_level(single._h, lp, n_global) == 0
+        single.lib.asph_set_step_number(single._h, step_number)
+        single.single_step_adaptivity(dt=0.002)
+        i1 = single.step_info()
+        for key in ("n_shared", "n_merged", "n_split_parents"):
+            report[key] = [int(info[key]), int(i1[key])]
+            if int(info[key]) != int(i1[key]):
+                report["mismatch"].append((key, int(info[key]), int(i1[key])))
+        report["n"] = [n_now, single.num_fluid_particles()]
+        if n_now != single.num_fluid_particles():
+            report["mismatch"].append(("n", n_now, single.num_fluid_particles()))
+        else:
+            m1 = single.get_field("mass")
+            bad = np.nonzero(fields["mass"] != m1)[0]
+            report["mass_bits_differ"] = int(len(bad))
+            report["first_bad"] = [int(b) for b in bad[:8]]
+            report["pos_maxdiff"] = float(np.abs(fields["position"] - single.get_field("position")).max())
+            report["vel_maxdiff"] = float(np.abs(fields["velocity"] - single.get_field("velocity")).max())
+        report["dt"] = [dt, dt1]
+        print("DIST_REPORT " + json.dumps(report))
+        single.close()
+    d.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def adaptive(A, dist, rank, world, steps, spacing, mode):
     """BASELINE configs[2] recipe in small (tests/test_gpu_parity.py::test_adaptive_dam_break_mid_size): level set and, in mode
     "adaptive", share / merge / split across the slabs.  Every step: the particle count, the level sweeps and the resampling
@@ -141,6 +212,16 @@ def adaptive(A, dist, rank, world, steps, spacing, mode):
             if abs(dt - dt1) > 2e-6 * dt1:
                 report["mismatch"].append((k, "dt", dt, dt1))
             report["rows"].append(row)
+        if os.environ.get("ASPH_DIST_TRACE"):  # per-step distance of the two runs (diagnostics; a gather per step)
+            gm, gl, gx = d.gather_field("mass"), d.gather_field("level"), d.gather_field("position")
+            if single is not None:
+                sm_, sl_, sx_ = single.get_field("mass"), single.get_field("level"), single.get_field("position")
+                if gm.shape == sm_.shape:
+                    bad = np.nonzero(gm != sm_)[0]
+                    report.setdefault("trace", []).append({"step": k, "mass_diff": int(len(bad)), "first_bad": [int(b) for b in bad[:6]],
+                                                           "level_maxdiff": float(np.abs(gl - sl_).max()), "pos_maxdiff": float(np.abs(gx - sx_).max())})
+                else:
+                    report.setdefault("trace", []).append({"step": k, "shape": [int(gm.shape[0]), int(sm_.shape[0])]})
     fields = {name: d.gather_field(name) for name in ("position", "velocity", "mass", "level")}
     owned = d.num_fluid_particles()
     counts = [None] * world
@@ -157,6 +238,7 @@ def adaptive(A, dist, rank, world, steps, spacing, mode):
         report["err"] = err
         report["owned"] = counts
         report["n_end"] = [int(len(fields["mass"])), single.num_fluid_particles()]
+        report["mass_total"] = [float(fields["mass"].astype(np.float64).sum()), float(single.get_field("mass").astype(np.float64).sum())]
         report["merged_total"] = int(sum(r["n_merged"][1] for r in report["rows"]))
         report["split_total"] = int(sum(r["n_split_parents"][1] for r in report["rows"]))
         report["shared_total"] = int(sum(r["n_shared"][1] for r in report["rows"]))

