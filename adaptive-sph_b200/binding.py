@@ -100,6 +100,8 @@ def _declare(lib):
     lib.asph_get_kernel_timing.restype = C.c_int
     lib.asph_adapt_rounds.argtypes = [_P]
     lib.asph_adapt_rounds.restype = C.c_uint64
+    lib.asph_debug_greedy_duplicates.argtypes = [_P]
+    lib.asph_debug_greedy_duplicates.restype = C.c_uint64
     lib.asph_set_level.argtypes = [_P, _FP, C.c_uint64]
     lib.asph_set_level.restype = C.c_int
     lib.asph_set_step_number.argtypes = [_P, C.c_uint64]
@@ -293,6 +295,9 @@ class FluidSimulation:
         self._check(self.lib.asph_get_kernel_timing(self._h, ms, cnt))
         names = ["accel_sweep", "jacobi_sweep", "neighbors", "sort_grid", "level_propagate", "partner_search"]
         return {names[k]: (ms[k], cnt[k]) for k in range(6)}
+
+    def greedy_duplicates(self):
+        return int(self.lib.asph_debug_greedy_duplicates(self._h))
 
     def adapt_rounds(self):
         """Dependency rounds of the greedy partner searches in the last resampling phase (0 on the CPU oracle)."""

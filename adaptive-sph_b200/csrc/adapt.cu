@@ -91,7 +91,7 @@ __device__ __forceinline__ bool static_eligible(const AdaptArgs& A, const Packed
 
 __global__ void k_partner_ctl_reset(StepCtl* ctl) {
   ctl->work_n[0] = 0; ctl->work_n[1] = 0; ctl->ready_n = 0; ctl->rounds = 0; ctl->n_claims = 0; ctl->greedy_done = 0;
-  ctl->mail_sent = 0; ctl->greedy_barriers = 0; ctl->validate_why = 0;
+  ctl->mail_sent = 0; ctl->greedy_barriers = 0; ctl->validate_why = 0; ctl->greedy_duplicates = 0;
 }
 
 // ---- the greedy partner search as one persistent cooperative kernel ------------------------------------------------
@@ -210,6 +210,7 @@ k_greedy(const GreedyArgs G, const PackedParams P, const CoopPeer C) {
   volatile uint32_t* ready_n = &ctl->ready_n;
   unsigned int bar = C.seq0 + 1u;  // PEER: number of the next cross-GPU barrier; mail posted before it uses its parity
 
+  bool mailed = false;  // this thread has written to another GPU since the last exchange
   auto is_ghost = [&](uint32_t i) { return PEER && nb_ghost(__ldg(&A.L.cnt[i])); };
   // one message to the neighbour on `side` (0 = rank - 1)
   auto mail = [&](int side, uint32_t slot, uint32_t kind, uint32_t payload) {
@@ -218,6 +219,7 @@ k_greedy(const GreedyArgs G, const PackedParams P, const CoopPeer C) {
     if (k < C.mbox_cap) C.nb_mbox[side][size_t(par * 2u + uint32_t(1 - side)) * C.mbox_cap + k] = make_uint2(slot | (kind << 28), payload);
     else atomicOr(&ctl->error_flags, ERRF_PEER_TIMEOUT);
     ctl->mail_sent = bar;
+    mailed = true;
   };
   // what the ghost copies of owned particle i have to hear
   auto mail_copies = [&](uint32_t i, uint32_t kind, uint32_t payload) {
@@ -274,7 +276,7 @@ k_greedy(const GreedyArgs G, const PackedParams P, const CoopPeer C) {
     uint32_t z = __ldcg(G.head + b);
     if (z == NONE_) return;
     G.head[b] = NONE_;
-    while (z != NONE_) {
+    for (uint32_t guard = 0; z != NONE_ && guard <= n; guard++) {  // (a list is a chain of distinct donors: at most n long)
       const uint32_t nz = __ldcg(G.next + z);
       out[atomicAdd(&ctl->work_n[slot], 1u)] = z;
       z = nz;
@@ -282,7 +284,7 @@ k_greedy(const GreedyArgs G, const PackedParams P, const CoopPeer C) {
   };
   // PEER: fence, meet the other GPUs, take in their mail; returns whether any rank has work or mail outstanding
   auto exchange = [&](uint32_t pout) {
-    __threadfence_system();
+    if (mailed) { __threadfence_system(); mailed = false; }  // only the threads that wrote to another GPU pay for a system-scope fence
     grid.sync();
     if (gtid == 0) {
       const unsigned int mine = (work_n[pout] > 0u ? 1u : 0u) | (*reinterpret_cast<volatile unsigned int*>(&ctl->mail_sent) == bar ? 2u : 0u);
@@ -418,6 +420,15 @@ k_greedy(const GreedyArgs G, const PackedParams P, const CoopPeer C) {
     };
     for (uint32_t w = ready_begin + gwarp; w < ready_end; w += nwarps) {
       const uint32_t d = __ldcg(G.ready + w);
+      // a donor decides ONCE: the state word changes hands atomically (a second entry for the same donor — none is known to
+      // arise, the counter below would say so — must not run the loop again over receivers the first run has claimed)
+      uint32_t mine_to_decide = 0;
+      if (lane == 0) {
+        const uint32_t iv = __ldcg(G.info + d);
+        mine_to_decide = ((iv & 0xffu) == GI_PENDING && atomicCAS(G.info + d, iv, (iv & ~0xffu) | GI_DONE) == iv) ? 1u : 0u;
+        if (!mine_to_decide) atomicAdd(&ctl->greedy_duplicates, 1u);
+      }
+      if (!__shfl_sync(0xffffffffu, mine_to_decide, 0)) continue;
       const DonorRegs D = donor_regs(A, P, merging, G.dt, d);
       uint32_t mine;
       const uint32_t c = donor_loop<false>(A, P, merging, D, lane, mine, [&](uint32_t j) { if (lane == 0) claimed(j, d); });
@@ -794,6 +805,7 @@ int find_partners(asph_sim* sim, bool merging, float dt, uint32_t* claims) {
   if (sim->ctl_host->error_flags & ERRF_PEER_TIMEOUT) return check_error_flags(sim);
   if (!sim->ctl_host->greedy_done) { sim->last_error = "partner search did not terminate"; return ASPH_ERR_INVALID; }
   sim->adapt_rounds += sim->ctl_host->rounds;
+  sim->greedy_duplicates += sim->ctl_host->greedy_duplicates;
   unsigned long long c = sim->ctl_host->n_claims;
   if (sim->dist) TRY(dist_allreduce_host(sim, &c, 1, 0));  // every rank reports (and branches on) the claims of the whole fluid
   *claims = uint32_t(c);

@@ -731,6 +731,7 @@ int asph_set_level(asph_sim* sim, const float* level_ref_order, uint64_t n) {
 }
 void asph_set_step_number(asph_sim* sim, uint64_t k) { if (sim) sim->step_number = k; }
 uint64_t asph_adapt_rounds(const asph_sim* sim) { return sim ? sim->adapt_rounds : 0; }
+uint64_t asph_debug_greedy_duplicates(const asph_sim* sim) { return sim ? sim->greedy_duplicates : 0; }
 
 int asph_set_kernel_timing(asph_sim* sim, int sample_every) {
   if (!sim) return ASPH_ERR_INVALID;

@@ -247,6 +247,7 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
       const unsigned int seq = P.seq0 + unsigned(t), par = seq & 1u;
       // mail the border particles assigned in this sweep to their ghost copies
       const uint32_t e0 = exported[pout], e1 = tail[pout];
+      bool mailed = false;
       for (uint32_t f = e0 + gtid; f < e1; f += gthreads) {
         const uint32_t i = __ldcg(fout + f);
         const unsigned int bits = __ldcg(level_bits + i);
@@ -256,9 +257,10 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
           if (sl == 0xffffffffu || !P.nb_mbox[side]) continue;
           const uint32_t k = atomicAdd_system(&P.nb_ctl[side]->mbox_n[par][1 - side], 1u);  // I am that neighbour's other side
           if (k < P.mbox_cap) P.nb_mbox[side][size_t(par * 2u + uint32_t(1 - side)) * P.mbox_cap + k] = make_uint2(sl, bits);
+          mailed = true;
         }
       }
-      __threadfence_system();
+      if (mailed) __threadfence_system();  // only the few threads that wrote to another GPU pay for a system-scope fence
       grid.sync();
       if (gtid == 0) {
         const unsigned int mine = (e1 > e0 ? 1u : 0u) | (live_sweep[pout] == t ? 2u : 0u);

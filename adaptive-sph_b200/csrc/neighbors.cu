@@ -12,6 +12,7 @@
 namespace {
 
 constexpr int kThreads = 128;
+constexpr uint32_t kStageCap = 48;  // hits a thread stages in shared memory between its scan and the writing of its column
 
 // LookupTable1D::get over [-1, 1], 10000 steps (lookup_table.rs:32-48), same operation order
 __device__ __forceinline__ float lut_get(const float* __restrict__ data, float x) {
@@ -98,6 +99,7 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
             uint32_t* __restrict__ far_idx, uint32_t* __restrict__ far_cnt,
             float* __restrict__ rho_out, float2* __restrict__ gB_out, float4* __restrict__ pconst, float* __restrict__ lam_sum_out,
             float2* __restrict__ lam_grad_out, float2* __restrict__ nrm_out, const uint32_t* __restrict__ gid) {
+  __shared__ uint32_t s_stage[kStageCap * kThreads];  // [hit][thread]: conflict-free
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t i0 = i & ~(ASPH_PAIR_BLOCK - 1u);  // the index bias is per 256-particle block (lists.cuh)
@@ -110,21 +112,34 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
   if (active) me = xyhm[i];
   const float xi = me.x, yi = me.y, hi = me.z;
 
-  // pass 1: counts — 2h neighbours inside / outside the pair passes' shared-memory window (lists.cuh), the extended
-  // range, and whether every index stored outside the window segment fits 16 bits around the block
+  // pass 1, the ONE scan of the candidates: counts — 2h neighbours inside / outside the pair passes' shared-memory window
+  // (lists.cuh), the extended range, and whether every index stored outside the window segment fits 16 bits around the
+  // block —, the pair sums over N_2(i) (density, a_ii and the surface normal need nothing but the snapshot), and the hits
+  // themselves, staged in shared memory (index | 2h flag) so that writing the lists needs no second scan.  A thread with
+  // more than kStageCap hits (a coarse particle next to fine ones) scans again in pass 2.
   const uint32_t win0 = i0 - ASPH_PAIR_HALO;
   uint32_t cw = 0, cf = 0, ce = 0;
   bool fits = true, fits_far = true, fits_ext = true;
+  float rho = 0.f, Sx = 0.f, Sy = 0.f, Q = 0.f, Nx = 0.f, Ny = 0.f;
   if (active) {
     for_each_candidate(xi, yi, hi, ctl_in, cellstart, f_ext, [&](uint32_t j) {
       const float4 o = __ldg(&xyhm[j]);
-      const float d2 = dist_sq_exact(__fsub_rn(xi, o.x), __fsub_rn(yi, o.y));
+      const float ddx = __fsub_rn(xi, o.x), ddy = __fsub_rn(yi, o.y);
+      const float d2 = dist_sq_exact(ddx, ddy);
       if (d2 < support_sq_exact(hi, o.z, f_ext)) {
+        const bool near = d2 < support_sq_exact(hi, o.z, f_near);
+        if (ce < kStageCap) s_stage[ce * kThreads + threadIdx.x] = j | (near ? 0x80000000u : 0u);
         ce++;
-        if (d2 < support_sq_exact(hi, o.z, f_near) && j - win0 < ASPH_PAIR_WIN) cw++;
-        else if (d2 < support_sq_exact(hi, o.z, f_near)) {
-          cf++;
-          if (j - i0 + 32768u > 65535u) fits_far = false;
+        if (near) {
+          if (j - win0 < ASPH_PAIR_WIN) cw++;
+          else { cf++; if (j - i0 + 32768u > 65535u) fits_far = false; }
+          float w, g;
+          pair_wg(d2, (hi + o.z) * 0.5f, w, g);
+          rho += o.w * w;
+          const float c = o.w * g;
+          Sx += c * ddx; Sy += c * ddy;
+          Q += c * g * d2;  // m_j |gradW|^2
+          Nx += g * ddx; Ny += g * ddy;
         } else if (j - i0 + 32768u > 65535u) {
           fits_ext = false;
         }
@@ -177,15 +192,13 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
   cnt[i] = cw | (min(cf, 0x7ffffu) << 12) | ((gid && (gid[i] & ASPH_GHOST_BIT)) ? 0x80000000u : 0u);
   cnt_ext[i] = ce;
 
-  // pass 2: write the entries (window segment, far 2h segment, extended-range rest)
+  // pass 2: write the entries (window segment, far 2h segment, extended-range rest), in the order of the scan
   uint16_t* slice = pool + size_t(base64) * 64u;
   const uint32_t bias = i0 - 32768u;
   {
     uint32_t kw = 0, kf = 0, ke = nb_pad4(cf), kt = 0;
-    for_each_candidate(xi, yi, hi, ctl_in, cellstart, f_ext, [&](uint32_t j) {
-      const float4 o = __ldg(&xyhm[j]);
-      const float d2 = dist_sq_exact(__fsub_rn(xi, o.x), __fsub_rn(yi, o.y));
-      if (d2 < support_sq_exact(hi, o.z, f_near)) {
+    auto place = [&](uint32_t j, bool near) {
+      if (near) {
         if (j - win0 < ASPH_PAIR_WIN) {
           if (!(P.self_last && j == i)) nb_store_w(slice, lane, kw++, (j - win0) * 16u);
         } else if (in_table) {
@@ -195,10 +208,23 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
         } else {
           nb_store_fe(slice, wide, lane, cw, kf++, j, bias);
         }
-      } else if (d2 < support_sq_exact(hi, o.z, f_ext)) {
+      } else {
         nb_store_fe(slice, wide, lane, cw, ke++, j, bias);
       }
-    });
+    };
+    if (ce <= kStageCap) {
+      for (uint32_t k = 0; k < ce; k++) {
+        const uint32_t e = s_stage[k * kThreads + threadIdx.x];
+        place(e & 0x7fffffffu, (e >> 31) != 0u);
+      }
+    } else {
+      for_each_candidate(xi, yi, hi, ctl_in, cellstart, f_ext, [&](uint32_t j) {
+        const float4 o = __ldg(&xyhm[j]);
+        const float d2 = dist_sq_exact(__fsub_rn(xi, o.x), __fsub_rn(yi, o.y));
+        if (d2 < support_sq_exact(hi, o.z, f_near)) place(j, true);
+        else if (d2 < support_sq_exact(hi, o.z, f_ext)) place(j, false);
+      });
+    }
     if (P.self_last) nb_store_w(slice, lane, kw++, (i - win0) * 16u);  // the particle's own row closes the W segment (solver.cu, R4)
     for (uint32_t r = cw; r < nb_pad8(cw); r++) nb_store_w(slice, lane, r, (i - win0) * 16u);  // padding: the particle itself
     for (uint32_t k = cf; k < nb_pad4(cf); k++) nb_store_fe(slice, wide, lane, cw, k, i, bias);
@@ -207,23 +233,6 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
   // boundary terms
   float lam, Gx, Gy;
   boundary_terms(P, lut, xi, yi, hi, lam, Gx, Gy);
-
-  // pass 3: pair sums over the thread's own 2h column (all lanes busy, no predicate divergence)
-  float rho = 0.f, Sx = 0.f, Sy = 0.f, Q = 0.f, Nx = 0.f, Ny = 0.f;
-  {
-    for (uint32_t k = 0; k < cn; k++) {
-      const uint32_t j = nb_get(slice, far_idx, wide, i, k, cw, cf);
-      const float4 o = __ldg(&xyhm[j]);
-      const float dx = xi - o.x, dy = yi - o.y;
-      float w, g;
-      pair_wg(dx * dx + dy * dy, (hi + o.z) * 0.5f, w, g);
-      rho += o.w * w;
-      const float c = o.w * g;
-      Sx += c * dx; Sy += c * dy;
-      Q += c * g * (dx * dx + dy * dy);  // m_j |gradW|^2
-      Nx += g * dx; Ny += g * dy;
-    }
-  }
 
   // density, simulation.rs:1018-1047
   rho += lam;

@@ -90,6 +90,7 @@ struct StepCtl {
   uint32_t n_shared, n_merged, n_split_parents;
   uint32_t work_n[2], rounds, n_claims, ready_n, greedy_done;
   uint32_t mail_sent, greedy_barriers;  // several GPUs: number of the last barrier mail was posted for; barriers a search ran
+  uint32_t greedy_duplicates;             // ready-list entries whose donor had been decided already (diagnostics; expected 0)
   uint32_t validate_why, validate_at[4];  // first broken partner invariant: which, particle, counter, partner, what was found
   uint32_t list_n, local_extra;         // several GPUs: entries in this rank's delete / split list; children this rank appends
   double mass_before, mass_after;
@@ -233,6 +234,7 @@ struct asph_sim {
   DevBuf<uint32_t> g_info, g_head, g_next, g_resume;
   DevBuf<float> g_drop;
   uint64_t adapt_rounds = 0;
+  uint64_t greedy_duplicates = 0;  // over the lifetime of the handle (diagnostics)
   DevBuf<float> scratch_f;
   DevBuf<float> lut;         // 2 * 10001 floats: λ then λ′
   DevBuf<float> split_pos;   // flattened patterns

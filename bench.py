@@ -340,6 +340,7 @@ def run_ours(args):
     same_work = all(abs(e2e["work"].get(k, 0) - sm.get(k, 0)) <= 1.0 for k in ("avg_div_sweeps", "avg_density_sweeps", "avg_level_sweeps"))
     e2e["same_work_as_device_arm"] = bool(same_work)
     sim_time = sim.time
+    dup = sim.greedy_duplicates()
     sim.close()
     if not same_work:
         raise SystemExit(f"bench: the e2e arm did not do the work of the device arm: {e2e['work']} vs {sm}")
@@ -354,7 +355,7 @@ def run_ours(args):
         "config": dict({"workload": workload_name(n0), "particles_initial": n0, "preroll_steps": PREROLL_STEPS, "preroll_wall_s": t_pre,
                         "l2": "working set per step (neighbour lists + SoA, > 1 GB) exceeds the 126 MB L2; no flush",
                         "timing": "CUDA events on the library stream around every step (PerformanceCounters 'simulation-step': physics + resampling)",
-                        "wall_ms_per_step": wall * 1e3 / max(K, 1), "phase_ms_per_step": phases, "simulated_time": sim_time,
+                        "wall_ms_per_step": wall * 1e3 / max(K, 1), "phase_ms_per_step": phases, "simulated_time": sim_time, "greedy_duplicates": dup,
                         "kernels": tab, "switches": {k: os.environ[k] for k in ("ASPH_BULK", "ASPH_SWEEP_GRID", "ASPH_BENCH_SPACING", "ASPH_BENCH_PREROLL") if k in os.environ}}, **sm),
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "step_roofline": step_roof, "cpu_baseline": cpu,
     }

@@ -239,6 +239,9 @@ int asph_get_kernel_timing(asph_sim* sim, double ms_sum[ASPH_KT_COUNT], uint64_t
 int asph_set_level(asph_sim* sim, const float* level_ref_order, uint64_t n);
 void asph_set_step_number(asph_sim* sim, uint64_t step_number);
 uint64_t asph_adapt_rounds(const asph_sim* sim);
+/* ready-list entries of the partner searches whose donor had been decided already, over the handle's lifetime (a
+ * consistency counter of the CUDA implementation; expected 0, always 0 on the CPU oracle) */
+uint64_t asph_debug_greedy_duplicates(const asph_sim* sim);
 
 /* ------------------------------------------------------------------ pure helpers (host side, no GPU needed)
  * sph_kernels.rs:49-71 (cubic spline, h = smoothing length, support 2h) and

@@ -205,6 +205,7 @@ void oracle_set_step_number(asph_sim* sim, uint64_t k) { sim->s.step_number = k;
 int asph_set_level(asph_sim* sim, const float* level, uint64_t n) { return oracle_set_level(sim, level, n); }
 void asph_set_step_number(asph_sim* sim, uint64_t k) { oracle_set_step_number(sim, k); }
 uint64_t asph_adapt_rounds(const asph_sim*) { return 0; }
+uint64_t asph_debug_greedy_duplicates(const asph_sim*) { return 0; }
 void oracle_set_threads(int n) {
 #ifdef _OPENMP
   if (n > 0) omp_set_num_threads(n);
