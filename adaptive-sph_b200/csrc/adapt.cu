@@ -91,7 +91,7 @@ __device__ __forceinline__ bool static_eligible(const AdaptArgs& A, const Packed
 
 __global__ void k_partner_ctl_reset(StepCtl* ctl) {
   ctl->work_n[0] = 0; ctl->work_n[1] = 0; ctl->ready_n = 0; ctl->rounds = 0; ctl->n_claims = 0; ctl->greedy_done = 0;
-  ctl->mail_sent = 0; ctl->greedy_barriers = 0; ctl->validate_why = 0; ctl->greedy_duplicates = 0;
+  ctl->mail_sent = 0; ctl->mail_n[0] = 0; ctl->mail_n[1] = 0; ctl->greedy_barriers = 0; ctl->validate_why = 0; ctl->greedy_duplicates = 0;
 }
 
 // ---- the greedy partner search as one persistent cooperative kernel ------------------------------------------------
@@ -210,17 +210,9 @@ k_greedy(const GreedyArgs G, const PackedParams P, const CoopPeer C) {
   volatile uint32_t* ready_n = &ctl->ready_n;
   unsigned int bar = C.seq0 + 1u;  // PEER: number of the next cross-GPU barrier; mail posted before it uses its parity
 
-  bool mailed = false;  // this thread has written to another GPU since the last exchange
   auto is_ghost = [&](uint32_t i) { return PEER && nb_ghost(__ldg(&A.L.cnt[i])); };
   // one message to the neighbour on `side` (0 = rank - 1)
-  auto mail = [&](int side, uint32_t slot, uint32_t kind, uint32_t payload) {
-    const uint32_t par = bar & 1u;
-    const uint32_t k = atomicAdd_system(&C.nb_ctl[side]->mbox_n[par][1 - side], 1u);
-    if (k < C.mbox_cap) C.nb_mbox[side][size_t(par * 2u + uint32_t(1 - side)) * C.mbox_cap + k] = make_uint2(slot | (kind << 28), payload);
-    else atomicOr(&ctl->error_flags, ERRF_PEER_TIMEOUT);
-    ctl->mail_sent = bar;
-    mailed = true;
-  };
+  auto mail = [&](int side, uint32_t slot, uint32_t kind, uint32_t payload) { coop_mail(C, ctl, bar, side, slot | (kind << 28), payload); };
   // what the ghost copies of owned particle i have to hear
   auto mail_copies = [&](uint32_t i, uint32_t kind, uint32_t payload) {
 #pragma unroll
@@ -284,10 +276,10 @@ k_greedy(const GreedyArgs G, const PackedParams P, const CoopPeer C) {
   };
   // PEER: fence, meet the other GPUs, take in their mail; returns whether any rank has work or mail outstanding
   auto exchange = [&](uint32_t pout) {
-    if (mailed) { __threadfence_system(); mailed = false; }  // only the threads that wrote to another GPU pay for a system-scope fence
     grid.sync();
     if (gtid == 0) {
-      const unsigned int mine = (work_n[pout] > 0u ? 1u : 0u) | (*reinterpret_cast<volatile unsigned int*>(&ctl->mail_sent) == bar ? 2u : 0u);
+      const bool sent = coop_publish_mail(C, ctl, bar);
+      const unsigned int mine = (work_n[pout] > 0u ? 1u : 0u) | (sent ? 2u : 0u);
       const unsigned int all = coop_barrier(C, bar, mine, ctl);
       *C.verdict = ((all & 3u) != 0u && !(all & 0x80000000u)) ? 1u : 0u;
       __threadfence();
@@ -315,7 +307,6 @@ k_greedy(const GreedyArgs G, const PackedParams P, const CoopPeer C) {
       }
     }
     grid.sync();
-    if (gtid == 0) { C.self->mbox_n[par][0] = 0u; C.self->mbox_n[par][1] = 0u; }  // next written two barriers from now
     bar++;
     return go;
   };

@@ -34,6 +34,7 @@ __global__ void k_level_reset(StepCtl* ctl) {
   ctl->front_n[0] = 0; ctl->front_n[1] = 0; ctl->cand_n[0] = 0; ctl->cand_n[1] = 0;
   ctl->level_live[0] = 0; ctl->level_live[1] = 0;
   ctl->level_sweep = 0; ctl->level_done = 0;
+  ctl->mail_n[0] = 0; ctl->mail_n[1] = 0;
 }
 
 // K3 for particle i; returns whether it is a surface particle
@@ -185,15 +186,18 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
           cand[u] = k < ce;
           iu[u] = cand[u] ? col.get(k) : 0u;
         }
+        // the stamp and the position of a neighbour are requested together (most neighbours of a front particle are still
+        // unassigned, so few of the positions are wasted): one round trip less in the chain
+        float2 ou[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) su[u] = cand[u] ? __ldcg(stamp + iu[u]) : 0;
+        for (int u = 0; u < 4; u++) {
+          su[u] = cand[u] ? __ldcg(stamp + iu[u]) : 0;
+          ou[u] = cand[u] ? __ldg(reinterpret_cast<const float2*>(xyhm + iu[u])) : make_float2(0.f, 0.f);
+        }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           cand[u] = cand[u] && (su[u] == -1 || su[u] == t) && !(PEER && nb_ghost(__ldg(&L.cnt[iu[u]])));
         }
-        float4 ou[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) ou[u] = cand[u] ? __ldg(&xyhm[iu[u]]) : make_float4(0.f, 0.f, 0.f, 0.f);
         bool won[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -247,22 +251,18 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
       const unsigned int seq = P.seq0 + unsigned(t), par = seq & 1u;
       // mail the border particles assigned in this sweep to their ghost copies
       const uint32_t e0 = exported[pout], e1 = tail[pout];
-      bool mailed = false;
       for (uint32_t f = e0 + gtid; f < e1; f += gthreads) {
         const uint32_t i = __ldcg(fout + f);
         const unsigned int bits = __ldcg(level_bits + i);
 #pragma unroll
         for (int side = 0; side < 2; side++) {
           const uint32_t sl = __ldg(&P.rslot[side][i]);
-          if (sl == 0xffffffffu || !P.nb_mbox[side]) continue;
-          const uint32_t k = atomicAdd_system(&P.nb_ctl[side]->mbox_n[par][1 - side], 1u);  // I am that neighbour's other side
-          if (k < P.mbox_cap) P.nb_mbox[side][size_t(par * 2u + uint32_t(1 - side)) * P.mbox_cap + k] = make_uint2(sl, bits);
-          mailed = true;
+          if (sl != 0xffffffffu && P.nb_mbox[side]) coop_mail(P, ctl, seq, side, sl, bits);
         }
       }
-      if (mailed) __threadfence_system();  // only the few threads that wrote to another GPU pay for a system-scope fence
       grid.sync();
       if (gtid == 0) {
+        coop_publish_mail(P, ctl, seq);
         const unsigned int mine = (e1 > e0 ? 1u : 0u) | (live_sweep[pout] == t ? 2u : 0u);
         const unsigned int all = coop_barrier(P, seq, mine, ctl);
         *P.verdict = ((all & 3u) == 3u && !(all & 0x80000000u) && t <= (1 << 29)) ? 1u : 0u;
@@ -283,7 +283,6 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
         }
       }
       grid.sync();
-      if (gtid == 0) { P.self->mbox_n[par][0] = 0u; P.self->mbox_n[par][1] = 0u; }  // next written two barriers from now
       exported[pout] = tail[pout];
     }
   }
@@ -355,7 +354,7 @@ int launch_level_estimation(asph_sim* sim) {
     int per_sm = 0, per_sm_peer = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<false>, kPropThreads, 0));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_peer, k_propagate<true>, kPropThreads, 0));
-    sim->prop_grid = std::max(1, std::min(std::min(per_sm, per_sm_peer), 2) * sim->sm_count);  // more blocks only make the barrier dearer
+    sim->prop_grid = std::max(1, std::min(std::min(per_sm, per_sm_peer), 2) * sim->sm_count);  // a third block per SM (42 registers, spills) measured no faster
   }
   // a front rarely holds more than a few ten thousand particles: one warp each
   uint32_t grid = uint32_t(std::max(1, std::min<int>(sim->prop_grid, int((n + 4u * kPropThreads - 1) / (4u * kPropThreads)))));

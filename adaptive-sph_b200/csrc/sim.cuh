@@ -89,6 +89,7 @@ struct StepCtl {
   uint32_t n_new;  // particle count after merge / split
   uint32_t n_shared, n_merged, n_split_parents;
   uint32_t work_n[2], rounds, n_claims, ready_n, greedy_done;
+  uint32_t mail_n[2];                   // several GPUs: messages written into the mailbox of neighbour rank - 1 / rank + 1 since the last barrier
   uint32_t mail_sent, greedy_barriers;  // several GPUs: number of the last barrier mail was posted for; barriers a search ran
   uint32_t greedy_duplicates;             // ready-list entries whose donor had been decided already (diagnostics; expected 0)
   uint32_t validate_why, validate_at[4];  // first broken partner invariant: which, particle, counter, partner, what was found
@@ -156,7 +157,8 @@ struct PeerCtl {
 };
 // What a persistent cooperative kernel needs to talk to the other GPUs (by value; self == nullptr: single GPU).
 // A message is a uint2 {ghost slot on the receiving rank, payload}: a border particle's new value travels to its ghost
-// copy as one 8-byte store into the neighbour's mailbox over NVLink, after one system-scope atomic for the position.
+// copy as one posted 8-byte store into the neighbour's mailbox over NVLink.  The sender counts its messages in its own
+// memory (StepCtl::mail_n) and hands the count over with the barrier (coop_publish_mail): nothing waits for a round trip.
 struct CoopPeer {
   PeerCtl* self;
   PeerCtl* const* all_ctl;   // every rank's PeerCtl (device array)
@@ -383,6 +385,26 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 // synchronised and fenced (system scope): every rank leaves seq << 4 | payload with every other rank and waits for
 // theirs; returns the OR of all payloads, or 0x80000000 if a rank did not show up within about 2 s (the step then fails
 // on the host instead of hanging).  A rank can be at most one barrier ahead of another, hence two flag sets.
+// position of the next message to the neighbour on `side` (0 = rank - 1) before barrier number `seq`; ~0 = mailbox full
+__device__ __forceinline__ void coop_mail(const CoopPeer& P, StepCtl* ctl, unsigned int seq, int side, uint32_t slot_and_kind, uint32_t payload) {
+  const uint32_t par = seq & 1u;
+  const uint32_t k = atomicAdd(&ctl->mail_n[side], 1u);
+  if (k < P.mbox_cap) P.nb_mbox[side][size_t(par * 2u + uint32_t(1 - side)) * P.mbox_cap + k] = make_uint2(slot_and_kind, payload);  // I am that neighbour's other side
+  else atomicOr(&ctl->error_flags, ERRF_PEER_TIMEOUT);
+}
+// ONE thread, after the grid has synchronised behind the last coop_mail and before coop_barrier(seq): the message counts
+// go to the neighbours (ordered before the barrier flag by its release); returns whether anything was mailed
+__device__ __forceinline__ bool coop_publish_mail(const CoopPeer& P, StepCtl* ctl, unsigned int seq) {
+  const uint32_t par = seq & 1u;
+  bool any = false;
+  for (int side = 0; side < 2; side++) {
+    const uint32_t c = min(*reinterpret_cast<volatile uint32_t*>(&ctl->mail_n[side]), P.mbox_cap);
+    if (P.nb_ctl[side]) *reinterpret_cast<volatile unsigned int*>(&P.nb_ctl[side]->mbox_n[par][1 - side]) = c;
+    any = any || c != 0u;
+    ctl->mail_n[side] = 0u;
+  }
+  return any;
+}
 __device__ __forceinline__ unsigned int coop_barrier(const CoopPeer& P, unsigned int seq, unsigned int payload, StepCtl* ctl) {
   const unsigned int par = seq & 1u, word = (seq << 4) | (payload & 15u);
   for (int q = 0; q < P.nranks; q++)
