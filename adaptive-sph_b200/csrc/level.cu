@@ -132,6 +132,7 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
             uint32_t* __restrict__ front0, uint32_t* __restrict__ front1, StepCtl* ctl, float neg_dmax, int use_cutoff, const CoopPeer P) {
   cg::grid_group grid = cg::this_grid();
   constexpr uint32_t kStage = 192;
+  constexpr uint32_t kLanes = 8, kPerWarp = 32 / kLanes;
   __shared__ uint32_t s_stage[kPropThreads / 32][kStage];
   __shared__ uint32_t s_count[kPropThreads / 32], s_base;
   unsigned int* level_bits = reinterpret_cast<unsigned int*>(level);
@@ -155,12 +156,69 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
     const uint32_t* __restrict__ fin = pin ? front1 : front0;
     uint32_t* __restrict__ fout = pout ? front1 : front0;
     bool live = false;
-    // Eight lanes per front particle, four front particles per warp, and up to four neighbours per lane requested
-    // together: a sweep is a chain of dependent memory round trips (front entry -> column header -> list entry ->
-    // stamp -> atomics), so what counts is how many of them are in flight at once, not how many lanes are busy.
-    const uint32_t sub = lane & 7u, grp = lane >> 3;
     uint32_t wcount = 0;  // claims staged by this warp in this sweep (warp-uniform)
-    for (uint32_t f0 = begin + gwarp * 4u; f0 < end; f0 += nwarps * 4u) {
+    // Up to 4 * stride neighbours of front particle j, four per lane requested together: lane handles k0 + first + stride * u.
+    // Called by the whole warp with warp-uniform trip counts (ballots inside); a lane without a particle passes ce = 0.
+    auto push = [&](const float4& me, float lj, uint32_t ce, const NbCol& col, uint32_t k0, uint32_t first, uint32_t stride) {
+      uint32_t iu[4];
+      int su[4];
+      bool cand[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t k = k0 + first + stride * uint32_t(u);
+        cand[u] = k < ce;
+        iu[u] = cand[u] ? col.get(k) : 0u;
+      }
+      // the stamp and the position of a neighbour are requested together (most neighbours of a front particle are still
+      // unassigned, so few of the positions are wasted): one round trip less in the chain
+      float2 ou[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        su[u] = cand[u] ? __ldcg(stamp + iu[u]) : 0;
+        ou[u] = cand[u] ? __ldg(reinterpret_cast<const float2*>(xyhm + iu[u])) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        cand[u] = cand[u] && (su[u] == -1 || su[u] == t) && !(PEER && nb_ghost(__ldg(&L.cnt[iu[u]])));
+      }
+      bool won[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        won[u] = false;
+        if (cand[u]) {
+          const float d = __fsqrt_rn(dist_sq_exact(__fsub_rn(me.x, ou[u].x), __fsub_rn(me.y, ou[u].y)));
+          const float v = __fsub_rn(lj, d);  // <= 0: the largest float is the smallest bit pattern
+          atomicMin(level_bits + iu[u], __float_as_uint(v));
+          if (su[u] == -1) won[u] = atomicCAS(stamp + iu[u], -1, t) == -1;
+          if (!use_cutoff || v > neg_dmax) live = true;
+        }
+      }
+      // the newly claimed particles go into this warp's staging buffer: the tail of front(t) is ONE word, and an atomic per
+      // warp and batch on it (some ten thousand per sweep, all to the same address) was most of a sweep's time
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const unsigned int mask = __ballot_sync(0xffffffffu, won[u]);
+        if (mask) {
+          const uint32_t cnt = uint32_t(__popc(mask));
+          if (wcount + cnt > kStage) {  // full (a sweep rarely claims more than a few dozen per warp): to the front right away
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&ctl->front_n[pout], wcount);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (uint32_t e = lane; e < wcount; e += 32u) fout[base + e] = s_stage[wid][e];
+            __syncwarp();
+            wcount = 0;
+          }
+          if (won[u]) s_stage[wid][wcount + uint32_t(__popc(mask & ((1u << lane) - 1u)))] = iu[u];
+          wcount += cnt;
+        }
+      }
+    };
+    // A sweep is a chain of dependent memory round trips (front entry -> column header -> list entry -> stamp -> atomics)
+    // ended by a grid-wide barrier, so its time is the time of the SLOWEST warp.  Eight lanes per front particle, four
+    // particles per warp cover a column of up to 32 neighbours in one round; a longer column (a coarse particle next to
+    // fine ones has a hundred and more) would take its eight lanes many rounds, so it is handed to the whole warp afterwards.
+    const uint32_t sub = lane & (kLanes - 1u), grp = lane / kLanes;
+    for (uint32_t f0 = begin + gwarp * kPerWarp; f0 < end; f0 += nwarps * kPerWarp) {
       const uint32_t f = f0 + grp;
       const bool have = f < end;
       uint32_t j = 0, ce = 0;
@@ -174,61 +232,17 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
         ce = __ldg(&L.cnt_ext[j]);
         col = NbCol(L, j);
       }
-      uint32_t ce_max = ce;
-      for (int o = 16; o >= 8; o >>= 1) ce_max = max(ce_max, __shfl_xor_sync(0xffffffffu, ce_max, o));
-      for (uint32_t k0 = 0; k0 < ce_max; k0 += 32u) {
-        uint32_t iu[4];
-        int su[4];
-        bool cand[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const uint32_t k = k0 + sub + 8u * uint32_t(u);
-          cand[u] = k < ce;
-          iu[u] = cand[u] ? col.get(k) : 0u;
-        }
-        // the stamp and the position of a neighbour are requested together (most neighbours of a front particle are still
-        // unassigned, so few of the positions are wasted): one round trip less in the chain
-        float2 ou[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          su[u] = cand[u] ? __ldcg(stamp + iu[u]) : 0;
-          ou[u] = cand[u] ? __ldg(reinterpret_cast<const float2*>(xyhm + iu[u])) : make_float2(0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          cand[u] = cand[u] && (su[u] == -1 || su[u] == t) && !(PEER && nb_ghost(__ldg(&L.cnt[iu[u]])));
-        }
-        bool won[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          won[u] = false;
-          if (cand[u]) {
-            const float d = __fsqrt_rn(dist_sq_exact(__fsub_rn(me.x, ou[u].x), __fsub_rn(me.y, ou[u].y)));
-            const float v = __fsub_rn(lj, d);  // <= 0: the largest float is the smallest bit pattern
-            atomicMin(level_bits + iu[u], __float_as_uint(v));
-            if (su[u] == -1) won[u] = atomicCAS(stamp + iu[u], -1, t) == -1;
-            if (!use_cutoff || v > neg_dmax) live = true;
-          }
-        }
-        // the newly claimed particles go into this warp's staging buffer: the tail of front(t) is ONE word, and an atomic per
-        // warp and batch on it (some ten thousand per sweep, all to the same address) was most of a sweep's time
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const unsigned int mask = __ballot_sync(0xffffffffu, won[u]);
-          if (mask) {
-            const uint32_t cnt = uint32_t(__popc(mask));
-            if (wcount + cnt > kStage) {  // full (a sweep rarely claims more than a few dozen per warp): to the front right away
-              uint32_t base = 0;
-              if (lane == 0) base = atomicAdd(&ctl->front_n[pout], wcount);
-              base = __shfl_sync(0xffffffffu, base, 0);
-              for (uint32_t e = lane; e < wcount; e += 32u) fout[base + e] = s_stage[wid][e];
-              __syncwarp();
-              wcount = 0;
-            }
-            if (won[u]) s_stage[wid][wcount + uint32_t(__popc(mask & ((1u << lane) - 1u)))] = iu[u];
-            wcount += cnt;
-          }
-        }
+      const bool big = ce > 4u * kLanes;
+      const unsigned int bigmask = __ballot_sync(0xffffffffu, big && sub == 0u);
+      if (__any_sync(0xffffffffu, have && !big)) push(me, lj, big ? 0u : ce, col, 0u, sub, kLanes);
+      for (unsigned int m = bigmask; m; m &= m - 1u) {
+        const int src = __ffs(m) - 1;
+        const uint32_t jb = __shfl_sync(0xffffffffu, j, src);
+        const float4 meb = __ldg(&xyhm[jb]);
+        const float ljb = __ldcg(level + jb);
+        const uint32_t ceb = __ldg(&L.cnt_ext[jb]);
+        const NbCol colb(L, jb);
+        for (uint32_t k0 = 0; k0 < ceb; k0 += 128u) push(meb, ljb, ceb, colb, k0, lane, 32u);
       }
     }
     // one atomic per block: the warps' staged claims behind one another at the tail of front(t)
