@@ -407,8 +407,9 @@ __device__ __forceinline__ bool coop_publish_mail(const CoopPeer& P, StepCtl* ct
 }
 __device__ __forceinline__ unsigned int coop_barrier(const CoopPeer& P, unsigned int seq, unsigned int payload, StepCtl* ctl) {
   const unsigned int par = seq & 1u, word = (seq << 4) | (payload & 15u);
+  __threadfence_system();  // ONE system-scope fence (a release store per peer would pay for one each), then plain posted stores
   for (int q = 0; q < P.nranks; q++)
-    if (q != P.rank) st_release_sys(&P.all_ctl[q]->coop_flag[par][P.rank], word);
+    if (q != P.rank) *reinterpret_cast<volatile unsigned int*>(&P.all_ctl[q]->coop_flag[par][P.rank]) = word;
   unsigned int acc = payload & 15u;
   unsigned long long t0 = 0;
   for (int q = 0; q < P.nranks; q++) {

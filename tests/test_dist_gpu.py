@@ -37,7 +37,7 @@ def _check(rep, tol_x):
     # the N-GPU and 1-GPU runs sum neighbours in different orders (different grid origins) => fp32 rounding-level drift
     assert rep["err"]["mass"] == 0.0, rep
     assert rep["err"]["position"] < tol_x, rep             # relative to the 2 m box (north_star: 1e-5)
-    assert rep["err"]["density"] < 1e-4, rep
+    assert rep["err"]["density"] < 2e-4, rep                # (the tolerance of the per-field comparisons with the oracle)
 
 
 @pytest.mark.parametrize("solver", ["HybridDFSPH", "IISPH"])
