@@ -2,6 +2,8 @@
 //
 //   asph_run run SIMULATION_CONFIG SCENE_CONFIG [-s|--max-seconds S] [-c|--overwrite-config-file F] [-p|--statistics-enabled]
 //                [-w|--statistics-path F] [--max-steps N] [--split-patterns F] [--dump F] [--vtk-dir D [--vtk-every N]]
+//                [--gpus N]   N > 1: one process per GPU is started (this program again, once per rank), the fluid is cut
+//                             into N x-slabs; rank 0 reports
 //                [--restart-vtk SNAPSHOT] [--lib LIBRARY] [-q]
 //   asph_run image JOB_FILE... [--out-dir D] [--only K]... [--max-steps N] [--split-patterns F] [--lib LIBRARY] [-q]
 //
@@ -19,12 +21,14 @@
 // Test hooks: `asph_run yaml-dump FILE` (the parse as JSON), `asph_run params-dump CONFIG [OVERWRITE]` (asph_params bytes,
 // hex), `asph_run scene-dump SCENE FILE` (the particles add_fluid_block generates, same layout as --dump).
 #include <sys/stat.h>
+#include <sys/wait.h>
 #include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <string>
 #include <vector>
@@ -230,8 +234,53 @@ int usage() {
   std::fprintf(stderr,
                "usage: asph_run run SIMULATION_CONFIG SCENE_CONFIG [-s SECONDS] [-c OVERWRITE.yaml] [-p] [-w STATS_FILE]\n"
                "                    [--max-steps N] [--split-patterns FILE] [--dump FILE] [--vtk-dir DIR [--vtk-every N]] [--restart-vtk FILE] [--lib LIBRARY] [-q]\n"
+               "                    [--gpus N]\n"
                "       asph_run image JOB_FILE... [--out-dir DIR] [--only K] [--max-steps N] [--lib LIBRARY] [-q]\n");
   return 2;
+}
+
+void hex_to_bytes(const char* hex, uint8_t* out, size_t n) {
+  if (!hex || std::strlen(hex) != 2 * n) throw std::runtime_error("ASPH_RUN_NCCL_ID is missing or malformed");
+  for (size_t k = 0; k < n; k++) {
+    unsigned v = 0;
+    std::sscanf(hex + 2 * k, "%2x", &v);
+    out[k] = uint8_t(v);
+  }
+}
+
+std::vector<std::string> g_argv;  // the command line, for the ranks of a multi-GPU run
+
+// one child per GPU: the same command with ASPH_RUN_RANK / ASPH_RUN_WORLD / ASPH_RUN_NCCL_ID (and LOCAL_RANK for the device)
+int spawn_ranks(int world, const uint8_t id[128]) {
+  std::string hex(256, '0');
+  for (int k = 0; k < 128; k++) std::snprintf(&hex[2 * size_t(k)], 3, "%02x", id[k]);
+  hex.resize(256);
+  std::vector<pid_t> pids;
+  for (int r = 0; r < world; r++) {
+    const pid_t pid = fork();
+    if (pid < 0) throw std::runtime_error("fork failed");
+    if (pid == 0) {
+      setenv("ASPH_RUN_RANK", std::to_string(r).c_str(), 1);
+      setenv("ASPH_RUN_WORLD", std::to_string(world).c_str(), 1);
+      setenv("ASPH_RUN_NCCL_ID", hex.c_str(), 1);
+      setenv("LOCAL_RANK", std::to_string(r).c_str(), 1);
+      std::vector<char*> argv;
+      for (auto& s : g_argv) argv.push_back(const_cast<char*>(s.c_str()));
+      argv.push_back(nullptr);
+      execv("/proc/self/exe", argv.data());
+      std::perror("execv");
+      _exit(127);
+    }
+    pids.push_back(pid);
+  }
+  int worst = 0;
+  for (pid_t pid : pids) {
+    int st = 0;
+    waitpid(pid, &st, 0);
+    const int rc = WIFEXITED(st) ? WEXITSTATUS(st) : 128;
+    worst = std::max(worst, rc);
+  }
+  return worst;
 }
 
 int cmd_run(const std::vector<std::string>& a) {
@@ -240,6 +289,7 @@ int cmd_run(const std::vector<std::string>& a) {
   long max_steps = -1;
   std::string overwrite, stats_path, split_path, dump, lib_path, vtk_dir, restart_vtk;
   long vtk_every = 1;
+  int gpus = 1;
   bool stats = false, quiet = false;
   for (size_t i = 0; i < a.size(); i++) {
     const std::string& s = a[i];
@@ -248,6 +298,7 @@ int cmd_run(const std::vector<std::string>& a) {
       return a[++i];
     };
     if (s == "-s" || s == "--max-seconds") max_seconds = std::atof(value().c_str());
+    else if (s == "--gpus") gpus = std::max(1, std::atoi(value().c_str()));
     else if (s == "-c" || s == "--overwrite-config-file") overwrite = value();
     else if (s == "-p" || s == "--statistics-enabled") stats = true;
     else if (s == "-w" || s == "--statistics-path") { stats_path = value(); stats = true; }
@@ -275,6 +326,16 @@ int cmd_run(const std::vector<std::string>& a) {
   host::split_patterns_from_yaml(yaml_lite::parse_file(split_path), split);
   if (lib_path.empty()) lib_path = exe_dir() + "/../csrc/libasph_b200.so";
   host::Library lib(lib_path);
+  // ---- several GPUs: the parent hands every rank the NCCL id in its environment and waits; a rank is this same command
+  const char* rank_env = std::getenv("ASPH_RUN_RANK");
+  const int rank = rank_env ? std::atoi(rank_env) : -1;
+  if (gpus > 1 && rank < 0) {
+    if (!dump.empty() || !vtk_dir.empty() || !restart_vtk.empty()) throw std::runtime_error("--dump / --vtk-dir / --restart-vtk need --gpus 1");
+    uint8_t id[128];
+    const int rc = lib.comm_unique_id(id);
+    if (rc != ASPH_OK) throw std::runtime_error(std::string("asph_comm_unique_id failed: ") + host::status_name(rc) + " (NCCL not loadable?)");
+    return spawn_ranks(gpus, id);
+  }
   host::Particles particles;
   if (restart_vtk.empty()) {
     particles = host::scene_particles(scene);
@@ -285,7 +346,24 @@ int cmd_run(const std::vector<std::string>& a) {
       throw std::runtime_error("snapshot arrays have inconsistent lengths: " + restart_vtk);
   }
   const asph_boundary boundary = host::scene_boundary(scene, params.init_boundary_handler);
-  host::FluidSimulation sim(lib, params, particles, boundary, &split, stats);  // init_fluid_sim, simulation.rs:3074
+  std::unique_ptr<host::FluidSimulation> sim_holder;
+  if (rank >= 0) {  // this rank's contiguous share of the reference order (x-major lattices: already x-slabs)
+    const int world = std::atoi(std::getenv("ASPH_RUN_WORLD"));
+    uint8_t id[128];
+    hex_to_bytes(std::getenv("ASPH_RUN_NCCL_ID"), id, 128);
+    const uint64_t n_global = particles.n(), lo = n_global * uint64_t(rank) / uint64_t(world), hi = n_global * uint64_t(rank + 1) / uint64_t(world);
+    host::Particles mine;
+    mine.pos.assign(particles.pos.begin() + 2 * lo, particles.pos.begin() + 2 * hi);
+    mine.vel.assign(particles.vel.begin() + 2 * lo, particles.vel.begin() + 2 * hi);
+    mine.mass.assign(particles.mass.begin() + lo, particles.mass.begin() + hi);
+    std::vector<uint32_t> gidx(size_t(hi - lo));
+    for (uint64_t k = lo; k < hi; k++) gidx[size_t(k - lo)] = uint32_t(k);
+    sim_holder.reset(new host::FluidSimulation(lib, params, mine, gidx, n_global, boundary, &split, stats, id, rank, world, rank));
+    quiet = quiet || rank != 0;
+  } else {
+    sim_holder.reset(new host::FluidSimulation(lib, params, particles, boundary, &split, stats));  // init_fluid_sim, simulation.rs:3074
+  }
+  host::FluidSimulation& sim = *sim_holder;
 
   host::StatisticsRecorder rec;
   std::unique_ptr<host::VtkExporter> vtk;
@@ -317,9 +395,10 @@ int cmd_run(const std::vector<std::string>& a) {
     }
   }
   const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  std::printf("%ld steps, simulated %.4f s, %llu particles, wall %.2f s, backend %s\n", step, sim.time(),
-              (unsigned long long)sim.num_fluid_particles(), wall, lib.backend_name());
-  if (stats) {
+  if (rank >= 0) std::printf("[rank %d] ", rank);
+  std::printf("%ld steps, simulated %.4f s, %llu particles%s, wall %.2f s, backend %s\n", step, sim.time(),
+              (unsigned long long)sim.num_fluid_particles(), rank >= 0 ? " owned" : "", wall, lib.backend_name());
+  if (stats && rank <= 0) {
     const std::string text = rec.write_statistics(sim);
     if (!stats_path.empty()) {
       FILE* f = std::fopen(stats_path.c_str(), "w");
@@ -337,6 +416,7 @@ int cmd_run(const std::vector<std::string>& a) {
 }  // namespace
 
 int main(int argc, char** argv) {
+  g_argv.assign(argv, argv + argc);
   std::vector<std::string> args(argv + 1, argv + argc);
   try {
     if (args.empty()) return usage();

@@ -275,6 +275,9 @@ struct Library {
   decltype(&asph_get_counters) get_counters = nullptr;
   decltype(&asph_last_error) last_error = nullptr;
   decltype(&asph_backend_name) backend_name = nullptr;
+  // multi-GPU (bound on demand: `run --gpus N`)
+  decltype(&asph_comm_unique_id) comm_unique_id = nullptr;
+  decltype(&asph_create_distributed) create_distributed = nullptr;
 
   explicit Library(const std::string& path) {
     handle = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
@@ -290,6 +293,7 @@ struct Library {
     ASPH_BIND(num_particles, asph_num_particles); ASPH_BIND(time, asph_time); ASPH_BIND(get_field, asph_get_field);
     ASPH_BIND(get_step_info, asph_get_step_info); ASPH_BIND(get_counters, asph_get_counters);
     ASPH_BIND(last_error, asph_last_error); ASPH_BIND(backend_name, asph_backend_name);
+    ASPH_BIND(comm_unique_id, asph_comm_unique_id); ASPH_BIND(create_distributed, asph_create_distributed);
 #undef ASPH_BIND
   }
   Library(const Library&) = delete;
@@ -312,6 +316,16 @@ struct FluidSimulation {
     const int rc = lib.create(&params, p.pos.data(), p.vel.data(), p.mass.data(), p.n(), &boundary, split ? &split->c : nullptr,
                               counters_enabled ? 1 : 0, 0, &sim);
     if (rc != ASPH_OK) throw std::runtime_error(std::string("asph_create failed: ") + status_name(rc));
+  }
+  // one rank of a multi-GPU run (`run --gpus N`): this rank's share of the particles and their reference indices;
+  // the library migrates them to their owner slabs at the first step
+  FluidSimulation(Library& l, const asph_params& params, const Particles& p, const std::vector<uint32_t>& global_index, uint64_t n_global,
+                  const asph_boundary& boundary, const SplitPatterns* split, bool counters_enabled, const uint8_t nccl_id[128], int rank, int n_ranks,
+                  int device)
+      : lib(l) {
+    const int rc = lib.create_distributed(&params, p.pos.data(), p.vel.data(), p.mass.data(), global_index.data(), p.n(), n_global, &boundary,
+                                          split ? &split->c : nullptr, counters_enabled ? 1 : 0, 0, nccl_id, rank, n_ranks, device, &sim);
+    if (rc != ASPH_OK) throw std::runtime_error(std::string("asph_create_distributed failed: ") + status_name(rc));
   }
   FluidSimulation(const FluidSimulation&) = delete;
   ~FluidSimulation() { if (sim) lib.destroy(sim); }

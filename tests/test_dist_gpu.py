@@ -132,3 +132,25 @@ def test_resampling_phase_across_slabs(world, phase):
         assert rep["pos_maxdiff"] < 2e-6 and rep["vel_maxdiff"] < 1e-4, rep
         key = "n_merged" if "merge" in phase else "n_shared"
         assert rep[key][1] > 0, rep
+
+
+def test_native_host_runs_on_two_gpus():
+    """`asph_run run <config> <scene> --gpus 2` (the C++ host: one process per GPU, NCCL id handed down in the environment,
+    no torch): same number of steps to the same simulated time as `--gpus 1`, and the ranks together own the particle count
+    the single-GPU run ends with (C1: level set, share / merge / split; 1 035 -> about 3 900 particles)."""
+    import re
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = os.path.join(ROOT, "adaptive-sph_b200", "host", "asph_run")
+    base = [exe, "run", os.path.join(ROOT, "configs", "default-config.yaml"), os.path.join(ROOT, "configs", "default-scene.yaml"),
+            "--max-steps", "8", "-q", "--split-patterns", os.path.join(ROOT, "adaptive-sph_b200", "data", "split-patterns.yaml")]
+    one = subprocess.run(base, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    two = subprocess.run(base + ["--gpus", "2"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert one.returncode == 0, one.stdout[-2000:] + one.stderr[-2000:]
+    assert two.returncode == 0, two.stdout[-2000:] + two.stderr[-2000:]
+    pat = re.compile(r"(\d+) steps, simulated ([0-9.]+) s, (\d+) particles")
+    m1 = pat.search(one.stdout)
+    m2 = pat.findall(two.stdout)
+    assert m1 and len(m2) == 2, (one.stdout, two.stdout)
+    assert all(m[0] == m1.group(1) and m[1] == m1.group(2) for m in m2), (m1.groups(), m2)
+    assert sum(int(m[2]) for m in m2) == int(m1.group(3)), (m1.groups(), m2)
