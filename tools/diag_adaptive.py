@@ -1,4 +1,4 @@
-"""Per-step diagnostics of the adaptive dam break (tools/bench_adaptive.py recipe): particle count, level-set sweeps, greedy
+"""Per-step diagnostics of the adaptive dam break (the recipe of bench.py without the ramp): particle count, level-set sweeps, greedy
 rounds of the partner searches, resampling statistics and the device time of every PerformanceCounters label, one JSON
 line per step.
 
