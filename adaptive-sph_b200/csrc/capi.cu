@@ -497,6 +497,7 @@ int asph_create(const asph_params* params, const float* pos, const float* vel, c
   memset(sim->ctl_host, 0, sizeof(StepCtl));
   sim->counters = counters_enabled != 0;
   if (const char* e = getenv("ASPH_BULK")) sim->bulk = atoi(e) != 0;
+  if (const char* e = getenv("ASPH_CELL_SCALE")) sim->cell_scale = std::min(1.f, std::max(0.25f, float(atof(e))));
   if (boundary) sim->boundary = *boundary; else memset(&sim->boundary, 0, sizeof(sim->boundary));
   {  // λ / λ′ lookup tables (BoundaryWinchenbach2020::new, boundary_winchenbach2020.rs:33-45)
     std::vector<float> lam, dlam;

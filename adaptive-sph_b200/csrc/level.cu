@@ -317,17 +317,25 @@ k_smooth(uint32_t n, Lists L, const float2* __restrict__ pos, const float4* __re
   const uint32_t cn = nb_cn(L.cnt[i]);
   const NbCol col(L, i);
   float num = 0.f, den = 0.f;
-  for (uint32_t k = 0; k < cn; k++) {
-    const uint32_t j = col.get(k);
-    const float2 xj = __ldg(&pos[j]);
-    const float4 o = __ldg(&xyhm[j]);
-    const float lj = __ldg(&level[j]);
-    const float dx = xi.x - xj.x, dy = xi.y - xj.y;
-    const float w = kernel_w(sqrtf(dx * dx + dy * dy), (hi + o.z) * 0.5f);
-    const float dist = (lj > 0.f) ? -dmax : fmaxf(lj, -dmax);
-    const float vw = o.w / __ldg(&rho[j]) * w;
-    num += dist * vw;
-    den += vw;
+  for (uint32_t k0 = 0; k0 < cn; k0 += 4u) {  // four neighbours' records requested together, summed in list order
+    uint32_t j[4];
+    float2 xj[4];
+    float4 o[4];
+    float lj[4], rj[4];
+#pragma unroll
+    for (uint32_t u = 0; u < 4u; u++) j[u] = col.get(min(k0 + u, cn - 1u));
+#pragma unroll
+    for (uint32_t u = 0; u < 4u; u++) { xj[u] = __ldg(&pos[j[u]]); o[u] = __ldg(&xyhm[j[u]]); lj[u] = __ldg(&level[j[u]]); rj[u] = __ldg(&rho[j[u]]); }
+#pragma unroll
+    for (uint32_t u = 0; u < 4u; u++) {
+      if (k0 + u >= cn) break;
+      const float dx = xi.x - xj[u].x, dy = xi.y - xj[u].y;
+      const float w = kernel_w(sqrtf(dx * dx + dy * dy), (hi + o[u].z) * 0.5f);
+      const float dist = (lj[u] > 0.f) ? -dmax : fmaxf(lj[u], -dmax);
+      const float vw = o[u].w / rj[u] * w;
+      num += dist * vw;
+      den += vw;
+    }
   }
   if (!isfinite(den) || !(den > 0.f)) atomicOr(&ctl->error_flags, ERRF_LEVEL_WEIGHT);
   level_out[i] = num / den;

@@ -67,9 +67,11 @@ __device__ __forceinline__ void boundary_terms(const PackedParams& P, const floa
 }
 
 // Visit every particle j stored in a grid cell that overlaps the search box of particle i, level by level.
+// f(j, xyhm[j]): the candidates' records are requested four at a time before the first of them is looked at (the scan is
+// a chain load -> test otherwise: a third of the kernel's stall samples sat on the first use of the loaded record)
 template <class F>
 __device__ __forceinline__ void for_each_candidate(float xi, float yi, float hi, const StepCtl* __restrict__ ctl,
-                                                   const uint32_t* __restrict__ cellstart, float f_search, F f) {
+                                                   const uint32_t* __restrict__ cellstart, const float4* __restrict__ xyhm, float f_search, F f) {
   const int nl = ctl->nlevels;
   const float ox = ctl->origin_x, oy = ctl->origin_y;
   for (int b = 0; b < nl; b++) {
@@ -86,7 +88,13 @@ __device__ __forceinline__ void for_each_candidate(float xi, float yi, float hi,
       for (int st = cx0 >> sl; st <= (cx1 >> sl); st++) {
         const int ca = max(cx0, st << sl), cb = min(cx1, (st << sl) + (1 << sl) - 1);
         const uint32_t s = cellstart[cell_index(g, ca, cy)], e = cellstart[cell_index(g, cb, cy) + 1];
-        for (uint32_t j = s; j < e; j++) f(j);
+        for (uint32_t j = s; j < e; j += 4u) {
+          float4 o[4];
+#pragma unroll
+          for (uint32_t u = 0; u < 4u; u++) o[u] = __ldg(&xyhm[min(j + u, e - 1u)]);
+#pragma unroll
+          for (uint32_t u = 0; u < 4u; u++) if (j + u < e) f(j + u, o[u]);
+        }
       }
     }
   }
@@ -122,8 +130,7 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
   bool fits = true, fits_far = true, fits_ext = true;
   float rho = 0.f, Sx = 0.f, Sy = 0.f, Q = 0.f, Nx = 0.f, Ny = 0.f;
   if (active) {
-    for_each_candidate(xi, yi, hi, ctl_in, cellstart, f_ext, [&](uint32_t j) {
-      const float4 o = __ldg(&xyhm[j]);
+    for_each_candidate(xi, yi, hi, ctl_in, cellstart, xyhm, f_ext, [&](uint32_t j, const float4& o) {
       const float ddx = __fsub_rn(xi, o.x), ddy = __fsub_rn(yi, o.y);
       const float d2 = dist_sq_exact(ddx, ddy);
       if (d2 < support_sq_exact(hi, o.z, f_ext)) {
@@ -218,8 +225,7 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
         place(e & 0x7fffffffu, (e >> 31) != 0u);
       }
     } else {
-      for_each_candidate(xi, yi, hi, ctl_in, cellstart, f_ext, [&](uint32_t j) {
-        const float4 o = __ldg(&xyhm[j]);
+      for_each_candidate(xi, yi, hi, ctl_in, cellstart, xyhm, f_ext, [&](uint32_t j, const float4& o) {
         const float d2 = dist_sq_exact(__fsub_rn(xi, o.x), __fsub_rn(yi, o.y));
         if (d2 < support_sq_exact(hi, o.z, f_near)) place(j, true);
         else if (d2 < support_sq_exact(hi, o.z, f_ext)) place(j, false);

@@ -264,6 +264,7 @@ struct asph_sim {
   uint64_t pc_calls[ASPH_PC_COUNT] = {0};
   void* pc = nullptr;  // PerformanceCounters state (capi.cu: open intervals + event pool)
   int sm_count = 148;
+  float cell_scale = 0.f;  // cell edge of a grid level in units of the level's largest search radius; 0 = chosen per step (grid.cu); ASPH_CELL_SCALE overrides
   bool bulk = true;    // bulk-copy (cp.async.bulk + mbarrier) stage fill of the single-GPU sweep kernels; ASPH_BULK=0 at asph_create: per-thread copies
   bool sweep_attr_done = false;  // dynamic shared-memory limit of the sweep kernels raised on this handle's device
   int prop_grid = 0, greedy_grid = 0, greedy_grid_peer = 0;  // co-resident blocks of the persistent cooperative kernels (level.cu, adapt.cu) on this device
