@@ -475,8 +475,6 @@ def test_resampling_equals_the_python_restatement(asph, oracle64, default_params
 
 
 @pytest.mark.gpu
-@pytest.mark.isolated(timeout=75)  # tests/conftest.py: the body runs in a child process
-@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent (max_iters = 0 has not run on hardware): first run pending")
 @pytest.mark.parametrize("solver", ["HybridDFSPH", "IISPH"])
 def test_cuda_step_equals_the_numpy_restatement(asph, cuda_lib, default_params, solver):
     """The CUDA path against the numpy restatement directly (no oracle in between): one-sweep step in the corner of the
