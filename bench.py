@@ -355,6 +355,7 @@ def run_ours(args):
         "config": dict({"workload": workload_name(n0), "particles_initial": n0, "preroll_steps": PREROLL_STEPS, "preroll_wall_s": t_pre,
                         "l2": "working set per step (neighbour lists + SoA, > 1 GB) exceeds the 126 MB L2; no flush",
                         "timing": "CUDA events on the library stream around every step (PerformanceCounters 'simulation-step': physics + resampling)",
+                        "level_sweeps_note": "the propagation stops once a whole sweep has assigned only values below -maximum_surface_distance (they are clamped downstream, simulation.rs:833-836: identical results); the reference and the CPU arms sweep on until nothing changes (about 230 sweeps on this state)",
                         "wall_ms_per_step": wall * 1e3 / max(K, 1), "phase_ms_per_step": phases, "simulated_time": sim_time, "greedy_duplicates": dup,
                         "kernels": tab, "switches": {k: os.environ[k] for k in ("ASPH_BULK", "ASPH_SWEEP_GRID", "ASPH_BENCH_SPACING", "ASPH_BENCH_PREROLL") if k in os.environ}}, **sm),
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "step_roofline": step_roof, "cpu_baseline": cpu,
