@@ -277,36 +277,39 @@ k_greedy(const GreedyArgs G, const PackedParams P, const CoopPeer C) {
   // PEER: fence, meet the other GPUs, take in their mail; returns whether any rank has work or mail outstanding
   auto exchange = [&](uint32_t pout) {
     grid.sync();
-    if (gtid == 0) {
-      const bool sent = coop_publish_mail(C, ctl, bar);
-      const unsigned int mine = (work_n[pout] > 0u ? 1u : 0u) | (sent ? 2u : 0u);
-      const unsigned int all = coop_barrier(C, bar, mine, ctl);
-      *C.verdict = ((all & 3u) != 0u && !(all & 0x80000000u)) ? 1u : 0u;
-      __threadfence();
-    }
-    grid.sync();
-    const bool go = *reinterpret_cast<volatile unsigned int*>(C.verdict) != 0u;
-    const uint32_t par = bar & 1u;
+    // block 0 alone meets the other GPUs and takes in their mail (a round's mail is a handful of messages; the first
+    // exchange's — the border donors' states — a few thousand), the other blocks wait at the second grid barrier
+    if (blockIdx.x == 0) {
+      if (threadIdx.x == 0) {
+        const bool sent = coop_publish_mail(C, ctl, bar);
+        const unsigned int mine = (work_n[pout] > 0u ? 1u : 0u) | (sent ? 2u : 0u);
+        const unsigned int all = coop_barrier(C, bar, mine, ctl);
+        *C.verdict = ((all & 3u) != 0u && !(all & 0x80000000u)) ? 1u : 0u;
+      }
+      __syncthreads();
+      const uint32_t par = bar & 1u;
 #pragma unroll
-    for (int side = 0; side < 2; side++) {
-      const uint32_t n_in = min(*reinterpret_cast<volatile unsigned int*>(&C.self->mbox_n[par][side]), C.mbox_cap);
-      const uint2* __restrict__ box = C.mbox + size_t(par * 2u + uint32_t(side)) * C.mbox_cap;
-      for (uint32_t e = gtid; e < n_in; e += gthreads) {
-        const uint2 m = __ldcg(box + e);
-        const uint32_t slot = m.x & kSlotMask;
-        switch (m.x >> 28) {
-          case MAIL_INFO: G.info[slot] = m.y; break;
-          case MAIL_DROP: G.drop[slot] = __uint_as_float(m.y); break;
-          case MAIL_PARTNER: A.partner[slot] = m.y; break;
-          case MAIL_COUNTER: A.counter[slot] = m.y; break;
-          case MAIL_CLAIM:  // one of my particles was claimed by a donor of the neighbour rank (m.y = that donor's ghost here)
-            A.partner[slot] = m.y;
-            wake(slot, G.work[pout], pout);
-            break;
+      for (int side = 0; side < 2; side++) {
+        const uint32_t n_in = min(*reinterpret_cast<volatile unsigned int*>(&C.self->mbox_n[par][side]), C.mbox_cap);
+        const uint2* __restrict__ box = C.mbox + size_t(par * 2u + uint32_t(side)) * C.mbox_cap;
+        for (uint32_t e = threadIdx.x; e < n_in; e += blockDim.x) {
+          const uint2 m = __ldcg(box + e);
+          const uint32_t slot = m.x & kSlotMask;
+          switch (m.x >> 28) {
+            case MAIL_INFO: G.info[slot] = m.y; break;
+            case MAIL_DROP: G.drop[slot] = __uint_as_float(m.y); break;
+            case MAIL_PARTNER: A.partner[slot] = m.y; break;
+            case MAIL_COUNTER: A.counter[slot] = m.y; break;
+            case MAIL_CLAIM:  // one of my particles was claimed by a donor of the neighbour rank (m.y = that donor's ghost here)
+              A.partner[slot] = m.y;
+              wake(slot, G.work[pout], pout);
+              break;
+          }
         }
       }
     }
     grid.sync();
+    const bool go = *reinterpret_cast<volatile unsigned int*>(C.verdict) != 0u;
     bar++;
     return go;
   };

@@ -23,10 +23,22 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int kThreads = 256;
+#ifndef ASPH_PROP_BATCH
+#define ASPH_PROP_BATCH 4  // neighbours a lane of k_propagate has in flight
+#endif
 constexpr int kPropThreads = 512;                 // block of the persistent propagation kernel
 constexpr unsigned int kUnassigned = 0xFFFFFFFFu;  // bit pattern of a level value no push has reached yet
+constexpr int kGhostPending = -3;                  // stamp of a ghost copy its owner has not assigned yet (multi-GPU)
+constexpr int kBorderUnassigned = -2;              // stamp of an unassigned particle that has ghost copies on a neighbour GPU
 
 typedef NbLists Lists;
+
+#ifdef ASPH_PROP_TRACE  // development only: per-sweep cycle counts of k_propagate (tools/prop_trace.py)
+__device__ unsigned long long g_prop_trace[6][512];
+#define PROP_TRACE(stmt) stmt
+#else
+#define PROP_TRACE(stmt)
+#endif
 
 // front_n[p] = tail of the front array of the sweeps of parity p; level_live[p] = the last sweep of parity p that assigned
 // a value above the cutoff (k_propagate)
@@ -105,12 +117,22 @@ k_surface(uint32_t n, Lists L, const float4* __restrict__ xyhm, const float2* __
 }
 
 // multi-GPU, after the owners' level / stamp values of the ghosts have arrived: ghosts on the detected surface join front(0)
-__global__ void k_ghost_front(uint32_t count, const uint32_t* __restrict__ ghost_idx, const int* __restrict__ stamp, uint32_t* __restrict__ front,
+// The other ghosts get the stamp kGhostPending: no local push may assign them (k_propagate), their owners' values come by mail.
+__global__ void k_ghost_front(uint32_t count, const uint32_t* __restrict__ ghost_idx, int* __restrict__ stamp, uint32_t* __restrict__ front,
                               StepCtl* ctl) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= count) return;
   const uint32_t i = ghost_idx[k];
   if (stamp[i] == 0) front[atomicAdd(&ctl->front_n[0], 1u)] = i;
+  else stamp[i] = kGhostPending;
+}
+
+// multi-GPU: unassigned particles with ghost copies on a neighbour GPU get their own stamp, so that the push that claims
+// one knows without another load that the value has to be mailed
+__global__ void k_mark_border(uint32_t n, const uint32_t* __restrict__ rslot0, const uint32_t* __restrict__ rslot1, int* __restrict__ stamp) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if ((rslot0[i] != 0xffffffffu || rslot1[i] != 0xffffffffu) && stamp[i] == -1) stamp[i] = kBorderUnassigned;
 }
 
 // K4 (simulation.rs:739-800) as one persistent cooperative kernel.  One warp per front particle j, one lane per
@@ -127,12 +149,14 @@ __global__ void k_ghost_front(uint32_t count, const uint32_t* __restrict__ ghost
 // border particle is mailed to its ghost copies (CoopPeer, sim.cuh), the GPUs meet in a barrier that also tells every
 // rank whether any of them assigned anything (above the cutoff), and the mail — slot, value — joins the local front(t).
 template <bool PEER>
-__global__ void __launch_bounds__(kPropThreads)
+__global__ void __launch_bounds__(kPropThreads, 2)
 k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restrict__ level, int* __restrict__ stamp,
-            uint32_t* __restrict__ front0, uint32_t* __restrict__ front1, StepCtl* ctl, float neg_dmax, int use_cutoff, const CoopPeer P) {
+            uint32_t* __restrict__ front0, uint32_t* __restrict__ front1, uint32_t* __restrict__ border, StepCtl* ctl, float neg_dmax,
+            int use_cutoff, const CoopPeer P) {
   cg::grid_group grid = cg::this_grid();
   constexpr uint32_t kStage = 192;
-  constexpr uint32_t kLanes = 8, kPerWarp = 32 / kLanes;
+  constexpr uint32_t kLanes = 8, kPerWarp = 32 / kLanes, kBatch = ASPH_PROP_BATCH;
+  constexpr uint32_t kGroupRounds = 4;  // columns of up to kGroupRounds * 4 * kLanes neighbours are walked by the particle's own lanes
   __shared__ uint32_t s_stage[kPropThreads / 32][kStage];
   __shared__ uint32_t s_count[kPropThreads / 32], s_base;
   unsigned int* level_bits = reinterpret_cast<unsigned int*>(level);
@@ -142,8 +166,8 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
   volatile uint32_t* tail = ctl->front_n;
   volatile int* live_sweep = ctl->level_live;
   uint32_t consumed[2] = {0u, 0u};  // how much of each parity's array earlier sweeps have read
-  uint32_t exported[2] = {0u, 0u};  // PEER: how much of it has been looked at for mail (front(0) needs none: the halo exchange did it)
-  if (PEER) exported[0] = tail[0];
+  uint32_t seen[2] = {0u, 0u};      // PEER: the tail at the end of the parity's previous sweep (front(0): the halo exchange delivered it)
+  if (PEER) seen[0] = tail[0];
   bool go = true;                   // PEER: the verdict of the last barrier
   int sweeps = 0;
   for (int t = 1; t < (1 << 30); t++) {
@@ -157,46 +181,49 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
     uint32_t* __restrict__ fout = pout ? front1 : front0;
     bool live = false;
     uint32_t wcount = 0;  // claims staged by this warp in this sweep (warp-uniform)
+    PROP_TRACE(const long long tr0 = clock64();)
+    // a staged claim goes to front(t); a border particle (PEER) also to the list block 0 mails from after the barrier
+    auto flush = [&](uint32_t* __restrict__ dst, uint32_t at, uint32_t v) {
+      dst[at] = v & 0x7fffffffu;
+      if (PEER && (v & 0x80000000u)) border[atomicAdd(&ctl->cand_n[0], 1u)] = v & 0x7fffffffu;
+    };
     // Up to 4 * stride neighbours of front particle j, four per lane requested together: lane handles k0 + first + stride * u.
     // Called by the whole warp with warp-uniform trip counts (ballots inside); a lane without a particle passes ce = 0.
-    auto push = [&](const float4& me, float lj, uint32_t ce, const NbCol& col, uint32_t k0, uint32_t first, uint32_t stride) {
-      uint32_t iu[4];
-      int su[4];
-      bool cand[4];
+    auto push = [&](float mex, float mey, float lj, uint32_t ce, const NbCol& col, uint32_t k0, uint32_t first, uint32_t stride) {
+      uint32_t iu[kBatch];
+      bool cand[kBatch];
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < int(kBatch); u++) {
         const uint32_t k = k0 + first + stride * uint32_t(u);
         cand[u] = k < ce;
         iu[u] = cand[u] ? col.get(k) : 0u;
       }
-      // the stamp and the position of a neighbour are requested together (most neighbours of a front particle are still
-      // unassigned, so few of the positions are wasted): one round trip less in the chain
-      float2 ou[4];
+      // the stamp (L2: other SMs write it) and the position (never changes: through L1, neighbouring front particles share
+      // most of their neighbours) of a neighbour are requested together: one round trip less in the chain
+      int su[kBatch];
+      float2 ou[kBatch];
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < int(kBatch); u++) {
         su[u] = cand[u] ? __ldcg(stamp + iu[u]) : 0;
         ou[u] = cand[u] ? __ldg(reinterpret_cast<const float2*>(xyhm + iu[u])) : make_float2(0.f, 0.f);
       }
+      bool won[kBatch];
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        cand[u] = cand[u] && (su[u] == -1 || su[u] == t) && !(PEER && nb_ghost(__ldg(&L.cnt[iu[u]])));
-      }
-      bool won[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < int(kBatch); u++) {
         won[u] = false;
-        if (cand[u]) {
-          const float d = __fsqrt_rn(dist_sq_exact(__fsub_rn(me.x, ou[u].x), __fsub_rn(me.y, ou[u].y)));
+        // a ghost is never a candidate: its stamp is kGhostPending, or the sweep its mail came in
+        if (cand[u] && (su[u] == -1 || su[u] == t || (PEER && su[u] == kBorderUnassigned))) {
+          const float d = __fsqrt_rn(dist_sq_exact(__fsub_rn(mex, ou[u].x), __fsub_rn(mey, ou[u].y)));
           const float v = __fsub_rn(lj, d);  // <= 0: the largest float is the smallest bit pattern
           atomicMin(level_bits + iu[u], __float_as_uint(v));
-          if (su[u] == -1) won[u] = atomicCAS(stamp + iu[u], -1, t) == -1;
+          if (su[u] != t) won[u] = atomicCAS(stamp + iu[u], su[u], t) == su[u];
           if (!use_cutoff || v > neg_dmax) live = true;
         }
       }
       // the newly claimed particles go into this warp's staging buffer: the tail of front(t) is ONE word, and an atomic per
       // warp and batch on it (some ten thousand per sweep, all to the same address) was most of a sweep's time
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < int(kBatch); u++) {
         const unsigned int mask = __ballot_sync(0xffffffffu, won[u]);
         if (mask) {
           const uint32_t cnt = uint32_t(__popc(mask));
@@ -204,47 +231,49 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(&ctl->front_n[pout], wcount);
             base = __shfl_sync(0xffffffffu, base, 0);
-            for (uint32_t e = lane; e < wcount; e += 32u) fout[base + e] = s_stage[wid][e];
+            for (uint32_t e = lane; e < wcount; e += 32u) flush(fout, base + e, s_stage[wid][e]);
             __syncwarp();
             wcount = 0;
           }
-          if (won[u]) s_stage[wid][wcount + uint32_t(__popc(mask & ((1u << lane) - 1u)))] = iu[u];
+          if (won[u])  // bit 31: a border particle, its ghost copies on the neighbour GPUs need the value
+            s_stage[wid][wcount + uint32_t(__popc(mask & ((1u << lane) - 1u)))] = iu[u] | ((PEER && su[u] == kBorderUnassigned) ? 0x80000000u : 0u);
           wcount += cnt;
         }
       }
     };
     // A sweep is a chain of dependent memory round trips (front entry -> column header -> list entry -> stamp -> atomics)
     // ended by a grid-wide barrier, so its time is the time of the SLOWEST warp.  Eight lanes per front particle, four
-    // particles per warp cover a column of up to 32 neighbours in one round; a longer column (a coarse particle next to
-    // fine ones has a hundred and more) would take its eight lanes many rounds, so it is handed to the whole warp afterwards.
+    // particles per warp, 32 neighbours of each per round, the four columns walked side by side; a very long column (a
+    // coarse particle next to fine ones has hundreds) would take its eight lanes many rounds, so it is handed to the whole
+    // warp afterwards.
     const uint32_t sub = lane & (kLanes - 1u), grp = lane / kLanes;
     for (uint32_t f0 = begin + gwarp * kPerWarp; f0 < end; f0 += nwarps * kPerWarp) {
-      const uint32_t f = f0 + grp;
-      const bool have = f < end;
-      uint32_t j = 0, ce = 0;
-      float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
-      float lj = 0.f;
+      struct { uint32_t j, ce; float x, y, lj; } cur{0u, 0u, 0.f, 0.f, 0.f};
       NbCol col;
-      if (have) {
-        j = __ldcg(fin + f);
-        me = __ldg(&xyhm[j]);
-        lj = __ldcg(level + j);
-        ce = __ldg(&L.cnt_ext[j]);
-        col = NbCol(L, j);
+      if (f0 + grp < end) {
+        cur.j = __ldcg(fin + f0 + grp);
+        const float2 p = __ldg(reinterpret_cast<const float2*>(xyhm + cur.j));
+        cur.x = p.x; cur.y = p.y;
+        cur.lj = __ldcg(level + cur.j);
+        cur.ce = __ldg(&L.cnt_ext[cur.j]);
+        col = NbCol(L, cur.j);
       }
-      const bool big = ce > 4u * kLanes;
+      // an extended-range column holds about 60 neighbours (f_ext = 2.9 supports): two rounds of kBatch * kLanes for the group
+      const bool big = cur.ce > kGroupRounds * kBatch * kLanes;
       const unsigned int bigmask = __ballot_sync(0xffffffffu, big && sub == 0u);
-      if (__any_sync(0xffffffffu, have && !big)) push(me, lj, big ? 0u : ce, col, 0u, sub, kLanes);
+      const uint32_t ce_grp = big ? 0u : cur.ce;
+      for (uint32_t k0 = 0; __any_sync(0xffffffffu, k0 < ce_grp); k0 += kBatch * kLanes) push(cur.x, cur.y, cur.lj, ce_grp, col, k0, sub, kLanes);
       for (unsigned int m = bigmask; m; m &= m - 1u) {
         const int src = __ffs(m) - 1;
-        const uint32_t jb = __shfl_sync(0xffffffffu, j, src);
-        const float4 meb = __ldg(&xyhm[jb]);
+        const uint32_t jb = __shfl_sync(0xffffffffu, cur.j, src);
+        const float2 pb = __ldg(reinterpret_cast<const float2*>(xyhm + jb));
         const float ljb = __ldcg(level + jb);
         const uint32_t ceb = __ldg(&L.cnt_ext[jb]);
         const NbCol colb(L, jb);
-        for (uint32_t k0 = 0; k0 < ceb; k0 += 128u) push(meb, ljb, ceb, colb, k0, lane, 32u);
+        for (uint32_t k0 = 0; k0 < ceb; k0 += 32u * kBatch) push(pb.x, pb.y, ljb, ceb, colb, k0, lane, 32u);
       }
     }
+    PROP_TRACE(if (t < 512 && lane == 0) { const unsigned long long d = (unsigned long long)(clock64() - tr0); atomicMax(&g_prop_trace[1][t], d); atomicAdd(&g_prop_trace[2][t], d); if (gtid == 0) g_prop_trace[0][t] = end - begin; })
     // one atomic per block: the warps' staged claims behind one another at the tail of front(t)
     __syncwarp();
     if (lane == 0) s_count[wid] = wcount;
@@ -257,47 +286,52 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
     __syncthreads();
     {
       const uint32_t base = s_base + s_count[wid];
-      for (uint32_t e = lane; e < wcount; e += 32u) fout[base + e] = s_stage[wid][e];
+      for (uint32_t e = lane; e < wcount; e += 32u) flush(fout, base + e, s_stage[wid][e]);
     }
     if (__any_sync(0xffffffffu, live) && lane == 0) live_sweep[pout] = t;
+    PROP_TRACE(if (t < 512 && gtid == 0) g_prop_trace[3][t] = (unsigned long long)(clock64() - tr0);)
     grid.sync();
+    PROP_TRACE(if (t < 512 && gtid == 0) { g_prop_trace[4][t] = (unsigned long long)(clock64() - tr0); g_prop_trace[5][t] = nwarps; })
     if (PEER) {
-      const unsigned int seq = P.seq0 + unsigned(t), par = seq & 1u;
-      // mail the border particles assigned in this sweep to their ghost copies
-      const uint32_t e0 = exported[pout], e1 = tail[pout];
-      for (uint32_t f = e0 + gtid; f < e1; f += gthreads) {
-        const uint32_t i = __ldcg(fout + f);
-        const unsigned int bits = __ldcg(level_bits + i);
+      // Between two grid barriers block 0 alone talks to the other GPUs (a sweep assigns a few dozen border particles, and
+      // every grid barrier less is more than a microsecond of the sweep): mail out, barrier across the GPUs, mail in.
+      if (blockIdx.x == 0) {
+        const unsigned int seq = P.seq0 + unsigned(t), par = seq & 1u;
+        const uint32_t nb = *reinterpret_cast<volatile uint32_t*>(&ctl->cand_n[0]);
+        for (uint32_t e = threadIdx.x; e < nb; e += blockDim.x) {
+          const uint32_t i = __ldcg(border + e);
+          const unsigned int bits = __ldcg(level_bits + i);
+#pragma unroll
+          for (int side = 0; side < 2; side++) {
+            const uint32_t sl = __ldg(&P.rslot[side][i]);
+            if (sl != 0xffffffffu && P.nb_mbox[side]) coop_mail(P, ctl, seq, side, sl, bits);
+          }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          ctl->cand_n[0] = 0u;
+          coop_publish_mail(P, ctl, seq);
+          const unsigned int mine = (tail[pout] > seen[pout] ? 1u : 0u) | (live_sweep[pout] == t ? 2u : 0u);
+          const unsigned int all = coop_barrier(P, seq, mine, ctl);
+          *P.verdict = ((all & 3u) == 3u && !(all & 0x80000000u) && t <= (1 << 29)) ? 1u : 0u;
+        }
+        __syncthreads();
+        // the mail of this sweep: the ghosts' values and their place in front(t)
 #pragma unroll
         for (int side = 0; side < 2; side++) {
-          const uint32_t sl = __ldg(&P.rslot[side][i]);
-          if (sl != 0xffffffffu && P.nb_mbox[side]) coop_mail(P, ctl, seq, side, sl, bits);
+          const uint32_t n_in = min(*reinterpret_cast<volatile unsigned int*>(&P.self->mbox_n[par][side]), P.mbox_cap);
+          const uint2* __restrict__ box = P.mbox + size_t(par * 2u + uint32_t(side)) * P.mbox_cap;
+          for (uint32_t e = threadIdx.x; e < n_in; e += blockDim.x) {
+            const uint2 m = __ldcg(box + e);
+            level_bits[m.x] = m.y;
+            stamp[m.x] = t;
+            fout[atomicAdd(&ctl->front_n[pout], 1u)] = m.x;
+          }
         }
-      }
-      grid.sync();
-      if (gtid == 0) {
-        coop_publish_mail(P, ctl, seq);
-        const unsigned int mine = (e1 > e0 ? 1u : 0u) | (live_sweep[pout] == t ? 2u : 0u);
-        const unsigned int all = coop_barrier(P, seq, mine, ctl);
-        *P.verdict = ((all & 3u) == 3u && !(all & 0x80000000u) && t <= (1 << 29)) ? 1u : 0u;
-        __threadfence();
       }
       grid.sync();
       go = *reinterpret_cast<volatile unsigned int*>(P.verdict) != 0u;
-      // the mail of this sweep: the ghosts' values and their place in front(t)
-#pragma unroll
-      for (int side = 0; side < 2; side++) {
-        const uint32_t n_in = min(*reinterpret_cast<volatile unsigned int*>(&P.self->mbox_n[par][side]), P.mbox_cap);
-        const uint2* __restrict__ box = P.mbox + size_t(par * 2u + uint32_t(side)) * P.mbox_cap;
-        for (uint32_t e = gtid; e < n_in; e += gthreads) {
-          const uint2 m = __ldcg(box + e);
-          level_bits[m.x] = m.y;
-          stamp[m.x] = t;
-          fout[atomicAdd(&ctl->front_n[pout], 1u)] = m.x;
-        }
-      }
-      grid.sync();
-      exported[pout] = tail[pout];
+      seen[pout] = tail[pout];
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->level_sweep = sweeps; ctl->level_done = 1; }
@@ -355,10 +389,10 @@ int launch_level_estimation(asph_sim* sim) {
   float* level = sim->level[sim->cur].p;
   k_level_reset<<<1, 1, 0, st>>>(sim->ctl);
   LAUNCH_CHECK();
+  const bool peer = dist_p2p(sim);
   k_surface<<<blocks, kThreads, 0, st>>>(n, L, sim->xyhm.p, sim->nrm.p, sim->pp, cos_threshold, level, sim->stamp.p, sim->flags.p,
                                          sim->front[0].p, sim->ctl);
   LAUNCH_CHECK();
-  const bool peer = dist_p2p(sim);
   if (sim->dist && dist_ranks(sim) > 1 && !peer) { sim->last_error = "level estimation across GPU slabs needs the peer-memory path (ASPH_DIST_P2P)"; return ASPH_ERR_UNSUPPORTED; }
   if (peer) {  // the owners' verdict on the ghosts (their own neighbourhoods are incomplete here), then front(0) with them
     TRY(dist_halo_words(sim, level));
@@ -369,6 +403,9 @@ int launch_level_estimation(asph_sim* sim) {
       k_ghost_front<<<(n_ghost + kThreads - 1) / kThreads, kThreads, 0, st>>>(n_ghost, ghost_idx, sim->stamp.p, sim->front[0].p, sim->ctl);
       LAUNCH_CHECK();
     }
+    const CoopPeer cp = dist_coop_peer(sim);
+    k_mark_border<<<blocks, kThreads, 0, st>>>(n, cp.rslot[0], cp.rslot[1], sim->stamp.p);
+    LAUNCH_CHECK();
   }
   int use_cutoff = sim->level_cutoff ? 1 : 0;
   float neg_dmax = -sim->pp.maximum_surface_distance;
@@ -383,12 +420,13 @@ int launch_level_estimation(asph_sim* sim) {
   uint32_t n_arg = n;
   float* level_arg = level;
   int* stamp_arg = sim->stamp.p;
+  const float4* xyhm_arg = sim->xyhm.p;
   uint32_t* front_arg = sim->front[0].p;
   uint32_t* front1_arg = sim->front[1].p;
-  const float4* xyhm_arg = sim->xyhm.p;
+  uint32_t* border_arg = sim->cand.p;
   StepCtl* ctl_arg = sim->ctl;
   CoopPeer coop = dist_coop_peer(sim);
-  void* args[] = {&n_arg, &L, &xyhm_arg, &level_arg, &stamp_arg, &front_arg, &front1_arg, &ctl_arg, &neg_dmax, &use_cutoff, &coop};
+  void* args[] = {&n_arg, &L, &xyhm_arg, &level_arg, &stamp_arg, &front_arg, &front1_arg, &border_arg, &ctl_arg, &neg_dmax, &use_cutoff, &coop};
   cudaEvent_t kt0 = nullptr, kt1 = nullptr;
   if (sim->kt_every > 0) { kt0 = kt_event(sim); kt1 = kt_event(sim); cudaEventRecord(kt0, st); }
   CUDA_TRY(cudaLaunchCooperativeKernel(peer ? (void*)k_propagate<true> : (void*)k_propagate<false>, dim3(grid), dim3(kPropThreads), args, 0, st));
@@ -409,6 +447,14 @@ int launch_level_estimation(asph_sim* sim) {
   sim->info.level_sweeps = std::max(1, sim->ctl_host->level_sweep);
   return ASPH_OK;
 }
+
+#ifdef ASPH_PROP_TRACE
+extern "C" int asph_debug_prop_trace(unsigned long long* out, int reset) {
+  if (cudaMemcpyFromSymbol(out, g_prop_trace, sizeof(unsigned long long) * 6 * 512) != cudaSuccess) return -1;
+  if (reset) { static unsigned long long z[6 * 512]; cudaMemcpyToSymbol(g_prop_trace, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 int launch_level_smoothing(asph_sim* sim) {
   const uint32_t n = sim->n;

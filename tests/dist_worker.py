@@ -144,7 +144,7 @@ def resample(A, dist, rank, world, seed, mode):
     d.lib.asph_set_step_number(d._h, step_number)
     d.single_step_adaptivity(dt=0.002)
     info = d.step_info()
-    report = {"world": world, "mode": mode, "seed": seed, "n_global": n_global, "mismatch": []}
+    report = {"world": world, "mode": mode, "seed": seed, "n_global": n_global, "mismatch": [], "rounds": [d.adapt_rounds(), None]}
     n_now = d.num_global_particles()
     fields = {name: d.gather_field(name) for name in ("mass", "position", "velocity")}
     if single is not None:
@@ -153,6 +153,7 @@ def resample(A, dist, rank, world, seed, mode):
         single.lib.asph_set_step_number(single._h, step_number)
         single.single_step_adaptivity(dt=0.002)
         i1 = single.step_info()
+        report["rounds"][1] = single.adapt_rounds()
         for key in ("n_shared", "n_merged", "n_split_parents"):
             report[key] = [int(info[key]), int(i1[key])]
             if int(info[key]) != int(i1[key]):
