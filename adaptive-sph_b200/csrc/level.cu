@@ -34,7 +34,7 @@ constexpr int kBorderUnassigned = -2;              // stamp of an unassigned par
 typedef NbLists Lists;
 
 #ifdef ASPH_PROP_TRACE  // development only: per-sweep cycle counts of k_propagate (tools/prop_trace.py)
-__device__ unsigned long long g_prop_trace[6][512];
+__device__ unsigned long long g_prop_trace[12][512];
 #define PROP_TRACE(stmt) stmt
 #else
 #define PROP_TRACE(stmt)
@@ -308,12 +308,14 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
           }
         }
         __syncthreads();
+        PROP_TRACE(if (t < 512 && gtid == 0) { g_prop_trace[6][t] = (unsigned long long)(clock64() - tr0); g_prop_trace[10][t] = nb; })
         if (threadIdx.x == 0) {
           ctl->cand_n[0] = 0u;
           coop_publish_mail(P, ctl, seq);
           const unsigned int mine = (tail[pout] > seen[pout] ? 1u : 0u) | (live_sweep[pout] == t ? 2u : 0u);
           const unsigned int all = coop_barrier(P, seq, mine, ctl);
           *P.verdict = ((all & 3u) == 3u && !(all & 0x80000000u) && t <= (1 << 29)) ? 1u : 0u;
+          PROP_TRACE(if (t < 512) g_prop_trace[7][t] = (unsigned long long)(clock64() - tr0);)
         }
         __syncthreads();
         // the mail of this sweep: the ghosts' values and their place in front(t)
@@ -329,7 +331,9 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
           }
         }
       }
+      PROP_TRACE(if (t < 512 && gtid == 0) g_prop_trace[8][t] = (unsigned long long)(clock64() - tr0);)
       grid.sync();
+      PROP_TRACE(if (t < 512 && gtid == 0) g_prop_trace[9][t] = (unsigned long long)(clock64() - tr0);)
       go = *reinterpret_cast<volatile unsigned int*>(P.verdict) != 0u;
       seen[pout] = tail[pout];
     }
@@ -450,8 +454,8 @@ int launch_level_estimation(asph_sim* sim) {
 
 #ifdef ASPH_PROP_TRACE
 extern "C" int asph_debug_prop_trace(unsigned long long* out, int reset) {
-  if (cudaMemcpyFromSymbol(out, g_prop_trace, sizeof(unsigned long long) * 6 * 512) != cudaSuccess) return -1;
-  if (reset) { static unsigned long long z[6 * 512]; cudaMemcpyToSymbol(g_prop_trace, z, sizeof(z)); }
+  if (cudaMemcpyFromSymbol(out, g_prop_trace, sizeof(unsigned long long) * 12 * 512) != cudaSuccess) return -1;
+  if (reset) { static unsigned long long z[12 * 512]; cudaMemcpyToSymbol(g_prop_trace, z, sizeof(z)); }
   return 0;
 }
 #endif

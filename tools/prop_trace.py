@@ -22,7 +22,7 @@ def main():
     bench.preroll_adaptive(sim, A, base, bench.SPACING)
     for _ in range(3):
         sim.single_step(base)
-    buf = np.zeros((6, 512), dtype=np.uint64)
+    buf = np.zeros((12, 512), dtype=np.uint64)
     ptr = buf.ctypes.data_as(C.POINTER(C.c_ulonglong))
     lib.asph_debug_prop_trace(ptr, 1)
     sim.single_step(base)
