@@ -185,7 +185,10 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
     // a staged claim goes to front(t); a border particle (PEER) also to the list block 0 mails from after the barrier
     auto flush = [&](uint32_t* __restrict__ dst, uint32_t at, uint32_t v) {
       dst[at] = v & 0x7fffffffu;
-      if (PEER && (v & 0x80000000u)) border[atomicAdd(&ctl->cand_n[0], 1u)] = v & 0x7fffffffu;
+      if (PEER && (v & 0x80000000u)) {  // with its ghost slots: block 0 then needs the value only
+        const uint32_t i = v & 0x7fffffffu, k = atomicAdd(&ctl->cand_n[0], 1u);
+        border[3u * k] = i; border[3u * k + 1u] = __ldg(&P.rslot[0][i]); border[3u * k + 2u] = __ldg(&P.rslot[1][i]);
+      }
     };
     // Up to 4 * stride neighbours of front particle j, four per lane requested together: lane handles k0 + first + stride * u.
     // Called by the whole warp with warp-uniform trip counts (ballots inside); a lane without a particle passes ce = 0.
@@ -296,40 +299,57 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
       // Between two grid barriers block 0 alone talks to the other GPUs (a sweep assigns a few dozen border particles, and
       // every grid barrier less is more than a microsecond of the sweep): mail out, barrier across the GPUs, mail in.
       if (blockIdx.x == 0) {
+        // (the block's own message counters and its private view of the front's tail: every round trip to ctl saved here
+        // is a microsecond of every sweep)
+        __shared__ uint32_t s_mail[2], s_tail;
         const unsigned int seq = P.seq0 + unsigned(t), par = seq & 1u;
+        if (threadIdx.x < 2u) s_mail[threadIdx.x] = 0u;
+        uint32_t tail_now = 0;
+        int live_now = 0;
+        if (threadIdx.x == 0) { tail_now = tail[pout]; live_now = live_sweep[pout]; }  // in flight while the mail goes out
         const uint32_t nb = *reinterpret_cast<volatile uint32_t*>(&ctl->cand_n[0]);
+        __syncthreads();
         for (uint32_t e = threadIdx.x; e < nb; e += blockDim.x) {
-          const uint32_t i = __ldcg(border + e);
+          const uint32_t i = __ldcg(border + 3u * e), sl0 = __ldcg(border + 3u * e + 1u), sl1 = __ldcg(border + 3u * e + 2u);
           const unsigned int bits = __ldcg(level_bits + i);
 #pragma unroll
           for (int side = 0; side < 2; side++) {
-            const uint32_t sl = __ldg(&P.rslot[side][i]);
-            if (sl != 0xffffffffu && P.nb_mbox[side]) coop_mail(P, ctl, seq, side, sl, bits);
+            const uint32_t sl = side ? sl1 : sl0;
+            if (sl == 0xffffffffu || !P.nb_mbox[side]) continue;
+            const uint32_t k = atomicAdd(&s_mail[side], 1u);
+            if (k < P.mbox_cap) P.nb_mbox[side][size_t(par * 2u + uint32_t(1 - side)) * P.mbox_cap + k] = make_uint2(sl, bits);  // I am that neighbour's other side
+            else atomicOr(&ctl->error_flags, ERRF_PEER_TIMEOUT);
           }
         }
         __syncthreads();
         PROP_TRACE(if (t < 512 && gtid == 0) { g_prop_trace[6][t] = (unsigned long long)(clock64() - tr0); g_prop_trace[10][t] = nb; })
         if (threadIdx.x == 0) {
           ctl->cand_n[0] = 0u;
-          coop_publish_mail(P, ctl, seq);
-          const unsigned int mine = (tail[pout] > seen[pout] ? 1u : 0u) | (live_sweep[pout] == t ? 2u : 0u);
+          for (int side = 0; side < 2; side++)  // the counts go ahead of the barrier flag (ordered by its fence)
+            if (P.nb_ctl[side]) *reinterpret_cast<volatile unsigned int*>(&P.nb_ctl[side]->mbox_n[par][1 - side]) = min(s_mail[side], P.mbox_cap);
+          const unsigned int mine = (tail_now > seen[pout] ? 1u : 0u) | (live_now == t ? 2u : 0u);
           const unsigned int all = coop_barrier(P, seq, mine, ctl);
           *P.verdict = ((all & 3u) == 3u && !(all & 0x80000000u) && t <= (1 << 29)) ? 1u : 0u;
+          s_tail = tail_now;
           PROP_TRACE(if (t < 512) g_prop_trace[7][t] = (unsigned long long)(clock64() - tr0);)
         }
         __syncthreads();
-        // the mail of this sweep: the ghosts' values and their place in front(t)
+        // the mail of this sweep: the ghosts' values, and their place behind the local claims in front(t) (nobody else
+        // appends now)
+        const uint32_t n_in0 = min(*reinterpret_cast<volatile unsigned int*>(&P.self->mbox_n[par][0]), P.mbox_cap);
+        const uint32_t n_in1 = min(*reinterpret_cast<volatile unsigned int*>(&P.self->mbox_n[par][1]), P.mbox_cap);
 #pragma unroll
         for (int side = 0; side < 2; side++) {
-          const uint32_t n_in = min(*reinterpret_cast<volatile unsigned int*>(&P.self->mbox_n[par][side]), P.mbox_cap);
+          const uint32_t n_in = side ? n_in1 : n_in0, at = s_tail + (side ? n_in0 : 0u);
           const uint2* __restrict__ box = P.mbox + size_t(par * 2u + uint32_t(side)) * P.mbox_cap;
           for (uint32_t e = threadIdx.x; e < n_in; e += blockDim.x) {
             const uint2 m = __ldcg(box + e);
             level_bits[m.x] = m.y;
             stamp[m.x] = t;
-            fout[atomicAdd(&ctl->front_n[pout], 1u)] = m.x;
+            fout[at + e] = m.x;
           }
         }
+        if (threadIdx.x == 0 && n_in0 + n_in1 != 0u) ctl->front_n[pout] = s_tail + n_in0 + n_in1;
       }
       PROP_TRACE(if (t < 512 && gtid == 0) g_prop_trace[8][t] = (unsigned long long)(clock64() - tr0);)
       grid.sync();
