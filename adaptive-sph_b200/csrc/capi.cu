@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <type_traits>
 
 #include "lists.cuh"
 
@@ -38,6 +39,7 @@ int pack_params(asph_sim* sim, const asph_params* p) {
   q.np_before_div = p->hybrid_dfsph_non_pressure_accel_before_divergence_free; q.penalty = p->boundary_penalty_term;
   q.sizing = p->sizing_function; q.opdisc = p->operator_discretization;
   q.self_last = 1;
+  q.constrain = p->constrain_neighborhood_count ? 1 : 0;
   q.h_mode = p->support_length_estimation;
   q.level_cut = (q.h_mode == ASPH_H_FROM_DISTRIBUTION || q.h_mode == ASPH_H_FROM_DISTRIBUTION2) ? float(p->maximum_range) : 0.f;
   q.boundary_is_fluid_surface = p->boundary_is_fluid_surface;
@@ -78,13 +80,26 @@ int pack_params(asph_sim* sim, const asph_params* p) {
     q.h_mode = ASPH_H_FROM_MASS; q.level_cut = 0.f; q.opdisc = ASPH_OP_CONSISTENT_SIMPLE_GRADIENT; q.solver = ASPH_SOLVER_HYBRID_DFSPH;
     return ASPH_ERR_UNSUPPORTED;
   };
-  if (p->constrain_neighborhood_count) return unsupported("constrain_neighborhood_count");
-  if (p->level_estimation_method == ASPH_LEVEL_CENTER_DIFF) return unsupported("level_estimation_method CenterDiff");
+  // constrain_neighborhood_count rewrites h in the middle of the step: single GPU, h from the masses
+  if (p->constrain_neighborhood_count && (sim->dist || p->support_length_estimation != ASPH_H_FROM_MASS)) {
+    q.constrain = 0;
+    return unsupported("constrain_neighborhood_count across GPU slabs or with support_length_estimation != FromMass");
+  }
   // single-GPU only so far: the per-particle state these modes carry from step to step does not migrate between slabs
   if (p->support_length_estimation != ASPH_H_FROM_MASS && sim->dist) return unsupported("support_length_estimation != FromMass across GPU slabs");
   if (p->pressure_solver_method == ASPH_SOLVER_IISPH2 && sim->dist) return unsupported("pressure_solver_method IISPH2 across GPU slabs");
   if (p->viscosity_type == ASPH_VISC_XSPH) return unsupported("viscosity_type XSPH (todo!() in the reference)");
-  if (p->level_estimation_after_advection) return unsupported("level_estimation_after_advection");
+  // level_estimation_after_advection (simulation.rs:2678-2707) sorts and searches a second time in the middle of the step
+  if (p->level_estimation_after_advection && p->level_estimation_method != ASPH_LEVEL_NONE) {
+    if (sim->dist) return unsupported("level_estimation_after_advection across GPU slabs");
+    if (!p->use_extended_range_for_level_estimation) return unsupported("level_estimation_after_advection without use_extended_range_for_level_estimation");
+    if (p->support_length_estimation != ASPH_H_FROM_MASS) return unsupported("level_estimation_after_advection with support_length_estimation != FromMass");
+    if (p->constrain_neighborhood_count) return unsupported("level_estimation_after_advection with constrain_neighborhood_count");
+    // the reference's resampling then walks the extended-range lists; here it walks N_2, the same thing as long as no
+    // partner can be further away than the support
+    if ((p->sharing && p->max_share_distance > 2.0) || (p->merging && p->max_merge_distance > 2.0))
+      return unsupported("level_estimation_after_advection with a share / merge distance beyond the kernel support");
+  }
   return ASPH_OK;
 }
 
@@ -231,6 +246,7 @@ int check_error_flags(asph_sim* sim) {
   if (f & ERRF_NEG_AII) { sim->last_error = "AII should not be negative!"; return ASPH_ERR_NEG_AII; }
   if (f & ERRF_SOLVER_NONFINITE) { sim->last_error = "'!a_p.is_finite()' failed. Pressure values probably have exploded!"; return ASPH_ERR_NONFINITE; }
   if (f & ERRF_LEVEL_WEIGHT) { sim->last_error = "smooth_level_estimation_field: weight <= 0"; return ASPH_ERR_NONFINITE; }
+  if (f & ERRF_CONSTRAIN) { sim->last_error = "constrain_neighborhood_count: assert!(*p_h_next < h) / assert!(*p_h_next >= 0.) failed"; return ASPH_ERR_INVALID; }
   if (f & ERRF_PARTICLE_CAPACITY) { sim->last_error = "particle capacity exhausted by splitting"; return ASPH_ERR_CAPACITY; }
   if (f & ERRF_SPLIT_PATTERN) { sim->last_error = "no split pattern for a 1-to-n split"; return ASPH_ERR_INVALID; }
   if (f & ERRF_SPLIT_CHILDREN) { sim->last_error = "assert!(num_children > 1)"; return ASPH_ERR_INVALID; }
@@ -247,7 +263,7 @@ int check_error_flags(asph_sim* sim) {
 
 // One attempt at the physics part of the step from the neighbour pass on.  Returns ASPH_RETRY_LISTS when the first
 // synchronisation shows that the neighbour pool was too small (nothing irreversible has happened by then).
-static int physics_after_sort(asph_sim* sim, bool lvl, float f_ext) {
+static int physics_after_sort(asph_sim* sim, bool lvl, float f_ext, bool smooth) {
   const PackedParams& P = sim->pp;
   cudaEvent_t kt1 = nullptr, kt2 = nullptr;
   if (sim->kt_every > 0) { kt1 = kt_event(sim); kt2 = kt_event(sim); cudaEventRecord(kt1, sim->stream); }
@@ -272,8 +288,19 @@ static int physics_after_sort(asph_sim* sim, bool lvl, float f_ext) {
       pc_end(sim, ASPH_PC_LEVEL_ESTIMATION);
       TRY(check_error_flags(sim));  // density / a_ii asserts of the neighbour pass (simulation.rs:1046-1047, 1390)
     }
+    if (P.constrain) {  // simulation.rs:2145-2177, after the level estimation (simulation.rs:2018-2057) and before everything that uses h
+      if (!lvl) {  // the lists the new lengths are chosen from must be complete before h is overwritten
+        if (!guard(sync_ctl(sim))) break;
+        if (sim->ctl_host->error_flags & ERRF_LIST_CAPACITY) { rc = ASPH_RETRY_LISTS; break; }
+        if (!guard(check_error_flags(sim))) break;
+      }
+      if (!guard(launch_constrain_neighborhood(sim))) break;
+      pc_begin(sim, ASPH_PC_NEIGHBORHOOD, false);
+      if (!guard(launch_neighbors(sim, P.f_near, P.f_near))) break;
+      pc_end(sim, ASPH_PC_NEIGHBORHOOD);
+    }
     int iters = 0, sweeps = 0;
-    bool first = !lvl;  // the first synchronisation after the neighbour pass also validates its error flags
+    bool first = !lvl || P.constrain;  // the first synchronisation after the neighbour pass also validates its error flags
     auto solve = [&](bool density, float tol, double* avg) {
       int r = launch_solver(sim, density, tol, &iters, &sweeps, avg);
       if (r == ASPH_OK && first) { r = check_error_flags(sim); first = false; }
@@ -322,7 +349,7 @@ static int physics_after_sort(asph_sim* sim, bool lvl, float f_ext) {
         break;
     }
     if (rc != ASPH_OK) break;
-    if (lvl) {
+    if (smooth) {
       pc_begin(sim, ASPH_PC_LEVEL_ESTIMATION, false);
       if (!guard(launch_level_smoothing(sim))) break;
       pc_end(sim, ASPH_PC_LEVEL_ESTIMATION);
@@ -334,14 +361,73 @@ static int physics_after_sort(asph_sim* sim, bool lvl, float f_ext) {
   return rc;
 }
 
+template <class T>
+__global__ void k_gather(uint32_t n, const uint32_t* __restrict__ order, const T* __restrict__ in, T* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[order[i]];
+}
+__global__ void k_restore_dt(StepCtl* ctl, float dt) { ctl->dt = dt; }
+
+// level_estimation_after_advection (simulation.rs:2678-2720): the advected particles are sorted and searched again with
+// the extended range, the level set is estimated and smoothed on those lists, and the resampling phase that follows uses
+// them too.  The per-step fields of the physics part (density — K17 reads it —, pressure, a_ii, ...) follow the
+// particles through the second sort; the second neighbour pass writes lists and surface normals only.
+static int level_after_advection(asph_sim* sim) {
+  const PackedParams& P = sim->pp;
+  const uint32_t n = sim->n;
+  if (n == 0) return ASPH_OK;
+  const uint32_t blocks = (n + 255u) / 256u;
+  cudaStream_t st = sim->stream;
+  const float dt = sim->ctl_host->dt;  // the step's dt: the second sort would compute one from the new velocities
+  const unsigned int sweeps_parity = sim->p_cur;
+  TRY(launch_sort_and_grid(sim, std::max(P.f_ext, P.f_near)));
+  void* tmp = sim->xv[1].p;  // free between the sort (which fills xv[0]) and the next step
+  auto follow = [&](auto* arr) -> int {
+    using T = std::remove_pointer_t<decltype(arr)>;
+    k_gather<T><<<blocks, 256, 0, st>>>(n, sim->order.p, arr, static_cast<T*>(tmp));
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(arr, tmp, size_t(n) * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    return ASPH_OK;
+  };
+  TRY(follow(sim->rho.p));
+  TRY(follow(sim->packP[sweeps_parity].p));
+  TRY(follow(sim->pconst.p));
+  TRY(follow(sim->packA.p));
+  TRY(follow(sim->lam_sum.p));
+  TRY(follow(sim->lam_grad.p));
+  for (int attempt = 0;; attempt++) {
+    TRY(launch_neighbors(sim, P.f_ext, P.f_near, true));
+    TRY(sync_ctl(sim));
+    if (!(sim->ctl_host->error_flags & ERRF_LIST_CAPACITY)) break;
+    if (attempt == 5) { sim->last_error = "neighbour list pool could not be sized"; return ASPH_ERR_CAPACITY; }
+    TRY(neighbors_grow(sim));
+  }
+  TRY(check_error_flags(sim));
+  k_restore_dt<<<1, 1, 0, st>>>(sim->ctl, dt);
+  LAUNCH_CHECK();
+  pc_begin(sim, ASPH_PC_LEVEL_ESTIMATION);
+  TRY(launch_level_estimation(sim));
+  pc_end(sim, ASPH_PC_LEVEL_ESTIMATION);
+  pc_begin(sim, ASPH_PC_LEVEL_ESTIMATION, false);
+  TRY(launch_level_smoothing(sim));
+  pc_end(sim, ASPH_PC_LEVEL_ESTIMATION);
+  TRY(sync_ctl(sim));
+  return check_error_flags(sim);
+}
+
 static int step_physics(asph_sim* sim, const asph_params* params, float* dt_out) {
   TRY(pack_params(sim, params));
   const PackedParams& P = sim->pp;
   memset(&sim->info, 0, sizeof(sim->info));
   sim->info.n_particles_begin = sim->n;
-  const bool lvl = P.level_method != ASPH_LEVEL_NONE;
+  const bool after = P.level_method != ASPH_LEVEL_NONE && params->level_estimation_after_advection;
+  const bool lvl = P.level_method != ASPH_LEVEL_NONE && !after;  // level estimation as the first thing in the step
   if (lvl && !params->use_extended_range_for_level_estimation) {  // simulation.rs:2020
     sim->last_error = "level estimation before advection needs use_extended_range_for_level_estimation";
+    return ASPH_ERR_INVALID;
+  }
+  if (lvl && P.level_method == ASPH_LEVEL_CENTER_DIFF) {  // simulation.rs:2021
+    sim->last_error = "center diff level estimation method needs density values which are not available when performing level estimation as first step in loop";
     return ASPH_ERR_INVALID;
   }
   pc_begin(sim, ASPH_PC_SIMULATION_STEP);
@@ -373,7 +459,7 @@ static int step_physics(asph_sim* sim, const asph_params* params, float* dt_out)
     int rc = ASPH_OK;
     for (int attempt = 0; attempt < 6; attempt++) {
       sim->xv_cur = 0;
-      rc = physics_after_sort(sim, lvl, f_ext);
+      rc = physics_after_sort(sim, lvl, f_ext, lvl);
       if (rc != ASPH_RETRY_LISTS) break;
       { const int rc0 = neighbors_grow(sim); if (rc0 != ASPH_OK) { pc_discard(sim); return rc0; } }
       pc_begin(sim, ASPH_PC_NEIGHBORHOOD, false);
@@ -386,6 +472,7 @@ static int step_physics(asph_sim* sim, const asph_params* params, float* dt_out)
       kt_release(sim, kt0); kt_release(sim, kt1);
     }
     if (rc == ASPH_RETRY_LISTS) { sim->last_error = "neighbour list pool could not be sized"; rc = ASPH_ERR_CAPACITY; }
+    if (rc == ASPH_OK && after) rc = level_after_advection(sim);
     if (rc != ASPH_OK) { pc_collect(sim); return rc; }
     sim->info.dt = sim->ctl_host->dt;
   }

@@ -99,6 +99,61 @@ __device__ __forceinline__ bool surface_of(uint32_t i, const Lists& L, const flo
   flags[i] = fl;
   return !interior;
 }
+// CenterDiff detects surface particles with values of either sign, and the propagation keeps the LARGEST candidate with an
+// unsigned atomicMin on the stored word.  For values <= 0 the float's own bit pattern orders that way (EmptyAngle: the
+// array holds plain floats throughout); in signed mode (SIGNED) the array holds keys during the propagation — a negative
+// float's pattern, 0x7FFFFFFF - pattern for a positive one — and k_propagate turns them back into floats at its end.
+__device__ __forceinline__ unsigned int level_key(float v) {
+  const unsigned int b = __float_as_uint(v);
+  return (b & 0x80000000u) ? b : 0x7FFFFFFFu - b;
+}
+__device__ __forceinline__ float level_of_key(unsigned int k) { return __uint_as_float((k & 0x80000000u) ? k : 0x7FFFFFFFu - k); }
+
+// K3': surface_detection_by_center_diff (simulation.rs:631-695) over the current lists (all ce entries count as
+// neighbours; the kernel weight of those beyond the 2h support is zero).  Writes keys (see above).
+__global__ void __launch_bounds__(kThreads)
+k_center_diff(uint32_t n, Lists L, const float4* __restrict__ xyhm, const PackedParams P, float* __restrict__ level, int* __restrict__ stamp,
+              uint8_t* __restrict__ flags, uint32_t* __restrict__ front, StepCtl* ctl) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool surf = false;
+  if (i < n) {
+    const float4 me = xyhm[i];
+    const uint32_t ce = L.cnt_ext[i];
+    const NbCol col(L, i);
+    float wsum = 0.f, avg_r = 0.f, cx = 0.f, cy = 0.f;
+    for (uint32_t k = 0; k < ce; k++) {
+      const float4 o = __ldg(&xyhm[col.get(k)]);
+      const float vol = o.w / P.rest_density;
+      const float rad = volume_to_radius(vol);
+      const float dx = me.x - o.x, dy = me.y - o.y;
+      const float w = kernel_w(sqrtf(dx * dx + dy * dy), (me.z + o.z) * 0.5f) * vol;
+      cx += o.x * w; cy += o.y * w;
+      avg_r += rad * w;
+      wsum += w;
+    }
+    avg_r /= wsum;
+    const float surface_level = -0.85f * avg_r;
+    float phi;
+    if (ce < 5u) phi = surface_level;
+    else {
+      cx /= wsum; cy /= wsum;
+      const float dx = me.x - cx, dy = me.y - cy;
+      phi = sqrtf(dx * dx + dy * dy) - avg_r;
+    }
+    surf = phi >= surface_level;
+    reinterpret_cast<unsigned int*>(level)[i] = surf ? level_key(phi) : kUnassigned;
+    stamp[i] = surf ? 0 : -1;
+    flags[i] = surf ? 1u : 0u;
+  }
+  const unsigned int mask = __ballot_sync(0xffffffffu, surf);
+  if (!mask) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(&ctl->front_n[0], uint32_t(__popc(mask)));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (surf) front[base + uint32_t(__popc(mask & ((1u << lane) - 1u)))] = i;
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_surface(uint32_t n, Lists L, const float4* __restrict__ xyhm, const float2* __restrict__ nrm, const PackedParams P, float cos_threshold,
           float* __restrict__ level, int* __restrict__ stamp, uint8_t* __restrict__ flags, uint32_t* __restrict__ front, StepCtl* ctl) {
@@ -148,7 +203,7 @@ __global__ void k_mark_border(uint32_t n, const uint32_t* __restrict__ rslot0, c
 // their neighbourhoods are incomplete; the owner's value comes in.  After the pushes of sweep t every newly assigned
 // border particle is mailed to its ghost copies (CoopPeer, sim.cuh), the GPUs meet in a barrier that also tells every
 // rank whether any of them assigned anything (above the cutoff), and the mail — slot, value — joins the local front(t).
-template <bool PEER>
+template <bool PEER, bool SIGNED>
 __global__ void __launch_bounds__(kPropThreads, 2)
 k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restrict__ level, int* __restrict__ stamp,
             uint32_t* __restrict__ front0, uint32_t* __restrict__ front1, uint32_t* __restrict__ border, StepCtl* ctl, float neg_dmax,
@@ -217,8 +272,8 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
         // a ghost is never a candidate: its stamp is kGhostPending, or the sweep its mail came in
         if (cand[u] && (su[u] == -1 || su[u] == t || (PEER && su[u] == kBorderUnassigned))) {
           const float d = __fsqrt_rn(dist_sq_exact(__fsub_rn(mex, ou[u].x), __fsub_rn(mey, ou[u].y)));
-          const float v = __fsub_rn(lj, d);  // <= 0: the largest float is the smallest bit pattern
-          atomicMin(level_bits + iu[u], __float_as_uint(v));
+          const float v = __fsub_rn(lj, d);  // <= 0 (EmptyAngle): the largest float is the smallest bit pattern
+          atomicMin(level_bits + iu[u], SIGNED ? level_key(v) : __float_as_uint(v));
           if (su[u] != t) won[u] = atomicCAS(stamp + iu[u], su[u], t) == su[u];
           if (!use_cutoff || v > neg_dmax) live = true;
         }
@@ -257,7 +312,7 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
         cur.j = __ldcg(fin + f0 + grp);
         const float2 p = __ldg(reinterpret_cast<const float2*>(xyhm + cur.j));
         cur.x = p.x; cur.y = p.y;
-        cur.lj = __ldcg(level + cur.j);
+        cur.lj = SIGNED ? level_of_key(__ldcg(level_bits + cur.j)) : __ldcg(level + cur.j);
         cur.ce = __ldg(&L.cnt_ext[cur.j]);
         col = NbCol(L, cur.j);
       }
@@ -270,7 +325,7 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
         const int src = __ffs(m) - 1;
         const uint32_t jb = __shfl_sync(0xffffffffu, cur.j, src);
         const float2 pb = __ldg(reinterpret_cast<const float2*>(xyhm + jb));
-        const float ljb = __ldcg(level + jb);
+        const float ljb = SIGNED ? level_of_key(__ldcg(level_bits + jb)) : __ldcg(level + jb);
         const uint32_t ceb = __ldg(&L.cnt_ext[jb]);
         const NbCol colb(L, jb);
         for (uint32_t k0 = 0; k0 < ceb; k0 += 32u * kBatch) push(pb.x, pb.y, ljb, ceb, colb, k0, lane, 32u);
@@ -360,8 +415,11 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->level_sweep = sweeps; ctl->level_done = 1; }
   // particles no push has reached stay FluidInterior
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    if (__ldcg(level_bits + i) == kUnassigned) level[i] = ASPH_LEVEL_INTERIOR;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned int b = __ldcg(level_bits + i);
+    if (b == kUnassigned) level[i] = ASPH_LEVEL_INTERIOR;
+    else if (SIGNED) level[i] = level_of_key(b);
+  }
 }
 
 // K17: φ_i = Σ φ~_j V_j W_ij / Σ V_j W_ij with post-advection positions, pre-advection lists / densities
@@ -414,9 +472,14 @@ int launch_level_estimation(asph_sim* sim) {
   k_level_reset<<<1, 1, 0, st>>>(sim->ctl);
   LAUNCH_CHECK();
   const bool peer = dist_p2p(sim);
-  k_surface<<<blocks, kThreads, 0, st>>>(n, L, sim->xyhm.p, sim->nrm.p, sim->pp, cos_threshold, level, sim->stamp.p, sim->flags.p,
-                                         sim->front[0].p, sim->ctl);
+  const bool center_diff = sim->pp.level_method == ASPH_LEVEL_CENTER_DIFF;
+  if (center_diff)
+    k_center_diff<<<blocks, kThreads, 0, st>>>(n, L, sim->xyhm.p, sim->pp, level, sim->stamp.p, sim->flags.p, sim->front[0].p, sim->ctl);
+  else
+    k_surface<<<blocks, kThreads, 0, st>>>(n, L, sim->xyhm.p, sim->nrm.p, sim->pp, cos_threshold, level, sim->stamp.p, sim->flags.p,
+                                           sim->front[0].p, sim->ctl);
   LAUNCH_CHECK();
+  if (center_diff && sim->dist) { sim->last_error = "level_estimation_method CenterDiff across GPU slabs"; return ASPH_ERR_UNSUPPORTED; }
   if (sim->dist && dist_ranks(sim) > 1 && !peer) { sim->last_error = "level estimation across GPU slabs needs the peer-memory path (ASPH_DIST_P2P)"; return ASPH_ERR_UNSUPPORTED; }
   if (peer) {  // the owners' verdict on the ghosts (their own neighbourhoods are incomplete here), then front(0) with them
     TRY(dist_halo_words(sim, level));
@@ -435,8 +498,8 @@ int launch_level_estimation(asph_sim* sim) {
   float neg_dmax = -sim->pp.maximum_surface_distance;
   if (sim->prop_grid == 0) {  // co-resident blocks of the persistent kernel on this device
     int per_sm = 0, per_sm_peer = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<false>, kPropThreads, 0));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_peer, k_propagate<true>, kPropThreads, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<false, false>, kPropThreads, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_peer, k_propagate<true, false>, kPropThreads, 0));
     sim->prop_grid = std::max(1, std::min(std::min(per_sm, per_sm_peer), 2) * sim->sm_count);  // a third block per SM (42 registers, spills) measured no faster
   }
   // a front rarely holds more than a few ten thousand particles: one warp each
@@ -453,7 +516,8 @@ int launch_level_estimation(asph_sim* sim) {
   void* args[] = {&n_arg, &L, &xyhm_arg, &level_arg, &stamp_arg, &front_arg, &front1_arg, &border_arg, &ctl_arg, &neg_dmax, &use_cutoff, &coop};
   cudaEvent_t kt0 = nullptr, kt1 = nullptr;
   if (sim->kt_every > 0) { kt0 = kt_event(sim); kt1 = kt_event(sim); cudaEventRecord(kt0, st); }
-  CUDA_TRY(cudaLaunchCooperativeKernel(peer ? (void*)k_propagate<true> : (void*)k_propagate<false>, dim3(grid), dim3(kPropThreads), args, 0, st));
+  void* kernel = peer ? (void*)k_propagate<true, false> : center_diff ? (void*)k_propagate<false, true> : (void*)k_propagate<false, false>;
+  CUDA_TRY(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kPropThreads), args, 0, st));
   sim->kernel_launches++;
   if (kt1) cudaEventRecord(kt1, st);
   const int rc_sync = sync_ctl(sim);

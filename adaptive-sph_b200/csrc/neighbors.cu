@@ -236,6 +236,9 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
     for (uint32_t k = cf; k < nb_pad4(cf); k++) nb_store_fe(slice, wide, lane, cw, k, i, bias);
   }
 
+  nrm_out[i] = make_float2(Nx, Ny);  // Σ_j ∇W_ij; K3 scales it by -(m_i/ρ0)
+  if (rho_out == nullptr) return;    // lists (and the surface normal) only: the second pass of level_estimation_after_advection
+
   // boundary terms
   float lam, Gx, Gy;
   boundary_terms(P, lut, xi, yi, hi, lam, Gx, Gy);
@@ -262,7 +265,6 @@ k_neighbors(uint32_t n, const float4* __restrict__ xyhm, const StepCtl* __restri
   pconst[i] = make_float4(rho0 * Gx / rho, rho0 * Gy / rho, aii, 0.f);
   lam_sum_out[i] = lam;
   lam_grad_out[i] = make_float2(Gx, Gy);
-  nrm_out[i] = make_float2(Nx, Ny);  // Σ_j ∇W_ij; K3 scales it by -(m_i/ρ0)
 }
 
 // Winchenbach2020 operator.  Its divergence weights every neighbour with m_j / rho_j instead of
@@ -350,9 +352,98 @@ k_estimate_h(uint32_t n, NbLists L, const float4* __restrict__ xyhm, const float
   lamprev[i] = lam_sum[i];  // this step's boundary terms (k_neighbors) are what the next step's estimate sees
 }
 
+// ---- constrain_neighborhood_count (simulation.rs:2145-2177) ---------------------------------------------------------
+// A particle with more than optimal_neighbor_number + 5 = 19 neighbours in N_2 takes, as its new smoothing length, the
+// (count - 19)-th largest of the "fringe" values 2 |x_ij| - 2 h_j of its neighbours (all read from this step's h: the new
+// lengths go to a second array first).  The operations follow the reference one by one: the neighbour predicate of
+// everything after depends on h.  The reference keeps its lists and lets the pairs that fall out of the shrunken supports
+// contribute zeros; here the lists are rebuilt from the new h instead (launch_neighbors after this), which leaves the
+// same non-zero pairs — the pair passes assume that every stored pair lies inside the support.
+constexpr uint32_t kConstrainTarget = 19u;  // (ETA * 2)^2 = 14.44 as usize, + 5 (simulation.rs:386, 2147)
+__global__ void __launch_bounds__(kThreads)
+k_constrain(uint32_t n, NbLists L, const float4* __restrict__ xyhm, float* __restrict__ h_next, StepCtl* ctl) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 me = xyhm[i];
+  const NbCol col(L, i);
+  const uint32_t cn = col.cn;
+  float hn = me.z;
+  if (cn > kConstrainTarget) {
+    auto fringe = [&](uint32_t k) {
+      const float4 o = __ldg(&xyhm[col.get(k)]);
+      const float d = __fsqrt_rn(dist_sq_exact(__fsub_rn(me.x, o.x), __fsub_rn(me.y, o.y)));
+      return __fsub_rn(__fmul_rn(2.f, d), __fmul_rn(o.z, 2.f));
+    };
+    // the value of rank r in descending order, by counting (a column has some thirty entries; the mode is not a hot path)
+    const uint32_t r = cn - kConstrainTarget;
+    bool found = false;
+    for (uint32_t k = 0; k < cn && !found; k++) {
+      const float v = fringe(k);
+      uint32_t greater = 0, equal = 0;
+      for (uint32_t m = 0; m < cn; m++) {
+        const float w = fringe(m);
+        greater += w > v ? 1u : 0u;
+        equal += w == v ? 1u : 0u;
+      }
+      if (greater <= r && r < greater + equal) { hn = v; found = true; }
+    }
+    if (!found || !(hn < me.z) || !(hn >= 0.f)) { atomicOr(&ctl->error_flags, ERRF_CONSTRAIN); hn = me.z; }
+  }
+  h_next[i] = hn;
+}
+// the new lengths replace the old ones wherever a later kernel reads them; h range and CFL minimum of the new lengths
+// ((2h)^2 / (v.v + 0.01) with the new h, simulation.rs:2182-2191: the reference computes dt after this)
+__global__ void __launch_bounds__(kThreads)
+k_apply_h(uint32_t n, const float* __restrict__ h_next, const float4* __restrict__ xv, float4* __restrict__ xyhm, float2* __restrict__ hm, StepCtl* ctl) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float inf = __int_as_float(0x7f800000);
+  float hmin = inf, hmax = -inf, cfl = inf;
+  if (i < n) {
+    const float h = h_next[i];
+    float4 r = xyhm[i]; r.z = h; xyhm[i] = r;
+    float2 q = hm[i]; q.x = h; hm[i] = q;
+    const float4 v = xv[i];
+    const float sr = __fmul_rn(h, 2.f);
+    cfl = __fdiv_rn(__fmul_rn(sr, sr), __fadd_rn(dist_sq_exact(v.z, v.w), 0.01f));
+    hmin = hmax = h;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    hmin = fminf(hmin, __shfl_xor_sync(0xffffffffu, hmin, o)); hmax = fmaxf(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
+    cfl = fminf(cfl, __shfl_xor_sync(0xffffffffu, cfl, o));
+  }
+  if ((threadIdx.x & 31u) == 0u && hmin <= hmax) {
+    atomicMin(&ctl->hmin_enc, enc_f(hmin)); atomicMax(&ctl->hmax_enc, enc_f(hmax)); atomicMin(&ctl->cfl_enc, enc_f(cfl));
+  }
+}
+__global__ void k_constrain_begin(StepCtl* ctl) { ctl->hmin_enc = 0xFFFFFFFFu; ctl->hmax_enc = 0u; ctl->cfl_enc = 0xFFFFFFFFu; }
+// (the grid keeps its levels: their h_max still bound every particle's h from above, which is all the candidate scan needs)
+__global__ void k_constrain_end(StepCtl* ctl, float max_dt, float cfl_factor) {
+  ctl->hmin = dec_f(ctl->hmin_enc); ctl->hmax = dec_f(ctl->hmax_enc);
+  ctl->dt = fminf(max_dt, __fmul_rn(cfl_factor, __fsqrt_rn(dec_f(ctl->cfl_enc))));
+  ctl->list_used = 0; ctl->max_count = 0;
+}
+
 }  // namespace
 
-int launch_neighbors(asph_sim* sim, float f_ext, float f_near) {
+int launch_constrain_neighborhood(asph_sim* sim) {
+  const uint32_t n = sim->n;
+  if (n == 0) return ASPH_OK;
+  const uint32_t blocks = (n + kThreads - 1) / kThreads;
+  cudaStream_t st = sim->stream;
+  NbLists L;
+  L.pool = sim->nbpool.p; L.slice_base = sim->slice_base.p; L.cnt = sim->cnt.p; L.cnt_ext = sim->cnt_ext.p; L.far_idx = sim->far_idx.p; L.far_cnt = sim->far_cnt.p;
+  k_constrain<<<blocks, kThreads, 0, st>>>(n, L, sim->xyhm.p, sim->scratch_f.p, sim->ctl);
+  LAUNCH_CHECK();
+  k_constrain_begin<<<1, 1, 0, st>>>(sim->ctl);
+  LAUNCH_CHECK();
+  k_apply_h<<<blocks, kThreads, 0, st>>>(n, sim->scratch_f.p, sim->xv[sim->xv_cur].p, sim->xyhm.p, sim->hm.p, sim->ctl);
+  LAUNCH_CHECK();
+  k_constrain_end<<<1, 1, 0, st>>>(sim->ctl, sim->pp.max_dt, sim->pp.cfl_factor);
+  LAUNCH_CHECK();
+  return ASPH_OK;
+}
+
+int launch_neighbors(asph_sim* sim, float f_ext, float f_near, bool lists_only) {
   const uint32_t n = sim->n;
   sim->lists_valid = false;
   if (n == 0) { sim->lists_valid = true; return ASPH_OK; }
@@ -365,10 +456,11 @@ int launch_neighbors(asph_sim* sim, float f_ext, float f_near) {
   const uint32_t cap64 = uint32_t(std::min<size_t>(sim->nbpool.cap / 64, 0x7FFFFFF0u));
   CUDA_TRY(cudaMemsetAsync(sim->far_cnt.p, 0, (size_t(n + ASPH_PAIR_BLOCK - 1) / ASPH_PAIR_BLOCK) * sizeof(uint32_t), sim->stream));
   k_neighbors<<<blocks, kThreads, 0, sim->stream>>>(n, sim->xyhm.p, sim->ctl, sim->ctl, sim->cellstart.p, sim->pp, sim->lut.p, f_ext, f_near,
-                                                    cap64, sim->nbpool.p, sim->slice_base.p, sim->cnt.p, sim->cnt_ext.p, sim->far_idx.p, sim->far_cnt.p, sim->rho.p, sim->gB.p,
+                                                    cap64, sim->nbpool.p, sim->slice_base.p, sim->cnt.p, sim->cnt_ext.p, sim->far_idx.p, sim->far_cnt.p, lists_only ? nullptr : sim->rho.p, sim->gB.p,
                                                     sim->pconst.p, sim->lam_sum.p, sim->lam_grad.p, sim->nrm.p,
                                                     sim->dist ? sim->refid[sim->cur].p : nullptr);
   LAUNCH_CHECK();
+  if (lists_only) { sim->lists_valid = true; return ASPH_OK; }
   if (sim->dist) TRY(dist_halo(sim, sim->rho.p, 4));  // K12 / K17 read the neighbours' densities
   if (h_from_distribution(sim)) {
     NbLists L;

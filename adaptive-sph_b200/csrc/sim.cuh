@@ -28,7 +28,8 @@
 enum {
   ERRF_NONFINITE = 1, ERRF_NEG_AII = 2, ERRF_DENSITY = 4, ERRF_NEIGHBOR_OVERFLOW = 8, ERRF_LIST_CAPACITY = 16,
   ERRF_PARTICLE_CAPACITY = 32, ERRF_SPLIT_PATTERN = 64, ERRF_LEVEL_WEIGHT = 128, ERRF_CELL_BUDGET = 256,
-  ERRF_SPLIT_CHILDREN = 512, ERRF_SOLVER_NONFINITE = 1024, ERRF_PARTNER_VALIDATION = 2048, ERRF_PEER_TIMEOUT = 4096
+  ERRF_SPLIT_CHILDREN = 512, ERRF_SOLVER_NONFINITE = 1024, ERRF_PARTNER_VALIDATION = 2048, ERRF_PEER_TIMEOUT = 4096,
+  ERRF_CONSTRAIN = 8192
 };
 
 // Cells of a level are numbered STRIP-MAJOR: the grid is cut into vertical strips of 2^strip_log2 columns; inside a
@@ -105,7 +106,7 @@ struct PackedParams {  // SimulationParams rounded once to fp32 (what serde does
   float f_ext, f_near;  // range factors: level_estimation_range / ETA and 2
   float pull_x, pull_y;
   int has_pull, viscosity_type, level_method, solver, density_source, np_before_div, penalty, sizing, opdisc;
-  int boundary_is_fluid_surface, max_iters;
+  int boundary_is_fluid_surface, max_iters, constrain;
   int min_share_partners, min_merge_partners, allow_merge_optimal, allow_share_optimal, allow_share_too_small,
       allow_merge_size_diff, fail_on_missing_split_pattern;
   int n_planes;
@@ -323,7 +324,8 @@ inline bool h_from_distribution(const asph_sim* sim) { return sim->pp.h_mode != 
 int launch_exclusive_scan(asph_sim* sim, const uint32_t* in, uint32_t* out, const uint32_t* n_dev, uint32_t n_add,
                           uint32_t n_max);  // out[i] = sum(in[0..i)) for i < *n_dev + n_add
 // neighbors.cu
-int launch_neighbors(asph_sim* sim, float f_ext, float f_near);
+int launch_neighbors(asph_sim* sim, float f_ext, float f_near, bool lists_only = false);
+int launch_constrain_neighborhood(asph_sim* sim);       // constrain_neighborhood_count (simulation.rs:2145-2177): shrinks h, then the lists are rebuilt
 inline bool op_w2020(const asph_sim* sim) { return sim->pp.opdisc == ASPH_OP_WINCHENBACH2020; }
 int neighbors_grow(asph_sim* sim);
 // solver.cu

@@ -10,6 +10,7 @@ the CUDA step through the C ABI against the CPU oracle on the same inputs, same 
   * boundary_penalty_term: None / Linear / Quadratic2 (boundary_winchenbach2020.rs:87-118)
   * sizing_function: Mass / Radius2 (simulation.rs:213-237)
   * BASELINE configs[3] geometry (ratio-stress-test scene, radius ratio 16:1, IISPH) at a size the oracle steps in seconds
+  * constrain_neighborhood_count (simulation.rs:2145-2177), level_estimation_after_advection (:2678-2707), CenterDiff (:631-695)
   * the bulk-copy sweep kernels against the per-thread-copy ones, bit for bit
   * north star: positions within 1e-5 relative after 100 steps (a trajectory that is not chaotic, noise floor printed)
 """
@@ -284,6 +285,114 @@ def test_ratio_16_to_1_blocks_in_contact(asph, cuda_lib, oracle32, default_param
     assert _rel(g.get_field("density"), o.get_field("density"), 1.0) <= 2e-4
     pmax = max(float(np.abs(o.get_field("pressure")).max()), 1e-6)
     assert _rel(g.get_field("pressure"), o.get_field("pressure"), pmax) <= 5e-4
+    g.close(); o.close()
+
+
+# ---- constrain_neighborhood_count (simulation.rs:2145-2177) ------------------------------------------------------------------
+def _rings(asph, centers=((0.0, 0.0), (0.3, 0.1), (-0.4, 0.2)), n=21, seed=3):
+    """Rings of 21 particles of diameter 1.3 h: every particle has the 20 others of its ring as neighbours (one more than
+    optimal_neighbor_number + 5 = 19) and its second-farthest lies between h and 1.5 h away, so the reference's asserts on
+    the new length (0 <= h_next < h) hold — for an ordinary particle distribution with a free surface they never do."""
+    sc = asph.SceneConfig.dam_break(0.02)
+    _, _, mass = asph.scene_particles(sc)
+    m0 = np.float32(mass[0])
+    h0 = 1.9 * np.sqrt(float(m0) / np.pi)  # rest_density 1
+    rng = np.random.default_rng(seed)
+    pts = []
+    for c in centers:
+        a = np.linspace(0, 2 * np.pi, n, endpoint=False) + rng.uniform(0, 1)
+        r = 0.65 * h0 * (1 + rng.uniform(-0.03, 0.03, n))
+        pts.append(np.stack([c[0] + r * np.cos(a), c[1] + r * np.sin(a)], 1))
+    pos = np.concatenate(pts).astype(np.float32)
+    return sc, pos, np.zeros_like(pos), np.full(len(pos), m0, np.float32)
+
+
+@pytest.mark.parametrize("level", ["None", "EmptyAngle"])
+def test_constrain_neighborhood_count_shrinks_h(asph, cuda_lib, oracle32, default_params, level):
+    """The new smoothing lengths are bit-identical (the neighbour predicate of everything after depends on them), dt is
+    taken from them (simulation.rs:2182-2191 comes after), and the step's fields agree as in every other mode.  The
+    reference keeps its lists and lets the pairs outside the shrunken supports contribute zeros; the CUDA path rebuilds
+    the lists, so neighbor_count is not compared."""
+    sc, pos, vel, mass = _rings(asph)
+    params = default_params.replace(constrain_neighborhood_count=True, sharing=False, merging=False, splitting=False,
+                                    level_estimation_method=level)
+    g, o = _pair(asph, cuda_lib, oracle32, params, pos, vel, mass, asph.scene_boundary(sc, "AnalyticOverestimate"))
+    dg = g.single_step_without_adaptivity(); do = o.single_step_without_adaptivity()
+    assert dg == do
+    hg, ho = g.get_field("h"), o.get_field("h")
+    assert np.array_equal(hg, ho)
+    h0 = 1.9 * np.sqrt(float(mass[0]) / np.pi)
+    assert ho.max() < 0.7 * h0  # every particle was over the target and got a shorter length
+    gi, oi = g.step_info(), o.step_info()
+    assert (gi["div_sweeps"], gi["density_sweeps"]) == (oi["div_sweeps"], oi["density_sweeps"]), (gi, oi)
+    _compare_step_fields(g, o, 2e-4, [("density", 1.0), ("aii", None), ("ppe_source_term", None)])
+    assert _rel(g.get_field("position"), o.get_field("position"), 2.0) <= 1e-6
+    if level != "None":
+        assert np.array_equal(g.get_field("flag_is_fluid_surface"), o.get_field("flag_is_fluid_surface"))
+        assert _rel(g.get_field("level"), o.get_field("level"), 1.0) <= 1e-5
+    g.close(); o.close()
+
+
+def test_constrain_neighborhood_count_assert_like_the_reference(asph, cuda_lib, oracle32, default_params):
+    """On a particle distribution with a free surface the reference's assert!(*p_h_next < h) fires; so do the oracle and the
+    CUDA path, with the same error code."""
+    sc, pos, vel, mass = _mixed_cloud(asph)
+    params = default_params.replace(constrain_neighborhood_count=True, sharing=False, merging=False, splitting=False)
+    g, o = _pair(asph, cuda_lib, oracle32, params, pos, vel, mass, asph.scene_boundary(sc, "AnalyticOverestimate"))
+    codes = []
+    for sim in (g, o):
+        with pytest.raises(asph.AsphError) as e:
+            sim.single_step_without_adaptivity()
+        assert "constrain_neighborhood_count" in str(e.value)
+        codes.append(e.value.code)
+    assert codes[0] == codes[1]
+    g.close(); o.close()
+
+
+# ---- level_estimation_after_advection (simulation.rs:2678-2707) and CenterDiff (simulation.rs:631-695) -------------------------
+@pytest.mark.parametrize("method", ["EmptyAngle", "CenterDiff"])
+def test_level_estimation_after_advection_single_step(asph, cuda_lib, oracle32, default_params, method):
+    """One step of the mixed-size cloud: the level set is estimated on lists rebuilt (extended range) at the advected
+    positions, smoothed with the step's densities; the per-step fields follow the particles through the second sort."""
+    sc, pos, vel, mass = _mixed_cloud(asph)
+    params = default_params.replace(level_estimation_after_advection=True, level_estimation_method=method, sharing=False, merging=False,
+                                    splitting=False)
+    g, o = _pair(asph, cuda_lib, oracle32, params, pos, vel, mass, asph.scene_boundary(sc, "AnalyticOverestimate"))
+    dg = g.single_step_without_adaptivity(); do = o.single_step_without_adaptivity()
+    assert dg == do
+    gi, oi = g.step_info(), o.step_info()
+    assert (gi["div_sweeps"], gi["density_sweeps"], gi["level_sweeps"]) == (oi["div_sweeps"], oi["density_sweeps"], oi["level_sweeps"]), (gi, oi)
+    pmax = max(float(np.abs(o.get_field("pressure")).max()), 1e-6)
+    _compare_step_fields(g, o, 2e-4, [("density", 1.0), ("aii", None), ("ppe_source_term", None), ("pressure", pmax)])
+    assert _rel(g.get_field("position"), o.get_field("position"), 2.0) <= 1e-6
+    assert np.array_equal(g.get_field("flag_is_fluid_surface"), o.get_field("flag_is_fluid_surface"))
+    lg, lo = g.get_field("level"), o.get_field("level")
+    assert np.array_equal(lg > 0, lo > 0)  # the same particles are FluidInterior
+    assert _rel(lg, lo, 1.0) <= 1e-5
+    if method == "CenterDiff":
+        assert (lo[lo <= 0] < 0).any() and o.get_field("flag_is_fluid_surface").sum() > 0
+    g.close(); o.close()
+
+
+@pytest.mark.parametrize("method", ["EmptyAngle", "CenterDiff"])
+def test_level_estimation_after_advection_default_scene_with_resampling(asph, cuda_lib, oracle32, default_params, split_patterns, method):
+    """C1, 12 full steps: the resampling phase runs on the lists of the second neighbour pass.  Identical particle counts,
+    resampling statistics, density and level sweep counts every step.  (The divergence solve of the free-falling blocks is
+    degenerate — the divergence is rounding noise, and whether ANY particle ends a sweep with positive pressure decides
+    between one sweep and three: not compared here.)"""
+    params = default_params.replace(level_estimation_after_advection=True, level_estimation_method=method)
+    _steps_with_resampling(asph, cuda_lib, oracle32, params, split_patterns, 12,
+                           RESAMPLING_KEYS + ("density_sweeps", "level_sweeps"), 1e-5)
+
+
+def test_center_diff_before_advection_is_refused_like_the_reference(asph, cuda_lib, oracle32, default_params):
+    """simulation.rs:2021: CenterDiff needs densities, which the level estimation at the top of the step does not have."""
+    sc, pos, vel, mass = _corner_block(asph)
+    params = default_params.replace(level_estimation_method="CenterDiff", sharing=False, merging=False, splitting=False)
+    g, o = _pair(asph, cuda_lib, oracle32, params, pos, vel, mass, asph.scene_boundary(sc, "AnalyticOverestimate"))
+    for sim in (g, o):
+        with pytest.raises(asph.AsphError):
+            sim.single_step_without_adaptivity()
     g.close(); o.close()
 
 
