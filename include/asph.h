@@ -135,7 +135,9 @@ typedef struct asph_step_info {
   int32_t div_iterations;       /* `num_pressure_iters` of the divergence solve (sweeps executed − 1) */
   int32_t density_iterations;   /* same for the density solve                                         */
   int32_t div_sweeps, density_sweeps;
-  int32_t level_sweeps;         /* sweeps of propagate_level_set_from_surface_detection               */
+  int32_t level_sweeps;         /* sweeps of propagate_level_set_from_surface_detection (the CUDA path stops
+                                   once a sweep assigned only values below -maximum_surface_distance, which
+                                   the smoothing clamps anyway: fewer sweeps than the reference, same field) */
   int32_t n_shared, n_merged, n_split_parents;
   uint64_t n_particles_begin, n_particles_end;
   double last_avg_error_div, last_avg_error_density;
