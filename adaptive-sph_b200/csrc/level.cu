@@ -16,6 +16,8 @@
 // `level` encoding: value <= 0 = FluidSurface(value); ASPH_LEVEL_INTERIOR (1.0) = FluidInterior.
 #include <cooperative_groups.h>
 
+#include <type_traits>
+
 #include "lists.cuh"
 
 namespace cg = cooperative_groups;
@@ -210,8 +212,8 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
             int use_cutoff, const CoopPeer P) {
   cg::grid_group grid = cg::this_grid();
   constexpr uint32_t kStage = 192;
-  constexpr uint32_t kLanes = 8, kPerWarp = 32 / kLanes, kBatch = ASPH_PROP_BATCH;
-  constexpr uint32_t kGroupRounds = 4;  // columns of up to kGroupRounds * 4 * kLanes neighbours are walked by the particle's own lanes
+  constexpr uint32_t kBatch = ASPH_PROP_BATCH;
+  constexpr uint32_t kGroupRounds = 4;  // columns of up to kGroupRounds * kBatch * lanes neighbours are walked by the particle's own lanes
   __shared__ uint32_t s_stage[kPropThreads / 32][kStage];
   __shared__ uint32_t s_count[kPropThreads / 32], s_base;
   unsigned int* level_bits = reinterpret_cast<unsigned int*>(level);
@@ -304,33 +306,43 @@ k_propagate(uint32_t n, Lists L, const float4* __restrict__ xyhm, float* __restr
     // particles per warp, 32 neighbours of each per round, the four columns walked side by side; a very long column (a
     // coarse particle next to fine ones has hundreds) would take its eight lanes many rounds, so it is handed to the whole
     // warp afterwards.
-    const uint32_t sub = lane & (kLanes - 1u), grp = lane / kLanes;
-    for (uint32_t f0 = begin + gwarp * kPerWarp; f0 < end; f0 += nwarps * kPerWarp) {
-      struct { uint32_t j, ce; float x, y, lj; } cur{0u, 0u, 0.f, 0.f, 0.f};
-      NbCol col;
-      if (f0 + grp < end) {
-        cur.j = __ldcg(fin + f0 + grp);
-        const float2 p = __ldg(reinterpret_cast<const float2*>(xyhm + cur.j));
-        cur.x = p.x; cur.y = p.y;
-        cur.lj = SIGNED ? level_of_key(__ldcg(level_bits + cur.j)) : __ldcg(level + cur.j);
-        cur.ce = __ldg(&L.cnt_ext[cur.j]);
-        col = NbCol(L, cur.j);
+    // Lanes per front particle: eight (four particles per warp) when the front has more particles than the grid has warps
+    // to give them two each — the usual case on one GPU —, sixteen or all thirty-two when it is small (late sweeps, small
+    // scenes, the slabs of a multi-GPU run): fewer rounds in the chain of the warp that the sweep waits for.  (A lane count
+    // chosen at run time inside ONE loop cost 4 % on one GPU: three instantiations.)
+    auto walk = [&](auto lanes_c) {
+      constexpr uint32_t kLanes = decltype(lanes_c)::value, kPerWarp = 32u / kLanes;
+      const uint32_t sub = lane & (kLanes - 1u), grp = lane / kLanes;
+      for (uint32_t f0 = begin + gwarp * kPerWarp; f0 < end; f0 += nwarps * kPerWarp) {
+        struct { uint32_t j, ce; float x, y, lj; } cur{0u, 0u, 0.f, 0.f, 0.f};
+        NbCol col;
+        if (f0 + grp < end) {
+          cur.j = __ldcg(fin + f0 + grp);
+          const float2 p = __ldg(reinterpret_cast<const float2*>(xyhm + cur.j));
+          cur.x = p.x; cur.y = p.y;
+          cur.lj = SIGNED ? level_of_key(__ldcg(level_bits + cur.j)) : __ldcg(level + cur.j);
+          cur.ce = __ldg(&L.cnt_ext[cur.j]);
+          col = NbCol(L, cur.j);
+        }
+        // an extended-range column holds about 60 neighbours (f_ext = 2.9 supports): two rounds of kBatch * kLanes for the group
+        const bool big = cur.ce > kGroupRounds * kBatch * kLanes;
+        const unsigned int bigmask = __ballot_sync(0xffffffffu, big && sub == 0u);
+        const uint32_t ce_grp = big ? 0u : cur.ce;
+        for (uint32_t k0 = 0; __any_sync(0xffffffffu, k0 < ce_grp); k0 += kBatch * kLanes) push(cur.x, cur.y, cur.lj, ce_grp, col, k0, sub, kLanes);
+        for (unsigned int m = bigmask; m; m &= m - 1u) {
+          const int src = __ffs(m) - 1;
+          const uint32_t jb = __shfl_sync(0xffffffffu, cur.j, src);
+          const float2 pb = __ldg(reinterpret_cast<const float2*>(xyhm + jb));
+          const float ljb = SIGNED ? level_of_key(__ldcg(level_bits + jb)) : __ldcg(level + jb);
+          const uint32_t ceb = __ldg(&L.cnt_ext[jb]);
+          const NbCol colb(L, jb);
+          for (uint32_t k0 = 0; k0 < ceb; k0 += 32u * kBatch) push(pb.x, pb.y, ljb, ceb, colb, k0, lane, 32u);
+        }
       }
-      // an extended-range column holds about 60 neighbours (f_ext = 2.9 supports): two rounds of kBatch * kLanes for the group
-      const bool big = cur.ce > kGroupRounds * kBatch * kLanes;
-      const unsigned int bigmask = __ballot_sync(0xffffffffu, big && sub == 0u);
-      const uint32_t ce_grp = big ? 0u : cur.ce;
-      for (uint32_t k0 = 0; __any_sync(0xffffffffu, k0 < ce_grp); k0 += kBatch * kLanes) push(cur.x, cur.y, cur.lj, ce_grp, col, k0, sub, kLanes);
-      for (unsigned int m = bigmask; m; m &= m - 1u) {
-        const int src = __ffs(m) - 1;
-        const uint32_t jb = __shfl_sync(0xffffffffu, cur.j, src);
-        const float2 pb = __ldg(reinterpret_cast<const float2*>(xyhm + jb));
-        const float ljb = SIGNED ? level_of_key(__ldcg(level_bits + jb)) : __ldcg(level + jb);
-        const uint32_t ceb = __ldg(&L.cnt_ext[jb]);
-        const NbCol colb(L, jb);
-        for (uint32_t k0 = 0; k0 < ceb; k0 += 32u * kBatch) push(pb.x, pb.y, ljb, ceb, colb, k0, lane, 32u);
-      }
-    }
+    };
+    if (end - begin <= nwarps) walk(std::integral_constant<uint32_t, 32u>());
+    else if (end - begin <= 2u * nwarps) walk(std::integral_constant<uint32_t, 16u>());
+    else walk(std::integral_constant<uint32_t, 8u>());
     PROP_TRACE(if (t < 512 && lane == 0) { const unsigned long long d = (unsigned long long)(clock64() - tr0); atomicMax(&g_prop_trace[1][t], d); atomicAdd(&g_prop_trace[2][t], d); if (gtid == 0) g_prop_trace[0][t] = end - begin; })
     // one atomic per block: the warps' staged claims behind one another at the tail of front(t)
     __syncwarp();
